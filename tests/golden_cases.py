@@ -1,0 +1,26 @@
+"""Shared access to tests/golden (manifest + dumps) -- test infrastructure."""
+import json
+import os
+
+from vcfgl_b200 import args as vargs
+
+import vgl_dump
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MANIFEST = json.load(open(os.path.join(GOLD, "manifest.json")))
+CASE_IDS = sorted(MANIFEST)
+
+
+def case_args(cid) -> vargs.SimArgs:
+    m = MANIFEST[cid]
+    # file arguments (--qs-bins, --depths-file) were inlined by tools/make_golden.py
+    return vargs.parse_args(m["argv"], qs_bins=m.get("qs_bins"), depths=m.get("depths"))
+
+
+_cache = {}
+
+
+def case_sites(cid):
+    if cid not in _cache:
+        _cache[cid] = vgl_dump.read_dump(os.path.join(GOLD, cid + ".vgld.gz"))
+    return _cache[cid]

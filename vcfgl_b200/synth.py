@@ -1,0 +1,74 @@
+"""Synthetic "msprime-shaped" genotype inputs.
+
+tskit VCF dialect: one contig "1" of length L, REF=0 ALT=1, phased a|b GT,
+samples tsk_0.., biallelic sites whose derived-allele count k follows the
+neutral site-frequency spectrum P(k) ~ 1/k on [1, 2S-1]; the k carrier
+haplotypes are chosen uniformly without replacement.  The same generator
+produces (a) VCF text for the reference CPU binary and (b) the packed-nibble
+genotype matrix the C-ABI consumes (include/vgl.h), from one seed.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GT_MISSING = 0xF
+
+
+def sfs_genotypes(n_sites: int, n_samples: int, seed: int, missing_rate: float = 0.0) -> np.ndarray:
+    """-> int8 [n_sites, 2*n_samples] binary haplotype alleles (0/1, -1 missing)."""
+    rng = np.random.default_rng(seed)
+    H = 2 * n_samples
+    ks = np.arange(1, H)
+    p = 1.0 / ks
+    p /= p.sum()
+    k = rng.choice(ks, size=n_sites, p=p)
+    # k smallest of H iid uniforms per site == uniform k-subset
+    u = rng.random((n_sites, H))
+    thresh = np.partition(u, kth=np.minimum(k, H - 1) - 1, axis=1)[np.arange(n_sites), k - 1]
+    hap = (u <= thresh[:, None]).astype(np.int8)
+    if missing_rate > 0:
+        miss = rng.random((n_sites, n_samples)) < missing_rate
+        hap = hap.reshape(n_sites, n_samples, 2)
+        hap[miss] = -1
+        hap = hap.reshape(n_sites, H)
+    return hap
+
+
+def pack_gt(hap_acgt: np.ndarray) -> np.ndarray:
+    """int8 [n_sites, 2S] ACGT ints (-1 missing) -> uint8 [n_sites, S]:
+    low nibble = first haplotype, high nibble = second, 0xF = missing."""
+    h = hap_acgt.astype(np.int16)
+    h = np.where(h < 0, GT_MISSING, h).astype(np.uint8)
+    return (h[:, 0::2] | (h[:, 1::2] << 4)).astype(np.uint8)
+
+
+def positions(n_sites: int, length: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed + 7)
+    if n_sites > length:
+        raise ValueError("more sites than positions")
+    if n_sites * 4 > length:
+        return np.sort(rng.choice(length, size=n_sites, replace=False)) + 1
+    pos = np.unique(rng.integers(1, length + 1, size=int(n_sites * 1.2) + 16))
+    while len(pos) < n_sites:
+        pos = np.unique(np.concatenate([pos, rng.integers(1, length + 1, size=n_sites)]))
+    return np.sort(rng.choice(pos, size=n_sites, replace=False))
+
+
+def write_vcf(path: str, hap: np.ndarray, pos: np.ndarray, length: int, contig: str = "1",
+              ref: str = "0", alt: str = "1") -> None:
+    """Write binary haplotypes as a tskit-style VCF (for the reference CPU binary)."""
+    n_sites, H = hap.shape
+    S = H // 2
+    lut = {(-1, -1): ".|.", (0, 0): "0|0", (0, 1): "0|1", (1, 0): "1|0", (1, 1): "1|1"}
+    codes = (hap[:, 0::2].astype(np.int16) + 1) * 3 + (hap[:, 1::2].astype(np.int16) + 1)
+    table = np.array([lut.get((a - 1, b - 1), ".|.") for a in range(3) for b in range(3)])
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n##source=vcfgl_b200.synth\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n")
+        fh.write("##contig=<ID=%s,length=%d>\n" % (contig, length))
+        fh.write("##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n")
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" +
+                 "\t".join("tsk_%d" % i for i in range(S)) + "\n")
+        for i in range(n_sites):
+            fh.write("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t" % (contig, pos[i], ref, alt))
+            fh.write("\t".join(table[codes[i]]))
+            fh.write("\n")
