@@ -1,0 +1,211 @@
+/*
+ * vgl.h -- C ABI of the B200-native vcfgl simulation core (libvgl.so).
+ *
+ * Drop-in boundary for the reference's per-site hot path.  The reference has
+ * no plugin ABI; its operator interface for this path is internal:
+ *
+ *   static int simulate_record_values(simRecord*)          vcfgl.cpp:327
+ *   void (*calculate_gls)(simRecord*)                      vcfgl.cpp:222, gl_methods.h:6-10
+ *   inputs through globals: args (io.h:40-148), true_gts_acgt_int and
+ *   n_sim_reads_arr (vcfgl.cpp:66-67), libc RNG state (vcfgl.cpp:214-219)
+ *   outputs: the simRecord tag arrays handed to htslib by
+ *   simRecord::add_tags()                                  bcf_utils.cpp:426-507
+ *
+ * The replacement works on BATCHES of sites: the host driver loop
+ * (vcfgl.cpp:1469-1565) appends each site's packed true genotypes to a pinned
+ * input buffer instead of calling simulate_record_values(), submits the batch,
+ * and one batch later walks vgl_batch_out in site order feeding the returned
+ * arrays to bcf_update_format_* / bcf_update_info_* with zero repacking.
+ *
+ * Conventions: every function returns VGL_OK (0) or a negative vgl_status and
+ * never exits the process (the reference's ERROR()/ASSERT() exit(1),
+ * shared.h:292-327; the host maps codes back to that).  All memory handed out
+ * is owned by the context and stays valid until the slot is submitted again
+ * or the context is destroyed.  One host thread per context; one context per
+ * GPU.  Site ids are global running indices, so results do not depend on batch
+ * size or on how sites are sharded over GPUs.
+ *
+ * There is no CPU fallback: vgl_create() fails with VGL_ENODEV without a CUDA
+ * device.
+ */
+#ifndef VGL_H
+#define VGL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGL_ABI_VERSION 1
+
+#define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
+#define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
+
+/* packed true genotype of one (site, sample) cell: low nibble = first
+ * haplotype, high nibble = second; value = ACGT int 0..3 (what
+ * check_rec_alleles() stores in true_gts_acgt_int, vcfgl.cpp:133-146),
+ * 0xF = missing (-1 there). */
+#define VGL_GT_MISSING 0xF
+#define VGL_GT_PACK(h0, h1) ((uint8_t)(((h0) & 0xF) | (((h1) & 0xF) << 4)))
+
+/* missing sentinels, identical to htslib's (htslib/vcf.c:56, htslib/htslib/vcf.h:1325) */
+#define VGL_F32_MISSING_BITS 0x7F800001u
+#define VGL_I32_MISSING INT32_MIN
+
+typedef enum vgl_status {
+    VGL_OK = 0,
+    VGL_EINVAL = -1,  /* bad argument / unsupported option combination (io.cpp:860-1000) */
+    VGL_ENOMEM = -2,
+    VGL_ECUDA = -3,   /* CUDA runtime error; vgl_last_error() has the text */
+    VGL_ESTATE = -4,  /* slot busy / not submitted */
+    VGL_ERANGE = -5,  /* a quality score fell outside every --qs-bins range (vcfgl.cpp:63) */
+    VGL_ENODEV = -6   /* no CUDA device: there is no CPU path */
+} vgl_status;
+
+/* vgl_params.tag_mask: which tags add_tags() would emit (io.h:90-102) */
+enum {
+    VGL_TAG_GL = 1 << 0, VGL_TAG_GP = 1 << 1, VGL_TAG_PL = 1 << 2, VGL_TAG_I16 = 1 << 3,
+    VGL_TAG_QS = 1 << 4, VGL_TAG_FMT_DP = 1 << 5, VGL_TAG_INFO_DP = 1 << 6,
+    VGL_TAG_FMT_AD = 1 << 7, VGL_TAG_INFO_AD = 1 << 8, VGL_TAG_FMT_ADF = 1 << 9,
+    VGL_TAG_INFO_ADF = 1 << 10, VGL_TAG_FMT_ADR = 1 << 11, VGL_TAG_INFO_ADR = 1 << 12
+};
+
+enum { VGL_DEPTH_POISSON = 0,            /* --depth x        rng.h:284 */
+       VGL_DEPTH_POISSON_PER_SAMPLE = 1, /* --depths-file    rng.h:318 */
+       VGL_DEPTH_FIXED = 2 };            /* every cell gets exactly (int)depth_mean reads */
+
+/* how the native simulator draws a cell (replay ignores this) */
+enum { VGL_SAMPLER_AUTO = 0,     /* COUNTS when the GL depends on base counts only, else PER_READ */
+       VGL_SAMPLER_PER_READ = 1, /* one Philox block per read; ordered reads (all modes) */
+       VGL_SAMPLER_COUNTS = 2 }; /* binomial/multinomial per cell: GL model 1 with --error-qs 0/1 only */
+
+/* = the argStruct fields the hot path reads (io.h:40-148) */
+typedef struct vgl_params {
+    int32_t abi_version;  /* VGL_ABI_VERSION */
+    int32_t n_samples;
+    int64_t seed;         /* --seed */
+    int32_t depth_mode;
+    double depth_mean;          /* --depth (io.h:63) */
+    const double* depth_means;  /* [n_samples] for PER_SAMPLE (io.h:125), else NULL */
+    double error_rate;    /* --error-rate (io.h:66) */
+    int32_t error_qs;     /* --error-qs 0|1|2 (io.h:67) */
+    double beta_variance; /* --beta-variance (io.h:68); shape from rng.h:370-371 */
+    int32_t gl_model;     /* --gl-model 1|2 (io.h:69) */
+    double gl1_theta;     /* --gl1-theta (io.h:70) */
+    int32_t precise_gl;   /* --precise-gl (io.h:72) */
+    int32_t adjust_qs;    /* --adjust-qs bitmask (io.h:75, shared.h:103-117) */
+    double adjust_by;     /* --adjust-by (io.h:76) */
+    int32_t n_qs_bins;    /* --qs-bins (io.h:145-146): [start, end, value] */
+    uint8_t qs_bins[255][3];
+    int32_t do_unobserved;  /* -doUnobserved 0..5 (io.h:81) */
+    int32_t rm_invar_sites; /* --rm-invar-sites bitmask; only bit 4 (simulated invariant) is device-side */
+    int32_t rm_empty_sites; /* --rm-empty-sites */
+    int32_t do_gvcf;        /* -doGVCF (only changes the no-reads site, vcfgl.cpp:242-246) */
+    uint32_t tag_mask;
+    int32_t i16_mapq;       /* --i16-mapq (io.h:73) */
+    /* engine configuration (no reference counterpart) */
+    int32_t device_id;       /* CUDA device ordinal */
+    int32_t max_batch_sites; /* capacity of one slot */
+    int32_t n_slots;         /* >= 1; 2 = double buffering */
+    int32_t sampler;         /* VGL_SAMPLER_* */
+    int32_t host_output;     /* 1: vgl_wait() copies results to pinned host memory; 0: results stay in HBM */
+} vgl_params;
+
+/* Replay input: the reference's own draws for a batch (from the instrumented
+ * reference, oracle/ref_dump_hooks.h), all HOST pointers.  Cells are indexed
+ * c = site_in_batch * n_samples + sample; reads of all cells are concatenated
+ * in (cell, read) order and cover only cells whose genotype is not missing. */
+typedef struct vgl_replay {
+    const int32_t* depths;       /* [n_sites*S] depth drawn per cell, also for missing-GT cells (vcfgl.cpp:364-368) */
+    const int64_t* read_offsets; /* [n_sites*S + 1] start of each cell's reads */
+    int64_t n_reads;
+    const uint8_t* bases;        /* [n_reads] observed base 0..3 (vcfgl.cpp:485-488) */
+    const uint8_t* strands;      /* [n_reads] 0 fwd / 1 rev (vcfgl.cpp:581-586) or NULL */
+    const uint8_t* qs;           /* [n_reads] per-read qs, --error-qs 2 (vcfgl.cpp:506-523) or NULL */
+    const uint8_t* adj_qs;       /* [n_reads] adjusted qs (--adjust-qs != 0) or NULL */
+    const double* error_probs;   /* [n_reads] beta-drawn error prob (--precise-gl 1, vcfgl.cpp:544) or NULL */
+    const uint8_t* tail_dists;   /* [n_reads] capped tail distance, -addI16 (vcfgl.cpp:653-656) or NULL */
+    /* GL model 1 cells deeper than 255 reads: the 255 read codes (qs<<5|base) kept by
+     * errmod_cal's shuffle (htslib/errmod.c:156-159), 255 per such cell in cell order */
+    int64_t n_deep_cells;
+    const uint16_t* deep_codes;  /* [n_deep_cells*255] or NULL */
+} vgl_replay;
+
+/* per-site results: everything INFO-level plus where the site's FORMAT blocks start */
+typedef struct vgl_site_out {
+    int32_t skip_code;          /* 0 keep; -3 simulated invariant (vcfgl.cpp:677); -4 empty (vcfgl.cpp:401) */
+    int32_t n_alleles;          /* sim->nAlleles */
+    int32_t n_alleles_observed; /* sim->nAllelesObserved */
+    int32_t n_genotypes;        /* sim->nGenotypes */
+    int8_t alleles2acgt[8];     /* [5] used; 4 = <*>/<NON_REF>, -1 = none (bcf_utils.h:167-180) */
+    int8_t acgt2alleles[8];     /* [5] used */
+    int32_t info_dp;            /* INFO/DP; 0 => "no reads" record (vcfgl.cpp:228-315) */
+    int32_t info_ad[5], info_adf[5], info_adr[5];
+    float qs[5];                /* INFO/QS */
+    float i16[16];              /* INFO/I16 */
+    int32_t _pad;
+    int64_t g_off; /* element offset of this site's [n_samples][n_genotypes] block in gl/pl/gp */
+    int64_t r_off; /* element offset of this site's [n_samples][n_alleles] block in ad/adf/adr */
+} vgl_site_out;
+
+/* results of one batch.  With host_output=1 the pointers are pinned host memory,
+ * otherwise device memory.  Planes not requested by tag_mask are NULL. */
+typedef struct vgl_batch_out {
+    int32_t n_sites;
+    int32_t n_samples;
+    const vgl_site_out* sites; /* [n_sites], always host memory */
+    const int32_t* dp;         /* FORMAT/DP [n_sites][n_samples] */
+    const float* gl;           /* per site: [n_samples][n_genotypes] at sites[i].g_off */
+    const int32_t* pl;
+    const float* gp;
+    const int32_t* ad;         /* per site: [n_samples][n_alleles] at sites[i].r_off */
+    const int32_t* adf;
+    const int32_t* adr;
+    int64_t g_elems, r_elems;  /* used elements of the G- and R-shaped planes */
+    int32_t status;            /* VGL_OK or e.g. VGL_ERANGE raised on the device */
+} vgl_batch_out;
+
+/* timing of a slot's last completed submit, CUDA events on the slot's stream (ms) */
+enum { VGL_T_H2D = 0, VGL_T_SIM = 1, VGL_T_SITE = 2, VGL_T_SCAN = 3, VGL_T_EMIT = 4, VGL_T_D2H = 5,
+       VGL_T_TOTAL = 6, VGL_T_COUNT = 7 };
+
+/* submit flags */
+enum { VGL_SUBMIT_GT_ON_DEVICE = 1 << 0 }; /* skip the H2D copy: reuse the genotypes already in the slot's device buffer */
+
+typedef struct vgl_ctx vgl_ctx;
+
+/* builds the errmod / LUT tables, device buffers, streams and pinned rings */
+int vgl_create(const vgl_params* params, vgl_ctx** out);
+
+void vgl_destroy(vgl_ctx* ctx);
+
+/* pinned host input buffer of a slot: uint8 [max_batch_sites][n_samples] packed genotypes */
+int vgl_input_buffer(vgl_ctx* ctx, int slot, uint8_t** gt, int64_t* capacity_sites);
+
+/* asynchronous: H2D of the slot's genotypes, all kernels, (host_output) D2H of site records */
+int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites,
+               const vgl_replay* replay /* NULL = native Philox simulation */, uint32_t flags);
+
+/* blocks until the slot's batch is complete and describes it */
+int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out);
+
+/* make the slot run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the slot's own */
+int vgl_set_stream(vgl_ctx* ctx, int slot, void* cuda_stream);
+
+int vgl_slot_timing(vgl_ctx* ctx, int slot, float ms[VGL_T_COUNT]);
+
+/* number of kernel launches issued by this context so far */
+int64_t vgl_launch_count(const vgl_ctx* ctx);
+
+/* algorithmic bytes of a finished batch as defined in DESIGN.md / SURVEY.md 8(d) */
+int64_t vgl_algorithmic_bytes(const vgl_batch_out* out, uint32_t tag_mask);
+
+const char* vgl_strerror(int status);
+const char* vgl_last_error(const vgl_ctx* ctx);
+int vgl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGL_H */

@@ -1,0 +1,77 @@
+"""GPU parity (the first gate): the CUDA path in REPLAY mode, driven through the C ABI with the
+reference's own draws, must reproduce the reference's outputs -- integer tags bit-exactly, float
+tags bit-exactly except where CUDA's log10/exp10 differ from glibc's in the last place
+(--precise-gl 1 GLs and GP), which must stay within 1e-6 relative (north_star)."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import oracle_lib
+import replay_util
+from vcfgl_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+INT_KEYS = ["pl", "fmt_ad", "fmt_adf", "fmt_adr", "info_ad", "info_adf", "info_adr"]
+REL_TOL = 1e-6
+
+
+def bits(x):
+    return np.ascontiguousarray(x).view(np.uint32)
+
+
+def close_f32(got, want):
+    """bit-equal, or both finite and within REL_TOL relative"""
+    same = bits(got) == bits(want)
+    g, w = got.astype(np.float64), want.astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        near = np.isfinite(g) & np.isfinite(w) & (np.abs(g - w) <= REL_TOL * np.maximum(np.abs(w), 1e-30))
+    return same | near, same
+
+
+@pytest.mark.parametrize("cid", gc.CASE_IDS)
+def test_replay_matches_reference(cid):
+    a = gc.case_args(cid)
+    sites = gc.case_sites(cid)
+    S = sites[0].S
+    gt, rp = replay_util.batch_from_dump(sites, a)
+    prm = capi.params_from_args(a, S, max_batch_sites=len(sites), n_slots=1)
+    ctx = capi.Context(prm)
+    ctx.input_buffer(0)[:len(sites)] = gt
+    ctx.submit(0, 1000, len(sites), replay=rp)
+    b = ctx.wait(0)
+    assert b.status == 0
+    orc = oracle_lib.Oracle(a, S)
+    exact_float_required = not (a.precise_gl and a.error_qs == 2)
+    n_f = n_f_exact = n_i = 0
+    for k, d in enumerate(sites):
+        o = b.site(k)
+        assert o["skip_code"] == d.ret, (cid, k)
+        assert np.array_equal(o["fmt_dp"], d.fmt_dp), (cid, k)
+        assert o["info_dp"] == d.info_dp
+        if d.ret != 0 or not d.out:
+            continue
+        assert (o["n_alleles"], o["n_alleles_observed"], o["n_genotypes"]) == \
+            (d.n_alleles, d.n_alleles_observed, d.n_genotypes), (cid, k)
+        if d.info_dp > 0:
+            assert np.array_equal(o["alleles2acgt"], d.alleles2acgt), (cid, k)
+            assert np.array_equal(o["acgt2alleles"], d.acgt2alleles), (cid, k)
+        # the oracle must agree with the dump too (it is pinned separately; cheap cross-check)
+        oo = orc.site_from_dump(d)
+        for key in INT_KEYS:
+            if key in d.out and o.get(key) is not None:
+                assert np.array_equal(o[key], d.out[key]), (cid, k, key, o[key], d.out[key])
+                assert np.array_equal(oo[key], d.out[key])
+                n_i += d.out[key].size
+        for key in ("gl", "gp", "qs", "i16"):
+            if key in d.out and o.get(key) is not None:
+                ok, same = close_f32(o[key], d.out[key])
+                assert ok.all(), (cid, k, key, o[key][~ok], d.out[key][~ok])
+                if key in ("gl", "qs", "i16") and exact_float_required:
+                    assert same.all(), (cid, k, key, o[key][~same], d.out[key][~same])
+                n_f += same.size
+                n_f_exact += int(same.sum())
+    assert n_i + n_f > 0
+    # north_star: >= 95 % of tags bit-exact (100 % of integer tags, asserted above)
+    assert n_f == 0 or n_f_exact / n_f >= 0.95, (cid, n_f_exact, n_f)
+    ctx.close()

@@ -1,0 +1,282 @@
+"""ctypes binding of the C ABI in include/vgl.h (libvgl.so).
+
+This is the only way Python reaches the CUDA kernels; there is no fallback: if
+the shared library is missing or no CUDA device is present, loading or
+`vgl_create` fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import args as vargs
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvgl.so")
+
+VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV = 0, -1, -2, -3, -4, -5, -6
+T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
+SUBMIT_GT_ON_DEVICE = 1
+F32_MISSING_BITS = 0x7F800001
+I32_MISSING = -(2 ** 31)
+
+EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
+           "vgl_slot_timing", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
+           "vgl_last_error", "vgl_abi_version"]
+
+
+class VglParams(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_samples", C.c_int32), ("seed", C.c_int64),
+                ("depth_mode", C.c_int32), ("depth_mean", C.c_double), ("depth_means", C.POINTER(C.c_double)),
+                ("error_rate", C.c_double), ("error_qs", C.c_int32), ("beta_variance", C.c_double),
+                ("gl_model", C.c_int32), ("gl1_theta", C.c_double), ("precise_gl", C.c_int32),
+                ("adjust_qs", C.c_int32), ("adjust_by", C.c_double), ("n_qs_bins", C.c_int32),
+                ("qs_bins", (C.c_uint8 * 3) * 255), ("do_unobserved", C.c_int32),
+                ("rm_invar_sites", C.c_int32), ("rm_empty_sites", C.c_int32), ("do_gvcf", C.c_int32),
+                ("tag_mask", C.c_uint32), ("i16_mapq", C.c_int32), ("device_id", C.c_int32),
+                ("max_batch_sites", C.c_int32), ("n_slots", C.c_int32), ("sampler", C.c_int32),
+                ("host_output", C.c_int32)]
+
+
+class VglReplay(C.Structure):
+    _fields_ = [("depths", C.c_void_p), ("read_offsets", C.c_void_p), ("n_reads", C.c_int64),
+                ("bases", C.c_void_p), ("strands", C.c_void_p), ("qs", C.c_void_p), ("adj_qs", C.c_void_p),
+                ("error_probs", C.c_void_p), ("tail_dists", C.c_void_p), ("n_deep_cells", C.c_int64),
+                ("deep_codes", C.c_void_p)]
+
+
+class VglSiteOut(C.Structure):
+    _fields_ = [("skip_code", C.c_int32), ("n_alleles", C.c_int32), ("n_alleles_observed", C.c_int32),
+                ("n_genotypes", C.c_int32), ("alleles2acgt", C.c_int8 * 8), ("acgt2alleles", C.c_int8 * 8),
+                ("info_dp", C.c_int32), ("info_ad", C.c_int32 * 5), ("info_adf", C.c_int32 * 5),
+                ("info_adr", C.c_int32 * 5), ("qs", C.c_float * 5), ("i16", C.c_float * 16),
+                ("_pad", C.c_int32), ("g_off", C.c_int64), ("r_off", C.c_int64)]
+
+
+SITE_DTYPE = np.dtype([("skip_code", "<i4"), ("n_alleles", "<i4"), ("n_alleles_observed", "<i4"),
+                       ("n_genotypes", "<i4"), ("alleles2acgt", "i1", 8), ("acgt2alleles", "i1", 8),
+                       ("info_dp", "<i4"), ("info_ad", "<i4", 5), ("info_adf", "<i4", 5), ("info_adr", "<i4", 5),
+                       ("qs", "<f4", 5), ("i16", "<f4", 16), ("_pad", "<i4"), ("g_off", "<i8"), ("r_off", "<i8")])
+assert SITE_DTYPE.itemsize == C.sizeof(VglSiteOut), (SITE_DTYPE.itemsize, C.sizeof(VglSiteOut))
+
+
+class VglBatchOut(C.Structure):
+    _fields_ = [("n_sites", C.c_int32), ("n_samples", C.c_int32), ("sites", C.POINTER(VglSiteOut)),
+                ("dp", C.c_void_p), ("gl", C.c_void_p), ("pl", C.c_void_p), ("gp", C.c_void_p),
+                ("ad", C.c_void_p), ("adf", C.c_void_p), ("adr", C.c_void_p),
+                ("g_elems", C.c_int64), ("r_elems", C.c_int64), ("status", C.c_int32)]
+
+
+class VglError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libvgl: %s (status %d)" % (msg, code))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libvgl.so; raises if it was not built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: the CUDA extension must be built (make -C vcfgl_b200/csrc); "
+                          "there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.vgl_create.argtypes = [C.POINTER(VglParams), C.POINTER(C.c_void_p)]
+    L.vgl_destroy.argtypes = [C.c_void_p]
+    L.vgl_destroy.restype = None
+    L.vgl_input_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.vgl_submit.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.POINTER(VglReplay), C.c_uint32]
+    L.vgl_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(VglBatchOut)]
+    L.vgl_set_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.vgl_slot_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    L.vgl_launch_count.argtypes = [C.c_void_p]
+    L.vgl_launch_count.restype = C.c_int64
+    L.vgl_algorithmic_bytes.argtypes = [C.POINTER(VglBatchOut), C.c_uint32]
+    L.vgl_algorithmic_bytes.restype = C.c_int64
+    L.vgl_strerror.argtypes = [C.c_int]
+    L.vgl_strerror.restype = C.c_char_p
+    L.vgl_last_error.argtypes = [C.c_void_p]
+    L.vgl_last_error.restype = C.c_char_p
+    L.vgl_abi_version.restype = C.c_int
+    _lib = L
+    return L
+
+
+def params_from_args(a: vargs.SimArgs, n_samples: int, max_batch_sites: int, n_slots: int = 2,
+                     device_id: int = 0, host_output: bool = True, sampler: int = 0,
+                     fixed_depth: bool = False) -> VglParams:
+    """SimArgs (the reference CLI contract) -> vgl_params"""
+    p = VglParams()
+    p.abi_version = 1
+    p.n_samples = n_samples
+    p.seed = a.seed if a.seed != -1 else 0
+    if a.depths is not None:
+        p.depth_mode = vargs.DEPTH_POISSON_PER_SAMPLE
+        arr = (C.c_double * n_samples)(*a.depths)
+        p._keep = arr
+        p.depth_means = C.cast(arr, C.POINTER(C.c_double))
+        p.depth_mean = 0.0
+    else:
+        p.depth_mode = vargs.DEPTH_FIXED if fixed_depth else vargs.DEPTH_POISSON
+        p.depth_mean = a.depth
+    p.error_rate = a.error_rate
+    p.error_qs = a.error_qs
+    p.beta_variance = a.beta_variance
+    p.gl_model = a.gl_model
+    p.gl1_theta = a.gl1_theta
+    p.precise_gl = a.precise_gl
+    p.adjust_qs = a.adjust_qs
+    p.adjust_by = a.adjust_by
+    bins = a.qs_bins or []
+    p.n_qs_bins = len(bins)
+    for i, (s, e, q) in enumerate(bins):
+        p.qs_bins[i][0], p.qs_bins[i][1], p.qs_bins[i][2] = s, e, q
+    p.do_unobserved = a.do_unobserved
+    p.rm_invar_sites = a.rm_invar_sites
+    p.rm_empty_sites = a.rm_empty_sites
+    p.do_gvcf = a.do_gvcf
+    p.tag_mask = a.tag_mask
+    p.i16_mapq = a.i16_mapq
+    p.device_id = device_id
+    p.max_batch_sites = max_batch_sites
+    p.n_slots = n_slots
+    p.sampler = sampler
+    p.host_output = 1 if host_output else 0
+    return p
+
+
+class Batch:
+    """A finished batch: numpy views over the pinned host result buffers (host_output=1)."""
+
+    def __init__(self, out: VglBatchOut, tag_mask: int, host: bool):
+        self.raw = out
+        self.n_sites = out.n_sites
+        self.S = out.n_samples
+        self.status = out.status
+        self.g_elems = out.g_elems
+        self.r_elems = out.r_elems
+        self.host = host
+        self.tag_mask = tag_mask
+        self.sites = np.ctypeslib.as_array(C.cast(out.sites, C.POINTER(C.c_uint8)),
+                                           shape=(out.n_sites * SITE_DTYPE.itemsize,)).view(SITE_DTYPE)
+
+        def view(ptr, dtype, n):
+            if not ptr or not host:
+                return None
+            ct = {np.float32: C.c_float, np.int32: C.c_int32}[dtype]
+            if n == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+        self.dp = view(out.dp, np.int32, out.n_sites * out.n_samples)
+        self.gl = view(out.gl, np.float32, out.g_elems)
+        self.pl = view(out.pl, np.int32, out.g_elems)
+        self.gp = view(out.gp, np.float32, out.g_elems)
+        self.ad = view(out.ad, np.int32, out.r_elems)
+        self.adf = view(out.adf, np.int32, out.r_elems)
+        self.adr = view(out.adr, np.int32, out.r_elems)
+
+    def site(self, i: int) -> dict:
+        """Everything add_tags() (bcf_utils.cpp:426-507) would emit for site i, as arrays."""
+        s = self.sites[i]
+        S, G, A = self.S, int(s["n_genotypes"]), int(s["n_alleles"])
+        d = dict(skip_code=int(s["skip_code"]), n_alleles=A, n_alleles_observed=int(s["n_alleles_observed"]),
+                 n_genotypes=G, alleles2acgt=s["alleles2acgt"][:5].astype(np.int32),
+                 acgt2alleles=s["acgt2alleles"][:5].astype(np.int32), info_dp=int(s["info_dp"]),
+                 info_ad=s["info_ad"][:A].copy(), info_adf=s["info_adf"][:A].copy(), info_adr=s["info_adr"][:A].copy(),
+                 qs=s["qs"][:A].copy(), i16=s["i16"].copy(),
+                 fmt_dp=self.dp[i * S:(i + 1) * S] if self.dp is not None else None)
+        if d["skip_code"] == 0:
+            g0, r0 = int(s["g_off"]), int(s["r_off"])
+            for k, plane in (("gl", self.gl), ("pl", self.pl), ("gp", self.gp)):
+                d[k] = plane[g0:g0 + S * G] if plane is not None else None
+            for k, plane in (("fmt_ad", self.ad), ("fmt_adf", self.adf), ("fmt_adr", self.adr)):
+                d[k] = plane[r0:r0 + S * A] if plane is not None else None
+        return d
+
+
+class Context:
+    """Owns one vgl_ctx (one GPU)."""
+
+    def __init__(self, params: VglParams):
+        self.L = load()
+        self.params = params
+        self.h = C.c_void_p()
+        rc = self.L.vgl_create(C.byref(params), C.byref(self.h))
+        if rc != VGL_OK:
+            raise VglError(rc, self.L.vgl_strerror(rc).decode())
+        self.S = params.n_samples
+        self.cap = params.max_batch_sites
+        self._keep = {}
+
+    def close(self):
+        if self.h:
+            self.L.vgl_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != VGL_OK:
+            raise VglError(rc, "%s: %s" % (self.L.vgl_strerror(rc).decode(), self.L.vgl_last_error(self.h).decode()))
+
+    def input_buffer(self, slot: int) -> np.ndarray:
+        ptr, cap = C.c_void_p(), C.c_int64()
+        self._ck(self.L.vgl_input_buffer(self.h, slot, C.byref(ptr), C.byref(cap)))
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(cap.value, self.S))
+
+    def set_stream(self, slot: int, stream_ptr: Optional[int]):
+        self._ck(self.L.vgl_set_stream(self.h, slot, C.c_void_p(stream_ptr or 0)))
+
+    def submit(self, slot: int, first_site_id: int, n_sites: int, replay: Optional[dict] = None, flags: int = 0):
+        rp = None
+        if replay is not None:
+            keep = []
+
+            def ptr(x, dt):
+                if x is None:
+                    return None
+                x = np.ascontiguousarray(x, dtype=dt)
+                keep.append(x)
+                return x.ctypes.data
+            r = VglReplay()
+            r.depths = ptr(replay["depths"], np.int32)
+            r.read_offsets = ptr(replay["read_offsets"], np.int64)
+            r.n_reads = int(replay["n_reads"])
+            r.bases = ptr(replay.get("bases"), np.uint8)
+            r.strands = ptr(replay.get("strands"), np.uint8)
+            r.qs = ptr(replay.get("qs"), np.uint8)
+            r.adj_qs = ptr(replay.get("adj_qs"), np.uint8)
+            r.error_probs = ptr(replay.get("error_probs"), np.float64)
+            r.tail_dists = ptr(replay.get("tail_dists"), np.uint8)
+            r.n_deep_cells = int(replay.get("n_deep_cells", 0))
+            r.deep_codes = ptr(replay.get("deep_codes"), np.uint16)
+            self._keep[slot] = keep
+            rp = C.byref(r)
+        self._ck(self.L.vgl_submit(self.h, slot, first_site_id, n_sites, rp, flags))
+
+    def wait(self, slot: int) -> Batch:
+        out = VglBatchOut()
+        self._ck(self.L.vgl_wait(self.h, slot, C.byref(out)))
+        return Batch(out, self.params.tag_mask, bool(self.params.host_output))
+
+    def timing(self, slot: int) -> np.ndarray:
+        ms = (C.c_float * T_COUNT)()
+        self._ck(self.L.vgl_slot_timing(self.h, slot, ms))
+        return np.array(ms[:], np.float64)
+
+    def launch_count(self) -> int:
+        return int(self.L.vgl_launch_count(self.h))
+
+    def algorithmic_bytes(self, batch: Batch) -> int:
+        return int(self.L.vgl_algorithmic_bytes(C.byref(batch.raw), self.params.tag_mask))

@@ -1,0 +1,525 @@
+// C-ABI layer of libvgl.so (include/vgl.h): context, slots, pinned rings, streams,
+// batch submit / wait.  Host code here only moves data and launches kernels; every
+// per-cell computation happens in kernels.cu.  There is no CPU path.
+#include "tables.h"
+#include "vgl_internal.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace vgl;
+
+namespace {
+
+enum { EV_START = 0, EV_H2D, EV_SIM, EV_SITE, EV_SCAN, EV_EMIT, EV_META, EV_D2H0, EV_D2H1, EV_COUNT };
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Slot {
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool submitted = false;
+    bool waited = false;
+    int32_t n_sites = 0;
+    // host (pinned)
+    uint8_t* h_gt = nullptr;
+    vgl_site_out* h_sites = nullptr;
+    int64_t* h_totals = nullptr; // [2] + status in [2]
+    int32_t* h_dp = nullptr;
+    float *h_gl = nullptr, *h_gp = nullptr;
+    int32_t *h_pl = nullptr, *h_ad = nullptr, *h_adf = nullptr, *h_adr = nullptr;
+    // device
+    uint8_t* d_gt = nullptr;
+    int32_t* d_dp = nullptr;
+    CellRec* d_cell = nullptr;
+    CellQ* d_cellq = nullptr;
+    CellTail* d_celltail = nullptr;
+    vgl_site_out* d_sites = nullptr;
+    int64_t* d_totals = nullptr; // [2] totals, then int32 status at [2]
+    float *d_gl = nullptr, *d_gp = nullptr;
+    int32_t *d_pl = nullptr, *d_ad = nullptr, *d_adf = nullptr, *d_adr = nullptr;
+    // replay uploads (grown on demand)
+    DevBuf r_depths, r_off, r_bases, r_strands, r_qs, r_adjqs, r_eprob, r_tails, r_deep_cells, r_deep_codes;
+    float ms[VGL_T_COUNT] = {};
+    bool had_d2h = false;
+};
+
+} // namespace
+
+struct vgl_ctx {
+    vgl_params prm;
+    std::vector<double> depth_means;
+    int gl_mode = 0;
+    PreCalc pre;
+    double beta_a = 0, beta_b = 0;
+    int sample_strand = 0, need_cellq = 0, need_tail = 0;
+    uint8_t bin_lut[256];
+    int bin_max = -1;
+    // device tables
+    double *d_lut = nullptr, *d_m1_bsum = nullptr, *d_m1_het = nullptr, *d_fk = nullptr, *d_beta = nullptr, *d_depth_means = nullptr;
+    std::vector<Slot> slots;
+    size_t g_cap = 0, r_cap = 0; // per-slot plane capacity in elements
+    int64_t launches = 0;
+    std::string err;
+};
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            return VGL_ECUDA;                                                              \
+        }                                                                                  \
+    } while (0)
+
+static int fail(vgl_ctx* ctx, int code, const char* msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+extern "C" int vgl_abi_version(void) { return VGL_ABI_VERSION; }
+
+extern "C" const char* vgl_strerror(int s)
+{
+    switch (s) {
+    case VGL_OK: return "ok";
+    case VGL_EINVAL: return "invalid argument or unsupported option combination";
+    case VGL_ENOMEM: return "out of memory";
+    case VGL_ECUDA: return "CUDA runtime error";
+    case VGL_ESTATE: return "slot in wrong state";
+    case VGL_ERANGE: return "quality score outside every --qs-bins range";
+    case VGL_ENODEV: return "no CUDA device available (libvgl has no CPU path)";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char* vgl_last_error(const vgl_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int64_t vgl_algorithmic_bytes(const vgl_batch_out* o, uint32_t tag_mask)
+{
+    // 1 B packed genotype in + int32/float32 planes as handed to htslib
+    int64_t b = 0;
+    const int64_t S = o->n_samples;
+    for (int i = 0; i < o->n_sites; ++i) {
+        const vgl_site_out& s = o->sites[i];
+        b += S; // genotypes are read for every site, also skipped ones
+        if (s.skip_code != 0) continue;
+        const int64_t G = s.n_genotypes, A = s.n_alleles;
+        const int ng = !!(tag_mask & VGL_TAG_GL) + !!(tag_mask & VGL_TAG_PL) + !!(tag_mask & VGL_TAG_GP);
+        const int na = !!(tag_mask & VGL_TAG_FMT_AD) + !!(tag_mask & VGL_TAG_FMT_ADF) + !!(tag_mask & VGL_TAG_FMT_ADR);
+        b += 4 * S * (G * ng + A * na + !!(tag_mask & VGL_TAG_FMT_DP));
+        b += 4 * (16 * !!(tag_mask & VGL_TAG_I16) + A * (!!(tag_mask & VGL_TAG_QS) + !!(tag_mask & VGL_TAG_INFO_AD) +
+                                                          !!(tag_mask & VGL_TAG_INFO_ADF) + !!(tag_mask & VGL_TAG_INFO_ADR)) +
+                  !!(tag_mask & VGL_TAG_INFO_DP));
+    }
+    return b;
+}
+
+static int validate(const vgl_params* p, std::string& why)
+{
+    // the option rules of io.cpp:860-1000 that concern the hot path
+    if (p->abi_version != VGL_ABI_VERSION) { why = "abi_version mismatch"; return VGL_EINVAL; }
+    if (p->n_samples < 1) { why = "n_samples < 1"; return VGL_EINVAL; }
+    if (p->max_batch_sites < 1 || p->n_slots < 1 || p->n_slots > 8) { why = "bad max_batch_sites / n_slots"; return VGL_EINVAL; }
+    if (p->depth_mode < 0 || p->depth_mode > 2) { why = "bad depth_mode"; return VGL_EINVAL; }
+    if (p->depth_mode == VGL_DEPTH_POISSON_PER_SAMPLE && !p->depth_means) { why = "depth_means missing"; return VGL_EINVAL; }
+    if (p->depth_mode != VGL_DEPTH_POISSON_PER_SAMPLE && !(p->depth_mean >= 0.0 && p->depth_mean <= 500.0)) { why = "--depth out of [0,500]"; return VGL_EINVAL; }
+    if (!(p->error_rate >= 0.0 && p->error_rate < 1.0)) { why = "--error-rate out of [0,1)"; return VGL_EINVAL; }
+    if (p->error_qs < 0 || p->error_qs > 2) { why = "--error-qs out of [0,2]"; return VGL_EINVAL; }
+    if (p->gl_model < 1 || p->gl_model > 2) { why = "--gl-model out of [1,2]"; return VGL_EINVAL; }
+    if (!(p->gl1_theta >= 0.0 && p->gl1_theta <= 1.0)) { why = "--gl1-theta out of [0,1]"; return VGL_EINVAL; }
+    if (p->precise_gl && p->gl_model == 1) { why = "--precise-gl 1 is not supported with --gl-model 1"; return VGL_EINVAL; }
+    if (p->adjust_qs < 0 || p->adjust_qs > 31) { why = "--adjust-qs out of range"; return VGL_EINVAL; }
+    if (p->adjust_qs && p->adjust_by == 0.0) { why = "--adjust-qs requires non-zero --adjust-by"; return VGL_EINVAL; }
+    if ((p->adjust_qs & 1) && p->precise_gl) { why = "--adjust-qs 1 requires --precise-gl 0"; return VGL_EINVAL; }
+    if ((p->adjust_qs & 2) && !(p->tag_mask & VGL_TAG_QS)) { why = "--adjust-qs 2 requires -addQS 1"; return VGL_EINVAL; }
+    if (p->error_qs != 0) {
+        if (!(p->error_rate > 0.0)) { why = "--error-qs 1|2 requires --error-rate > 0"; return VGL_EINVAL; }
+        if (!(p->beta_variance > 0.0)) { why = "--error-qs 1|2 requires --beta-variance > 0"; return VGL_EINVAL; }
+    }
+    if (p->do_unobserved < 0 || p->do_unobserved > 5) { why = "-doUnobserved out of [0,5]"; return VGL_EINVAL; }
+    if (p->i16_mapq < 0 || p->i16_mapq > 60) { why = "--i16-mapq out of [0,60]"; return VGL_EINVAL; }
+    if (p->n_qs_bins < 0 || p->n_qs_bins > 255) { why = "bad n_qs_bins"; return VGL_EINVAL; }
+    if (p->sampler == VGL_SAMPLER_COUNTS && !(p->gl_model == 1 && p->error_qs != 2)) { why = "count-level sampler needs --gl-model 1 and --error-qs 0|1"; return VGL_EINVAL; }
+    return VGL_OK;
+}
+
+template <typename T>
+static cudaError_t upload(T** d, const std::vector<T>& h)
+{
+    cudaError_t e = cudaMalloc((void**)d, h.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" void vgl_destroy(vgl_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->prm.device_id);
+    for (Slot& s : ctx->slots) {
+        if (s.own_stream) cudaStreamSynchronize(s.own_stream);
+        for (auto& e : s.ev)
+            if (e) cudaEventDestroy(e);
+        cudaFreeHost(s.h_gt); cudaFreeHost(s.h_sites); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_dp);
+        cudaFreeHost(s.h_gl); cudaFreeHost(s.h_gp); cudaFreeHost(s.h_pl);
+        cudaFreeHost(s.h_ad); cudaFreeHost(s.h_adf); cudaFreeHost(s.h_adr);
+        cudaFree(s.d_gt); cudaFree(s.d_dp); cudaFree(s.d_cell); cudaFree(s.d_cellq); cudaFree(s.d_celltail);
+        cudaFree(s.d_sites); cudaFree(s.d_totals);
+        cudaFree(s.d_gl); cudaFree(s.d_gp); cudaFree(s.d_pl); cudaFree(s.d_ad); cudaFree(s.d_adf); cudaFree(s.d_adr);
+        for (DevBuf* b : {&s.r_depths, &s.r_off, &s.r_bases, &s.r_strands, &s.r_qs, &s.r_adjqs, &s.r_eprob, &s.r_tails, &s.r_deep_cells, &s.r_deep_codes})
+            cudaFree(b->p);
+        if (s.own_stream) cudaStreamDestroy(s.own_stream);
+    }
+    cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
+    cudaFree(ctx->d_depth_means);
+    delete ctx;
+}
+
+static int create_impl(vgl_ctx* ctx)
+{
+    const vgl_params& p = ctx->prm;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(ctx, VGL_ENODEV, "no CUDA device");
+    if (p.device_id < 0 || p.device_id >= n_dev) return fail(ctx, VGL_EINVAL, "device_id out of range");
+    CK(cudaSetDevice(p.device_id));
+
+    // ---- derived run constants (vcfgl.cpp:1661-1766, rng.h:368-371)
+    if (precalc(p.error_rate, p.error_qs, p.gl_model, p.precise_gl, p.adjust_qs, p.adjust_by, p.n_qs_bins, p.qs_bins, &ctx->pre) != 0)
+        return fail(ctx, VGL_ERANGE, "the fixed quality score falls outside every --qs-bins range");
+    if (p.error_qs != 2) ctx->gl_mode = p.gl_model == 1 ? GL_M1_FIXED : GL_M2_FIXED;
+    else ctx->gl_mode = p.gl_model == 1 ? GL_M1_PERREAD : (p.precise_gl ? GL_M2_PRECISE : GL_M2_LUT);
+    if (p.error_qs != 0) {
+        const double m = p.error_rate, one_over = 1.0 / m;
+        ctx->beta_a = (((1.0 - m) / p.beta_variance) - one_over) * pow(m, 2);
+        ctx->beta_b = ctx->beta_a * (one_over - 1);
+        if (!(ctx->beta_a > 0.0) || !(ctx->beta_b > 0.0)) return fail(ctx, VGL_EINVAL, "beta shape parameters must be positive (rng.h:373-388)");
+    }
+    const uint32_t t = p.tag_mask;
+    ctx->sample_strand = (t & (VGL_TAG_I16 | VGL_TAG_FMT_ADF | VGL_TAG_FMT_ADR | VGL_TAG_INFO_ADF | VGL_TAG_INFO_ADR)) != 0;
+    ctx->need_cellq = p.error_qs == 2 && (t & (VGL_TAG_QS | VGL_TAG_I16));
+    ctx->need_tail = (t & VGL_TAG_I16) != 0;
+    memset(ctx->bin_lut, 0, sizeof ctx->bin_lut);
+    ctx->bin_max = -1;
+    for (int i = 0; i < p.n_qs_bins; ++i) // first matching range wins (vcfgl.cpp:57-64)
+        for (int q = p.qs_bins[i][0]; q <= p.qs_bins[i][1]; ++q)
+            if (q > ctx->bin_max) { ctx->bin_lut[q] = p.qs_bins[i][2]; ctx->bin_max = q; }
+
+    // ---- tables
+    {
+        std::vector<double> lut(&kLutLog10Gl[0][0], &kLutLog10Gl[0][0] + 3 * 257);
+        CK(upload(&ctx->d_lut, lut));
+    }
+    if (p.gl_model == 1) {
+        ErrmodTables em;
+        em.build(1.0 - p.gl1_theta); // io.cpp:1276
+        CK(upload(&ctx->d_m1_het, em.het_term()));
+        if (ctx->gl_mode == GL_M1_FIXED) {
+            const int q = (p.adjust_qs & 1) ? ctx->pre.adj_qs : ctx->pre.qs; // gl_methods.cpp:318
+            CK(upload(&ctx->d_m1_bsum, em.fixed_q_bsum(q)));
+        } else {
+            CK(upload(&ctx->d_fk, em.fk));
+            CK(upload(&ctx->d_beta, em.beta));
+        }
+    }
+    if (p.depth_mode == VGL_DEPTH_POISSON_PER_SAMPLE) CK(upload(&ctx->d_depth_means, ctx->depth_means));
+
+    // ---- slots
+    const size_t B = (size_t)p.max_batch_sites, S = (size_t)p.n_samples, cells = B * S;
+    ctx->g_cap = B * ((S * 15 + 3) & ~(size_t)3);
+    ctx->r_cap = B * ((S * 5 + 3) & ~(size_t)3);
+    ctx->slots.resize(p.n_slots);
+    for (Slot& s : ctx->slots) {
+        CK(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+        s.stream = s.own_stream;
+        for (auto& e : s.ev) CK(cudaEventCreate(&e));
+        CK(cudaHostAlloc((void**)&s.h_gt, cells, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&s.h_sites, B * sizeof(vgl_site_out), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&s.h_totals, 4 * sizeof(int64_t), cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&s.d_gt, cells));
+        CK(cudaMalloc((void**)&s.d_dp, cells * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&s.d_cell, cells * sizeof(CellRec)));
+        if (ctx->need_cellq) CK(cudaMalloc((void**)&s.d_cellq, cells * sizeof(CellQ)));
+        if (ctx->need_tail) CK(cudaMalloc((void**)&s.d_celltail, cells * sizeof(CellTail)));
+        CK(cudaMalloc((void**)&s.d_sites, B * sizeof(vgl_site_out)));
+        CK(cudaMalloc((void**)&s.d_totals, 4 * sizeof(int64_t)));
+        CK(cudaMemset(s.d_totals, 0, 4 * sizeof(int64_t)));
+        if (t & VGL_TAG_GL) CK(cudaMalloc((void**)&s.d_gl, ctx->g_cap * 4));
+        if (t & VGL_TAG_GP) CK(cudaMalloc((void**)&s.d_gp, ctx->g_cap * 4));
+        if (t & VGL_TAG_PL) CK(cudaMalloc((void**)&s.d_pl, ctx->g_cap * 4));
+        if (t & VGL_TAG_FMT_AD) CK(cudaMalloc((void**)&s.d_ad, ctx->r_cap * 4));
+        if (t & VGL_TAG_FMT_ADF) CK(cudaMalloc((void**)&s.d_adf, ctx->r_cap * 4));
+        if (t & VGL_TAG_FMT_ADR) CK(cudaMalloc((void**)&s.d_adr, ctx->r_cap * 4));
+        if (p.host_output) {
+            CK(cudaHostAlloc((void**)&s.h_dp, cells * sizeof(int32_t), cudaHostAllocDefault));
+            if (t & VGL_TAG_GL) CK(cudaHostAlloc((void**)&s.h_gl, ctx->g_cap * 4, cudaHostAllocDefault));
+            if (t & VGL_TAG_GP) CK(cudaHostAlloc((void**)&s.h_gp, ctx->g_cap * 4, cudaHostAllocDefault));
+            if (t & VGL_TAG_PL) CK(cudaHostAlloc((void**)&s.h_pl, ctx->g_cap * 4, cudaHostAllocDefault));
+            if (t & VGL_TAG_FMT_AD) CK(cudaHostAlloc((void**)&s.h_ad, ctx->r_cap * 4, cudaHostAllocDefault));
+            if (t & VGL_TAG_FMT_ADF) CK(cudaHostAlloc((void**)&s.h_adf, ctx->r_cap * 4, cudaHostAllocDefault));
+            if (t & VGL_TAG_FMT_ADR) CK(cudaHostAlloc((void**)&s.h_adr, ctx->r_cap * 4, cudaHostAllocDefault));
+        }
+    }
+    return VGL_OK;
+}
+
+extern "C" int vgl_create(const vgl_params* params, vgl_ctx** out)
+{
+    if (!params || !out) return VGL_EINVAL;
+    *out = nullptr;
+    std::string why;
+    const int v = validate(params, why);
+    if (v != VGL_OK) {
+        fprintf(stderr, "[vgl] invalid parameters: %s\n", why.c_str());
+        return v;
+    }
+    vgl_ctx* ctx = new (std::nothrow) vgl_ctx();
+    if (!ctx) return VGL_ENOMEM;
+    ctx->prm = *params;
+    if (params->depth_mode == VGL_DEPTH_POISSON_PER_SAMPLE) {
+        ctx->depth_means.assign(params->depth_means, params->depth_means + params->n_samples);
+        for (double d : ctx->depth_means)
+            if (!(d >= 0.0 && d <= 500.0)) {
+                delete ctx;
+                return VGL_EINVAL;
+            }
+    }
+    ctx->prm.depth_means = nullptr;
+    const int rc = create_impl(ctx);
+    if (rc != VGL_OK) {
+        fprintf(stderr, "[vgl] vgl_create failed: %s (%s)\n", vgl_strerror(rc), ctx->err.c_str());
+        vgl_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return VGL_OK;
+}
+
+extern "C" int vgl_input_buffer(vgl_ctx* ctx, int slot, uint8_t** gt, int64_t* capacity_sites)
+{
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    if (gt) *gt = ctx->slots[slot].h_gt;
+    if (capacity_sites) *capacity_sites = ctx->prm.max_batch_sites;
+    return VGL_OK;
+}
+
+extern "C" int vgl_set_stream(vgl_ctx* ctx, int slot, void* cuda_stream)
+{
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    Slot& s = ctx->slots[slot];
+    if (s.submitted && !s.waited) return VGL_ESTATE;
+    s.stream = cuda_stream ? (cudaStream_t)cuda_stream : s.own_stream;
+    return VGL_OK;
+}
+
+template <typename T>
+static int stage_replay(vgl_ctx* ctx, DevBuf& b, const T* h, size_t n, cudaStream_t st, const T** d_out)
+{
+    *d_out = nullptr;
+    if (!h || n == 0) return VGL_OK;
+    const size_t bytes = n * sizeof(T);
+    if (b.cap < bytes) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        CK(cudaMalloc(&b.p, bytes));
+        b.cap = bytes;
+    }
+    CK(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, st));
+    *d_out = (const T*)b.p;
+    return VGL_OK;
+}
+
+extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites, const vgl_replay* rp, uint32_t flags)
+{
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    if (n_sites < 1 || n_sites > ctx->prm.max_batch_sites || first_site_id < 0) return fail(ctx, VGL_EINVAL, "n_sites / first_site_id out of range");
+    Slot& s = ctx->slots[slot];
+    if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight: call vgl_wait first");
+    const vgl_params& prm = ctx->prm;
+    CK(cudaSetDevice(prm.device_id));
+    cudaStream_t st = s.stream;
+    const int64_t S = prm.n_samples, cells = (int64_t)n_sites * S;
+
+    DevParams p;
+    memset(&p, 0, sizeof p);
+    p.S = (int32_t)S;
+    p.n_sites = n_sites;
+    p.first_site = first_site_id;
+    p.n_cells = cells;
+    p.k0 = (uint32_t)((uint64_t)prm.seed & 0xFFFFFFFFu);
+    p.k1 = (uint32_t)((uint64_t)prm.seed >> 32);
+    p.depth_mode = prm.depth_mode;
+    p.depth_mean = prm.depth_mean;
+    p.depth_means = ctx->d_depth_means;
+    p.error_rate = prm.error_rate;
+    p.error_qs = prm.error_qs;
+    p.beta_a = ctx->beta_a;
+    p.beta_b = ctx->beta_b;
+    p.gl_mode = ctx->gl_mode;
+    p.adjust_qs = prm.adjust_qs;
+    p.adjust_by = prm.adjust_by;
+    p.use_bins = prm.n_qs_bins > 0;
+    p.bin_max = ctx->bin_max;
+    memcpy(p.bin_lut, ctx->bin_lut, 256);
+    p.do_unobserved = prm.do_unobserved;
+    p.rm_invar_sim = (prm.rm_invar_sites & 4) != 0;
+    p.rm_empty = prm.rm_empty_sites != 0;
+    p.do_gvcf = prm.do_gvcf != 0;
+    p.tag_mask = prm.tag_mask;
+    p.i16_mapq = prm.i16_mapq;
+    p.pre_qs = ctx->pre.qs;
+    p.pre_adj_qs = ctx->pre.adj_qs;
+    p.homT = ctx->pre.homT;
+    p.het = ctx->pre.het;
+    p.homF = ctx->pre.homF;
+    p.sample_strand = ctx->sample_strand;
+    p.need_cellq = ctx->need_cellq;
+    p.need_tail = ctx->need_tail;
+    p.lut_log10 = ctx->d_lut;
+    p.m1_bsum = ctx->d_m1_bsum;
+    p.m1_het = ctx->d_m1_het;
+    p.em_fk = ctx->d_fk;
+    p.em_beta = ctx->d_beta;
+    p.gt = s.d_gt;
+    p.dp = s.d_dp;
+    p.cell = s.d_cell;
+    p.cellq = s.d_cellq;
+    p.celltail = s.d_celltail;
+    p.sites = s.d_sites;
+    p.totals = s.d_totals;
+    p.status = reinterpret_cast<int32_t*>(s.d_totals + 2);
+    p.gl = s.d_gl; p.pl = s.d_pl; p.gp = s.d_gp;
+    p.ad = s.d_ad; p.adf = s.d_adf; p.adr = s.d_adr;
+
+    CK(cudaEventRecord(s.ev[EV_START], st));
+    if (!(flags & VGL_SUBMIT_GT_ON_DEVICE)) CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(s.d_totals, 0, 4 * sizeof(int64_t), st));
+    if (rp) {
+        if (!rp->depths || !rp->read_offsets || (rp->n_reads > 0 && !rp->bases)) return fail(ctx, VGL_EINVAL, "replay: depths/read_offsets/bases required");
+        if (prm.error_qs == 2 && rp->n_reads > 0 && !rp->qs) return fail(ctx, VGL_EINVAL, "replay: per-read qs required with --error-qs 2");
+        if (prm.error_qs == 2 && prm.adjust_qs && rp->n_reads > 0 && !rp->adj_qs) return fail(ctx, VGL_EINVAL, "replay: adjusted qs required with --adjust-qs");
+        if (ctx->gl_mode == GL_M2_PRECISE && rp->n_reads > 0 && !rp->error_probs) return fail(ctx, VGL_EINVAL, "replay: error_probs required with --precise-gl 1");
+        if (ctx->need_tail && rp->n_reads > 0 && !rp->tail_dists) return fail(ctx, VGL_EINVAL, "replay: tail_dists required with -addI16");
+        if (ctx->sample_strand && rp->n_reads > 0 && !rp->strands) return fail(ctx, VGL_EINVAL, "replay: strands required when the strand is sampled");
+        p.replay = 1;
+        int rc;
+        const size_t nr = (size_t)rp->n_reads;
+        if ((rc = stage_replay(ctx, s.r_depths, rp->depths, (size_t)cells, st, &p.rp_depths))) return rc;
+        if ((rc = stage_replay(ctx, s.r_off, rp->read_offsets, (size_t)cells + 1, st, &p.rp_off))) return rc;
+        if ((rc = stage_replay(ctx, s.r_bases, rp->bases, nr, st, &p.rp_bases))) return rc;
+        if ((rc = stage_replay(ctx, s.r_strands, rp->strands, nr, st, &p.rp_strands))) return rc;
+        if ((rc = stage_replay(ctx, s.r_qs, rp->qs, nr, st, &p.rp_qs))) return rc;
+        if ((rc = stage_replay(ctx, s.r_adjqs, rp->adj_qs, nr, st, &p.rp_adjqs))) return rc;
+        if ((rc = stage_replay(ctx, s.r_eprob, rp->error_probs, nr, st, &p.rp_eprob))) return rc;
+        if ((rc = stage_replay(ctx, s.r_tails, rp->tail_dists, nr, st, &p.rp_tails))) return rc;
+        // cells deeper than 255 reads under GL model 1: their ids, in cell order (input packing, not simulation)
+        if (prm.gl_model == 1 && rp->n_deep_cells > 0) {
+            std::vector<int64_t> deep;
+            for (int64_t c = 0; c < cells; ++c) {
+                const uint8_t g = s.h_gt[c];
+                if ((g & 0xF) != VGL_GT_MISSING && (g >> 4) != VGL_GT_MISSING && rp->depths[c] > 255) deep.push_back(c);
+            }
+            if ((int64_t)deep.size() != rp->n_deep_cells) return fail(ctx, VGL_EINVAL, "replay: n_deep_cells does not match the depths");
+            if ((rc = stage_replay(ctx, s.r_deep_cells, deep.data(), deep.size(), st, &p.rp_deep_cells))) return rc;
+            CK(cudaStreamSynchronize(st)); // `deep` is a temporary
+            if ((rc = stage_replay(ctx, s.r_deep_codes, rp->deep_codes, deep.size() * 255, st, &p.rp_deep_codes))) return rc;
+            p.rp_n_deep = (int64_t)deep.size();
+        }
+    }
+    CK(cudaEventRecord(s.ev[EV_H2D], st));
+    launch_sim(p, st);
+    CK(cudaEventRecord(s.ev[EV_SIM], st));
+    launch_site(p, st);
+    CK(cudaEventRecord(s.ev[EV_SITE], st));
+    launch_scan(p, st);
+    CK(cudaEventRecord(s.ev[EV_SCAN], st));
+    launch_emit(p, st);
+    CK(cudaEventRecord(s.ev[EV_EMIT], st));
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[EV_META], st));
+    s.submitted = true;
+    s.waited = false;
+    s.n_sites = n_sites;
+    s.had_d2h = false;
+    return VGL_OK;
+}
+
+extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
+{
+    if (!ctx || !out || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    Slot& s = ctx->slots[slot];
+    if (!s.submitted) return fail(ctx, VGL_ESTATE, "slot was not submitted");
+    const vgl_params& prm = ctx->prm;
+    CK(cudaSetDevice(prm.device_id));
+    CK(cudaEventSynchronize(s.ev[EV_META]));
+    const int64_t g_elems = s.h_totals[0], r_elems = s.h_totals[1];
+    const int32_t status = *reinterpret_cast<int32_t*>(s.h_totals + 2);
+    if (prm.host_output && !s.waited) {
+        cudaStream_t st = s.stream;
+        CK(cudaEventRecord(s.ev[EV_D2H0], st));
+        if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d_pl) CK(cudaMemcpyAsync(s.h_pl, s.d_pl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d_ad) CK(cudaMemcpyAsync(s.h_ad, s.d_ad, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d_adf) CK(cudaMemcpyAsync(s.h_adf, s.d_adf, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d_adr) CK(cudaMemcpyAsync(s.h_adr, s.d_adr, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(s.ev[EV_D2H1], st));
+        CK(cudaEventSynchronize(s.ev[EV_D2H1]));
+        s.had_d2h = true;
+    }
+    if (!s.waited) {
+        float* ms = s.ms;
+        CK(cudaEventElapsedTime(&ms[VGL_T_H2D], s.ev[EV_START], s.ev[EV_H2D]));
+        CK(cudaEventElapsedTime(&ms[VGL_T_SIM], s.ev[EV_H2D], s.ev[EV_SIM]));
+        CK(cudaEventElapsedTime(&ms[VGL_T_SITE], s.ev[EV_SIM], s.ev[EV_SITE]));
+        CK(cudaEventElapsedTime(&ms[VGL_T_SCAN], s.ev[EV_SITE], s.ev[EV_SCAN]));
+        CK(cudaEventElapsedTime(&ms[VGL_T_EMIT], s.ev[EV_SCAN], s.ev[EV_EMIT]));
+        float meta = 0.f, d2h = 0.f;
+        CK(cudaEventElapsedTime(&meta, s.ev[EV_EMIT], s.ev[EV_META]));
+        if (s.had_d2h) CK(cudaEventElapsedTime(&d2h, s.ev[EV_D2H0], s.ev[EV_D2H1]));
+        ms[VGL_T_D2H] = meta + d2h;
+        CK(cudaEventElapsedTime(&ms[VGL_T_TOTAL], s.ev[EV_START], s.had_d2h ? s.ev[EV_D2H1] : s.ev[EV_META]));
+    }
+    s.waited = true;
+    memset(out, 0, sizeof *out);
+    out->n_sites = s.n_sites;
+    out->n_samples = prm.n_samples;
+    out->sites = s.h_sites;
+    const bool h = prm.host_output != 0;
+    out->dp = h ? s.h_dp : s.d_dp;
+    out->gl = h ? s.h_gl : s.d_gl;
+    out->pl = h ? s.h_pl : s.d_pl;
+    out->gp = h ? s.h_gp : s.d_gp;
+    out->ad = h ? s.h_ad : s.d_ad;
+    out->adf = h ? s.h_adf : s.d_adf;
+    out->adr = h ? s.h_adr : s.d_adr;
+    out->g_elems = g_elems;
+    out->r_elems = r_elems;
+    out->status = status;
+    return VGL_OK;
+}
+
+extern "C" int vgl_slot_timing(vgl_ctx* ctx, int slot, float ms[VGL_T_COUNT])
+{
+    if (!ctx || !ms || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    Slot& s = ctx->slots[slot];
+    if (!s.waited) return VGL_ESTATE;
+    memcpy(ms, s.ms, sizeof s.ms);
+    return VGL_OK;
+}

@@ -1,0 +1,130 @@
+// Host-side constant tables.  Compiled with -ffp-contract=off: the table values
+// must equal the reference's bit for bit (plain x86-64 SSE2 double arithmetic,
+// separate multiply and add roundings), because GL model 1 likelihoods are sums
+// of table entries.
+#include "tables.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace vgl {
+
+const double kLutLog10Gl[3][257] = {
+#include "lut_log10_gl.inc"
+};
+
+namespace {
+// log C(n, k), 1 <= k <= n < 256; 0 elsewhere (errmod.c:51-64)
+std::vector<double> log_binomial()
+{
+    std::vector<double> t(256 * 256, 0.0);
+    std::vector<double> lfact(256);
+    for (int n = 0; n < 256; ++n) lfact[n] = lgamma(n + 1);
+    for (int n = 1; n < 256; ++n)
+        for (int k = 1; k <= n; ++k) t[n << 8 | k] = lfact[n] - lfact[k] - lfact[n - k];
+    return t;
+}
+} // namespace
+
+void ErrmodTables::build(double depcorr, double eta)
+{
+    const std::vector<double> lc = log_binomial();
+    fk.assign(256, 0.0);
+    fk[0] = 1.0;
+    for (int n = 1; n < 256; ++n) fk[n] = pow(1. - depcorr, n) * (1.0 - eta) + eta; // errmod.c:75-77
+
+    beta.assign((size_t)64 * 256 * 256, 0.0);
+    for (int q = 1; q < 64; ++q) { // errmod.c:86-99
+        const double e = pow(10.0, -q / 10.0);
+        const double le = log(e), le1 = log(1.0 - e);
+        for (int n = 1; n <= 255; ++n) {
+            double* row = beta.data() + ((size_t)q << 16 | (size_t)n << 8);
+            double upper = lc[n << 8 | n] + n * le; // log of the binomial tail P(K >= k+1)
+            row[n] = HUGE_VAL;
+            for (int k = n - 1; k >= 0; --k) {
+                const double with_k = upper + log1p(exp(lc[n << 8 | k] + k * le + (n - k) * le1 - upper));
+                row[k] = -10. / M_LN10 * (upper - with_k);
+                upper = with_k;
+            }
+        }
+    }
+    lhet.assign(256 * 256, 0.0);
+    for (int n = 0; n < 256; ++n) // errmod.c:107-109
+        for (int k = 0; k < 256; ++k) lhet[n << 8 | k] = lc[n << 8 | k] - M_LN2 * n;
+}
+
+std::vector<double> ErrmodTables::fixed_q_bsum(int q) const
+{
+    if (q < 4) q = 4; // errmod.c:168-169
+    if (q > 63) q = 63;
+    std::vector<double> t(256 * 256, 0.0);
+    for (int n = 1; n <= 255; ++n) {
+        const double* row = beta.data() + ((size_t)q << 16 | (size_t)n << 8);
+        double acc = 0.0;
+        for (int c = 0; c < n; ++c) {
+            acc += fk[c] * row[c]; // two roundings; must not be contracted into an FMA
+            t[n << 8 | (c + 1)] = acc;
+        }
+    }
+    return t;
+}
+
+std::vector<double> ErrmodTables::het_term() const
+{
+    std::vector<double> t(256 * 256);
+    for (int i = 0; i < 256 * 256; ++i) t[i] = -4.343 * lhet[i];
+    return t;
+}
+
+static int bin_lookup(int n_bins, const uint8_t bins[][3], int qs)
+{
+    for (int i = 0; i < n_bins; ++i)
+        if (qs >= bins[i][0] && qs <= bins[i][1]) return bins[i][2];
+    return -1000;
+}
+
+int precalc(double error_rate, int error_qs, int gl_model, int precise_gl, int adjust_qs, double adjust_by,
+            int n_bins, const uint8_t bins[][3], PreCalc* out)
+{
+    *out = PreCalc();
+    if (error_qs == 2) return 0; // per-read quality scores: nothing to precompute
+    int qs, adj = -1;
+    if (error_rate == 0.0) {
+        qs = adj = 63;
+    } else if (error_rate == 1.0) {
+        qs = adj = 0;
+    } else {
+        const double phred = -10.0 * log10(error_rate);
+        qs = (int)phred;
+        if (adjust_qs) adj = (int)(phred + adjust_by);
+    }
+    if (n_bins) {
+        qs = bin_lookup(n_bins, bins, qs);
+        if (adjust_qs) adj = bin_lookup(n_bins, bins, adj);
+        if (qs < 0 || (adjust_qs && adj < 0)) return -1;
+    } else {
+        if (qs > 63) qs = 63;
+        if (adjust_qs && adj > 63) adj = 63;
+    }
+    out->qs = qs;
+    if (adjust_qs) out->adj_qs = adj;
+    if (gl_model == 2) {
+        if (!precise_gl) {
+            const int q = (adjust_qs & 1) ? out->adj_qs : out->qs;
+            out->homT = kLutLog10Gl[0][q];
+            out->het = kLutLog10Gl[1][q];
+            out->homF = kLutLog10Gl[2][q];
+        } else if (error_rate == 0.0) {
+            out->homT = 0;
+            out->het = -0.3010299956639812;
+            out->homF = -INFINITY;
+        } else {
+            out->homT = log10(1.0 - error_rate);
+            out->het = log10((1.0 - error_rate) / 2.0 + error_rate / 6.0);
+            out->homF = log10(error_rate) - 0.47712125471966244;
+        }
+    }
+    return 0;
+}
+
+} // namespace vgl

@@ -1,0 +1,36 @@
+// Host-side constant tables of the simulation core (built once in vgl_create()).
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace vgl {
+
+// samtools/bcftools "revised MAQ" error-model coefficients
+// (reference: htslib/errmod.c:51-125, errmod_init(1 - theta) at io.cpp:1276)
+struct ErrmodTables {
+    std::vector<double> fk;   // [256]          dependency decay  fk[n] = (1-depcorr)^n (1-eta) + eta
+    std::vector<double> beta; // [64][256][256] phred-scaled binomial tail ratios, index q<<16 | n<<8 | k
+    std::vector<double> lhet; // [256][256]     log C(n,k) - n ln 2, index n<<8 | k
+    void build(double depcorr, double eta = 0.03);
+    // for a FIXED quality score q: the running sum errmod_cal() would reach after walking
+    // c reads of one base at depth n:  bsum[n<<8 | c] = sum_{i<c} fk[i] * beta[q][n][i]
+    // (errmod.c:174-177 with w == c because the strand bit is never set, gl_methods.cpp:329)
+    std::vector<double> fixed_q_bsum(int q) const;
+    // -4.343 * lhet[n<<8 | k]  (errmod.c:200)
+    std::vector<double> het_term() const;
+};
+
+// qScore_to_log10_gl[3][257] (shared.cpp:110-114)
+extern const double kLutLog10Gl[3][257];
+
+// derived per-run constants (reference: preCalcStruct io.h:22-32, filled at vcfgl.cpp:1661-1743)
+struct PreCalc {
+    int qs = -1, adj_qs = -1;
+    double homT = -1.0, het = -1.0, homF = -1.0;
+};
+
+// returns 0, or -1 when a qs falls outside the --qs-bins ranges (vcfgl.cpp:63)
+int precalc(double error_rate, int error_qs, int gl_model, int precise_gl, int adjust_qs, double adjust_by,
+            int n_bins, const uint8_t bins[][3], PreCalc* out);
+
+} // namespace vgl

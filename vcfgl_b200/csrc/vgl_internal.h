@@ -1,0 +1,97 @@
+// Internal declarations shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vgl.h"
+
+namespace vgl {
+
+enum GlMode : int {
+    GL_M1_FIXED = 0,   // gl_methods.cpp:304-369  model 1, one qs for every read -> depends on base counts only
+    GL_M1_PERREAD = 1, // gl_methods.cpp:233-302  model 1, per-read qs
+    GL_M2_FIXED = 2,   // gl_methods.cpp:4-69     model 2, run-constant homT/het/homF
+    GL_M2_LUT = 3,     // gl_methods.cpp:71-150   model 2, qs -> LUT
+    GL_M2_PRECISE = 4  // gl_methods.cpp:152-231  model 2, log10 of the per-read error probability
+};
+
+// per-cell record written by the simulate kernel, read by the site and emit kernels (16 B)
+struct __align__(16) CellRec {
+    uint16_t ad[4];  // reads per observed base A,C,G,T
+    uint16_t fwd[4]; // of those, forward-strand reads (0 when the strand is not sampled)
+};
+
+// per-cell quality sums, only when per-read qs AND (QS or I16) are on (32 B)
+struct __align__(16) CellQ {
+    int32_t qsum[4];
+    int32_t qsumsq[4];
+};
+
+// per-cell tail-distance sums, only with I16 (16 B)
+struct __align__(16) CellTail {
+    uint32_t sum, sumsq;
+    int32_t last_base; // base of the cell's last read, -1 if no reads
+    uint32_t _pad;
+};
+
+struct DevParams {
+    // geometry
+    int32_t S, n_sites;
+    int64_t first_site;
+    int64_t n_cells;
+    uint32_t k0, k1; // Philox key
+    // simulation parameters
+    int32_t depth_mode;
+    double depth_mean;
+    const double* depth_means;
+    double error_rate;
+    int32_t error_qs;
+    double beta_a, beta_b;
+    int32_t gl_mode;
+    int32_t adjust_qs;
+    double adjust_by;
+    int32_t use_bins, bin_max;
+    uint8_t bin_lut[256];
+    int32_t do_unobserved, rm_invar_sim, rm_empty, do_gvcf;
+    uint32_t tag_mask;
+    int32_t i16_mapq;
+    int32_t pre_qs, pre_adj_qs; // fixed-qs runs (vcfgl.cpp:1697-1703)
+    double homT, het, homF;     // GL_M2_FIXED constants
+    int32_t sample_strand;      // shared.h:160 PROGRAM_WILL_SAMPLE_STRAND
+    int32_t need_cellq, need_tail;
+    // tables
+    const double* lut_log10;  // [3*257]
+    const double* m1_bsum;    // [256*256] fixed-qs running sums
+    const double* m1_het;     // [256*256] -4.343*lhet
+    const double* em_fk;      // [256]
+    const double* em_beta;    // [64*256*256]
+    // buffers
+    const uint8_t* gt;
+    int32_t* dp;
+    CellRec* cell;
+    CellQ* cellq;
+    CellTail* celltail;
+    vgl_site_out* sites;
+    int64_t* totals; // [2] used G / R elements
+    float* gl;
+    int32_t* pl;
+    float* gp;
+    int32_t *ad, *adf, *adr;
+    int32_t* status;
+    // replay
+    int32_t replay;
+    const int32_t* rp_depths;
+    const int64_t* rp_off;
+    const uint8_t *rp_bases, *rp_strands, *rp_qs, *rp_adjqs, *rp_tails;
+    const double* rp_eprob;
+    const int64_t* rp_deep_cells; // sorted cell ids with depth > 255 (GL model 1)
+    int64_t rp_n_deep;
+    const uint16_t* rp_deep_codes;
+};
+
+void launch_sim(const DevParams& p, cudaStream_t st);
+void launch_site(const DevParams& p, cudaStream_t st);
+void launch_scan(const DevParams& p, cudaStream_t st);
+void launch_emit(const DevParams& p, cudaStream_t st);
+
+} // namespace vgl
