@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the vcfgl simulate-and-score hot path on B200.
+
+Metric (BASELINE.json): simulate+GL throughput in site x sample cells/s.
+Workload (configs[1]): synthetic msprime-shaped genotypes, 100 diploid samples x 1M biallelic
+sites, Poisson depth 10, error 0.01, GL model 1, tags GL+PL+AD(+DP).  One STEP = one pass of the
+hot path over one batch of 131072 sites (13.1 M cells, ~1.9 GB of tag planes -- larger than the
+126 MB L2, so no L2 flush is needed between steps); 8 steps = 1,048,576 sites.
+
+  value  kernel-side throughput: genotypes resident in HBM, results left in HBM, CUDA events
+         on the launching stream (torch's current stream, handed to libvgl).
+  e2e    the same metric through the C ABI with HOST buffers: pinned H2D of the packed
+         genotypes and D2H of every tag plane inside the timed region, two slots in flight.
+  roofline      algorithmic bytes / device time of the kernels, against the
+                measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference binary itself (oracle/_ref/vcfgl_ref, built from /root/reference)
+                on a bounded sample of the same workload on this box's host, 1 thread.
+
+`--impl reference` times the reference CPU binary with one process per host core on contiguous
+site shards (the reference cannot thread its simulation).
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 via torch.distributed.run.
+"""
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sim+GL site x sample cells/s"
+UNIT = "cells/s"
+N_SAMPLES = 100
+BATCH_SITES = 131072
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "vcfgl_ref")
+VCFGL_ARGS = "-d 10 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1".split()
+WORKLOAD = ("cfg2: 100 samples x 1M sites (steps of %d sites), Poisson depth 10, e=0.01, GL model 1, "
+            "tags GL+PL+AD+DP, seed 42" % BATCH_SITES)
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def sim_args():
+    from vcfgl_b200 import args as vargs
+    return vargs.parse_args(["--seed", "42"] + VCFGL_ARGS)
+
+
+# --------------------------------------------------------------------------- reference CPU arm
+def run_reference_shards(n_proc, sites_per_proc, seed, tmp):
+    """P processes of the unmodified reference on P contiguous site shards; returns (cells, wall_s)"""
+    from vcfgl_b200 import synth
+    paths = []
+    for r in range(n_proc):
+        hap = synth.sfs_genotypes(sites_per_proc, N_SAMPLES, seed + r)
+        pos = synth.positions(sites_per_proc, sites_per_proc * 10, seed + r)
+        path = os.path.join(tmp, "shard%d.vcf" % r)
+        synth.write_vcf(path, hap, pos, sites_per_proc * 10)
+        paths.append(path)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen([REF_BIN, "-i", path, "-o", path + ".out", "-O", "u", "--seed", "42"] + VCFGL_ARGS,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for path in paths]
+    rcs = [p.wait() for p in procs]
+    wall = time.perf_counter() - t0
+    if any(rcs):
+        raise RuntimeError("reference binary failed: %s" % rcs)
+    for path in paths:
+        for ext in (".out.bcf", ".out.arg"):
+            try:
+                os.remove(path + ext)
+            except OSError:
+                pass
+    return n_proc * sites_per_proc * N_SAMPLES, wall
+
+
+def reference_arm(opt):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/vcfgl_ref was not built (needs /root/reference at build time)"}))
+        return
+    cores = os.cpu_count() or 1
+    sites_per_proc = 8192
+    tmp = tempfile.mkdtemp(prefix="vgl_refbench_")
+    try:
+        for w in range(opt.warmup):
+            run_reference_shards(cores, 1024, 1000 + w, tmp)
+        cells = 0
+        wall = 0.0
+        for k in range(opt.steps):
+            c, t = run_reference_shards(cores, sites_per_proc, 2000 + 97 * k, tmp)
+            cells += c
+            wall += t
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    value = cells / wall
+    sample = "%d steps x %d processes x %d sites x %d samples, -O u, one process per host core" % (
+        opt.steps, cores, sites_per_proc, N_SAMPLES)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opt.gpus, "steps": opt.steps,
+        "warmup": opt.warmup, "ms_per_step": 1e3 * wall / opt.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU binary (vcfgl v1.3.0 da6a334), whole program: VCF parse + simulate + BCF -O u"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def gpu_arm(opt):
+    import numpy as np
+    import torch
+    from vcfgl_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libvgl has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    a = sim_args()
+    B, S, K, W = BATCH_SITES, N_SAMPLES, opt.steps, opt.warmup
+    cells_per_step = B * S
+    # contiguous site range of this rank (weak scaling: every rank simulates K + W batches of its own)
+    site0 = rank * (K + W + 4) * B
+    hap = synth.sfs_genotypes(B, S, 20260002 + rank)
+    gt = synth.pack_gt(hap)      # binary source: REF=0 -> A, ALT=1 -> C (vcfgl.cpp:103-128)
+    stream = torch.cuda.Stream()   # an explicit stream: libvgl treats a NULL stream as "use the slot's own"
+
+    # ---------------- value: genotypes resident in HBM, results stay in HBM
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=False))
+    for s in (0, 1):
+        ctx.set_stream(s, stream.cuda_stream)
+        ctx.input_buffer(s)[:] = gt
+        ctx.submit(s, site0, B)          # uploads the genotypes once (untimed)
+        ctx.wait(s)
+    step = [0]
+
+    def run_steps(n, flags):
+        # two slots in flight on one stream keeps the GPU queue non-empty
+        pend = []
+        for _ in range(n):
+            s = step[0] & 1
+            if len(pend) == 2:
+                ctx.wait(pend.pop(0))
+            ctx.submit(s, site0 + step[0] * B, B, flags=flags)
+            pend.append(s)
+            step[0] += 1
+        for s in pend:
+            ctx.wait(s)
+
+    run_steps(W, capi.SUBMIT_GT_ON_DEVICE)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = np.zeros(capi.T_COUNT)
+    ev0.record(stream)
+    pend = []
+    for _ in range(K):
+        s = step[0] & 1
+        if len(pend) == 2:
+            d = pend.pop(0)
+            ctx.wait(d)
+            kern_ms += ctx.timing(d)
+        ctx.submit(s, site0 + step[0] * B, B, flags=capi.SUBMIT_GT_ON_DEVICE)
+        pend.append(s)
+        step[0] += 1
+    for d in pend:
+        last = ctx.wait(d)
+        kern_ms += ctx.timing(d)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    ctx.copy_sites(d, last)
+    alg_bytes = ctx.algorithmic_bytes(last)           # of one step (last batch)
+    g_share = float((last.sites["n_genotypes"] == 15).mean())
+    ctx.close()
+    t_max = ms
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_max = float(t.item())
+    value = world * K * cells_per_step / (t_max * 1e-3)
+
+    # ---------------- e2e: host buffers, H2D + kernels + D2H inside the timed region
+    if opt.skip_e2e:     # profiling runs only (ncu); such a line is not a bench result
+        if rank == 0:
+            print(json.dumps({"profiling_only": True, "value": value, "kernel_ms": (kern_ms / K).tolist()}))
+        return
+    Ke = max(2, min(K, 4))
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=True))
+    s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+    ctx.set_stream(0, s_a.cuda_stream)
+    ctx.set_stream(1, s_b.cuda_stream)
+    bufs = [ctx.input_buffer(0), ctx.input_buffer(1)]
+
+    def e2e_steps(n, first):
+        pend = []
+        d2h = 0
+        for i in range(n):
+            s = i & 1
+            if len(pend) == 2:
+                b = ctx.wait(pend.pop(0))
+                d2h = out_bytes(b)
+            bufs[s][:] = gt                       # the caller packs this step's genotypes into pinned memory
+            ctx.submit(s, first + i * B, B)
+            pend.append(s)
+        for s in pend:
+            b = ctx.wait(s)
+            d2h = out_bytes(b)
+        return d2h
+
+    def out_bytes(b):
+        n = b.n_sites * S * 4 + b.n_sites * capi.SITE_DTYPE.itemsize
+        n += 4 * b.g_elems * sum(x is not None for x in (b.gl, b.pl, b.gp))
+        n += 4 * b.r_elems * sum(x is not None for x in (b.ad, b.adf, b.adr))
+        return int(n)
+
+    e2e_steps(2, site0 + (K + W) * B)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s_a)
+    d2h_bytes = e2e_steps(Ke, site0 + (K + W) * B)
+    s_a.wait_stream(s_b)
+    e1.record(s_a)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * Ke * cells_per_step / (e2e_ms * 1e-3)
+    ctx.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the kernels (device time inside the timed region)
+    peak, peak_src = measured_peak()
+    kern_ms /= K
+    dev_ms = float(kern_ms[capi.T_SIM] + kern_ms[capi.T_SITE] + kern_ms[capi.T_SCAN] + kern_ms[capi.T_EMIT])
+    achieved = alg_bytes / (dev_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "kernel": "k_sim+k_site+k_scan+k_emit (one step; algorithmic bytes of the whole path / summed kernel time)",
+            "algorithmic_bytes_per_step": alg_bytes, "bytes_per_cell": alg_bytes / cells_per_step,
+            "kernel_ms": {"k_sim": float(kern_ms[capi.T_SIM]), "k_site": float(kern_ms[capi.T_SITE]),
+                          "k_scan": float(kern_ms[capi.T_SCAN]), "k_emit": float(kern_ms[capi.T_EMIT])},
+            "emit_only": {"achieved": alg_bytes / (float(kern_ms[capi.T_EMIT]) * 1e-3) / 1e9,
+                          "note": "k_emit alone writes every tag plane"}}
+
+    # ---------------- CPU baseline: the reference binary, 1 thread, bounded sample
+    cpu = None
+    if world == 1 and not opt.no_cpu_baseline:
+        if os.path.exists(REF_BIN):
+            tmp = tempfile.mkdtemp(prefix="vgl_cpubase_")
+            try:
+                n_sites = 65536
+                cells, wall = run_reference_shards(1, n_sites, 4242, tmp)
+                cpu = {"value": cells / wall, "unit": UNIT, "cores": 1, "kind": "reference",
+                       "sample": "%d sites x %d samples of the same workload, reference binary -O u, wall %.1f s" % (n_sites, S, wall)}
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/vcfgl_ref missing"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_sites": B, "cells_per_step": cells_per_step,
+                   "l2": "no flush: each step writes %.2f GB of tag planes (> 126 MB L2)" % (alg_bytes / 1e9),
+                   "sites_with_15_genotypes": g_share, "sharding": "contiguous site ranges per GPU, no collective"},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * S), "d2h_bytes_per_step": d2h_bytes,
+                "steps": Ke},
+        "gpu_launches": int(launches), "clocks": clk}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling only: stop after the kernel-side loop")
+    opt = ap.parse_args()
+    opt.warmup = max(opt.warmup, 3) if opt.impl == "b200" else opt.warmup
+    if opt.impl == "reference":
+        reference_arm(opt)
+    else:
+        gpu_arm(opt)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,12 +149,14 @@ typedef struct vgl_site_out {
     int64_t r_off; /* element offset of this site's [n_samples][n_alleles] block in ad/adf/adr */
 } vgl_site_out;
 
-/* results of one batch.  With host_output=1 the pointers are pinned host memory,
- * otherwise device memory.  Planes not requested by tag_mask are NULL. */
+/* results of one batch.  With host_output=1 every pointer is pinned host memory,
+ * with host_output=0 every pointer (also `sites`) is device memory and nothing but
+ * the two totals and the status word crosses PCIe.  Planes not requested by
+ * tag_mask are NULL. */
 typedef struct vgl_batch_out {
     int32_t n_sites;
     int32_t n_samples;
-    const vgl_site_out* sites; /* [n_sites], always host memory */
+    const vgl_site_out* sites; /* [n_sites] */
     const int32_t* dp;         /* FORMAT/DP [n_sites][n_samples] */
     const float* gl;           /* per site: [n_samples][n_genotypes] at sites[i].g_off */
     const int32_t* pl;
@@ -194,6 +196,22 @@ int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out);
 int vgl_set_stream(vgl_ctx* ctx, int slot, void* cuda_stream);
 
 int vgl_slot_timing(vgl_ctx* ctx, int slot, float ms[VGL_T_COUNT]);
+
+/* host_output=0 only: fetch the per-site records of a waited slot into host memory */
+int vgl_copy_sites(vgl_ctx* ctx, int slot, vgl_site_out* host_dst);
+
+/* The native simulator's own draws for a range of sites, in exactly the layout of vgl_replay
+ * (so they can be replayed, fed to the CPU oracle, or printed as a pileup like the reference's
+ * -printPileup, vcfgl.cpp:616-634).  Uses the genotypes currently in the slot's input buffer.
+ * Synchronous; host arrays are owned by the context and valid until the next call on the slot. */
+typedef struct vgl_draws {
+    int64_t n_cells, n_reads;
+    const int32_t* depths;       /* [n_cells] (0 where the genotype is missing) */
+    const int64_t* read_offsets; /* [n_cells + 1] */
+    const uint8_t *bases, *strands, *qs, *adj_qs, *tail_dists; /* [n_reads]; qs/adj_qs only with --error-qs 2 */
+    const double* error_probs;   /* [n_reads], --error-qs 2 */
+} vgl_draws;
+int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites, vgl_draws* out);
 
 /* number of kernel launches issued by this context so far */
 int64_t vgl_launch_count(const vgl_ctx* ctx);

@@ -1,0 +1,91 @@
+"""The product's host-side constant tables (vcfgl_b200/csrc/tables.cpp) against the oracle and, in
+the build container, against the reference's own tables -- bit for bit."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from vcfgl_b200 import args as vargs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "tests", "_tables_shim.so")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    srcs = [os.path.join(ROOT, "tests", "tables_shim.cpp"), os.path.join(ROOT, "vcfgl_b200", "csrc", "tables.cpp")]
+    if not os.path.exists(SHIM) or os.path.getmtime(SHIM) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", SHIM] + srcs)
+    L = C.CDLL(SHIM)
+    for f in ("shim_lut", "shim_fk", "shim_beta", "shim_lhet"):
+        getattr(L, f).restype = C.POINTER(C.c_double)
+    L.shim_errmod.restype = C.c_void_p
+    L.shim_errmod.argtypes = [C.c_double]
+    for f in ("shim_fk", "shim_beta", "shim_lhet", "shim_free"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.shim_fixed_bsum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.shim_precalc.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int),
+                               C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    return L
+
+
+def u64(x):
+    return np.ascontiguousarray(x).view(np.uint64)
+
+
+def test_lut_equals_oracle_lut(shim):
+    got = np.ctypeslib.as_array(shim.shim_lut(), shape=(771,))
+    want = np.ctypeslib.as_array(oracle_lib.lib().vgo_lut_log10_gl(), shape=(771,))
+    assert np.array_equal(u64(got), u64(want))
+    # SURVEY 8(c) anchor values (shared.cpp:111-113, qs 20)
+    assert got[20] == -0.004364805 and got[257 + 20] == -0.303935 and got[514 + 20] == -2.477121
+
+
+@pytest.mark.parametrize("theta", [0.83, 0.6])
+def test_errmod_tables_equal_oracle(shim, theta):
+    a = vargs.parse_args(("-d 1 -e 0.01 -GL 1 --gl1-theta %g" % theta).split())
+    orc = oracle_lib.Oracle(a, 1)
+    t = shim.shim_errmod(1.0 - theta)
+    L = oracle_lib.lib()
+    for name, n in (("fk", 256), ("beta", 64 * 256 * 256), ("lhet", 256 * 256)):
+        got = np.ctypeslib.as_array(getattr(shim, "shim_" + name)(t), shape=(n,))
+        want = np.ctypeslib.as_array(getattr(L, "vgo_errmod_" + name)(orc.ctx), shape=(n,))
+        assert np.array_equal(u64(got), u64(want)), name
+    # fixed-qs running sums: bsum[n][c] = sequential sum_{i<c} fk[i]*beta[q][n][i]
+    fk = np.ctypeslib.as_array(shim.shim_fk(t), shape=(256,))
+    beta = np.ctypeslib.as_array(shim.shim_beta(t), shape=(64, 256, 256))
+    for q in (7, 20, 2, 63):
+        out = np.zeros(65536)
+        shim.shim_fixed_bsum(t, q, out.ctypes.data)
+        out = out.reshape(256, 256)
+        qq = min(max(q, 4), 63)
+        for n in (1, 2, 17, 255):
+            acc = 0.0
+            for c in range(n):
+                acc = acc + fk[c] * beta[qq, n, c]
+                assert out[n, c + 1] == acc
+    shim.shim_free(t)
+
+
+def test_precalc_equals_oracle(shim):
+    for argv in ("-d 1 -e 0.2 -GL 1 --adjust-qs 3 -addQS 1", "-d 1 -e 0.01 -GL 2", "-d 1 -e 0.013 -GL 2 --precise-gl 1",
+                 "-d 1 -e 0 -GL 2", "-d 1 -e 0 -GL 2 --precise-gl 1", "-d 1 -e 0.000001 -GL 2 --adjust-qs 1"):
+        a = vargs.parse_args(argv.split())
+        qs, adj, g = oracle_lib.Oracle(a, 1).precalc()
+        q1, q2, g3 = C.c_int(), C.c_int(), (C.c_double * 3)()
+        assert shim.shim_precalc(a.error_rate, a.error_qs, a.gl_model, a.precise_gl, a.adjust_qs, a.adjust_by,
+                                 C.byref(q1), C.byref(q2), g3) == 0
+        assert (q1.value, q2.value) == (qs, adj), argv
+        assert np.array_equal(u64(np.array(g3[:])), u64(np.array(g))), argv
+
+
+@pytest.mark.container
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle/_ref/libref_shared.so")), reason="needs oracle/_ref")
+def test_lut_equals_reference_table(shim):
+    ref = C.CDLL(os.path.join(ROOT, "oracle/_ref/libref_shared.so"))
+    want = np.array((C.c_double * 771).in_dll(ref, "qScore_to_log10_gl")[:])
+    got = np.ctypeslib.as_array(shim.shim_lut(), shape=(771,))
+    assert np.array_equal(u64(got), u64(want))

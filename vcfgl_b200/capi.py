@@ -24,7 +24,7 @@ F32_MISSING_BITS = 0x7F800001
 I32_MISSING = -(2 ** 31)
 
 EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
-           "vgl_slot_timing", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
+           "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
            "vgl_last_error", "vgl_abi_version"]
 
 
@@ -70,6 +70,13 @@ class VglBatchOut(C.Structure):
                 ("g_elems", C.c_int64), ("r_elems", C.c_int64), ("status", C.c_int32)]
 
 
+class VglDraws(C.Structure):
+    _fields_ = [("n_cells", C.c_int64), ("n_reads", C.c_int64), ("depths", C.c_void_p),
+                ("read_offsets", C.c_void_p), ("bases", C.c_void_p), ("strands", C.c_void_p),
+                ("qs", C.c_void_p), ("adj_qs", C.c_void_p), ("tail_dists", C.c_void_p),
+                ("error_probs", C.c_void_p)]
+
+
 class VglError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libvgl: %s (status %d)" % (msg, code))
@@ -96,6 +103,8 @@ def load():
     L.vgl_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(VglBatchOut)]
     L.vgl_set_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.vgl_slot_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    L.vgl_copy_sites.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.vgl_native_draws.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.POINTER(VglDraws)]
     L.vgl_launch_count.argtypes = [C.c_void_p]
     L.vgl_launch_count.restype = C.c_int64
     L.vgl_algorithmic_bytes.argtypes = [C.POINTER(VglBatchOut), C.c_uint32]
@@ -164,8 +173,10 @@ class Batch:
         self.r_elems = out.r_elems
         self.host = host
         self.tag_mask = tag_mask
-        self.sites = np.ctypeslib.as_array(C.cast(out.sites, C.POINTER(C.c_uint8)),
-                                           shape=(out.n_sites * SITE_DTYPE.itemsize,)).view(SITE_DTYPE)
+        self.sites = None
+        if host:
+            self.sites = np.ctypeslib.as_array(C.cast(out.sites, C.POINTER(C.c_uint8)),
+                                               shape=(out.n_sites * SITE_DTYPE.itemsize,)).view(SITE_DTYPE)
 
         def view(ptr, dtype, n):
             if not ptr or not host:
@@ -270,6 +281,31 @@ class Context:
         self._ck(self.L.vgl_wait(self.h, slot, C.byref(out)))
         return Batch(out, self.params.tag_mask, bool(self.params.host_output))
 
+    def copy_sites(self, slot: int, batch: Batch) -> np.ndarray:
+        """host_output=0: fetch the per-site records of a waited slot (also stored on `batch.sites`)"""
+        arr = np.zeros(batch.n_sites, SITE_DTYPE)
+        self._ck(self.L.vgl_copy_sites(self.h, slot, arr.ctypes.data))
+        batch.sites = arr
+        return arr
+
+    def native_draws(self, slot: int, first_site_id: int, n_sites: int) -> dict:
+        """The Philox simulator's own draws for the genotypes in the slot's input buffer, as a replay
+        dict (copies) that can be passed back to submit(replay=...) or to the CPU oracle."""
+        d = VglDraws()
+        self._ck(self.L.vgl_native_draws(self.h, slot, first_site_id, n_sites, C.byref(d)))
+
+        def arr(ptr, ct, n, dt):
+            if not ptr or n == 0:
+                return None if not ptr else np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+        nc, nr = d.n_cells, d.n_reads
+        return dict(depths=arr(d.depths, C.c_int32, nc, np.int32),
+                    read_offsets=arr(d.read_offsets, C.c_int64, nc + 1, np.int64), n_reads=int(nr),
+                    bases=arr(d.bases, C.c_uint8, nr, np.uint8), strands=arr(d.strands, C.c_uint8, nr, np.uint8),
+                    qs=arr(d.qs, C.c_uint8, nr, np.uint8), adj_qs=arr(d.adj_qs, C.c_uint8, nr, np.uint8),
+                    tail_dists=arr(d.tail_dists, C.c_uint8, nr, np.uint8),
+                    error_probs=arr(d.error_probs, C.c_double, nr, np.float64))
+
     def timing(self, slot: int) -> np.ndarray:
         ms = (C.c_float * T_COUNT)()
         self._ck(self.L.vgl_slot_timing(self.h, slot, ms))
@@ -279,4 +315,9 @@ class Context:
         return int(self.L.vgl_launch_count(self.h))
 
     def algorithmic_bytes(self, batch: Batch) -> int:
-        return int(self.L.vgl_algorithmic_bytes(C.byref(batch.raw), self.params.tag_mask))
+        """SURVEY.md 8(d) bytes of a batch; needs the site records on the host"""
+        assert batch.sites is not None, "call copy_sites() first (host_output=0)"
+        raw = VglBatchOut()
+        C.memmove(C.byref(raw), C.byref(batch.raw), C.sizeof(raw))
+        raw.sites = C.cast(batch.sites.ctypes.data, C.POINTER(VglSiteOut))
+        return int(self.L.vgl_algorithmic_bytes(C.byref(raw), self.params.tag_mask))

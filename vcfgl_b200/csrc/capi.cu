@@ -50,6 +50,11 @@ struct Slot {
     DevBuf r_depths, r_off, r_bases, r_strands, r_qs, r_adjqs, r_eprob, r_tails, r_deep_cells, r_deep_codes;
     float ms[VGL_T_COUNT] = {};
     bool had_d2h = false;
+    // vgl_native_draws() results (host)
+    std::vector<int32_t> dr_depths;
+    std::vector<int64_t> dr_off;
+    std::vector<uint8_t> dr_bases, dr_strands, dr_qs, dr_adjqs, dr_tails;
+    std::vector<double> dr_eprob;
 };
 
 } // namespace
@@ -341,18 +346,10 @@ static int stage_replay(vgl_ctx* ctx, DevBuf& b, const T* h, size_t n, cudaStrea
     return VGL_OK;
 }
 
-extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites, const vgl_replay* rp, uint32_t flags)
+static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id, int32_t n_sites, DevParams& p)
 {
-    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
-    if (n_sites < 1 || n_sites > ctx->prm.max_batch_sites || first_site_id < 0) return fail(ctx, VGL_EINVAL, "n_sites / first_site_id out of range");
-    Slot& s = ctx->slots[slot];
-    if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight: call vgl_wait first");
     const vgl_params& prm = ctx->prm;
-    CK(cudaSetDevice(prm.device_id));
-    cudaStream_t st = s.stream;
     const int64_t S = prm.n_samples, cells = (int64_t)n_sites * S;
-
-    DevParams p;
     memset(&p, 0, sizeof p);
     p.S = (int32_t)S;
     p.n_sites = n_sites;
@@ -403,6 +400,21 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     p.gl = s.d_gl; p.pl = s.d_pl; p.gp = s.d_gp;
     p.ad = s.d_ad; p.adf = s.d_adf; p.adr = s.d_adr;
 
+}
+
+extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites, const vgl_replay* rp, uint32_t flags)
+{
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    if (n_sites < 1 || n_sites > ctx->prm.max_batch_sites || first_site_id < 0) return fail(ctx, VGL_EINVAL, "n_sites / first_site_id out of range");
+    Slot& s = ctx->slots[slot];
+    if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight: call vgl_wait first");
+    const vgl_params& prm = ctx->prm;
+    CK(cudaSetDevice(prm.device_id));
+    cudaStream_t st = s.stream;
+    const int64_t S = prm.n_samples, cells = (int64_t)n_sites * S;
+
+    DevParams p;
+    fill_params(ctx, s, first_site_id, n_sites, p);
     CK(cudaEventRecord(s.ev[EV_START], st));
     if (!(flags & VGL_SUBMIT_GT_ON_DEVICE)) CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(s.d_totals, 0, 4 * sizeof(int64_t), st));
@@ -449,7 +461,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     CK(cudaEventRecord(s.ev[EV_EMIT], st));
     ctx->launches += 4;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
+    if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_META], st));
@@ -500,8 +512,8 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
     memset(out, 0, sizeof *out);
     out->n_sites = s.n_sites;
     out->n_samples = prm.n_samples;
-    out->sites = s.h_sites;
     const bool h = prm.host_output != 0;
+    out->sites = h ? s.h_sites : s.d_sites;
     out->dp = h ? s.h_dp : s.d_dp;
     out->gl = h ? s.h_gl : s.d_gl;
     out->pl = h ? s.h_pl : s.d_pl;
@@ -512,6 +524,76 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
     out->g_elems = g_elems;
     out->r_elems = r_elems;
     out->status = status;
+    return VGL_OK;
+}
+
+extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites, vgl_draws* out)
+{
+    if (!ctx || !out || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    if (n_sites < 1 || n_sites > ctx->prm.max_batch_sites || first_site_id < 0) return fail(ctx, VGL_EINVAL, "n_sites / first_site_id out of range");
+    Slot& s = ctx->slots[slot];
+    if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight");
+    const vgl_params& prm = ctx->prm;
+    CK(cudaSetDevice(prm.device_id));
+    cudaStream_t st = s.stream;
+    const int64_t cells = (int64_t)n_sites * prm.n_samples;
+    DevParams p;
+    fill_params(ctx, s, first_site_id, n_sites, p);
+    CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
+    launch_sim(p, st); // depths (and counts, unused here)
+    ctx->launches += 1;
+    s.dr_depths.resize((size_t)cells);
+    CK(cudaMemcpyAsync(s.dr_depths.data(), s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s.dr_off.resize((size_t)cells + 1);
+    s.dr_off[0] = 0;
+    for (int64_t c = 0; c < cells; ++c) s.dr_off[c + 1] = s.dr_off[c] + s.dr_depths[c]; // output layout only
+    const size_t nr = (size_t)s.dr_off[cells];
+    int64_t* d_off = nullptr;
+    uint8_t* d_u8 = nullptr;
+    double* d_e = nullptr;
+    CK(cudaMalloc((void**)&d_off, ((size_t)cells + 1) * 8));
+    CK(cudaMalloc((void**)&d_u8, 5 * nr + 16));
+    CK(cudaMalloc((void**)&d_e, nr * 8 + 16));
+    CK(cudaMemsetAsync(d_u8, 0, 5 * nr + 16, st));
+    CK(cudaMemsetAsync(d_e, 0, nr * 8 + 16, st));
+    CK(cudaMemcpyAsync(d_off, s.dr_off.data(), ((size_t)cells + 1) * 8, cudaMemcpyHostToDevice, st));
+    launch_draws(p, st, d_off, d_u8, d_u8 + nr, d_u8 + 2 * nr, d_u8 + 3 * nr, d_u8 + 4 * nr, d_e);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    s.dr_bases.resize(nr); s.dr_strands.resize(nr); s.dr_qs.resize(nr); s.dr_adjqs.resize(nr); s.dr_tails.resize(nr);
+    s.dr_eprob.resize(nr);
+    if (nr) {
+        CK(cudaMemcpyAsync(s.dr_bases.data(), d_u8, nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.dr_strands.data(), d_u8 + nr, nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.dr_qs.data(), d_u8 + 2 * nr, nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.dr_adjqs.data(), d_u8 + 3 * nr, nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.dr_tails.data(), d_u8 + 4 * nr, nr, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.dr_eprob.data(), d_e, nr * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_off); cudaFree(d_u8); cudaFree(d_e);
+    out->n_cells = cells;
+    out->n_reads = (int64_t)nr;
+    out->depths = s.dr_depths.data();
+    out->read_offsets = s.dr_off.data();
+    out->bases = s.dr_bases.data();
+    out->strands = s.dr_strands.data();
+    out->qs = prm.error_qs == 2 ? s.dr_qs.data() : nullptr;
+    out->adj_qs = prm.error_qs == 2 && prm.adjust_qs ? s.dr_adjqs.data() : nullptr;
+    out->tail_dists = s.dr_tails.data();
+    out->error_probs = prm.error_qs == 2 ? s.dr_eprob.data() : nullptr;
+    return VGL_OK;
+}
+
+extern "C" int vgl_copy_sites(vgl_ctx* ctx, int slot, vgl_site_out* host_dst)
+{
+    if (!ctx || !host_dst || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    Slot& s = ctx->slots[slot];
+    if (!s.waited) return fail(ctx, VGL_ESTATE, "vgl_copy_sites: call vgl_wait first");
+    CK(cudaSetDevice(ctx->prm.device_id));
+    CK(cudaMemcpyAsync(host_dst, s.d_sites, (size_t)s.n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
     return VGL_OK;
 }
 

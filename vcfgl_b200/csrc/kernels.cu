@@ -222,6 +222,41 @@ __global__ void __launch_bounds__(VGL_BLOCK) k_sim(const __grid_constant__ DevPa
 }
 
 // ==========================================================================
+// k_draws: write every read of the native simulator out (pileup / self-replay support,
+// reference: -printPileup vcfgl.cpp:616-634 exposes the same per-read data)
+// ==========================================================================
+__global__ void __launch_bounds__(VGL_BLOCK) k_draws(const __grid_constant__ DevParams p, const int64_t* __restrict__ off,
+                                                     uint8_t* bases, uint8_t* strands, uint8_t* qs, uint8_t* adjqs,
+                                                     uint8_t* tails, double* eprob)
+{
+    const int64_t c = (int64_t)blockIdx.x * VGL_BLOCK + threadIdx.x;
+    if (c >= p.n_cells) return;
+    const int n = p.dp[c];
+    if (n == 0) return;
+    CellSource cs;
+    cs.init(p, c, p.gt[c]);
+    const int64_t o = off[c];
+    for (int i = 0; i < n; ++i) {
+        const Read r = cs.read(p, i);
+        bases[o + i] = (uint8_t)r.base;
+        strands[o + i] = (uint8_t)r.strand;
+        tails[o + i] = (uint8_t)r.tail;
+        if (p.error_qs == 2) {
+            qs[o + i] = (uint8_t)(r.qs < 0 ? 0 : r.qs);
+            adjqs[o + i] = (uint8_t)(r.adjqs < 0 ? 0 : r.adjqs);
+            eprob[o + i] = r.eprob;
+        }
+    }
+}
+
+void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
+                  uint8_t* adjqs, uint8_t* tails, double* eprob)
+{
+    const unsigned grid = (unsigned)((p.n_cells + VGL_BLOCK - 1) / VGL_BLOCK);
+    k_draws<<<grid, VGL_BLOCK, 0, st>>>(p, off, bases, strands, qs, adjqs, tails, eprob);
+}
+
+// ==========================================================================
 // k_site
 // ==========================================================================
 __device__ __forceinline__ int warp_sum(int v)

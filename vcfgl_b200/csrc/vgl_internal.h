@@ -93,5 +93,7 @@ void launch_sim(const DevParams& p, cudaStream_t st);
 void launch_site(const DevParams& p, cudaStream_t st);
 void launch_scan(const DevParams& p, cudaStream_t st);
 void launch_emit(const DevParams& p, cudaStream_t st);
+void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
+                  uint8_t* adjqs, uint8_t* tails, double* eprob);
 
 } // namespace vgl

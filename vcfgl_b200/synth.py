@@ -24,7 +24,7 @@ def sfs_genotypes(n_sites: int, n_samples: int, seed: int, missing_rate: float =
     k = rng.choice(ks, size=n_sites, p=p)
     # k smallest of H iid uniforms per site == uniform k-subset
     u = rng.random((n_sites, H))
-    thresh = np.partition(u, kth=np.minimum(k, H - 1) - 1, axis=1)[np.arange(n_sites), k - 1]
+    thresh = np.sort(u, axis=1)[np.arange(n_sites), k - 1]
     hap = (u <= thresh[:, None]).astype(np.int8)
     if missing_rate > 0:
         miss = rng.random((n_sites, n_samples)) < missing_rate
@@ -59,16 +59,22 @@ def write_vcf(path: str, hap: np.ndarray, pos: np.ndarray, length: int, contig: 
     """Write binary haplotypes as a tskit-style VCF (for the reference CPU binary)."""
     n_sites, H = hap.shape
     S = H // 2
-    lut = {(-1, -1): ".|.", (0, 0): "0|0", (0, 1): "0|1", (1, 0): "1|0", (1, 1): "1|1"}
-    codes = (hap[:, 0::2].astype(np.int16) + 1) * 3 + (hap[:, 1::2].astype(np.int16) + 1)
-    table = np.array([lut.get((a - 1, b - 1), ".|.") for a in range(3) for b in range(3)])
-    with open(path, "w") as fh:
-        fh.write("##fileformat=VCFv4.2\n##source=vcfgl_b200.synth\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n")
-        fh.write("##contig=<ID=%s,length=%d>\n" % (contig, length))
-        fh.write("##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n")
-        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" +
-                 "\t".join("tsk_%d" % i for i in range(S)) + "\n")
+    # one 4-byte field per sample: "a|b\t" (".|.\t" when missing)
+    ch = np.where(hap < 0, ord("."), hap + ord("0")).astype(np.uint8)
+    body = np.empty((n_sites, S, 4), np.uint8)
+    body[:, :, 0] = ch[:, 0::2]
+    body[:, :, 1] = ord("|")
+    body[:, :, 2] = ch[:, 1::2]
+    body[:, :, 3] = ord("\t")
+    body = body.reshape(n_sites, S * 4)
+    body[:, -1] = ord("\n")
+    with open(path, "wb") as fh:
+        fh.write(("##fileformat=VCFv4.2\n##source=vcfgl_b200.synth\n"
+                  "##FILTER=<ID=PASS,Description=\"All filters passed\">\n"
+                  "##contig=<ID=%s,length=%d>\n"
+                  "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+                  "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n"
+                  % (contig, length, "\t".join("tsk_%d" % i for i in range(S)))).encode())
         for i in range(n_sites):
-            fh.write("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t" % (contig, pos[i], ref, alt))
-            fh.write("\t".join(table[codes[i]]))
-            fh.write("\n")
+            fh.write(("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t" % (contig, pos[i], ref, alt)).encode())
+            fh.write(body[i].tobytes())
