@@ -1,0 +1,206 @@
+// vgl_host.hpp -- C++ host side above the C ABI (include/vgl.h), mirroring the reference's operator
+// interface for the hot path so that the reference's driver loop can switch over with a few lines:
+//
+//   reference                                   here
+//   ---------                                   ----
+//   simRecord (bcf_utils.h:81-396)              vgl::SimRecordView  (same member names, read-only views)
+//   simulate_record_values(sim) per site        vgl::BatchSimulator::push_site() + on_record callback
+//     (vcfgl.cpp:327, called :1522,1552,1611)
+//   return codes 0 / -3 / -4                    SimRecordView::ret
+//   sim->add_tags()  (bcf_utils.cpp:426-507)    the callback passes the view's arrays to bcf_update_*
+//   ERROR()/exit(1)  (shared.h:292-327)         vgl::Error exception carrying the vgl_status
+//
+// Header-only; link with -lvgl.  One BatchSimulator per GPU (one host thread each).
+#pragma once
+#include "../../include/vgl.h"
+
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace vgl {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string& what) : std::runtime_error(what), status(s) {}
+};
+
+// One site's results with the reference's simRecord field names (bcf_utils.h:85-211).
+struct SimRecordView {
+    int64_t site_id = 0;  // global running index given to push_site()
+    void* user = nullptr; // whatever the caller attached to the site (e.g. its bcf1_t*)
+    int ret = 0;          // 0, -3 (simulated invariant, vcfgl.cpp:677), -4 (empty, vcfgl.cpp:401)
+    int nSamples = 0, nAlleles = 0, nAllelesObserved = 0, nGenotypes = 0;
+    int allele_unobserved = -1;
+    int alleles2acgt[5], acgt2alleles[5];
+    std::string alleles;  // "A,C,<*>" ... as passed to bcf_update_alleles_str (vcfgl.cpp:739-782)
+    const int32_t* fmt_dp_arr = nullptr; // [nSamples]
+    int32_t info_dp_arr[1] = {0};
+    const float* gl_arr = nullptr;       // [nSamples*nGenotypes]
+    const int32_t* pl_arr = nullptr;
+    const float* gp_arr = nullptr;
+    const int32_t *fmt_ad_arr = nullptr, *fmt_adf_arr = nullptr, *fmt_adr_arr = nullptr; // [nSamples*nAlleles]
+    const int32_t *info_ad_arr = nullptr, *info_adf_arr = nullptr, *info_adr_arr = nullptr; // [nAlleles]
+    const float* qs_arr = nullptr;       // [nAlleles]
+    const float* i16_arr = nullptr;      // [16]
+    // current_size_bcf_tag_number[] equivalents (bcf_utils.h:25-36)
+    int size_fmt_G() const { return nSamples * nGenotypes; }
+    int size_fmt_R() const { return nSamples * nAlleles; }
+};
+
+// allele string of a simulated site; no-reads sites follow simulate_site_with_no_reads (vcfgl.cpp:228-315)
+inline std::string alleles_string(const vgl_site_out& s, int do_unobserved, int do_gvcf)
+{
+    const char* nonref = (do_unobserved == 2 || do_unobserved == 5) ? "<NON_REF>" : "<*>";
+    if (s.info_dp == 0) {
+        if (do_gvcf) return "<NON_REF>";
+        switch (do_unobserved) {
+        case 0: return ".";
+        case 1: return "<*>";
+        case 2: return "<NON_REF>";
+        case 3: return "A,C,G,T";
+        case 4: return "A,C,G,T,<*>";
+        default: return "A,C,G,T,<NON_REF>";
+        }
+    }
+    std::string out;
+    for (int a = 0; a < s.n_alleles; ++a) {
+        if (a) out += ',';
+        const int b = s.alleles2acgt[a];
+        if (b == 4) out += nonref;
+        else out += "ACGT"[b];
+    }
+    return out;
+}
+
+class BatchSimulator {
+public:
+    using Callback = std::function<void(const SimRecordView&)>;
+
+    // params: fill from the parsed argStruct (io.h:40-148); host_output is forced on.
+    BatchSimulator(vgl_params params, Callback on_record) : prm_(params), cb_(std::move(on_record))
+    {
+        prm_.abi_version = VGL_ABI_VERSION;
+        prm_.host_output = 1;
+        if (prm_.n_slots < 2) prm_.n_slots = 2;
+        const int rc = vgl_create(&prm_, &ctx_);
+        if (rc != VGL_OK) throw Error(rc, std::string("vgl_create: ") + vgl_strerror(rc));
+        pending_.resize(prm_.n_slots);
+        open_slot();
+    }
+    ~BatchSimulator() { vgl_destroy(ctx_); }
+    BatchSimulator(const BatchSimulator&) = delete;
+    BatchSimulator& operator=(const BatchSimulator&) = delete;
+
+    // In place of simulate_record_values(sim): true_gts_acgt_int is what check_rec_alleles() filled
+    // (vcfgl.cpp:133-146): 2*nSamples ints in {-1,0,1,2,3}.  Results arrive later through the callback,
+    // strictly in push order.
+    void push_site(const int* true_gts_acgt_int, void* user = nullptr)
+    {
+        uint8_t* row = in_ + (size_t)fill_ * prm_.n_samples;
+        for (int s = 0; s < prm_.n_samples; ++s) {
+            const int h0 = true_gts_acgt_int[2 * s], h1 = true_gts_acgt_int[2 * s + 1];
+            row[s] = VGL_GT_PACK(h0 < 0 ? VGL_GT_MISSING : h0, h1 < 0 ? VGL_GT_MISSING : h1);
+        }
+        pending_[cur_].users.push_back(user);
+        if (++fill_ == prm_.max_batch_sites) submit_current();
+    }
+
+    // end of input: run the partial batch and deliver everything outstanding
+    void finish()
+    {
+        if (fill_ > 0) submit_current();
+        for (int k = 0; k < prm_.n_slots; ++k) drain((cur_ + k) % prm_.n_slots);
+    }
+
+    int64_t sites_pushed() const { return next_site_; }
+
+private:
+    struct Pending {
+        bool in_flight = false;
+        int64_t first = 0;
+        std::vector<void*> users;
+    };
+
+    void check(int rc, const char* what)
+    {
+        if (rc != VGL_OK) throw Error(rc, std::string(what) + ": " + vgl_strerror(rc) + " (" + vgl_last_error(ctx_) + ")");
+    }
+
+    void open_slot()
+    {
+        drain(cur_); // the slot we are about to refill must have been delivered
+        int64_t cap = 0;
+        check(vgl_input_buffer(ctx_, cur_, &in_, &cap), "vgl_input_buffer");
+        fill_ = 0;
+        pending_[cur_].users.clear();
+    }
+
+    void submit_current()
+    {
+        Pending& p = pending_[cur_];
+        p.first = next_site_;
+        check(vgl_submit(ctx_, cur_, next_site_, fill_, nullptr, 0), "vgl_submit");
+        p.in_flight = true;
+        next_site_ += fill_;
+        cur_ = (cur_ + 1) % prm_.n_slots;
+        open_slot(); // delivers the older batch while this one runs on the GPU
+    }
+
+    void drain(int slot)
+    {
+        Pending& p = pending_[slot];
+        if (!p.in_flight) return;
+        vgl_batch_out out;
+        check(vgl_wait(ctx_, slot, &out), "vgl_wait");
+        if (out.status != VGL_OK) throw Error(out.status, vgl_strerror(out.status));
+        SimRecordView v;
+        v.nSamples = out.n_samples;
+        const int S = out.n_samples;
+        for (int i = 0; i < out.n_sites; ++i) {
+            const vgl_site_out& s = out.sites[i];
+            v.site_id = p.first + i;
+            v.user = p.users[(size_t)i];
+            v.ret = s.skip_code;
+            v.nAlleles = s.n_alleles;
+            v.nAllelesObserved = s.n_alleles_observed;
+            v.nGenotypes = s.n_genotypes;
+            v.allele_unobserved = -1;
+            for (int a = 0; a < 5; ++a) {
+                v.alleles2acgt[a] = s.alleles2acgt[a];
+                v.acgt2alleles[a] = s.acgt2alleles[a];
+                if (s.alleles2acgt[a] == 4) v.allele_unobserved = a;
+            }
+            v.alleles = s.skip_code == 0 ? alleles_string(s, prm_.do_unobserved, prm_.do_gvcf) : std::string();
+            v.fmt_dp_arr = out.dp + (size_t)i * S;
+            v.info_dp_arr[0] = s.info_dp;
+            v.gl_arr = out.gl ? out.gl + s.g_off : nullptr;
+            v.pl_arr = out.pl ? out.pl + s.g_off : nullptr;
+            v.gp_arr = out.gp ? out.gp + s.g_off : nullptr;
+            v.fmt_ad_arr = out.ad ? out.ad + s.r_off : nullptr;
+            v.fmt_adf_arr = out.adf ? out.adf + s.r_off : nullptr;
+            v.fmt_adr_arr = out.adr ? out.adr + s.r_off : nullptr;
+            v.info_ad_arr = s.info_ad;
+            v.info_adf_arr = s.info_adf;
+            v.info_adr_arr = s.info_adr;
+            v.qs_arr = s.qs;
+            v.i16_arr = s.i16;
+            cb_(v);
+        }
+        p.in_flight = false;
+    }
+
+    vgl_params prm_;
+    Callback cb_;
+    vgl_ctx* ctx_ = nullptr;
+    std::vector<Pending> pending_;
+    uint8_t* in_ = nullptr;
+    int cur_ = 0;
+    int32_t fill_ = 0;
+    int64_t next_site_ = 0;
+};
+
+} // namespace vgl
