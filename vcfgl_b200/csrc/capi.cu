@@ -44,6 +44,8 @@ struct Slot {
     CellTail* d_celltail = nullptr;
     vgl_site_out* d_sites = nullptr;
     int64_t* d_totals = nullptr; // [2] totals, then int32 status at [2]
+    uint64_t* d_pairmap = nullptr;
+    unsigned long long* d_tile_state = nullptr; // fused: [max tiles] look-back words, then the ticket
     float *d_gl = nullptr, *d_gp = nullptr;
     int32_t *d_pl = nullptr, *d_ad = nullptr, *d_adf = nullptr, *d_adr = nullptr;
     // replay uploads (grown on demand)
@@ -69,6 +71,9 @@ struct vgl_ctx {
     uint8_t bin_lut[256];
     int bin_max = -1;
     // device tables
+    int use_fused = 0, n_sms = 148;
+    unsigned long long* d_pois = nullptr;
+    int pois_n = 0;
     double *d_lut = nullptr, *d_m1_bsum = nullptr, *d_m1_het = nullptr, *d_fk = nullptr, *d_beta = nullptr, *d_depth_means = nullptr;
     std::vector<Slot> slots;
     size_t g_cap = 0, r_cap = 0; // per-slot plane capacity in elements
@@ -156,7 +161,9 @@ static int validate(const vgl_params* p, std::string& why)
     if (p->do_unobserved < 0 || p->do_unobserved > 5) { why = "-doUnobserved out of [0,5]"; return VGL_EINVAL; }
     if (p->i16_mapq < 0 || p->i16_mapq > 60) { why = "--i16-mapq out of [0,60]"; return VGL_EINVAL; }
     if (p->n_qs_bins < 0 || p->n_qs_bins > 255) { why = "bad n_qs_bins"; return VGL_EINVAL; }
+    if (p->sampler < 0 || p->sampler > 2) { why = "bad sampler"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && !(p->gl_model == 1 && p->error_qs != 2)) { why = "count-level sampler needs --gl-model 1 and --error-qs 0|1"; return VGL_EINVAL; }
+    if (p->sampler == VGL_SAMPLER_COUNTS && (p->tag_mask & (VGL_TAG_QS | VGL_TAG_I16))) { why = "count-level sampler does not produce QS / I16 (use VGL_SAMPLER_PER_READ)"; return VGL_EINVAL; }
     return VGL_OK;
 }
 
@@ -180,14 +187,14 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         cudaFreeHost(s.h_gl); cudaFreeHost(s.h_gp); cudaFreeHost(s.h_pl);
         cudaFreeHost(s.h_ad); cudaFreeHost(s.h_adf); cudaFreeHost(s.h_adr);
         cudaFree(s.d_gt); cudaFree(s.d_dp); cudaFree(s.d_cell); cudaFree(s.d_cellq); cudaFree(s.d_celltail);
-        cudaFree(s.d_sites); cudaFree(s.d_totals);
+        cudaFree(s.d_sites); cudaFree(s.d_totals); cudaFree(s.d_pairmap); cudaFree(s.d_tile_state);
         cudaFree(s.d_gl); cudaFree(s.d_gp); cudaFree(s.d_pl); cudaFree(s.d_ad); cudaFree(s.d_adf); cudaFree(s.d_adr);
         for (DevBuf* b : {&s.r_depths, &s.r_off, &s.r_bases, &s.r_strands, &s.r_qs, &s.r_adjqs, &s.r_eprob, &s.r_tails, &s.r_deep_cells, &s.r_deep_codes})
             cudaFree(b->p);
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois);
     delete ctx;
 }
 
@@ -238,6 +245,21 @@ static int create_impl(vgl_ctx* ctx)
         }
     }
     if (p.depth_mode == VGL_DEPTH_POISSON_PER_SAMPLE) CK(upload(&ctx->d_depth_means, ctx->depth_means));
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, p.device_id));
+        ctx->n_sms = prop.multiProcessorCount;
+    }
+    // the fused single-kernel path: native RNG, GL model 1 with a run-constant qs, count-level sampler
+    const size_t g_cap_elems = (size_t)p.max_batch_sites * (((size_t)p.n_samples * 15 + 3) & ~(size_t)3);
+    ctx->use_fused = ctx->gl_mode == GL_M1_FIXED && p.sampler != VGL_SAMPLER_PER_READ &&
+                     !(t & (VGL_TAG_QS | VGL_TAG_I16)) && g_cap_elems < (1ull << 31);
+    if (p.sampler == VGL_SAMPLER_COUNTS && !ctx->use_fused) return fail(ctx, VGL_EINVAL, "count-level sampler unavailable for this configuration (plane too large)");
+    if (ctx->use_fused && p.depth_mode == VGL_DEPTH_POISSON) {
+        const std::vector<unsigned long long> cdf = poisson_cdf_u64(p.depth_mean, 1024);
+        ctx->pois_n = (int)cdf.size();
+        CK(upload(&ctx->d_pois, cdf));
+    }
 
     // ---- slots
     const size_t B = (size_t)p.max_batch_sites, S = (size_t)p.n_samples, cells = B * S;
@@ -258,6 +280,8 @@ static int create_impl(vgl_ctx* ctx)
         if (ctx->need_tail) CK(cudaMalloc((void**)&s.d_celltail, cells * sizeof(CellTail)));
         CK(cudaMalloc((void**)&s.d_sites, B * sizeof(vgl_site_out)));
         CK(cudaMalloc((void**)&s.d_totals, 4 * sizeof(int64_t)));
+        CK(cudaMalloc((void**)&s.d_pairmap, B * sizeof(uint64_t)));
+        if (ctx->use_fused) CK(cudaMalloc((void**)&s.d_tile_state, (B + 2) * sizeof(unsigned long long)));
         CK(cudaMemset(s.d_totals, 0, 4 * sizeof(int64_t)));
         if (t & VGL_TAG_GL) CK(cudaMalloc((void**)&s.d_gl, ctx->g_cap * 4));
         if (t & VGL_TAG_GP) CK(cudaMalloc((void**)&s.d_gp, ctx->g_cap * 4));
@@ -396,6 +420,17 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.celltail = s.d_celltail;
     p.sites = s.d_sites;
     p.totals = s.d_totals;
+    p.pairmap = s.d_pairmap;
+    p.pois_cdf = ctx->d_pois;
+    p.pois_n = ctx->pois_n;
+    {
+        int T = 1024 / (int)S;
+        T = T < 1 ? 1 : (T > 128 ? 128 : T);
+        p.sites_per_tile = T;
+        p.n_tiles = (n_sites + T - 1) / T;
+        p.tile_state = s.d_tile_state;
+        p.ticket = s.d_tile_state ? reinterpret_cast<uint32_t*>(s.d_tile_state + p.n_tiles) : nullptr;
+    }
     p.status = reinterpret_cast<int32_t*>(s.d_totals + 2);
     p.gl = s.d_gl; p.pl = s.d_pl; p.gp = s.d_gp;
     p.ad = s.d_ad; p.adf = s.d_adf; p.adr = s.d_adr;
@@ -450,16 +485,28 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             p.rp_n_deep = (int64_t)deep.size();
         }
     }
+    const bool fused = ctx->use_fused && !rp;
+    if (fused) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));
-    launch_sim(p, st);
-    CK(cudaEventRecord(s.ev[EV_SIM], st));
-    launch_site(p, st);
-    CK(cudaEventRecord(s.ev[EV_SITE], st));
-    launch_scan(p, st);
-    CK(cudaEventRecord(s.ev[EV_SCAN], st));
-    launch_emit(p, st);
-    CK(cudaEventRecord(s.ev[EV_EMIT], st));
-    ctx->launches += 4;
+    if (fused) {
+        // one kernel does everything; its time is reported as VGL_T_EMIT (SIM / SITE / SCAN = 0)
+        CK(cudaEventRecord(s.ev[EV_SIM], st));
+        CK(cudaEventRecord(s.ev[EV_SITE], st));
+        CK(cudaEventRecord(s.ev[EV_SCAN], st));
+        launch_fused_m1f(p, st, ctx->n_sms);
+        CK(cudaEventRecord(s.ev[EV_EMIT], st));
+        ctx->launches += 1;
+    } else {
+        launch_sim(p, st);
+        CK(cudaEventRecord(s.ev[EV_SIM], st));
+        launch_site(p, st);
+        CK(cudaEventRecord(s.ev[EV_SITE], st));
+        launch_scan(p, st);
+        CK(cudaEventRecord(s.ev[EV_SCAN], st));
+        launch_emit(p, st);
+        CK(cudaEventRecord(s.ev[EV_EMIT], st));
+        ctx->launches += 4;
+    }
     CK(cudaGetLastError());
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -533,6 +580,7 @@ extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, i
     if (n_sites < 1 || n_sites > ctx->prm.max_batch_sites || first_site_id < 0) return fail(ctx, VGL_EINVAL, "n_sites / first_site_id out of range");
     Slot& s = ctx->slots[slot];
     if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight");
+    if (ctx->use_fused) return fail(ctx, VGL_ESTATE, "per-read draws do not exist under the count-level sampler (create the context with VGL_SAMPLER_PER_READ)");
     const vgl_params& prm = ctx->prm;
     CK(cudaSetDevice(prm.device_id));
     cudaStream_t st = s.stream;

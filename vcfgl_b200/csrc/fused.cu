@@ -1,0 +1,431 @@
+// k_fused_m1f -- the whole hot path in ONE kernel for the headline configuration: native RNG,
+// GL model 1 with a run-constant quality score (--error-qs 0/1), count-level sampler.
+//
+// Persistent CTAs (one wave, a multiple of the SM count) pull TILES of whole sites from an atomic
+// ticket.  Per tile:
+//   phase 1  every cell of the tile is sampled (counts_sampler.cuh); FORMAT/DP is written; per-site
+//            totals are reduced in shared memory (warp REDUX + shared atomics)
+//   phase 2  one thread per site: allele order, unobserved allele, skip code, INFO tags
+//            (vcfgl.cpp:665-782); the tile's output size is published and its base offset obtained by
+//            decoupled look-back over earlier tiles -> deterministic, compact, in-order layout
+//   phase 3  every cell is sampled AGAIN (counter-based RNG: identical draws, nothing is stored) and
+//            scored: errmod GL, PL, GP, AD/ADF/ADR in allele order, staged per 256-cell chunk in
+//            shared memory and written with 128-bit stores
+// HBM traffic = 1 B/cell in, the tag planes out; nothing intermediate touches DRAM.
+#include "counts_sampler.cuh"
+#include "m1f.cuh"
+
+namespace vgl {
+
+#define FUSED_BLOCK 256
+#define FUSED_TILE_CELLS 1024
+#define FUSED_MAX_SITES 128
+#define FUSED_POIS_MAX 1024
+#define FUSED_STAGE (FUSED_BLOCK * 16 + 8)
+
+struct TileSite {
+    uint64_t pairmap;
+    int64_t g_off, r_off;
+    int32_t A, G, skip;
+    uint32_t a2b;   // nibble a = base of allele a (0xF none)
+    double e;       // base-picking error probability of the site
+    float l2, er;   // log2(1-e) (0 = use the slow binomial), e/(1-e)
+};
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// tile_state word: flag (2 bits: 1 = aggregate, 2 = inclusive prefix) | g elements (31 bits) | r elements (31 bits)
+#define TS_PACK(flag, g, r) (((unsigned long long)(flag) << 62) | ((unsigned long long)(g) << 31) | (unsigned long long)(r))
+#define TS_FLAG(w) ((int)((w) >> 62))
+#define TS_G(w) ((long long)(((w) >> 31) & 0x7FFFFFFFull))
+#define TS_R(w) ((long long)((w)&0x7FFFFFFFull))
+
+__device__ __forceinline__ void store_span_f(uint32_t* __restrict__ plane, const uint32_t* stage, int64_t base, int64_t lo, int64_t hi)
+{
+    const int n_chunks = (int)((hi - base + 3) >> 2);
+    for (int ch = threadIdx.x; ch < n_chunks; ch += FUSED_BLOCK) {
+        const int64_t e = base + 4ll * ch;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + 4 * ch);
+        if (e >= lo && e + 4 <= hi) {
+            __stcs(reinterpret_cast<uint4*>(plane + e), v); // streaming 128-bit store
+        } else {
+            if (e + 0 >= lo && e + 0 < hi) plane[e + 0] = v.x;
+            if (e + 1 >= lo && e + 1 < hi) plane[e + 1] = v.y;
+            if (e + 2 >= lo && e + 2 < hi) plane[e + 2] = v.z;
+            if (e + 3 >= lo && e + 3 < hi) plane[e + 3] = v.w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_constant__ DevParams p)
+{
+    __shared__ __align__(16) uint32_t stage_a[FUSED_STAGE];
+    __shared__ __align__(16) uint32_t stage_b[FUSED_STAGE];
+    __shared__ TileSite st[FUSED_MAX_SITES];
+    __shared__ int tot[FUSED_MAX_SITES][9]; // dp, ad[4], fwd[4]
+    extern __shared__ unsigned long long pois[]; // [pois_n] Poisson CDF (dynamic)
+    __shared__ int64_t span[4];
+    __shared__ int64_t s_base[2];
+    __shared__ int s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int S = p.S, T = p.sites_per_tile;
+    for (int i = tid; i < p.pois_n; i += FUSED_BLOCK) pois[i] = p.pois_cdf[i];
+    CountsParams cp;
+    cp.key.k0 = p.k0;
+    cp.key.k1 = p.k1;
+    cp.depth_mode = p.depth_mode;
+    cp.depth_mean = p.depth_mean;
+    cp.depth_means = p.depth_means;
+    cp.pois_cdf = pois;
+    cp.pois_n = p.pois_n;
+    cp.sample_strand = p.sample_strand;
+    // i / S for i < 1024 when a tile holds several sites (exact for S < 1024)
+    const uint32_t inv_s = (uint32_t)(((1u << 20) + S - 1) / S);
+    const bool explode = p.do_unobserved >= 3;
+    const bool add_unobs = p.do_unobserved == 1 || p.do_unobserved == 2 || p.do_unobserved == 4 || p.do_unobserved == 5;
+
+    for (;;) {
+        __syncthreads(); // previous tile fully done with shared memory
+        if (tid == 0) s_tile = (int)atomicAdd(p.ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= p.n_tiles) break;
+        const int site0 = tile * T;
+        const int nsl = min(T, p.n_sites - site0);
+        const int ncell = nsl * S;
+        const int64_t cell0 = (int64_t)site0 * S;
+
+        // ---------------- phase 0: per-site constants
+        for (int i = tid; i < nsl * 9; i += FUSED_BLOCK) (&tot[0][0])[i] = 0;
+        if (tid < nsl) {
+            double e = p.error_rate;
+            if (p.error_qs == 1) { // per-site beta-distributed error rate (vcfgl.cpp:425-437)
+                Stream bs;
+                bs.init(cp.key, p.first_site + site0 + tid, 0xFFFFFFFFu, 0, P_SITE);
+                e = beta_draw(bs, p.beta_a, p.beta_b);
+            }
+            st[tid].e = e;
+            st[tid].l2 = (e > 0.0 && e <= 0.5) ? log2f((float)(1.0 - e)) : 0.0f;
+            st[tid].er = (float)(e / (1.0 - e));
+        }
+        __syncthreads();
+
+        // ---------------- phase 1: sample, FORMAT/DP, per-site totals
+        for (int i0 = 0; i0 < ncell; i0 += FUSED_BLOCK) {
+            const int i = i0 + tid;
+            const bool live = i < ncell;
+            int sl = 0, sample = i;
+            if (T > 1) { sl = (int)(((uint32_t)i * inv_s) >> 20); sample = i - sl * S; }
+            CellCounts cc;
+            cc.n = 0; cc.ad = cc.fwd = 0;
+            if (live) {
+                const uint8_t gt = p.gt[cell0 + i];
+                cc = sample_counts(cp, p.first_site + site0 + sl, (uint32_t)sample, gt, st[sl].e, st[sl].l2, st[sl].er);
+                p.dp[cell0 + i] = cc.n;
+            } else {
+                sl = -1;
+            }
+            // warp-aggregated reduction into the site totals
+            const int first = __shfl_sync(0xffffffffu, sl, 0);
+            const bool uniform = __all_sync(0xffffffffu, sl == first || sl < 0);
+            int v[9];
+            v[0] = cc.n;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                v[1 + b] = (int)((cc.ad >> (16 * b)) & 0xFFFF);
+                v[5 + b] = (int)((cc.fwd >> (16 * b)) & 0xFFFF);
+            }
+            if (uniform) {
+                if (first >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        if (k >= 5 && !p.sample_strand) break;
+                        const int s = __reduce_add_sync(0xffffffffu, v[k]);
+                        if (lane == 0 && s) atomicAdd(&tot[first][k], s);
+                    }
+                }
+            } else if (live) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    if (v[k]) atomicAdd(&tot[sl][k], v[k]);
+            }
+        }
+        __syncthreads();
+
+        // ---------------- phase 2: per-site record (vcfgl.cpp:396-404, 665-782, 806-843 INFO part)
+        int64_t my_g = 0, my_r = 0;
+        vgl_site_out o;
+        if (tid < nsl) {
+            const int* t = tot[tid];
+            const int dp = t[0];
+            o.skip_code = 0;
+            o.n_alleles = o.n_alleles_observed = o.n_genotypes = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.alleles2acgt[i] = o.acgt2alleles[i] = -1;
+            o.info_dp = dp;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { o.info_ad[i] = o.info_adf[i] = o.info_adr[i] = 0; o.qs[i] = 0.0f; }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o.i16[i] = 0.0f;
+            o._pad = 0;
+            int b2a[5] = {-1, -1, -1, -1, -1};
+            uint32_t a2b = 0xFFFFFFFFu;
+            if (dp == 0) {
+                if (p.rm_empty) o.skip_code = -4;
+                else if (!p.do_gvcf) {
+                    if (p.do_unobserved <= 2) { o.n_alleles = 1; o.n_genotypes = 1; o.n_alleles_observed = 0; }
+                    else if (p.do_unobserved == 3) { o.n_alleles = 4; o.n_genotypes = 10; o.n_alleles_observed = 4; }
+                    else { o.n_alleles = 5; o.n_genotypes = 15; o.n_alleles_observed = 4; }
+                }
+            } else {
+                int n_obs = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) n_obs += t[1 + b] > 0;
+                if (p.rm_invar_sim && n_obs == 1) {
+                    o.skip_code = -3;
+                } else {
+                    int n_alleles = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        int rank = 0;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) rank += (t[1 + x] > t[1 + b]) || (t[1 + x] == t[1 + b] && x < b);
+                        if (t[1 + b] > 0 || explode) {
+                            b2a[b] = rank;
+                            o.acgt2alleles[b] = (int8_t)rank;
+                            a2b = (a2b & ~(0xFu << (4 * rank))) | ((uint32_t)b << (4 * rank));
+                            ++n_alleles;
+                        }
+                    }
+                    o.n_alleles_observed = n_alleles;
+                    if (add_unobs) {
+                        b2a[4] = n_alleles;
+                        o.acgt2alleles[4] = (int8_t)n_alleles;
+                        a2b = (a2b & ~(0xFu << (4 * n_alleles))) | (4u << (4 * n_alleles));
+                        ++n_alleles;
+                    }
+                    o.n_alleles = n_alleles;
+                    o.n_genotypes = n_alleles * (n_alleles + 1) / 2;
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) {
+                        const int b = (int)((a2b >> (4 * a)) & 0xF);
+                        o.alleles2acgt[a] = b == 0xF ? (int8_t)-1 : (int8_t)b;
+                        if (a < n_alleles && b < 4) {
+                            if (p.tag_mask & VGL_TAG_INFO_AD) o.info_ad[a] = t[1 + b];
+                            if (p.tag_mask & VGL_TAG_INFO_ADF) o.info_adf[a] = t[5 + b];
+                            if (p.tag_mask & VGL_TAG_INFO_ADR) o.info_adr[a] = t[1 + b] - t[5 + b];
+                        }
+                    }
+                }
+            }
+            const bool keep = o.skip_code == 0 && o.n_alleles > 0;
+            st[tid].A = keep ? o.n_alleles : 0;
+            st[tid].G = keep ? o.n_genotypes : 0;
+            st[tid].skip = !keep;
+            st[tid].a2b = a2b;
+            st[tid].pairmap = make_pairmap(b2a);
+            if (o.skip_code == 0) {
+                my_g = (((int64_t)S * o.n_genotypes) + 3) & ~3ll;
+                my_r = (((int64_t)S * o.n_alleles) + 3) & ~3ll;
+            }
+        }
+        // exclusive scan of the tile's block sizes (nsl <= 128: warps 0..3, then 4 partials)
+        {
+            int64_t ig = my_g, ir = my_r;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int64_t tg = __shfl_up_sync(0xffffffffu, ig, off);
+                const int64_t tr = __shfl_up_sync(0xffffffffu, ir, off);
+                if (lane >= off) { ig += tg; ir += tr; }
+            }
+            int64_t* wsum = reinterpret_cast<int64_t*>(stage_a); // [8][2] scratch
+            if (lane == 31) { wsum[2 * (tid >> 5)] = ig; wsum[2 * (tid >> 5) + 1] = ir; }
+            __syncthreads();
+            int64_t pre_g = 0, pre_r = 0, tile_g = 0, tile_r = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { // only the first 128 threads carry sites
+                if (w < (tid >> 5)) { pre_g += wsum[2 * w]; pre_r += wsum[2 * w + 1]; }
+                tile_g += wsum[2 * w];
+                tile_r += wsum[2 * w + 1];
+            }
+            const int64_t ex_g = pre_g + ig - my_g, ex_r = pre_r + ir - my_r;
+            // decoupled look-back (warp 0): base offset of this tile = sum of all earlier tiles
+            if (tid < 32) {
+                if (lane == 0) st_state(p.tile_state + tile, TS_PACK(1, tile_g, tile_r));
+                int64_t bg = 0, br = 0;
+                int look = tile - 1;
+                while (look >= 0) {
+                    const int idx = look - lane;
+                    unsigned long long w = TS_PACK(2, 0, 0); // lanes before tile 0 behave as a zero inclusive prefix
+                    if (idx >= 0) {
+                        do { w = ld_state(p.tile_state + idx); } while (TS_FLAG(w) == 0);
+                    }
+                    const unsigned incl = __ballot_sync(0xffffffffu, TS_FLAG(w) == 2);
+                    const int stop = incl ? (__ffs(incl) - 1) : 31; // nearest inclusive prefix
+                    int64_t g = lane <= stop ? TS_G(w) : 0, r = lane <= stop ? TS_R(w) : 0;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        g += __shfl_xor_sync(0xffffffffu, g, off);
+                        r += __shfl_xor_sync(0xffffffffu, r, off);
+                    }
+                    bg += g;
+                    br += r;
+                    if (incl) break;
+                    look -= 32;
+                }
+                if (lane == 0) {
+                    st_state(p.tile_state + tile, TS_PACK(2, bg + tile_g, br + tile_r));
+                    s_base[0] = bg;
+                    s_base[1] = br;
+                    if (tile == p.n_tiles - 1) { p.totals[0] = bg + tile_g; p.totals[1] = br + tile_r; }
+                }
+            }
+            __syncthreads();
+            if (tid < nsl) {
+                o.g_off = s_base[0] + ex_g;
+                o.r_off = s_base[1] + ex_r;
+                st[tid].g_off = o.g_off;
+                st[tid].r_off = o.r_off;
+                p.sites[site0 + tid] = o;
+            }
+        }
+        __syncthreads();
+
+        // ---------------- phase 3: re-sample, score, emit (chunks of 256 cells)
+        for (int i0 = 0; i0 < ncell; i0 += FUSED_BLOCK) {
+            const int i = i0 + tid;
+            const bool live = i < ncell;
+            int sl = nsl - 1, sample = S; // dead lanes sit just past the last cell of the tile
+            if (live) {
+                sl = 0; sample = i;
+                if (T > 1) { sl = (int)(((uint32_t)i * inv_s) >> 20); sample = i - sl * S; }
+            }
+            const TileSite& ts = st[sl];
+            const int A = ts.A, G = ts.G;
+            int64_t gpos = ts.g_off + (int64_t)sample * G, rpos = ts.r_off + (int64_t)sample * A;
+            if (!live && !ts.skip) { // end of the last site's padded block
+                gpos = ts.g_off + ((((int64_t)S * G) + 3) & ~3ll);
+                rpos = ts.r_off + ((((int64_t)S * A) + 3) & ~3ll);
+            }
+            const bool pad_owner = live && !ts.skip && sample == S - 1;
+            if (tid == 0) { span[0] = gpos; span[2] = rpos; }
+            if (tid == FUSED_BLOCK - 1) {
+                int64_t ge = gpos + (live ? G : 0), re = rpos + (live ? A : 0);
+                if (pad_owner) { ge = (ge + 3) & ~3ll; re = (re + 3) & ~3ll; }
+                span[1] = ge; span[3] = re;
+            }
+            __syncthreads();
+            const int64_t g_lo = span[0], g_hi = span[1], r_lo = span[2], r_hi = span[3];
+            const int64_t g_base = g_lo & ~3ll, r_base = r_lo & ~3ll;
+            float* my_gl = reinterpret_cast<float*>(stage_a) + (gpos - g_base);
+            int32_t* my_pl = reinterpret_cast<int32_t*>(stage_b) + (gpos - g_base);
+            const int g_pad = pad_owner ? (int)((((int64_t)S * G + 3) & ~3ll) - (int64_t)S * G) : 0;
+            const int r_pad = pad_owner ? (int)((((int64_t)S * A + 3) & ~3ll) - (int64_t)S * A) : 0;
+            CellCounts cc;
+            cc.n = 0; cc.ad = cc.fwd = 0;
+            if (live && !ts.skip) {
+                const int64_t site = p.first_site + site0 + sl;
+                cc = sample_counts(cp, site, (uint32_t)sample, p.gt[cell0 + i], ts.e, ts.l2, ts.er);
+                if (cc.n == 0) { // gl_methods.cpp:359-366
+                    for (int g = 0; g < G; ++g) { my_gl[g] = f32_missing(); my_pl[g] = VGL_I32_MISSING; }
+                } else {
+                    uint64_t ad = cc.ad;
+                    int nn = cc.n;
+                    if (nn > 255) { ad = subsample_counts_255(cp, site, (uint32_t)sample, ad, nn); nn = 255; } // errmod.c:156-159
+                    float q[15];
+                    m1f_scores(nn, (int)(ad & 0xFFFF), (int)((ad >> 16) & 0xFFFF), (int)((ad >> 32) & 0xFFFF), (int)(ad >> 48),
+                               p.m1_bsum, p.m1_het, q);
+                    float mx = -CUDART_INF_F;
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) {
+                        q[k] = neg_div10(q[k]);
+                        if (((ts.pairmap >> (4 * k)) & 0xF) != 0xF) mx = fmaxf(mx, q[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) {
+                        const int slot = (int)((ts.pairmap >> (4 * k)) & 0xF);
+                        if (slot != 0xF) {
+                            const float v = __fsub_rn(q[k], mx);
+                            my_gl[slot] = v;
+                            my_pl[slot] = pl_from_gl(v);
+                        }
+                    }
+                }
+                for (int g = 0; g < g_pad; ++g) { my_gl[G + g] = 0.0f; my_pl[G + g] = 0; }
+            }
+            __syncthreads();
+            if (p.gl) store_span_f(reinterpret_cast<uint32_t*>(p.gl), stage_a, g_base, g_lo, g_hi);
+            if (p.pl) store_span_f(reinterpret_cast<uint32_t*>(p.pl), stage_b, g_base, g_lo, g_hi);
+            if (p.gp) { // vcfgl.cpp:941-970
+                __syncthreads();
+                if (live && !ts.skip) {
+                    float* gp = reinterpret_cast<float*>(my_pl);
+                    if (cc.n == 0) {
+                        for (int g = 0; g < G; ++g) gp[g] = f32_missing();
+                    } else {
+                        float sum = 0.0f;
+                        for (int g = 0; g < G; ++g) {
+                            const float v = __double2float_rn(exp10((double)my_gl[g]));
+                            gp[g] = v;
+                            sum = __fadd_rn(sum, v);
+                        }
+                        for (int g = 0; g < G; ++g) gp[g] = __fdiv_rn(gp[g], sum);
+                    }
+                }
+                __syncthreads();
+                store_span_f(reinterpret_cast<uint32_t*>(p.gp), stage_b, g_base, g_lo, g_hi);
+            }
+            __syncthreads();
+            // AD / ADF / ADR in allele order (vcfgl.cpp:806-831): AD -> stage_a, ADF -> stage_b, then ADR -> stage_a
+            if (p.ad || p.adf || p.adr) {
+                int32_t* ra = reinterpret_cast<int32_t*>(stage_a) + (rpos - r_base);
+                int32_t* rb = reinterpret_cast<int32_t*>(stage_b) + (rpos - r_base);
+                if (live && !ts.skip) {
+                    for (int a = 0; a < A; ++a) {
+                        const int b = (int)((ts.a2b >> (4 * a)) & 0xF);
+                        const int c = b < 4 ? (int)((cc.ad >> (16 * b)) & 0xFFFF) : 0;
+                        const int f = b < 4 ? (int)((cc.fwd >> (16 * b)) & 0xFFFF) : 0;
+                        ra[a] = c;
+                        rb[a] = f;
+                    }
+                    for (int a = 0; a < r_pad; ++a) { ra[A + a] = 0; rb[A + a] = 0; }
+                }
+                __syncthreads();
+                if (p.ad) store_span_f(reinterpret_cast<uint32_t*>(p.ad), stage_a, r_base, r_lo, r_hi);
+                if (p.adf) store_span_f(reinterpret_cast<uint32_t*>(p.adf), stage_b, r_base, r_lo, r_hi);
+                if (p.adr) {
+                    __syncthreads();
+                    if (live && !ts.skip)
+                        for (int a = 0; a < A; ++a) ra[a] = ra[a] - rb[a];
+                    __syncthreads();
+                    store_span_f(reinterpret_cast<uint32_t*>(p.adr), stage_a, r_base, r_lo, r_hi);
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms)
+{
+    int per_sm = 1;
+    const size_t dyn = (size_t)(p.pois_n > 0 ? p.pois_n : 1) * sizeof(unsigned long long);
+    cudaFuncSetAttribute(k_fused_m1f, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_POIS_MAX * 8);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_m1f, FUSED_BLOCK, dyn);
+    if (per_sm < 1) per_sm = 1;
+    int grid = n_sms * per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    k_fused_m1f<<<grid, FUSED_BLOCK, dyn, st>>>(p);
+}
+
+} // namespace vgl

@@ -1,0 +1,101 @@
+// GL model 1 with one quality score for every read (gl_methods.cpp:304-369 +
+// htslib/errmod.c:143-208): the 5x5 errmod matrix depends only on the four base counts.
+// Branch-free restatement in base-pair space, bit-exact with the reference's float/double mixing.
+#pragma once
+#include "vgl_internal.h"
+
+#include <math_constants.h>
+
+namespace vgl {
+
+// base-pair index of the unordered pair (j <= k): k*(k+1)/2 + j, j,k in 0..4 (4 = unobserved allele)
+// pairmap: nibble `pair` holds the output (allele-space) genotype slot of that base pair, 0xF = the
+// site does not have both alleles.  Built once per site.
+__device__ __forceinline__ uint64_t make_pairmap(const int (&b2a)[5])
+{
+    uint64_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int j = 0; j <= k; ++j) {
+            const int aj = b2a[j], ak = b2a[k];
+            uint64_t slot = 0xF;
+            if (aj >= 0 && ak >= 0) {
+                const int hi = aj > ak ? aj : ak, lo = aj > ak ? ak : aj;
+                slot = (uint64_t)(hi * (hi + 1) / 2 + lo); // bcf_alleles2gt, htslib/vcf.h:902
+            }
+            m |= slot << (4 * (k * (k + 1) / 2 + j));
+        }
+    return m;
+}
+
+// float accumulator fed a double (errmod.c:182,187,197): tmp1 += bsum  <=>  (float)((double)tmp1 + bsum)
+__device__ __forceinline__ float acc_add(float acc, double b) { return __double2float_rn(__dadd_rn((double)acc, b)); }
+
+// (float)((-1.0 * (double)q) / 10.0), gl_methods.cpp:343.  One correctly rounded float division gives
+// the same float: q/10 is never closer than 0.1 ulp to a float rounding boundary, so the double
+// intermediate cannot change the result.
+__device__ __forceinline__ float neg_div10(float q) { return -__fdiv_rn(q, 10.0f); }
+
+// lroundf((float)(-10.0 * (double)gl)) capped at 255 (vcfgl.cpp:931-934) for gl <= 0: the double
+// product is exact so one float multiply rounds identically; round-half-away via trunc + fraction.
+__device__ __forceinline__ int pl_from_gl(float gl)
+{
+    const float x = fminf(__fmul_rn(-10.0f, gl), 300.0f);
+    int i = __float2int_rz(x);
+    i += (x - (float)i) >= 0.5f;
+    return i > 255 ? 255 : i;
+}
+
+// phred-scaled errmod likelihoods q[pair] for all 15 base pairs from the counts c0..c3 of a cell with
+// n = c0+c1+c2+c3 reads, 1 <= n <= 255.  bsum = fixed-qs running-sum table [n<<8|c], het = -4.343*lhet.
+__device__ __forceinline__ void m1f_scores(int n, int c0, int c1, int c2, int c3, const double* __restrict__ bsum,
+                                           const double* __restrict__ het, float (&q)[15])
+{
+    const double* row = bsum + (n << 8);
+    const double b0 = __ldg(row + c0), b1 = __ldg(row + c1), b2 = __ldg(row + c2), b3 = __ldg(row + c3);
+    // sequential float sums over base subsets, in base order (adding a 0.0 term is the identity, so
+    // "skip if no reads" branches of the reference are not needed)
+    const float f0 = __double2float_rn(b0), f1 = __double2float_rn(b1), f2 = __double2float_rn(b2);
+    const float p01 = acc_add(f0, b1), p02 = acc_add(f0, b2), p03 = acc_add(f0, b3);
+    const float p12 = acc_add(f1, b2), p13 = acc_add(f1, b3), p23 = acc_add(f2, b3);
+    const float t012 = acc_add(p01, b2), t013 = acc_add(p01, b3), t023 = acc_add(p02, b3), t123 = acc_add(p12, b3);
+    const float q0123 = acc_add(t012, b3);
+    // homozygous jj: everything that is not j (errmod.c:185-191)
+    q[0] = t123; q[2] = t023; q[5] = t013; q[9] = t012; q[14] = q0123;
+    // heterozygous jk, j<k<4 (errmod.c:193-202): -4.343*lhet[cj+ck][ck] + the other two bases
+#define VGL_HET(cj, ck, rest) __double2float_rn(__dadd_rn(__ldg(het + (((cj) + (ck)) << 8 | (ck))), (double)(rest)))
+    q[1] = VGL_HET(c0, c1, p23);
+    q[3] = VGL_HET(c0, c2, p13);
+    q[4] = VGL_HET(c1, c2, p03);
+    q[6] = VGL_HET(c0, c3, p12);
+    q[7] = VGL_HET(c1, c3, p02);
+    q[8] = VGL_HET(c2, c3, p01);
+    // j with the unobserved allele (index 4, no reads): lhet[cj][0] + everything that is not j
+    q[10] = VGL_HET(c0, 0, t123);
+    q[11] = VGL_HET(c1, 0, t023);
+    q[12] = VGL_HET(c2, 0, t013);
+    q[13] = VGL_HET(c3, 0, t012);
+#undef VGL_HET
+#pragma unroll
+    for (int i = 0; i < 15; ++i) q[i] = q[i] < 0.0f ? 0.0f : q[i]; // errmod.c:204
+}
+
+// scatter the base-pair scores into the cell's allele-ordered GL slots (shared memory), rescale to
+// max 0 (gl_methods.cpp:338-357)
+__device__ __forceinline__ void m1f_store_gl(const float (&q)[15], uint64_t pairmap, int G, float* my_gl)
+{
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) {
+        const int slot = (int)((pairmap >> (4 * i)) & 0xF);
+        const float v = neg_div10(q[i]);
+        if (slot != 0xF) {
+            my_gl[slot] = v;
+            mx = fmaxf(mx, v);
+        }
+    }
+    for (int g = 0; g < G; ++g) my_gl[g] = __fsub_rn(my_gl[g], mx);
+}
+
+} // namespace vgl

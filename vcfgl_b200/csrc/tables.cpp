@@ -76,6 +76,26 @@ std::vector<double> ErrmodTables::het_term() const
     return t;
 }
 
+std::vector<unsigned long long> poisson_cdf_u64(double lambda, int max_n)
+{
+    std::vector<unsigned long long> t;
+    const long double two64 = 18446744073709551616.0L;
+    long double cdf = 0.0L;
+    for (int k = 0; k < max_n; ++k) {
+        long double pmf;
+        if (lambda <= 0.0) pmf = k == 0 ? 1.0L : 0.0L;
+        else pmf = expl(-(long double)lambda + k * logl((long double)lambda) - lgammal((long double)k + 1.0L));
+        cdf += pmf;
+        if (cdf >= 1.0L - 1e-19L || k == max_n - 1) {
+            t.push_back(~0ull);
+            break;
+        }
+        const long double scaled = cdf * two64;
+        t.push_back(scaled >= two64 ? ~0ull : (unsigned long long)scaled);
+    }
+    return t;
+}
+
 static int bin_lookup(int n_bins, const uint8_t bins[][3], int qs)
 {
     for (int i = 0; i < n_bins; ++i)

@@ -20,6 +20,10 @@ struct ErrmodTables {
     std::vector<double> het_term() const;
 };
 
+// Poisson(lambda) CDF as 2^64 fixed-point thresholds: n = smallest k with u < cdf[k] for a 64-bit
+// uniform u.  At most max_n entries; the last entry is 2^64-1.  (native count-level sampler)
+std::vector<unsigned long long> poisson_cdf_u64(double lambda, int max_n);
+
 // qScore_to_log10_gl[3][257] (shared.cpp:110-114)
 extern const double kLutLog10Gl[3][257];
 

@@ -73,11 +73,18 @@ struct DevParams {
     CellTail* celltail;
     vgl_site_out* sites;
     int64_t* totals; // [2] used G / R elements
+    uint64_t* pairmap; // [n_sites] base-pair -> genotype-slot map (GL model 1), written by k_site
     float* gl;
     int32_t* pl;
     float* gp;
     int32_t *ad, *adf, *adr;
     int32_t* status;
+    // fused tile kernel (native, GL model 1 fixed qs, count-level sampler)
+    const unsigned long long* pois_cdf; // [pois_n] Poisson CDF, 2^64 fixed point
+    int32_t pois_n;
+    int32_t sites_per_tile, n_tiles;
+    unsigned long long* tile_state;     // [n_tiles] decoupled look-back words
+    uint32_t* ticket;                   // dynamic tile counter
     // replay
     int32_t replay;
     const int32_t* rp_depths;
@@ -93,6 +100,7 @@ void launch_sim(const DevParams& p, cudaStream_t st);
 void launch_site(const DevParams& p, cudaStream_t st);
 void launch_scan(const DevParams& p, cudaStream_t st);
 void launch_emit(const DevParams& p, cudaStream_t st);
+void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms);
 void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
                   uint8_t* adjqs, uint8_t* tails, double* eprob);
 
