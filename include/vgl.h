@@ -219,6 +219,11 @@ int64_t vgl_launch_count(const vgl_ctx* ctx);
 /* algorithmic bytes of a finished batch as defined in DESIGN.md / SURVEY.md 8(d) */
 int64_t vgl_algorithmic_bytes(const vgl_batch_out* out, uint32_t tag_mask);
 
+/* Exhaustive on-device check (all 2^32 float bit patterns) that the kernels' arithmetic shortcuts --
+ * the 3-instruction /10 and the branch-free lroundf -- equal the reference's expressions
+ * (gl_methods.cpp:343, vcfgl.cpp:931).  *n_mismatch must come back 0. */
+int vgl_selftest(int device_id, int64_t* n_mismatch, uint32_t* first_mismatch_bits);
+
 const char* vgl_strerror(int status);
 const char* vgl_last_error(const vgl_ctx* ctx);
 int vgl_abi_version(void);

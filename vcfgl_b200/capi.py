@@ -24,7 +24,7 @@ F32_MISSING_BITS = 0x7F800001
 I32_MISSING = -(2 ** 31)
 
 EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
-           "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
+           "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
            "vgl_last_error", "vgl_abi_version"]
 
 
@@ -105,6 +105,7 @@ def load():
     L.vgl_slot_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
     L.vgl_copy_sites.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.vgl_native_draws.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.POINTER(VglDraws)]
+    L.vgl_selftest.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
     L.vgl_launch_count.argtypes = [C.c_void_p]
     L.vgl_launch_count.restype = C.c_int64
     L.vgl_algorithmic_bytes.argtypes = [C.POINTER(VglBatchOut), C.c_uint32]

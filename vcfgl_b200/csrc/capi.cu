@@ -71,7 +71,7 @@ struct vgl_ctx {
     uint8_t bin_lut[256];
     int bin_max = -1;
     // device tables
-    int use_fused = 0, n_sms = 148;
+    int use_fused = 0, n_sms = 148, fast_div = 0;
     unsigned long long* d_pois = nullptr;
     int pois_n = 0;
     double *d_lut = nullptr, *d_m1_bsum = nullptr, *d_m1_het = nullptr, *d_fk = nullptr, *d_beta = nullptr, *d_depth_means = nullptr;
@@ -235,10 +235,13 @@ static int create_impl(vgl_ctx* ctx)
     if (p.gl_model == 1) {
         ErrmodTables em;
         em.build(1.0 - p.gl1_theta); // io.cpp:1276
-        CK(upload(&ctx->d_m1_het, em.het_term()));
+        const std::vector<double> het = em.het_term();
+        CK(upload(&ctx->d_m1_het, het));
         if (ctx->gl_mode == GL_M1_FIXED) {
             const int q = (p.adjust_qs & 1) ? ctx->pre.adj_qs : ctx->pre.qs; // gl_methods.cpp:318
-            CK(upload(&ctx->d_m1_bsum, em.fixed_q_bsum(q)));
+            const std::vector<double> bsum = em.fixed_q_bsum(q);
+            ctx->fast_div = ErrmodTables::scores_safe_for_fast_div(bsum, het) ? 1 : 0;
+            CK(upload(&ctx->d_m1_bsum, bsum));
         } else {
             CK(upload(&ctx->d_fk, em.fk));
             CK(upload(&ctx->d_beta, em.beta));
@@ -408,6 +411,7 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.sample_strand = ctx->sample_strand;
     p.need_cellq = ctx->need_cellq;
     p.need_tail = ctx->need_tail;
+    p.fast_div = ctx->fast_div;
     p.lut_log10 = ctx->d_lut;
     p.m1_bsum = ctx->d_m1_bsum;
     p.m1_het = ctx->d_m1_het;
@@ -631,6 +635,20 @@ extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, i
     out->adj_qs = prm.error_qs == 2 && prm.adjust_qs ? s.dr_adjqs.data() : nullptr;
     out->tail_dists = s.dr_tails.data();
     out->error_probs = prm.error_qs == 2 ? s.dr_eprob.data() : nullptr;
+    return VGL_OK;
+}
+
+extern "C" int vgl_selftest(int device_id, int64_t* n_mismatch, uint32_t* first_mismatch_bits)
+{
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return VGL_ENODEV;
+    if (device_id < 0 || device_id >= n_dev || !n_mismatch) return VGL_EINVAL;
+    if (cudaSetDevice(device_id) != cudaSuccess) return VGL_ECUDA;
+    unsigned long long bad = 0;
+    unsigned int first = 0;
+    if (run_selftest(&bad, &first) != 0) return VGL_ECUDA;
+    *n_mismatch = (int64_t)bad;
+    if (first_mismatch_bits) *first_mismatch_bits = first;
     return VGL_OK;
 }
 

@@ -70,6 +70,7 @@ struct CountsParams {
     double depth_mean;
     const double* depth_means;
     const unsigned long long* pois_cdf; // shared memory
+    const unsigned short* pois_guide;    // shared memory: [256] lower bound of the answer by the top byte of u
     int pois_n;
     int sample_strand;
     float l2_1me_fast;  // log2(1-e) when e <= 0.5 and p0 does not underflow in float (fast path), else 0
@@ -90,7 +91,10 @@ __device__ __forceinline__ CellCounts sample_counts(const CountsParams& cp, int6
     st.block = 1;
     int n;
     if (cp.depth_mode == VGL_DEPTH_POISSON) {
-        n = cdf_search(cp.pois_cdf, cp.pois_n, ((unsigned long long)w.x << 32) | w.y);
+        // guided inversion: the top byte of u gives a lower bound, then a short linear walk (exact to 2^-64)
+        const unsigned long long u = ((unsigned long long)w.x << 32) | w.y;
+        n = cp.pois_guide[w.x >> 24];
+        while (n < cp.pois_n - 1 && u >= cp.pois_cdf[n]) ++n;
     } else if (cp.depth_mode == VGL_DEPTH_FIXED) {
         n = (int)cp.depth_mean;
     } else {

@@ -15,6 +15,9 @@
 #include "counts_sampler.cuh"
 #include "m1f.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace vgl {
 
 #define FUSED_BLOCK 256
@@ -49,30 +52,38 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 #define TS_G(w) ((long long)(((w) >> 31) & 0x7FFFFFFFull))
 #define TS_R(w) ((long long)((w)&0x7FFFFFFFull))
 
+// CTA-wide copy of a staged span to global memory.  stage[i] holds plane element (base + i), base % 4 == 0;
+// only elements in [lo, hi) belong to this chunk.  32-bit relative indices keep the loop short.
 __device__ __forceinline__ void store_span_f(uint32_t* __restrict__ plane, const uint32_t* stage, int64_t base, int64_t lo, int64_t hi)
 {
-    const int n_chunks = (int)((hi - base + 3) >> 2);
+    uint32_t* __restrict__ dst = plane + base;
+    const int rlo = (int)(lo - base), rhi = (int)(hi - base);
+    const int n_chunks = (rhi + 3) >> 2;
     for (int ch = threadIdx.x; ch < n_chunks; ch += FUSED_BLOCK) {
-        const int64_t e = base + 4ll * ch;
-        const uint4 v = *reinterpret_cast<const uint4*>(stage + 4 * ch);
-        if (e >= lo && e + 4 <= hi) {
-            __stcs(reinterpret_cast<uint4*>(plane + e), v); // streaming 128-bit store
+        const int e = 4 * ch;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + e);
+        if (e >= rlo && e + 4 <= rhi) {
+            __stcs(reinterpret_cast<uint4*>(dst + e), v); // streaming 128-bit store
         } else {
-            if (e + 0 >= lo && e + 0 < hi) plane[e + 0] = v.x;
-            if (e + 1 >= lo && e + 1 < hi) plane[e + 1] = v.y;
-            if (e + 2 >= lo && e + 2 < hi) plane[e + 2] = v.z;
-            if (e + 3 >= lo && e + 3 < hi) plane[e + 3] = v.w;
+            if (e + 0 >= rlo && e + 0 < rhi) dst[e + 0] = v.x;
+            if (e + 1 >= rlo && e + 1 < rhi) dst[e + 1] = v.y;
+            if (e + 2 >= rlo && e + 2 < rhi) dst[e + 2] = v.z;
+            if (e + 3 >= rlo && e + 3 < rhi) dst[e + 3] = v.w;
         }
     }
 }
 
-__global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_constant__ DevParams p)
+__global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_constant__ DevParams p)
 {
     __shared__ __align__(16) uint32_t stage_a[FUSED_STAGE];
     __shared__ __align__(16) uint32_t stage_b[FUSED_STAGE];
     __shared__ TileSite st[FUSED_MAX_SITES];
     __shared__ int tot[FUSED_MAX_SITES][9]; // dp, ad[4], fwd[4]
-    extern __shared__ unsigned long long pois[]; // [pois_n] Poisson CDF (dynamic)
+    extern __shared__ unsigned long long dyn_smem[];
+    unsigned long long* pois = dyn_smem;                                  // [pois_n] Poisson CDF
+    unsigned long long* cnt_sm = dyn_smem + ((p.pois_n + 15) & ~15);     // [1024] per-cell AD counts of the tile
+    unsigned long long* fwd_sm = cnt_sm + FUSED_TILE_CELLS;              // [1024] forward counts (strand runs only)
+    unsigned short* guide = reinterpret_cast<unsigned short*>(p.sample_strand ? fwd_sm + FUSED_TILE_CELLS : fwd_sm); // [256]
     __shared__ int64_t span[4];
     __shared__ int64_t s_base[2];
     __shared__ int s_tile;
@@ -80,6 +91,13 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
     const int tid = threadIdx.x, lane = tid & 31;
     const int S = p.S, T = p.sites_per_tile;
     for (int i = tid; i < p.pois_n; i += FUSED_BLOCK) pois[i] = p.pois_cdf[i];
+    __syncthreads();
+    if (p.pois_n > 0) { // guide[j] = smallest k whose CDF exceeds every u with top byte j-1, i.e. a lower bound for top byte j
+        int k = 0;
+        const unsigned long long floor_u = (unsigned long long)tid << 56;
+        while (k < p.pois_n - 1 && pois[k] <= floor_u) ++k;
+        guide[tid] = (unsigned short)k;
+    }
     CountsParams cp;
     cp.key.k0 = p.k0;
     cp.key.k1 = p.k1;
@@ -87,6 +105,7 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
     cp.depth_mean = p.depth_mean;
     cp.depth_means = p.depth_means;
     cp.pois_cdf = pois;
+    cp.pois_guide = guide;
     cp.pois_n = p.pois_n;
     cp.sample_strand = p.sample_strand;
     // i / S for i < 1024 when a tile holds several sites (exact for S < 1024)
@@ -104,6 +123,7 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
         const int nsl = min(T, p.n_sites - site0);
         const int ncell = nsl * S;
         const int64_t cell0 = (int64_t)site0 * S;
+        const bool keep_counts = ncell <= FUSED_TILE_CELLS; // tile fits the shared-memory count cache
 
         // ---------------- phase 0: per-site constants
         for (int i = tid; i < nsl * 9; i += FUSED_BLOCK) (&tot[0][0])[i] = 0;
@@ -132,6 +152,10 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
                 const uint8_t gt = p.gt[cell0 + i];
                 cc = sample_counts(cp, p.first_site + site0 + sl, (uint32_t)sample, gt, st[sl].e, st[sl].l2, st[sl].er);
                 p.dp[cell0 + i] = cc.n;
+                if (keep_counts) {
+                    cnt_sm[i] = cc.ad;
+                    if (p.sample_strand) fwd_sm[i] = cc.fwd;
+                }
             } else {
                 sl = -1;
             }
@@ -163,11 +187,11 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
         __syncthreads();
 
         // ---------------- phase 2: per-site record (vcfgl.cpp:396-404, 665-782, 806-843 INFO part)
-        int64_t my_g = 0, my_r = 0;
-        vgl_site_out o;
+        int my_g = 0, my_r = 0; // this site's block sizes in 4-byte elements (padded to 16 B)
         if (tid < nsl) {
             const int* t = tot[tid];
             const int dp = t[0];
+            vgl_site_out o;
             o.skip_code = 0;
             o.n_alleles = o.n_alleles_observed = o.n_genotypes = 0;
 #pragma unroll
@@ -178,6 +202,7 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
 #pragma unroll
             for (int i = 0; i < 16; ++i) o.i16[i] = 0.0f;
             o._pad = 0;
+            o.g_off = o.r_off = 0; // patched after the look-back
             int b2a[5] = {-1, -1, -1, -1, -1};
             uint32_t a2b = 0xFFFFFFFFu;
             if (dp == 0) {
@@ -235,38 +260,43 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
             st[tid].a2b = a2b;
             st[tid].pairmap = make_pairmap(b2a);
             if (o.skip_code == 0) {
-                my_g = (((int64_t)S * o.n_genotypes) + 3) & ~3ll;
-                my_r = (((int64_t)S * o.n_alleles) + 3) & ~3ll;
+                my_g = (S * o.n_genotypes + 3) & ~3;
+                my_r = (S * o.n_alleles + 3) & ~3;
             }
+            p.sites[site0 + tid] = o;
         }
-        // exclusive scan of the tile's block sizes (nsl <= 128: warps 0..3, then 4 partials)
-        {
-            int64_t ig = my_g, ir = my_r;
+        // exclusive scan of the tile's block sizes: at most 128 sites -> warps 0..3
+        int* wsum = reinterpret_cast<int*>(stage_a); // [4][2] scratch
+        int ig = my_g, ir = my_r;
+        if (tid < FUSED_MAX_SITES) {
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                const int64_t tg = __shfl_up_sync(0xffffffffu, ig, off);
-                const int64_t tr = __shfl_up_sync(0xffffffffu, ir, off);
+                const int tg = __shfl_up_sync(0xffffffffu, ig, off);
+                const int tr = __shfl_up_sync(0xffffffffu, ir, off);
                 if (lane >= off) { ig += tg; ir += tr; }
             }
-            int64_t* wsum = reinterpret_cast<int64_t*>(stage_a); // [8][2] scratch
             if (lane == 31) { wsum[2 * (tid >> 5)] = ig; wsum[2 * (tid >> 5) + 1] = ir; }
-            __syncthreads();
-            int64_t pre_g = 0, pre_r = 0, tile_g = 0, tile_r = 0;
+        }
+        __syncthreads();
+        int ex_g = 0, ex_r = 0;
+        if (tid < FUSED_MAX_SITES) {
+            int pre_g = 0, pre_r = 0, tile_g = 0, tile_r = 0;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) { // only the first 128 threads carry sites
+            for (int w = 0; w < 4; ++w) {
                 if (w < (tid >> 5)) { pre_g += wsum[2 * w]; pre_r += wsum[2 * w + 1]; }
                 tile_g += wsum[2 * w];
                 tile_r += wsum[2 * w + 1];
             }
-            const int64_t ex_g = pre_g + ig - my_g, ex_r = pre_r + ir - my_r;
-            // decoupled look-back (warp 0): base offset of this tile = sum of all earlier tiles
+            ex_g = pre_g + ig - my_g;
+            ex_r = pre_r + ir - my_r;
+            // decoupled look-back (warp 0): base offset of this tile = total size of all earlier tiles
             if (tid < 32) {
                 if (lane == 0) st_state(p.tile_state + tile, TS_PACK(1, tile_g, tile_r));
                 int64_t bg = 0, br = 0;
                 int look = tile - 1;
                 while (look >= 0) {
                     const int idx = look - lane;
-                    unsigned long long w = TS_PACK(2, 0, 0); // lanes before tile 0 behave as a zero inclusive prefix
+                    unsigned long long w = TS_PACK(2, 0, 0); // lanes before tile 0 act as a zero inclusive prefix
                     if (idx >= 0) {
                         do { w = ld_state(p.tile_state + idx); } while (TS_FLAG(w) == 0);
                     }
@@ -290,14 +320,14 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
                     if (tile == p.n_tiles - 1) { p.totals[0] = bg + tile_g; p.totals[1] = br + tile_r; }
                 }
             }
-            __syncthreads();
-            if (tid < nsl) {
-                o.g_off = s_base[0] + ex_g;
-                o.r_off = s_base[1] + ex_r;
-                st[tid].g_off = o.g_off;
-                st[tid].r_off = o.r_off;
-                p.sites[site0 + tid] = o;
-            }
+        }
+        __syncthreads();
+        if (tid < nsl) {
+            const int64_t go = s_base[0] + ex_g, ro = s_base[1] + ex_r;
+            st[tid].g_off = go;
+            st[tid].r_off = ro;
+            p.sites[site0 + tid].g_off = go;
+            p.sites[site0 + tid].r_off = ro;
         }
         __syncthreads();
 
@@ -335,7 +365,13 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
             cc.n = 0; cc.ad = cc.fwd = 0;
             if (live && !ts.skip) {
                 const int64_t site = p.first_site + site0 + sl;
-                cc = sample_counts(cp, site, (uint32_t)sample, p.gt[cell0 + i], ts.e, ts.l2, ts.er);
+                if (keep_counts) {
+                    cc.ad = cnt_sm[i];
+                    cc.fwd = p.sample_strand ? fwd_sm[i] : 0ull;
+                    cc.n = (int)((cc.ad & 0xFFFF) + ((cc.ad >> 16) & 0xFFFF) + ((cc.ad >> 32) & 0xFFFF) + (cc.ad >> 48));
+                } else { // big sites: sample again (counter-based RNG: identical draws, nothing stored)
+                    cc = sample_counts(cp, site, (uint32_t)sample, p.gt[cell0 + i], ts.e, ts.l2, ts.er);
+                }
                 if (cc.n == 0) { // gl_methods.cpp:359-366
                     for (int g = 0; g < G; ++g) { my_gl[g] = f32_missing(); my_pl[g] = VGL_I32_MISSING; }
                 } else {
@@ -348,7 +384,7 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
                     float mx = -CUDART_INF_F;
 #pragma unroll
                     for (int k = 0; k < 15; ++k) {
-                        q[k] = neg_div10(q[k]);
+                        q[k] = neg_div10(q[k], p.fast_div != 0);
                         if (((ts.pairmap >> (4 * k)) & 0xF) != 0xF) mx = fmaxf(mx, q[k]);
                     }
 #pragma unroll
@@ -416,11 +452,72 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 3) k_fused_m1f(const __grid_const
     }
 }
 
+// exhaustive device self-test of the arithmetic shortcuts (all 2^32 float bit patterns)
+// diagnostic: range of q >= 0 where the UNGUARDED 3-instruction division differs from __fdiv_rn
+__global__ void k_div10_range(unsigned int* lo_hi)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= 0x7F800000ull; i += stride) {
+        const float x = __uint_as_float((unsigned int)i);
+        if (__float_as_uint(neg_div10_fast(x)) != __float_as_uint(neg_div10_ref(x))) {
+            atomicMin(lo_hi, (unsigned int)i);
+            atomicMax(lo_hi + 1, (unsigned int)i);
+            atomicAdd(lo_hi + 2, 1u);
+            if (i >= 0x0D800000u && i < 0x7F800000u) atomicAdd(lo_hi + 3, 1u); // mismatches among q >= 2^-100, finite
+        }
+    }
+}
+
+__global__ void k_selftest(unsigned long long* bad, unsigned int* first_bad)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+        const float x = __uint_as_float((unsigned int)i);
+        bool ok = true;
+        if ((unsigned int)i == 0u || (x >= 7.888609052210118e-31f && x < CUDART_INF_F)) { // +0 or finite >= 2^-100
+            ok = __float_as_uint(neg_div10_fast(x)) == __float_as_uint(neg_div10_ref(x));
+        }
+        if (x <= 0.0f || __float_as_uint(x) == 0x80000000u) { // a rescaled GL is <= 0 (or -0)
+            ok = ok && (pl_from_gl(x) == pl_from_gl_ref(x));
+        }
+        if (!ok) {
+            atomicAdd(bad, 1ull);
+            atomicMin(first_bad, (unsigned int)i);
+        }
+    }
+}
+
+int run_selftest(unsigned long long* n_bad, unsigned int* first_bad)
+{
+    unsigned long long* d_bad = nullptr;
+    unsigned int* d_first = nullptr;
+    if (cudaMalloc((void**)&d_bad, 8) != cudaSuccess || cudaMalloc((void**)&d_first, 4) != cudaSuccess) return -1;
+    cudaMemset(d_bad, 0, 8);
+    cudaMemset(d_first, 0xFF, 4);
+    k_selftest<<<148 * 8, 256>>>(d_bad, d_first);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (getenv("VGL_SELFTEST_VERBOSE")) {
+        unsigned int* d_r = nullptr;
+        unsigned int h[4] = {0xFFFFFFFFu, 0, 0, 0};
+        cudaMalloc((void**)&d_r, 16);
+        cudaMemcpy(d_r, h, 16, cudaMemcpyHostToDevice);
+        k_div10_range<<<148 * 8, 256>>>(d_r);
+        cudaMemcpy(h, d_r, 16, cudaMemcpyDeviceToHost);
+        cudaFree(d_r);
+        fprintf(stderr, "[vgl selftest] unguarded div10: %u mismatches, bits 0x%08x..0x%08x, %u with q in [2^-100, inf)\n", h[2], h[0], h[1], h[3]);
+    }
+    cudaMemcpy(n_bad, d_bad, 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(first_bad, d_first, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    cudaFree(d_first);
+    return e == cudaSuccess ? 0 : -1;
+}
+
 void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms)
 {
     int per_sm = 1;
-    const size_t dyn = (size_t)(p.pois_n > 0 ? p.pois_n : 1) * sizeof(unsigned long long);
-    cudaFuncSetAttribute(k_fused_m1f, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_POIS_MAX * 8);
+    const size_t dyn = (size_t)(((p.pois_n + 15) & ~15) + FUSED_TILE_CELLS * (p.sample_strand ? 2 : 1)) * 8 + 512;
+    cudaFuncSetAttribute(k_fused_m1f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FUSED_POIS_MAX + 2 * FUSED_TILE_CELLS) * 8 + 512));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_m1f, FUSED_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     int grid = n_sms * per_sm;

@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(VGL_BLOCK) k_emit(const __grid_constant__ DevP
                 float mx = -CUDART_INF_F;
 #pragma unroll
                 for (int k = 0; k < 15; ++k) {
-                    q[k] = neg_div10(q[k]); // gl_methods.cpp:343
+                    q[k] = neg_div10(q[k], p.fast_div != 0); // gl_methods.cpp:343
                     if (((pairmap >> (4 * k)) & 0xF) != 0xF) mx = fmaxf(mx, q[k]);
                 }
 #pragma unroll

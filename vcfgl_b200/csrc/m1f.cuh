@@ -35,10 +35,30 @@ __device__ __forceinline__ float acc_add(float acc, double b) { return __double2
 // (float)((-1.0 * (double)q) / 10.0), gl_methods.cpp:343.  One correctly rounded float division gives
 // the same float: q/10 is never closer than 0.1 ulp to a float rounding boundary, so the double
 // intermediate cannot change the result.
-__device__ __forceinline__ float neg_div10(float q) { return -__fdiv_rn(q, 10.0f); }
+__device__ __forceinline__ float neg_div10_ref(float q) { return -__fdiv_rn(q, 10.0f); }
+
+// The same value in three instructions: y = q*RN(0.1); r = fma(-10, y, q) (exact residual);
+// y' = fma(r, RN(0.1), y).  vgl_selftest() checks it against __fdiv_rn for +0 and EVERY finite float
+// >= 2^-100 (tests/test_gpu_selftest.py; it is wrong only for tinier values, -0 and +inf).  The
+// host proves at table-build time that no score below 2^-100 other than +0 can occur
+// (ErrmodTables::scores_safe_for_fast_div) and passes that as `fast`.
+__device__ __forceinline__ float neg_div10_fast(float q)
+{
+    const float y = __fmul_rn(q, 0.1f);
+    const float r = __fmaf_rn(-10.0f, y, q);
+    return -__fmaf_rn(r, 0.1f, y);
+}
+__device__ __forceinline__ float neg_div10(float q, bool fast) { return fast ? neg_div10_fast(q) : neg_div10_ref(q); }
 
 // lroundf((float)(-10.0 * (double)gl)) capped at 255 (vcfgl.cpp:931-934) for gl <= 0: the double
 // product is exact so one float multiply rounds identically; round-half-away via trunc + fraction.
+__device__ __forceinline__ int pl_from_gl_ref(float gl) // the reference's expression, for the self-test
+{
+    if (gl == -CUDART_INF_F) return 255;
+    const long x = lroundf(__double2float_rn(__dmul_rn(-10.0, (double)gl)));
+    return x > 255 ? 255 : (int)x;
+}
+
 __device__ __forceinline__ int pl_from_gl(float gl)
 {
     const float x = fminf(__fmul_rn(-10.0f, gl), 300.0f);
@@ -89,7 +109,7 @@ __device__ __forceinline__ void m1f_store_gl(const float (&q)[15], uint64_t pair
 #pragma unroll
     for (int i = 0; i < 15; ++i) {
         const int slot = (int)((pairmap >> (4 * i)) & 0xF);
-        const float v = neg_div10(q[i]);
+        const float v = neg_div10_ref(q[i]);
         if (slot != 0xF) {
             my_gl[slot] = v;
             mx = fmaxf(mx, v);

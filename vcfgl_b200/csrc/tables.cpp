@@ -96,6 +96,17 @@ std::vector<unsigned long long> poisson_cdf_u64(double lambda, int max_n)
     return t;
 }
 
+bool ErrmodTables::scores_safe_for_fast_div(const std::vector<double>& bsum, const std::vector<double>& het)
+{
+    const double lo = ldexp(1.0, -100), hi = ldexp(1.0, 100);
+    for (const std::vector<double>* t : {&bsum, &het})
+        for (double v : *t) {
+            if (!(v >= 0.0) || v > hi) return false;        // negative, NaN or huge
+            if (v != 0.0 && v < lo) return false;           // positive but tiny
+        }
+    return true;
+}
+
 static int bin_lookup(int n_bins, const uint8_t bins[][3], int qs)
 {
     for (int i = 0; i < n_bins; ++i)

@@ -18,6 +18,9 @@ struct ErrmodTables {
     std::vector<double> fixed_q_bsum(int q) const;
     // -4.343 * lhet[n<<8 | k]  (errmod.c:200)
     std::vector<double> het_term() const;
+    // true when every errmod score (a float sum of non-negative table terms) is +0 or >= 2^-100 and
+    // finite: each positive term of both tables is itself >= 2^-100, and all are finite and >= 0
+    static bool scores_safe_for_fast_div(const std::vector<double>& bsum, const std::vector<double>& het);
 };
 
 // Poisson(lambda) CDF as 2^64 fixed-point thresholds: n = smallest k with u < cdf[k] for a 64-bit

@@ -59,6 +59,7 @@ struct DevParams {
     double homT, het, homF;     // GL_M2_FIXED constants
     int32_t sample_strand;      // shared.h:160 PROGRAM_WILL_SAMPLE_STRAND
     int32_t need_cellq, need_tail;
+    int32_t fast_div;           // table-derived proof that the 3-instruction /10 is exact for every score
     // tables
     const double* lut_log10;  // [3*257]
     const double* m1_bsum;    // [256*256] fixed-qs running sums
@@ -100,6 +101,7 @@ void launch_sim(const DevParams& p, cudaStream_t st);
 void launch_site(const DevParams& p, cudaStream_t st);
 void launch_scan(const DevParams& p, cudaStream_t st);
 void launch_emit(const DevParams& p, cudaStream_t st);
+int run_selftest(unsigned long long* n_bad, unsigned int* first_bad);
 void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms);
 void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
                   uint8_t* adjqs, uint8_t* tails, double* eprob);
