@@ -24,7 +24,8 @@ namespace vgl {
 #define FUSED_TILE_CELLS 1024
 #define FUSED_MAX_SITES 128
 #define FUSED_POIS_MAX 1024
-#define FUSED_STAGE (FUSED_BLOCK * 16 + 8)
+#define WARP_STAGE (32 * 16 + 8) // 4-byte elements per warp slice: 32 cells x (15 values padded to 16) + alignment slack
+#define FUSED_STAGE (8 * WARP_STAGE)
 
 struct TileSite {
     uint64_t pairmap;
@@ -52,24 +53,31 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 #define TS_G(w) ((long long)(((w) >> 31) & 0x7FFFFFFFull))
 #define TS_R(w) ((long long)((w)&0x7FFFFFFFull))
 
-// CTA-wide copy of a staged span to global memory.  stage[i] holds plane element (base + i), base % 4 == 0;
-// only elements in [lo, hi) belong to this chunk.  32-bit relative indices keep the loop short.
-__device__ __forceinline__ void store_span_f(uint32_t* __restrict__ plane, const uint32_t* stage, int64_t base, int64_t lo, int64_t hi)
+// Warp-wide copy of a staged span to global memory.  stage[i] holds plane element (base + i), base % 4 == 0;
+// only elements in [lo, hi) belong to this warp.  Complete 16-byte chunks go out as 128-bit streaming
+// stores without any bounds logic; the (at most 3 + 3) edge elements are written by six lanes.
+__device__ __forceinline__ void store_span_w(uint32_t* __restrict__ plane, const uint32_t* stage, int64_t base, int64_t lo,
+                                             int64_t hi, int lane)
 {
     uint32_t* __restrict__ dst = plane + base;
     const int rlo = (int)(lo - base), rhi = (int)(hi - base);
-    const int n_chunks = (rhi + 3) >> 2;
-    for (int ch = threadIdx.x; ch < n_chunks; ch += FUSED_BLOCK) {
-        const int e = 4 * ch;
-        const uint4 v = *reinterpret_cast<const uint4*>(stage + e);
-        if (e >= rlo && e + 4 <= rhi) {
-            __stcs(reinterpret_cast<uint4*>(dst + e), v); // streaming 128-bit store
-        } else {
-            if (e + 0 >= rlo && e + 0 < rhi) dst[e + 0] = v.x;
-            if (e + 1 >= rlo && e + 1 < rhi) dst[e + 1] = v.y;
-            if (e + 2 >= rlo && e + 2 < rhi) dst[e + 2] = v.z;
-            if (e + 3 >= rlo && e + 3 < rhi) dst[e + 3] = v.w;
-        }
+    const int first_full = (rlo + 3) >> 2, last_full = rhi >> 2;
+    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    // a warp slice holds at most WARP_STAGE / 4 = 130 chunks -> at most 5 per lane; fixed trip count, predicated
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int ch = first_full + lane + 32 * k;
+        if (ch < last_full) __stcs(d4 + ch, s4[ch]);
+    }
+    const int head_end = min(first_full * 4, rhi);       // [rlo, head_end): before the first complete chunk
+    const int tail_beg = max(last_full * 4, head_end);   // [tail_beg, rhi): after the last complete chunk
+    if (lane < 4) {
+        const int e = rlo + lane;
+        if (e < head_end) dst[e] = stage[e];
+    } else if (lane < 8) {
+        const int e = tail_beg + lane - 4;
+        if (e < rhi) dst[e] = stage[e];
     }
 }
 
@@ -84,7 +92,6 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_const
     unsigned long long* cnt_sm = dyn_smem + ((p.pois_n + 15) & ~15);     // [1024] per-cell AD counts of the tile
     unsigned long long* fwd_sm = cnt_sm + FUSED_TILE_CELLS;              // [1024] forward counts (strand runs only)
     unsigned short* guide = reinterpret_cast<unsigned short*>(p.sample_strand ? fwd_sm + FUSED_TILE_CELLS : fwd_sm); // [256]
-    __shared__ int64_t span[4];
     __shared__ int64_t s_base[2];
     __shared__ int s_tile;
 
@@ -159,9 +166,10 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_const
             } else {
                 sl = -1;
             }
-            // warp-aggregated reduction into the site totals
+            // warp-aggregated reduction into the site totals: a warp of 32 consecutive cells spans at most
+            // two sites when S >= 32 -> two masked REDUX rounds; otherwise per-thread shared atomics
             const int first = __shfl_sync(0xffffffffu, sl, 0);
-            const bool uniform = __all_sync(0xffffffffu, sl == first || sl < 0);
+            const bool two = __all_sync(0xffffffffu, sl < 0 || sl == first || sl == first + 1);
             int v[9];
             v[0] = cc.n;
 #pragma unroll
@@ -169,13 +177,18 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_const
                 v[1 + b] = (int)((cc.ad >> (16 * b)) & 0xFFFF);
                 v[5 + b] = (int)((cc.fwd >> (16 * b)) & 0xFFFF);
             }
-            if (uniform) {
+            if (two) {
                 if (first >= 0) {
+                    const bool any_second = __any_sync(0xffffffffu, sl == first + 1);
 #pragma unroll
                     for (int k = 0; k < 9; ++k) {
                         if (k >= 5 && !p.sample_strand) break;
-                        const int s = __reduce_add_sync(0xffffffffu, v[k]);
-                        if (lane == 0 && s) atomicAdd(&tot[first][k], s);
+                        const int s0 = __reduce_add_sync(0xffffffffu, sl == first ? v[k] : 0);
+                        if (lane == 0 && s0) atomicAdd(&tot[first][k], s0);
+                        if (any_second) {
+                            const int s1 = __reduce_add_sync(0xffffffffu, sl == first + 1 ? v[k] : 0);
+                            if (lane == 0 && s1) atomicAdd(&tot[first + 1][k], s1);
+                        }
                     }
                 }
             } else if (live) {
@@ -331,7 +344,10 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_const
         }
         __syncthreads();
 
-        // ---------------- phase 3: re-sample, score, emit (chunks of 256 cells)
+        // ---------------- phase 3: score + emit.  Each WARP stages the contiguous output span of its 32
+        // cells in its own shared-memory slice and copies it out itself: no CTA barriers in this phase.
+        uint32_t* const wa = stage_a + (tid >> 5) * WARP_STAGE; // GL, later AD / ADR
+        uint32_t* const wb = stage_b + (tid >> 5) * WARP_STAGE; // PL, later GP, ADF
         for (int i0 = 0; i0 < ncell; i0 += FUSED_BLOCK) {
             const int i = i0 + tid;
             const bool live = i < ncell;
@@ -342,28 +358,24 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_const
             }
             const TileSite& ts = st[sl];
             const int A = ts.A, G = ts.G;
+            const bool act = live && !ts.skip;
+            const bool pad_owner = act && sample == S - 1;
+            const int g_pad = pad_owner ? ((S * G + 3) & ~3) - S * G : 0;
+            const int r_pad = pad_owner ? ((S * A + 3) & ~3) - S * A : 0;
             int64_t gpos = ts.g_off + (int64_t)sample * G, rpos = ts.r_off + (int64_t)sample * A;
             if (!live && !ts.skip) { // end of the last site's padded block
-                gpos = ts.g_off + ((((int64_t)S * G) + 3) & ~3ll);
-                rpos = ts.r_off + ((((int64_t)S * A) + 3) & ~3ll);
+                gpos = ts.g_off + ((S * G + 3) & ~3);
+                rpos = ts.r_off + ((S * A + 3) & ~3);
             }
-            const bool pad_owner = live && !ts.skip && sample == S - 1;
-            if (tid == 0) { span[0] = gpos; span[2] = rpos; }
-            if (tid == FUSED_BLOCK - 1) {
-                int64_t ge = gpos + (live ? G : 0), re = rpos + (live ? A : 0);
-                if (pad_owner) { ge = (ge + 3) & ~3ll; re = (re + 3) & ~3ll; }
-                span[1] = ge; span[3] = re;
-            }
-            __syncthreads();
-            const int64_t g_lo = span[0], g_hi = span[1], r_lo = span[2], r_hi = span[3];
+            // the warp's span: first lane's start .. last lane's end (positions are monotone in the cell index)
+            const int64_t g_lo = __shfl_sync(0xffffffffu, gpos, 0), r_lo = __shfl_sync(0xffffffffu, rpos, 0);
+            const int64_t g_hi = __shfl_sync(0xffffffffu, gpos + (live ? G + g_pad : 0), 31);
+            const int64_t r_hi = __shfl_sync(0xffffffffu, rpos + (live ? A + r_pad : 0), 31);
             const int64_t g_base = g_lo & ~3ll, r_base = r_lo & ~3ll;
-            float* my_gl = reinterpret_cast<float*>(stage_a) + (gpos - g_base);
-            int32_t* my_pl = reinterpret_cast<int32_t*>(stage_b) + (gpos - g_base);
-            const int g_pad = pad_owner ? (int)((((int64_t)S * G + 3) & ~3ll) - (int64_t)S * G) : 0;
-            const int r_pad = pad_owner ? (int)((((int64_t)S * A + 3) & ~3ll) - (int64_t)S * A) : 0;
+            const int go = (int)(gpos - g_base), ro = (int)(rpos - r_base); // this cell's offset in the warp slice
             CellCounts cc;
             cc.n = 0; cc.ad = cc.fwd = 0;
-            if (live && !ts.skip) {
+            if (act) {
                 const int64_t site = p.first_site + site0 + sl;
                 if (keep_counts) {
                     cc.ad = cnt_sm[i];
@@ -373,7 +385,8 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_const
                     cc = sample_counts(cp, site, (uint32_t)sample, p.gt[cell0 + i], ts.e, ts.l2, ts.er);
                 }
                 if (cc.n == 0) { // gl_methods.cpp:359-366
-                    for (int g = 0; g < G; ++g) { my_gl[g] = f32_missing(); my_pl[g] = VGL_I32_MISSING; }
+#pragma unroll 1
+                    for (int g = 0; g < G; ++g) { wa[go + g] = VGL_F32_MISSING_BITS; wb[go + g] = (uint32_t)VGL_I32_MISSING; }
                 } else {
                     uint64_t ad = cc.ad;
                     int nn = cc.n;
@@ -381,73 +394,85 @@ __global__ void __launch_bounds__(FUSED_BLOCK, 4) k_fused_m1f(const __grid_const
                     float q[15];
                     m1f_scores(nn, (int)(ad & 0xFFFF), (int)((ad >> 16) & 0xFFFF), (int)((ad >> 32) & 0xFFFF), (int)(ad >> 48),
                                p.m1_bsum, p.m1_het, q);
+                    if (p.fast_div) {
+#pragma unroll
+                        for (int k = 0; k < 15; ++k) q[k] = neg_div10_fast(q[k]); // gl_methods.cpp:343
+                    } else {
+#pragma unroll 1
+                        for (int k = 0; k < 15; ++k) q[k] = neg_div10_ref(q[k]);
+                    }
+                    const uint32_t pm_lo = (uint32_t)ts.pairmap, pm_hi = (uint32_t)(ts.pairmap >> 32);
                     float mx = -CUDART_INF_F;
 #pragma unroll
                     for (int k = 0; k < 15; ++k) {
-                        q[k] = neg_div10(q[k], p.fast_div != 0);
-                        if (((ts.pairmap >> (4 * k)) & 0xF) != 0xF) mx = fmaxf(mx, q[k]);
+                        const uint32_t slot = ((k < 8 ? pm_lo >> (4 * k) : pm_hi >> (4 * (k - 8))) & 0xF);
+                        mx = fmaxf(mx, slot != 0xF ? q[k] : -CUDART_INF_F);
                     }
 #pragma unroll
-                    for (int k = 0; k < 15; ++k) {
-                        const int slot = (int)((ts.pairmap >> (4 * k)) & 0xF);
+                    for (int k = 0; k < 15; ++k) { // gl_methods.cpp:355-357, vcfgl.cpp:907-939
+                        const uint32_t slot = ((k < 8 ? pm_lo >> (4 * k) : pm_hi >> (4 * (k - 8))) & 0xF);
                         if (slot != 0xF) {
                             const float v = __fsub_rn(q[k], mx);
-                            my_gl[slot] = v;
-                            my_pl[slot] = pl_from_gl(v);
+                            wa[go + slot] = __float_as_uint(v);
+                            wb[go + slot] = (uint32_t)pl_from_gl(v);
                         }
                     }
                 }
-                for (int g = 0; g < g_pad; ++g) { my_gl[G + g] = 0.0f; my_pl[G + g] = 0; }
+#pragma unroll 1
+                for (int g = 0; g < g_pad; ++g) { wa[go + G + g] = 0u; wb[go + G + g] = 0u; }
             }
-            __syncthreads();
-            if (p.gl) store_span_f(reinterpret_cast<uint32_t*>(p.gl), stage_a, g_base, g_lo, g_hi);
-            if (p.pl) store_span_f(reinterpret_cast<uint32_t*>(p.pl), stage_b, g_base, g_lo, g_hi);
+            __syncwarp();
+            if (p.gl) store_span_w(reinterpret_cast<uint32_t*>(p.gl), wa, g_base, g_lo, g_hi, lane);
+            if (p.pl) store_span_w(reinterpret_cast<uint32_t*>(p.pl), wb, g_base, g_lo, g_hi, lane);
             if (p.gp) { // vcfgl.cpp:941-970
-                __syncthreads();
-                if (live && !ts.skip) {
-                    float* gp = reinterpret_cast<float*>(my_pl);
+                __syncwarp();
+                if (act) {
                     if (cc.n == 0) {
-                        for (int g = 0; g < G; ++g) gp[g] = f32_missing();
+                        for (int g = 0; g < G; ++g) wb[go + g] = VGL_F32_MISSING_BITS;
                     } else {
                         float sum = 0.0f;
                         for (int g = 0; g < G; ++g) {
-                            const float v = __double2float_rn(exp10((double)my_gl[g]));
-                            gp[g] = v;
+                            const float v = __double2float_rn(exp10((double)__uint_as_float(wa[go + g])));
+                            wb[go + g] = __float_as_uint(v);
                             sum = __fadd_rn(sum, v);
                         }
-                        for (int g = 0; g < G; ++g) gp[g] = __fdiv_rn(gp[g], sum);
+                        for (int g = 0; g < G; ++g) wb[go + g] = __float_as_uint(__fdiv_rn(__uint_as_float(wb[go + g]), sum));
                     }
                 }
-                __syncthreads();
-                store_span_f(reinterpret_cast<uint32_t*>(p.gp), stage_b, g_base, g_lo, g_hi);
+                __syncwarp();
+                store_span_w(reinterpret_cast<uint32_t*>(p.gp), wb, g_base, g_lo, g_hi, lane);
             }
-            __syncthreads();
-            // AD / ADF / ADR in allele order (vcfgl.cpp:806-831): AD -> stage_a, ADF -> stage_b, then ADR -> stage_a
+            // AD / ADF / ADR in allele order (vcfgl.cpp:806-831)
             if (p.ad || p.adf || p.adr) {
-                int32_t* ra = reinterpret_cast<int32_t*>(stage_a) + (rpos - r_base);
-                int32_t* rb = reinterpret_cast<int32_t*>(stage_b) + (rpos - r_base);
-                if (live && !ts.skip) {
-                    for (int a = 0; a < A; ++a) {
-                        const int b = (int)((ts.a2b >> (4 * a)) & 0xF);
-                        const int c = b < 4 ? (int)((cc.ad >> (16 * b)) & 0xFFFF) : 0;
-                        const int f = b < 4 ? (int)((cc.fwd >> (16 * b)) & 0xFFFF) : 0;
-                        ra[a] = c;
-                        rb[a] = f;
+                __syncwarp();
+                if (act) {
+                    const uint32_t a2b = ts.a2b;
+                    const bool want_f = p.adf || p.adr;
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) {
+                        if (a < A) {
+                            const uint32_t b = (a2b >> (4 * a)) & 0xF;
+                            const int sh = (int)(b & 3) * 16;
+                            const uint32_t c = b < 4 ? (uint32_t)(cc.ad >> sh) & 0xFFFFu : 0u;
+                            wa[ro + a] = c;
+                            if (want_f) wb[ro + a] = b < 4 ? (uint32_t)(cc.fwd >> sh) & 0xFFFFu : 0u;
+                        }
                     }
-                    for (int a = 0; a < r_pad; ++a) { ra[A + a] = 0; rb[A + a] = 0; }
+#pragma unroll 1
+                    for (int a = 0; a < r_pad; ++a) { wa[ro + A + a] = 0u; wb[ro + A + a] = 0u; }
                 }
-                __syncthreads();
-                if (p.ad) store_span_f(reinterpret_cast<uint32_t*>(p.ad), stage_a, r_base, r_lo, r_hi);
-                if (p.adf) store_span_f(reinterpret_cast<uint32_t*>(p.adf), stage_b, r_base, r_lo, r_hi);
+                __syncwarp();
+                if (p.ad) store_span_w(reinterpret_cast<uint32_t*>(p.ad), wa, r_base, r_lo, r_hi, lane);
+                if (p.adf) store_span_w(reinterpret_cast<uint32_t*>(p.adf), wb, r_base, r_lo, r_hi, lane);
                 if (p.adr) {
-                    __syncthreads();
-                    if (live && !ts.skip)
-                        for (int a = 0; a < A; ++a) ra[a] = ra[a] - rb[a];
-                    __syncthreads();
-                    store_span_f(reinterpret_cast<uint32_t*>(p.adr), stage_a, r_base, r_lo, r_hi);
+                    __syncwarp();
+                    if (act)
+                        for (int a = 0; a < A; ++a) wa[ro + a] -= wb[ro + a];
+                    __syncwarp();
+                    store_span_w(reinterpret_cast<uint32_t*>(p.adr), wa, r_base, r_lo, r_hi, lane);
                 }
-                __syncthreads();
             }
+            __syncwarp();
         }
     }
 }
@@ -518,6 +543,7 @@ void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms)
     int per_sm = 1;
     const size_t dyn = (size_t)(((p.pois_n + 15) & ~15) + FUSED_TILE_CELLS * (p.sample_strand ? 2 : 1)) * 8 + 512;
     cudaFuncSetAttribute(k_fused_m1f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FUSED_POIS_MAX + 2 * FUSED_TILE_CELLS) * 8 + 512));
+    cudaFuncSetAttribute(k_fused_m1f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_m1f, FUSED_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     int grid = n_sms * per_sm;

@@ -98,7 +98,7 @@ __device__ __forceinline__ void m1f_scores(int n, int c0, int c1, int c2, int c3
     q[13] = VGL_HET(c3, 0, t012);
 #undef VGL_HET
 #pragma unroll
-    for (int i = 0; i < 15; ++i) q[i] = q[i] < 0.0f ? 0.0f : q[i]; // errmod.c:204
+    for (int i = 0; i < 15; ++i) q[i] = fmaxf(q[i], 0.0f); // errmod.c:204 (scores are sums of non-negative terms: never -0 or NaN)
 }
 
 // scatter the base-pair scores into the cell's allele-ordered GL slots (shared memory), rescale to

@@ -86,7 +86,8 @@ std::vector<unsigned long long> poisson_cdf_u64(double lambda, int max_n)
         if (lambda <= 0.0) pmf = k == 0 ? 1.0L : 0.0L;
         else pmf = expl(-(long double)lambda + k * logl((long double)lambda) - lgammal((long double)k + 1.0L));
         cdf += pmf;
-        if (cdf >= 1.0L - 1e-19L || k == max_n - 1) {
+        // stop once the remaining tail is below the 2^-64 resolution of the uniform
+        if (cdf >= 1.0L - 1e-19L || (k > lambda && pmf < 1e-22L) || k == max_n - 1) {
             t.push_back(~0ull);
             break;
         }
