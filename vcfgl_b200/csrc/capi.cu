@@ -71,8 +71,9 @@ struct vgl_ctx {
     uint8_t bin_lut[256];
     int bin_max = -1;
     // device tables
-    int use_fused = 0, n_sms = 148, fast_div = 0;
-    unsigned long long* d_pois = nullptr;
+    int use_fused = 0, use_tile = 0, n_sms = 148, fast_div = 0;
+    unsigned long long *d_pois = nullptr, *d_alias = nullptr;
+    uint32_t* d_errcdf = nullptr;
     int pois_n = 0;
     double *d_lut = nullptr, *d_m1_bsum = nullptr, *d_m1_het = nullptr, *d_fk = nullptr, *d_beta = nullptr, *d_depth_means = nullptr;
     std::vector<Slot> slots;
@@ -194,7 +195,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf);
     delete ctx;
 }
 
@@ -258,10 +259,21 @@ static int create_impl(vgl_ctx* ctx)
     ctx->use_fused = ctx->gl_mode == GL_M1_FIXED && p.sampler != VGL_SAMPLER_PER_READ &&
                      !(t & (VGL_TAG_QS | VGL_TAG_I16)) && g_cap_elems < (1ull << 31);
     if (p.sampler == VGL_SAMPLER_COUNTS && !ctx->use_fused) return fail(ctx, VGL_EINVAL, "count-level sampler unavailable for this configuration (plane too large)");
+    std::vector<unsigned long long> alias(256, 0ull);
+    bool alias_ok = p.depth_mode == VGL_DEPTH_FIXED && p.depth_mean < 256.0;
     if (ctx->use_fused && p.depth_mode == VGL_DEPTH_POISSON) {
         const std::vector<unsigned long long> cdf = poisson_cdf_u64(p.depth_mean, 1024);
         ctx->pois_n = (int)cdf.size();
         CK(upload(&ctx->d_pois, cdf));
+        const std::vector<unsigned long long> al = poisson_alias_u64(cdf); // empty: depth can exceed 255
+        if (!al.empty()) { alias = al; alias_ok = true; }
+    }
+    // the tile kernel (tile_m1f.cu): the fused path's headline special case
+    ctx->use_tile = ctx->use_fused && alias_ok && p.error_qs == 0 && !ctx->sample_strand && !(t & VGL_TAG_GP) && ctx->fast_div &&
+                    p.n_samples >= 29 && p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
+    if (ctx->use_tile) {
+        CK(upload(&ctx->d_alias, alias));
+        CK(upload(&ctx->d_errcdf, binomial_cdf4_u32(p.error_rate)));
     }
 
     // ---- slots
@@ -427,9 +439,12 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.pairmap = s.d_pairmap;
     p.pois_cdf = ctx->d_pois;
     p.pois_n = ctx->pois_n;
+    p.pois_alias = ctx->d_alias;
+    p.err_cdf = ctx->d_errcdf;
     {
         int T = 1024 / (int)S;
         T = T < 1 ? 1 : (T > 128 ? 128 : T);
+        if (ctx->use_tile) T = tile_m1f_sites_per_tile((int)S);
         p.sites_per_tile = T;
         p.n_tiles = (n_sites + T - 1) / T;
         p.tile_state = s.d_tile_state;
@@ -497,7 +512,8 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         CK(cudaEventRecord(s.ev[EV_SIM], st));
         CK(cudaEventRecord(s.ev[EV_SITE], st));
         CK(cudaEventRecord(s.ev[EV_SCAN], st));
-        launch_fused_m1f(p, st, ctx->n_sms);
+        if (ctx->use_tile) launch_tile_m1f(p, st, ctx->n_sms);
+        else launch_fused_m1f(p, st, ctx->n_sms);
         CK(cudaEventRecord(s.ev[EV_EMIT], st));
         ctx->launches += 1;
     } else {

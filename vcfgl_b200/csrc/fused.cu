@@ -503,7 +503,7 @@ __global__ void k_selftest(unsigned long long* bad, unsigned int* first_bad)
             ok = __float_as_uint(neg_div10_fast(x)) == __float_as_uint(neg_div10_ref(x));
         }
         if (x <= 0.0f || __float_as_uint(x) == 0x80000000u) { // a rescaled GL is <= 0 (or -0)
-            ok = ok && (pl_from_gl(x) == pl_from_gl_ref(x));
+            ok = ok && (pl_from_gl(x) == pl_from_gl_ref(x)) && (pl_from_gl_magic(x) == pl_from_gl_ref(x));
         }
         if (!ok) {
             atomicAdd(bad, 1ull);

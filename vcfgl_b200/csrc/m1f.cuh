@@ -67,10 +67,22 @@ __device__ __forceinline__ int pl_from_gl(float gl)
     return i > 255 ? 255 : i;
 }
 
+// lroundf((float)(-10.0 * (double)gl)) capped at 255 (vcfgl.cpp:931-934) for gl <= 0 without a
+// float->int conversion: the product is exact in double so one float multiply rounds identically;
+// floor(x + 0.5) by a round-toward-zero add (x >= 0), and the integer read off the mantissa after
+// adding 2^23.  Checked against the reference expression for every float <= 0 (vgl_selftest).
+__device__ __forceinline__ int pl_from_gl_magic(float gl)
+{
+    const float x = fminf(__fmul_rn(-10.0f, gl), 255.0f);
+    const float u = __fadd_rz(__fadd_rz(x, 0.5f), 8388608.0f);
+    return __float_as_int(u) & 0x1FF;
+}
+
 // phred-scaled errmod likelihoods q[pair] for all 15 base pairs from the counts c0..c3 of a cell with
 // n = c0+c1+c2+c3 reads, 1 <= n <= 255.  bsum = fixed-qs running-sum table [n<<8|c], het = -4.343*lhet.
-__device__ __forceinline__ void m1f_scores(int n, int c0, int c1, int c2, int c3, const double* __restrict__ bsum,
-                                           const double* __restrict__ het, float (&q)[15])
+template <bool CLAMP>
+__device__ __forceinline__ void m1f_scores_t(int n, int c0, int c1, int c2, int c3, const double* __restrict__ bsum,
+                                             const double* __restrict__ het, float (&q)[15])
 {
     const double* row = bsum + (n << 8);
     const double b0 = __ldg(row + c0), b1 = __ldg(row + c1), b2 = __ldg(row + c2), b3 = __ldg(row + c3);
@@ -97,8 +109,25 @@ __device__ __forceinline__ void m1f_scores(int n, int c0, int c1, int c2, int c3
     q[12] = VGL_HET(c2, 0, t013);
     q[13] = VGL_HET(c3, 0, t012);
 #undef VGL_HET
+    if (CLAMP) {
 #pragma unroll
-    for (int i = 0; i < 15; ++i) q[i] = fmaxf(q[i], 0.0f); // errmod.c:204 (scores are sums of non-negative terms: never -0 or NaN)
+        for (int i = 0; i < 15; ++i) q[i] = fmaxf(q[i], 0.0f); // errmod.c:204
+    }
+}
+
+__device__ __forceinline__ void m1f_scores(int n, int c0, int c1, int c2, int c3, const double* __restrict__ bsum,
+                                           const double* __restrict__ het, float (&q)[15])
+{
+    m1f_scores_t<true>(n, c0, c1, c2, c3, bsum, het, q);
+}
+
+// errmod.c:204 clamps negative scores to 0.  When the host has proven that every table term is >= +0
+// (ErrmodTables::scores_safe_for_fast_div) the scores are sums of non-negative terms, never negative,
+// -0 or NaN, and the clamp is the identity.
+__device__ __forceinline__ void m1f_scores_noclamp(int n, int c0, int c1, int c2, int c3, const double* __restrict__ bsum,
+                                                   const double* __restrict__ het, float (&q)[15])
+{
+    m1f_scores_t<false>(n, c0, c1, c2, c3, bsum, het, q);
 }
 
 // scatter the base-pair scores into the cell's allele-ordered GL slots (shared memory), rescale to

@@ -97,6 +97,63 @@ std::vector<unsigned long long> poisson_cdf_u64(double lambda, int max_n)
     return t;
 }
 
+std::vector<unsigned long long> poisson_alias_u64(const std::vector<unsigned long long>& cdf)
+{
+    typedef unsigned __int128 u128;
+    const int K = 256;
+    if (cdf.empty() || cdf.size() > (size_t)K) return {};
+    const u128 one = (u128)1 << 64;
+    // mass of outcome k scaled by K, in units of 2^-64 of a column: m[k] = K * pmf[k], sum = K * 2^64
+    std::vector<u128> m(K, 0);
+    u128 prev = 0;
+    for (size_t k = 0; k < cdf.size(); ++k) {
+        const u128 c = k + 1 == cdf.size() ? one : (u128)cdf[k];
+        m[k] = (c - prev) * K;
+        prev = c;
+    }
+    std::vector<unsigned long long> out(K);
+    std::vector<int> small, large;
+    for (int k = 0; k < K; ++k) (m[k] < one ? small : large).push_back(k);
+    std::vector<u128> stay(K, one);
+    std::vector<int> alias(K);
+    for (int k = 0; k < K; ++k) alias[k] = k;
+    while (!small.empty() && !large.empty()) {
+        const int s = small.back(), l = large.back();
+        small.pop_back();
+        stay[s] = m[s];
+        alias[s] = l;
+        m[l] -= one - m[s];
+        if (m[l] < one) {
+            large.pop_back();
+            small.push_back(l);
+        }
+    }
+    // leftovers hold exactly one column each (integer arithmetic: no rounding residue)
+    for (int k = 0; k < K; ++k) {
+        if (alias[k] == k) { out[k] = (unsigned long long)k; continue; } // threshold irrelevant: both branches give k
+        const u128 t56 = (stay[k] + 255) >> 8; // frac56 < ceil(stay / 256)  <=>  frac56 * 256 < stay
+        out[k] = (unsigned long long)(t56 << 8) | (unsigned long long)alias[k];
+    }
+    return out;
+}
+
+std::vector<uint32_t> binomial_cdf4_u32(double e)
+{
+    std::vector<uint32_t> t(256 * 4, 0xFFFFFFFFu);
+    if (!(e > 0.0)) return t; // never an error: every u < 2^32-1 gives E = 0
+    const long double le = logl((long double)e), l1 = log1pl(-(long double)e);
+    for (int n = 0; n < 256; ++n) {
+        long double cdf = 0.0L;
+        for (int j = 0; j < 4 && j <= n; ++j) {
+            const long double lp = lgammal(n + 1.0L) - lgammal(j + 1.0L) - lgammal(n - j + 1.0L) + j * le + (n - j) * l1;
+            cdf += expl(lp);
+            const long double sc = cdf * 4294967296.0L;
+            t[n * 4 + j] = sc >= 4294967295.0L ? 0xFFFFFFFFu : (uint32_t)sc;
+        }
+    }
+    return t;
+}
+
 bool ErrmodTables::scores_safe_for_fast_div(const std::vector<double>& bsum, const std::vector<double>& het)
 {
     const double lo = ldexp(1.0, -100), hi = ldexp(1.0, 100);

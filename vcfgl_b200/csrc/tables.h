@@ -27,6 +27,16 @@ struct ErrmodTables {
 // uniform u.  At most max_n entries; the last entry is 2^64-1.  (native count-level sampler)
 std::vector<unsigned long long> poisson_cdf_u64(double lambda, int max_n);
 
+// Walker alias table over 256 columns for the same distribution (tile kernel): with a 64-bit uniform u,
+// column = u >> 56; the cell keeps `column` when (u << 8) < (entry & ~0xFF), else takes entry & 0xFF.
+// Built in exact integer arithmetic from the CDF above, so P(n) is reproduced to 2^-64.
+// Returns an empty vector when the support does not fit 256 outcomes.
+std::vector<unsigned long long> poisson_alias_u64(const std::vector<unsigned long long>& cdf);
+
+// number of mis-called reads E ~ Binomial(n, e): thresholds floor(P(E <= j | n) * 2^32), j = 0..3, n = 0..255
+// (saturated at 2^32-1); E = #{j : u >= t[n][j]} for a 32-bit uniform u, 4 = "beyond the table".
+std::vector<uint32_t> binomial_cdf4_u32(double e);
+
 // qScore_to_log10_gl[3][257] (shared.cpp:110-114)
 extern const double kLutLog10Gl[3][257];
 

@@ -86,6 +86,9 @@ struct DevParams {
     int32_t sites_per_tile, n_tiles;
     unsigned long long* tile_state;     // [n_tiles] decoupled look-back words
     uint32_t* ticket;                   // dynamic tile counter
+    // tile kernel (tile_m1f.cu)
+    const unsigned long long* pois_alias; // [256] Walker alias table of the depth distribution: t56 << 8 | alias
+    const uint32_t* err_cdf;              // [256][4] P(E <= j | n reads) * 2^32, j = 0..3
     // replay
     int32_t replay;
     const int32_t* rp_depths;
@@ -103,6 +106,9 @@ void launch_scan(const DevParams& p, cudaStream_t st);
 void launch_emit(const DevParams& p, cudaStream_t st);
 int run_selftest(unsigned long long* n_bad, unsigned int* first_bad);
 void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms);
+void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms);
+int tile_m1f_max_samples();
+int tile_m1f_sites_per_tile(int S);
 void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
                   uint8_t* adjqs, uint8_t* tails, double* eprob);
 
