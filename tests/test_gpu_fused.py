@@ -54,14 +54,18 @@ def test_fused_tags_match_oracle_on_own_counts(name):
     first = 987654321
     sites, (g_off, r_off, g_elems, r_elems) = run(a, S, gt, first, n_sites)
     orc = oracle_lib.Oracle(a, S)
-    # (2) layout: blocks in site order, 16-byte aligned, exactly tiling the used prefix
+    # (2) layout: blocks in site order, 16-byte aligned, disjoint, inside the used extent.  (The tile kernel packs
+    # blocks densely within a tile of sites and starts every tile at a fixed stride; the general kernels pack all.)
     pos_g = pos_r = 0
     for i, d in enumerate(sites):
-        assert g_off[i] == pos_g and r_off[i] == pos_r, (name, i)
+        assert g_off[i] >= pos_g and r_off[i] >= pos_r, (name, i)
+        assert g_off[i] % 4 == 0 and r_off[i] % 4 == 0, (name, i)
+        pos_g, pos_r = g_off[i], r_off[i]
         if d["skip_code"] == 0:
             pos_g += (S * d["n_genotypes"] + 3) // 4 * 4
             pos_r += (S * d["n_alleles"] + 3) // 4 * 4
-    assert (pos_g, pos_r) == (g_elems, r_elems)
+    assert pos_g <= g_elems and pos_r <= r_elems
+    assert g_elems <= n_sites * ((S * 15 + 3) // 4 * 4) and r_elems <= n_sites * ((S * 5 + 3) // 4 * 4)
     # (1) oracle on the kernel's own counts
     n_cmp = 0
     for i, d in enumerate(sites):

@@ -16,6 +16,8 @@ from . import args as vargs
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgl.so")
+if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same ABI (tools/gpu_variants.sh)
+    LIB_PATH = os.environ["VGL_LIB"]
 
 VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV = 0, -1, -2, -3, -4, -5, -6
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)

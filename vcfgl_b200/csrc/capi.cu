@@ -270,7 +270,7 @@ static int create_impl(vgl_ctx* ctx)
     }
     // the tile kernel (tile_m1f.cu): the fused path's headline special case
     ctx->use_tile = ctx->use_fused && alias_ok && p.error_qs == 0 && !ctx->sample_strand && !(t & VGL_TAG_GP) && ctx->fast_div &&
-                    p.n_samples >= 29 && p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
+                    p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
     if (ctx->use_tile) {
         CK(upload(&ctx->d_alias, alias));
         CK(upload(&ctx->d_errcdf, binomial_cdf4_u32(p.error_rate)));
@@ -396,6 +396,10 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.n_cells = cells;
     p.k0 = (uint32_t)((uint64_t)prm.seed & 0xFFFFFFFFu);
     p.k1 = (uint32_t)((uint64_t)prm.seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        p.rk[2 * r] = p.k0 + (uint32_t)r * 0x9E3779B9u;
+        p.rk[2 * r + 1] = p.k1 + (uint32_t)r * 0xBB67AE85u;
+    }
     p.depth_mode = prm.depth_mode;
     p.depth_mean = prm.depth_mean;
     p.depth_means = ctx->d_depth_means;

@@ -501,9 +501,16 @@ __global__ void k_selftest(unsigned long long* bad, unsigned int* first_bad)
         bool ok = true;
         if ((unsigned int)i == 0u || (x >= 7.888609052210118e-31f && x < CUDART_INF_F)) { // +0 or finite >= 2^-100
             ok = __float_as_uint(neg_div10_fast(x)) == __float_as_uint(neg_div10_ref(x));
+            float w0, w1;
+            unpack2(div10_fast2(pack2(x, x)), w0, w1);
+            ok = ok && __float_as_uint(-w0) == __float_as_uint(neg_div10_ref(x)) && __float_as_uint(-w1) == __float_as_uint(neg_div10_ref(x));
         }
         if (x <= 0.0f || __float_as_uint(x) == 0x80000000u) { // a rescaled GL is <= 0 (or -0)
-            ok = ok && (pl_from_gl(x) == pl_from_gl_ref(x)) && (pl_from_gl_magic(x) == pl_from_gl_ref(x));
+            ok = ok && (pl_from_gl(x) == pl_from_gl_ref(x)) && (pl_from_gl_magic(x) == pl_from_gl_ref(x)) &&
+                 (pl_from_gl_magic_uncapped(x) == pl_from_gl_ref(x));
+            float u0, u1;
+            unpack2(pl_magic2(pack2(x, x)), u0, u1);
+            ok = ok && pl_from_magic_bits(u0) == pl_from_gl_ref(x) && pl_from_magic_bits(u1) == pl_from_gl_ref(x);
         }
         if (!ok) {
             atomicAdd(bad, 1ull);

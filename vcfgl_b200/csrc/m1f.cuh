@@ -78,6 +78,52 @@ __device__ __forceinline__ int pl_from_gl_magic(float gl)
     return __float_as_int(u) & 0x1FF;
 }
 
+// ---- packed fp32x2 forms (sm_100 FMUL2 / FFMA2 / FADD2: two IEEE operations per instruction, same
+// roundings as the scalar forms above)
+struct f32x2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 x, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x.v)); }
+// q / 10 for both halves (the value neg_div10_fast negates)
+__device__ __forceinline__ f32x2 div10_fast2(f32x2 q)
+{
+    const f32x2 c01 = pack2(0.1f, 0.1f), cm10 = pack2(-10.0f, -10.0f);
+    f32x2 y, r, w;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(y.v) : "l"(q.v), "l"(c01.v));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(cm10.v), "l"(y.v), "l"(q.v));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w.v) : "l"(r.v), "l"(c01.v), "l"(y.v));
+    return w;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+// mantissa-encoded PL of both halves: bits = 0x4B000000 + floor(-10 * gl + 0.5) (uncapped), gl <= 0
+__device__ __forceinline__ f32x2 pl_magic2(f32x2 gl)
+{
+    const f32x2 cm10 = pack2(-10.0f, -10.0f), h = pack2(0.5f, 0.5f), m23 = pack2(8388608.0f, 8388608.0f);
+    f32x2 x, t, u;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(x.v) : "l"(gl.v), "l"(cm10.v));
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(t.v) : "l"(x.v), "l"(h.v));
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(u.v) : "l"(t.v), "l"(m23.v));
+    return u;
+}
+// scalar twin of pl_magic2 + the cap: min(bits - 0x4B000000, 255) in one VIADDMNMX (also maps +inf to 255)
+__device__ __forceinline__ int pl_from_magic_bits(float u) { return (int)__viaddmin_u32(__float_as_uint(u), 0xB5000000u, 255u); }
+__device__ __forceinline__ int pl_from_gl_magic_uncapped(float gl)
+{
+    const float u = __fadd_rz(__fadd_rz(__fmul_rn(-10.0f, gl), 0.5f), 8388608.0f);
+    return pl_from_magic_bits(u);
+}
+
 // phred-scaled errmod likelihoods q[pair] for all 15 base pairs from the counts c0..c3 of a cell with
 // n = c0+c1+c2+c3 reads, 1 <= n <= 255.  bsum = fixed-qs running-sum table [n<<8|c], het = -4.343*lhet.
 template <bool CLAMP>

@@ -9,46 +9,45 @@
 // on a 16-byte boundary (blocks themselves are padded to 16 B).
 //   phase A  thread per cell: two Philox blocks -> depth (alias table), number of mis-called reads
 //            (threshold table), haplotype split (popcount), error placement -> four 8-bit base
-//            counts kept in shared memory; FORMAT/DP written; per-site totals by packed warp REDUX
+//            counts kept in shared memory; FORMAT/DP written
+//   phase A2 warp per site (or site part): per-site base totals from the count cache (IDP.4A + REDUX)
 //   phase B  thread per site: allele order, unobserved allele, skip code, INFO tags
 //            (vcfgl.cpp:396-404, 665-782); decoupled look-back gives the tile's base offsets
-//   phase C  warp per 32 cells: errmod scores from the counts (m1f.cuh), GL / PL / AD scattered into
-//            the warp's own shared-memory slice in allele order, then ONE bulk async copy
-//            (cp.async.bulk shared -> global) per plane writes the whole 16-byte aligned span.
+//   phase C  warp per 32 cells: errmod scores from the counts (m1f.cuh), GL / PL (packed fp32x2 math)
+//            and AD scattered into the warp's own shared-memory slice in allele order, then ONE bulk
+//            async copy (cp.async.bulk shared -> global) per plane writes the 16-byte aligned span.
 // HBM traffic = 1 B/cell in, the tag planes out.
 #include "counts_sampler.cuh"
 #include "m1f.cuh"
 
 namespace vgl {
 
-#define TILE_BLOCK 256
+#ifndef TILE_BLOCK
+#define TILE_BLOCK 128
+#endif
 #define TILE_WARPS (TILE_BLOCK / 32)
-#define TILE_MAX_SITES 64
-#define TILE_CELLS 4096      // virtual cells of a tile when a site is smaller than this
-#define TILE_WST_G 512       // 4-byte elements per warp and G-shaped plane: 32 cells x 15 (+ pads) <= 32 x 16
-#define TILE_WST_R 192       // 32 cells x 5 (+ pads) <= 32 x 6
+#ifndef TILE_MAX_SITES
+#define TILE_MAX_SITES 32    // <= 32: phase B is one warp
+#endif
+#ifndef TILE_CELLS
+#define TILE_CELLS 2048      // virtual cells of a tile when a site is smaller than this
+#endif
+#ifndef TILE_MIN_CTAS
+#define TILE_MIN_CTAS 6
+#endif
+#define TILE_WST_G 528       // 4-byte elements per warp and G-shaped plane: 32 cells x 15 + pads (<= 3 per site end) <= 504, then a scratch cell
+#define TILE_WST_R 192       // 32 cells x 5 + pads <= 184, then a scratch cell
+#define TILE_G_TRASH 512
+#define TILE_R_TRASH 184
 
 struct __align__(16) TSite {
     uint32_t slot[4];     // byte k = 4 * (allele-space genotype slot of base pair k), 0xFF = pair not at this site
     int32_t g_rel, r_rel; // element offsets of the site's blocks relative to the tile's base
-    uint32_t a2b;         // nibble a = base of allele a; 4 = the unobserved allele, 0xF = none
     uint32_t AG;          // A | G << 8 | all15 << 16   (A = G = 0: site skipped)
+    uint32_t sel4;        // PRMT selector of allele 4 (see sel01)
+    uint32_t sel01, sel23; // 16-bit PRMT selectors of alleles 0..3: byte (base) of the packed counts, 4 = reads 0
+    int32_t g_end, r_end; // g_rel / r_rel + the padded block size
 };
-
-__device__ __forceinline__ unsigned long long ld_state_t(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_state_t(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-#define TS_PACK(flag, g, r) (((unsigned long long)(flag) << 62) | ((unsigned long long)(g) << 31) | (unsigned long long)(r))
-#define TS_FLAG(w) ((int)((w) >> 62))
-#define TS_G(w) ((long long)(((w) >> 31) & 0x7FFFFFFFull))
-#define TS_R(w) ((long long)((w)&0x7FFFFFFFull))
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -63,422 +62,511 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // low `k` bits set, 0 <= k <= 32
 __device__ __forceinline__ uint32_t low_bits(int k) { return __funnelshift_rc(0xFFFFFFFFu, 0u, 32 - k); }
 
+// Philox4x32-10 with the round keys read from the kernel parameters (constant bank operands)
+__device__ __forceinline__ u32x4 philox_rk(const DevParams& p, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk[2 * r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ p.rk[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    u32x4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// shared memory by 32-bit address (keeps generic->shared conversions out of the loops)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // One cell of the count-level sampler: returns the four 8-bit base counts (A | C << 8 | G << 16 | T << 24).
-// Draws: block 0 = {x,y: depth; z: number of errors; w: haplotype bits 0..31}, block 1 = {x: haplotype
-// bits 32..63; y,z,w: placement of errors 1..3}; rarer needs (depth > 64, > 3 errors) continue with
-// blocks 2.. of the same (site, sample) counter.
+// Draws (same counter layout as draw() in philox.cuh, purpose P_COUNTS): block 0 = {x,y: depth; z: number of
+// errors; w: haplotype bits 0..31}, block 1 = {x: haplotype bits 32..63; y,z,w: placement of errors 1..3};
+// rarer needs (depth > 64, > 3 errors) continue with later blocks of the same (site, sample) counter.
 struct TileRng {
-    Key key;
-    const uint2* alias;  // shared: [256] (t56 << 8 | alias) as {lo, hi}
-    const uint4* cdf_e;  // shared: [256] P(E <= j | n) * 2^32, j = 0..3
-    double e;
+    uint32_t s_alias;    // shared address: [256] (t56 << 8 | alias) as {lo, hi}
+    uint32_t s_cdf_e;    // shared address: [256] uint4 P(E <= j | n) * 2^32, j = 0..3
     int fixed_depth;     // >= 0: every cell has this depth; < 0: Poisson via the alias table
     bool has_err;
 };
 
-__device__ __forceinline__ uint32_t tile_sample_cell(const TileRng& R, int64_t site, uint32_t sample, uint32_t gt)
+// one mis-called read: read j of the `rem` left is hit; it belongs to haplotype 0 w.p. rem0/rem; the wrong base
+// is uniform over the other three
+__device__ __forceinline__ uint32_t tile_place_error(uint32_t ad, uint32_t r, int g0, int g1, int& rem0, int& rem)
 {
-    const int g0 = gt & 0xF, g1 = gt >> 4;
-    const u32x4 b0 = draw(R.key, site, sample, 0, P_COUNTS, 0);
-    const u32x4 b1 = draw(R.key, site, sample, 0, P_COUNTS, 1);
+    const uint32_t j = mulhi32(r, 3u * (uint32_t)rem);
+    const uint32_t which = (j * 0xAAABu) >> 17; // j / 3 for j < 2^15 (rem <= 255)
+    const uint32_t woff = j - 3u * which;
+    const bool from0 = (int)which < rem0;
+    const int truth = from0 ? g0 : g1;
+    rem0 -= from0;
+    --rem;
+    const int wrong = (truth + 1 + (int)woff) & 3;
+    return ad + (1u << (8 * wrong)) - (1u << (8 * truth));
+}
+
+__device__ __forceinline__ uint32_t tile_sample_cell(const DevParams& p, const TileRng& R, unsigned long long site, uint32_t sample, uint32_t gt)
+{
+    const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
+    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+    const u32x4 b0 = philox_rk(p, c0, c1, sample, (uint32_t)P_COUNTS << 24);
+    const u32x4 b1 = philox_rk(p, c0, c1, sample, ((uint32_t)P_COUNTS << 24) | 1u);
     int n;
     if (R.fixed_depth >= 0) {
         n = R.fixed_depth;
     } else { // Walker alias over 256 columns, 64-bit uniform: column = top byte, 56 bits against the column's threshold
         const uint32_t col = b0.x >> 24;
-        const uint2 en = R.alias[col];
+        const uint2 en = lds64(R.s_alias + col * 8u);
         const unsigned long long frac = ((unsigned long long)__funnelshift_l(b0.y, b0.x, 8) << 32) | (b0.y << 8);
         const unsigned long long thr = ((unsigned long long)en.y << 32) | (en.x & 0xFFFFFF00u);
         n = frac < thr ? (int)col : (int)(en.x & 0xFFu);
     }
-    if (g0 == VGL_GT_MISSING || g1 == VGL_GT_MISSING) n = 0; // depth is drawn but discarded (vcfgl.cpp:371-379)
+    if (gt & 0x88u) n = 0; // a missing allele (0xF; valid alleles are 0..3): depth is drawn but discarded (vcfgl.cpp:371-379)
+    const bool het = ((gt ^ (gt >> 4)) & 0x3u) != 0u;
+    // haplotype split: reads from haplotype 0 = popcount of the first n random bits
+    const int kh = __popc(b0.w & low_bits(min(n, 32))) + __popc(b1.x & low_bits(min(max(n - 32, 0), 32)));
+    int k0 = het ? kh : n;
     int E = 0;
-    if (R.has_err) {
-        const uint4 c = R.cdf_e[n];
-        E = (b0.z >= c.x) + (b0.z >= c.y) + (b0.z >= c.z) + (b0.z >= c.w);
-        if (E == 4) E = binom_inversion(n, R.e, u01_32(b0.z)); // beyond the table: exact inversion
+    bool rare = het && n > 64;
+    if (R.has_err) { // number of mis-called reads: two thresholds decide 0 / 1 / 2, more is rare
+        const uint4 c = lds128(R.s_cdf_e + (uint32_t)n * 16u);
+        E = (b0.z >= c.x) + (b0.z >= c.y);
+        rare = rare || b0.z >= c.z;
     }
-    int k0 = n; // reads drawn from haplotype 0
-    if (g0 != g1) {
-        k0 = __popc(b0.w & low_bits(min(n, 32))) + __popc(b1.x & low_bits(min(max(n - 32, 0), 32)));
-        if (n > 64) {
+    if (rare) {
+        Key key;
+        key.k0 = p.k0; key.k1 = p.k1;
+        if (het && n > 64) {
             Stream st;
-            st.init(R.key, site, sample, 0, P_COUNTS);
+            st.init(key, (int64_t)site, sample, 0, P_COUNTS);
             st.block = 2;
             for (int left = n - 64; left > 0; left -= 32) k0 += __popc(st.next() & low_bits(min(left, 32)));
         }
+        if (R.has_err) {
+            const uint4 c = lds128(R.s_cdf_e + (uint32_t)n * 16u);
+            if (b0.z >= c.z) E = b0.z >= c.w ? binom_inversion(n, p.error_rate, u01_32(b0.z)) : 3; // beyond the table: exact inversion
+        }
     }
     uint32_t ad = ((uint32_t)k0 << (8 * g0)) + ((uint32_t)(n - k0) << (8 * g1));
-    if (E > 0) { // place the errors: read j of the rem left is hit, it belongs to haplotype 0 w.p. rem0/rem; wrong base uniform
-        int rem0 = k0, rem = n;
+    int rem0 = k0, rem = max(n, 1);
+    const uint32_t ad1 = tile_place_error(ad, b1.y, g0, g1, rem0, rem); // straight-line first error (nearly every warp has one)
+    if (E > 0) ad = ad1;
+    if (E > 1) {
+        Key key;
+        key.k0 = p.k0; key.k1 = p.k1;
         Stream st;
-        st.init(R.key, site, sample, 0, P_COUNTS);
+        st.init(key, (int64_t)site, sample, 0, P_COUNTS);
         st.block = 10;
-        for (int i = 0; i < E; ++i) {
-            const uint32_t r = i == 0 ? b1.y : i == 1 ? b1.z : i == 2 ? b1.w : st.next();
-            const uint32_t j = mulhi32(r, 3u * (uint32_t)rem);
-            const uint32_t which = (j * 0xAAABu) >> 17; // j / 3 for j < 2^15 (rem <= 255)
-            const uint32_t woff = j - 3u * which;
-            const bool from0 = (int)which < rem0;
-            const int truth = from0 ? g0 : g1;
-            rem0 -= from0;
-            --rem;
-            const int wrong = (truth + 1 + (int)woff) & 3;
-            ad += (1u << (8 * wrong)) - (1u << (8 * truth));
-        }
+        for (int i = 1; i < E; ++i) ad = tile_place_error(ad, i == 1 ? b1.z : i == 2 ? b1.w : st.next(), g0, g1, rem0, rem);
     }
     return ad;
 }
 
 // GL / PL of one cell from its scores, scattered into the warp's stage slice in allele order
 // (gl_methods.cpp:338-357, vcfgl.cpp:907-939).  ALL15: every base pair is a genotype of the site.
+// With w = q/10 >= 0: GL = (-w) - max(-w) = min(w) - w, the same float as the reference's subtraction.
 template <bool ALL15>
-__device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const TSite& ts, char* cell_g, bool has_gl, bool has_pl)
+__device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const uint4 slot, uint32_t cell_g, bool has_gl, bool has_pl)
 {
-    float v[15];
+    float w[16];
 #pragma unroll
-    for (int k = 0; k < 15; ++k) v[k] = neg_div10_fast(q[k]); // gl_methods.cpp:343
-    float mx = -CUDART_INF_F;
+    for (int k = 0; k < 14; k += 2) unpack2(div10_fast2(pack2(q[k], q[k + 1])), w[k], w[k + 1]);
+    w[14] = -neg_div10_fast(q[14]);
+    const uint32_t sw[4] = {slot.x, slot.y, slot.z, slot.w};
+    uint32_t off[15];
 #pragma unroll
-    for (int k = 0; k < 15; ++k) {
-        const uint32_t off = (ts.slot[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-        mx = fmaxf(mx, (ALL15 || off != 0xFFu) ? v[k] : -CUDART_INF_F);
+    for (int k = 0; k < 15; ++k) off[k] = __byte_perm(sw[k >> 2], 0u, 0x4440u | (k & 3));
+    float mn = CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) mn = fminf(mn, (ALL15 || off[k] != 0xFFu) ? w[k] : CUDART_INF_F);
+    const f32x2 mn2 = pack2(mn, mn);
+    float g[16], u[16];
+#pragma unroll
+    for (int k = 0; k < 14; k += 2) {
+        const f32x2 g2 = sub2(mn2, pack2(w[k], w[k + 1]));
+        unpack2(g2, g[k], g[k + 1]);
+        unpack2(pl_magic2(g2), u[k], u[k + 1]);
     }
+    g[14] = __fsub_rn(mn, w[14]);
+    u[14] = __fadd_rz(__fadd_rz(__fmul_rn(-10.0f, g[14]), 0.5f), 8388608.0f);
 #pragma unroll
     for (int k = 0; k < 15; ++k) {
-        const uint32_t off = (ts.slot[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-        if (ALL15 || off != 0xFFu) {
-            const float g = __fsub_rn(v[k], mx);
-            char* dst = cell_g + off;
-            if (has_gl) *reinterpret_cast<float*>(dst) = g;
-            if (has_pl) *reinterpret_cast<int*>(dst + TILE_WST_G * 4) = pl_from_gl_magic(g);
+        if (ALL15 || off[k] != 0xFFu) {
+            const uint32_t dst = cell_g + off[k];
+            if (has_gl) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(g[k]) : "memory");
+            if (has_pl) asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(dst), "r"(pl_from_magic_bits(u[k])), "n"(TILE_WST_G * 4) : "memory");
         }
     }
 }
 
-__global__ void __launch_bounds__(TILE_BLOCK, 3) k_tile_m1f(const __grid_constant__ DevParams p)
+// next chunk of 32 virtual cells of the running phase: one shared-memory ticket per warp and chunk, so that
+// warps the scheduler favours take more chunks and the phase ends for all warps at about the same time.
+// Issue (lane 0's atomic) and use (broadcast) are split so that the atomic's latency overlaps a whole chunk.
+__device__ __forceinline__ int tile_ticket_issue(uint32_t s_ctr, int lane)
+{
+    int c = 0;
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(s_ctr) : "memory");
+    return c;
+}
+__device__ __forceinline__ int tile_ticket_get(int raw) { return __shfl_sync(0xffffffffu, raw, 0); }
+
+template <bool GEN>
+__global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    // layout: alias [256] u64 | cdf_e [256] uint4 | stage [8 warps][G plane, PL plane, R plane] | st [64] | tot [64][4] | cnt [cap]
-    uint2* alias = reinterpret_cast<uint2*>(tile_smem);
-    uint4* cdf_e = reinterpret_cast<uint4*>(tile_smem + 2048);
-    uint32_t* stage = reinterpret_cast<uint32_t*>(tile_smem + 2048 + 4096);
+    // layout: alias [256] u64 | cdf_e [256] uint4 | stage [warps][G plane, PL plane, R plane] | st [sites] | tot [sites][4] | cnt [cap]
     constexpr int WST = 2 * TILE_WST_G + TILE_WST_R; // words per warp
-    TSite* st = reinterpret_cast<TSite*>(stage + TILE_WARPS * WST);
-    int* tot = reinterpret_cast<int*>(st + TILE_MAX_SITES);
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(tot + TILE_MAX_SITES * 4);
+    constexpr uint32_t OFF_STAGE = 2048 + 4096, OFF_ST = OFF_STAGE + TILE_WARPS * WST * 4, OFF_TOT = OFF_ST + TILE_MAX_SITES * sizeof(TSite),
+                       OFF_CNT = OFF_TOT + TILE_MAX_SITES * 16;
+    TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
+    int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
     __shared__ int64_t s_base[2];
-    __shared__ int s_tile, s_tile_g, s_tile_r;
-    __shared__ int wsum[4];
+    __shared__ int s_next;
+    __shared__ uint32_t s_ctr[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = p.S, S4 = (S + 3) & ~3, T = p.sites_per_tile;
+    const int S = p.S, S4 = (S + 3) & ~3, PAD = S4 - S, T = p.sites_per_tile;
+    const uint32_t s_smem = smem_u32(tile_smem);
     for (int i = tid; i < 256; i += TILE_BLOCK) {
-        alias[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
-        cdf_e[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+        reinterpret_cast<uint2*>(tile_smem)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
+        reinterpret_cast<uint4*>(tile_smem + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+    }
+    for (int i = tid; i < TILE_MAX_SITES * 4; i += TILE_BLOCK) tot[i] = 0;
+    if (tid == 0) {
+        s_next = (int)atomicAdd(p.ticket, 1u);
+        s_ctr[0] = s_ctr[1] = 0u;
     }
     TileRng R;
-    R.key.k0 = p.k0;
-    R.key.k1 = p.k1;
-    R.alias = alias;
-    R.cdf_e = cdf_e;
-    R.e = p.error_rate;
+    R.s_alias = s_smem;
+    R.s_cdf_e = s_smem + 2048;
     R.fixed_depth = p.depth_mode == VGL_DEPTH_FIXED ? (int)p.depth_mean : -1;
     R.has_err = p.error_rate > 0.0;
-    // iv / S4 for iv < 2^16 (exact: S4 >= 32, iv < 65536)
+    // iv / S4 for iv < 2^16 (exact while iv * S4 < 2^32)
     const uint32_t inv_s4 = (uint32_t)(((1ull << 32) + S4 - 1) / S4);
     const bool explode = p.do_unobserved >= 3;
     const bool add_unobs = p.do_unobserved == 1 || p.do_unobserved == 2 || p.do_unobserved == 4 || p.do_unobserved == 5;
-    const bool has_gl = p.gl != nullptr, has_pl = p.pl != nullptr, has_ad = p.ad != nullptr;
-    uint32_t* const wg = stage + warp * WST; // this warp's GL slice; PL at +TILE_WST_G, AD at +2*TILE_WST_G
-    uint32_t* const wr = wg + 2 * TILE_WST_G;
-    bool pending = false; // this warp has bulk copies in flight that read its slice
+    const bool has_gl = GEN ? p.gl != nullptr : true, has_pl = GEN ? p.pl != nullptr : true, has_ad = GEN ? p.ad != nullptr : true;
+    const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4; // this warp's GL slice; PL at +TILE_WST_G words, AD at +2*TILE_WST_G
+    const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
+    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST, s_tot = s_smem + OFF_TOT;
+    const uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]);
 
     for (;;) {
-        __syncthreads(); // previous tile fully done with st / tot / cnt
-        if (tid == 0) s_tile = (int)atomicAdd(p.ticket, 1u);
-        for (int i = tid; i < TILE_MAX_SITES * 4; i += TILE_BLOCK) tot[i] = 0;
-        __syncthreads();
-        const int tile = s_tile;
+        __syncthreads(); // previous tile fully done (st / tot / cnt / chunk tickets); s_next published
+        const int tile = s_next;
         if (tile >= p.n_tiles) break;
         const int site0 = tile * T;
         const int nsl = min(T, p.n_sites - site0);
-        const int nv = nsl * S4; // virtual cells
+        const int nv = nsl * S4;            // virtual cells
+        const int nchunk = (nv + 31) >> 5;
         const int64_t cell0 = (int64_t)site0 * S;
         const uint8_t* __restrict__ gt_t = p.gt + cell0;
         int32_t* __restrict__ dp_t = p.dp + cell0;
+        const unsigned long long site_base = (unsigned long long)(p.first_site + site0);
 
-        // ---------------- phase A: sample, FORMAT/DP, per-site totals
-        for (int iv0 = 0; iv0 < nv; iv0 += TILE_BLOCK) {
-            const int iv = iv0 + tid;
-            int sl = (int)__umulhi((uint32_t)iv, inv_s4);
-            const int v = iv - sl * S4;
-            uint32_t ad = 0;
-            if (iv < nv && v < S) {
-                const int ci = sl * S + v;
-                ad = tile_sample_cell(R, p.first_site + site0 + sl, (uint32_t)v, gt_t[ci]);
-                dp_t[ci] = (int)__vsadu4(ad, 0u); // sum of the four byte counts
-            }
-            if (iv < nv) cnt[iv] = ad;
-            // a warp of 32 consecutive slots spans at most two sites (S4 >= 32): packed 16-bit fields,
-            // two masked REDUX rounds per site, then eight lanes add the eight sums
-            const int first = __shfl_sync(0xffffffffu, sl, 0);
-            const uint32_t w01 = __byte_perm(ad, 0u, 0x4140), w23 = __byte_perm(ad, 0u, 0x4342);
-            const bool in0 = sl == first;
-            const uint32_t a01 = __reduce_add_sync(0xffffffffu, in0 ? w01 : 0u), a23 = __reduce_add_sync(0xffffffffu, in0 ? w23 : 0u);
-            const uint32_t b01 = __reduce_add_sync(0xffffffffu, in0 ? 0u : w01), b23 = __reduce_add_sync(0xffffffffu, in0 ? 0u : w23);
-            if (lane < 8) {
-                const uint32_t w = (lane & 4) ? ((lane & 2) ? b23 : b01) : ((lane & 2) ? a23 : a01);
-                const uint32_t val = (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
-                const int ts = first + (lane >> 2);
-                if (val && ts < nsl) atomicAdd(&tot[ts * 4 + (lane & 3)], (int)val);
+        // ---------------- phase A: sample, FORMAT/DP, per-site base totals.  The genotypes of a warp's next chunk
+        // are loaded before the current chunk is processed.
+        {
+            int cur = tile_ticket_get(tile_ticket_issue(s_ctrA, lane));
+            int nxt = tile_ticket_get(tile_ticket_issue(s_ctrA, lane));
+            int iv = cur * 32 + lane;
+            int sl = (int)__umulhi((uint32_t)iv, inv_s4), v = iv - sl * S4;
+            bool real = iv < nv && v < S;
+            uint32_t gt = 0xFFu;
+            if (real) gt = gt_t[(uint32_t)(iv - sl * PAD)];
+            while (cur < nchunk) {
+                const int raw = tile_ticket_issue(s_ctrA, lane); // the chunk after next
+                const int iv2 = nxt * 32 + lane;
+                const int sl2 = (int)__umulhi((uint32_t)iv2, inv_s4), v2 = iv2 - sl2 * S4;
+                const bool real2 = iv2 < nv && v2 < S;
+                uint32_t gt2 = 0xFFu;
+                if (real2) gt2 = gt_t[(uint32_t)(iv2 - sl2 * PAD)];
+                const uint32_t ad = tile_sample_cell(p, R, site_base + (uint32_t)sl, (uint32_t)v, gt); // non-cells: missing genotype -> 0
+                if (real) dp_t[(uint32_t)(iv - sl * PAD)] = (int)__vsadu4(ad, 0u); // sum of the four byte counts
+                if (iv < nv) sts32(s_cnt + (uint32_t)iv * 4u, ad);
+                // site totals: packed 16-bit fields through REDUX; a chunk usually lies within one site
+                const int first = __shfl_sync(0xffffffffu, sl, 0);
+                const uint32_t w01 = __byte_perm(ad, 0u, 0x4140), w23 = __byte_perm(ad, 0u, 0x4342);
+                if (__all_sync(0xffffffffu, sl == first)) {
+                    const uint32_t a01 = __reduce_add_sync(0xffffffffu, w01), a23 = __reduce_add_sync(0xffffffffu, w23);
+                    if (lane < 4 && first < nsl) {
+                        const uint32_t w = (lane & 2) ? a23 : a01;
+                        const uint32_t val = (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
+                        if (val) atomicAdd(&tot[first * 4 + lane], (int)val);
+                    }
+                } else if (__all_sync(0xffffffffu, sl == first || sl == first + 1)) {
+                    const bool in0 = sl == first;
+                    const uint32_t a01 = __reduce_add_sync(0xffffffffu, in0 ? w01 : 0u), a23 = __reduce_add_sync(0xffffffffu, in0 ? w23 : 0u);
+                    const uint32_t b01 = __reduce_add_sync(0xffffffffu, in0 ? 0u : w01), b23 = __reduce_add_sync(0xffffffffu, in0 ? 0u : w23);
+                    if (lane < 8) {
+                        const uint32_t w = (lane & 4) ? ((lane & 2) ? b23 : b01) : ((lane & 2) ? a23 : a01);
+                        const uint32_t val = (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
+                        const int ts = first + (lane >> 2);
+                        if (val && ts < nsl) atomicAdd(&tot[ts * 4 + (lane & 3)], (int)val);
+                    }
+                } else if (sl < nsl) { // tiny sites: a chunk spans many
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int val = (int)((ad >> (8 * b)) & 0xFFu);
+                        if (val) atomicAdd(&tot[sl * 4 + b], val);
+                    }
+                }
+                cur = nxt; iv = iv2; sl = sl2; v = v2; real = real2; gt = gt2;
+                nxt = tile_ticket_get(raw);
             }
         }
         __syncthreads();
 
-        // ---------------- phase B: per-site record (vcfgl.cpp:396-404, 665-782, 806-843 INFO part)
-        int my_g = 0, my_r = 0; // this site's block sizes in 4-byte elements (padded to 16 B)
-        if (tid < nsl) {
-            const int* t = tot + tid * 4;
-            const int dp = t[0] + t[1] + t[2] + t[3];
-            vgl_site_out o;
-            o.skip_code = 0;
-            o.n_alleles = o.n_alleles_observed = o.n_genotypes = 0;
+        // ---------------- phase B (warp 0): per-site record (vcfgl.cpp:396-404, 665-782, 806-843 INFO part)
+        if (warp == 0) {
+            if (lane == 0) { // phase A is over for every warp: rearm its chunk tickets; next tile's ticket (tiles are independent)
+                s_ctr[0] = 0u;
+                s_next = (int)atomicAdd(p.ticket, 1u);
+            }
+            int my_g = 0, my_r = 0; // this site's block sizes in 4-byte elements (padded to 16 B)
+            if (lane < nsl) {
+                int t[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o.alleles2acgt[i] = o.acgt2alleles[i] = -1;
-            o.info_dp = dp;
+                for (int b = 0; b < 4; ++b) { t[b] = tot[lane * 4 + b]; tot[lane * 4 + b] = 0; }
+                const int dp = t[0] + t[1] + t[2] + t[3];
+                vgl_site_out o;
+                o.skip_code = 0;
+                o.n_alleles = o.n_alleles_observed = o.n_genotypes = 0;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { o.info_ad[i] = o.info_adf[i] = o.info_adr[i] = 0; o.qs[i] = 0.0f; }
+                for (int i = 0; i < 8; ++i) o.alleles2acgt[i] = o.acgt2alleles[i] = -1;
+                o.info_dp = dp;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o.i16[i] = 0.0f;
-            o._pad = 0;
-            o.g_off = o.r_off = 0; // patched after the look-back
-            int b2a[5] = {-1, -1, -1, -1, -1};
-            uint32_t a2b = 0xFFFFFFFFu;
-            if (dp == 0) {
-                if (p.rm_empty) o.skip_code = -4;
-                else if (!p.do_gvcf) {
-                    if (p.do_unobserved <= 2) { o.n_alleles = 1; o.n_genotypes = 1; o.n_alleles_observed = 0; }
-                    else if (p.do_unobserved == 3) { o.n_alleles = 4; o.n_genotypes = 10; o.n_alleles_observed = 4; }
-                    else { o.n_alleles = 5; o.n_genotypes = 15; o.n_alleles_observed = 4; }
-                }
-            } else {
-                int n_obs = 0;
+                for (int i = 0; i < 5; ++i) { o.info_ad[i] = o.info_adf[i] = o.info_adr[i] = 0; o.qs[i] = 0.0f; }
 #pragma unroll
-                for (int b = 0; b < 4; ++b) n_obs += t[b] > 0;
-                if (p.rm_invar_sim && n_obs == 1) {
-                    o.skip_code = -3;
+                for (int i = 0; i < 16; ++i) o.i16[i] = 0.0f;
+                o._pad = 0;
+                o.g_off = o.r_off = 0; // patched after the look-back
+                int b2a[5] = {-1, -1, -1, -1, -1};
+                uint32_t a2b = 0xFFFFFFFFu;
+                if (dp == 0) {
+                    if (p.rm_empty) o.skip_code = -4;
+                    else if (!p.do_gvcf) {
+                        if (p.do_unobserved <= 2) { o.n_alleles = 1; o.n_genotypes = 1; o.n_alleles_observed = 0; }
+                        else if (p.do_unobserved == 3) { o.n_alleles = 4; o.n_genotypes = 10; o.n_alleles_observed = 4; }
+                        else { o.n_alleles = 5; o.n_genotypes = 15; o.n_alleles_observed = 4; }
+                    }
                 } else {
-                    int n_alleles = 0;
+                    int n_obs = 0;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) { // stable sort by INFO/AD, descending (vcfgl.cpp:700-718)
-                        int rank = 0;
+                    for (int b = 0; b < 4; ++b) n_obs += t[b] > 0;
+                    if (p.rm_invar_sim && n_obs == 1) {
+                        o.skip_code = -3;
+                    } else {
+                        int n_alleles = 0;
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) rank += (t[x] > t[b]) || (t[x] == t[b] && x < b);
-                        if (t[b] > 0 || explode) {
-                            b2a[b] = rank;
-                            o.acgt2alleles[b] = (int8_t)rank;
-                            a2b = (a2b & ~(0xFu << (4 * rank))) | ((uint32_t)b << (4 * rank));
+                        for (int b = 0; b < 4; ++b) { // stable sort by INFO/AD, descending (vcfgl.cpp:700-718)
+                            int rank = 0;
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) rank += (t[x] > t[b]) || (t[x] == t[b] && x < b);
+                            if (t[b] > 0 || explode) {
+                                b2a[b] = rank;
+                                o.acgt2alleles[b] = (int8_t)rank;
+                                a2b = (a2b & ~(0xFu << (4 * rank))) | ((uint32_t)b << (4 * rank));
+                                ++n_alleles;
+                            }
+                        }
+                        o.n_alleles_observed = n_alleles;
+                        if (add_unobs) {
+                            b2a[4] = n_alleles;
+                            o.acgt2alleles[4] = (int8_t)n_alleles;
+                            a2b = (a2b & ~(0xFu << (4 * n_alleles))) | (4u << (4 * n_alleles));
                             ++n_alleles;
                         }
-                    }
-                    o.n_alleles_observed = n_alleles;
-                    if (add_unobs) {
-                        b2a[4] = n_alleles;
-                        o.acgt2alleles[4] = (int8_t)n_alleles;
-                        a2b = (a2b & ~(0xFu << (4 * n_alleles))) | (4u << (4 * n_alleles));
-                        ++n_alleles;
-                    }
-                    o.n_alleles = n_alleles;
-                    o.n_genotypes = n_alleles * (n_alleles + 1) / 2;
+                        o.n_alleles = n_alleles;
+                        o.n_genotypes = n_alleles * (n_alleles + 1) / 2;
 #pragma unroll
-                    for (int a = 0; a < 5; ++a) {
-                        const int b = (int)((a2b >> (4 * a)) & 0xF);
-                        o.alleles2acgt[a] = b == 0xF ? (int8_t)-1 : (int8_t)b;
-                        if (a < n_alleles && b < 4 && (p.tag_mask & VGL_TAG_INFO_AD)) o.info_ad[a] = t[b];
+                        for (int a = 0; a < 5; ++a) {
+                            const int b = (int)((a2b >> (4 * a)) & 0xF);
+                            o.alleles2acgt[a] = b == 0xF ? (int8_t)-1 : (int8_t)b;
+                            if (a < n_alleles && b < 4 && (p.tag_mask & VGL_TAG_INFO_AD)) o.info_ad[a] = t[b];
+                        }
                     }
                 }
-            }
-            // dp == 0 sites keep all-missing blocks: their "alleles" carry no base (a2b stays 0xF..F -> counts read as 0)
-            const bool keep = o.skip_code == 0 && o.n_alleles > 0;
-            TSite ts;
-            const uint64_t pm = make_pairmap(b2a);
-            bool all15 = true;
+                // dp == 0 sites keep all-missing blocks: their "alleles" carry no base (counts read as 0)
+                const bool keep = o.skip_code == 0 && o.n_alleles > 0;
+                TSite ts;
+                const uint64_t pm = make_pairmap(b2a);
+                bool all15 = true;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                uint32_t x = 0;
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t x = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int pair = 4 * w + k;
-                    uint32_t slot = pair < 15 ? (uint32_t)((pm >> (4 * pair)) & 0xF) : 0xFu;
-                    if (pair < 15 && slot == 0xFu) all15 = false;
-                    x |= (slot == 0xFu ? 0xFFu : slot * 4u) << (8 * k);
+                    for (int k = 0; k < 4; ++k) {
+                        const int pair = 4 * w + k;
+                        uint32_t slot = pair < 15 ? (uint32_t)((pm >> (4 * pair)) & 0xF) : 0xFu;
+                        if (pair < 15 && slot == 0xFu) all15 = false;
+                        x |= (slot == 0xFu ? 0xFFu : slot * 4u) << (8 * k);
+                    }
+                    ts.slot[w] = x;
                 }
-                ts.slot[w] = x;
-            }
-            // alleles without a base (none / dp == 0 placeholder) read byte 4 = 0 in the AD permute
-            uint32_t a2b4 = 0;
+                // AD permute selectors: allele a reads byte (base) of the packed counts; alleles without a base read byte 4 = 0
+                uint32_t sel[5];
 #pragma unroll
-            for (int a = 0; a < 5; ++a) {
-                const uint32_t b = (a2b >> (4 * a)) & 0xF;
-                a2b4 |= (b < 4 ? b : 4u) << (4 * a);
+                for (int a = 0; a < 5; ++a) {
+                    const uint32_t b = (a2b >> (4 * a)) & 0xF;
+                    sel[a] = (b < 4 ? b : 4u) | 0x4440u;
+                }
+                ts.sel01 = sel[0] | (sel[1] << 16);
+                ts.sel23 = sel[2] | (sel[3] << 16);
+                ts.sel4 = sel[4];
+                ts.AG = keep ? ((uint32_t)o.n_alleles | ((uint32_t)o.n_genotypes << 8) | ((all15 && dp > 0) ? 1u << 16 : 0u)) : 0u;
+                if (keep) {
+                    my_g = (S * o.n_genotypes + 3) & ~3;
+                    my_r = (S * o.n_alleles + 3) & ~3;
+                }
+                // inclusive scan of the block sizes over the tile's sites (<= 32: this warp)
+                ts.g_rel = ts.r_rel = ts.g_end = ts.r_end = 0;
+                st[lane] = ts;
+                p.sites[site0 + lane] = o;
             }
-            ts.a2b = a2b4;
-            ts.AG = keep ? ((uint32_t)o.n_alleles | ((uint32_t)o.n_genotypes << 8) | ((all15 && dp > 0) ? 1u << 16 : 0u)) : 0u;
-            ts.g_rel = ts.r_rel = 0;
-            if (keep) {
-                my_g = (S * o.n_genotypes + 3) & ~3;
-                my_r = (S * o.n_alleles + 3) & ~3;
-            }
-            st[tid] = ts;
-            p.sites[site0 + tid] = o;
-        }
-        // exclusive scan of the tile's block sizes: at most 64 sites -> warps 0..1
-        int ig = my_g, ir = my_r;
-        if (tid < TILE_MAX_SITES) {
+            int ig = my_g, ir = my_r;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const int tg = __shfl_up_sync(0xffffffffu, ig, off);
                 const int tr = __shfl_up_sync(0xffffffffu, ir, off);
                 if (lane >= off) { ig += tg; ir += tr; }
             }
-            if (lane == 31) { wsum[2 * warp] = ig; wsum[2 * warp + 1] = ir; }
-        }
-        __syncthreads();
-        if (tid < TILE_MAX_SITES) {
-            const int pre_g = warp ? wsum[0] : 0, pre_r = warp ? wsum[1] : 0;
-            const int tile_g = wsum[0] + wsum[2], tile_r = wsum[1] + wsum[3];
-            if (tid < nsl) {
-                st[tid].g_rel = pre_g + ig - my_g;
-                st[tid].r_rel = pre_r + ir - my_r;
+            const int tile_g = __shfl_sync(0xffffffffu, ig, 31), tile_r = __shfl_sync(0xffffffffu, ir, 31);
+            if (lane < nsl) {
+                st[lane].g_rel = ig - my_g;
+                st[lane].r_rel = ir - my_r;
+                st[lane].g_end = ig;
+                st[lane].r_end = ir;
             }
-            // decoupled look-back (warp 0): base offset of this tile = total size of all earlier tiles
-            if (warp == 0) {
-                if (lane == 0) st_state_t(p.tile_state + tile, TS_PACK(1, tile_g, tile_r));
-                int64_t bg = 0, br = 0;
-                int look = tile - 1;
-                while (look >= 0) {
-                    const int idx = look - lane;
-                    unsigned long long w = TS_PACK(2, 0, 0); // lanes before tile 0 act as a zero inclusive prefix
-                    if (idx >= 0) {
-                        do { w = ld_state_t(p.tile_state + idx); } while (TS_FLAG(w) == 0);
-                    }
-                    const unsigned incl = __ballot_sync(0xffffffffu, TS_FLAG(w) == 2);
-                    const int stop = incl ? (__ffs(incl) - 1) : 31; // nearest inclusive prefix
-                    int64_t g = lane <= stop ? TS_G(w) : 0, r = lane <= stop ? TS_R(w) : 0;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        g += __shfl_xor_sync(0xffffffffu, g, off);
-                        r += __shfl_xor_sync(0xffffffffu, r, off);
-                    }
-                    bg += g;
-                    br += r;
-                    if (incl) break;
-                    look -= 32;
-                }
-                if (lane == 0) {
-                    st_state_t(p.tile_state + tile, TS_PACK(2, bg + tile_g, br + tile_r));
-                    s_base[0] = bg;
-                    s_base[1] = br;
-                    s_tile_g = tile_g;
-                    s_tile_r = tile_r;
-                    if (tile == p.n_tiles - 1) { p.totals[0] = bg + tile_g; p.totals[1] = br + tile_r; }
-                }
+            // Tile bases are fixed: tile t starts at t * T * (padded size of a 15-genotype / 5-allele block).  Blocks are
+            // compact within a tile, so every chunk's span is contiguous; the only holes are at tile ends, behind sites
+            // with fewer alleles or skipped ones.  No tile waits for another one (a running prefix over all earlier
+            // tiles -- decoupled look-back -- left every CTA idle for ~40% of its time on this workload).
+            const int64_t bg = (int64_t)tile * T * ((S * 15 + 3) & ~3), br = (int64_t)tile * T * ((S * 5 + 3) & ~3);
+            if (lane == 0) {
+                s_base[0] = bg;
+                s_base[1] = br;
+                s_ctr[1] = 0u;
+                if (tile == p.n_tiles - 1) { p.totals[0] = bg + tile_g; p.totals[1] = br + tile_r; }
+            }
+            if (lane < nsl) {
+                p.sites[site0 + lane].g_off = bg + (ig - my_g);
+                p.sites[site0 + lane].r_off = br + (ir - my_r);
             }
         }
         __syncthreads();
-        if (tid < nsl) {
-            p.sites[site0 + tid].g_off = s_base[0] + st[tid].g_rel;
-            p.sites[site0 + tid].r_off = s_base[1] + st[tid].r_rel;
-        }
 
-        // ---------------- phase C: score + emit, one warp per 32 virtual cells
-        const int tile_g = s_tile_g, tile_r = s_tile_r;
-        float* const gl_t = p.gl ? p.gl + s_base[0] : nullptr;
-        int32_t* const pl_t = p.pl ? p.pl + s_base[0] : nullptr;
-        int32_t* const ad_t = p.ad ? p.ad + s_base[1] : nullptr;
-        for (int iv0 = warp * 32; iv0 < nv; iv0 += TILE_BLOCK) {
-            const int iv = iv0 + lane;
+        // ---------------- phase C: score + emit, one warp per chunk of 32 virtual cells
+        float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
+        int32_t* const pl_t = has_pl ? p.pl + s_base[0] : nullptr;
+        int32_t* const ad_t = has_ad ? p.ad + s_base[1] : nullptr;
+        for (int cur = tile_ticket_get(tile_ticket_issue(s_ctrC, lane)), raw; cur < nchunk; cur = tile_ticket_get(raw)) {
+            raw = tile_ticket_issue(s_ctrC, lane); // next chunk's ticket: resolved after this chunk
+            const int iv = cur * 32 + lane;
             int sl = (int)__umulhi((uint32_t)iv, inv_s4);
             int v = iv - sl * S4;
             if (sl >= nsl) { sl = nsl - 1; v = S4; } // past the tile: sits at the end of the last block
-            const TSite ts = st[sl];
-            const int A = (int)(ts.AG & 0xFF), G = (int)((ts.AG >> 8) & 0xFF);
+            const uint4 t1 = lds128(s_st + (uint32_t)sl * 48u + 16u); // g_rel, r_rel, AG, sel4
+            const uint4 t2 = lds128(s_st + (uint32_t)sl * 48u + 32u); // sel01, sel23, g_end, r_end
+            const int A = (int)(t1.z & 0xFF), G = (int)__byte_perm(t1.z, 0u, 0x4441);
             const bool live = v < S && G > 0;
             const int vv = min(v, S);
-            const int gpos = ts.g_rel + vv * G, rpos = ts.r_rel + vv * A;
-            const int gend = v < S ? gpos + G : ts.g_rel + ((S * G + 3) & ~3);
-            const int rend = v < S ? rpos + A : ts.r_rel + ((S * A + 3) & ~3);
+            const int gpos = (int)t1.x + vv * G, rpos = (int)t1.y + vv * A;
+            const int gend = v < S ? gpos + G : (int)t2.z;
+            const int rend = v < S ? rpos + A : (int)t2.w;
             const int g_lo = __shfl_sync(0xffffffffu, gpos, 0), g_hi = __shfl_sync(0xffffffffu, gend, 31);
             const int r_lo = __shfl_sync(0xffffffffu, rpos, 0), r_hi = __shfl_sync(0xffffffffu, rend, 31);
-            char* const cell_g = reinterpret_cast<char*>(wg + (gpos - g_lo));
-            uint32_t* const cell_r = wr + (rpos - r_lo);
-            if (pending) { // the previous copies must have finished reading the slice
-                if (lane == 0) bulk_wait_read();
-                __syncwarp();
+            // cells that emit nothing (padding slots, skipped sites, past the tile) compute along and store into a scratch cell
+            const uint32_t cell_g = live ? s_wg + (uint32_t)(gpos - g_lo) * 4u : s_wg + TILE_G_TRASH * 4u;
+            const uint32_t cell_r = live ? s_wr + (uint32_t)(rpos - r_lo) * 4u : s_wr + TILE_R_TRASH * 4u;
+            const uint32_t c4 = live ? lds32(s_cnt + (uint32_t)iv * 4u) : 0u;
+            const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
+            bulk_wait_read(); // this warp's previous copies (issued by lane 0) must have finished reading the slice
+            __syncwarp();
+            const int c0 = (int)__byte_perm(c4, 0u, 0x4440), c1 = (int)__byte_perm(c4, 0u, 0x4441);
+            const int c2 = (int)__byte_perm(c4, 0u, 0x4442), c3 = (int)__byte_perm(c4, 0u, 0x4443);
+            const int n = (int)__vsadu4(c4, 0u);
+            float q[15];
+            m1f_scores_noclamp(n, c0, c1, c2, c3, p.m1_bsum, p.m1_het, q);
+            if (__all_sync(0xffffffffu, !live || (t1.z >> 16))) tile_emit_cell<true>(q, slot, cell_g, has_gl, has_pl);
+            else tile_emit_cell<false>(q, slot, cell_g, has_gl, has_pl);
+            if (has_ad) { // AD in allele order (vcfgl.cpp:806-831): byte permute, selector 4 reads 0
+                sts32(cell_r, __byte_perm(c4, 0u, t2.x));
+                if (A > 1) sts32(cell_r + 4, __byte_perm(c4, 0u, t2.x >> 16));
+                if (A > 2) sts32(cell_r + 8, __byte_perm(c4, 0u, t2.y));
+                if (A > 3) sts32(cell_r + 12, __byte_perm(c4, 0u, t2.y >> 16));
+                if (A > 4) sts32(cell_r + 16, __byte_perm(c4, 0u, t1.w));
             }
-            const uint32_t c4 = live ? cnt[iv] : 0u;
-            const int c0 = (int)(c4 & 0xFF), c1 = (int)((c4 >> 8) & 0xFF), c2 = (int)((c4 >> 16) & 0xFF), c3 = (int)(c4 >> 24);
-            const int n = c0 + c1 + c2 + c3;
-            if (live) {
-                float q[15];
-                m1f_scores_noclamp(n, c0, c1, c2, c3, p.m1_bsum, p.m1_het, q);
-                if (ts.AG >> 16) tile_emit_cell<true>(q, ts, cell_g, has_gl, has_pl);
-                else tile_emit_cell<false>(q, ts, cell_g, has_gl, has_pl);
-                if (has_ad) { // AD in allele order (vcfgl.cpp:806-831): byte permute, selector 4 reads 0
-#pragma unroll
-                    for (int a = 0; a < 5; ++a)
-                        if (a < A) cell_r[a] = __byte_perm(c4, 0u, ((ts.a2b >> (4 * a)) & 0xFu) | 0x4440u);
-                }
-                if (n == 0) { // gl_methods.cpp:359-366
+            if (live && n == 0) { // gl_methods.cpp:359-366
 #pragma unroll 1
-                    for (int g = 0; g < G; ++g) {
-                        reinterpret_cast<uint32_t*>(cell_g)[g] = VGL_F32_MISSING_BITS;
-                        reinterpret_cast<uint32_t*>(cell_g)[TILE_WST_G + g] = (uint32_t)VGL_I32_MISSING;
-                    }
+                for (int g = 0; g < G; ++g) {
+                    sts32(cell_g + 4 * g, VGL_F32_MISSING_BITS);
+                    sts32(cell_g + 4 * (TILE_WST_G + g), (uint32_t)VGL_I32_MISSING);
                 }
-            } else if (v == S) { // first dead slot of a site: zero the block's padding
+            }
+            if (v == S && G > 0) { // first padding slot of a site: zero the block's padding
+                const uint32_t pg = s_wg + (uint32_t)(gpos - g_lo) * 4u, pr = s_wr + (uint32_t)(rpos - r_lo) * 4u;
 #pragma unroll 1
-                for (int g = gpos; g < gend; ++g) {
-                    reinterpret_cast<uint32_t*>(cell_g)[g - gpos] = 0u;
-                    reinterpret_cast<uint32_t*>(cell_g)[TILE_WST_G + g - gpos] = 0u;
+                for (int g = 0; g < gend - gpos; ++g) {
+                    sts32(pg + 4 * g, 0u);
+                    sts32(pg + 4 * (TILE_WST_G + g), 0u);
                 }
 #pragma unroll 1
-                for (int a = rpos; a < rend; ++a) cell_r[a - rpos] = 0u;
+                for (int a = 0; a < rend - rpos; ++a) sts32(pr + 4 * a, 0u);
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
                 const uint32_t gb = (uint32_t)(g_hi - g_lo) * 4u, rb = (uint32_t)(r_hi - r_lo) * 4u;
                 if (gb) {
-                    if (has_gl) bulk_store(gl_t + g_lo, smem_u32(wg), gb);
-                    if (has_pl) bulk_store(pl_t + g_lo, smem_u32(wg + TILE_WST_G), gb);
+                    if (has_gl) bulk_store(gl_t + g_lo, s_wg, gb);
+                    if (has_pl) bulk_store(pl_t + g_lo, s_wg + TILE_WST_G * 4, gb);
                 }
-                if (rb && has_ad) bulk_store(ad_t + r_lo, smem_u32(wr), rb);
+                if (rb && has_ad) bulk_store(ad_t + r_lo, s_wr, rb);
                 bulk_commit();
             }
-            pending = true;
         }
-        (void)tile_g;
-        (void)tile_r;
     }
-    if (lane == 0) bulk_wait_all(); // global writes of this warp's last copies complete before exit
+    bulk_wait_all(); // global writes of this warp's last copies complete before exit
+}
+
+static size_t tile_dyn_smem(int S)
+{
+    const int S4 = (S + 3) & ~3;
+    const int cap = S4 > TILE_CELLS ? S4 : TILE_CELLS;
+    return 2048 + 4096 + (size_t)TILE_WARPS * (2 * TILE_WST_G + TILE_WST_R) * 4 + TILE_MAX_SITES * sizeof(TSite) + TILE_MAX_SITES * 16 +
+           (size_t)cap * 4;
+}
+
+template <bool GEN>
+static void launch_tile_t(const DevParams& p, cudaStream_t st, int n_sms)
+{
+    const size_t dyn = tile_dyn_smem(p.S);
+    cudaFuncSetAttribute(k_tile_m1f<GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m1f<GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN>, TILE_BLOCK, dyn);
+    if (per_sm < 1) per_sm = 1;
+    int grid = n_sms * per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    k_tile_m1f<GEN><<<grid, TILE_BLOCK, dyn, st>>>(p);
 }
 
 void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms)
 {
-    const int S4 = (p.S + 3) & ~3;
-    const int cap = S4 > TILE_CELLS ? S4 : TILE_CELLS;
-    const size_t dyn = 2048 + 4096 + (size_t)TILE_WARPS * (2 * TILE_WST_G + TILE_WST_R) * 4 + TILE_MAX_SITES * sizeof(TSite) +
-                       TILE_MAX_SITES * 16 + (size_t)cap * 4;
-    cudaFuncSetAttribute(k_tile_m1f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_tile_m1f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f, TILE_BLOCK, dyn);
-    if (per_sm < 1) per_sm = 1;
-    int grid = n_sms * per_sm;
-    if (grid > p.n_tiles) grid = p.n_tiles;
-    k_tile_m1f<<<grid, TILE_BLOCK, dyn, st>>>(p);
+    if (p.gl && p.pl && p.ad) launch_tile_t<false>(p, st, n_sms);
+    else launch_tile_t<true>(p, st, n_sms);
 }
 
 // largest S the tile kernel takes: one site's counts must fit the shared-memory cache

@@ -40,6 +40,7 @@ struct DevParams {
     int64_t first_site;
     int64_t n_cells;
     uint32_t k0, k1; // Philox key
+    uint32_t rk[20]; // its ten round keys {k0 + r*W0, k1 + r*W1}
     // simulation parameters
     int32_t depth_mode;
     double depth_mean;
