@@ -215,8 +215,11 @@ __device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const uint4
 // Issue (lane 0's atomic) and use (broadcast) are split so that the atomic's latency overlaps a whole chunk.
 __device__ __forceinline__ int tile_ticket_issue(uint32_t s_ctr, int lane)
 {
+    // one predicated ATOMS by lane 0.  The caller adds a zero it loaded from shared memory to the address: with a
+    // provably warp-uniform address ptxas rewrites the atomic into its leader-election / aggregate / broadcast
+    // sequence, whose internal shuffle waits for the atomic right away.
     int c = 0;
-    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(s_ctr) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], 1;\n\t}" : "+r"(c) : "r"(s_ctr), "r"(lane) : "memory");
     return c;
 }
 __device__ __forceinline__ int tile_ticket_get(int raw) { return __shfl_sync(0xffffffffu, raw, 0); }
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
     __shared__ int64_t s_base[2];
     __shared__ int s_next;
     __shared__ uint32_t s_ctr[2];
+    __shared__ uint32_t s_zero[32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.S, S4 = (S + 3) & ~3, PAD = S4 - S, T = p.sites_per_tile;
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
         s_next = (int)atomicAdd(p.ticket, 1u);
         s_ctr[0] = s_ctr[1] = 0u;
     }
+    if (tid < 32) s_zero[tid] = 0u;
     TileRng R;
     R.s_alias = s_smem;
     R.s_cdf_e = s_smem + 2048;
@@ -260,12 +265,19 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4; // this warp's GL slice; PL at +TILE_WST_G words, AD at +2*TILE_WST_G
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
     const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST, s_tot = s_smem + OFF_TOT;
-    const uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]);
+    uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]);
+    bool first_tile = true;
 
     for (;;) {
         __syncthreads(); // previous tile fully done (st / tot / cnt / chunk tickets); s_next published
         const int tile = s_next;
         if (tile >= p.n_tiles) break;
+        if (first_tile) { // see tile_ticket_issue
+            const uint32_t opaque_zero = lds32(smem_u32(&s_zero[lane])); // 0, but not provably the same in every lane
+            s_ctrA += opaque_zero;
+            s_ctrC += opaque_zero;
+            first_tile = false;
+        }
         const int site0 = tile * T;
         const int nsl = min(T, p.n_sites - site0);
         const int nv = nsl * S4;            // virtual cells
