@@ -44,6 +44,17 @@ WORKLOAD = ("cfg2: 100 samples x 1M sites (steps of %d sites), Poisson depth 10,
             "tags GL+PL+AD+DP, seed 42" % BATCH_SITES)
 
 
+def set_workload(name):
+    """cfg2 is the bench line (BASELINE.json configs[1]); cfg5 is the shape of the scaling config (10 000 samples,
+    depth 30) at a per-step size that fits one GPU -- used for profiling and reported separately."""
+    global N_SAMPLES, BATCH_SITES, VCFGL_ARGS, WORKLOAD
+    if name == "cfg5":
+        N_SAMPLES, BATCH_SITES = 10000, 4440   # 5 x (148 SMs x 6 resident CTAs) tiles
+        VCFGL_ARGS = "-d 30 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1".split()
+        WORKLOAD = ("cfg5 shape: 10000 samples, steps of %d sites, Poisson depth 30, e=0.01, GL model 1, "
+                    "tags GL+PL+AD+DP, seed 42" % BATCH_SITES)
+
+
 def measured_peak():
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -362,7 +373,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: stop after the kernel-side loop")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"])
     opt = ap.parse_args()
+    set_workload(opt.workload)
     opt.warmup = max(opt.warmup, 3) if opt.impl == "b200" else opt.warmup
     if opt.impl == "reference":
         reference_arm(opt)

@@ -27,6 +27,7 @@ CASES = {
     "eq1": ("--seed 9 -d 5 -e 0.05 -eq 1 -bv 1e-3 -GL 1 -addPL 1 -addFormatAD 1 --adjust-qs 1", 64, 300),
     "s1": ("--seed 10 -d 4 -e 0.05 -GL 1 -addPL 1 -addFormatAD 1", 1, 3000),
     "s1300": ("--seed 11 -d 8 -e 0.01 -GL 1 -addPL 1 -addFormatAD 1", 1300, 40),
+    "s2501_scratch": ("--seed 14 -d 3 -e 0.02 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1", 2501, 12),
     "e_high": ("--seed 12 -d 12 -e 0.9 -GL 1 -addPL 1 -addFormatAD 1", 33, 300),
     "deep": ("--seed 13 -d 280 -e 0.01 -GL 1 -addPL 1 -addFormatAD 1", 6, 60),
 }

@@ -73,7 +73,7 @@ struct vgl_ctx {
     // device tables
     int use_fused = 0, use_tile = 0, n_sms = 148, fast_div = 0;
     unsigned long long *d_pois = nullptr, *d_alias = nullptr;
-    uint32_t* d_errcdf = nullptr;
+    uint32_t *d_errcdf = nullptr, *d_cnt_scratch = nullptr;
     int pois_n = 0;
     double *d_lut = nullptr, *d_m1_bsum = nullptr, *d_m1_het = nullptr, *d_fk = nullptr, *d_beta = nullptr, *d_depth_means = nullptr;
     std::vector<Slot> slots;
@@ -195,7 +195,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch);
     delete ctx;
 }
 
@@ -274,6 +274,8 @@ static int create_impl(vgl_ctx* ctx)
     if (ctx->use_tile) {
         CK(upload(&ctx->d_alias, alias));
         CK(upload(&ctx->d_errcdf, binomial_cdf4_u32(p.error_rate)));
+        const size_t words = tile_m1f_scratch_words(p.n_samples, ctx->n_sms);
+        if (words) CK(cudaMalloc((void**)&ctx->d_cnt_scratch, words * 4));
     }
 
     // ---- slots
@@ -296,7 +298,10 @@ static int create_impl(vgl_ctx* ctx)
         CK(cudaMalloc((void**)&s.d_sites, B * sizeof(vgl_site_out)));
         CK(cudaMalloc((void**)&s.d_totals, 4 * sizeof(int64_t)));
         CK(cudaMalloc((void**)&s.d_pairmap, B * sizeof(uint64_t)));
-        if (ctx->use_fused) CK(cudaMalloc((void**)&s.d_tile_state, (B + 2) * sizeof(unsigned long long)));
+        if (ctx->use_fused) {
+            CK(cudaMalloc((void**)&s.d_tile_state, (B + 2) * sizeof(unsigned long long)));
+            CK(cudaMemset(s.d_tile_state, 0, (B + 2) * sizeof(unsigned long long)));
+        }
         CK(cudaMemset(s.d_totals, 0, 4 * sizeof(int64_t)));
         if (t & VGL_TAG_GL) CK(cudaMalloc((void**)&s.d_gl, ctx->g_cap * 4));
         if (t & VGL_TAG_GP) CK(cudaMalloc((void**)&s.d_gp, ctx->g_cap * 4));
@@ -440,11 +445,13 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.celltail = s.d_celltail;
     p.sites = s.d_sites;
     p.totals = s.d_totals;
+    p.totals_host = s.h_totals; // pinned + mapped (UVA): the tile kernel also posts the totals there, sparing the tiny D2H copy
     p.pairmap = s.d_pairmap;
     p.pois_cdf = ctx->d_pois;
     p.pois_n = ctx->pois_n;
     p.pois_alias = ctx->d_alias;
     p.err_cdf = ctx->d_errcdf;
+    p.cnt_scratch = ctx->d_cnt_scratch;
     {
         int T = 1024 / (int)S;
         T = T < 1 ? 1 : (T > 128 ? 128 : T);
@@ -452,7 +459,7 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
         p.sites_per_tile = T;
         p.n_tiles = (n_sites + T - 1) / T;
         p.tile_state = s.d_tile_state;
-        p.ticket = s.d_tile_state ? reinterpret_cast<uint32_t*>(s.d_tile_state + p.n_tiles) : nullptr;
+        p.ticket = s.d_tile_state ? reinterpret_cast<uint32_t*>(s.d_tile_state + (ctx->use_tile ? 0 : p.n_tiles)) : nullptr;
     }
     p.status = reinterpret_cast<int32_t*>(s.d_totals + 2);
     p.gl = s.d_gl; p.pl = s.d_pl; p.gp = s.d_gp;
@@ -475,7 +482,8 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     fill_params(ctx, s, first_site_id, n_sites, p);
     CK(cudaEventRecord(s.ev[EV_START], st));
     if (!(flags & VGL_SUBMIT_GT_ON_DEVICE)) CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(s.d_totals, 0, 4 * sizeof(int64_t), st));
+    const bool tile_launch = ctx->use_tile && !rp; // the tile kernel rearms its own ticket and writes the totals itself
+    if (!tile_launch) CK(cudaMemsetAsync(s.d_totals, 0, 4 * sizeof(int64_t), st));
     if (rp) {
         if (!rp->depths || !rp->read_offsets || (rp->n_reads > 0 && !rp->bases)) return fail(ctx, VGL_EINVAL, "replay: depths/read_offsets/bases required");
         if (prm.error_qs == 2 && rp->n_reads > 0 && !rp->qs) return fail(ctx, VGL_EINVAL, "replay: per-read qs required with --error-qs 2");
@@ -509,7 +517,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         }
     }
     const bool fused = ctx->use_fused && !rp;
-    if (fused) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
+    if (fused && !tile_launch) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));
     if (fused) {
         // one kernel does everything; its time is reported as VGL_T_EMIT (SIM / SITE / SCAN = 0)
@@ -533,7 +541,8 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     }
     CK(cudaGetLastError());
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (tile_launch) s.h_totals[2] = 0; // status word: the tile kernel raises no device-side errors
+    else CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_META], st));
     s.submitted = true;

@@ -37,6 +37,7 @@ namespace vgl {
 #endif
 #define TILE_WST_G 528       // 4-byte elements per warp and G-shaped plane: 32 cells x 15 + pads (<= 3 per site end) <= 504, then a scratch cell
 #define TILE_WST_R 192       // 32 cells x 5 + pads <= 184, then a scratch cell
+#define TILE_SCRATCH_CTAS_PER_SM 8 // BIG variant: resident CTAs per SM the count scratch is sized for
 #define TILE_G_TRASH 512
 #define TILE_R_TRASH 184
 
@@ -163,12 +164,18 @@ __device__ __forceinline__ uint32_t tile_sample_cell(const DevParams& p, const T
     const uint32_t ad1 = tile_place_error(ad, b1.y, g0, g1, rem0, rem); // straight-line first error (nearly every warp has one)
     if (E > 0) ad = ad1;
     if (E > 1) {
-        Key key;
-        key.k0 = p.k0; key.k1 = p.k1;
-        Stream st;
-        st.init(key, (int64_t)site, sample, 0, P_COUNTS);
-        st.block = 10;
-        for (int i = 1; i < E; ++i) ad = tile_place_error(ad, i == 1 ? b1.z : i == 2 ? b1.w : st.next(), g0, g1, rem0, rem);
+        ad = tile_place_error(ad, b1.z, g0, g1, rem0, rem);
+        if (E > 2) {
+            ad = tile_place_error(ad, b1.w, g0, g1, rem0, rem);
+            if (E > 3) {
+                Key key;
+                key.k0 = p.k0; key.k1 = p.k1;
+                Stream st;
+                st.init(key, (int64_t)site, sample, 0, P_COUNTS);
+                st.block = 10;
+                for (int i = 3; i < E; ++i) ad = tile_place_error(ad, st.next(), g0, g1, rem0, rem);
+            }
+        }
     }
     return ad;
 }
@@ -224,7 +231,9 @@ __device__ __forceinline__ int tile_ticket_issue(uint32_t s_ctr, int lane)
 }
 __device__ __forceinline__ int tile_ticket_get(int raw) { return __shfl_sync(0xffffffffu, raw, 0); }
 
-template <bool GEN>
+// GEN: any subset of the GL / PL / AD planes (else all three); BIG: a site's counts do not fit the shared-memory
+// cache -> they pass through a per-CTA scratch row in global memory (L2-resident), read one chunk ahead
+template <bool GEN, bool BIG>
 __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -239,8 +248,13 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
     __shared__ uint32_t s_ctr[2];
     __shared__ uint32_t s_zero[32];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = p.S, S4 = (S + 3) & ~3, PAD = S4 - S, T = p.sites_per_tile;
+    // thread ids and the sample count are pinned in registers (volatile moves cannot be rematerialised): ptxas
+    // otherwise re-reads SR_TID / the constant bank inside the chunk loops and stalls on their latency
+    int tid, S;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("mov.u32 %0, %1;" : "=r"(S) : "r"(p.S));
+    const int lane = tid & 31, warp = tid >> 5;
+    const int S4 = (S + 3) & ~3, PAD = S4 - S, T = p.sites_per_tile;
     const uint32_t s_smem = smem_u32(tile_smem);
     for (int i = tid; i < 256; i += TILE_BLOCK) {
         reinterpret_cast<uint2*>(tile_smem)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
@@ -264,7 +278,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
     const bool has_gl = GEN ? p.gl != nullptr : true, has_pl = GEN ? p.pl != nullptr : true, has_ad = GEN ? p.ad != nullptr : true;
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4; // this warp's GL slice; PL at +TILE_WST_G words, AD at +2*TILE_WST_G
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
-    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST, s_tot = s_smem + OFF_TOT;
+    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST;
+    uint32_t* const cnt_g = BIG ? p.cnt_scratch + (size_t)blockIdx.x * S4 : nullptr;
     uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]);
     bool first_tile = true;
 
@@ -306,7 +321,10 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
                 if (real2) gt2 = gt_t[(uint32_t)(iv2 - sl2 * PAD)];
                 const uint32_t ad = tile_sample_cell(p, R, site_base + (uint32_t)sl, (uint32_t)v, gt); // non-cells: missing genotype -> 0
                 if (real) dp_t[(uint32_t)(iv - sl * PAD)] = (int)__vsadu4(ad, 0u); // sum of the four byte counts
-                if (iv < nv) sts32(s_cnt + (uint32_t)iv * 4u, ad);
+                if (iv < nv) {
+                    if (BIG) cnt_g[iv] = ad;
+                    else sts32(s_cnt + (uint32_t)iv * 4u, ad);
+                }
                 // site totals: packed 16-bit fields through REDUX; a chunk usually lies within one site
                 const int first = __shfl_sync(0xffffffffu, sl, 0);
                 const uint32_t w01 = __byte_perm(ad, 0u, 0x4140), w23 = __byte_perm(ad, 0u, 0x4342);
@@ -345,6 +363,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
             if (lane == 0) { // phase A is over for every warp: rearm its chunk tickets; next tile's ticket (tiles are independent)
                 s_ctr[0] = 0u;
                 s_next = (int)atomicAdd(p.ticket, 1u);
+            }
+            { // pull the next tile's genotypes into L2 while this tile is scored (its first loads would otherwise wait on DRAM)
+                const int nt = __shfl_sync(0xffffffffu, lane == 0 ? s_next : 0, 0);
+                const int64_t lo = (int64_t)nt * T * S + lane * 128;
+                if (nt < p.n_tiles && lane * 128 < T * S && lo < p.n_cells) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gt + lo));
             }
             int my_g = 0, my_r = 0; // this site's block sizes in 4-byte elements (padded to 16 B)
             if (lane < nsl) {
@@ -470,7 +493,10 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
                 s_base[0] = bg;
                 s_base[1] = br;
                 s_ctr[1] = 0u;
-                if (tile == p.n_tiles - 1) { p.totals[0] = bg + tile_g; p.totals[1] = br + tile_r; }
+                if (tile == p.n_tiles - 1) {
+                    p.totals[0] = p.totals_host[0] = bg + tile_g;
+                    p.totals[1] = p.totals_host[1] = br + tile_r;
+                }
             }
             if (lane < nsl) {
                 p.sites[site0 + lane].g_off = bg + (ig - my_g);
@@ -483,8 +509,18 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
         float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
         int32_t* const pl_t = has_pl ? p.pl + s_base[0] : nullptr;
         int32_t* const ad_t = has_ad ? p.ad + s_base[1] : nullptr;
-        for (int cur = tile_ticket_get(tile_ticket_issue(s_ctrC, lane)), raw; cur < nchunk; cur = tile_ticket_get(raw)) {
-            raw = tile_ticket_issue(s_ctrC, lane); // next chunk's ticket: resolved after this chunk
+        // chunk tickets run two ahead and the counts of the next chunk are fetched before the current one is scored
+        auto load_counts = [&](int chunk) -> uint32_t {
+            const int i = chunk * 32 + lane;
+            if (i >= nv) return 0u;
+            return BIG ? cnt_g[i] : lds32(s_cnt + (uint32_t)i * 4u);
+        };
+        int cur = tile_ticket_get(tile_ticket_issue(s_ctrC, lane));
+        int nxt = tile_ticket_get(tile_ticket_issue(s_ctrC, lane));
+        uint32_t c4 = load_counts(cur);
+        for (; cur < nchunk;) {
+            const int raw = tile_ticket_issue(s_ctrC, lane);
+            const uint32_t c4_next = load_counts(nxt);
             const int iv = cur * 32 + lane;
             int sl = (int)__umulhi((uint32_t)iv, inv_s4);
             int v = iv - sl * S4;
@@ -502,7 +538,6 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
             // cells that emit nothing (padding slots, skipped sites, past the tile) compute along and store into a scratch cell
             const uint32_t cell_g = live ? s_wg + (uint32_t)(gpos - g_lo) * 4u : s_wg + TILE_G_TRASH * 4u;
             const uint32_t cell_r = live ? s_wr + (uint32_t)(rpos - r_lo) * 4u : s_wr + TILE_R_TRASH * 4u;
-            const uint32_t c4 = live ? lds32(s_cnt + (uint32_t)iv * 4u) : 0u;
             const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
             bulk_wait_read(); // this warp's previous copies (issued by lane 0) must have finished reading the slice
             __syncwarp();
@@ -548,46 +583,65 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
                 if (rb && has_ad) bulk_store(ad_t + r_lo, s_wr, rb);
                 bulk_commit();
             }
+            cur = nxt;
+            c4 = c4_next;
+            nxt = tile_ticket_get(raw);
         }
     }
     bulk_wait_all(); // global writes of this warp's last copies complete before exit
+    // the last CTA to leave rearms the tile ticket for the next launch on this slot (no memset between launches)
+    if (tid == 0) {
+        const unsigned done = atomicAdd(p.ticket + 1, 1u);
+        if (done == gridDim.x - 1) {
+            p.ticket[0] = 0u;
+            p.ticket[1] = 0u;
+        }
+    }
 }
 
-static size_t tile_dyn_smem(int S)
+static size_t tile_dyn_smem(bool big)
 {
-    const int S4 = (S + 3) & ~3;
-    const int cap = S4 > TILE_CELLS ? S4 : TILE_CELLS;
     return 2048 + 4096 + (size_t)TILE_WARPS * (2 * TILE_WST_G + TILE_WST_R) * 4 + TILE_MAX_SITES * sizeof(TSite) + TILE_MAX_SITES * 16 +
-           (size_t)cap * 4;
+           (big ? 0 : (size_t)TILE_CELLS * 4);
 }
 
-template <bool GEN>
+template <bool GEN, bool BIG>
 static void launch_tile_t(const DevParams& p, cudaStream_t st, int n_sms)
 {
-    const size_t dyn = tile_dyn_smem(p.S);
-    cudaFuncSetAttribute(k_tile_m1f<GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_tile_m1f<GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const size_t dyn = tile_dyn_smem(BIG);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN>, TILE_BLOCK, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN, BIG>, TILE_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
     int grid = n_sms * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    k_tile_m1f<GEN><<<grid, TILE_BLOCK, dyn, st>>>(p);
+    k_tile_m1f<GEN, BIG><<<grid, TILE_BLOCK, dyn, st>>>(p);
 }
 
 void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms)
 {
-    if (p.gl && p.pl && p.ad) launch_tile_t<false>(p, st, n_sms);
-    else launch_tile_t<true>(p, st, n_sms);
+    const bool all3 = p.gl && p.pl && p.ad, big = tile_m1f_scratch_words(p.S, 1) > 0;
+    if (all3 && !big) launch_tile_t<false, false>(p, st, n_sms);
+    else if (all3) launch_tile_t<false, true>(p, st, n_sms);
+    else if (!big) launch_tile_t<true, false>(p, st, n_sms);
+    else launch_tile_t<true, true>(p, st, n_sms);
 }
 
-// largest S the tile kernel takes: one site's counts must fit the shared-memory cache
-int tile_m1f_max_samples() { return 16384; }
+// largest S the tile kernel takes (the slot arithmetic needs (S4 + block) * S4 < 2^32)
+int tile_m1f_max_samples() { return 60000; }
 int tile_m1f_sites_per_tile(int S)
 {
     const int S4 = (S + 3) & ~3;
     int T = TILE_CELLS / S4;
     return T < 1 ? 1 : (T > TILE_MAX_SITES ? TILE_MAX_SITES : T);
+}
+// 32-bit words of global scratch the kernel needs for S samples on a device with n_sms SMs (0: counts fit shared memory)
+size_t tile_m1f_scratch_words(int S, int n_sms)
+{
+    const int S4 = (S + 3) & ~3;
+    return S4 > TILE_CELLS ? (size_t)S4 * TILE_SCRATCH_CTAS_PER_SM * n_sms : 0;
 }
 
 } // namespace vgl

@@ -75,6 +75,7 @@ struct DevParams {
     CellTail* celltail;
     vgl_site_out* sites;
     int64_t* totals; // [2] used G / R elements
+    int64_t* totals_host; // the same two words in pinned host memory (device-accessible)
     uint64_t* pairmap; // [n_sites] base-pair -> genotype-slot map (GL model 1), written by k_site
     float* gl;
     int32_t* pl;
@@ -90,6 +91,7 @@ struct DevParams {
     // tile kernel (tile_m1f.cu)
     const unsigned long long* pois_alias; // [256] Walker alias table of the depth distribution: t56 << 8 | alias
     const uint32_t* err_cdf;              // [256][4] P(E <= j | n reads) * 2^32, j = 0..3
+    uint32_t* cnt_scratch;                // per-CTA rows of packed counts when a site does not fit shared memory
     // replay
     int32_t replay;
     const int32_t* rp_depths;
@@ -110,6 +112,7 @@ void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms);
 void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms);
 int tile_m1f_max_samples();
 int tile_m1f_sites_per_tile(int S);
+size_t tile_m1f_scratch_words(int S, int n_sms);
 void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
                   uint8_t* adjqs, uint8_t* tails, double* eprob);
 
