@@ -44,15 +44,36 @@ WORKLOAD = ("cfg2: 100 samples x 1M sites (steps of %d sites), Poisson depth 10,
             "tags GL+PL+AD+DP, seed 42" % BATCH_SITES)
 
 
+QS_BINS = None          # --qs-bins ranges of the workload (start, end, value)
+INVARIANT_SHARE = 0.0   # share of all-hom-ref sites in the synthetic genotypes (gVCF / -explode runs)
+
+
 def set_workload(name):
-    """cfg2 is the bench line (BASELINE.json configs[1]); cfg5 is the shape of the scaling config (10 000 samples,
-    depth 30) at a per-step size that fits one GPU -- used for profiling and reported separately."""
-    global N_SAMPLES, BATCH_SITES, VCFGL_ARGS, WORKLOAD
+    """cfg2 is the bench line (BASELINE.json configs[1]).  The others are the remaining BASELINE.json configs at a
+    per-step size that fits one GPU; they are measured with `--workload` for DESIGN.md and never replace the cfg2 line."""
+    global N_SAMPLES, BATCH_SITES, VCFGL_ARGS, WORKLOAD, QS_BINS, INVARIANT_SHARE
     if name == "cfg5":
         N_SAMPLES, BATCH_SITES = 10000, 4440   # 5 x (148 SMs x 6 resident CTAs) tiles
         VCFGL_ARGS = "-d 30 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1".split()
         WORKLOAD = ("cfg5 shape: 10000 samples, steps of %d sites, Poisson depth 30, e=0.01, GL model 1, "
                     "tags GL+PL+AD+DP, seed 42" % BATCH_SITES)
+    elif name == "cfg3a":
+        N_SAMPLES, BATCH_SITES = 1000, 8192
+        VCFGL_ARGS = "-d 10 -e 0.01 -GL 2 -eq 1 -bv 1e-5 -addGL 1 -addPL 1".split()
+        WORKLOAD = ("cfg3(i): 1000 samples, steps of %d sites, Poisson depth 10, GL model 2, per-site beta error "
+                    "(mean 0.01, var 1e-5), tags GL+PL+DP, seed 42" % BATCH_SITES)
+    elif name == "cfg3b":
+        N_SAMPLES, BATCH_SITES = 1000, 8192
+        VCFGL_ARGS = "-d 10 -e 0.01 -GL 2 -eq 2 -bv 1e-5 -addGL 1 -addPL 1".split()
+        QS_BINS = [(0, 2, 2), (3, 14, 12), (15, 30, 23), (31, 63, 37)]   # RTA3 bins, last range opened to 63
+        WORKLOAD = ("cfg3(ii): 1000 samples, steps of %d sites, Poisson depth 10, GL model 2, per-read beta error "
+                    "(mean 0.01, var 1e-5) + RTA3 qs bins, tags GL+PL+DP, seed 42" % BATCH_SITES)
+    elif name == "cfg4":
+        N_SAMPLES, BATCH_SITES = 100, 131072
+        VCFGL_ARGS = "-d 10 -e 0.001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,5,10 -addGL 1 -addPL 1 -addI16 1 -addQS 1".split()
+        INVARIANT_SHARE = 0.99
+        WORKLOAD = ("cfg4: 100 samples, steps of %d sites of which 99%% invariant (-explode), Poisson depth 10, e=0.001, "
+                    "GL model 1, <*> allele, tags GL+PL+DP+I16+QS, seed 42" % BATCH_SITES)
 
 
 def measured_peak():
@@ -110,7 +131,7 @@ class ClockSampler:
 
 def sim_args():
     from vcfgl_b200 import args as vargs
-    return vargs.parse_args(["--seed", "42"] + VCFGL_ARGS)
+    return vargs.parse_args(["--seed", "42"] + VCFGL_ARGS, qs_bins=QS_BINS)
 
 
 # --------------------------------------------------------------------------- reference CPU arm
@@ -202,11 +223,15 @@ def gpu_arm(opt):
     # contiguous site range of this rank (weak scaling: every rank simulates K + W batches of its own)
     site0 = rank * (K + W + 4) * B
     hap = synth.sfs_genotypes(B, S, 20260002 + rank)
+    if INVARIANT_SHARE > 0:      # positions absent from the input VCF: hom-ref records synthesised by -explode
+        inv = np.random.default_rng(7 + rank).random(B) < INVARIANT_SHARE
+        hap[inv] = 0
     gt = synth.pack_gt(hap)      # binary source: REF=0 -> A, ALT=1 -> C (vcfgl.cpp:103-128)
     stream = torch.cuda.Stream()   # an explicit stream: libvgl treats a NULL stream as "use the slot's own"
 
     # ---------------- value: genotypes resident in HBM, results stay in HBM
     ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=False))
+    kernels = ctx.native_kernels()
     for s in (0, 1):
         ctx.set_stream(s, stream.cuda_stream)
         ctx.input_buffer(s)[:] = gt
@@ -323,16 +348,24 @@ def gpu_arm(opt):
     # ---------------- roofline of the kernels (device time inside the timed region)
     peak, peak_src = measured_peak()
     kern_ms /= K
-    dev_ms = float(kern_ms[capi.T_SIM] + kern_ms[capi.T_SITE] + kern_ms[capi.T_SCAN] + kern_ms[capi.T_EMIT])
+    fused = "+" not in kernels       # one kernel does the whole path; libvgl reports its time in the T_EMIT interval
+    dev_ms = float(kern_ms[capi.T_EMIT]) if fused else \
+        float(kern_ms[capi.T_SIM] + kern_ms[capi.T_SITE] + kern_ms[capi.T_SCAN] + kern_ms[capi.T_EMIT])
     achieved = alg_bytes / (dev_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:    # DRAM bytes of one launch from the last `ncu --set full` capture of this workload (profiles/README.md)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[opt.workload]
+        traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
-            "kernel": "k_sim+k_site+k_scan+k_emit (one step; algorithmic bytes of the whole path / summed kernel time)",
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "kernel": "%s (%s per step; algorithmic bytes of the whole path / its average launch duration, CUDA events "
+                      "on the launching stream)" % (kernels, "one launch" if fused else "four launches"),
             "algorithmic_bytes_per_step": alg_bytes, "bytes_per_cell": alg_bytes / cells_per_step,
-            "kernel_ms": {"k_sim": float(kern_ms[capi.T_SIM]), "k_site": float(kern_ms[capi.T_SITE]),
-                          "k_scan": float(kern_ms[capi.T_SCAN]), "k_emit": float(kern_ms[capi.T_EMIT])},
-            "emit_only": {"achieved": alg_bytes / (float(kern_ms[capi.T_EMIT]) * 1e-3) / 1e9,
-                          "note": "k_emit alone writes every tag plane"}}
+            "kernel_ms": {kernels: dev_ms} if fused else
+                         {"k_sim": float(kern_ms[capi.T_SIM]), "k_site": float(kern_ms[capi.T_SITE]),
+                          "k_scan": float(kern_ms[capi.T_SCAN]), "k_emit": float(kern_ms[capi.T_EMIT])}}
 
     # ---------------- CPU baseline: the reference binary, 1 thread, bounded sample
     cpu = None
@@ -340,7 +373,7 @@ def gpu_arm(opt):
         if os.path.exists(REF_BIN):
             tmp = tempfile.mkdtemp(prefix="vgl_cpubase_")
             try:
-                n_sites = 65536
+                n_sites = 196608
                 cells, wall = run_reference_shards(1, n_sites, 4242, tmp)
                 cpu = {"value": cells / wall, "unit": UNIT, "cores": 1, "kind": "reference",
                        "sample": "%d sites x %d samples of the same workload, reference binary -O u, wall %.1f s" % (n_sites, S, wall)}
@@ -355,6 +388,7 @@ def gpu_arm(opt):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_sites": B, "cells_per_step": cells_per_step,
                    "l2": "no flush: each step writes %.2f GB of tag planes (> 126 MB L2)" % (alg_bytes / 1e9),
+                   "n_samples": S,
                    "sites_with_15_genotypes": g_share, "sharding": "contiguous site ranges per GPU, no collective"},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * S), "d2h_bytes_per_step": d2h_bytes,
@@ -373,7 +407,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: stop after the kernel-side loop")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3a", "cfg3b", "cfg4", "cfg5"])
     opt = ap.parse_args()
     set_workload(opt.workload)
     opt.warmup = max(opt.warmup, 3) if opt.impl == "b200" else opt.warmup

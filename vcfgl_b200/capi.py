@@ -27,7 +27,7 @@ I32_MISSING = -(2 ** 31)
 
 EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
            "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
-           "vgl_last_error", "vgl_abi_version"]
+           "vgl_last_error", "vgl_abi_version", "vgl_native_kernels"]
 
 
 class VglParams(C.Structure):
@@ -110,6 +110,8 @@ def load():
     L.vgl_selftest.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
     L.vgl_launch_count.argtypes = [C.c_void_p]
     L.vgl_launch_count.restype = C.c_int64
+    L.vgl_native_kernels.argtypes = [C.c_void_p]
+    L.vgl_native_kernels.restype = C.c_char_p
     L.vgl_algorithmic_bytes.argtypes = [C.POINTER(VglBatchOut), C.c_uint32]
     L.vgl_algorithmic_bytes.restype = C.c_int64
     L.vgl_strerror.argtypes = [C.c_int]
@@ -316,6 +318,9 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.L.vgl_launch_count(self.h))
+
+    def native_kernels(self):
+        return self.L.vgl_native_kernels(self.h).decode()
 
     def algorithmic_bytes(self, batch: Batch) -> int:
         """SURVEY.md 8(d) bytes of a batch; needs the site records on the host"""

@@ -117,6 +117,12 @@ extern "C" const char* vgl_last_error(const vgl_ctx* ctx) { return ctx ? ctx->er
 
 extern "C" int64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" const char* vgl_native_kernels(const vgl_ctx* ctx)
+{
+    if (!ctx) return "";
+    return ctx->use_tile ? "k_tile_m1f" : ctx->use_fused ? "k_fused_m1f" : "k_sim+k_site+k_scan+k_emit";
+}
+
 extern "C" int64_t vgl_algorithmic_bytes(const vgl_batch_out* o, uint32_t tag_mask)
 {
     // 1 B packed genotype in + int32/float32 planes as handed to htslib
