@@ -18,4 +18,15 @@ int shim_precalc(double e, int eq, int gl, int precise, int adj, double adjby, i
     *qs = pc.qs; *adjqs = pc.adj_qs; g3[0] = pc.homT; g3[1] = pc.het; g3[2] = pc.homF;
     return rc;
 }
+double shim_inc_beta(double a, double b, double x) { return vgl::inc_beta(a, b, x); }
+// returns the number of table words (0: no table); prob512[2q + err]
+int shim_qs_classes(double a, double b, double shift, int use_bins, const uint8_t* bin_lut, int bin_max, uint32_t* words, double* prob512)
+{
+    std::vector<double> pr;
+    auto w = vgl::qs_class_table(a, b, shift, use_bins != 0, bin_lut, bin_max, &pr);
+    if (w.empty()) return 0;
+    memcpy(words, w.data(), w.size() * 4);
+    memcpy(prob512, pr.data(), 512 * 8);
+    return (int)w.size();
+}
 }

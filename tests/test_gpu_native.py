@@ -44,11 +44,18 @@ SELF_CASES = {
 
 @pytest.mark.parametrize("name", sorted(SELF_CASES))
 def test_native_tags_match_oracle_on_own_draws(name):
-    a = vargs.parse_args(SELF_CASES[name].split())
     S, n_sites = (6, 40) if "deep" in name else (37, 300)
-    hap = synth.sfs_genotypes(n_sites, S, 99, missing_rate=0.05)
+    self_replay(name, SELF_CASES[name], 1, S, n_sites)
+
+
+def self_replay(name, argv, sampler, S, n_sites, kernels=None, qs_bins=None):
+    a = vargs.parse_args(argv.split(), qs_bins=qs_bins)
+    hap = synth.sfs_genotypes(n_sites, S, 99, missing_rate=0.05) if S > 1 else \
+        np.random.default_rng(1).integers(0, 2, (n_sites, 2)).astype(np.int8)
     gt = synth.pack_gt(hap)
-    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=n_sites, n_slots=1, sampler=1))
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=n_sites, n_slots=1, sampler=sampler))
+    if kernels:
+        assert ctx.native_kernels() == kernels, ctx.native_kernels()
     ctx.input_buffer(0)[:n_sites] = gt
     first = 123456789012
     ctx.submit(0, first, n_sites)
@@ -134,12 +141,24 @@ def chi2_two_sample(a, b, min_expected=5):
 
 @pytest.mark.parametrize("name", sorted(STATS))
 def test_native_distributions_match_reference(name):
+    distributions(name, 1)
+
+
+def distributions(name, sampler, kernels=None, strand=True):
     st = STATS[name]
-    a = vargs.parse_args(st["argv"], qs_bins=st.get("qs_bins"))
+    argv = list(st["argv"])
+    if not strand:   # kernels without strand tags: drop the ADF/ADR flags of the fixture's command line
+        for flag in ("-addFormatADF", "-addFormatADR", "-addInfoADF", "-addInfoADR"):
+            while flag in argv:
+                i = argv.index(flag)
+                del argv[i:i + 2]
+    a = vargs.parse_args(argv, qs_bins=st.get("qs_bins"))
     S, n_sites = st["S"], st["n_sites"]
     hap = synth.sfs_genotypes(n_sites, S, st["gt_seed"])
     gt = synth.pack_gt(hap)
-    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=n_sites, n_slots=1, sampler=1))
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=n_sites, n_slots=1, sampler=sampler))
+    if kernels:
+        assert ctx.native_kernels() == kernels, ctx.native_kernels()
     ctx.input_buffer(0)[:n_sites] = gt
     ctx.submit(0, 0, n_sites)
     b = ctx.wait(0)
@@ -165,7 +184,7 @@ def test_native_distributions_match_reference(name):
     het = ~hom
     pvals["het_hap_pick"] = chi2_two_sample([(rp["bases"][het] == g0[het]).sum(), (rp["bases"][het] == g1[het]).sum()],
                                             st["het_reads"])
-    if sum(st["strand"][1:]) > 0:
+    if strand and sum(st["strand"][1:]) > 0:
         pvals["strand"] = chi2_two_sample(np.bincount(rp["strands"], minlength=2), st["strand"])
     if a.error_qs == 2:
         pvals["qs"] = chi2_two_sample(np.bincount(rp["qs"], minlength=256), st["qs_hist"])

@@ -29,6 +29,9 @@ def shim():
     L.shim_fixed_bsum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.shim_precalc.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int),
                                C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.shim_inc_beta.restype = C.c_double
+    L.shim_inc_beta.argtypes = [C.c_double] * 3
+    L.shim_qs_classes.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -89,3 +92,75 @@ def test_lut_equals_reference_table(shim):
     want = np.array((C.c_double * 771).in_dll(ref, "qScore_to_log10_gl")[:])
     got = np.ctypeslib.as_array(shim.shim_lut(), shape=(771,))
     assert np.array_equal(u64(got), u64(want))
+
+
+def beta_shapes(mean, var):
+    a = (((1.0 - mean) / var) - 1.0 / mean) * mean ** 2   # rng.h:370-371
+    return a, a * (1.0 / mean - 1.0)
+
+
+def test_incomplete_beta_matches_scipy(shim):
+    from scipy import special
+    for mean, var in ((0.01, 1e-5), (0.02, 1e-4), (0.05, 1e-3), (0.3, 0.01)):
+        a, b = beta_shapes(mean, var)
+        for x in (1e-8, 1e-4, 0.003, 0.01, 0.02, 0.1, 0.5, 0.79, 0.999):
+            for aa in (a, a + 1.0):
+                got, want = shim.shim_inc_beta(aa, b, x), special.betainc(aa, b, x)
+                assert abs(got - want) <= 1e-12 + 1e-10 * want, (mean, var, x, got, want)
+
+
+@pytest.mark.parametrize("mean,var,shift,bins", [(0.01, 1e-5, 0.0, None), (0.01, 1e-5, 0.499, None), (0.02, 1e-4, 0.0, "rta3"),
+                                                  (0.3, 0.02, 0.0, None)])
+def test_qs_class_table_is_the_beta_law(shim, mean, var, shift, bins):
+    """class probabilities = Monte-Carlo-free check against scipy: P(q) from the Beta CDF, P(q, error) from E[p; class];
+    the alias table reproduces the quantised probabilities exactly (integer arithmetic)."""
+    from scipy import stats
+    a, b = beta_shapes(mean, var)
+    lut = np.zeros(256, np.uint8)
+    bin_max = -1
+    if bins:
+        for lo, hi, val in ((0, 2, 2), (3, 14, 12), (15, 30, 23), (31, 63, 37)):
+            lut[lo:hi + 1] = val
+            bin_max = hi
+    words = np.zeros(512, np.uint32)
+    prob = np.zeros(512, np.float64)
+    n = shim.shim_qs_classes(a, b, shift, int(bins is not None), lut.ctypes.data, bin_max, words.ctypes.data, prob.ctypes.data)
+    if bins and stats.beta.sf(10 ** (-64 / 10.0), a, b) < 1.0 and stats.beta.cdf(10 ** (-64 / 10.0), a, b) * 2 ** 32 >= 0.5:
+        assert n == 0
+        return
+    assert n == 512
+    assert abs(prob.sum() - 1.0) < 1e-9
+    # expected law by direct integration on a fine grid of phred classes
+    want = np.zeros(512)
+    d = stats.beta(a, b)
+    d1 = stats.beta(a + 1.0, b)
+    for k in range(0, 421):
+        lo = 0.0 if k == 0 else k - shift
+        hi = k + 1.0 - shift
+        if hi <= 0:
+            continue
+        lo = max(lo, 0.0)
+        p_hi, p_lo = 10 ** (-lo / 10.0), (0.0 if k == 420 else 10 ** (-hi / 10.0))
+        P = d.cdf(p_hi) - d.cdf(p_lo)
+        M = mean * (d1.cdf(p_hi) - d1.cdf(p_lo))
+        if bins and k > bin_max:
+            continue
+        q = int(lut[k]) if bins else min(k, 63)
+        want[2 * q] += P - M
+        want[2 * q + 1] += M
+    assert np.abs(prob - want).max() < 2e-9, np.abs(prob - want).max()
+    assert abs(prob[1::2].sum() - mean) < 1e-8            # P(mis-called) = E[p]
+    # the alias table: exact column arithmetic
+    alias, thr = words[:256] & 0xFF, (words[:256] >> 8).astype(np.int64)
+    info = words[256:]
+    mass = np.zeros(256, np.int64)
+    for k in range(256):
+        if alias[k] == k:
+            mass[k] += 1 << 24
+        else:
+            mass[k] += thr[k]
+            mass[alias[k]] += (1 << 24) - thr[k]
+    for c in range(256):
+        if mass[c]:
+            q, err = int(info[c] & 0xFF), int(info[c] >> 8)
+            assert mass[c] == round(prob[2 * q + err] * 2 ** 32), (c, q, err)

@@ -72,6 +72,8 @@ struct vgl_ctx {
     int bin_max = -1;
     // device tables
     int use_fused = 0, use_tile = 0, n_sms = 148, fast_div = 0;
+    int use_tile_m2 = 0, tile_m2_mode = 0; // tile_m2.cu; mode 0 / 1 / 2 = --error-qs
+    uint32_t* d_qcls = nullptr;
     unsigned long long *d_pois = nullptr, *d_alias = nullptr;
     uint32_t *d_errcdf = nullptr, *d_cnt_scratch = nullptr;
     int pois_n = 0;
@@ -120,7 +122,7 @@ extern "C" int64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->laun
 extern "C" const char* vgl_native_kernels(const vgl_ctx* ctx)
 {
     if (!ctx) return "";
-    return ctx->use_tile ? "k_tile_m1f" : ctx->use_fused ? "k_fused_m1f" : "k_sim+k_site+k_scan+k_emit";
+    return ctx->use_tile ? "k_tile_m1f" : ctx->use_tile_m2 ? "k_tile_m2" : ctx->use_fused ? "k_fused_m1f" : "k_sim+k_site+k_scan+k_emit";
 }
 
 extern "C" int64_t vgl_algorithmic_bytes(const vgl_batch_out* o, uint32_t tag_mask)
@@ -201,7 +203,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls);
     delete ctx;
 }
 
@@ -265,9 +267,14 @@ static int create_impl(vgl_ctx* ctx)
     ctx->use_fused = ctx->gl_mode == GL_M1_FIXED && p.sampler != VGL_SAMPLER_PER_READ &&
                      !(t & (VGL_TAG_QS | VGL_TAG_I16)) && g_cap_elems < (1ull << 31);
     if (p.sampler == VGL_SAMPLER_COUNTS && !ctx->use_fused) return fail(ctx, VGL_EINVAL, "count-level sampler unavailable for this configuration (plane too large)");
+    // model-2 tile kernel (tile_m2.cu): native RNG, GL model 2 with run constants (--error-qs 0/1) or the qs LUT (--error-qs 2,
+    // --precise-gl 0), tags within GL / PL / AD / DP / INFO AD, DP
+    const uint32_t m2_tags = VGL_TAG_GL | VGL_TAG_PL | VGL_TAG_FMT_AD | VGL_TAG_FMT_DP | VGL_TAG_INFO_AD | VGL_TAG_INFO_DP;
+    const bool m2_cand = p.gl_model == 2 && p.sampler == VGL_SAMPLER_AUTO && !(p.error_qs == 2 && p.precise_gl) && !(t & ~m2_tags) &&
+                         g_cap_elems < (1ull << 31) && p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
     std::vector<unsigned long long> alias(256, 0ull);
     bool alias_ok = p.depth_mode == VGL_DEPTH_FIXED && p.depth_mean < 256.0;
-    if (ctx->use_fused && p.depth_mode == VGL_DEPTH_POISSON) {
+    if ((ctx->use_fused || m2_cand) && p.depth_mode == VGL_DEPTH_POISSON) {
         const std::vector<unsigned long long> cdf = poisson_cdf_u64(p.depth_mean, 1024);
         ctx->pois_n = (int)cdf.size();
         CK(upload(&ctx->d_pois, cdf));
@@ -277,7 +284,17 @@ static int create_impl(vgl_ctx* ctx)
     // the tile kernel (tile_m1f.cu): the fused path's headline special case
     ctx->use_tile = ctx->use_fused && alias_ok && p.error_qs == 0 && !ctx->sample_strand && !(t & VGL_TAG_GP) && ctx->fast_div &&
                     p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
-    if (ctx->use_tile) {
+    if (m2_cand && alias_ok) {
+        ctx->tile_m2_mode = p.error_qs;
+        ctx->use_tile_m2 = 1;
+        if (p.error_qs == 2) {
+            const bool gl_adj = (p.adjust_qs & 1) != 0;
+            const std::vector<uint32_t> qc = qs_class_table(ctx->beta_a, ctx->beta_b, gl_adj ? p.adjust_by : 0.0, p.n_qs_bins > 0, ctx->bin_lut, ctx->bin_max);
+            if (qc.empty()) ctx->use_tile_m2 = 0; // classes outside the bins / too many: the per-read kernels keep the reference's behaviour
+            else CK(upload(&ctx->d_qcls, qc));
+        }
+    }
+    if (ctx->use_tile || ctx->use_tile_m2) {
         CK(upload(&ctx->d_alias, alias));
         CK(upload(&ctx->d_errcdf, binomial_cdf4_u32(p.error_rate)));
         const size_t words = tile_m1f_scratch_words(p.n_samples, ctx->n_sms);
@@ -304,7 +321,7 @@ static int create_impl(vgl_ctx* ctx)
         CK(cudaMalloc((void**)&s.d_sites, B * sizeof(vgl_site_out)));
         CK(cudaMalloc((void**)&s.d_totals, 4 * sizeof(int64_t)));
         CK(cudaMalloc((void**)&s.d_pairmap, B * sizeof(uint64_t)));
-        if (ctx->use_fused) {
+        if (ctx->use_fused || ctx->use_tile_m2) {
             CK(cudaMalloc((void**)&s.d_tile_state, (B + 2) * sizeof(unsigned long long)));
             CK(cudaMemset(s.d_tile_state, 0, (B + 2) * sizeof(unsigned long long)));
         }
@@ -458,14 +475,15 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.pois_alias = ctx->d_alias;
     p.err_cdf = ctx->d_errcdf;
     p.cnt_scratch = ctx->d_cnt_scratch;
+    p.qcls = ctx->d_qcls;
     {
         int T = 1024 / (int)S;
         T = T < 1 ? 1 : (T > 128 ? 128 : T);
-        if (ctx->use_tile) T = tile_m1f_sites_per_tile((int)S);
+        if (ctx->use_tile || ctx->use_tile_m2) T = tile_m1f_sites_per_tile((int)S);
         p.sites_per_tile = T;
         p.n_tiles = (n_sites + T - 1) / T;
         p.tile_state = s.d_tile_state;
-        p.ticket = s.d_tile_state ? reinterpret_cast<uint32_t*>(s.d_tile_state + (ctx->use_tile ? 0 : p.n_tiles)) : nullptr;
+        p.ticket = s.d_tile_state ? reinterpret_cast<uint32_t*>(s.d_tile_state + ((ctx->use_tile || ctx->use_tile_m2) ? 0 : p.n_tiles)) : nullptr;
     }
     p.status = reinterpret_cast<int32_t*>(s.d_totals + 2);
     p.gl = s.d_gl; p.pl = s.d_pl; p.gp = s.d_gp;
@@ -488,7 +506,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     fill_params(ctx, s, first_site_id, n_sites, p);
     CK(cudaEventRecord(s.ev[EV_START], st));
     if (!(flags & VGL_SUBMIT_GT_ON_DEVICE)) CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
-    const bool tile_launch = ctx->use_tile && !rp; // the tile kernel rearms its own ticket and writes the totals itself
+    const bool tile_launch = (ctx->use_tile || ctx->use_tile_m2) && !rp; // the tile kernel rearms its own ticket and writes the totals itself
     if (!tile_launch) CK(cudaMemsetAsync(s.d_totals, 0, 4 * sizeof(int64_t), st));
     if (rp) {
         if (!rp->depths || !rp->read_offsets || (rp->n_reads > 0 && !rp->bases)) return fail(ctx, VGL_EINVAL, "replay: depths/read_offsets/bases required");
@@ -522,7 +540,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             p.rp_n_deep = (int64_t)deep.size();
         }
     }
-    const bool fused = ctx->use_fused && !rp;
+    const bool fused = (ctx->use_fused || ctx->use_tile_m2) && !rp;
     if (fused && !tile_launch) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));
     if (fused) {
@@ -531,6 +549,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         CK(cudaEventRecord(s.ev[EV_SITE], st));
         CK(cudaEventRecord(s.ev[EV_SCAN], st));
         if (ctx->use_tile) launch_tile_m1f(p, st, ctx->n_sms);
+        else if (ctx->use_tile_m2) launch_tile_m2(p, st, ctx->n_sms, ctx->tile_m2_mode);
         else launch_fused_m1f(p, st, ctx->n_sms);
         CK(cudaEventRecord(s.ev[EV_EMIT], st));
         ctx->launches += 1;
@@ -627,7 +646,9 @@ extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, i
     DevParams p;
     fill_params(ctx, s, first_site_id, n_sites, p);
     CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
-    launch_sim(p, st); // depths (and counts, unused here)
+    const bool m2 = ctx->use_tile_m2 != 0; // the model-2 tile kernel's own sampler (read order matters there)
+    if (m2) launch_tile_m2_draws(p, st, ctx->tile_m2_mode, 0, s.d_dp, nullptr, nullptr, nullptr);
+    else launch_sim(p, st); // depths (and counts, unused here)
     ctx->launches += 1;
     s.dr_depths.resize((size_t)cells);
     CK(cudaMemcpyAsync(s.dr_depths.data(), s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
@@ -645,7 +666,13 @@ extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, i
     CK(cudaMemsetAsync(d_u8, 0, 5 * nr + 16, st));
     CK(cudaMemsetAsync(d_e, 0, nr * 8 + 16, st));
     CK(cudaMemcpyAsync(d_off, s.dr_off.data(), ((size_t)cells + 1) * 8, cudaMemcpyHostToDevice, st));
-    launch_draws(p, st, d_off, d_u8, d_u8 + nr, d_u8 + 2 * nr, d_u8 + 3 * nr, d_u8 + 4 * nr, d_e);
+    if (m2) {
+        launch_tile_m2_draws(p, st, ctx->tile_m2_mode, 1, nullptr, d_off, d_u8, d_u8 + 2 * nr);
+        // the class table holds the score the GL uses: export it as both the raw and the adjusted score
+        if (nr) CK(cudaMemcpyAsync(d_u8 + 3 * nr, d_u8 + 2 * nr, nr, cudaMemcpyDeviceToDevice, st));
+    } else {
+        launch_draws(p, st, d_off, d_u8, d_u8 + nr, d_u8 + 2 * nr, d_u8 + 3 * nr, d_u8 + 4 * nr, d_e);
+    }
     ctx->launches += 1;
     CK(cudaGetLastError());
     s.dr_bases.resize(nr); s.dr_strands.resize(nr); s.dr_qs.resize(nr); s.dr_adjqs.resize(nr); s.dr_tails.resize(nr);

@@ -154,6 +154,120 @@ std::vector<uint32_t> binomial_cdf4_u32(double e)
     return t;
 }
 
+double inc_beta(double a, double b, double x)
+{
+    if (!(x > 0.0)) return 0.0;
+    if (!(x < 1.0)) return 1.0;
+    // use the symmetry I_x(a,b) = 1 - I_{1-x}(b,a) where the continued fraction converges fast
+    const bool flip = x > (a + 1.0) / (a + b + 2.0);
+    const double aa = flip ? b : a, bb = flip ? a : b, xx = flip ? 1.0 - x : x;
+    const double lfront = lgamma(aa + bb) - lgamma(aa) - lgamma(bb) + aa * log(xx) + bb * log1p(-xx);
+    const double tiny = 1e-300;
+    double c = 1.0, d = 1.0 - (aa + bb) * xx / (aa + 1.0);
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 20000; ++m) {
+        const double m2 = 2.0 * m;
+        double num = m * (bb - m) * xx / ((aa + m2 - 1.0) * (aa + m2));
+        d = 1.0 + num * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + num / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        num = -(aa + m) * (aa + bb + m) * xx / ((aa + m2) * (aa + m2 + 1.0));
+        d = 1.0 + num * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + num / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    const double v = exp(lfront) * h / aa;
+    return flip ? 1.0 - v : v;
+}
+
+std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_bins, const uint8_t* bin_lut, int bin_max,
+                                     std::vector<double>* prob)
+{
+    typedef unsigned long long u64;
+    if (!(shift >= 0.0)) return {};
+    const int KMAX = 420; // phred beyond this has no representable mass for any admissible Beta
+    // mass [0]/[1] = P(q, correct) / P(q, mis-called), indexed by the final quality score q (0..255)
+    std::vector<long double> mass(512, 0.0L);
+    const double mean = a / (a + b);
+    long double out_of_bins = 0.0L;
+    for (int k = 0; k <= KMAX; ++k) {
+        // q index k <=> phred + shift in [k, k+1) (k = 0 also takes the part below 0 of the shifted axis: (int) truncates)
+        double lo = k == 0 ? 0.0 : (double)k - shift, hi = (double)k + 1.0 - shift;
+        if (k == KMAX) hi = INFINITY;
+        if (hi <= 0.0) continue;
+        if (lo < 0.0) lo = 0.0;
+        const double p_hi = pow(10.0, -lo / 10.0), p_lo = std::isinf(hi) ? 0.0 : pow(10.0, -hi / 10.0);
+        const long double P = (long double)inc_beta(a, b, p_hi) - (long double)inc_beta(a, b, p_lo);
+        const long double M = (long double)mean * ((long double)inc_beta(a + 1.0, b, p_hi) - (long double)inc_beta(a + 1.0, b, p_lo));
+        if (!(P > 0.0L)) continue;
+        int q;
+        if (use_bins) {
+            if (k > bin_max) { out_of_bins += P; continue; }
+            q = bin_lut[k];
+        } else {
+            q = k > 63 ? 63 : k;
+        }
+        const long double Mc = M < 0.0L ? 0.0L : (M > P ? P : M);
+        mass[2 * q] += P - Mc;
+        mass[2 * q + 1] += Mc;
+    }
+    if (out_of_bins * 4294967296.0L >= 0.5L) return {};
+    // classes with mass, quantised to 2^-32 with the rounding residue given to the heaviest class
+    std::vector<int> cls_info;
+    std::vector<u64> wq;
+    long double total = 0.0L;
+    for (long double m : mass) total += m;
+    if (!(total > 0.5L)) return {};
+    u64 sum = 0;
+    int heavy = 0;
+    for (int i = 0; i < 512; ++i) {
+        const u64 w = (u64)(mass[i] / total * 4294967296.0L + 0.5L);
+        if (w == 0) continue;
+        cls_info.push_back((i >> 1) | ((i & 1) << 8));
+        wq.push_back(w);
+        if (w > wq[heavy]) heavy = (int)wq.size() - 1;
+        sum += w;
+    }
+    const int K = 256;
+    if (wq.empty() || (int)wq.size() > K) return {};
+    const u64 one32 = 1ull << 32;
+    if (sum > one32) { if (wq[heavy] <= sum - one32) return {}; wq[heavy] -= sum - one32; }
+    else wq[heavy] += one32 - sum;
+    if (prob) {
+        prob->assign(512, 0.0);
+        for (size_t i = 0; i < wq.size(); ++i) (*prob)[(cls_info[i] & 0xFF) * 2 + (cls_info[i] >> 8)] = (double)wq[i] / 4294967296.0;
+    }
+    // Walker alias over K columns of capacity 2^24 each (K * 2^24 = 2^32: exact integer arithmetic)
+    const u64 cap = 1ull << 24;
+    std::vector<u64> m(K, 0);
+    for (size_t i = 0; i < wq.size(); ++i) m[i] = wq[i];
+    std::vector<int> small, large, alias(K);
+    std::vector<u64> stay(K, cap);
+    for (int k = 0; k < K; ++k) { alias[k] = k; (m[k] < cap ? small : large).push_back(k); }
+    while (!small.empty() && !large.empty()) {
+        const int s = small.back(), l = large.back();
+        small.pop_back();
+        stay[s] = m[s];
+        alias[s] = l;
+        m[l] -= cap - m[s];
+        if (m[l] < cap) { large.pop_back(); small.push_back(l); }
+    }
+    // leftovers hold exactly one column each (integer arithmetic): alias = itself, any threshold
+    std::vector<uint32_t> out(512, 0u);
+    for (int k = 0; k < K; ++k) {
+        if (alias[k] == k) out[k] = (uint32_t)((cap - 1) << 8) | (uint32_t)k;
+        else out[k] = (uint32_t)(stay[k] << 8) | (uint32_t)alias[k]; // keep the column when the low 24 bits of the draw < stay
+    }
+    for (size_t i = 0; i < cls_info.size(); ++i) out[256 + i] = (uint32_t)cls_info[i];
+    return out;
+}
+
 bool ErrmodTables::scores_safe_for_fast_div(const std::vector<double>& bsum, const std::vector<double>& het)
 {
     const double lo = ldexp(1.0, -100), hi = ldexp(1.0, 100);

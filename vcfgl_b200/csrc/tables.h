@@ -37,6 +37,20 @@ std::vector<unsigned long long> poisson_alias_u64(const std::vector<unsigned lon
 // (saturated at 2^32-1); E = #{j : u >= t[n][j]} for a 32-bit uniform u, 4 = "beyond the table".
 std::vector<uint32_t> binomial_cdf4_u32(double e);
 
+// regularized incomplete beta function I_x(a, b) (continued fraction, Lentz), x in [0, 1]
+double inc_beta(double a, double b, double x);
+
+// Per-read (quality score used by the GL, mis-called or not) classes of a Beta(a, b) error probability p
+// (--error-qs 2; vcfgl.cpp:494-523): phred = -10 log10 p, q = (int)(phred + shift) (shift = --adjust-by when the
+// GL uses the adjusted score, else 0), then --qs-bins or the cap at 63.  P(q) = I(p_hi) - I(p_lo) and
+// P(q and error) = E[p; p in the class] = a/(a+b) (I_{a+1,b}(p_hi) - I_{a+1,b}(p_lo)) since the read is mis-called
+// with probability p (vcfgl.cpp:485).  Returned: 512 words = a Walker alias table over 256 columns
+// (threshold24 << 8 | alias; probabilities quantised to 2^-32) followed by the class info words (q | err << 8);
+// `prob` receives the quantised class probabilities (for tests).  Empty when the classes do not fit or a class
+// with positive probability falls outside the --qs-bins ranges (the reference exits there, vcfgl.cpp:63).
+std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_bins, const uint8_t* bin_lut, int bin_max,
+                                     std::vector<double>* prob = nullptr);
+
 // qScore_to_log10_gl[3][257] (shared.cpp:110-114)
 extern const double kLutLog10Gl[3][257];
 

@@ -1,0 +1,622 @@
+// k_tile_m2 -- GL model 2 (the GATK-style per-read likelihood, gl_methods.cpp:4-150) in the tile framework of
+// tile_m1f.cu: native RNG, same-mean Poisson or fixed depth, tags GL / PL / AD / DP (+ INFO/AD, INFO/DP).
+//   FIXED  one run-constant quality score (--error-qs 0, or --error-qs 1 = per-site beta-distributed base-picking
+//          error rate, vcfgl.cpp:425-437): homT / het / homF are run constants (vcfgl.cpp:1713-1740)
+//   LUT    per-read quality score (--error-qs 2, --precise-gl 0): each read's error probability is beta-distributed,
+//          its (binned / adjusted) quality score picks the three constants from qScore_to_log10_gl (gl_methods.cpp:99-104)
+//
+// Model 2 adds one of three constants to every genotype for every read and max-normalises the vector after EVERY
+// read in float (gl_methods.cpp:27-58), so the result depends on the ORDER of a cell's reads: the kernel works on
+// the read sequence, not on counts.  The sequence is still drawn at count level where that is exact:
+//   depth            alias table (as the model-1 tile kernel)
+//   haplotype picks  one random bit per read
+//   FIXED: number of mis-called reads E ~ Binomial(n, e), their positions uniform without replacement, wrong base
+//          uniform over the other three -- the joint law of n iid reads with P(error) = e
+//   LUT:   per read one draw from the joint law of (quality-score class, mis-called or not) of a Beta(a, b)
+//          error probability p: P(class k) = I(hi_k) - I(lo_k), P(class k and error) = E[p; p in class k]
+//          = a/(a+b) * (I_{a+1,b}(hi_k) - I_{a+1,b}(lo_k)); tabulated on the host (tables.cpp), alias-sampled here
+// Every draw is a pure function of (seed, site, sample[, read]); phase C re-derives the sequence of phase A instead
+// of storing it.  Cells deeper than 64 reads use one Philox block per read (the per-read sampler of kernels.cu).
+//
+// Phases per tile as in tile_m1f.cu: A sample + FORMAT/DP + site totals, B per-site record, C score + emit
+// (scatter in allele order into the warp's shared-memory slice, one bulk async copy per plane).
+#include "tile_common.cuh"
+
+namespace vgl {
+
+struct __align__(16) M2SiteE {
+    double e;  // base-picking error probability of the site
+    float l2;  // log2(1 - e) when the float CDF walk is usable, else 0
+    float er;  // e / (1 - e)
+};
+
+struct M2Rng {
+    uint32_t s_alias; // shared address: Poisson alias table
+    uint32_t s_cdf_e; // shared address: [256] uint4 P(E <= j | n) * 2^32 (run-constant error rate)
+    uint32_t s_qcls;  // shared address: LUT mode, [256] (threshold24 << 8 | alias) then [256] class -> (qs | err << 8)
+    int fixed_depth;
+    bool has_err;
+};
+
+// bit i of x moves to bit 2i (x < 2^16)
+__device__ __forceinline__ uint32_t spread16(uint32_t x)
+{
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// read i of a cell deeper than 64 reads: one Philox block per read, as CellSource::read (cell_source.cuh)
+__device__ __forceinline__ int m2_deep_base(const DevParams& p, unsigned long long site, uint32_t sample, int i, int g0, int g1, double e)
+{
+    const u32x4 w = philox_rk(p, (uint32_t)site, ((uint32_t)(site >> 32) & 0xFFu) | ((uint32_t)i << 8), sample, (uint32_t)P_READ << 24);
+    const int truth = (w.y >> 31) ? g1 : g0;
+    int base = truth;
+    if (u01_32(w.x) < e) base = (truth + 1 + (int)mulhi32(w.z, 3u)) & 3;
+    return base;
+}
+
+// depth of a cell from block 0 of its P_COUNTS counter
+__device__ __forceinline__ int m2_depth(const M2Rng& R, const u32x4& b0, uint32_t gt)
+{
+    int n;
+    if (R.fixed_depth >= 0) {
+        n = R.fixed_depth;
+    } else {
+        const uint32_t col = b0.x >> 24;
+        const uint2 en = lds64(R.s_alias + col * 8u);
+        const unsigned long long frac = ((unsigned long long)__funnelshift_l(b0.y, b0.x, 8) << 32) | (b0.y << 8);
+        const unsigned long long thr = ((unsigned long long)en.y << 32) | (en.x & 0xFFFFFF00u);
+        n = frac < thr ? (int)col : (int)(en.x & 0xFFu);
+    }
+    if (gt & 0x88u) n = 0; // missing genotype: depth drawn but discarded (vcfgl.cpp:371-379)
+    return n;
+}
+
+// One FIXED-mode cell.  Returns the packed 8-bit base counts; with SEQ also the read sequence as 2-bit codes
+// (read i in bits 2(i&15) of w[i>>4]) when n <= 64.  Draws: block 0 = {x,y: depth; z: number of errors; w: haplotype
+// bits 0..31}, block 1 = {x: haplotype bits 32..63; y,z,w: errors 1..3}; further errors and re-draws of occupied
+// positions from block 10 on.
+template <bool SEQ, bool SITE_E>
+__device__ __forceinline__ uint32_t m2_cell_fixed(const DevParams& p, const M2Rng& R, unsigned long long site, uint32_t sample, uint32_t gt,
+                                                  const M2SiteE& se, int& n_out, uint32_t (&w)[4])
+{
+    const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
+    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+    const u32x4 b0 = philox_rk(p, c0, c1, sample, (uint32_t)P_COUNTS << 24);
+    const int n = m2_depth(R, b0, gt);
+    n_out = n;
+    if (SEQ) w[0] = w[1] = w[2] = w[3] = 0u;
+    if (n == 0) return 0u;
+    if (n > 64) { // deep cell: per-read draws
+        uint32_t ad = 0u;
+        for (int i = 0; i < n; ++i) ad += 1u << (8 * m2_deep_base(p, site, sample, i, g0, g1, se.e));
+        return ad;
+    }
+    const u32x4 b1 = philox_rk(p, c0, c1, sample, ((uint32_t)P_COUNTS << 24) | 1u);
+    const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
+    const unsigned long long hm = h & (n >= 64 ? ~0ull : ((1ull << n) - 1ull));
+    const bool het = g0 != g1;
+    const int k0 = het ? __popcll(hm) : n;
+    uint32_t ad = ((uint32_t)k0 << (8 * g0)) + ((uint32_t)(n - k0) << (8 * g1));
+    if (SEQ) {
+        const uint32_t base = 0x55555555u * (uint32_t)g1, dx = (uint32_t)(g0 ^ g1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (16 * k < n) w[k] = base ^ (spread16((uint32_t)(h >> (16 * k)) & 0xFFFFu) * dx);
+    }
+    // number of mis-called reads
+    int E = 0;
+    if (SITE_E) {
+        if (se.e > 0.0) {
+            const float p0 = exp2f((float)n * se.l2);
+            const float uf = ((float)(b0.z >> 8) + 0.5f) * 5.9604645e-08f;
+            if (se.l2 != 0.0f && p0 > 1e-30f) {
+                float pr = p0, cdf = p0;
+                while (uf > cdf && E < n) {
+                    pr *= (float)(n - E) / (float)(E + 1) * se.er;
+                    cdf += pr;
+                    ++E;
+                }
+            } else {
+                E = binom_inversion(n, se.e, u01_32(b0.z));
+            }
+        }
+    } else if (R.has_err) {
+        const uint4 c = lds128(R.s_cdf_e + (uint32_t)n * 16u);
+        E = (b0.z >= c.x) + (b0.z >= c.y) + (b0.z >= c.z);
+        if (b0.z >= c.w) E = binom_inversion(n, se.e, u01_32(b0.z));
+    }
+    if (E > 0) {
+        unsigned long long hit = 0ull;
+        Stream st;
+        Key key;
+        key.k0 = p.k0; key.k1 = p.k1;
+        st.init(key, (int64_t)site, sample, 0, P_COUNTS);
+        st.block = 10;
+        for (int j = 0; j < E; ++j) {
+            uint32_t r = j == 0 ? b1.y : (j == 1 ? b1.z : (j == 2 ? b1.w : st.next()));
+            uint32_t pos, woff;
+            for (;;) {
+                const uint32_t q = mulhi32(r, 3u * (uint32_t)n);
+                pos = (q * 0xAAABu) >> 17; // q / 3, q < 192
+                woff = q - 3u * pos;
+                if (!((hit >> pos) & 1ull)) break;
+                r = st.next();
+            }
+            hit |= 1ull << pos;
+            const int old = het ? (((h >> pos) & 1ull) ? g0 : g1) : g0;
+            const int neu = (old + 1 + (int)woff) & 3;
+            ad += (1u << (8 * neu)) - (1u << (8 * old));
+            if (SEQ) {
+                const uint32_t sh = 2u * (pos & 15u), flip = (uint32_t)(old ^ neu) << sh;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((int)(pos >> 4) == k) w[k] ^= flip;
+            }
+        }
+    }
+    return ad;
+}
+
+// LUT-mode cell: per read one word of purpose P_QS (block i>>2, word i&3) -> alias draw of (class, error);
+// haplotype bit i from block 0/1 of P_COUNTS as in FIXED mode; the wrong base of a mis-called read from word z of
+// the read's P_READ block.  Cells deeper than 64 reads take their haplotype bits from the P_READ block as well.
+struct M2LutRead {
+    int base, qs;
+};
+__device__ __forceinline__ M2LutRead m2_lut_read(const DevParams& p, const M2Rng& R, unsigned long long site, uint32_t sample, int i, int g0,
+                                                 int g1, unsigned long long h, u32x4& qblk)
+{
+    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+    if ((i & 3) == 0) qblk = philox_rk(p, c0, c1, sample, ((uint32_t)P_QS << 24) | (uint32_t)(i >> 2));
+    const uint32_t r = (i & 3) == 0 ? qblk.x : ((i & 3) == 1 ? qblk.y : ((i & 3) == 2 ? qblk.z : qblk.w));
+    const uint32_t col = r >> 24;
+    const uint32_t en = lds32(R.s_qcls + col * 4u);
+    const uint32_t cls = (r & 0xFFFFFFu) < (en >> 8) ? col : (en & 0xFFu);
+    const uint32_t info = lds32(R.s_qcls + 1024u + cls * 4u); // qs | err << 8
+    M2LutRead out;
+    out.qs = (int)(info & 0xFFu);
+    int hb;
+    u32x4 rd;
+    const bool err = (info >> 8) & 1u;
+    if (i >= 64 || err) rd = philox_rk(p, c0, c1 | ((uint32_t)i << 8), sample, (uint32_t)P_READ << 24);
+    if (i < 64) hb = (int)((h >> i) & 1ull);
+    else hb = (int)(rd.y >> 31);
+    const int truth = hb ? g0 : g1;
+    out.base = err ? (truth + 1 + (int)mulhi32(rd.z, 3u)) & 3 : truth;
+    return out;
+}
+
+// one read of base b (ACGT int) with constants c2 / c1 / c0 (both / one / no allele of the genotype equals the
+// read) added to all 15 base pairs, then the max over the site's genotypes is subtracted (gl_methods.cpp:27-58).
+// Base pairs that are not genotypes of the site were initialised to -inf and stay there.
+__device__ __forceinline__ void m2_update(float (&gl)[15], int b, double c2, double c1, double c0)
+{
+    const bool p0 = b == 0, p1 = b == 1, p2 = b == 2, p3 = b == 3;
+    double a[15];
+    a[0] = p0 ? c2 : c0;
+    a[2] = p1 ? c2 : c0;
+    a[5] = p2 ? c2 : c0;
+    a[9] = p3 ? c2 : c0;
+    a[14] = c0;
+    a[1] = (p0 || p1) ? c1 : c0;
+    a[3] = (p0 || p2) ? c1 : c0;
+    a[4] = (p1 || p2) ? c1 : c0;
+    a[6] = (p0 || p3) ? c1 : c0;
+    a[7] = (p1 || p3) ? c1 : c0;
+    a[8] = (p2 || p3) ? c1 : c0;
+    a[10] = p0 ? c1 : c0;
+    a[11] = p1 ? c1 : c0;
+    a[12] = p2 ? c1 : c0;
+    a[13] = p3 ? c1 : c0;
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        gl[k] = __double2float_rn(__dadd_rn((double)gl[k], a[k])); // float += double
+        mx = fmaxf(mx, gl[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) gl[k] = __fsub_rn(gl[k], mx);
+}
+
+// final GL / PL of a cell, scattered into the warp's stage slice in allele order (vcfgl.cpp:907-939)
+__device__ __forceinline__ void m2_emit_cell(const float (&gl)[15], const uint4 slot, uint32_t cell_g, bool has_gl, bool has_pl)
+{
+    const uint32_t sw[4] = {slot.x, slot.y, slot.z, slot.w};
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        const uint32_t off = __byte_perm(sw[k >> 2], 0u, 0x4440u | (k & 3));
+        if (off != 0xFFu) {
+            const uint32_t dst = cell_g + off;
+            if (has_gl) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(gl[k]) : "memory");
+            if (has_pl) {
+                const float u = __fadd_rz(__fadd_rz(__fmul_rn(-10.0f, gl[k]), 0.5f), 8388608.0f);
+                asm volatile("st.shared.b32 [%0+%2], %1;" ::"r"(dst), "r"(pl_from_magic_bits(u)), "n"(TILE_WST_G * 4) : "memory");
+            }
+        }
+    }
+}
+
+// MODE 0: FIXED with the run-constant error rate, 1: FIXED with a per-site error rate, 2: LUT (per-read qs)
+template <int MODE, bool BIG>
+__global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant__ DevParams p)
+{
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    // layout: alias [256] u64 | cdf_e [256] uint4 (LUT: class alias + class info) | stage | st [sites] | tot [sites][4] | site_e [sites] | cnt [cap]
+    constexpr int WST = 2 * TILE_WST_G + TILE_WST_R;
+    constexpr uint32_t OFF_STAGE = 2048 + 4096, OFF_ST = OFF_STAGE + TILE_WARPS * WST * 4, OFF_TOT = OFF_ST + TILE_MAX_SITES * sizeof(TSite),
+                       OFF_SE = OFF_TOT + TILE_MAX_SITES * 16, OFF_CNT = OFF_SE + TILE_MAX_SITES * sizeof(M2SiteE);
+    TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
+    int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
+    M2SiteE* site_e = reinterpret_cast<M2SiteE*>(tile_smem + OFF_SE);
+    __shared__ int64_t s_base[2];
+    __shared__ int s_next;
+    __shared__ uint32_t s_ctr[2];
+    __shared__ uint32_t s_zero[32];
+
+    int tid, S;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("mov.u32 %0, %1;" : "=r"(S) : "r"(p.S));
+    const int lane = tid & 31, warp = tid >> 5;
+    const int S4 = (S + 3) & ~3, PAD = S4 - S, T = p.sites_per_tile;
+    const uint32_t s_smem = smem_u32(tile_smem);
+    for (int i = tid; i < 256; i += TILE_BLOCK) {
+        reinterpret_cast<uint2*>(tile_smem)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
+        if (MODE == 2) {
+            reinterpret_cast<uint2*>(tile_smem + 2048)[i] = reinterpret_cast<const uint2*>(p.qcls)[i]; // 512 words
+        } else {
+            reinterpret_cast<uint4*>(tile_smem + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+        }
+    }
+    for (int i = tid; i < TILE_MAX_SITES * 4; i += TILE_BLOCK) tot[i] = 0;
+    if (tid == 0) {
+        s_next = (int)atomicAdd(p.ticket, 1u);
+        s_ctr[0] = s_ctr[1] = 0u;
+    }
+    if (tid < 32) s_zero[tid] = 0u;
+    M2Rng R;
+    R.s_alias = s_smem;
+    R.s_cdf_e = s_smem + 2048;
+    R.s_qcls = s_smem + 2048;
+    R.fixed_depth = p.depth_mode == VGL_DEPTH_FIXED ? (int)p.depth_mean : -1;
+    R.has_err = p.error_rate > 0.0;
+    const uint32_t inv_s4 = (uint32_t)(((1ull << 32) + S4 - 1) / S4);
+    const bool explode = p.do_unobserved >= 3;
+    const bool add_unobs = p.do_unobserved == 1 || p.do_unobserved == 2 || p.do_unobserved == 4 || p.do_unobserved == 5;
+    const bool has_gl = p.gl != nullptr, has_pl = p.pl != nullptr, has_ad = p.ad != nullptr;
+    const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4;
+    const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
+    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST;
+    uint32_t* const cnt_g = BIG ? p.cnt_scratch + (size_t)blockIdx.x * S4 : nullptr;
+    uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]);
+    bool first_tile = true;
+    M2SiteE run_e;
+    run_e.e = p.error_rate;
+    run_e.l2 = 0.0f;
+    run_e.er = 0.0f;
+    const bool gl_adj = (p.adjust_qs & 1) != 0;
+    (void)gl_adj;
+
+    for (;;) {
+        __syncthreads();
+        const int tile = s_next;
+        if (tile >= p.n_tiles) break;
+        if (first_tile) {
+            const uint32_t opaque_zero = lds32(smem_u32(&s_zero[lane]));
+            s_ctrA += opaque_zero;
+            s_ctrC += opaque_zero;
+            first_tile = false;
+        }
+        const int site0 = tile * T;
+        const int nsl = min(T, p.n_sites - site0);
+        const int nv = nsl * S4;
+        const int nchunk = (nv + 31) >> 5;
+        const int64_t cell0 = (int64_t)site0 * S;
+        const uint8_t* __restrict__ gt_t = p.gt + cell0;
+        int32_t* __restrict__ dp_t = p.dp + cell0;
+        const unsigned long long site_base = (unsigned long long)(p.first_site + site0);
+
+        if (MODE == 1) { // per-site beta-distributed base-picking error rate (vcfgl.cpp:425-437), same draw as cell_source.cuh
+            if (tid < nsl) {
+                Stream bs;
+                Key key;
+                key.k0 = p.k0; key.k1 = p.k1;
+                bs.init(key, (int64_t)(site_base + (unsigned)tid), 0xFFFFFFFFu, 0, P_SITE);
+                const double e = beta_draw(bs, p.beta_a, p.beta_b);
+                M2SiteE se;
+                se.e = e;
+                se.l2 = (e > 0.0 && e <= 0.5) ? log2f((float)(1.0 - e)) : 0.0f;
+                se.er = (float)(e / (1.0 - e));
+                site_e[tid] = se;
+            }
+            __syncthreads();
+        }
+
+        // ---------------- phase A: counts, FORMAT/DP, per-site base totals
+        {
+            int cur = tile_ticket_get(tile_ticket_issue(s_ctrA, lane));
+            while (cur < nchunk) {
+                const int raw = tile_ticket_issue(s_ctrA, lane);
+                const int iv = cur * 32 + lane;
+                const int sl = (int)__umulhi((uint32_t)iv, inv_s4), v = iv - sl * S4;
+                const bool real = iv < nv && v < S;
+                uint32_t gt = 0xFFu;
+                if (real) gt = gt_t[(uint32_t)(iv - sl * PAD)];
+                uint32_t ad = 0u;
+                if (real) {
+                    int n;
+                    uint32_t wseq[4];
+                    if (MODE == 2) {
+                        const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
+                        const unsigned long long site = site_base + (uint32_t)sl;
+                        const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+                        const u32x4 b0 = philox_rk(p, c0, c1, (uint32_t)v, (uint32_t)P_COUNTS << 24);
+                        n = m2_depth(R, b0, gt);
+                        if (n > 0) {
+                            const u32x4 b1 = philox_rk(p, c0, c1, (uint32_t)v, ((uint32_t)P_COUNTS << 24) | 1u);
+                            const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
+                            u32x4 qblk;
+                            for (int i = 0; i < n; ++i) ad += 1u << (8 * m2_lut_read(p, R, site, (uint32_t)v, i, g0, g1, h, qblk).base);
+                        }
+                    } else {
+                        ad = m2_cell_fixed<false, MODE == 1>(p, R, site_base + (uint32_t)sl, (uint32_t)v, gt, MODE == 1 ? site_e[sl] : run_e, n, wseq);
+                    }
+                    dp_t[(uint32_t)(iv - sl * PAD)] = n;
+                }
+                if (iv < nv) {
+                    if (BIG) cnt_g[iv] = ad;
+                    else sts32(s_cnt + (uint32_t)iv * 4u, ad);
+                }
+                // site totals (counts of one chunk stay below 2^16 per base: 32 cells x 255 reads)
+                const int first = __shfl_sync(0xffffffffu, sl, 0);
+                const uint32_t w01 = __byte_perm(ad, 0u, 0x4140), w23 = __byte_perm(ad, 0u, 0x4342);
+                if (__all_sync(0xffffffffu, sl == first)) {
+                    const uint32_t a01 = __reduce_add_sync(0xffffffffu, w01), a23 = __reduce_add_sync(0xffffffffu, w23);
+                    if (lane < 4 && first < nsl) {
+                        const uint32_t ww = (lane & 2) ? a23 : a01;
+                        const uint32_t val = (lane & 1) ? (ww >> 16) : (ww & 0xFFFFu);
+                        if (val) atomicAdd(&tot[first * 4 + lane], (int)val);
+                    }
+                } else if (sl < nsl) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int val = (int)((ad >> (8 * b)) & 0xFFu);
+                        if (val) atomicAdd(&tot[sl * 4 + b], val);
+                    }
+                }
+                cur = tile_ticket_get(raw);
+            }
+        }
+        __syncthreads();
+
+        // ---------------- phase B (warp 0): per-site record
+        if (warp == 0) {
+            if (lane == 0) {
+                s_ctr[0] = 0u;
+                s_next = (int)atomicAdd(p.ticket, 1u);
+            }
+            tile_phase_b(p, lane, nsl, site0, tile, S, T, tot, st, explode, add_unobs, s_base, s_ctr);
+        }
+        __syncthreads();
+
+        // ---------------- phase C: score + emit, one warp per chunk of 32 virtual cells
+        float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
+        int32_t* const pl_t = has_pl ? p.pl + s_base[0] : nullptr;
+        int32_t* const ad_t = has_ad ? p.ad + s_base[1] : nullptr;
+        int cur = tile_ticket_get(tile_ticket_issue(s_ctrC, lane));
+        for (; cur < nchunk;) {
+            const int raw = tile_ticket_issue(s_ctrC, lane);
+            const int iv = cur * 32 + lane;
+            const uint32_t c4 = iv < nv ? (BIG ? cnt_g[iv] : lds32(s_cnt + (uint32_t)iv * 4u)) : 0u;
+            int sl = (int)__umulhi((uint32_t)iv, inv_s4);
+            int v = iv - sl * S4;
+            if (sl >= nsl) { sl = nsl - 1; v = S4; }
+            const uint4 t1 = lds128(s_st + (uint32_t)sl * 48u + 16u); // g_rel, r_rel, AG, sel4
+            const uint4 t2 = lds128(s_st + (uint32_t)sl * 48u + 32u); // sel01, sel23, g_end, r_end
+            const int A = (int)(t1.z & 0xFF), G = (int)__byte_perm(t1.z, 0u, 0x4441);
+            const bool live = v < S && G > 0;
+            const int vv = min(v, S);
+            const int gpos = (int)t1.x + vv * G, rpos = (int)t1.y + vv * A;
+            const int gend = v < S ? gpos + G : (int)t2.z;
+            const int rend = v < S ? rpos + A : (int)t2.w;
+            const int g_lo = __shfl_sync(0xffffffffu, gpos, 0), g_hi = __shfl_sync(0xffffffffu, gend, 31);
+            const int r_lo = __shfl_sync(0xffffffffu, rpos, 0), r_hi = __shfl_sync(0xffffffffu, rend, 31);
+            const uint32_t cell_g = live ? s_wg + (uint32_t)(gpos - g_lo) * 4u : s_wg + TILE_G_TRASH * 4u;
+            const uint32_t cell_r = live ? s_wr + (uint32_t)(rpos - r_lo) * 4u : s_wr + TILE_R_TRASH * 4u;
+            const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
+            // ---- the cell's reads, in order
+            float gl[15];
+            {
+                const uint32_t sw[4] = {slot.x, slot.y, slot.z, slot.w};
+#pragma unroll
+                for (int k = 0; k < 15; ++k) gl[k] = __byte_perm(sw[k >> 2], 0u, 0x4440u | (k & 3)) != 0xFFu ? -0.0f : -CUDART_INF_F; // bcf_utils.h:310
+            }
+            const int n = (int)__vsadu4(c4, 0u);
+            if (live && n > 0) {
+                uint32_t gt = gt_t[(uint32_t)(iv - sl * PAD)];
+                const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
+                const unsigned long long site = site_base + (uint32_t)sl;
+                if (MODE == 2) {
+                    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+                    const u32x4 b0 = philox_rk(p, c0, c1, (uint32_t)v, (uint32_t)P_COUNTS << 24);
+                    const u32x4 b1 = philox_rk(p, c0, c1, (uint32_t)v, ((uint32_t)P_COUNTS << 24) | 1u);
+                    const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
+                    u32x4 qblk;
+                    for (int i = 0; i < n; ++i) {
+                        const M2LutRead r = m2_lut_read(p, R, site, (uint32_t)v, i, g0, g1, h, qblk);
+                        const double c2 = __ldg(p.lut_log10 + r.qs), c1d = __ldg(p.lut_log10 + 257 + r.qs), c0d = __ldg(p.lut_log10 + 514 + r.qs);
+                        m2_update(gl, r.base, c2, c1d, c0d);
+                    }
+                } else {
+                    const M2SiteE se = MODE == 1 ? site_e[sl] : run_e;
+                    const double c2 = p.homT, c1d = p.het, c0d = p.homF;
+                    if (n > 64) {
+                        for (int i = 0; i < n; ++i) m2_update(gl, m2_deep_base(p, site, (uint32_t)v, i, g0, g1, se.e), c2, c1d, c0d);
+                    } else {
+                        int nn;
+                        uint32_t wseq[4];
+                        m2_cell_fixed<true, MODE == 1>(p, R, site, (uint32_t)v, gt, se, nn, wseq);
+                        uint32_t curw = 0u;
+                        for (int i = 0; i < n; ++i) {
+                            if ((i & 15) == 0) curw = (i >> 4) == 0 ? wseq[0] : ((i >> 4) == 1 ? wseq[1] : ((i >> 4) == 2 ? wseq[2] : wseq[3]));
+                            m2_update(gl, (int)(curw & 3u), c2, c1d, c0d);
+                            curw >>= 2;
+                        }
+                    }
+                }
+            }
+            bulk_wait_read();
+            __syncwarp();
+            m2_emit_cell(gl, slot, cell_g, has_gl, has_pl);
+            if (has_ad) {
+                sts32(cell_r, __byte_perm(c4, 0u, t2.x));
+                if (A > 1) sts32(cell_r + 4, __byte_perm(c4, 0u, t2.x >> 16));
+                if (A > 2) sts32(cell_r + 8, __byte_perm(c4, 0u, t2.y));
+                if (A > 3) sts32(cell_r + 12, __byte_perm(c4, 0u, t2.y >> 16));
+                if (A > 4) sts32(cell_r + 16, __byte_perm(c4, 0u, t1.w));
+            }
+            if (live && n == 0) { // gl_methods.cpp:60-66
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    sts32(cell_g + 4 * g, VGL_F32_MISSING_BITS);
+                    sts32(cell_g + 4 * (TILE_WST_G + g), (uint32_t)VGL_I32_MISSING);
+                }
+            }
+            if (v == S && G > 0) {
+                const uint32_t pg = s_wg + (uint32_t)(gpos - g_lo) * 4u, pr = s_wr + (uint32_t)(rpos - r_lo) * 4u;
+#pragma unroll 1
+                for (int g = 0; g < gend - gpos; ++g) {
+                    sts32(pg + 4 * g, 0u);
+                    sts32(pg + 4 * (TILE_WST_G + g), 0u);
+                }
+#pragma unroll 1
+                for (int a = 0; a < rend - rpos; ++a) sts32(pr + 4 * a, 0u);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t gb = (uint32_t)(g_hi - g_lo) * 4u, rb = (uint32_t)(r_hi - r_lo) * 4u;
+                if (gb) {
+                    if (has_gl) bulk_store(gl_t + g_lo, s_wg, gb);
+                    if (has_pl) bulk_store(pl_t + g_lo, s_wg + TILE_WST_G * 4, gb);
+                }
+                if (rb && has_ad) bulk_store(ad_t + r_lo, s_wr, rb);
+                bulk_commit();
+            }
+            cur = tile_ticket_get(raw);
+        }
+    }
+    bulk_wait_all();
+    if (tid == 0) {
+        const unsigned done = atomicAdd(p.ticket + 1, 1u);
+        if (done == gridDim.x - 1) {
+            p.ticket[0] = 0u;
+            p.ticket[1] = 0u;
+        }
+    }
+}
+
+static size_t tile_m2_dyn_smem(bool big)
+{
+    return 2048 + 4096 + (size_t)TILE_WARPS * (2 * TILE_WST_G + TILE_WST_R) * 4 + TILE_MAX_SITES * sizeof(TSite) + TILE_MAX_SITES * 16 +
+           TILE_MAX_SITES * sizeof(M2SiteE) + (big ? 0 : (size_t)TILE_CELLS * 4);
+}
+
+template <int MODE, bool BIG>
+static void launch_tile_m2_t(const DevParams& p, cudaStream_t st, int n_sms)
+{
+    const size_t dyn = tile_m2_dyn_smem(BIG);
+    cudaFuncSetAttribute(k_tile_m2<MODE, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m2<MODE, BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m2<MODE, BIG>, TILE_BLOCK, dyn);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
+    int grid = n_sms * per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    k_tile_m2<MODE, BIG><<<grid, TILE_BLOCK, dyn, st>>>(p);
+}
+
+// mode: 0 FIXED / run-constant error rate, 1 FIXED / per-site error rate, 2 LUT (per-read quality scores)
+void launch_tile_m2(const DevParams& p, cudaStream_t st, int n_sms, int mode)
+{
+    const bool big = tile_m1f_scratch_words(p.S, 1) > 0;
+    if (mode == 0) { if (big) launch_tile_m2_t<0, true>(p, st, n_sms); else launch_tile_m2_t<0, false>(p, st, n_sms); }
+    else if (mode == 1) { if (big) launch_tile_m2_t<1, true>(p, st, n_sms); else launch_tile_m2_t<1, false>(p, st, n_sms); }
+    else { if (big) launch_tile_m2_t<2, true>(p, st, n_sms); else launch_tile_m2_t<2, false>(p, st, n_sms); }
+}
+
+// ---- the sampler's per-read draws in the replay layout (vgl_native_draws): pass 0 writes the depths, pass 1 the reads
+__global__ void k_tile_m2_draws(const DevParams p, int mode, int pass, int32_t* depths, const int64_t* off, uint8_t* bases, uint8_t* qs)
+{
+    __shared__ __align__(16) unsigned char sm[2048 + 4096];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        reinterpret_cast<uint2*>(sm)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
+        if (mode == 2) reinterpret_cast<uint2*>(sm + 2048)[i] = reinterpret_cast<const uint2*>(p.qcls)[i];
+        else reinterpret_cast<uint4*>(sm + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+    }
+    __syncthreads();
+    M2Rng R;
+    R.s_alias = smem_u32(sm);
+    R.s_cdf_e = R.s_qcls = R.s_alias + 2048;
+    R.fixed_depth = p.depth_mode == VGL_DEPTH_FIXED ? (int)p.depth_mean : -1;
+    R.has_err = p.error_rate > 0.0;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n_cells) return;
+    const int64_t sl = c / p.S;
+    const uint32_t sample = (uint32_t)(c - sl * p.S);
+    const unsigned long long site = (unsigned long long)(p.first_site + sl);
+    const uint32_t gt = p.gt[c];
+    const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
+    M2SiteE se;
+    se.e = p.error_rate;
+    se.l2 = se.er = 0.0f;
+    if (mode == 1) {
+        Stream bs;
+        Key key;
+        key.k0 = p.k0; key.k1 = p.k1;
+        bs.init(key, (int64_t)site, 0xFFFFFFFFu, 0, P_SITE);
+        const double e = beta_draw(bs, p.beta_a, p.beta_b);
+        se.e = e;
+        se.l2 = (e > 0.0 && e <= 0.5) ? log2f((float)(1.0 - e)) : 0.0f;
+        se.er = (float)(e / (1.0 - e));
+    }
+    int n;
+    uint32_t w[4];
+    if (mode == 2) {
+        const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+        const u32x4 b0 = philox_rk(p, c0, c1, sample, (uint32_t)P_COUNTS << 24);
+        n = m2_depth(R, b0, gt);
+        if (pass == 0) { depths[c] = n; return; }
+        if (n == 0) return;
+        const u32x4 b1 = philox_rk(p, c0, c1, sample, ((uint32_t)P_COUNTS << 24) | 1u);
+        const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
+        u32x4 qblk;
+        for (int i = 0; i < n; ++i) {
+            const M2LutRead r = m2_lut_read(p, R, site, sample, i, g0, g1, h, qblk);
+            bases[off[c] + i] = (uint8_t)r.base;
+            qs[off[c] + i] = (uint8_t)r.qs;
+        }
+        return;
+    }
+    if (mode == 1) m2_cell_fixed<true, true>(p, R, site, sample, gt, se, n, w);
+    else m2_cell_fixed<true, false>(p, R, site, sample, gt, se, n, w);
+    if (pass == 0) { depths[c] = n; return; }
+    for (int i = 0; i < n; ++i) {
+        int b;
+        if (n > 64) b = m2_deep_base(p, site, sample, i, g0, g1, se.e);
+        else b = (int)((w[i >> 4] >> (2 * (i & 15))) & 3u);
+        bases[off[c] + i] = (uint8_t)b;
+    }
+}
+
+void launch_tile_m2_draws(const DevParams& p, cudaStream_t st, int mode, int pass, int32_t* depths, const int64_t* off, uint8_t* bases, uint8_t* qs)
+{
+    const unsigned grid = (unsigned)((p.n_cells + 127) / 128);
+    k_tile_m2_draws<<<grid, 128, 0, st>>>(p, mode, pass, depths, off, bases, qs);
+}
+
+} // namespace vgl

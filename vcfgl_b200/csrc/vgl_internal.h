@@ -92,6 +92,8 @@ struct DevParams {
     const unsigned long long* pois_alias; // [256] Walker alias table of the depth distribution: t56 << 8 | alias
     const uint32_t* err_cdf;              // [256][4] P(E <= j | n reads) * 2^32, j = 0..3
     uint32_t* cnt_scratch;                // per-CTA rows of packed counts when a site does not fit shared memory
+    // model-2 tile kernel (tile_m2.cu), --error-qs 2: alias table + info words of the per-read (quality score, error) classes
+    const uint32_t* qcls;                 // [512], tables.h qs_class_table()
     // replay
     int32_t replay;
     const int32_t* rp_depths;
@@ -110,6 +112,9 @@ void launch_emit(const DevParams& p, cudaStream_t st);
 int run_selftest(unsigned long long* n_bad, unsigned int* first_bad);
 void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms);
 void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms);
+void launch_tile_m2(const DevParams& p, cudaStream_t st, int n_sms, int mode);
+void launch_tile_m2_draws(const DevParams& p, cudaStream_t st, int mode, int pass, int32_t* depths, const int64_t* off, uint8_t* bases,
+                          uint8_t* qs);
 int tile_m1f_max_samples();
 int tile_m1f_sites_per_tile(int S);
 size_t tile_m1f_scratch_words(int S, int n_sms);
