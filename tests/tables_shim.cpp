@@ -26,7 +26,7 @@ int shim_qs_classes(double a, double b, double shift, int use_bins, const uint8_
     auto w = vgl::qs_class_table(a, b, shift, use_bins != 0, bin_lut, bin_max, &pr);
     if (w.empty()) return 0;
     memcpy(words, w.data(), w.size() * 4);
-    memcpy(prob512, pr.data(), 512 * 8);
+    memcpy(prob512, pr.data(), 257 * 8);
     return (int)w.size();
 }
 }

@@ -73,7 +73,9 @@ struct vgl_ctx {
     // device tables
     int use_fused = 0, use_tile = 0, n_sms = 148, fast_div = 0;
     int use_tile_m2 = 0, tile_m2_mode = 0; // tile_m2.cu; mode 0 / 1 / 2 = --error-qs
-    uint32_t* d_qcls = nullptr;
+    uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr;
+    double* d_m2_tab = nullptr;
+    int m2_nq = 0;
     unsigned long long *d_pois = nullptr, *d_alias = nullptr;
     uint32_t *d_errcdf = nullptr, *d_cnt_scratch = nullptr;
     int pois_n = 0;
@@ -203,7 +205,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab);
     delete ctx;
 }
 
@@ -287,11 +289,26 @@ static int create_impl(vgl_ctx* ctx)
     if (m2_cand && alias_ok) {
         ctx->tile_m2_mode = p.error_qs;
         ctx->use_tile_m2 = 1;
+        std::vector<double> consts; // (homT, het, homF) per quality score in use
         if (p.error_qs == 2) {
             const bool gl_adj = (p.adjust_qs & 1) != 0;
-            const std::vector<uint32_t> qc = qs_class_table(ctx->beta_a, ctx->beta_b, gl_adj ? p.adjust_by : 0.0, p.n_qs_bins > 0, ctx->bin_lut, ctx->bin_max);
+            std::vector<int> qv;
+            const std::vector<uint32_t> qc = qs_class_table(ctx->beta_a, ctx->beta_b, gl_adj ? p.adjust_by : 0.0, p.n_qs_bins > 0, ctx->bin_lut, ctx->bin_max, nullptr, &qv);
             if (qc.empty()) ctx->use_tile_m2 = 0; // classes outside the bins / too many: the per-read kernels keep the reference's behaviour
             else CK(upload(&ctx->d_qcls, qc));
+            for (int q : qv) { consts.push_back(kLutLog10Gl[0][q]); consts.push_back(kLutLog10Gl[1][q]); consts.push_back(kLutLog10Gl[2][q]); }
+        } else {
+            consts = {ctx->pre.homT, ctx->pre.het, ctx->pre.homF};
+        }
+        // the table-driven update needs constants that are negative (finite and non-zero, or -inf): see m2_f2d() in tile_m2.cu
+        bool safe = true;
+        for (double c : consts) safe = safe && (c < 0.0);
+        if (ctx->use_tile_m2 && safe) {
+            ctx->m2_nq = (int)consts.size() / 3;
+            CK(upload(&ctx->d_m2_tab, m2_const_table(consts)));
+            CK(upload(&ctx->d_m2_cmap, m2_class_map()));
+        } else if (p.error_qs != 2) {
+            ctx->use_tile_m2 = 0; // e.g. --precise-gl 1 with --error-rate 0 (homT = 0): the per-read kernels
         }
     }
     if (ctx->use_tile || ctx->use_tile_m2) {
@@ -476,6 +493,9 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.err_cdf = ctx->d_errcdf;
     p.cnt_scratch = ctx->d_cnt_scratch;
     p.qcls = ctx->d_qcls;
+    p.m2_tab = ctx->d_m2_tab;
+    p.m2_nq = ctx->m2_nq;
+    p.m2_cmap = ctx->d_m2_cmap;
     {
         int T = 1024 / (int)S;
         T = T < 1 ? 1 : (T > 128 ? 128 : T);
@@ -540,6 +560,10 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             p.rp_n_deep = (int64_t)deep.size();
         }
     }
+    // status word: only the model-2 tile kernel in per-read-qs mode can raise a device-side error (a quality score outside
+    // the --qs-bins ranges); it goes through the device word, cleared and copied back in stream order
+    const bool tile_status = tile_launch && ctx->use_tile_m2 && ctx->tile_m2_mode == 2;
+    if (tile_status) CK(cudaMemsetAsync(s.d_totals + 2, 0, sizeof(int64_t), st));
     const bool fused = (ctx->use_fused || ctx->use_tile_m2) && !rp;
     if (fused && !tile_launch) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));
@@ -566,7 +590,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     }
     CK(cudaGetLastError());
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
-    if (tile_launch) s.h_totals[2] = 0; // status word: the tile kernel raises no device-side errors
+    if (tile_launch && !tile_status) s.h_totals[2] = 0; // the kernel posts the totals into the pinned words itself and raises no errors
     else CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_META], st));

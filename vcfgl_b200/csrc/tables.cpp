@@ -187,15 +187,13 @@ double inc_beta(double a, double b, double x)
 }
 
 std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_bins, const uint8_t* bin_lut, int bin_max,
-                                     std::vector<double>* prob)
+                                     std::vector<double>* prob, std::vector<int>* q_values)
 {
     typedef unsigned long long u64;
     if (!(shift >= 0.0)) return {};
     const int KMAX = 420; // phred beyond this has no representable mass for any admissible Beta
-    // mass [0]/[1] = P(q, correct) / P(q, mis-called), indexed by the final quality score q (0..255)
-    std::vector<long double> mass(512, 0.0L);
-    const double mean = a / (a + b);
-    long double out_of_bins = 0.0L;
+    // mass[q] = P(final quality score q), q = 0..255; [256]: scores beyond the last --qs-bins range
+    std::vector<long double> mass(257, 0.0L);
     for (int k = 0; k <= KMAX; ++k) {
         // q index k <=> phred + shift in [k, k+1) (k = 0 also takes the part below 0 of the shifted axis: (int) truncates)
         double lo = k == 0 ? 0.0 : (double)k - shift, hi = (double)k + 1.0 - shift;
@@ -204,20 +202,12 @@ std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_
         if (lo < 0.0) lo = 0.0;
         const double p_hi = pow(10.0, -lo / 10.0), p_lo = std::isinf(hi) ? 0.0 : pow(10.0, -hi / 10.0);
         const long double P = (long double)inc_beta(a, b, p_hi) - (long double)inc_beta(a, b, p_lo);
-        const long double M = (long double)mean * ((long double)inc_beta(a + 1.0, b, p_hi) - (long double)inc_beta(a + 1.0, b, p_lo));
         if (!(P > 0.0L)) continue;
         int q;
-        if (use_bins) {
-            if (k > bin_max) { out_of_bins += P; continue; }
-            q = bin_lut[k];
-        } else {
-            q = k > 63 ? 63 : k;
-        }
-        const long double Mc = M < 0.0L ? 0.0L : (M > P ? P : M);
-        mass[2 * q] += P - Mc;
-        mass[2 * q + 1] += Mc;
+        if (use_bins) q = k > bin_max ? 256 : bin_lut[k];
+        else q = k > 63 ? 63 : k;
+        mass[q] += P;
     }
-    if (out_of_bins * 4294967296.0L >= 0.5L) return {};
     // classes with mass, quantised to 2^-32 with the rounding residue given to the heaviest class
     std::vector<int> cls_info;
     std::vector<u64> wq;
@@ -226,10 +216,10 @@ std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_
     if (!(total > 0.5L)) return {};
     u64 sum = 0;
     int heavy = 0;
-    for (int i = 0; i < 512; ++i) {
+    for (int i = 0; i < 257; ++i) {
         const u64 w = (u64)(mass[i] / total * 4294967296.0L + 0.5L);
         if (w == 0) continue;
-        cls_info.push_back((i >> 1) | ((i & 1) << 8));
+        cls_info.push_back(i < 256 ? i : (1 << 9)); // out of range: score 0 + flag (what bin_qs() of the per-read kernels returns)
         wq.push_back(w);
         if (w > wq[heavy]) heavy = (int)wq.size() - 1;
         sum += w;
@@ -240,8 +230,8 @@ std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_
     if (sum > one32) { if (wq[heavy] <= sum - one32) return {}; wq[heavy] -= sum - one32; }
     else wq[heavy] += one32 - sum;
     if (prob) {
-        prob->assign(512, 0.0);
-        for (size_t i = 0; i < wq.size(); ++i) (*prob)[(cls_info[i] & 0xFF) * 2 + (cls_info[i] >> 8)] = (double)wq[i] / 4294967296.0;
+        prob->assign(257, 0.0);
+        for (size_t i = 0; i < wq.size(); ++i) (*prob)[((cls_info[i] >> 9) & 1) ? 256 : (cls_info[i] & 0xFF)] = (double)wq[i] / 4294967296.0;
     }
     // Walker alias over K columns of capacity 2^24 each (K * 2^24 = 2^32: exact integer arithmetic)
     const u64 cap = 1ull << 24;
@@ -264,8 +254,61 @@ std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_
         if (alias[k] == k) out[k] = (uint32_t)((cap - 1) << 8) | (uint32_t)k;
         else out[k] = (uint32_t)(stay[k] << 8) | (uint32_t)alias[k]; // keep the column when the low 24 bits of the draw < stay
     }
-    for (size_t i = 0; i < cls_info.size(); ++i) out[256 + i] = (uint32_t)cls_info[i];
+    // dense index of the quality scores in use (ascending)
+    std::vector<int> qidx(256, -1), qv;
+    for (int q = 0; q < 256; ++q)
+        for (int ci : cls_info)
+            if ((ci & 0xFF) == q && qidx[q] < 0) { qidx[q] = (int)qv.size(); qv.push_back(q); }
+    if (q_values) *q_values = qv;
+    for (size_t i = 0; i < cls_info.size(); ++i) out[256 + i] = (uint32_t)cls_info[i] | ((uint32_t)qidx[cls_info[i] & 0xFF] << 16);
     return out;
+}
+
+std::vector<double> m2_const_table(const std::vector<double>& c)
+{
+    const size_t nq = c.size() / 3;
+    std::vector<double> t(nq * M2_TAB_DOUBLES, 0.0);
+    for (size_t q = 0; q < nq; ++q) {
+        const double c2 = c[3 * q], c1 = c[3 * q + 1], c0 = c[3 * q + 2];
+        double* tq = t.data() + q * M2_TAB_DOUBLES;
+        for (int b = 0; b < 4; ++b)
+            for (int k = 0; k < 5; ++k)
+                for (int j = 0; j <= k; ++j) {
+                    const int hits = (j == b) + (k == b);
+                    tq[b * 17 + k * (k + 1) / 2 + j] = hits == 2 ? c2 : (hits == 1 ? c1 : c0);
+                }
+        double* tc = tq + 68;
+        // classes: 0 xx, 1 xy, 2 yy, 3 x., 4 y., 5 ..   [0]: the read is y, [1]: the read is x
+        const double rx[6] = {c2, c1, c0, c1, c0, c0}, ry[6] = {c0, c1, c2, c0, c1, c0};
+        for (int i = 0; i < 6; ++i) { tc[i] = ry[i]; tc[8 + i] = rx[i]; }
+    }
+    return t;
+}
+
+std::vector<uint32_t> m2_class_map()
+{
+    std::vector<uint32_t> m(16 * 8, 0u);
+    for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y) {
+            if (x == y) continue;
+            uint32_t* e = m.data() + (x * 4 + y) * 8;
+            unsigned long long ids = 0;
+            unsigned mask[6] = {0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < 5; ++k)
+                for (int j = 0; j <= k; ++j) {
+                    const int rj = j == x ? 0 : (j == y ? 1 : 2), rk = k == x ? 0 : (k == y ? 1 : 2);
+                    const int hi = rj > rk ? rj : rk, lo = rj > rk ? rk : rj;
+                    const int cls = hi * (hi + 1) / 2 + lo, pair = k * (k + 1) / 2 + j;
+                    ids |= (unsigned long long)cls << (3 * pair);
+                    mask[cls] |= 1u << pair;
+                }
+            e[0] = mask[0] | (mask[1] << 16);
+            e[1] = mask[2] | (mask[3] << 16);
+            e[2] = mask[4] | (mask[5] << 16);
+            e[4] = (uint32_t)ids;
+            e[5] = (uint32_t)(ids >> 32);
+        }
+    return m;
 }
 
 bool ErrmodTables::scores_safe_for_fast_div(const std::vector<double>& bsum, const std::vector<double>& het)

@@ -40,16 +40,27 @@ std::vector<uint32_t> binomial_cdf4_u32(double e);
 // regularized incomplete beta function I_x(a, b) (continued fraction, Lentz), x in [0, 1]
 double inc_beta(double a, double b, double x);
 
-// Per-read (quality score used by the GL, mis-called or not) classes of a Beta(a, b) error probability p
-// (--error-qs 2; vcfgl.cpp:494-523): phred = -10 log10 p, q = (int)(phred + shift) (shift = --adjust-by when the
-// GL uses the adjusted score, else 0), then --qs-bins or the cap at 63.  P(q) = I(p_hi) - I(p_lo) and
-// P(q and error) = E[p; p in the class] = a/(a+b) (I_{a+1,b}(p_hi) - I_{a+1,b}(p_lo)) since the read is mis-called
-// with probability p (vcfgl.cpp:485).  Returned: 512 words = a Walker alias table over 256 columns
-// (threshold24 << 8 | alias; probabilities quantised to 2^-32) followed by the class info words (q | err << 8);
-// `prob` receives the quantised class probabilities (for tests).  Empty when the classes do not fit or a class
-// with positive probability falls outside the --qs-bins ranges (the reference exits there, vcfgl.cpp:63).
+// Law of the per-read quality score the GL uses under --error-qs 2 (vcfgl.cpp:494-523): the read's error probability p
+// is Beta(a, b), phred = -10 log10 p, q = (int)(phred + shift) (shift = --adjust-by when the GL uses the adjusted score,
+// else 0), then --qs-bins or the cap at 63; P(q) = I(p_hi) - I(p_lo).  (The read is mis-called with the run-constant
+// --error-rate, independently of its quality score: vcfgl.cpp:485 draws before and apart from :495.)
+// Returned: 512 words = a Walker alias table over 256 columns (threshold24 << 8 | alias; probabilities quantised to
+// 2^-32) followed by the class info words: q | out-of-range << 9 | dense index of q << 16 (ascending q; `q_values`
+// receives the scores).  Scores beyond the last --qs-bins range (the reference exits when it draws one, vcfgl.cpp:63)
+// form a class of their own (score 0, bit 9) so that the kernel can raise VGL_ERANGE.  `prob` receives the quantised
+// probabilities ([q], out of range at [256]; for tests).  Empty when the classes do not fit 256 columns.
 std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_bins, const uint8_t* bin_lut, int bin_max,
-                                     std::vector<double>* prob = nullptr);
+                                     std::vector<double>* prob = nullptr, std::vector<int>* q_values = nullptr);
+
+// Constant tables of the model-2 tile kernel for each (homT, het, homF) triple: per triple M2_TAB_DOUBLES doubles =
+// [4 read bases][17] the constant each of the 15 base pairs (k*(k+1)/2 + j, 4 = unobserved allele) receives from a
+// read of that base (gl_methods.cpp:27-48), then [2][8] the constants of the six classes {xx, xy, yy, x., y., ..} of
+// a cell whose reads show two bases x, y for a read of y ([0]) or x ([1]).
+enum { M2_TAB_DOUBLES = 84 };
+std::vector<double> m2_const_table(const std::vector<double>& homT_het_homF);
+// [16 = x*4+y][8 words]: words 0..2 = six 16-bit masks of the base pairs in each class, words 4,5 = the class of
+// every base pair (3 bits each, pair k at bits 3k)
+std::vector<uint32_t> m2_class_map();
 
 // qScore_to_log10_gl[3][257] (shared.cpp:110-114)
 extern const double kLutLog10Gl[3][257];

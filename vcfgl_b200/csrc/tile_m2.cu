@@ -10,19 +10,24 @@
 // the read sequence, not on counts.  The sequence is still drawn at count level where that is exact:
 //   depth            alias table (as the model-1 tile kernel)
 //   haplotype picks  one random bit per read
-//   FIXED: number of mis-called reads E ~ Binomial(n, e), their positions uniform without replacement, wrong base
-//          uniform over the other three -- the joint law of n iid reads with P(error) = e
-//   LUT:   per read one draw from the joint law of (quality-score class, mis-called or not) of a Beta(a, b)
-//          error probability p: P(class k) = I(hi_k) - I(lo_k), P(class k and error) = E[p; p in class k]
-//          = a/(a+b) * (I_{a+1,b}(hi_k) - I_{a+1,b}(lo_k)); tabulated on the host (tables.cpp), alias-sampled here
+//   mis-calls        number of mis-called reads E ~ Binomial(n, e), their positions uniform without replacement, wrong
+//                    base uniform over the other three -- the joint law of n iid reads with P(error) = e
+//   LUT: quality     per read one alias-table draw from the law of the (binned / adjusted) quality score of a
+//        scores      Beta(a, b) error probability, P(q) = I(p_hi) - I(p_lo), tabulated on the host (tables.cpp).  The
+//                    reference draws a read's quality independently of whether the read was mis-called (vcfgl.cpp:485, 495)
 // Every draw is a pure function of (seed, site, sample[, read]); phase C re-derives the sequence of phase A instead
 // of storing it.  Cells deeper than 64 reads use one Philox block per read (the per-read sampler of kernels.cu).
 //
 // Phases per tile as in tile_m1f.cu: A sample + FORMAT/DP + site totals, B per-site record, C score + emit
 // (scatter in allele order into the warp's shared-memory slice, one bulk async copy per plane).
+#include "tables.h"
 #include "tile_common.cuh"
 
 namespace vgl {
+
+#define M2_TAB_BYTES (M2_TAB_DOUBLES * 8) // per quality score: pair table [4][17] doubles, then class table [2][8]
+#define M2_TAB_MAXQ 8                     // scores whose tables fit the shared-memory copy
+#define M2_TAB_CLS 544                    // byte offset of the class table
 
 struct __align__(16) M2SiteE {
     double e;  // base-picking error probability of the site
@@ -33,7 +38,7 @@ struct __align__(16) M2SiteE {
 struct M2Rng {
     uint32_t s_alias; // shared address: Poisson alias table
     uint32_t s_cdf_e; // shared address: [256] uint4 P(E <= j | n) * 2^32 (run-constant error rate)
-    uint32_t s_qcls;  // shared address: LUT mode, [256] (threshold24 << 8 | alias) then [256] class -> (qs | err << 8)
+    uint32_t s_qcls;  // shared address: LUT mode, [256] (threshold24 << 8 | alias) then [256] class info words
     int fixed_depth;
     bool has_err;
 };
@@ -161,33 +166,18 @@ __device__ __forceinline__ uint32_t m2_cell_fixed(const DevParams& p, const M2Rn
     return ad;
 }
 
-// LUT-mode cell: per read one word of purpose P_QS (block i>>2, word i&3) -> alias draw of (class, error);
-// haplotype bit i from block 0/1 of P_COUNTS as in FIXED mode; the wrong base of a mis-called read from word z of
-// the read's P_READ block.  Cells deeper than 64 reads take their haplotype bits from the P_READ block as well.
-struct M2LutRead {
-    int base, qs;
-};
-__device__ __forceinline__ M2LutRead m2_lut_read(const DevParams& p, const M2Rng& R, unsigned long long site, uint32_t sample, int i, int g0,
-                                                 int g1, unsigned long long h, u32x4& qblk)
+// LUT mode: the quality score of read i from word i&3 of block i>>2 of the cell's P_QS counter -> alias draw.
+// Returns the class info word (q | out-of-range << 9 | dense index << 16).
+__device__ __forceinline__ uint32_t m2_lut_qs(const DevParams& p, const M2Rng& R, unsigned long long site, uint32_t sample, int i, u32x4& qblk)
 {
-    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
-    if ((i & 3) == 0) qblk = philox_rk(p, c0, c1, sample, ((uint32_t)P_QS << 24) | (uint32_t)(i >> 2));
+    if ((i & 3) == 0) qblk = philox_rk(p, (uint32_t)site, (uint32_t)(site >> 32) & 0xFFu, sample, ((uint32_t)P_QS << 24) | (uint32_t)(i >> 2));
     const uint32_t r = (i & 3) == 0 ? qblk.x : ((i & 3) == 1 ? qblk.y : ((i & 3) == 2 ? qblk.z : qblk.w));
     const uint32_t col = r >> 24;
     const uint32_t en = lds32(R.s_qcls + col * 4u);
     const uint32_t cls = (r & 0xFFFFFFu) < (en >> 8) ? col : (en & 0xFFu);
-    const uint32_t info = lds32(R.s_qcls + 1024u + cls * 4u); // qs | err << 8
-    M2LutRead out;
-    out.qs = (int)(info & 0xFFu);
-    int hb;
-    u32x4 rd;
-    const bool err = (info >> 8) & 1u;
-    if (i >= 64 || err) rd = philox_rk(p, c0, c1 | ((uint32_t)i << 8), sample, (uint32_t)P_READ << 24);
-    if (i < 64) hb = (int)((h >> i) & 1ull);
-    else hb = (int)(rd.y >> 31);
-    const int truth = hb ? g0 : g1;
-    out.base = err ? (truth + 1 + (int)mulhi32(rd.z, 3u)) & 3 : truth;
-    return out;
+    const uint32_t info = lds32(R.s_qcls + 1024u + cls * 4u);
+    if (info & 0x200u) atomicExch(p.status, (int)VGL_ERANGE); // apply_qs_bins() -> ERROR, vcfgl.cpp:63
+    return info;
 }
 
 // one read of base b (ACGT int) with constants c2 / c1 / c0 (both / one / no allele of the genotype equals the
@@ -222,6 +212,79 @@ __device__ __forceinline__ void m2_update(float (&gl)[15], int b, double c2, dou
     for (int k = 0; k < 15; ++k) gl[k] = __fsub_rn(gl[k], mx);
 }
 
+// ---- table-driven forms (constants finite and non-zero, or -inf; the host checks).  The float -> double conversion
+// of a GL value is done by integer arithmetic: every value is <= 0, so with the sign bit set
+// hi = (bits >> 3) + 0xA8000000, lo = bits << 29 is the exact double; +0 / -0 map to -2^-383 / -2^-127, which vanish
+// in the sum with any table constant, and -inf maps to -2^128, which the double -> float conversion turns back into -inf.
+__device__ __forceinline__ double m2_f2d(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return __hiloint2double((int)((b >> 3) + 0xA8000000u), (int)(b << 29));
+}
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+// one read on all 15 base pairs; t = shared address of the read base's row of the pair table
+__device__ __forceinline__ void m2_update_pairs(float (&gl)[15], uint32_t t)
+{
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        gl[k] = __double2float_rn(__dadd_rn(m2_f2d(gl[k]), lds_f64(t + 8u * k)));
+        mx = fmaxf(mx, gl[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) gl[k] = __fsub_rn(gl[k], mx);
+}
+// one read on the six classes of a two-base cell; t = shared address of the class row ([read is x])
+__device__ __forceinline__ void m2_update_classes(float (&gc)[6], uint32_t t)
+{
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        gc[k] = __double2float_rn(__dadd_rn(m2_f2d(gc[k]), lds_f64(t + 8u * k)));
+        mx = fmaxf(mx, gc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) gc[k] = __fsub_rn(gc[k], mx);
+}
+// bit i = byte i of x is non-zero
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x)
+{
+    return (((__vcmpne4(x, 0u)) & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+// the reads of one cell, in order
+template <int MODE>
+struct M2Reads {
+    uint32_t w0, w1, w2, w3, cur; // packed 2-bit base codes (cells of at most 64 reads)
+    bool deep;
+    unsigned long long site;
+    uint32_t sample;
+    int g0, g1;
+    double e;
+    u32x4 qblk;
+    // returns the base of read i (reads must be asked in order); qoff / qs: LUT mode
+    __device__ __forceinline__ int get(const DevParams& p, const M2Rng& R, int i, uint32_t& qoff, int& qs)
+    {
+        qoff = 0u;
+        qs = 0;
+        if (MODE == 2) {
+            const uint32_t info = m2_lut_qs(p, R, site, sample, i, qblk);
+            qs = (int)(info & 0xFFu);
+            qoff = ((info >> 16) & 0xFFu) * (uint32_t)M2_TAB_BYTES;
+        }
+        if (deep) return m2_deep_base(p, site, sample, i, g0, g1, e);
+        if ((i & 15) == 0) cur = (i >> 4) == 0 ? w0 : ((i >> 4) == 1 ? w1 : ((i >> 4) == 2 ? w2 : w3));
+        const int b = (int)(cur & 3u);
+        cur >>= 2;
+        return b;
+    }
+};
+
 // final GL / PL of a cell, scattered into the warp's stage slice in allele order (vcfgl.cpp:907-939)
 __device__ __forceinline__ void m2_emit_cell(const float (&gl)[15], const uint4 slot, uint32_t cell_g, bool has_gl, bool has_pl)
 {
@@ -241,14 +304,19 @@ __device__ __forceinline__ void m2_emit_cell(const float (&gl)[15], const uint4 
 }
 
 // MODE 0: FIXED with the run-constant error rate, 1: FIXED with a per-site error rate, 2: LUT (per-read qs)
-template <int MODE, bool BIG>
+// TAB: the constants of every quality score in use fit the shared-memory tables (always in FIXED mode) -> table-driven
+// updates and the six-class form for warps whose cells all show at most two bases
+template <int MODE, bool BIG, bool TAB>
 __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    // layout: alias [256] u64 | cdf_e [256] uint4 (LUT: class alias + class info) | stage | st [sites] | tot [sites][4] | site_e [sites] | cnt [cap]
+    // layout: alias [256] u64 | cdf_e [256] uint4 | stage | st [sites] | tot [sites][4] | site_e [sites] |
+    //         constant tables [M2_TAB_MAXQ] | class map [16][8] | class scratch [warps][6][32] | qs alias + info [512] | cnt [cap]
     constexpr int WST = 2 * TILE_WST_G + TILE_WST_R;
     constexpr uint32_t OFF_STAGE = 2048 + 4096, OFF_ST = OFF_STAGE + TILE_WARPS * WST * 4, OFF_TOT = OFF_ST + TILE_MAX_SITES * sizeof(TSite),
-                       OFF_SE = OFF_TOT + TILE_MAX_SITES * 16, OFF_CNT = OFF_SE + TILE_MAX_SITES * sizeof(M2SiteE);
+                       OFF_SE = OFF_TOT + TILE_MAX_SITES * 16, OFF_TAB = OFF_SE + TILE_MAX_SITES * sizeof(M2SiteE),
+                       OFF_CMAP = OFF_TAB + M2_TAB_MAXQ * M2_TAB_BYTES, OFF_SCR = OFF_CMAP + 512, OFF_QCLS = OFF_SCR + TILE_WARPS * 768,
+                       OFF_CNT = OFF_QCLS + 2048;
     TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
     int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
     M2SiteE* site_e = reinterpret_cast<M2SiteE*>(tile_smem + OFF_SE);
@@ -265,22 +333,24 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
     const uint32_t s_smem = smem_u32(tile_smem);
     for (int i = tid; i < 256; i += TILE_BLOCK) {
         reinterpret_cast<uint2*>(tile_smem)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
-        if (MODE == 2) {
-            reinterpret_cast<uint2*>(tile_smem + 2048)[i] = reinterpret_cast<const uint2*>(p.qcls)[i]; // 512 words
-        } else {
-            reinterpret_cast<uint4*>(tile_smem + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
-        }
+        reinterpret_cast<uint4*>(tile_smem + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+        if (MODE == 2) reinterpret_cast<uint2*>(tile_smem + OFF_QCLS)[i] = reinterpret_cast<const uint2*>(p.qcls)[i]; // 512 words
     }
     for (int i = tid; i < TILE_MAX_SITES * 4; i += TILE_BLOCK) tot[i] = 0;
+    if (TAB) {
+        for (int i = tid; i < p.m2_nq * M2_TAB_DOUBLES; i += TILE_BLOCK) reinterpret_cast<double*>(tile_smem + OFF_TAB)[i] = p.m2_tab[i];
+        for (int i = tid; i < 128; i += TILE_BLOCK) reinterpret_cast<uint32_t*>(tile_smem + OFF_CMAP)[i] = p.m2_cmap[i];
+    }
     if (tid == 0) {
         s_next = (int)atomicAdd(p.ticket, 1u);
         s_ctr[0] = s_ctr[1] = 0u;
     }
     if (tid < 32) s_zero[tid] = 0u;
+    const uint32_t s_tab = s_smem + OFF_TAB, s_cmap = s_smem + OFF_CMAP, s_scr = s_smem + OFF_SCR + warp * 768 + lane * 4;
     M2Rng R;
     R.s_alias = s_smem;
     R.s_cdf_e = s_smem + 2048;
-    R.s_qcls = s_smem + 2048;
+    R.s_qcls = s_smem + OFF_QCLS;
     R.fixed_depth = p.depth_mode == VGL_DEPTH_FIXED ? (int)p.depth_mean : -1;
     R.has_err = p.error_rate > 0.0;
     const uint32_t inv_s4 = (uint32_t)(((1ull << 32) + S4 - 1) / S4);
@@ -349,21 +419,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
                 if (real) {
                     int n;
                     uint32_t wseq[4];
-                    if (MODE == 2) {
-                        const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
-                        const unsigned long long site = site_base + (uint32_t)sl;
-                        const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
-                        const u32x4 b0 = philox_rk(p, c0, c1, (uint32_t)v, (uint32_t)P_COUNTS << 24);
-                        n = m2_depth(R, b0, gt);
-                        if (n > 0) {
-                            const u32x4 b1 = philox_rk(p, c0, c1, (uint32_t)v, ((uint32_t)P_COUNTS << 24) | 1u);
-                            const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
-                            u32x4 qblk;
-                            for (int i = 0; i < n; ++i) ad += 1u << (8 * m2_lut_read(p, R, site, (uint32_t)v, i, g0, g1, h, qblk).base);
-                        }
-                    } else {
-                        ad = m2_cell_fixed<false, MODE == 1>(p, R, site_base + (uint32_t)sl, (uint32_t)v, gt, MODE == 1 ? site_e[sl] : run_e, n, wseq);
-                    }
+                    ad = m2_cell_fixed<false, MODE == 1>(p, R, site_base + (uint32_t)sl, (uint32_t)v, gt, MODE == 1 ? site_e[sl] : run_e, n, wseq);
                     dp_t[(uint32_t)(iv - sl * PAD)] = n;
                 }
                 if (iv < nv) {
@@ -429,41 +485,75 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
             const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
             // ---- the cell's reads, in order
             float gl[15];
-            {
-                const uint32_t sw[4] = {slot.x, slot.y, slot.z, slot.w};
-#pragma unroll
-                for (int k = 0; k < 15; ++k) gl[k] = __byte_perm(sw[k >> 2], 0u, 0x4440u | (k & 3)) != 0xFFu ? -0.0f : -CUDART_INF_F; // bcf_utils.h:310
-            }
             const int n = (int)__vsadu4(c4, 0u);
-            if (live && n > 0) {
-                uint32_t gt = gt_t[(uint32_t)(iv - sl * PAD)];
-                const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
-                const unsigned long long site = site_base + (uint32_t)sl;
-                if (MODE == 2) {
-                    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
-                    const u32x4 b0 = philox_rk(p, c0, c1, (uint32_t)v, (uint32_t)P_COUNTS << 24);
-                    const u32x4 b1 = philox_rk(p, c0, c1, (uint32_t)v, ((uint32_t)P_COUNTS << 24) | 1u);
-                    const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
-                    u32x4 qblk;
-                    for (int i = 0; i < n; ++i) {
-                        const M2LutRead r = m2_lut_read(p, R, site, (uint32_t)v, i, g0, g1, h, qblk);
-                        const double c2 = __ldg(p.lut_log10 + r.qs), c1d = __ldg(p.lut_log10 + 257 + r.qs), c0d = __ldg(p.lut_log10 + 514 + r.qs);
-                        m2_update(gl, r.base, c2, c1d, c0d);
-                    }
+            const bool work = live && n > 0;
+            // base pairs that are genotypes of the site (bit k)
+            const uint32_t pv = (nonzero_bytes(~slot.x) | (nonzero_bytes(~slot.y) << 4) | (nonzero_bytes(~slot.z) << 8) | (nonzero_bytes(~slot.w) << 12)) & 0x7FFFu;
+            M2Reads<MODE> rd;
+            rd.deep = false;
+            rd.w0 = rd.w1 = rd.w2 = rd.w3 = rd.cur = 0u;
+            if (work) {
+                const uint32_t gt = gt_t[(uint32_t)(iv - sl * PAD)];
+                rd.g0 = gt & 0x3;
+                rd.g1 = (gt >> 4) & 0x3;
+                rd.site = site_base + (uint32_t)sl;
+                rd.sample = (uint32_t)v;
+                rd.e = MODE == 1 ? site_e[sl].e : run_e.e;
+                if (n > 64) {
+                    rd.deep = true;
                 } else {
-                    const M2SiteE se = MODE == 1 ? site_e[sl] : run_e;
-                    const double c2 = p.homT, c1d = p.het, c0d = p.homF;
-                    if (n > 64) {
-                        for (int i = 0; i < n; ++i) m2_update(gl, m2_deep_base(p, site, (uint32_t)v, i, g0, g1, se.e), c2, c1d, c0d);
-                    } else {
-                        int nn;
-                        uint32_t wseq[4];
-                        m2_cell_fixed<true, MODE == 1>(p, R, site, (uint32_t)v, gt, se, nn, wseq);
-                        uint32_t curw = 0u;
-                        for (int i = 0; i < n; ++i) {
-                            if ((i & 15) == 0) curw = (i >> 4) == 0 ? wseq[0] : ((i >> 4) == 1 ? wseq[1] : ((i >> 4) == 2 ? wseq[2] : wseq[3]));
-                            m2_update(gl, (int)(curw & 3u), c2, c1d, c0d);
-                            curw >>= 2;
+                    int nn;
+                    uint32_t wseq[4];
+                    m2_cell_fixed<true, MODE == 1>(p, R, rd.site, (uint32_t)v, gt, MODE == 1 ? site_e[sl] : run_e, nn, wseq);
+                    rd.w0 = wseq[0]; rd.w1 = wseq[1]; rd.w2 = wseq[2]; rd.w3 = wseq[3];
+                }
+            }
+            const uint32_t seen = nonzero_bytes(c4); // bases this cell's reads show
+            const bool two = TAB && __all_sync(0xffffffffu, !work || (__popc(seen) <= 2 && !rd.deep));
+            if (two) {
+                // at most two bases x, y in every cell of the warp: the 15 base pairs fall into six classes with
+                // identical histories {xx, xy, yy, x., y., ..} ('.' = any other allele); a class takes part in the
+                // max when one of its pairs is a genotype of the site
+                const int x = __ffs(seen | 16u) - 1, rest = seen & (seen - 1u);
+                const int y = rest ? __ffs(rest) - 1 : ((x + 1) & 3);
+                const uint32_t ent = s_cmap + (uint32_t)(((x & 3) * 4 + y) * 32);
+                const uint4 cm = lds128(ent);
+                const uint2 ids = lds64(ent + 16u);
+                float gc[6];
+                gc[0] = (pv & cm.x & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
+                gc[1] = (pv & (cm.x >> 16)) ? -0.0f : -CUDART_INF_F;
+                gc[2] = (pv & cm.y & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
+                gc[3] = (pv & (cm.y >> 16)) ? -0.0f : -CUDART_INF_F;
+                gc[4] = (pv & cm.z & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
+                gc[5] = (pv & (cm.z >> 16)) ? -0.0f : -CUDART_INF_F;
+                if (work) {
+                    for (int i = 0; i < n; ++i) {
+                        uint32_t qoff;
+                        int qs;
+                        const int b = rd.get(p, R, i, qoff, qs);
+                        m2_update_classes(gc, s_tab + qoff + M2_TAB_CLS + (b == x ? 64u : 0u));
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 6; ++k) sts32(s_scr + 128u * k, __float_as_uint(gc[k]));
+                const unsigned long long id64 = ((unsigned long long)ids.y << 32) | ids.x;
+#pragma unroll
+                for (int k = 0; k < 15; ++k) gl[k] = __uint_as_float(lds32(s_scr + 128u * (uint32_t)((id64 >> (3 * k)) & 7ull)));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 15; ++k) gl[k] = ((pv >> k) & 1u) ? -0.0f : -CUDART_INF_F; // bcf_utils.h:310
+                if (work) {
+                    for (int i = 0; i < n; ++i) {
+                        uint32_t qoff;
+                        int qs;
+                        const int b = rd.get(p, R, i, qoff, qs);
+                        if (TAB) {
+                            m2_update_pairs(gl, s_tab + qoff + (uint32_t)b * 136u);
+                        } else if (MODE == 2) {
+                            m2_update(gl, b, __ldg(p.lut_log10 + qs), __ldg(p.lut_log10 + 257 + qs), __ldg(p.lut_log10 + 514 + qs));
+                        } else {
+                            m2_update(gl, b, p.homT, p.het, p.homF);
                         }
                     }
                 }
@@ -522,46 +612,48 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
 static size_t tile_m2_dyn_smem(bool big)
 {
     return 2048 + 4096 + (size_t)TILE_WARPS * (2 * TILE_WST_G + TILE_WST_R) * 4 + TILE_MAX_SITES * sizeof(TSite) + TILE_MAX_SITES * 16 +
-           TILE_MAX_SITES * sizeof(M2SiteE) + (big ? 0 : (size_t)TILE_CELLS * 4);
+           TILE_MAX_SITES * sizeof(M2SiteE) + M2_TAB_MAXQ * M2_TAB_BYTES + 512 + TILE_WARPS * 768 + 2048 + (big ? 0 : (size_t)TILE_CELLS * 4);
 }
 
-template <int MODE, bool BIG>
+template <int MODE, bool BIG, bool TAB>
 static void launch_tile_m2_t(const DevParams& p, cudaStream_t st, int n_sms)
 {
     const size_t dyn = tile_m2_dyn_smem(BIG);
-    cudaFuncSetAttribute(k_tile_m2<MODE, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_tile_m2<MODE, BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m2<MODE, BIG>, TILE_BLOCK, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m2<MODE, BIG, TAB>, TILE_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
     int grid = n_sms * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    k_tile_m2<MODE, BIG><<<grid, TILE_BLOCK, dyn, st>>>(p);
+    k_tile_m2<MODE, BIG, TAB><<<grid, TILE_BLOCK, dyn, st>>>(p);
 }
 
 // mode: 0 FIXED / run-constant error rate, 1 FIXED / per-site error rate, 2 LUT (per-read quality scores)
 void launch_tile_m2(const DevParams& p, cudaStream_t st, int n_sms, int mode)
 {
-    const bool big = tile_m1f_scratch_words(p.S, 1) > 0;
-    if (mode == 0) { if (big) launch_tile_m2_t<0, true>(p, st, n_sms); else launch_tile_m2_t<0, false>(p, st, n_sms); }
-    else if (mode == 1) { if (big) launch_tile_m2_t<1, true>(p, st, n_sms); else launch_tile_m2_t<1, false>(p, st, n_sms); }
-    else { if (big) launch_tile_m2_t<2, true>(p, st, n_sms); else launch_tile_m2_t<2, false>(p, st, n_sms); }
+    const bool big = tile_m1f_scratch_words(p.S, 1) > 0, tab = p.m2_tab != nullptr && p.m2_nq <= M2_TAB_MAXQ;
+    if (mode == 0) { if (big) launch_tile_m2_t<0, true, true>(p, st, n_sms); else launch_tile_m2_t<0, false, true>(p, st, n_sms); }
+    else if (mode == 1) { if (big) launch_tile_m2_t<1, true, true>(p, st, n_sms); else launch_tile_m2_t<1, false, true>(p, st, n_sms); }
+    else if (tab) { if (big) launch_tile_m2_t<2, true, true>(p, st, n_sms); else launch_tile_m2_t<2, false, true>(p, st, n_sms); }
+    else { if (big) launch_tile_m2_t<2, true, false>(p, st, n_sms); else launch_tile_m2_t<2, false, false>(p, st, n_sms); }
 }
 
 // ---- the sampler's per-read draws in the replay layout (vgl_native_draws): pass 0 writes the depths, pass 1 the reads
 __global__ void k_tile_m2_draws(const DevParams p, int mode, int pass, int32_t* depths, const int64_t* off, uint8_t* bases, uint8_t* qs)
 {
-    __shared__ __align__(16) unsigned char sm[2048 + 4096];
+    __shared__ __align__(16) unsigned char sm[2048 + 4096 + 2048];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         reinterpret_cast<uint2*>(sm)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
-        if (mode == 2) reinterpret_cast<uint2*>(sm + 2048)[i] = reinterpret_cast<const uint2*>(p.qcls)[i];
-        else reinterpret_cast<uint4*>(sm + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+        reinterpret_cast<uint4*>(sm + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+        if (mode == 2) reinterpret_cast<uint2*>(sm + 6144)[i] = reinterpret_cast<const uint2*>(p.qcls)[i];
     }
     __syncthreads();
     M2Rng R;
     R.s_alias = smem_u32(sm);
-    R.s_cdf_e = R.s_qcls = R.s_alias + 2048;
+    R.s_cdf_e = R.s_alias + 2048;
+    R.s_qcls = R.s_alias + 6144;
     R.fixed_depth = p.depth_mode == VGL_DEPTH_FIXED ? (int)p.depth_mean : -1;
     R.has_err = p.error_rate > 0.0;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -586,22 +678,6 @@ __global__ void k_tile_m2_draws(const DevParams p, int mode, int pass, int32_t* 
     }
     int n;
     uint32_t w[4];
-    if (mode == 2) {
-        const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
-        const u32x4 b0 = philox_rk(p, c0, c1, sample, (uint32_t)P_COUNTS << 24);
-        n = m2_depth(R, b0, gt);
-        if (pass == 0) { depths[c] = n; return; }
-        if (n == 0) return;
-        const u32x4 b1 = philox_rk(p, c0, c1, sample, ((uint32_t)P_COUNTS << 24) | 1u);
-        const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
-        u32x4 qblk;
-        for (int i = 0; i < n; ++i) {
-            const M2LutRead r = m2_lut_read(p, R, site, sample, i, g0, g1, h, qblk);
-            bases[off[c] + i] = (uint8_t)r.base;
-            qs[off[c] + i] = (uint8_t)r.qs;
-        }
-        return;
-    }
     if (mode == 1) m2_cell_fixed<true, true>(p, R, site, sample, gt, se, n, w);
     else m2_cell_fixed<true, false>(p, R, site, sample, gt, se, n, w);
     if (pass == 0) { depths[c] = n; return; }
@@ -610,6 +686,10 @@ __global__ void k_tile_m2_draws(const DevParams p, int mode, int pass, int32_t* 
         if (n > 64) b = m2_deep_base(p, site, sample, i, g0, g1, se.e);
         else b = (int)((w[i >> 4] >> (2 * (i & 15))) & 3u);
         bases[off[c] + i] = (uint8_t)b;
+    }
+    if (mode == 2) {
+        u32x4 qblk;
+        for (int i = 0; i < n; ++i) qs[off[c] + i] = (uint8_t)(m2_lut_qs(p, R, site, sample, i, qblk) & 0xFFu);
     }
 }
 

@@ -94,6 +94,9 @@ struct DevParams {
     uint32_t* cnt_scratch;                // per-CTA rows of packed counts when a site does not fit shared memory
     // model-2 tile kernel (tile_m2.cu), --error-qs 2: alias table + info words of the per-read (quality score, error) classes
     const uint32_t* qcls;                 // [512], tables.h qs_class_table()
+    const double* m2_tab;                 // [m2_nq][M2_TAB_DOUBLES] constants per quality score in use, tables.h m2_const_table(); null: none
+    int32_t m2_nq;
+    const uint32_t* m2_cmap;              // [16][8], tables.h m2_class_map()
     // replay
     int32_t replay;
     const int32_t* rp_depths;
