@@ -11,6 +11,9 @@ hot path over one batch of 131072 sites (13.1 M cells, ~1.9 GB of tag planes -- 
          on the launching stream (torch's current stream, handed to libvgl).
   e2e    the same metric through the C ABI with HOST buffers: pinned H2D of the packed
          genotypes and D2H of every tag plane inside the timed region, two slots in flight.
+         Planes cross PCIe in the ABI's VGL_HOST_NARROW form (GL float32; PL / AD / DP as the
+         8-bit values BCF stores, narrowed on the device); `e2e.i32_planes` is the same loop
+         with the int32 planes of VGL_HOST_I32 (add_tags() layout) for comparison.
   roofline      algorithmic bytes / device time of the kernels, against the
                 measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the reference binary itself (oracle/_ref/vcfgl_ref, built from /root/reference)
@@ -296,13 +299,9 @@ def gpu_arm(opt):
             print(json.dumps({"profiling_only": True, "value": value, "kernel_ms": (kern_ms / K).tolist()}))
         return
     Ke = max(2, min(K, 4))
-    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=True))
     s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
-    ctx.set_stream(0, s_a.cuda_stream)
-    ctx.set_stream(1, s_b.cuda_stream)
-    bufs = [ctx.input_buffer(0), ctx.input_buffer(1)]
 
-    def e2e_steps(n, first):
+    def e2e_steps(ctx, bufs, n, first):
         pend = []
         d2h = 0
         for i in range(n):
@@ -319,26 +318,39 @@ def gpu_arm(opt):
         return d2h
 
     def out_bytes(b):
-        n = b.n_sites * S * 4 + b.n_sites * capi.SITE_DTYPE.itemsize
-        n += 4 * b.g_elems * sum(x is not None for x in (b.gl, b.pl, b.gp))
-        n += 4 * b.r_elems * sum(x is not None for x in (b.ad, b.adf, b.adr))
+        r = b.raw
+        w = (b.narrow_bits // 8) if b.narrow_bits else 4          # DP / AD element width
+        n = b.n_sites * S * w + b.n_sites * capi.SITE_DTYPE.itemsize
+        n += 4 * b.g_elems * sum(bool(x) for x in (r.gl, r.gp))
+        n += b.g_elems * (4 * bool(r.pl) + bool(r.pl_u8))
+        n += w * b.r_elems * sum(bool(x) for x in ((r.ad_n, r.adf_n, r.adr_n) if b.narrow_bits else (r.ad, r.adf, r.adr)))
         return int(n)
 
-    e2e_steps(2, site0 + (K + W) * B)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(s_a)
-    d2h_bytes = e2e_steps(Ke, site0 + (K + W) * B)
-    s_a.wait_stream(s_b)
-    e1.record(s_a)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * Ke * cells_per_step / (e2e_ms * 1e-3)
-    ctx.close()
+    def e2e_run(mode):
+        ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=mode))
+        ctx.set_stream(0, s_a.cuda_stream)
+        ctx.set_stream(1, s_b.cuda_stream)
+        bufs = [ctx.input_buffer(0), ctx.input_buffer(1)]
+        e2e_steps(ctx, bufs, 2, site0 + (K + W) * B)
+        barrier()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s_a)
+        d2h = e2e_steps(ctx, bufs, Ke, site0 + (K + W) * B)
+        s_a.wait_stream(s_b)
+        e1.record(s_a)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        n_launch = ctx.launch_count() - l0
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        ctx.close()
+        return world * Ke * cells_per_step / (ms * 1e-3), d2h, n_launch
+
+    e2e_i32, d2h_i32, _ = e2e_run(capi.HOST_I32)
+    e2e_value, d2h_bytes, e2e_launches = e2e_run(capi.HOST_NARROW)
 
     if rank != 0:
         if dist is not None:
@@ -392,7 +404,10 @@ def gpu_arm(opt):
                    "sites_with_15_genotypes": g_share, "sharding": "contiguous site ranges per GPU, no collective"},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * S), "d2h_bytes_per_step": d2h_bytes,
-                "steps": Ke},
+                "steps": Ke, "gpu_launches": int(e2e_launches),
+                "planes": "VGL_HOST_NARROW: GL float32, PL/AD/DP narrowed on the device to the 8-bit values BCF stores",
+                "i32_planes": {"value": e2e_i32, "d2h_bytes_per_step": d2h_i32,
+                               "planes": "VGL_HOST_I32: every plane int32/float32 as add_tags() hands them to htslib"}},
         "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(line))
     if dist is not None:

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 1
+#define VGL_ABI_VERSION 2
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -60,7 +60,8 @@ typedef enum vgl_status {
     VGL_ECUDA = -3,   /* CUDA runtime error; vgl_last_error() has the text */
     VGL_ESTATE = -4,  /* slot busy / not submitted */
     VGL_ERANGE = -5,  /* a quality score fell outside every --qs-bins range (vcfgl.cpp:63) */
-    VGL_ENODEV = -6   /* no CUDA device: there is no CPU path */
+    VGL_ENODEV = -6,  /* no CUDA device: there is no CPU path */
+    VGL_EOVERFLOW = -7 /* batch status with VGL_HOST_NARROW: a depth / allelic depth did not fit narrow_bits (values were saturated) */
 } vgl_status;
 
 /* vgl_params.tag_mask: which tags add_tags() would emit (io.h:90-102) */
@@ -74,6 +75,12 @@ enum {
 enum { VGL_DEPTH_POISSON = 0,            /* --depth x        rng.h:284 */
        VGL_DEPTH_POISSON_PER_SAMPLE = 1, /* --depths-file    rng.h:318 */
        VGL_DEPTH_FIXED = 2 };            /* every cell gets exactly (int)depth_mean reads */
+
+/* vgl_params.host_output: what vgl_wait() brings to pinned host memory */
+enum { VGL_HOST_NONE = 0,    /* nothing but the totals and the status word: results stay in HBM */
+       VGL_HOST_I32 = 1,     /* every plane exactly as add_tags() hands it to htslib (int32 / float32, bcf_utils.cpp:426-507) */
+       VGL_HOST_NARROW = 2 };/* GL / GP as float32; PL, AD, ADF, ADR and DP narrowed on the device to the width BCF stores them
+                              * in anyway (htslib/vcf.c:2249-2294 bcf_enc_vint): 1.8x fewer bytes over PCIe (see vgl_batch_out) */
 
 /* how the native simulator draws a cell (replay ignores this) */
 enum { VGL_SAMPLER_AUTO = 0,     /* COUNTS when the GL depends on base counts only, else PER_READ */
@@ -109,7 +116,7 @@ typedef struct vgl_params {
     int32_t max_batch_sites; /* capacity of one slot */
     int32_t n_slots;         /* >= 1; 2 = double buffering */
     int32_t sampler;         /* VGL_SAMPLER_* */
-    int32_t host_output;     /* 1: vgl_wait() copies results to pinned host memory; 0: results stay in HBM */
+    int32_t host_output;     /* VGL_HOST_* */
 } vgl_params;
 
 /* Replay input: the reference's own draws for a batch (from the instrumented
@@ -166,6 +173,16 @@ typedef struct vgl_batch_out {
     const int32_t* adr;
     int64_t g_elems, r_elems;  /* used elements of the G- and R-shaped planes */
     int32_t status;            /* VGL_OK or e.g. VGL_ERANGE raised on the device */
+    /* VGL_HOST_NARROW only (else 0 / NULL; then dp / pl / ad / adf / adr above are NULL and gl / gp are host pointers).
+     * Same element order and the same g_off / r_off element offsets as the int32 planes.
+     *   pl_u8   PL is 0..255 by construction (vcfgl.cpp:931-934); a MISSING PL (bcf_int32_missing: cells with FORMAT/DP == 0,
+     *           gl_methods.cpp:60-66, 359-366, and every cell of a site with INFO/DP == 0) is stored as 0 -- test dp_n.
+     *   dp_n, ad_n, adf_n, adr_n   unsigned, narrow_bits wide: 8 when the depth law is bounded by 255 reads per cell (fixed
+     *           depth < 256, or a same-mean Poisson depth with P(n > 255) < 2^-64), else 16.  A value that does not fit is
+     *           saturated and the batch status becomes VGL_EOVERFLOW. */
+    int32_t narrow_bits;
+    const uint8_t* pl_u8;
+    const void *dp_n, *ad_n, *adf_n, *adr_n;
 } vgl_batch_out;
 
 /* timing of a slot's last completed submit, CUDA events on the slot's stream (ms) */

@@ -19,7 +19,9 @@ LIB_PATH = os.path.join(_HERE, "libvgl.so")
 if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same ABI (tools/gpu_variants.sh)
     LIB_PATH = os.environ["VGL_LIB"]
 
-VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV = 0, -1, -2, -3, -4, -5, -6
+VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
+ABI_VERSION = 2
+HOST_NONE, HOST_I32, HOST_NARROW = 0, 1, 2
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
 F32_MISSING_BITS = 0x7F800001
@@ -69,7 +71,9 @@ class VglBatchOut(C.Structure):
     _fields_ = [("n_sites", C.c_int32), ("n_samples", C.c_int32), ("sites", C.POINTER(VglSiteOut)),
                 ("dp", C.c_void_p), ("gl", C.c_void_p), ("pl", C.c_void_p), ("gp", C.c_void_p),
                 ("ad", C.c_void_p), ("adf", C.c_void_p), ("adr", C.c_void_p),
-                ("g_elems", C.c_int64), ("r_elems", C.c_int64), ("status", C.c_int32)]
+                ("g_elems", C.c_int64), ("r_elems", C.c_int64), ("status", C.c_int32),
+                ("narrow_bits", C.c_int32), ("pl_u8", C.c_void_p), ("dp_n", C.c_void_p), ("ad_n", C.c_void_p),
+                ("adf_n", C.c_void_p), ("adr_n", C.c_void_p)]
 
 
 class VglDraws(C.Structure):
@@ -124,11 +128,11 @@ def load():
 
 
 def params_from_args(a: vargs.SimArgs, n_samples: int, max_batch_sites: int, n_slots: int = 2,
-                     device_id: int = 0, host_output: bool = True, sampler: int = 0,
+                     device_id: int = 0, host_output=True, sampler: int = 0,
                      fixed_depth: bool = False) -> VglParams:
     """SimArgs (the reference CLI contract) -> vgl_params"""
     p = VglParams()
-    p.abi_version = 1
+    p.abi_version = ABI_VERSION
     p.n_samples = n_samples
     p.seed = a.seed if a.seed != -1 else 0
     if a.depths is not None:
@@ -162,12 +166,15 @@ def params_from_args(a: vargs.SimArgs, n_samples: int, max_batch_sites: int, n_s
     p.max_batch_sites = max_batch_sites
     p.n_slots = n_slots
     p.sampler = sampler
-    p.host_output = 1 if host_output else 0
+    p.host_output = int(host_output)      # False / True / HOST_NARROW
     return p
 
 
 class Batch:
-    """A finished batch: numpy views over the pinned host result buffers (host_output=1)."""
+    """A finished batch: numpy views over the pinned host result buffers (host_output=1 or 2).
+
+    With HOST_NARROW the integer planes arrive narrowed (pl_u8, dp_n, ad_n, ...); `dp`, `pl`, `ad`, `adf`, `adr`
+    are then widened copies (what a host would hand to bcf_update_format_int32), missing PL restored from DP == 0."""
 
     def __init__(self, out: VglBatchOut, tag_mask: int, host: bool):
         self.raw = out
@@ -190,13 +197,42 @@ class Batch:
             if n == 0:
                 return np.zeros(0, dtype)
             return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
-        self.dp = view(out.dp, np.int32, out.n_sites * out.n_samples)
+        self._i32 = dict(dp=view(out.dp, np.int32, out.n_sites * out.n_samples), pl=view(out.pl, np.int32, out.g_elems),
+                         ad=view(out.ad, np.int32, out.r_elems), adf=view(out.adf, np.int32, out.r_elems),
+                         adr=view(out.adr, np.int32, out.r_elems))
         self.gl = view(out.gl, np.float32, out.g_elems)
-        self.pl = view(out.pl, np.int32, out.g_elems)
         self.gp = view(out.gp, np.float32, out.g_elems)
-        self.ad = view(out.ad, np.int32, out.r_elems)
-        self.adf = view(out.adf, np.int32, out.r_elems)
-        self.adr = view(out.adr, np.int32, out.r_elems)
+        self.narrow_bits = int(out.narrow_bits)
+        self.pl_u8 = self.dp_n = self.ad_n = self.adf_n = self.adr_n = None
+        if self.narrow_bits and host:
+            ct, dt = (C.c_uint8, np.uint8) if self.narrow_bits == 8 else (C.c_uint16, np.uint16)
+
+            def nview(ptr, ct, n, dt):
+                if not ptr:
+                    return None
+                if n == 0:
+                    return np.zeros(0, dt)
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+            self.pl_u8 = nview(out.pl_u8, C.c_uint8, out.g_elems, np.uint8)
+            self.dp_n = nview(out.dp_n, ct, out.n_sites * out.n_samples, dt)
+            self.ad_n = nview(out.ad_n, ct, out.r_elems, dt)
+            self.adf_n = nview(out.adf_n, ct, out.r_elems, dt)
+            self.adr_n = nview(out.adr_n, ct, out.r_elems, dt)
+
+    def _plane(self, k):
+        """int32 plane `k`; with HOST_NARROW a widened copy made on first use (PL: see site())"""
+        v = self._i32[k]
+        if v is None and self.narrow_bits and k != "pl":
+            n = getattr(self, k + "_n")
+            if n is not None:
+                v = self._i32[k] = n.astype(np.int32)
+        return v
+
+    dp = property(lambda self: self._plane("dp"))
+    pl = property(lambda self: self._plane("pl"))
+    ad = property(lambda self: self._plane("ad"))
+    adf = property(lambda self: self._plane("adf"))
+    adr = property(lambda self: self._plane("adr"))
 
     def site(self, i: int) -> dict:
         """Everything add_tags() (bcf_utils.cpp:426-507) would emit for site i, as arrays."""
@@ -212,6 +248,10 @@ class Batch:
             g0, r0 = int(s["g_off"]), int(s["r_off"])
             for k, plane in (("gl", self.gl), ("pl", self.pl), ("gp", self.gp)):
                 d[k] = plane[g0:g0 + S * G] if plane is not None else None
+            if self.pl_u8 is not None:      # narrow PL: a cell without reads has a missing PL (vgl.h)
+                pl = self.pl_u8[g0:g0 + S * G].astype(np.int32).reshape(S, G)
+                pl[d["fmt_dp"] == 0, :] = I32_MISSING
+                d["pl"] = pl.reshape(-1)
             for k, plane in (("fmt_ad", self.ad), ("fmt_adf", self.adf), ("fmt_adr", self.adr)):
                 d[k] = plane[r0:r0 + S * A] if plane is not None else None
         return d

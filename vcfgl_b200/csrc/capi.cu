@@ -36,6 +36,10 @@ struct Slot {
     int32_t* h_dp = nullptr;
     float *h_gl = nullptr, *h_gp = nullptr;
     int32_t *h_pl = nullptr, *h_ad = nullptr, *h_adf = nullptr, *h_adr = nullptr;
+    // VGL_HOST_NARROW: narrowed integer planes, device and pinned host
+    uint8_t *d_pl8 = nullptr, *h_pl8 = nullptr;
+    void *d_dpn = nullptr, *d_adn = nullptr, *d_adfn = nullptr, *d_adrn = nullptr;
+    void *h_dpn = nullptr, *h_adn = nullptr, *h_adfn = nullptr, *h_adrn = nullptr;
     // device
     uint8_t* d_gt = nullptr;
     int32_t* d_dp = nullptr;
@@ -73,6 +77,7 @@ struct vgl_ctx {
     // device tables
     int use_fused = 0, use_tile = 0, n_sms = 148, fast_div = 0;
     int use_tile_m2 = 0, tile_m2_mode = 0; // tile_m2.cu; mode 0 / 1 / 2 = --error-qs
+    int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr;
     double* d_m2_tab = nullptr;
     int m2_nq = 0;
@@ -113,6 +118,7 @@ extern "C" const char* vgl_strerror(int s)
     case VGL_ESTATE: return "slot in wrong state";
     case VGL_ERANGE: return "quality score outside every --qs-bins range";
     case VGL_ENODEV: return "no CUDA device available (libvgl has no CPU path)";
+    case VGL_EOVERFLOW: return "a depth did not fit the narrow planes (VGL_HOST_NARROW)";
     default: return "unknown status";
     }
 }
@@ -173,6 +179,7 @@ static int validate(const vgl_params* p, std::string& why)
     if (p->i16_mapq < 0 || p->i16_mapq > 60) { why = "--i16-mapq out of [0,60]"; return VGL_EINVAL; }
     if (p->n_qs_bins < 0 || p->n_qs_bins > 255) { why = "bad n_qs_bins"; return VGL_EINVAL; }
     if (p->sampler < 0 || p->sampler > 2) { why = "bad sampler"; return VGL_EINVAL; }
+    if (p->host_output < 0 || p->host_output > 2) { why = "bad host_output"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && !(p->gl_model == 1 && p->error_qs != 2)) { why = "count-level sampler needs --gl-model 1 and --error-qs 0|1"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && (p->tag_mask & (VGL_TAG_QS | VGL_TAG_I16))) { why = "count-level sampler does not produce QS / I16 (use VGL_SAMPLER_PER_READ)"; return VGL_EINVAL; }
     return VGL_OK;
@@ -197,6 +204,8 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         cudaFreeHost(s.h_gt); cudaFreeHost(s.h_sites); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_dp);
         cudaFreeHost(s.h_gl); cudaFreeHost(s.h_gp); cudaFreeHost(s.h_pl);
         cudaFreeHost(s.h_ad); cudaFreeHost(s.h_adf); cudaFreeHost(s.h_adr);
+        cudaFreeHost(s.h_pl8); cudaFreeHost(s.h_dpn); cudaFreeHost(s.h_adn); cudaFreeHost(s.h_adfn); cudaFreeHost(s.h_adrn);
+        cudaFree(s.d_pl8); cudaFree(s.d_dpn); cudaFree(s.d_adn); cudaFree(s.d_adfn); cudaFree(s.d_adrn);
         cudaFree(s.d_gt); cudaFree(s.d_dp); cudaFree(s.d_cell); cudaFree(s.d_cellq); cudaFree(s.d_celltail);
         cudaFree(s.d_sites); cudaFree(s.d_totals); cudaFree(s.d_pairmap); cudaFree(s.d_tile_state);
         cudaFree(s.d_gl); cudaFree(s.d_gp); cudaFree(s.d_pl); cudaFree(s.d_ad); cudaFree(s.d_adf); cudaFree(s.d_adr);
@@ -276,7 +285,7 @@ static int create_impl(vgl_ctx* ctx)
                          g_cap_elems < (1ull << 31) && p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
     std::vector<unsigned long long> alias(256, 0ull);
     bool alias_ok = p.depth_mode == VGL_DEPTH_FIXED && p.depth_mean < 256.0;
-    if ((ctx->use_fused || m2_cand) && p.depth_mode == VGL_DEPTH_POISSON) {
+    if ((ctx->use_fused || m2_cand || p.host_output == VGL_HOST_NARROW) && p.depth_mode == VGL_DEPTH_POISSON) {
         const std::vector<unsigned long long> cdf = poisson_cdf_u64(p.depth_mean, 1024);
         ctx->pois_n = (int)cdf.size();
         CK(upload(&ctx->d_pois, cdf));
@@ -311,6 +320,8 @@ static int create_impl(vgl_ctx* ctx)
             ctx->use_tile_m2 = 0; // e.g. --precise-gl 1 with --error-rate 0 (homT = 0): the per-read kernels
         }
     }
+    // narrow host planes: 8 bits when no cell can hold more than 255 reads (the truncated tail of the Poisson law is below 2^-64)
+    if (p.host_output == VGL_HOST_NARROW) ctx->narrow_bits = alias_ok ? 8 : 16;
     if (ctx->use_tile || ctx->use_tile_m2) {
         CK(upload(&ctx->d_alias, alias));
         CK(upload(&ctx->d_errcdf, binomial_cdf4_u32(p.error_rate)));
@@ -349,7 +360,20 @@ static int create_impl(vgl_ctx* ctx)
         if (t & VGL_TAG_FMT_AD) CK(cudaMalloc((void**)&s.d_ad, ctx->r_cap * 4));
         if (t & VGL_TAG_FMT_ADF) CK(cudaMalloc((void**)&s.d_adf, ctx->r_cap * 4));
         if (t & VGL_TAG_FMT_ADR) CK(cudaMalloc((void**)&s.d_adr, ctx->r_cap * 4));
-        if (p.host_output) {
+        if (p.host_output == VGL_HOST_NARROW) {
+            const size_t w = (size_t)ctx->narrow_bits / 8, cells4 = (cells + 3) & ~(size_t)3;
+            CK(cudaMalloc(&s.d_dpn, cells4 * w));
+            CK(cudaHostAlloc(&s.h_dpn, cells4 * w, cudaHostAllocDefault));
+            if (t & VGL_TAG_GL) CK(cudaHostAlloc((void**)&s.h_gl, ctx->g_cap * 4, cudaHostAllocDefault));
+            if (t & VGL_TAG_GP) CK(cudaHostAlloc((void**)&s.h_gp, ctx->g_cap * 4, cudaHostAllocDefault));
+            if (t & VGL_TAG_PL) {
+                CK(cudaMalloc((void**)&s.d_pl8, ctx->g_cap));
+                CK(cudaHostAlloc((void**)&s.h_pl8, ctx->g_cap, cudaHostAllocDefault));
+            }
+            if (t & VGL_TAG_FMT_AD) { CK(cudaMalloc(&s.d_adn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adn, ctx->r_cap * w, cudaHostAllocDefault)); }
+            if (t & VGL_TAG_FMT_ADF) { CK(cudaMalloc(&s.d_adfn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adfn, ctx->r_cap * w, cudaHostAllocDefault)); }
+            if (t & VGL_TAG_FMT_ADR) { CK(cudaMalloc(&s.d_adrn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adrn, ctx->r_cap * w, cudaHostAllocDefault)); }
+        } else if (p.host_output) {
             CK(cudaHostAlloc((void**)&s.h_dp, cells * sizeof(int32_t), cudaHostAllocDefault));
             if (t & VGL_TAG_GL) CK(cudaHostAlloc((void**)&s.h_gl, ctx->g_cap * 4, cudaHostAllocDefault));
             if (t & VGL_TAG_GP) CK(cudaHostAlloc((void**)&s.h_gp, ctx->g_cap * 4, cudaHostAllocDefault));
@@ -562,7 +586,8 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     }
     // status word: only the model-2 tile kernel in per-read-qs mode can raise a device-side error (a quality score outside
     // the --qs-bins ranges); it goes through the device word, cleared and copied back in stream order
-    const bool tile_status = tile_launch && ctx->use_tile_m2 && ctx->tile_m2_mode == 2;
+    const bool narrow = prm.host_output == VGL_HOST_NARROW; // the narrowing pass can raise VGL_EOVERFLOW
+    const bool tile_status = tile_launch && ((ctx->use_tile_m2 && ctx->tile_m2_mode == 2) || narrow);
     if (tile_status) CK(cudaMemsetAsync(s.d_totals + 2, 0, sizeof(int64_t), st));
     const bool fused = (ctx->use_fused || ctx->use_tile_m2) && !rp;
     if (fused && !tile_launch) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
@@ -588,11 +613,22 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         CK(cudaEventRecord(s.ev[EV_EMIT], st));
         ctx->launches += 4;
     }
+    if (narrow) { // integer planes -> narrow planes, over the used extents the kernels left in d_totals
+        int32_t* const d_status = reinterpret_cast<int32_t*>(s.d_totals + 2);
+        const int nb = ctx->narrow_bits;
+        launch_narrow(s.d_dp, s.d_dpn, nb, false, nullptr, cells, cells, d_status, st, ctx->n_sms);
+        ctx->launches += 1;
+        if (s.d_pl) { launch_narrow(s.d_pl, s.d_pl8, 8, true, s.d_totals, 0, (int64_t)ctx->g_cap, d_status, st, ctx->n_sms); ctx->launches += 1; }
+        if (s.d_ad) { launch_narrow(s.d_ad, s.d_adn, nb, false, s.d_totals + 1, 0, (int64_t)ctx->r_cap, d_status, st, ctx->n_sms); ctx->launches += 1; }
+        if (s.d_adf) { launch_narrow(s.d_adf, s.d_adfn, nb, false, s.d_totals + 1, 0, (int64_t)ctx->r_cap, d_status, st, ctx->n_sms); ctx->launches += 1; }
+        if (s.d_adr) { launch_narrow(s.d_adr, s.d_adrn, nb, false, s.d_totals + 1, 0, (int64_t)ctx->r_cap, d_status, st, ctx->n_sms); ctx->launches += 1; }
+    }
     CK(cudaGetLastError());
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
     if (tile_launch && !tile_status) s.h_totals[2] = 0; // the kernel posts the totals into the pinned words itself and raises no errors
     else CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
+    if (narrow) CK(cudaMemcpyAsync(s.h_dpn, s.d_dpn, (size_t)cells * (ctx->narrow_bits / 8), cudaMemcpyDeviceToHost, st));
+    else if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_META], st));
     s.submitted = true;
     s.waited = false;
@@ -616,10 +652,18 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
         CK(cudaEventRecord(s.ev[EV_D2H0], st));
         if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
         if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
-        if (s.d_pl) CK(cudaMemcpyAsync(s.h_pl, s.d_pl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
-        if (s.d_ad) CK(cudaMemcpyAsync(s.h_ad, s.d_ad, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
-        if (s.d_adf) CK(cudaMemcpyAsync(s.h_adf, s.d_adf, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
-        if (s.d_adr) CK(cudaMemcpyAsync(s.h_adr, s.d_adr, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (ctx->narrow_bits) {
+            const size_t w = (size_t)ctx->narrow_bits / 8;
+            if (s.d_pl8) CK(cudaMemcpyAsync(s.h_pl8, s.d_pl8, (size_t)g_elems, cudaMemcpyDeviceToHost, st));
+            if (s.d_adn) CK(cudaMemcpyAsync(s.h_adn, s.d_adn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
+            if (s.d_adfn) CK(cudaMemcpyAsync(s.h_adfn, s.d_adfn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
+            if (s.d_adrn) CK(cudaMemcpyAsync(s.h_adrn, s.d_adrn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (s.d_pl) CK(cudaMemcpyAsync(s.h_pl, s.d_pl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_ad) CK(cudaMemcpyAsync(s.h_ad, s.d_ad, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_adf) CK(cudaMemcpyAsync(s.h_adf, s.d_adf, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_adr) CK(cudaMemcpyAsync(s.h_adr, s.d_adr, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaEventRecord(s.ev[EV_D2H1], st));
         CK(cudaEventSynchronize(s.ev[EV_D2H1]));
         s.had_d2h = true;
@@ -650,6 +694,16 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
     out->ad = h ? s.h_ad : s.d_ad;
     out->adf = h ? s.h_adf : s.d_adf;
     out->adr = h ? s.h_adr : s.d_adr;
+    if (ctx->narrow_bits) { // the int32 planes stay on the device; the host gets the narrowed ones
+        out->dp = nullptr;
+        out->pl = out->ad = out->adf = out->adr = nullptr;
+        out->narrow_bits = ctx->narrow_bits;
+        out->pl_u8 = s.h_pl8;
+        out->dp_n = s.h_dpn;
+        out->ad_n = s.h_adn;
+        out->adf_n = s.h_adfn;
+        out->adr_n = s.h_adrn;
+    }
     out->g_elems = g_elems;
     out->r_elems = r_elems;
     out->status = status;

@@ -24,6 +24,7 @@ int main(int argc, char** argv)
     p.i16_mapq = 20;
     p.max_batch_sites = 4;
     p.n_slots = 2;
+    p.host_output = getenv("VGL_NARROW") ? VGL_HOST_NARROW : VGL_HOST_I32; // same records either way
     try {
         vgl::BatchSimulator sim(p, [&](const vgl::SimRecordView& r) {
             if (r.ret < 0) { printf("site %ld skipped (%d)\n", (long)r.site_id, r.ret); return; }

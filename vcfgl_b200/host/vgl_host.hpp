@@ -80,11 +80,13 @@ class BatchSimulator {
 public:
     using Callback = std::function<void(const SimRecordView&)>;
 
-    // params: fill from the parsed argStruct (io.h:40-148); host_output is forced on.
+    // params: fill from the parsed argStruct (io.h:40-148); host_output is forced on.  With VGL_HOST_NARROW the
+    // integer planes cross PCIe as 8/16-bit values and are widened here, one site at a time, into the int32
+    // arrays bcf_update_format_int32 takes (it narrows them again itself, htslib/vcf.c:2249-2294).
     BatchSimulator(vgl_params params, Callback on_record) : prm_(params), cb_(std::move(on_record))
     {
         prm_.abi_version = VGL_ABI_VERSION;
-        prm_.host_output = 1;
+        if (prm_.host_output != VGL_HOST_NARROW) prm_.host_output = VGL_HOST_I32;
         if (prm_.n_slots < 2) prm_.n_slots = 2;
         const int rc = vgl_create(&prm_, &ctx_);
         if (rc != VGL_OK) throw Error(rc, std::string("vgl_create: ") + vgl_strerror(rc));
@@ -175,14 +177,31 @@ private:
                 if (s.alleles2acgt[a] == 4) v.allele_unobserved = a;
             }
             v.alleles = s.skip_code == 0 ? alleles_string(s, prm_.do_unobserved, prm_.do_gvcf) : std::string();
-            v.fmt_dp_arr = out.dp + (size_t)i * S;
             v.info_dp_arr[0] = s.info_dp;
             v.gl_arr = out.gl ? out.gl + s.g_off : nullptr;
-            v.pl_arr = out.pl ? out.pl + s.g_off : nullptr;
             v.gp_arr = out.gp ? out.gp + s.g_off : nullptr;
-            v.fmt_ad_arr = out.ad ? out.ad + s.r_off : nullptr;
-            v.fmt_adf_arr = out.adf ? out.adf + s.r_off : nullptr;
-            v.fmt_adr_arr = out.adr ? out.adr + s.r_off : nullptr;
+            if (out.narrow_bits) {
+                const size_t c0 = (size_t)i * S, nG = (size_t)S * s.n_genotypes, nR = (size_t)S * s.n_alleles;
+                v.fmt_dp_arr = widen(w_dp_, out.dp_n, out.narrow_bits, c0, (size_t)S);
+                v.pl_arr = nullptr;
+                if (out.pl_u8 && s.skip_code == 0) { // a cell without reads has a missing PL (vgl.h)
+                    w_pl_.resize(nG);
+                    const uint8_t* src = out.pl_u8 + s.g_off;
+                    for (int smp = 0; smp < S; ++smp)
+                        for (int g = 0; g < s.n_genotypes; ++g)
+                            w_pl_[(size_t)smp * s.n_genotypes + g] = v.fmt_dp_arr[smp] ? (int32_t)src[(size_t)smp * s.n_genotypes + g] : VGL_I32_MISSING;
+                    v.pl_arr = w_pl_.data();
+                }
+                v.fmt_ad_arr = out.ad_n && s.skip_code == 0 ? widen(w_ad_, out.ad_n, out.narrow_bits, (size_t)s.r_off, nR) : nullptr;
+                v.fmt_adf_arr = out.adf_n && s.skip_code == 0 ? widen(w_adf_, out.adf_n, out.narrow_bits, (size_t)s.r_off, nR) : nullptr;
+                v.fmt_adr_arr = out.adr_n && s.skip_code == 0 ? widen(w_adr_, out.adr_n, out.narrow_bits, (size_t)s.r_off, nR) : nullptr;
+            } else {
+                v.fmt_dp_arr = out.dp + (size_t)i * S;
+                v.pl_arr = out.pl ? out.pl + s.g_off : nullptr;
+                v.fmt_ad_arr = out.ad ? out.ad + s.r_off : nullptr;
+                v.fmt_adf_arr = out.adf ? out.adf + s.r_off : nullptr;
+                v.fmt_adr_arr = out.adr ? out.adr + s.r_off : nullptr;
+            }
             v.info_ad_arr = s.info_ad;
             v.info_adf_arr = s.info_adf;
             v.info_adr_arr = s.info_adr;
@@ -193,6 +212,15 @@ private:
         p.in_flight = false;
     }
 
+    static const int32_t* widen(std::vector<int32_t>& dst, const void* src, int bits, size_t off, size_t n)
+    {
+        dst.resize(n);
+        if (bits == 8) { const uint8_t* p = (const uint8_t*)src + off; for (size_t k = 0; k < n; ++k) dst[k] = p[k]; }
+        else { const uint16_t* p = (const uint16_t*)src + off; for (size_t k = 0; k < n; ++k) dst[k] = p[k]; }
+        return dst.data();
+    }
+
+    std::vector<int32_t> w_dp_, w_pl_, w_ad_, w_adf_, w_adr_;
     vgl_params prm_;
     Callback cb_;
     vgl_ctx* ctx_ = nullptr;
