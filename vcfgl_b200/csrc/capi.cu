@@ -76,6 +76,7 @@ struct vgl_ctx {
     int bin_max = -1;
     // device tables
     int use_fused = 0, use_tile = 0, n_sms = 148, fast_div = 0;
+    int tile_aux = 0; // the tile kernel's AUX variant (QS / I16 / INFO ADF, ADR)
     int use_tile_m2 = 0, tile_m2_mode = 0; // tile_m2.cu; mode 0 / 1 / 2 = --error-qs
     int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr;
@@ -285,16 +286,20 @@ static int create_impl(vgl_ctx* ctx)
                          g_cap_elems < (1ull << 31) && p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
     std::vector<unsigned long long> alias(256, 0ull);
     bool alias_ok = p.depth_mode == VGL_DEPTH_FIXED && p.depth_mean < 256.0;
-    if ((ctx->use_fused || m2_cand || p.host_output == VGL_HOST_NARROW) && p.depth_mode == VGL_DEPTH_POISSON) {
+    if (p.depth_mode == VGL_DEPTH_POISSON) {
         const std::vector<unsigned long long> cdf = poisson_cdf_u64(p.depth_mean, 1024);
         ctx->pois_n = (int)cdf.size();
         CK(upload(&ctx->d_pois, cdf));
         const std::vector<unsigned long long> al = poisson_alias_u64(cdf); // empty: depth can exceed 255
         if (!al.empty()) { alias = al; alias_ok = true; }
     }
-    // the tile kernel (tile_m1f.cu): the fused path's headline special case
-    ctx->use_tile = ctx->use_fused && alias_ok && p.error_qs == 0 && !ctx->sample_strand && !(t & VGL_TAG_GP) && ctx->fast_div &&
-                    p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
+    // the tile kernel (tile_m1f.cu): the fused path's headline special case; its AUX variant also takes QS / I16 / INFO ADF, ADR
+    const bool tile_base = ctx->gl_mode == GL_M1_FIXED && p.sampler != VGL_SAMPLER_PER_READ && g_cap_elems < (1ull << 31) && alias_ok &&
+                           p.error_qs == 0 && ctx->fast_div && !(t & (VGL_TAG_GP | VGL_TAG_FMT_ADF | VGL_TAG_FMT_ADR)) &&
+                           p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
+    ctx->tile_aux = tile_base && (t & tile_m1f_aux_tags()) != 0;
+    ctx->use_tile = tile_base && (ctx->tile_aux || (ctx->use_fused && !ctx->sample_strand));
+    if (ctx->use_tile) ctx->use_fused = 1; // one launch; the tile kernel replaces k_fused_m1f
     if (m2_cand && alias_ok) {
         ctx->tile_m2_mode = p.error_qs;
         ctx->use_tile_m2 = 1;
@@ -597,7 +602,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         CK(cudaEventRecord(s.ev[EV_SIM], st));
         CK(cudaEventRecord(s.ev[EV_SITE], st));
         CK(cudaEventRecord(s.ev[EV_SCAN], st));
-        if (ctx->use_tile) launch_tile_m1f(p, st, ctx->n_sms);
+        if (ctx->use_tile) launch_tile_m1f(p, st, ctx->n_sms, ctx->tile_aux != 0);
         else if (ctx->use_tile_m2) launch_tile_m2(p, st, ctx->n_sms, ctx->tile_m2_mode);
         else launch_fused_m1f(p, st, ctx->n_sms);
         CK(cudaEventRecord(s.ev[EV_EMIT], st));
@@ -716,7 +721,7 @@ extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, i
     if (n_sites < 1 || n_sites > ctx->prm.max_batch_sites || first_site_id < 0) return fail(ctx, VGL_EINVAL, "n_sites / first_site_id out of range");
     Slot& s = ctx->slots[slot];
     if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight");
-    if (ctx->use_fused) return fail(ctx, VGL_ESTATE, "per-read draws do not exist under the count-level sampler (create the context with VGL_SAMPLER_PER_READ)");
+    if (ctx->use_fused && !ctx->use_tile) return fail(ctx, VGL_ESTATE, "per-read draws do not exist under the count-level sampler (create the context with VGL_SAMPLER_PER_READ)");
     const vgl_params& prm = ctx->prm;
     CK(cudaSetDevice(prm.device_id));
     cudaStream_t st = s.stream;
@@ -725,7 +730,9 @@ extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, i
     fill_params(ctx, s, first_site_id, n_sites, p);
     CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
     const bool m2 = ctx->use_tile_m2 != 0; // the model-2 tile kernel's own sampler (read order matters there)
+    const bool m1t = ctx->use_tile != 0;    // the model-1 tile kernel's count-level sampler, listed read by read
     if (m2) launch_tile_m2_draws(p, st, ctx->tile_m2_mode, 0, s.d_dp, nullptr, nullptr, nullptr);
+    else if (m1t) launch_tile_m1f_draws(p, st, 0, s.d_dp, nullptr, nullptr, nullptr, nullptr);
     else launch_sim(p, st); // depths (and counts, unused here)
     ctx->launches += 1;
     s.dr_depths.resize((size_t)cells);
@@ -748,6 +755,8 @@ extern "C" int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, i
         launch_tile_m2_draws(p, st, ctx->tile_m2_mode, 1, nullptr, d_off, d_u8, d_u8 + 2 * nr);
         // the class table holds the score the GL uses: export it as both the raw and the adjusted score
         if (nr) CK(cudaMemcpyAsync(d_u8 + 3 * nr, d_u8 + 2 * nr, nr, cudaMemcpyDeviceToDevice, st));
+    } else if (m1t) {
+        launch_tile_m1f_draws(p, st, 1, s.d_dp, d_off, d_u8, d_u8 + nr, d_u8 + 4 * nr);
     } else {
         launch_draws(p, st, d_off, d_u8, d_u8 + nr, d_u8 + 2 * nr, d_u8 + 3 * nr, d_u8 + 4 * nr, d_e);
     }

@@ -16,7 +16,10 @@ enum Purpose : uint32_t {
     P_SITE = 2,    // per site: beta-distributed error rate (--error-qs 1)
     P_QS = 3,      // per read: beta-distributed error probability (--error-qs 2)
     P_SUBSAMPLE = 4, // per cell: which 255 reads errmod keeps when depth > 255
-    P_COUNTS = 5   // per cell: count-level sampler (binomial / multinomial splits)
+    P_COUNTS = 5,  // per cell: count-level sampler (binomial / multinomial splits)
+    P_STRAND = 6,  // per cell, tile kernel with strand totals: bit r of the stream = read r (reads grouped A, C, G, T) is forward
+    P_TAIL = 7,    // per cell, tile kernel with I16: tail distances, twelve reads per block
+    P_LAST = 8     // per site, tile kernel with I16: which read of the site's last cell with reads is "the last read" (vcfgl.cpp:657)
 };
 
 struct u32x4 {

@@ -34,6 +34,17 @@ struct __align__(16) TSite {
     int32_t g_end, r_end; // g_rel / r_rel + the padded block size
 };
 
+// per-site scratch of the AUX variant of k_tile_m1f (QS / I16 / INFO ADF, ADR)
+struct __align__(16) TAux {
+    int fw[4];                 // phase A: forward-strand reads per base
+    unsigned long long ts, tq; // phase A: sum / sum of squares of the reads' tail distances
+    int last;                  // phase A: last sample that has reads, -1: none
+    int tot[4];                // phase B: reads per base (INFO/AD in ACGT order)
+    uint32_t b2a;              // phase B: nibble b = allele index of base b (4 = unobserved allele), 0xF = not an allele
+    uint32_t info;             // phase B: n_alleles | n_alleles_observed << 8 | (record kept and has reads) << 16
+    int _pad;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes)
@@ -93,7 +104,7 @@ __device__ __forceinline__ int tile_ticket_get(int raw) { return __shfl_sync(0xf
 // 665-782, 806-843 INFO part), the per-site scatter tables `st`, block offsets within the tile and the tile bases.
 __device__ __forceinline__ void tile_phase_b(const DevParams& p, const int lane, const int nsl, const int site0, const int tile, const int S,
                                              const int T, int* tot, TSite* st, const bool explode, const bool add_unobs, int64_t* s_base,
-                                             uint32_t* s_ctr)
+                                             uint32_t* s_ctr, TAux* aux = nullptr)
 {
     int my_g = 0, my_r = 0; // this site's block sizes in 4-byte elements (padded to 16 B)
     if (lane < nsl) {
@@ -156,11 +167,25 @@ __device__ __forceinline__ void tile_phase_b(const DevParams& p, const int lane,
                     const int b = (int)((a2b >> (4 * a)) & 0xF);
                     o.alleles2acgt[a] = b == 0xF ? (int8_t)-1 : (int8_t)b;
                     if (a < n_alleles && b < 4 && (p.tag_mask & VGL_TAG_INFO_AD)) o.info_ad[a] = t[b];
+                    if (aux && a < n_alleles && b < 4) { // vcfgl.cpp:833-841
+                        const int f = aux[lane].fw[b];
+                        if (p.tag_mask & VGL_TAG_INFO_ADF) o.info_adf[a] = f;
+                        if (p.tag_mask & VGL_TAG_INFO_ADR) o.info_adr[a] = t[b] - f;
+                    }
                 }
             }
         }
         // dp == 0 sites keep all-missing blocks: their "alleles" carry no base (counts read as 0)
         const bool keep = o.skip_code == 0 && o.n_alleles > 0;
+        if (aux) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) m |= (uint32_t)(b2a[b] & 0xF) << (4 * b);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) aux[lane].tot[b] = t[b];
+            aux[lane].b2a = m;
+            aux[lane].info = (uint32_t)o.n_alleles | ((uint32_t)o.n_alleles_observed << 8) | ((keep && dp > 0) ? 1u << 16 : 0u);
+        }
         TSite ts;
         const uint64_t pm = make_pairmap(b2a);
         bool all15 = true;

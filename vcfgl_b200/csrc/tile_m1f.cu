@@ -110,6 +110,204 @@ __device__ __forceinline__ uint32_t tile_sample_cell(const DevParams& p, const T
     return ad;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// AUX variant (QS, I16, INFO/ADF, INFO/ADR): the extra per-cell draws of the count-level sampler.
+//   strands        the reads of a cell are grouped A.., C.., G.., T..; read r is on the forward strand when bit r of the
+//                  cell's P_STRAND stream is 1 (iid fair coins, vcfgl.cpp:581-586) -> forward reads per base = popcounts
+//   tail distances read r draws 1 + U{0..49} capped at 25 (vcfgl.cpp:653-656) from digit r % 3 of word (r % 12) / 3 of
+//                  block r / 12 of the cell's P_TAIL stream: j = floor(word * 125000 / 2^32), digits of j in base 50
+//                  (relative bias of a value's probability <= 125000 / 2^32 = 2.9e-5)
+//   last read      all tail distances of a site are credited to the base of the site's LAST simulated read (the stale
+//                  r_base of vcfgl.cpp:647-663): a uniformly chosen read of the last cell that has reads (P_LAST)
+// vgl_native_draws() (k_tile_m1f_draws below) lists the same draws read by read.
+__device__ __forceinline__ uint32_t tile_word(const u32x4& b, int j) { return j == 0 ? b.x : (j == 1 ? b.y : (j == 2 ? b.z : b.w)); }
+
+// forward reads per base as four packed bytes; nmax = largest depth in the warp (uniform)
+__device__ __forceinline__ uint32_t tile_strand_counts(const DevParams& p, unsigned long long site, uint32_t sample, uint32_t c4, int nmax)
+{
+    const int e0 = (int)(c4 & 0xFFu), e1 = e0 + (int)((c4 >> 8) & 0xFFu), e2 = e1 + (int)((c4 >> 16) & 0xFFu), e3 = e2 + (int)(c4 >> 24);
+    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+    for (int kb = 0; kb * 128 < nmax; ++kb) {
+        const u32x4 blk = philox_rk(p, c0, c1, sample, ((uint32_t)P_STRAND << 24) | (uint32_t)kb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int base = kb * 128 + j * 32;
+            if (base < nmax) {
+                const uint32_t w = tile_word(blk, j);
+                const uint32_t m0 = low_bits(min(max(e0 - base, 0), 32)), m1 = low_bits(min(max(e1 - base, 0), 32));
+                const uint32_t m2 = low_bits(min(max(e2 - base, 0), 32)), m3 = low_bits(min(max(e3 - base, 0), 32));
+                f0 += __popc(w & m0);
+                f1 += __popc(w & (m1 ^ m0));
+                f2 += __popc(w & (m2 ^ m1));
+                f3 += __popc(w & (m3 ^ m2));
+            }
+        }
+    }
+    return f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
+}
+
+// the three tail distances of one 32-bit word
+__device__ __forceinline__ void tile_tail3(uint32_t w, int& t0, int& t1, int& t2)
+{
+    const uint32_t j = mulhi32(w, 125000u);
+    const uint32_t hi = j / 2500u, r = j - hi * 2500u, mid = r / 50u, lo = r - mid * 50u;
+    t0 = min((int)lo + 1, 25);
+    t1 = min((int)mid + 1, 25);
+    t2 = min((int)hi + 1, 25);
+}
+
+// sum and sum of squares of the tail distances of a cell's n reads; nmax = largest depth in the warp (uniform)
+__device__ __forceinline__ void tile_tail_sums(const DevParams& p, unsigned long long site, uint32_t sample, int n, int nmax, uint32_t& tsum,
+                                               uint32_t& tsq)
+{
+    const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
+    tsum = tsq = 0u;
+    for (int kb = 0; kb * 12 < nmax; ++kb) {
+        const u32x4 blk = philox_rk(p, c0, c1, sample, ((uint32_t)P_TAIL << 24) | (uint32_t)kb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int t0, t1, t2;
+            tile_tail3(tile_word(blk, j), t0, t1, t2);
+            const int r = kb * 12 + j * 3;
+            t0 = r < n ? t0 : 0;
+            t1 = r + 1 < n ? t1 : 0;
+            t2 = r + 2 < n ? t2 : 0;
+            tsum += (uint32_t)(t0 + t1 + t2);
+            tsq += (uint32_t)(t0 * t0 + t1 * t1 + t2 * t2);
+        }
+    }
+}
+
+// tail distance of read r of a cell (sequential fall-back and the draws export)
+__device__ __forceinline__ int tile_tail_of_read(const DevParams& p, unsigned long long site, uint32_t sample, int r)
+{
+    const u32x4 blk = philox_rk(p, (uint32_t)site, (uint32_t)(site >> 32) & 0xFFu, sample, ((uint32_t)P_TAIL << 24) | (uint32_t)(r / 12));
+    int t[3];
+    tile_tail3(tile_word(blk, (r % 12) / 3), t[0], t[1], t[2]);
+    return t[r % 3];
+}
+
+// index (in the grouped order A.., C.., G.., T..) of the read of cell (site, sample) that counts as the site's last read
+__device__ __forceinline__ int tile_last_read(const DevParams& p, unsigned long long site, uint32_t sample, int n)
+{
+    const u32x4 blk = philox_rk(p, (uint32_t)site, (uint32_t)(site >> 32) & 0xFFu, sample, (uint32_t)P_LAST << 24);
+    return (int)mulhi32(blk.x, (uint32_t)n);
+}
+__device__ __forceinline__ int tile_base_of_read(uint32_t c4, int j)
+{
+    const int e0 = (int)(c4 & 0xFFu), e1 = e0 + (int)((c4 >> 8) & 0xFFu), e2 = e1 + (int)((c4 >> 16) & 0xFFu);
+    return j < e0 ? 0 : (j < e1 ? 1 : (j < e2 ? 2 : 3));
+}
+
+// v += c, k times, as the reference's float accumulator would (vcfgl.cpp:1009-1022)
+__device__ __forceinline__ float tile_add_const_times(float v, int c, int k)
+{
+    const float cf = (float)c;
+    if (v + (float)k * cf < 16777216.0f && v == truncf(v)) return v + (float)(k * c);
+    for (int i = 0; i < k; ++i) v = __fadd_rn(v, cf);
+    return v;
+}
+
+// I16 of one site (vcfgl.cpp:982-1074) from the site totals.  Every accumulator of the reference is a float that
+// adds small non-negative integers in (sample, read) order; while the total stays below 2^24 every partial sum is an
+// exactly representable integer and the float equals the integer total.  Beyond that (deep, many samples) the sums
+// are redone in the reference's order from the cached counts (SEQ path, one thread: rare and slow, but exact).
+template <bool BIG>
+__device__ __noinline__ void tile_site_i16(const DevParams& p, const TAux& ax, const unsigned long long site, const int S, const uint32_t s_cnt_site,
+                                           const uint32_t* cnt_g, float* out)
+{
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+    const int A = (int)(ax.info & 0xFFu), n_obs = (int)((ax.info >> 8) & 0xFFu);
+    int a2b[5] = {-1, -1, -1, -1, -1};
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const int a = (int)((ax.b2a >> (4 * b)) & 0xFu);
+        if (a != 0xF) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                if (k == a) a2b[k] = b;
+        }
+    }
+    const int refb = a2b[0];
+    const int q = (p.adjust_qs & 2) ? p.pre_adj_qs : p.pre_qs, q2 = qs_squared(q), mq = p.i16_mapq, mq2 = mq * mq;
+    auto cnt = [&](int s) -> uint32_t { return BIG ? cnt_g[s] : lds32(s_cnt_site + 4u * (uint32_t)s); };
+    // the site's last read (stale r_base)
+    int stale = -1;
+    if (ax.last >= 0) {
+        const uint32_t c4 = cnt(ax.last);
+        stale = tile_base_of_read(c4, tile_last_read(p, site, (uint32_t)ax.last, (int)__vsadu4(c4, 0u)));
+    }
+    long long nonref = 0;
+    for (int a = 1; a < A; ++a) {
+        if (a == n_obs) continue;
+        const int b = a2b[a];
+        if (b < 0 || b == 4) continue;
+        nonref += ax.tot[b];
+    }
+    const long long ref = refb >= 0 && refb < 4 ? ax.tot[refb] : 0;
+    const long long qmax = max(max(q2, q), max(mq2, mq));
+    const bool exact = qmax * max(ref, nonref) < 16777216ll && ax.tq < 16777216ull;
+    float tsum, tsq;
+    if (exact) {
+        tsum = (float)ax.ts;
+        tsq = (float)ax.tq;
+        v[4] = (float)(q * ref); v[5] = (float)(q2 * ref);
+        v[8] = (float)(mq * ref); v[9] = (float)(mq2 * ref);
+        v[6] = (float)(q * nonref); v[7] = (float)(q2 * nonref);
+        v[10] = (float)(mq * nonref); v[11] = (float)(mq2 * nonref);
+    } else {
+        tsum = tsq = 0.0f;
+        for (int s = 0; s < S; ++s) {
+            const uint32_t c4 = cnt(s);
+            const int n = (int)__vsadu4(c4, 0u);
+            for (int i = 0; i < n; ++i) {
+                const int t = tile_tail_of_read(p, site, (uint32_t)s, i);
+                tsum = __fadd_rn(tsum, (float)t);
+                tsq = __fadd_rn(tsq, (float)(t * t));
+            }
+            const int cr = (int)((c4 >> (8 * refb)) & 0xFFu);
+            v[4] = __fadd_rn(v[4], (float)(q * cr));
+            v[5] = __fadd_rn(v[5], (float)(q2 * cr));
+            for (int a = 0; a < A; ++a) {
+                if (a == n_obs) continue;
+                const int b = a2b[a];
+                if (b < 0 || b == 4) continue;
+                const int k = (int)((c4 >> (8 * b)) & 0xFFu);
+                if (a == 0) { v[8] = tile_add_const_times(v[8], mq, k); v[9] = tile_add_const_times(v[9], mq2, k); }
+                else        { v[10] = tile_add_const_times(v[10], mq, k); v[11] = tile_add_const_times(v[11], mq2, k); }
+            }
+        }
+        for (int a = 1; a < A; ++a) {
+            if (a == n_obs) continue;
+            const int b = a2b[a];
+            if (b < 0 || b == 4) continue;
+            for (int s = 0; s < S; ++s) {
+                const int k = (int)((cnt(s) >> (8 * b)) & 0xFFu);
+                v[6] = __fadd_rn(v[6], (float)(q * k));
+                v[7] = __fadd_rn(v[7], (float)(q2 * k));
+            }
+        }
+    }
+    v[0] = (float)ax.fw[refb];
+    v[1] = (float)(ax.tot[refb] - ax.fw[refb]);
+    v[12] = refb == stale ? tsum : 0.0f;
+    v[13] = refb == stale ? tsq : 0.0f;
+    for (int a = 1; a < A; ++a) {
+        if (a == n_obs) continue;
+        const int b = a2b[a];
+        if (b < 0 || b == 4) continue;
+        v[2] = __fadd_rn(v[2], (float)ax.fw[b]);
+        v[3] = __fadd_rn(v[3], (float)(ax.tot[b] - ax.fw[b]));
+        v[14] = __fadd_rn(v[14], b == stale ? tsum : 0.0f);
+        v[15] = __fadd_rn(v[15], b == stale ? tsq : 0.0f);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+}
+
 // GL / PL of one cell from its scores, scattered into the warp's stage slice in allele order
 // (gl_methods.cpp:338-357, vcfgl.cpp:907-939).  ALL15: every base pair is a genotype of the site.
 // With w = q/10 >= 0: GL = (-w) - max(-w) = min(w) - w, the same float as the reference's subtraction.
@@ -149,17 +347,20 @@ __device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const uint4
 
 
 // GEN: any subset of the GL / PL / AD planes (else all three); BIG: a site's counts do not fit the shared-memory
-// cache -> they pass through a per-CTA scratch row in global memory (L2-resident), read one chunk ahead
-template <bool GEN, bool BIG>
-__global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
+// cache -> they pass through a per-CTA scratch row in global memory (L2-resident), read one chunk ahead;
+// AUX: QS / I16 / INFO ADF, ADR (strand and tail-distance draws in phase A, per-site sums in an extra phase after B)
+template <bool GEN, bool BIG, bool AUX>
+__global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    // layout: alias [256] u64 | cdf_e [256] uint4 | stage [warps][G plane, PL plane, R plane] | st [sites] | tot [sites][4] | cnt [cap]
+    // layout: alias [256] u64 | cdf_e [256] uint4 | stage [warps][G plane, PL plane, R plane] | st [sites] | tot [sites][4] |
+    //         aux [sites] (AUX only) | cnt [cap]
     constexpr int WST = 2 * TILE_WST_G + TILE_WST_R; // words per warp
     constexpr uint32_t OFF_STAGE = 2048 + 4096, OFF_ST = OFF_STAGE + TILE_WARPS * WST * 4, OFF_TOT = OFF_ST + TILE_MAX_SITES * sizeof(TSite),
-                       OFF_CNT = OFF_TOT + TILE_MAX_SITES * 16;
+                       OFF_AUX = OFF_TOT + TILE_MAX_SITES * 16, OFF_CNT = OFF_AUX + (AUX ? TILE_MAX_SITES * sizeof(TAux) : 0);
     TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
     int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
+    TAux* aux = reinterpret_cast<TAux*>(tile_smem + OFF_AUX);
     __shared__ int64_t s_base[2];
     __shared__ int s_next;
     __shared__ uint32_t s_ctr[2];
@@ -178,6 +379,15 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
         reinterpret_cast<uint4*>(tile_smem + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
     }
     for (int i = tid; i < TILE_MAX_SITES * 4; i += TILE_BLOCK) tot[i] = 0;
+    if (AUX && tid < TILE_MAX_SITES) {
+        TAux z;
+        z.fw[0] = z.fw[1] = z.fw[2] = z.fw[3] = 0;
+        z.ts = z.tq = 0ull;
+        z.last = -1;
+        z.tot[0] = z.tot[1] = z.tot[2] = z.tot[3] = 0;
+        z.b2a = 0xFFFFFu; z.info = 0u; z._pad = 0;
+        aux[tid] = z;
+    }
     if (tid == 0) {
         s_next = (int)atomicAdd(p.ticket, 1u);
         s_ctr[0] = s_ctr[1] = 0u;
@@ -193,6 +403,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
     const bool explode = p.do_unobserved >= 3;
     const bool add_unobs = p.do_unobserved == 1 || p.do_unobserved == 2 || p.do_unobserved == 4 || p.do_unobserved == 5;
     const bool has_gl = GEN ? p.gl != nullptr : true, has_pl = GEN ? p.pl != nullptr : true, has_ad = GEN ? p.ad != nullptr : true;
+    const bool want_tail = AUX && (p.tag_mask & VGL_TAG_I16) != 0;
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4; // this warp's GL slice; PL at +TILE_WST_G words, AD at +2*TILE_WST_G
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
     const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST;
@@ -269,6 +480,49 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
                         if (val) atomicAdd(&tot[sl * 4 + b], val);
                     }
                 }
+                if (AUX) { // strand and tail-distance draws, summed per site
+                    const int n = (int)__vsadu4(ad, 0u);
+                    const int nmax = __reduce_max_sync(0xffffffffu, n);
+                    const uint32_t fw4 = tile_strand_counts(p, site_base + (uint32_t)sl, (uint32_t)v, ad, nmax);
+                    uint32_t tsum = 0u, tsq = 0u;
+                    if (want_tail) tile_tail_sums(p, site_base + (uint32_t)sl, (uint32_t)v, n, nmax, tsum, tsq);
+                    const int lastv = n > 0 ? v : -1;
+                    const uint32_t f01 = __byte_perm(fw4, 0u, 0x4140), f23 = __byte_perm(fw4, 0u, 0x4342);
+                    const bool one = __all_sync(0xffffffffu, sl == first), two = __all_sync(0xffffffffu, sl == first || sl == first + 1);
+                    if (one || two) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (h == 1 && one) break;
+                            const bool in = sl == first + h;
+                            const uint32_t a01 = __reduce_add_sync(0xffffffffu, in ? f01 : 0u), a23 = __reduce_add_sync(0xffffffffu, in ? f23 : 0u);
+                            const uint32_t ts = __reduce_add_sync(0xffffffffu, in ? tsum : 0u), tq = __reduce_add_sync(0xffffffffu, in ? tsq : 0u);
+                            const int lm = __reduce_max_sync(0xffffffffu, in ? lastv : -1);
+                            const int site_h = first + h;
+                            if (site_h < nsl) {
+                                if (lane < 4) {
+                                    const uint32_t w = (lane & 2) ? a23 : a01;
+                                    const uint32_t val = (lane & 1) ? (w >> 16) : (w & 0xFFFFu);
+                                    if (val) atomicAdd(&aux[site_h].fw[lane], (int)val);
+                                } else if (lane == 4) {
+                                    if (ts) atomicAdd(&aux[site_h].ts, (unsigned long long)ts);
+                                } else if (lane == 5) {
+                                    if (tq) atomicAdd(&aux[site_h].tq, (unsigned long long)tq);
+                                } else if (lane == 6) {
+                                    if (lm >= 0) atomicMax(&aux[site_h].last, lm);
+                                }
+                            }
+                        }
+                    } else if (sl < nsl && n > 0) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int val = (int)((fw4 >> (8 * b)) & 0xFFu);
+                            if (val) atomicAdd(&aux[sl].fw[b], val);
+                        }
+                        if (tsum) atomicAdd(&aux[sl].ts, (unsigned long long)tsum);
+                        if (tsq) atomicAdd(&aux[sl].tq, (unsigned long long)tsq);
+                        atomicMax(&aux[sl].last, lastv);
+                    }
+                }
                 cur = nxt; iv = iv2; sl = sl2; v = v2; real = real2; gt = gt2;
                 nxt = tile_ticket_get(raw);
             }
@@ -286,9 +540,38 @@ __global__ void __launch_bounds__(TILE_BLOCK, TILE_MIN_CTAS) k_tile_m1f(const __
                 const int64_t lo = (int64_t)nt * T * S + lane * 128;
                 if (nt < p.n_tiles && lane * 128 < T * S && lo < p.n_cells) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gt + lo));
             }
-            tile_phase_b(p, lane, nsl, site0, tile, S, T, tot, st, explode, add_unobs, s_base, s_ctr);
+            tile_phase_b(p, lane, nsl, site0, tile, S, T, tot, st, explode, add_unobs, s_base, s_ctr, AUX ? aux : nullptr);
         }
         __syncthreads();
+
+        // ---------------- phase AUX: QS (thread per site and base; float sums in sample order, vcfgl.cpp:845-898) and
+        // I16 (thread per site, vcfgl.cpp:982-1074) from the cached counts and the site totals
+        if (AUX) {
+            const int sl = tid >> 2, b = tid & 3;
+            if (sl < nsl && (aux[sl].info >> 16)) {
+                const TAux ax = aux[sl];
+                const uint32_t s_cnt_site = s_cnt + (uint32_t)(sl * S4) * 4u;
+                vgl_site_out* const rec = p.sites + site0 + sl;
+                const int a = (int)((ax.b2a >> (4 * b)) & 0xFu);
+                if ((p.tag_mask & VGL_TAG_QS) && a != 0xF) {
+                    const int q = (p.adjust_qs & 2) ? p.pre_adj_qs : p.pre_qs;
+                    float acc = 0.0f;
+                    for (int s = 0; s < S; ++s) {
+                        const uint32_t c4 = BIG ? cnt_g[s] : lds32(s_cnt_site + 4u * (uint32_t)s);
+                        const float sum = (float)(q * (int)__vsadu4(c4, 0u));
+                        if (sum != 0.0f) acc = __fadd_rn(acc, __fdiv_rn((float)(q * (int)((c4 >> (8 * b)) & 0xFFu)), sum));
+                    }
+                    rec->qs[a] = acc;
+                }
+                if ((p.tag_mask & VGL_TAG_I16) && b == 0) tile_site_i16<BIG>(p, ax, site_base + (uint32_t)sl, S, s_cnt_site, cnt_g, rec->i16);
+            }
+            __syncthreads();
+            if (tid < nsl) { // clear the phase-A accumulators for the next tile
+                aux[tid].fw[0] = aux[tid].fw[1] = aux[tid].fw[2] = aux[tid].fw[3] = 0;
+                aux[tid].ts = aux[tid].tq = 0ull;
+                aux[tid].last = -1;
+            }
+        }
 
         // ---------------- phase C: score + emit, one warp per chunk of 32 virtual cells
         float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
@@ -390,29 +673,97 @@ static size_t tile_dyn_smem(bool big)
            (big ? 0 : (size_t)TILE_CELLS * 4);
 }
 
-template <bool GEN, bool BIG>
+template <bool GEN, bool BIG, bool AUX>
 static void launch_tile_t(const DevParams& p, cudaStream_t st, int n_sms)
 {
-    const size_t dyn = tile_dyn_smem(BIG);
-    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const size_t dyn = tile_dyn_smem(BIG) + (AUX ? TILE_MAX_SITES * sizeof(TAux) : 0);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN, BIG>, TILE_BLOCK, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN, BIG, AUX>, TILE_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
     int grid = n_sms * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    k_tile_m1f<GEN, BIG><<<grid, TILE_BLOCK, dyn, st>>>(p);
+    k_tile_m1f<GEN, BIG, AUX><<<grid, TILE_BLOCK, dyn, st>>>(p);
 }
 
-void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms)
+// aux: QS / I16 / INFO ADF, ADR wanted (tile_m1f_aux_tags)
+void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms, bool aux)
 {
     const bool all3 = p.gl && p.pl && p.ad, big = tile_m1f_scratch_words(p.S, 1) > 0;
-    if (all3 && !big) launch_tile_t<false, false>(p, st, n_sms);
-    else if (all3) launch_tile_t<false, true>(p, st, n_sms);
-    else if (!big) launch_tile_t<true, false>(p, st, n_sms);
-    else launch_tile_t<true, true>(p, st, n_sms);
+    if (aux) {
+        if (big) launch_tile_t<true, true, true>(p, st, n_sms);
+        else launch_tile_t<true, false, true>(p, st, n_sms);
+    } else if (all3 && !big) launch_tile_t<false, false, false>(p, st, n_sms);
+    else if (all3) launch_tile_t<false, true, false>(p, st, n_sms);
+    else if (!big) launch_tile_t<true, false, false>(p, st, n_sms);
+    else launch_tile_t<true, true, false>(p, st, n_sms);
 }
+
+// ---- the count-level sampler's draws read by read, in the replay layout (vgl_native_draws): pass 0 writes the depths,
+// pass 1 the reads.  The reads of a cell are listed grouped by base (A.., C.., G.., T..); in the site's last cell with
+// reads the read picked by P_LAST moves to the end (it is the site's last simulated read, vcfgl.cpp:657).  The read
+// listed at position k carries tail distance k of the cell's stream; strands follow their reads.
+__global__ void k_tile_m1f_draws(const DevParams p, int pass, int32_t* depths, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* tails)
+{
+    __shared__ __align__(16) unsigned char sm[2048 + 4096];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        reinterpret_cast<uint2*>(sm)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
+        reinterpret_cast<uint4*>(sm + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
+    }
+    __syncthreads();
+    TileRng R;
+    R.s_alias = smem_u32(sm);
+    R.s_cdf_e = R.s_alias + 2048;
+    R.fixed_depth = p.depth_mode == VGL_DEPTH_FIXED ? (int)p.depth_mean : -1;
+    R.has_err = p.error_rate > 0.0;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n_cells) return;
+    const int64_t sl = c / p.S;
+    const uint32_t sample = (uint32_t)(c - sl * p.S);
+    const unsigned long long site = (unsigned long long)(p.first_site + sl);
+    const uint32_t ad = tile_sample_cell(p, R, site, sample, p.gt[c]);
+    const int n = (int)__vsadu4(ad, 0u);
+    if (pass == 0) { depths[c] = n; return; }
+    if (n == 0) return;
+    bool last = true;
+    for (int s2 = (int)sample + 1; s2 < p.S && last; ++s2) last = depths[sl * p.S + s2] == 0;
+    const int pick = last ? tile_last_read(p, site, sample, n) : -1;
+    u32x4 blk;
+    int cur_blk = -1;
+    auto strand_of = [&](int r) -> uint8_t {
+        if ((r >> 7) != cur_blk) {
+            cur_blk = r >> 7;
+            blk = philox_rk(p, (uint32_t)site, (uint32_t)(site >> 32) & 0xFFu, sample, ((uint32_t)P_STRAND << 24) | (uint32_t)cur_blk);
+        }
+        return ((tile_word(blk, (r & 127) >> 5) >> (r & 31)) & 1u) ? 0 : 1; // 0 = forward
+    };
+    const int64_t o = off[c];
+    int k = 0;
+    for (int r = 0; r < n; ++r) {
+        if (r == pick) continue;
+        bases[o + k] = (uint8_t)tile_base_of_read(ad, r);
+        strands[o + k] = strand_of(r);
+        tails[o + k] = (uint8_t)tile_tail_of_read(p, site, sample, k);
+        ++k;
+    }
+    if (pick >= 0) {
+        bases[o + k] = (uint8_t)tile_base_of_read(ad, pick);
+        strands[o + k] = strand_of(pick);
+        tails[o + k] = (uint8_t)tile_tail_of_read(p, site, sample, k);
+    }
+}
+
+void launch_tile_m1f_draws(const DevParams& p, cudaStream_t st, int pass, int32_t* depths, const int64_t* off, uint8_t* bases, uint8_t* strands,
+                           uint8_t* tails)
+{
+    const unsigned grid = (unsigned)((p.n_cells + 127) / 128);
+    k_tile_m1f_draws<<<grid, 128, 0, st>>>(p, pass, depths, off, bases, strands, tails);
+}
+
+// tags the AUX variant adds to the tile kernel's GL / PL / AD / DP / INFO AD, DP
+uint32_t tile_m1f_aux_tags() { return VGL_TAG_QS | VGL_TAG_I16 | VGL_TAG_INFO_ADF | VGL_TAG_INFO_ADR; }
 
 // largest S the tile kernel takes (the slot arithmetic needs (S4 + block) * S4 < 2^32)
 int tile_m1f_max_samples() { return 60000; }

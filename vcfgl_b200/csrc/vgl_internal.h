@@ -114,7 +114,10 @@ void launch_scan(const DevParams& p, cudaStream_t st);
 void launch_emit(const DevParams& p, cudaStream_t st);
 int run_selftest(unsigned long long* n_bad, unsigned int* first_bad);
 void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms);
-void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms);
+void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms, bool aux);
+void launch_tile_m1f_draws(const DevParams& p, cudaStream_t st, int pass, int32_t* depths, const int64_t* off, uint8_t* bases, uint8_t* strands,
+                           uint8_t* tails);
+uint32_t tile_m1f_aux_tags();
 void launch_tile_m2(const DevParams& p, cudaStream_t st, int n_sms, int mode);
 void launch_tile_m2_draws(const DevParams& p, cudaStream_t st, int mode, int pass, int32_t* depths, const int64_t* off, uint8_t* bases,
                           uint8_t* qs);
