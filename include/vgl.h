@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 2
+#define VGL_ABI_VERSION 3
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -79,8 +79,32 @@ enum { VGL_DEPTH_POISSON = 0,            /* --depth x        rng.h:284 */
 /* vgl_params.host_output: what vgl_wait() brings to pinned host memory */
 enum { VGL_HOST_NONE = 0,    /* nothing but the totals and the status word: results stay in HBM */
        VGL_HOST_I32 = 1,     /* every plane exactly as add_tags() hands it to htslib (int32 / float32, bcf_utils.cpp:426-507) */
-       VGL_HOST_NARROW = 2 };/* GL / GP as float32; PL, AD, ADF, ADR and DP narrowed on the device to the width BCF stores them
+       VGL_HOST_NARROW = 2,  /* GL / GP as float32; PL, AD, ADF, ADR and DP narrowed on the device to the width BCF stores them
                               * in anyway (htslib/vcf.c:2249-2294 bcf_enc_vint): 1.8x fewer bytes over PCIe (see vgl_batch_out) */
+       VGL_HOST_BCF = 3 };   /* complete uncompressed BCF records, serialised on the device byte-for-byte as the reference's
+                              * add_tags() + bcf_write() would (bcf_utils.cpp:426-507, htslib/vcf.c:1773-1917, 1951-2001): the
+                              * host appends vgl_batch_out.bcf to the output stream (see vgl_bcf_site_in).  Not with -doGVCF:
+                              * the block merger (bcf_utils.cpp:662-942) consumes arrays. */
+
+/* VGL_HOST_BCF: dictionary ids of the simulator's tags in the OUTPUT header, bcf_hdr_id2int(hdr, BCF_DT_ID, "DP") etc.
+ * (FORMAT and INFO tags of the same name share one id).  Only ids of tags enabled in tag_mask are read. */
+typedef struct vgl_bcf_dict {
+    int32_t dp, gl, pl, gp, ad, adf, adr, qs, i16;
+} vgl_bcf_dict;
+
+/* VGL_HOST_BCF: what the input record passes through to the output record unchanged (the reference edits a bcf_copy of
+ * the input record: vcfgl.cpp:1540, bcf1_sync keeps the untouched pieces verbatim, htslib/vcf.c:1802-1838).
+ * The byte ranges index the slot's pass-through blob (vgl_bcf_input_buffer); with in_rec unpacked,
+ *   ID           = in_rec->shared.s[0 .. unpack_size[0])
+ *   FILTER+INFO  = in_rec->shared.s[unpack_size[0] + unpack_size[1] .. shared.l)
+ * A length of 0 selects the encoding of "." (ID: 0x07, FILTER: 0x00, no INFO). */
+typedef struct vgl_bcf_site_in {
+    int32_t rid, pos;             /* bcf1_t::rid, ::pos (0-based) */
+    uint32_t qual_bits;           /* bcf1_t::qual as raw bits; VGL_F32_MISSING_BITS for "." */
+    uint32_t n_info;              /* INFO fields the input record carries (they precede the simulator's) */
+    uint32_t id_off, id_len;
+    uint32_t flt_info_off, flt_info_len;
+} vgl_bcf_site_in;
 
 /* how the native simulator draws a cell (replay ignores this) */
 enum { VGL_SAMPLER_AUTO = 0,     /* COUNTS when the GL depends on base counts only, else PER_READ */
@@ -117,6 +141,9 @@ typedef struct vgl_params {
     int32_t n_slots;         /* >= 1; 2 = double buffering */
     int32_t sampler;         /* VGL_SAMPLER_* */
     int32_t host_output;     /* VGL_HOST_* */
+    /* VGL_HOST_BCF only */
+    vgl_bcf_dict bcf_dict;
+    int32_t bcf_blob_bytes_per_site; /* capacity of a slot's pass-through blob = max_batch_sites * this (0: 16) */
 } vgl_params;
 
 /* Replay input: the reference's own draws for a batch (from the instrumented
@@ -183,6 +210,12 @@ typedef struct vgl_batch_out {
     int32_t narrow_bits;
     const uint8_t* pl_u8;
     const void *dp_n, *ad_n, *adf_n, *adr_n;
+    /* VGL_HOST_BCF only (then every plane pointer above is NULL; `sites` is still filled): the records of the kept sites
+     * (skip_code == 0) back to back in site order, each one the bytes bcf_write() emits (l_shared, l_indiv, the six
+     * fixed words, shared block, FORMAT block).  Site i's record is bcf[bcf_off[i] .. bcf_off[i + 1]) (empty if skipped). */
+    const uint8_t* bcf;
+    const int64_t* bcf_off;    /* [n_sites + 1] */
+    int64_t bcf_bytes;         /* = bcf_off[n_sites] */
 } vgl_batch_out;
 
 /* timing of a slot's last completed submit, CUDA events on the slot's stream (ms) */
@@ -201,6 +234,10 @@ void vgl_destroy(vgl_ctx* ctx);
 
 /* pinned host input buffer of a slot: uint8 [max_batch_sites][n_samples] packed genotypes */
 int vgl_input_buffer(vgl_ctx* ctx, int slot, uint8_t** gt, int64_t* capacity_sites);
+
+/* VGL_HOST_BCF: pinned per-site pass-through records [max_batch_sites] and the blob their byte ranges index.  Fill them
+ * for the sites of a batch before vgl_submit(). */
+int vgl_bcf_input_buffer(vgl_ctx* ctx, int slot, vgl_bcf_site_in** sites, uint8_t** blob, int64_t* blob_capacity);
 
 /* asynchronous: H2D of the slot's genotypes, all kernels, (host_output) D2H of site records */
 int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites,

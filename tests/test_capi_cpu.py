@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libvgl.so does not export %s" % n
     assert sorted(capi.EXPORTS) == names
-    assert lib.vgl_abi_version() == capi.ABI_VERSION == 2
+    assert lib.vgl_abi_version() == capi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
@@ -33,6 +33,28 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.VglSiteOut) == 208 or C.sizeof(capi.VglSiteOut) == capi.SITE_DTYPE.itemsize
     assert capi.SITE_DTYPE.itemsize == C.sizeof(capi.VglSiteOut)
     assert C.sizeof(capi.VglParams) % 8 == 0
+
+
+def test_ctypes_mirror_has_the_compiled_layout(tmp_path):
+    # sizeof / offsetof as gcc lays out include/vgl.h == the ctypes mirror in vcfgl_b200/capi.py
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text("""#include <stdio.h>
+#include <stddef.h>
+#include "vgl.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vgl_params), offsetof(vgl_params, host_output), offsetof(vgl_params, bcf_dict),
+         offsetof(vgl_params, bcf_blob_bytes_per_site), sizeof(vgl_batch_out), offsetof(vgl_batch_out, bcf), offsetof(vgl_batch_out, bcf_bytes),
+         sizeof(vgl_bcf_site_in), sizeof(vgl_site_out));
+  return 0; }
+""")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    P, B = capi.VglParams, capi.VglBatchOut
+    want = [C.sizeof(P), P.host_output.offset, P.bcf_dict.offset, P.bcf_blob_bytes_per_site.offset, C.sizeof(B), B.bcf.offset,
+            B.bcf_bytes.offset, C.sizeof(capi.VglBcfSiteIn), C.sizeof(capi.VglSiteOut)]
+    assert got == want
 
 
 def test_strerror():

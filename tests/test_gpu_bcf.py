@@ -1,0 +1,230 @@
+"""GPU parity of the OUTPUT path (VGL_HOST_BCF, csrc/bcf.cu): the records serialised on the device must be the bytes
+the reference writes.
+
+(1) replay: every non-gVCF golden case is replayed through the C ABI with the reference's own draws and the device's
+    record stream is compared with the file the UNMODIFIED reference binary wrote with `-O u` (tests/golden/bcf/):
+    byte-identical, except inside float FORMAT blocks of runs whose floats may differ in the last place from glibc's
+    (GP, --precise-gl 1; see test_gpu_replay_parity.py), where 1e-6 relative applies and everything else must be equal.
+(2) native: the record stream of a native batch equals the CPU oracle's encoding (oracle/bcf_oracle.py, pinned on the
+    reference's bytes by test_bcf_oracle.py) of the arrays the same seed yields through VGL_HOST_I32 -- at sizes and
+    value ranges the reference captures do not reach (int16 / int32 vectors, long pass-through fields, odd alignments)."""
+import struct
+
+import numpy as np
+import pytest
+
+import bcf_util as bu
+import golden_cases as gc
+import replay_util
+from vcfgl_b200 import args as vargs
+from vcfgl_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+bo = bu.bo
+REL_TOL = 1e-6
+
+
+def dict_from_ids(ids):
+    d = {}
+    for k, v in ids.items():
+        kind, name = k.split("/")
+        if kind in ("FORMAT", "INFO"):
+            d[name] = v
+    return {k: v for k, v in d.items() if k.lower() in ("dp", "gl", "pl", "gp", "ad", "adf", "adr", "qs", "i16")}
+
+
+def assert_records_close(got, want, where):
+    """identical bytes, or identical in everything but float FORMAT payloads, which agree to REL_TOL"""
+    if got == want:
+        return True
+    g, w = bo.split_record(got), bo.split_record(want)
+    for k in ("rid", "pos", "rlen", "qual_bits", "n_info", "n_allele", "n_sample", "n_fmt", "id_bytes", "alleles", "filter_bytes"):
+        assert g[k] == w[k], (where, k, g[k], w[k])
+    assert [k for k, _ in g["infos"]] == [k for k, _ in w["infos"]]
+    for (kg, bg), (kw, bw) in zip(g["infos"], w["infos"]):
+        if bg != bw:   # INFO floats (QS) of the inexact cases
+            assert len(bg) == len(bw) and bg[:3] == bw[:3], (where, "info", kg)
+    for (kg, ng, tg, bg), (kw, nw, tw, bw) in zip(g["fmts"], w["fmts"]):
+        assert (kg, ng, tg, len(bg)) == (kw, nw, tw, len(bw)), (where, "fmt", kg)
+        if bg == bw:
+            continue
+        assert tg == bo.BT_FLOAT, (where, "integer FORMAT block differs", kg)
+        n = ng * g["n_sample"]
+        x = np.frombuffer(bg[-4 * n:], "<f4").astype(np.float64)
+        y = np.frombuffer(bw[-4 * n:], "<f4").astype(np.float64)
+        same = np.frombuffer(bg[-4 * n:], "<u4") == np.frombuffer(bw[-4 * n:], "<u4")
+        with np.errstate(invalid="ignore"):
+            near = np.isfinite(x) & np.isfinite(y) & (np.abs(x - y) <= REL_TOL * np.maximum(np.abs(y), 1e-30))
+        assert (same | near).all(), (where, "float FORMAT block", kg)
+    return False
+
+
+@pytest.mark.parametrize("cid", bu.BCF_CASES)
+def test_replay_records_equal_the_reference_file(cid):
+    a = gc.case_args(cid)
+    sites = gc.case_sites(cid)
+    S = sites[0].S
+    _, ids, recs = bu.reference_bcf(cid)
+    gt, rp = replay_util.batch_from_dump(sites, a)
+    n = len(sites)
+    prm = capi.params_from_args(a, S, max_batch_sites=n, n_slots=1, host_output=capi.HOST_BCF, bcf_dict=dict_from_ids(ids))
+    ctx = capi.Context(prm)
+    ctx.input_buffer(0)[:n] = gt
+    sin, blob = ctx.bcf_input(0)
+    # pass-through fields: what the reference kept of each INPUT record = the ID / FILTER (+ the input's own INFO) bytes of its
+    # output record; skipped sites have no record and keep the "." defaults
+    _, itags = bu.enabled_tags(a)
+    kept = [k for k, d in enumerate(sites) if d.ret == 0]
+    assert len(kept) == len(recs)
+    o = 0
+    sin[:n] = 0
+    for k, d in enumerate(sites):
+        sin[k]["rid"], sin[k]["pos"], sin[k]["qual_bits"] = d.rid, d.pos, capi.F32_MISSING_BITS
+    for k, rec in zip(kept, recs):
+        r = bo.split_record(rec)
+        n_in = r["n_info"] - len(itags)
+        pt = r["filter_bytes"] + b"".join(b for _, b in r["infos"][:n_in])
+        sin[k]["qual_bits"], sin[k]["n_info"] = r["qual_bits"], n_in
+        if r["id_bytes"] != b"\x07":
+            sin[k]["id_off"], sin[k]["id_len"] = o, len(r["id_bytes"])
+            blob[o:o + len(r["id_bytes"])] = np.frombuffer(r["id_bytes"], np.uint8)
+            o += len(r["id_bytes"])
+        if pt != b"\x00":
+            sin[k]["flt_info_off"], sin[k]["flt_info_len"] = o, len(pt)
+            blob[o:o + len(pt)] = np.frombuffer(pt, np.uint8)
+            o += len(pt)
+    ctx.submit(0, 1000, n, replay=rp)
+    b = ctx.wait(0)
+    assert b.status == 0
+    exact = not (a.add_gp or (a.precise_gl and a.error_qs == 2))
+    n_same = 0
+    for j, (k, want) in enumerate(zip(kept, recs)):
+        lo, hi = int(b.bcf_off[k]), int(b.bcf_off[k + 1])
+        got = bytes(b.bcf[lo:hi])
+        if exact:
+            assert got == want, (cid, k, sites[k].pos)
+            n_same += 1
+        else:
+            n_same += assert_records_close(got, want, (cid, k))
+    for k, d in enumerate(sites):
+        if d.ret != 0:
+            assert b.bcf_off[k] == b.bcf_off[k + 1] and b.sites[k]["skip_code"] == d.ret
+    assert b.bcf_bytes == int(b.bcf_off[n]) == sum(len(r) for r in recs)
+    if exact:   # the whole stream is what the reference wrote after its header
+        assert bytes(b.bcf) == b"".join(recs)
+    assert n_same >= 0.5 * len(recs)
+    ctx.close()
+
+
+def _native_pair(argv, S, n_sites, batch, passthrough_seed=None, missing=0.0, fixed_depth=False):
+    """run the same native batch through VGL_HOST_I32 and VGL_HOST_BCF; returns (expected stream from the oracle, got)"""
+    a = vargs.parse_args(argv.split())
+    hap = synth.sfs_genotypes(n_sites, S, 4242, missing)
+    gt = synth.pack_gt(hap)
+    ids = dict(DP=1, GL=2, PL=3, GP=4, AD=5, ADF=200, ADR=7, QS=40000, I16=9)   # ADF: 16-bit key, QS: 32-bit key
+    dict_ids = {"FORMAT/" + k: v for k, v in ids.items()}
+    dict_ids.update({"INFO/" + k: v for k, v in ids.items()})
+    rng = np.random.default_rng(passthrough_seed or 0)
+    ref = capi.Context(capi.params_from_args(a, S, max_batch_sites=batch, n_slots=1, host_output=capi.HOST_I32, fixed_depth=fixed_depth))
+    dev = capi.Context(capi.params_from_args(a, S, max_batch_sites=batch, n_slots=2, host_output=capi.HOST_BCF, bcf_dict=ids,
+                                             bcf_blob_bytes_per_site=64, fixed_depth=fixed_depth))
+    ftags, itags = bu.enabled_tags(a)
+    want, got = [], []
+    slot = 0
+    for s0 in range(0, n_sites, batch):
+        m = min(batch, n_sites - s0)
+        ref.input_buffer(0)[:m] = gt[s0:s0 + m]
+        ref.submit(0, s0, m)
+        rb = ref.wait(0)
+        dev.input_buffer(slot)[:m] = gt[s0:s0 + m]
+        sin, blob = dev.bcf_input(slot)
+        sin[:m] = 0
+        pts = []
+        o = 0
+        for k in range(m):
+            sin[k]["rid"], sin[k]["pos"], sin[k]["qual_bits"] = (s0 + k) % 3, 10 * (s0 + k) + 7, capi.F32_MISSING_BITS
+            idb, pt, n_in = b"\x07", b"\x00", 0
+            if passthrough_seed is not None and rng.random() < 0.7:
+                name = ("rs%d" % rng.integers(1, 10 ** int(rng.integers(1, 9)))).encode()
+                idb = bo.enc_vchar(name)
+                pt = bo.enc_vint([0] if rng.random() < 0.5 else [3, 5])
+                if rng.random() < 0.5:   # one INFO field of the input record: key 11, a float vector
+                    pt += bo.enc_int1(11) + bo.enc_vfloat(rng.random(int(rng.integers(1, 4))).astype(np.float32))
+                    n_in = 1
+                sin[k]["qual_bits"] = int(np.float32(rng.random() * 100).view(np.uint32))
+                sin[k]["id_off"], sin[k]["id_len"] = o, len(idb)
+                blob[o:o + len(idb)] = np.frombuffer(idb, np.uint8)
+                o += len(idb)
+                sin[k]["flt_info_off"], sin[k]["flt_info_len"] = o, len(pt)
+                blob[o:o + len(pt)] = np.frombuffer(pt, np.uint8)
+                o += len(pt)
+                sin[k]["n_info"] = n_in
+            pts.append((idb, pt, n_in, int(sin[k]["qual_bits"])))
+        dev.submit(slot, s0, m)
+        db = dev.wait(slot)
+        assert db.status == 0 and rb.status == 0
+        for k in range(m):
+            o_ = rb.site(k)
+            lo, hi = int(db.bcf_off[k]), int(db.bcf_off[k + 1])
+            assert db.sites[k]["skip_code"] == o_["skip_code"]
+            if o_["skip_code"] != 0:
+                assert lo == hi
+                continue
+            fmt = {t: {"DP": o_["fmt_dp"], "GL": o_.get("gl"), "PL": o_.get("pl"), "GP": o_.get("gp"), "AD": o_.get("fmt_ad"),
+                       "ADF": o_.get("fmt_adf"), "ADR": o_.get("fmt_adr")}[t] for t in ftags}
+            info = {t: {"DP": np.array([o_["info_dp"]]), "QS": o_["qs"], "I16": o_["i16"], "AD": o_["info_ad"], "ADF": o_["info_adf"],
+                        "ADR": o_["info_adr"]}[t] for t in itags}
+            alleles = bo.alleles_of_site(o_["n_alleles"], o_["alleles2acgt"], o_["info_dp"], a.do_unobserved, a.do_gvcf)
+            idb, pt, n_in, qb = pts[k]
+            want.append(bo.encode_record((s0 + k) % 3, 10 * (s0 + k) + 7, qb, idb, pt, n_in, alleles, S, dict_ids, fmt, info))
+            got.append(bytes(db.bcf[lo:hi]))
+        assert db.bcf_bytes == int(db.bcf_off[m])
+        slot ^= 1
+    ref.close()
+    dev.close()
+    return want, got
+
+
+def _check(want, got):
+    assert len(want) == len(got) and len(want) > 0
+    for k, (w, g) in enumerate(zip(want, got)):
+        assert g == w, (k, len(g), len(w), next((i for i in range(min(len(g), len(w))) if g[i] != w[i]), None))
+
+
+def test_native_cfg2_stream_equals_oracle():
+    want, got = _native_pair("--seed 42 -d 10 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1", 100, 3000, 1024)
+    _check(want, got)
+    kinds = {bo.split_record(g)["fmts"][2][2] for g in got}     # PL comes as int8 where max <= 127, else int16
+    assert kinds == {bo.BT_INT8, bo.BT_INT16} or kinds == {bo.BT_INT16}
+
+
+def test_native_all_tags_wide_vectors_and_passthrough():
+    # depth 300 -> FORMAT AD / DP need int16, 150 samples x 300 reads -> INFO AD / DP need int32; 16- and 32-bit dictionary keys;
+    # IDs, QUAL, FILTER lists and an INFO field of the input record ride along at every byte alignment
+    tags = "-addGP 1 -addPL 1 -addI16 1 -addQS 1 -addInfoDP 1 -addFormatAD 1 -addInfoAD 1 -addFormatADF 1 -addInfoADF 1 -addFormatADR 1 -addInfoADR 1"
+    want, got = _native_pair("--seed 7 -d 300 -e 0.02 -GL 2 -doUnobserved 2 " + tags, 150, 96, 40, passthrough_seed=5)
+    _check(want, got)
+    r = bo.split_record(got[0])
+    assert {t for _, _, t, _ in r["fmts"]} >= {bo.BT_INT16, bo.BT_FLOAT}
+
+
+@pytest.mark.parametrize("S", [1, 2, 3, 5, 33])
+def test_native_small_sample_counts_missing_and_empty_sites(S):
+    # tiny records (every word straddles segments), missing genotypes, sites without reads kept (--rm-empty-sites 0) in every
+    # -doUnobserved mode, one sample (bcf_enc_vint's n == 1 form)
+    for unobs in range(6):
+        want, got = _native_pair("--seed %d -d 0.4 -e 0.05 -GL 1 -doUnobserved %d -addPL 1 -addFormatAD 1 -addInfoAD 1 -addInfoDP 1 -addQS 1"
+                                 % (11 + unobs, unobs), S, 300, 128, passthrough_seed=unobs + 1, missing=0.2)
+        _check(want, got)
+
+
+def test_native_ten_thousand_samples():
+    want, got = _native_pair("--seed 42 -d 30 -e 0.01 -GL 1 -addPL 1 -addFormatAD 1", 10000, 24, 16)
+    _check(want, got)
+
+
+def test_bcf_mode_rejects_gvcf_and_overflow_is_reported():
+    a = vargs.parse_args("--seed 1 -d 10 -e 0.001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,5,10 -addPL 1".split())
+    with pytest.raises(capi.VglError) as e:
+        capi.Context(capi.params_from_args(a, 4, 16, host_output=capi.HOST_BCF))
+    assert e.value.code == capi.VGL_EINVAL

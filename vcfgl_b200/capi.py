@@ -20,16 +20,30 @@ if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same AB
     LIB_PATH = os.environ["VGL_LIB"]
 
 VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
-ABI_VERSION = 2
-HOST_NONE, HOST_I32, HOST_NARROW = 0, 1, 2
+ABI_VERSION = 3
+HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF = 0, 1, 2, 3
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
 F32_MISSING_BITS = 0x7F800001
 I32_MISSING = -(2 ** 31)
 
-EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
+EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_bcf_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
            "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
            "vgl_last_error", "vgl_abi_version", "vgl_native_kernels"]
+
+
+class VglBcfDict(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("dp", "gl", "pl", "gp", "ad", "adf", "adr", "qs", "i16")]
+
+
+class VglBcfSiteIn(C.Structure):
+    _fields_ = [("rid", C.c_int32), ("pos", C.c_int32), ("qual_bits", C.c_uint32), ("n_info", C.c_uint32),
+                ("id_off", C.c_uint32), ("id_len", C.c_uint32), ("flt_info_off", C.c_uint32), ("flt_info_len", C.c_uint32)]
+
+
+BCF_SITE_IN_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("qual_bits", "<u4"), ("n_info", "<u4"), ("id_off", "<u4"),
+                              ("id_len", "<u4"), ("flt_info_off", "<u4"), ("flt_info_len", "<u4")])
+assert BCF_SITE_IN_DTYPE.itemsize == C.sizeof(VglBcfSiteIn)
 
 
 class VglParams(C.Structure):
@@ -42,7 +56,7 @@ class VglParams(C.Structure):
                 ("rm_invar_sites", C.c_int32), ("rm_empty_sites", C.c_int32), ("do_gvcf", C.c_int32),
                 ("tag_mask", C.c_uint32), ("i16_mapq", C.c_int32), ("device_id", C.c_int32),
                 ("max_batch_sites", C.c_int32), ("n_slots", C.c_int32), ("sampler", C.c_int32),
-                ("host_output", C.c_int32)]
+                ("host_output", C.c_int32), ("bcf_dict", VglBcfDict), ("bcf_blob_bytes_per_site", C.c_int32)]
 
 
 class VglReplay(C.Structure):
@@ -73,7 +87,8 @@ class VglBatchOut(C.Structure):
                 ("ad", C.c_void_p), ("adf", C.c_void_p), ("adr", C.c_void_p),
                 ("g_elems", C.c_int64), ("r_elems", C.c_int64), ("status", C.c_int32),
                 ("narrow_bits", C.c_int32), ("pl_u8", C.c_void_p), ("dp_n", C.c_void_p), ("ad_n", C.c_void_p),
-                ("adf_n", C.c_void_p), ("adr_n", C.c_void_p)]
+                ("adf_n", C.c_void_p), ("adr_n", C.c_void_p),
+                ("bcf", C.c_void_p), ("bcf_off", C.c_void_p), ("bcf_bytes", C.c_int64)]
 
 
 class VglDraws(C.Structure):
@@ -105,6 +120,7 @@ def load():
     L.vgl_destroy.argtypes = [C.c_void_p]
     L.vgl_destroy.restype = None
     L.vgl_input_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.vgl_bcf_input_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.vgl_submit.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.POINTER(VglReplay), C.c_uint32]
     L.vgl_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(VglBatchOut)]
     L.vgl_set_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -129,7 +145,7 @@ def load():
 
 def params_from_args(a: vargs.SimArgs, n_samples: int, max_batch_sites: int, n_slots: int = 2,
                      device_id: int = 0, host_output=True, sampler: int = 0,
-                     fixed_depth: bool = False) -> VglParams:
+                     fixed_depth: bool = False, bcf_dict: Optional[dict] = None, bcf_blob_bytes_per_site: int = 0) -> VglParams:
     """SimArgs (the reference CLI contract) -> vgl_params"""
     p = VglParams()
     p.abi_version = ABI_VERSION
@@ -166,7 +182,11 @@ def params_from_args(a: vargs.SimArgs, n_samples: int, max_batch_sites: int, n_s
     p.max_batch_sites = max_batch_sites
     p.n_slots = n_slots
     p.sampler = sampler
-    p.host_output = int(host_output)      # False / True / HOST_NARROW
+    p.host_output = int(host_output)      # False / True / HOST_NARROW / HOST_BCF
+    if bcf_dict:                          # {"DP": id, "GL": id, ...}: bcf_hdr_id2int() of the output header
+        for k, v in bcf_dict.items():
+            setattr(p.bcf_dict, k.lower(), int(v))
+    p.bcf_blob_bytes_per_site = bcf_blob_bytes_per_site
     return p
 
 
@@ -203,6 +223,13 @@ class Batch:
         self.gl = view(out.gl, np.float32, out.g_elems)
         self.gp = view(out.gp, np.float32, out.g_elems)
         self.narrow_bits = int(out.narrow_bits)
+        # HOST_BCF: the serialised records and their byte offsets (views over pinned memory)
+        self.bcf = self.bcf_off = None
+        self.bcf_bytes = int(out.bcf_bytes)
+        if out.bcf_off and host:
+            self.bcf_off = np.ctypeslib.as_array(C.cast(out.bcf_off, C.POINTER(C.c_int64)), shape=(out.n_sites + 1,))
+            self.bcf = (np.ctypeslib.as_array(C.cast(out.bcf, C.POINTER(C.c_uint8)), shape=(self.bcf_bytes,))
+                        if self.bcf_bytes > 0 else np.zeros(0, np.uint8))
         self.pl_u8 = self.dp_n = self.ad_n = self.adf_n = self.adr_n = None
         if self.narrow_bits and host:
             ct, dt = (C.c_uint8, np.uint8) if self.narrow_bits == 8 else (C.c_uint16, np.uint16)
@@ -290,6 +317,14 @@ class Context:
         ptr, cap = C.c_void_p(), C.c_int64()
         self._ck(self.L.vgl_input_buffer(self.h, slot, C.byref(ptr), C.byref(cap)))
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(cap.value, self.S))
+
+    def bcf_input(self, slot: int):
+        """HOST_BCF: (per-site pass-through records [cap] as a structured array, blob bytes) of a slot, pinned"""
+        ps, pb, cap = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self.L.vgl_bcf_input_buffer(self.h, slot, C.byref(ps), C.byref(pb), C.byref(cap)))
+        sites = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_uint8)), shape=(self.cap * BCF_SITE_IN_DTYPE.itemsize,)).view(BCF_SITE_IN_DTYPE)
+        blob = np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_uint8)), shape=(cap.value,))
+        return sites, blob
 
     def set_stream(self, slot: int, stream_ptr: Optional[int]):
         self._ck(self.L.vgl_set_stream(self.h, slot, C.c_void_p(stream_ptr or 0)))

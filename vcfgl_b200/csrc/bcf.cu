@@ -1,0 +1,391 @@
+// VGL_HOST_BCF -- the reference's OUTPUT path on the device: every kept site becomes the exact bytes that
+// simRecord::add_tags() (bcf_utils.cpp:426-507) + bcf_write() (htslib/vcf.c:1951-2001, bcf1_sync :1773-1917) emit for it.
+//
+//   k_bcf_plan   block per site: min / max of the integer planes -> the int8 / int16 / int32 choice bcf_enc_vint makes
+//                per tag and record (htslib/vcf.c:2249-2294), then the record length
+//   k_bcf_scan   one block: exclusive prefix of the record lengths = byte offset of every record
+//   k_bcf_emit   block per site: thread 0 lays out the record as <= 24 segments (literal bytes built in shared memory:
+//                fixed words, allele strings, INFO values, FORMAT keys and descriptors; pass-through bytes of the input
+//                record; the tag planes); every thread then produces aligned 32-bit words of the record from whichever
+//                segments they fall in (funnel shift for float / int32 data, narrowing for int8 / int16)
+// The planes are read as the simulate kernels left them (int32 / float32, [S][G] and [S][A] blocks at g_off / r_off), so
+// the same pass serves every kernel set and both replay and native submits.  Records are packed back to back: the host
+// writes the buffer as it is.
+#include "vgl_internal.h"
+
+namespace vgl {
+
+namespace {
+
+enum { BT_NULL = 0, BT_INT8 = 1, BT_INT16 = 2, BT_INT32 = 3, BT_FLOAT = 5, BT_CHAR = 7 };
+enum { SEG_LIT = 0, SEG_BLOB = 1, SEG_VERB = 2, SEG_I8 = 3, SEG_I16 = 4 };
+constexpr int MAX_SEG = 24, LIT_CAP = 512;
+
+using SiteMinMax = BcfSiteMinMax; // per tag: 0 dp, 1 pl, 2 ad, 3 adf, 4 adr
+
+__device__ __forceinline__ int int_type(int32_t mn, int32_t mx) // htslib/vcf.c:2261-2294; no real value: max = INT32_MIN, min = INT32_MAX
+{
+    if (mx <= 127 && mn >= -120) return BT_INT8;
+    if (mx <= 32767 && mn >= -32760) return BT_INT16;
+    return BT_INT32;
+}
+__device__ __forceinline__ int type_width(int t) { return t == BT_INT8 ? 1 : (t == BT_INT16 ? 2 : 4); }
+
+struct Builder {
+    uint8_t* lit;      // shared memory, LIT_CAP bytes (null: count only)
+    uint32_t* seg_start;
+    uint32_t* seg_kind;
+    unsigned long long* seg_src;
+    int nseg = 0;
+    uint32_t pos = 0;  // bytes of the record so far
+    uint32_t nlit = 0;
+    bool in_lit = false;
+
+    __device__ void put(uint8_t b)
+    {
+        if (!in_lit) {
+            if (lit) { seg_start[nseg] = pos; seg_kind[nseg] = SEG_LIT; seg_src[nseg] = nlit; }
+            ++nseg;
+            in_lit = true;
+        }
+        if (lit) lit[nlit] = b;
+        ++nlit;
+        ++pos;
+    }
+    __device__ void put16(uint32_t v) { put((uint8_t)v); put((uint8_t)(v >> 8)); }
+    __device__ void put32(uint32_t v) { put16(v); put16(v >> 16); }
+    __device__ void ext(int kind, const void* src, uint32_t nbytes)
+    {
+        if (nbytes == 0) return;
+        if (lit) { seg_start[nseg] = pos; seg_kind[nseg] = (uint32_t)kind; seg_src[nseg] = (unsigned long long)src; }
+        ++nseg;
+        in_lit = false;
+        pos += nbytes;
+    }
+    // bcf_enc_size, htslib/vcf.h:1392-1414
+    __device__ void size(int n, int type)
+    {
+        if (n >= 15) {
+            put((uint8_t)(15 << 4 | type));
+            if (n >= 128) {
+                if (n >= 32768) { put(1 << 4 | BT_INT32); put32((uint32_t)n); }
+                else { put(1 << 4 | BT_INT16); put16((uint32_t)n); }
+            } else { put(1 << 4 | BT_INT8); put((uint8_t)n); }
+        } else put((uint8_t)(n << 4 | type));
+    }
+    // bcf_enc_int1, htslib/vcf.h:1423-1446
+    __device__ void int1(int32_t x)
+    {
+        if (x == VGL_I32_MISSING) { size(1, BT_INT8); put(0x80); }
+        else if (x == VGL_I32_MISSING + 1) { size(1, BT_INT8); put(0x81); }
+        else if (x <= 127 && x >= -120) { size(1, BT_INT8); put((uint8_t)x); }
+        else if (x <= 32767 && x >= -32760) { size(1, BT_INT16); put16((uint32_t)x); }
+        else { size(1, BT_INT32); put32((uint32_t)x); }
+    }
+    // bcf_enc_vint(s, n, a, -1) of a short INFO vector, htslib/vcf.c:2249-2294
+    __device__ void vint_small(const int32_t* a, int n)
+    {
+        if (n <= 0) { size(0, BT_NULL); return; }
+        if (n == 1) { int1(a[0]); return; }
+        int32_t mx = INT32_MIN, mn = INT32_MAX;
+        for (int i = 0; i < n; ++i) {
+            if (a[i] == VGL_I32_MISSING || a[i] == VGL_I32_MISSING + 1) continue;
+            mx = max(mx, a[i]);
+            mn = min(mn, a[i]);
+        }
+        const int t = int_type(mn, mx);
+        size(n, t);
+        for (int i = 0; i < n; ++i) {
+            const int32_t v = a[i];
+            if (t == BT_INT8) put(v == VGL_I32_MISSING ? 0x80 : (v == VGL_I32_MISSING + 1 ? 0x81 : (uint8_t)v));
+            else if (t == BT_INT16) put16(v == VGL_I32_MISSING ? 0x8000u : (v == VGL_I32_MISSING + 1 ? 0x8001u : (uint32_t)v));
+            else put32((uint32_t)v);
+        }
+    }
+    __device__ void vfloat_small(const float* a, int n) // bcf_enc_vfloat, htslib/vcf.c:2337-2343
+    {
+        size(n, BT_FLOAT);
+        for (int i = 0; i < n; ++i) put32(__float_as_uint(a[i]));
+    }
+    __device__ void str(const char* s, int n) // bcf_enc_vchar
+    {
+        size(n, BT_CHAR);
+        for (int i = 0; i < n; ++i) put((uint8_t)s[i]);
+    }
+};
+
+// Lays out site `i`'s record.  Returns its length; l_shared / l_indiv as bcf_write() counts them.
+__device__ uint32_t bcf_layout(const BcfArgs& a, int i, const vgl_site_out& s, const SiteMinMax& mm, Builder& b)
+{
+    const vgl_bcf_site_in in = a.site_in[i];
+    const int S = a.S, A = s.n_alleles, G = s.n_genotypes;
+    const uint32_t t = a.tag_mask;
+    const int n_info_sim = !!(t & VGL_TAG_INFO_DP) + !!(t & VGL_TAG_QS) + !!(t & VGL_TAG_I16) + !!(t & VGL_TAG_INFO_AD) +
+                           !!(t & VGL_TAG_INFO_ADF) + !!(t & VGL_TAG_INFO_ADR);
+    const int n_fmt = !!(t & VGL_TAG_FMT_DP) + !!(t & VGL_TAG_GL) + !!(t & VGL_TAG_PL) + !!(t & VGL_TAG_GP) + !!(t & VGL_TAG_FMT_AD) +
+                      !!(t & VGL_TAG_FMT_ADF) + !!(t & VGL_TAG_FMT_ADR);
+    // ---- the 32 fixed bytes (htslib/vcf.c:1984-1993); the two lengths are patched at the end
+    b.put32(0); b.put32(0);
+    b.put32((uint32_t)in.rid);
+    b.put32((uint32_t)in.pos);
+    const bool no_reads = s.info_dp == 0;
+    // allele strings (vcfgl.cpp:739-782; sites without reads :242-277) and rlen = strlen(REF) (htslib/vcf.c:4607-4611)
+    const bool nonref_name = a.do_unobserved == 2 || a.do_unobserved == 5 || (no_reads && a.do_gvcf);
+    int code[5]; // 0..3 = A,C,G,T; 4 = <*> / <NON_REF>; 5 = "."
+    for (int k = 0; k < 5; ++k) code[k] = k < A ? (int)s.alleles2acgt[k] : -1;
+    if (no_reads) {
+        if (a.do_gvcf || a.do_unobserved == 1 || a.do_unobserved == 2) code[0] = 4;
+        else if (a.do_unobserved == 0) code[0] = 5;
+        else { code[0] = 0; code[1] = 1; code[2] = 2; code[3] = 3; code[4] = 4; }
+    }
+    const int len0 = code[0] == 4 ? (nonref_name ? 9 : 3) : 1;
+    b.put32((uint32_t)len0);
+    b.put32(in.qual_bits);
+    b.put16((uint32_t)(in.n_info + n_info_sim));
+    b.put16((uint32_t)A);
+    b.put32(((uint32_t)n_fmt << 24) | ((uint32_t)S & 0xFFFFFFu));
+    // ---- shared block: ID, alleles, FILTER + the input's INFO, the simulator's INFO in add_tags() order
+    if (in.id_len) b.ext(SEG_BLOB, a.blob + in.id_off, in.id_len);
+    else b.put(0x07);
+    for (int k = 0; k < A; ++k) {
+        if (code[k] == 4) { if (nonref_name) b.str("<NON_REF>", 9); else b.str("<*>", 3); }
+        else if (code[k] == 5) b.str(".", 1);
+        else { const char c = "ACGT"[code[k] & 3]; b.str(&c, 1); }
+    }
+    if (in.flt_info_len) b.ext(SEG_BLOB, a.blob + in.flt_info_off, in.flt_info_len);
+    else b.put(0x00);
+    if (t & VGL_TAG_INFO_DP) { b.int1(a.dict.dp); b.int1(s.info_dp); }
+    if (t & VGL_TAG_QS) { b.int1(a.dict.qs); b.vfloat_small(s.qs, A); }
+    if (t & VGL_TAG_I16) { b.int1(a.dict.i16); b.vfloat_small(s.i16, 16); }
+    if (t & VGL_TAG_INFO_AD) { b.int1(a.dict.ad); b.vint_small(s.info_ad, A); }
+    if (t & VGL_TAG_INFO_ADF) { b.int1(a.dict.adf); b.vint_small(s.info_adf, A); }
+    if (t & VGL_TAG_INFO_ADR) { b.int1(a.dict.adr); b.vint_small(s.info_adr, A); }
+    const uint32_t l_shared = b.pos - 8;
+    // ---- FORMAT block in add_tags() order: typed key, (values per sample, type), S * nps values (htslib/vcf.c:4453-4470)
+    auto fmt_int = [&](int32_t key, const int32_t* src, int nps, int which) {
+        b.int1(key);
+        const int ty = int_type(mm.mn[which], mm.mx[which]);
+        b.size(nps, ty);
+        b.ext(ty == BT_INT8 ? SEG_I8 : (ty == BT_INT16 ? SEG_I16 : SEG_VERB), src, (uint32_t)S * nps * type_width(ty));
+    };
+    auto fmt_float = [&](int32_t key, const float* src, int nps) {
+        b.int1(key);
+        b.size(nps, BT_FLOAT);
+        b.ext(SEG_VERB, src, (uint32_t)S * nps * 4u);
+    };
+    if (t & VGL_TAG_FMT_DP) fmt_int(a.dict.dp, a.dp + (size_t)i * S, 1, 0);
+    if (t & VGL_TAG_GL) fmt_float(a.dict.gl, a.gl + s.g_off, G);
+    if (t & VGL_TAG_PL) fmt_int(a.dict.pl, a.pl + s.g_off, G, 1);
+    if (t & VGL_TAG_GP) fmt_float(a.dict.gp, a.gp + s.g_off, G);
+    if (t & VGL_TAG_FMT_AD) fmt_int(a.dict.ad, a.ad + s.r_off, A, 2);
+    if (t & VGL_TAG_FMT_ADF) fmt_int(a.dict.adf, a.adf + s.r_off, A, 3);
+    if (t & VGL_TAG_FMT_ADR) fmt_int(a.dict.adr, a.adr + s.r_off, A, 4);
+    const uint32_t l_indiv = b.pos - 8 - l_shared;
+    if (b.lit) {
+        const uint32_t v[2] = {l_shared, l_indiv};
+        for (int k = 0; k < 8; ++k) b.lit[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+    }
+    return b.pos;
+}
+
+__device__ __forceinline__ void mm_update(int32_t v, int32_t& mn, int32_t& mx)
+{
+    if (v != VGL_I32_MISSING && v != VGL_I32_MISSING + 1) { mn = min(mn, v); mx = max(mx, v); }
+}
+
+__global__ void __launch_bounds__(128) k_bcf_plan(const BcfArgs a)
+{
+    const int i = blockIdx.x, tid = threadIdx.x;
+    __shared__ vgl_site_out s;
+    __shared__ int32_t red[2][5][4];
+    if (tid == 0) s = a.sites[i];
+    __syncthreads();
+    if (s.skip_code != 0) {
+        if (tid == 0) a.rec_len[i] = 0u;
+        return;
+    }
+    const int S = a.S;
+    const int64_t nG = (int64_t)S * s.n_genotypes, nA = (int64_t)S * s.n_alleles;
+    int32_t mn[5], mx[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { mn[k] = INT32_MAX; mx[k] = INT32_MIN; }
+    if (a.tag_mask & VGL_TAG_FMT_DP) {
+        const int32_t* p = a.dp + (size_t)i * S;
+        for (int k = tid; k < S; k += 128) mm_update(p[k], mn[0], mx[0]);
+    }
+    if (a.pl) {
+        const int32_t* p = a.pl + s.g_off;
+        for (int64_t k = tid; k < nG; k += 128) mm_update(p[k], mn[1], mx[1]);
+    }
+    const int32_t* const rp[3] = {a.ad, a.adf, a.adr};
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        if (rp[q]) {
+            const int32_t* p = rp[q] + s.r_off;
+            for (int64_t k = tid; k < nA; k += 128) mm_update(p[k], mn[2 + q], mx[2 + q]);
+        }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
+        mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+        if ((tid & 31) == 0) { red[0][k][tid >> 5] = mn[k]; red[1][k][tid >> 5] = mx[k]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        SiteMinMax mm;
+        for (int k = 0; k < 5; ++k) {
+            mm.mn[k] = min(min(red[0][k][0], red[0][k][1]), min(red[0][k][2], red[0][k][3]));
+            mm.mx[k] = max(max(red[1][k][0], red[1][k][1]), max(red[1][k][2], red[1][k][3]));
+        }
+        a.minmax[i] = mm;
+        Builder b;
+        b.lit = nullptr;
+        a.rec_len[i] = bcf_layout(a, i, s, mm, b);
+    }
+}
+
+// exclusive prefix of rec_len -> rec_off[n + 1]; total also into totals[3] (device) for the host
+__global__ void __launch_bounds__(1024) k_bcf_scan(const BcfArgs a)
+{
+    __shared__ long long warp_sum[32];
+    __shared__ long long carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < a.n_sites; base += 1024) {
+        const int i = base + tid;
+        const long long v = i < a.n_sites ? (long long)a.rec_len[i] : 0;
+        long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            long long t = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            warp_sum[lane] = t;
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        const long long incl = carry + (w ? warp_sum[w - 1] : 0) + x;
+        if (i < a.n_sites) a.rec_off[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.rec_off[a.n_sites] = carry_s;
+        a.totals[3] = carry_s;
+        if (carry_s > a.out_cap) atomicExch(a.status, (int)VGL_EOVERFLOW);
+    }
+}
+
+struct SegView {
+    const uint32_t* start;
+    const uint32_t* kind;
+    const unsigned long long* src;
+    const uint8_t* lit;
+};
+
+__device__ __forceinline__ uint32_t seg_byte(const SegView& v, int sg, uint32_t r) // byte r of segment sg
+{
+    const unsigned long long src = v.src[sg];
+    switch (v.kind[sg]) {
+    case SEG_LIT: return v.lit[(uint32_t)src + r];
+    case SEG_BLOB: return reinterpret_cast<const uint8_t*>(src)[r];
+    case SEG_VERB: return (__ldg(reinterpret_cast<const uint32_t*>(src) + (r >> 2)) >> (8 * (r & 3))) & 0xFFu;
+    case SEG_I8: {
+        const int32_t x = __ldg(reinterpret_cast<const int32_t*>(src) + r);
+        return x == VGL_I32_MISSING ? 0x80u : (x == VGL_I32_MISSING + 1 ? 0x81u : (uint32_t)x & 0xFFu);
+    }
+    default: {
+        const int32_t x = __ldg(reinterpret_cast<const int32_t*>(src) + (r >> 1));
+        const uint32_t h = x == VGL_I32_MISSING ? 0x8000u : (x == VGL_I32_MISSING + 1 ? 0x8001u : (uint32_t)x & 0xFFFFu);
+        return (h >> (8 * (r & 1))) & 0xFFu;
+    }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bcf_emit(const BcfArgs a)
+{
+    const int i = blockIdx.x, tid = threadIdx.x;
+    __shared__ vgl_site_out s;
+    __shared__ uint32_t seg_start[MAX_SEG + 1], seg_kind[MAX_SEG];
+    __shared__ unsigned long long seg_src[MAX_SEG];
+    __shared__ __align__(4) uint8_t lit[LIT_CAP];
+    __shared__ int nseg_s;
+    const uint32_t len = a.rec_len[i];
+    if (len == 0) return;
+    const long long off = a.rec_off[i];
+    if (off + len > a.out_cap) return; // status already raised by the scan
+    if (tid == 0) {
+        s = a.sites[i];
+        Builder b;
+        b.lit = lit; b.seg_start = seg_start; b.seg_kind = seg_kind; b.seg_src = seg_src;
+        const uint32_t got = bcf_layout(a, i, s, a.minmax[i], b);
+        nseg_s = b.nseg;
+        seg_start[b.nseg] = got;
+    }
+    __syncthreads();
+    const int nseg = nseg_s;
+    SegView v{seg_start, seg_kind, seg_src, lit};
+    uint8_t* const out = a.out;
+    // aligned words of the output buffer that overlap [off, off + len)
+    const long long w0 = off >> 2, w1 = (off + len + 3) >> 2;
+    int sg = 0;
+    for (long long w = w0 + tid; w < w1; w += 256) {
+        const long long p0 = w * 4 - off; // record-relative position of the word's first byte (may be < 0)
+        const uint32_t rfirst = p0 < 0 ? 0u : (uint32_t)p0;
+        while (sg + 1 < nseg && seg_start[sg + 1] <= rfirst) ++sg;
+        if (p0 >= 0 && (uint32_t)p0 + 4u <= seg_start[sg + 1]) { // whole word inside one segment (or the record's end is beyond it)
+            const uint32_t r = (uint32_t)p0 - seg_start[sg];
+            const unsigned long long src = seg_src[sg];
+            uint32_t word;
+            const uint32_t kind = seg_kind[sg];
+            if (kind == SEG_VERB) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(src) + (r >> 2);
+                const uint32_t sh = r & 3u;
+                const uint32_t lo = __ldg(q);
+                word = sh ? __funnelshift_r(lo, __ldg(q + 1), 8 * sh) : lo;
+            } else if (kind == SEG_I8) {
+                const int32_t* q = reinterpret_cast<const int32_t*>(src) + r;
+                word = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int32_t x = __ldg(q + k);
+                    word |= (x == VGL_I32_MISSING ? 0x80u : (x == VGL_I32_MISSING + 1 ? 0x81u : (uint32_t)x & 0xFFu)) << (8 * k);
+                }
+            } else {
+                word = seg_byte(v, sg, r) | (seg_byte(v, sg, r + 1) << 8) | (seg_byte(v, sg, r + 2) << 16) | (seg_byte(v, sg, r + 3) << 24);
+            }
+            *reinterpret_cast<uint32_t*>(out + w * 4) = word;
+        } else { // a word that straddles segments or the record's ends: byte by byte, only this record's bytes
+            int g = sg;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long p = p0 + k;
+                if (p < 0 || p >= (long long)len) continue;
+                while (g + 1 < nseg && seg_start[g + 1] <= (uint32_t)p) ++g;
+                out[w * 4 + k] = (uint8_t)seg_byte(v, g, (uint32_t)p - seg_start[g]);
+            }
+        }
+    }
+}
+
+} // namespace
+
+void launch_bcf(const BcfArgs& a, cudaStream_t st)
+{
+    k_bcf_plan<<<(unsigned)a.n_sites, 128, 0, st>>>(a);
+    k_bcf_scan<<<1, 1024, 0, st>>>(a);
+    k_bcf_emit<<<(unsigned)a.n_sites, 256, 0, st>>>(a);
+}
+
+} // namespace vgl

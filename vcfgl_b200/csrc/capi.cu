@@ -40,6 +40,12 @@ struct Slot {
     uint8_t *d_pl8 = nullptr, *h_pl8 = nullptr;
     void *d_dpn = nullptr, *d_adn = nullptr, *d_adfn = nullptr, *d_adrn = nullptr;
     void *h_dpn = nullptr, *h_adn = nullptr, *h_adfn = nullptr, *h_adrn = nullptr;
+    // VGL_HOST_BCF: pass-through input (pinned + device), plan arrays, the record stream (device + pinned)
+    vgl_bcf_site_in *h_bcf_in = nullptr, *d_bcf_in = nullptr;
+    uint8_t *h_blob = nullptr, *d_blob = nullptr, *d_bcf = nullptr, *h_bcf = nullptr;
+    BcfSiteMinMax* d_minmax = nullptr;
+    uint32_t* d_rec_len = nullptr;
+    long long *d_rec_off = nullptr, *h_rec_off = nullptr;
     // device
     uint8_t* d_gt = nullptr;
     int32_t* d_dp = nullptr;
@@ -79,6 +85,7 @@ struct vgl_ctx {
     int tile_aux = 0; // the tile kernel's AUX variant (QS / I16 / INFO ADF, ADR)
     int use_tile_m2 = 0, tile_m2_mode = 0; // tile_m2.cu; mode 0 / 1 / 2 = --error-qs
     int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
+    size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr;
     double* d_m2_tab = nullptr;
     int m2_nq = 0;
@@ -180,7 +187,9 @@ static int validate(const vgl_params* p, std::string& why)
     if (p->i16_mapq < 0 || p->i16_mapq > 60) { why = "--i16-mapq out of [0,60]"; return VGL_EINVAL; }
     if (p->n_qs_bins < 0 || p->n_qs_bins > 255) { why = "bad n_qs_bins"; return VGL_EINVAL; }
     if (p->sampler < 0 || p->sampler > 2) { why = "bad sampler"; return VGL_EINVAL; }
-    if (p->host_output < 0 || p->host_output > 2) { why = "bad host_output"; return VGL_EINVAL; }
+    if (p->host_output < 0 || p->host_output > 3) { why = "bad host_output"; return VGL_EINVAL; }
+    if (p->host_output == VGL_HOST_BCF && p->do_gvcf) { why = "VGL_HOST_BCF does not take -doGVCF (the block merger consumes arrays)"; return VGL_EINVAL; }
+    if (p->host_output == VGL_HOST_BCF && (p->bcf_blob_bytes_per_site < 0 || p->bcf_blob_bytes_per_site > 65536)) { why = "bad bcf_blob_bytes_per_site"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && !(p->gl_model == 1 && p->error_qs != 2)) { why = "count-level sampler needs --gl-model 1 and --error-qs 0|1"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && (p->tag_mask & (VGL_TAG_QS | VGL_TAG_I16))) { why = "count-level sampler does not produce QS / I16 (use VGL_SAMPLER_PER_READ)"; return VGL_EINVAL; }
     return VGL_OK;
@@ -206,6 +215,8 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         cudaFreeHost(s.h_gl); cudaFreeHost(s.h_gp); cudaFreeHost(s.h_pl);
         cudaFreeHost(s.h_ad); cudaFreeHost(s.h_adf); cudaFreeHost(s.h_adr);
         cudaFreeHost(s.h_pl8); cudaFreeHost(s.h_dpn); cudaFreeHost(s.h_adn); cudaFreeHost(s.h_adfn); cudaFreeHost(s.h_adrn);
+        cudaFreeHost(s.h_bcf_in); cudaFreeHost(s.h_blob); cudaFreeHost(s.h_bcf); cudaFreeHost(s.h_rec_off);
+        cudaFree(s.d_bcf_in); cudaFree(s.d_blob); cudaFree(s.d_bcf); cudaFree(s.d_minmax); cudaFree(s.d_rec_len); cudaFree(s.d_rec_off);
         cudaFree(s.d_pl8); cudaFree(s.d_dpn); cudaFree(s.d_adn); cudaFree(s.d_adfn); cudaFree(s.d_adrn);
         cudaFree(s.d_gt); cudaFree(s.d_dp); cudaFree(s.d_cell); cudaFree(s.d_cellq); cudaFree(s.d_celltail);
         cudaFree(s.d_sites); cudaFree(s.d_totals); cudaFree(s.d_pairmap); cudaFree(s.d_tile_state);
@@ -378,6 +389,25 @@ static int create_impl(vgl_ctx* ctx)
             if (t & VGL_TAG_FMT_AD) { CK(cudaMalloc(&s.d_adn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adn, ctx->r_cap * w, cudaHostAllocDefault)); }
             if (t & VGL_TAG_FMT_ADF) { CK(cudaMalloc(&s.d_adfn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adfn, ctx->r_cap * w, cudaHostAllocDefault)); }
             if (t & VGL_TAG_FMT_ADR) { CK(cudaMalloc(&s.d_adrn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adrn, ctx->r_cap * w, cudaHostAllocDefault)); }
+        } else if (p.host_output == VGL_HOST_BCF) {
+            // worst case per record: every integer tag at the widest type its values can need (PL <= 255 -> int16; depths
+            // bounded by 255 reads under the alias-table law -> int16, else int32) + literals + the pass-through bytes
+            const size_t wc = alias_ok ? 2 : 4, per_site_blob = p.bcf_blob_bytes_per_site ? (size_t)p.bcf_blob_bytes_per_site : 16;
+            const size_t per_cell = ((t & VGL_TAG_FMT_DP) ? wc : 0) + ((t & VGL_TAG_GL) ? 60 : 0) + ((t & VGL_TAG_GP) ? 60 : 0) +
+                                    ((t & VGL_TAG_PL) ? 30 : 0) + 5 * wc * (!!(t & VGL_TAG_FMT_AD) + !!(t & VGL_TAG_FMT_ADF) + !!(t & VGL_TAG_FMT_ADR));
+            ctx->bcf_cap = ((cells * per_cell + B * (512 + per_site_blob)) + 15) & ~(size_t)15;
+            ctx->blob_cap = B * per_site_blob;
+            CK(cudaHostAlloc((void**)&s.h_bcf_in, B * sizeof(vgl_bcf_site_in), cudaHostAllocDefault));
+            CK(cudaHostAlloc((void**)&s.h_blob, ctx->blob_cap, cudaHostAllocDefault));
+            CK(cudaHostAlloc((void**)&s.h_bcf, ctx->bcf_cap, cudaHostAllocDefault));
+            CK(cudaHostAlloc((void**)&s.h_rec_off, (B + 1) * sizeof(long long), cudaHostAllocDefault));
+            memset(s.h_bcf_in, 0, B * sizeof(vgl_bcf_site_in));
+            CK(cudaMalloc((void**)&s.d_bcf_in, B * sizeof(vgl_bcf_site_in)));
+            CK(cudaMalloc((void**)&s.d_blob, ctx->blob_cap));
+            CK(cudaMalloc((void**)&s.d_bcf, ctx->bcf_cap));
+            CK(cudaMalloc((void**)&s.d_minmax, B * sizeof(BcfSiteMinMax)));
+            CK(cudaMalloc((void**)&s.d_rec_len, B * sizeof(uint32_t)));
+            CK(cudaMalloc((void**)&s.d_rec_off, (B + 1) * sizeof(long long)));
         } else if (p.host_output) {
             CK(cudaHostAlloc((void**)&s.h_dp, cells * sizeof(int32_t), cudaHostAllocDefault));
             if (t & VGL_TAG_GL) CK(cudaHostAlloc((void**)&s.h_gl, ctx->g_cap * 4, cudaHostAllocDefault));
@@ -428,6 +458,16 @@ extern "C" int vgl_input_buffer(vgl_ctx* ctx, int slot, uint8_t** gt, int64_t* c
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
     if (gt) *gt = ctx->slots[slot].h_gt;
     if (capacity_sites) *capacity_sites = ctx->prm.max_batch_sites;
+    return VGL_OK;
+}
+
+extern "C" int vgl_bcf_input_buffer(vgl_ctx* ctx, int slot, vgl_bcf_site_in** sites, uint8_t** blob, int64_t* blob_capacity)
+{
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    if (ctx->prm.host_output != VGL_HOST_BCF) return fail(ctx, VGL_ESTATE, "vgl_bcf_input_buffer: the context was not created with VGL_HOST_BCF");
+    if (sites) *sites = ctx->slots[slot].h_bcf_in;
+    if (blob) *blob = ctx->slots[slot].h_blob;
+    if (blob_capacity) *blob_capacity = (int64_t)ctx->blob_cap;
     return VGL_OK;
 }
 
@@ -592,7 +632,17 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     // status word: only the model-2 tile kernel in per-read-qs mode can raise a device-side error (a quality score outside
     // the --qs-bins ranges); it goes through the device word, cleared and copied back in stream order
     const bool narrow = prm.host_output == VGL_HOST_NARROW; // the narrowing pass can raise VGL_EOVERFLOW
-    const bool tile_status = tile_launch && ((ctx->use_tile_m2 && ctx->tile_m2_mode == 2) || narrow);
+    const bool bcf = prm.host_output == VGL_HOST_BCF;       // the serialiser posts its byte total (and VGL_EOVERFLOW) in the device words
+    const bool tile_status = tile_launch && ((ctx->use_tile_m2 && ctx->tile_m2_mode == 2) || narrow || bcf);
+    if (bcf) {
+        for (int32_t i = 0; i < n_sites; ++i) { // byte ranges must lie inside the blob
+            const vgl_bcf_site_in& b = s.h_bcf_in[i];
+            if ((size_t)b.id_off + b.id_len > ctx->blob_cap || (size_t)b.flt_info_off + b.flt_info_len > ctx->blob_cap)
+                return fail(ctx, VGL_EINVAL, "vgl_bcf_site_in: byte range outside the pass-through blob");
+        }
+        CK(cudaMemcpyAsync(s.d_bcf_in, s.h_bcf_in, (size_t)n_sites * sizeof(vgl_bcf_site_in), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.d_blob, s.h_blob, ctx->blob_cap, cudaMemcpyHostToDevice, st));
+    }
     if (tile_status) CK(cudaMemsetAsync(s.d_totals + 2, 0, sizeof(int64_t), st));
     const bool fused = (ctx->use_fused || ctx->use_tile_m2) && !rp;
     if (fused && !tile_launch) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
@@ -628,11 +678,26 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         if (s.d_adf) { launch_narrow(s.d_adf, s.d_adfn, nb, false, s.d_totals + 1, 0, (int64_t)ctx->r_cap, d_status, st, ctx->n_sms); ctx->launches += 1; }
         if (s.d_adr) { launch_narrow(s.d_adr, s.d_adrn, nb, false, s.d_totals + 1, 0, (int64_t)ctx->r_cap, d_status, st, ctx->n_sms); ctx->launches += 1; }
     }
+    if (bcf) { // planes -> BCF records (bcf.cu)
+        BcfArgs b;
+        memset(&b, 0, sizeof b);
+        b.S = (int32_t)S; b.n_sites = n_sites; b.tag_mask = prm.tag_mask;
+        b.do_unobserved = prm.do_unobserved; b.do_gvcf = prm.do_gvcf; b.dict = prm.bcf_dict;
+        b.sites = s.d_sites; b.site_in = s.d_bcf_in; b.blob = s.d_blob;
+        b.dp = s.d_dp; b.gl = s.d_gl; b.gp = s.d_gp; b.pl = s.d_pl; b.ad = s.d_ad; b.adf = s.d_adf; b.adr = s.d_adr;
+        b.minmax = s.d_minmax; b.rec_len = s.d_rec_len; b.rec_off = s.d_rec_off;
+        b.out = s.d_bcf; b.out_cap = (long long)ctx->bcf_cap;
+        b.totals = s.d_totals; b.status = reinterpret_cast<int32_t*>(s.d_totals + 2);
+        launch_bcf(b, st);
+        ctx->launches += 3;
+        CK(cudaMemcpyAsync(s.h_rec_off, s.d_rec_off, ((size_t)n_sites + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaGetLastError());
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
     if (tile_launch && !tile_status) s.h_totals[2] = 0; // the kernel posts the totals into the pinned words itself and raises no errors
     else CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (narrow) CK(cudaMemcpyAsync(s.h_dpn, s.d_dpn, (size_t)cells * (ctx->narrow_bits / 8), cudaMemcpyDeviceToHost, st));
+    else if (bcf) {}
     else if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_META], st));
     s.submitted = true;
@@ -655,6 +720,10 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
     if (prm.host_output && !s.waited) {
         cudaStream_t st = s.stream;
         CK(cudaEventRecord(s.ev[EV_D2H0], st));
+        if (prm.host_output == VGL_HOST_BCF) {
+            const int64_t nb = s.h_totals[3];
+            if (nb > 0 && nb <= (int64_t)ctx->bcf_cap) CK(cudaMemcpyAsync(s.h_bcf, s.d_bcf, (size_t)nb, cudaMemcpyDeviceToHost, st));
+        } else {
         if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
         if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
         if (ctx->narrow_bits) {
@@ -668,6 +737,7 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
             if (s.d_ad) CK(cudaMemcpyAsync(s.h_ad, s.d_ad, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
             if (s.d_adf) CK(cudaMemcpyAsync(s.h_adf, s.d_adf, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
             if (s.d_adr) CK(cudaMemcpyAsync(s.h_adr, s.d_adr, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+        }
         }
         CK(cudaEventRecord(s.ev[EV_D2H1], st));
         CK(cudaEventSynchronize(s.ev[EV_D2H1]));
@@ -708,6 +778,13 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
         out->ad_n = s.h_adn;
         out->adf_n = s.h_adfn;
         out->adr_n = s.h_adrn;
+    }
+    if (prm.host_output == VGL_HOST_BCF) { // the planes stay on the device; the host gets the serialised records
+        out->dp = nullptr; out->pl = out->ad = out->adf = out->adr = nullptr;
+        out->gl = out->gp = nullptr;
+        out->bcf = s.h_bcf;
+        out->bcf_off = reinterpret_cast<const int64_t*>(s.h_rec_off);
+        out->bcf_bytes = s.h_totals[3];
     }
     out->g_elems = g_elems;
     out->r_elems = r_elems;

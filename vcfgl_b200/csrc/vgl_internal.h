@@ -108,6 +108,31 @@ struct DevParams {
     const uint16_t* rp_deep_codes;
 };
 
+// VGL_HOST_BCF (bcf.cu): device serialisation of the kept sites as BCF records
+struct BcfSiteMinMax {
+    int32_t mn[5], mx[5]; // dp, pl, ad, adf, adr
+};
+struct BcfArgs {
+    int32_t S, n_sites;
+    uint32_t tag_mask;
+    int32_t do_unobserved, do_gvcf;
+    vgl_bcf_dict dict;
+    const vgl_site_out* sites;
+    const vgl_bcf_site_in* site_in;
+    const uint8_t* blob;
+    const int32_t* dp;
+    const float *gl, *gp;
+    const int32_t *pl, *ad, *adf, *adr;
+    BcfSiteMinMax* minmax; // [n_sites]
+    uint32_t* rec_len;     // [n_sites]
+    long long* rec_off;    // [n_sites + 1]
+    uint8_t* out;
+    long long out_cap;
+    int64_t* totals;       // [3] receives the total
+    int32_t* status;
+};
+void launch_bcf(const BcfArgs& a, cudaStream_t st);
+
 void launch_sim(const DevParams& p, cudaStream_t st);
 void launch_site(const DevParams& p, cudaStream_t st);
 void launch_scan(const DevParams& p, cudaStream_t st);
