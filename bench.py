@@ -301,7 +301,7 @@ def gpu_arm(opt):
     Ke = max(2, min(K, 4))
     s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
 
-    def e2e_steps(ctx, bufs, n, first):
+    def e2e_steps(ctx, bufs, n, first, bcf_in=None):
         pend = []
         d2h = 0
         for i in range(n):
@@ -310,6 +310,10 @@ def gpu_arm(opt):
                 b = ctx.wait(pend.pop(0))
                 d2h = out_bytes(b)
             bufs[s][:] = gt                       # the caller packs this step's genotypes into pinned memory
+            if bcf_in is not None:                # ... and the fields its input records pass through (CHROM, POS; ID ".", FILTER ".")
+                sin = bcf_in[s]
+                sin["pos"][:B] = np.arange(first + i * B, first + (i + 1) * B, dtype=np.int64) % (1 << 30)
+                sin["qual_bits"][:B] = capi.F32_MISSING_BITS
             ctx.submit(s, first + i * B, B)
             pend.append(s)
         for s in pend:
@@ -319,6 +323,8 @@ def gpu_arm(opt):
 
     def out_bytes(b):
         r = b.raw
+        if b.bcf_off is not None:   # VGL_HOST_BCF: the record stream, its offsets, the per-site records
+            return int(b.bcf_bytes + 8 * (b.n_sites + 1) + b.n_sites * capi.SITE_DTYPE.itemsize)
         w = (b.narrow_bits // 8) if b.narrow_bits else 4          # DP / AD element width
         n = b.n_sites * S * w + b.n_sites * capi.SITE_DTYPE.itemsize
         n += 4 * b.g_elems * sum(bool(x) for x in (r.gl, r.gp))
@@ -327,16 +333,18 @@ def gpu_arm(opt):
         return int(n)
 
     def e2e_run(mode):
-        ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=mode))
+        ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=mode,
+                                                 bcf_dict=dict(DP=1, GL=2, PL=3, GP=4, AD=5, ADF=6, ADR=7, QS=8, I16=9)))
         ctx.set_stream(0, s_a.cuda_stream)
         ctx.set_stream(1, s_b.cuda_stream)
         bufs = [ctx.input_buffer(0), ctx.input_buffer(1)]
-        e2e_steps(ctx, bufs, 2, site0 + (K + W) * B)
+        bcf_in = [ctx.bcf_input(0)[0], ctx.bcf_input(1)[0]] if mode == capi.HOST_BCF else None
+        e2e_steps(ctx, bufs, 2, site0 + (K + W) * B, bcf_in)
         barrier()
         l0 = ctx.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s_a)
-        d2h = e2e_steps(ctx, bufs, Ke, site0 + (K + W) * B)
+        d2h = e2e_steps(ctx, bufs, Ke, site0 + (K + W) * B, bcf_in)
         s_a.wait_stream(s_b)
         e1.record(s_a)
         barrier()
@@ -351,6 +359,12 @@ def gpu_arm(opt):
 
     e2e_i32, d2h_i32, _ = e2e_run(capi.HOST_I32)
     e2e_value, d2h_bytes, e2e_launches = e2e_run(capi.HOST_NARROW)
+    e2e_bcf = None
+    if not a.do_gvcf:   # serialised BCF records (the gVCF block merger consumes arrays)
+        v, nb, nl = e2e_run(capi.HOST_BCF)
+        e2e_bcf = {"value": v, "d2h_bytes_per_step": nb, "gpu_launches": int(nl),
+                   "planes": "VGL_HOST_BCF: complete BCF records serialised on the device (k_bcf_plan/scan/emit), byte-identical to "
+                             "the reference's -O u stream; the host only appends the buffer to the output"}
 
     if rank != 0:
         if dist is not None:
@@ -407,7 +421,8 @@ def gpu_arm(opt):
                 "steps": Ke, "gpu_launches": int(e2e_launches),
                 "planes": "VGL_HOST_NARROW: GL float32, PL/AD/DP narrowed on the device to the 8-bit values BCF stores",
                 "i32_planes": {"value": e2e_i32, "d2h_bytes_per_step": d2h_i32,
-                               "planes": "VGL_HOST_I32: every plane int32/float32 as add_tags() hands them to htslib"}},
+                               "planes": "VGL_HOST_I32: every plane int32/float32 as add_tags() hands them to htslib"},
+                "bcf_records": e2e_bcf},
         "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(line))
     if dist is not None:

@@ -228,3 +228,38 @@ def test_bcf_mode_rejects_gvcf_and_overflow_is_reported():
     with pytest.raises(capi.VglError) as e:
         capi.Context(capi.params_from_args(a, 4, 16, host_output=capi.HOST_BCF))
     assert e.value.code == capi.VGL_EINVAL
+
+
+def test_cpp_host_stream_writes_a_bcf_file_the_oracle_reads(tmp_path):
+    """vcfgl_b200/host/vgl_host.hpp BcfStreamSimulator (C++ host mirror over the C ABI): the file the example driver writes
+    parses as BCF and its records equal the oracle's encoding of the arrays the same parameters give through Python."""
+    import os
+    import subprocess
+    exe = os.path.join(bu.ROOT, "vcfgl_b200", "host", "example_driver")
+    if not os.path.exists(exe):
+        pytest.skip("example_driver not built")
+    out = str(tmp_path / "x.bcf")
+    n_sites, S = 11, 4
+    subprocess.check_call([exe, str(n_sites)], env=dict(os.environ, VGL_BCF_OUT=out))
+    _, ids, recs = bo.read_bcf(out)
+    a = vargs.parse_args("--seed 42 -d 4 -e 0.01 -GL 1 -doUnobserved 1 -addGL 1 -addPL 1 -addFormatAD 1 -addInfoDP 1".split())
+    gts = np.zeros((n_sites, 2 * S), np.int8)
+    for i in range(n_sites):
+        for s in range(S):
+            gts[i, 2 * s] = 1 if (i + s) % 3 == 2 else 0
+            gts[i, 2 * s + 1] = 1 if (i + s) % 3 >= 1 else 0
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=16, n_slots=1))
+    ctx.input_buffer(0)[:n_sites] = synth.pack_gt(gts)
+    ctx.submit(0, 0, n_sites)
+    b = ctx.wait(0)
+    want = []
+    for k in range(n_sites):
+        o = b.site(k)
+        if o["skip_code"] != 0:
+            continue
+        fmt = {"DP": o["fmt_dp"], "GL": o["gl"], "PL": o["pl"], "AD": o["fmt_ad"]}
+        alleles = bo.alleles_of_site(o["n_alleles"], o["alleles2acgt"], o["info_dp"], 1, 0)
+        want.append(bo.encode_record(0, 10 * k + 1, capi.F32_MISSING_BITS, b"\x07", b"\x11\x00", 0, alleles, S, ids, fmt,
+                                     {"DP": np.array([o["info_dp"]])}))
+    ctx.close()
+    assert recs == want

@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 int main(int argc, char** argv)
 {
@@ -25,6 +26,50 @@ int main(int argc, char** argv)
     p.max_batch_sites = 4;
     p.n_slots = 2;
     p.host_output = getenv("VGL_NARROW") ? VGL_HOST_NARROW : VGL_HOST_I32; // same records either way
+    if (const char* path = getenv("VGL_BCF_OUT")) { // VGL_HOST_BCF: write an uncompressed BCF file, records serialised on the device
+        try {
+            std::string hdr = "##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\",IDX=0>\n##contig=<ID=1,length=1000,IDX=0>\n";
+            hdr += "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"depth\",IDX=1>\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"depth\",IDX=1>\n";
+            hdr += "##FORMAT=<ID=GL,Number=G,Type=Float,Description=\"GL\",IDX=2>\n##FORMAT=<ID=PL,Number=G,Type=Integer,Description=\"PL\",IDX=3>\n";
+            hdr += "##FORMAT=<ID=AD,Number=R,Type=Integer,Description=\"AD\",IDX=4>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT";
+            for (int s = 0; s < S; ++s) hdr += "\tind" + std::to_string(s + 1);
+            hdr += "\n";
+            FILE* f = fopen(path, "wb");
+            if (!f) { perror(path); return 1; }
+            const uint32_t l_text = (uint32_t)hdr.size() + 1;
+            fwrite("BCF\2\2", 1, 5, f);
+            fwrite(&l_text, 4, 1, f);
+            fwrite(hdr.c_str(), 1, l_text, f);
+            vgl_bcf_dict dict;
+            memset(&dict, 0, sizeof dict);
+            dict.dp = 1; dict.gl = 2; dict.pl = 3; dict.ad = 4;
+            long n_rec_bytes = 0;
+            vgl::BcfStreamSimulator sim(p, dict, [&](const uint8_t* rec, size_t n, int n_sites_b, int n_skipped) {
+                fwrite(rec, 1, n, f); // the whole batch in one write: bcf_write() per record is gone
+                n_rec_bytes += (long)n;
+                fprintf(stderr, "batch: %d sites, %d skipped, %zu bytes\n", n_sites_b, n_skipped, n);
+            });
+            std::vector<int> gts(2 * S);
+            const uint8_t pass[2] = {0x11, 0x00}; // FILTER=PASS as the VCF parser encodes it
+            for (int i = 0; i < n_sites; ++i) {
+                for (int s = 0; s < S; ++s) {
+                    gts[2 * s] = (i + s) % 3 == 2 ? 1 : 0;
+                    gts[2 * s + 1] = (i + s) % 3 >= 1 ? 1 : 0;
+                }
+                float qual;
+                const uint32_t qmiss = VGL_F32_MISSING_BITS;
+                memcpy(&qual, &qmiss, 4);
+                sim.push_site(gts.data(), 0, 10 * i + 1, qual, nullptr, 0, pass, 2, 0);
+            }
+            sim.finish();
+            fclose(f);
+            printf("wrote %s: %d sites, %ld record bytes\n", path, n_sites, n_rec_bytes);
+            return 0;
+        } catch (const vgl::Error& e) {
+            fprintf(stderr, "vgl error %d: %s\n", e.status, e.what());
+            return e.status == VGL_ENODEV ? 3 : 1;
+        }
+    }
     try {
         vgl::BatchSimulator sim(p, [&](const vgl::SimRecordView& r) {
             if (r.ret < 0) { printf("site %ld skipped (%d)\n", (long)r.site_id, r.ret); return; }

@@ -231,4 +231,118 @@ private:
     int64_t next_site_ = 0;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// VGL_HOST_BCF: the reference's whole write path for a site -- add_tags() (bcf_utils.cpp:426-507) and bcf_write()
+// (htslib/vcf.c:1951-2001) -- happens on the device; the host only forwards what the input record passes through
+// and appends the returned bytes to the (uncompressed or BGZF) output stream.
+//
+//   reference                                            here
+//   ---------                                            ----
+//   simulate_record_values(sim) + write_record_values()  BcfStreamSimulator::push_site(gts, in_rec fields)
+//   bcf_write(out_fp, hdr, rec) per record               on_records(bytes, n_bytes, n_sites, n_skipped) per batch
+class BcfStreamSimulator {
+public:
+    using Sink = std::function<void(const uint8_t* records, size_t n_bytes, int n_sites, int n_skipped)>;
+
+    // dict: bcf_hdr_id2int(out_hdr, BCF_DT_ID, "DP" / "GL" / ...) of the output header
+    BcfStreamSimulator(vgl_params params, const vgl_bcf_dict& dict, Sink on_records) : prm_(params), sink_(std::move(on_records))
+    {
+        prm_.abi_version = VGL_ABI_VERSION;
+        prm_.host_output = VGL_HOST_BCF;
+        prm_.bcf_dict = dict;
+        if (prm_.n_slots < 2) prm_.n_slots = 2;
+        if (prm_.bcf_blob_bytes_per_site == 0) prm_.bcf_blob_bytes_per_site = 16;
+        const int rc = vgl_create(&prm_, &ctx_);
+        if (rc != VGL_OK) throw Error(rc, std::string("vgl_create: ") + vgl_strerror(rc));
+        in_flight_.assign(prm_.n_slots, false);
+        open_slot();
+    }
+    ~BcfStreamSimulator() { vgl_destroy(ctx_); }
+    BcfStreamSimulator(const BcfStreamSimulator&) = delete;
+    BcfStreamSimulator& operator=(const BcfStreamSimulator&) = delete;
+
+    // One input record (after check_rec_alleles, vcfgl.cpp:75-163).  id / flt_info: with in_rec unpacked,
+    //   id       = in_rec->shared.s[0 .. unpack_size[0])                              (nullptr / 0: ".")
+    //   flt_info = in_rec->shared.s[unpack_size[0] + unpack_size[1] .. shared.l)      (nullptr / 0: FILTER ".", no INFO)
+    void push_site(const int* true_gts_acgt_int, int32_t rid, int32_t pos, float qual, const uint8_t* id, uint32_t id_len,
+                   const uint8_t* flt_info, uint32_t flt_info_len, uint32_t n_info)
+    {
+        if (blob_fill_ + id_len + flt_info_len > (size_t)blob_cap_) {
+            if (fill_ == 0) throw Error(VGL_EINVAL, "pass-through fields of one record exceed the blob (raise bcf_blob_bytes_per_site)");
+            submit_current();
+        }
+        uint8_t* row = gt_ + (size_t)fill_ * prm_.n_samples;
+        for (int s = 0; s < prm_.n_samples; ++s) {
+            const int h0 = true_gts_acgt_int[2 * s], h1 = true_gts_acgt_int[2 * s + 1];
+            row[s] = VGL_GT_PACK(h0 < 0 ? VGL_GT_MISSING : h0, h1 < 0 ? VGL_GT_MISSING : h1);
+        }
+        vgl_bcf_site_in& r = sin_[fill_];
+        r.rid = rid;
+        r.pos = pos;
+        memcpy(&r.qual_bits, &qual, 4);
+        r.n_info = n_info;
+        r.id_off = (uint32_t)blob_fill_;
+        r.id_len = id_len;
+        if (id_len) memcpy(blob_ + blob_fill_, id, id_len);
+        blob_fill_ += id_len;
+        r.flt_info_off = (uint32_t)blob_fill_;
+        r.flt_info_len = flt_info_len;
+        if (flt_info_len) memcpy(blob_ + blob_fill_, flt_info, flt_info_len);
+        blob_fill_ += flt_info_len;
+        if (++fill_ == prm_.max_batch_sites) submit_current();
+    }
+
+    void finish()
+    {
+        if (fill_ > 0) submit_current();
+        for (int k = 0; k < prm_.n_slots; ++k) drain((cur_ + k) % prm_.n_slots);
+    }
+
+private:
+    void check(int rc, const char* what)
+    {
+        if (rc != VGL_OK) throw Error(rc, std::string(what) + ": " + vgl_strerror(rc) + " (" + vgl_last_error(ctx_) + ")");
+    }
+    void open_slot()
+    {
+        drain(cur_);
+        int64_t cap = 0;
+        check(vgl_input_buffer(ctx_, cur_, &gt_, &cap), "vgl_input_buffer");
+        check(vgl_bcf_input_buffer(ctx_, cur_, &sin_, &blob_, &blob_cap_), "vgl_bcf_input_buffer");
+        fill_ = 0;
+        blob_fill_ = 0;
+    }
+    void submit_current()
+    {
+        check(vgl_submit(ctx_, cur_, next_site_, fill_, nullptr, 0), "vgl_submit");
+        in_flight_[cur_] = true;
+        next_site_ += fill_;
+        cur_ = (cur_ + 1) % prm_.n_slots;
+        open_slot();
+    }
+    void drain(int slot)
+    {
+        if (!in_flight_[slot]) return;
+        vgl_batch_out out;
+        check(vgl_wait(ctx_, slot, &out), "vgl_wait");
+        if (out.status != VGL_OK) throw Error(out.status, vgl_strerror(out.status));
+        int skipped = 0;
+        for (int i = 0; i < out.n_sites; ++i) skipped += out.sites[i].skip_code != 0; // nSitesSkipped, vcfgl.cpp:1553-1558
+        sink_(out.bcf, (size_t)out.bcf_bytes, out.n_sites, skipped);
+        in_flight_[slot] = false;
+    }
+
+    vgl_params prm_;
+    Sink sink_;
+    vgl_ctx* ctx_ = nullptr;
+    std::vector<bool> in_flight_;
+    uint8_t *gt_ = nullptr, *blob_ = nullptr;
+    vgl_bcf_site_in* sin_ = nullptr;
+    int64_t blob_cap_ = 0;
+    size_t blob_fill_ = 0;
+    int cur_ = 0;
+    int32_t fill_ = 0;
+    int64_t next_site_ = 0;
+};
+
 } // namespace vgl
