@@ -366,6 +366,11 @@ def gpu_arm(opt):
                    "planes": "VGL_HOST_BCF: complete BCF records serialised on the device (k_bcf_plan/scan/emit), byte-identical to "
                              "the reference's -O u stream; the host only appends the buffer to the output"}
 
+    # ---------------- input path: VCF text -> packed genotypes on the device -> the same kernels
+    input_path = None
+    if world == 1 and not opt.no_input_path:
+        input_path = input_path_leg(a, gt, hap, B, S, site0 + (K + W + 2) * B, local, peak_of=measured_peak)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -423,10 +428,88 @@ def gpu_arm(opt):
                 "i32_planes": {"value": e2e_i32, "d2h_bytes_per_step": d2h_i32,
                                "planes": "VGL_HOST_I32: every plane int32/float32 as add_tags() hands them to htslib"},
                 "bcf_records": e2e_bcf},
+        "input_path": input_path,
         "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def input_path_leg(a, gt, hap, B, S, first_site, local, peak_of):
+    """k_vcf_lines + k_vcf_gt on one step's worth of msprime-shaped VCF text (B records x S samples):
+    `value`  text resident in HBM, kernels only (CUDA events on the parser's stream);
+    `e2e`    host text in pinned memory -> H2D -> parse -> place -> simulate -> D2H of the narrowed planes;
+    `cpu_baseline`  the oracle's single-threaded C restatement of the same parse on a bounded sample."""
+    import numpy as np
+    import torch
+    from vcfgl_b200 import capi, synth
+    pos = np.arange(1, B + 1, dtype=np.int64) * 7
+    body = synth.vcf_body(hap, pos)
+    n_text = len(body)
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=capi.HOST_NARROW))
+    ps = ctx.parser(n_text + 64, B)
+    res = ps.parse(body, capi.SOURCE_BINARY, 0)
+    assert res.n_records == B and res.n_errors == 0 and res.bytes_consumed == n_text, (res.n_records, res.n_errors)
+    assert np.array_equal(ps.rows(0, 64), gt[:64]) and np.array_equal(ps.rows(B - 64, 64), gt[B - 64:])
+    reps, ms = 6, []
+    for _ in range(2):
+        ps.parse(None, capi.SOURCE_BINARY, capi.PARSE_TEXT_ON_DEVICE, n_bytes=n_text)
+    for _ in range(reps):
+        ms.append(ps.parse(None, capi.SOURCE_BINARY, capi.PARSE_TEXT_ON_DEVICE, n_bytes=n_text).ms_kernels)
+    k_ms = float(np.mean(ms))
+    alg = n_text + B * S + B * capi.IN_SITE_DTYPE.itemsize
+    peak, peak_src = peak_of()
+    # end to end from text
+    def step(i, slot):
+        r = ps.parse(None, capi.SOURCE_BINARY, 0, n_bytes=n_text)          # H2D of the pinned text + kernels
+        ctx.place_rows(slot, ps, B)
+        ctx.submit(slot, first_site + i * B, B, flags=capi.SUBMIT_GT_ON_DEVICE)
+        return r
+    for i in range(2):
+        step(i, i & 1)
+    ctx.wait(0), ctx.wait(1)
+    torch.cuda.synchronize()
+    n_e2e = 4
+    import time as _t
+    t0 = _t.perf_counter()
+    pend = []
+    for i in range(n_e2e):
+        slot = i & 1
+        if len(pend) == 2:
+            ctx.wait(pend.pop(0))
+        step(i, slot)
+        pend.append(slot)
+    for slot in pend:
+        ctx.wait(slot)
+    torch.cuda.synchronize()
+    wall = _t.perf_counter() - t0
+    ps.close()
+    ctx.close()
+    # CPU baseline: oracle restatement, one thread, bounded sample
+    cpu = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import vcfin_oracle as vo
+        n_cpu = min(B, 32768)
+        cut = 0
+        for _ in range(n_cpu):
+            cut = body.index(b"\n", cut) + 1
+        t0 = _t.perf_counter()
+        sites, rows, used = vo.parse(body[:cut], S, 0)
+        dt = _t.perf_counter() - t0
+        assert len(sites) == n_cpu and np.array_equal(rows, gt[:n_cpu])
+        cpu = {"value": n_cpu * S / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "oracle/vcf_in_oracle.c on the first %d records (%.1f MB of text), %.3f s" % (n_cpu, cut / 1e6, dt)}
+    except Exception as e:      # the oracle is test infrastructure; its absence must not break the bench line
+        cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
+    return {"what": "VCF text -> packed genotypes on the device (k_vcf_lines + k_vcf_gt), %d records x %d samples, %.1f MB of text per step" % (B, S, n_text / 1e6),
+            "value": B * S / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "gpu_launches_per_step": 2,
+            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_step": alg, "bytes_per_cell": alg / (B * S)},
+            "e2e": {"value": n_e2e * B * S / wall, "unit": UNIT, "h2d_bytes_per_step": n_text, "steps": n_e2e,
+                    "note": "pinned host text -> H2D -> k_vcf_lines/k_vcf_gt -> k_place_rows -> simulate -> D2H (VGL_HOST_NARROW); host wall clock, two slots"},
+            "cpu_baseline": cpu}
 
 
 def main():
@@ -436,6 +519,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-input-path", action="store_true", help="skip the VCF-text input-path leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: stop after the kernel-side loop")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3a", "cfg3b", "cfg4", "cfg5"])
     opt = ap.parse_args()

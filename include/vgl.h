@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 3
+#define VGL_ABI_VERSION 4
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -282,6 +282,84 @@ int64_t vgl_algorithmic_bytes(const vgl_batch_out* out, uint32_t tag_mask);
  * the 3-instruction /10 and the branch-free lroundf -- equal the reference's expressions
  * (gl_methods.cpp:343, vcfgl.cpp:931).  *n_mismatch must come back 0. */
 int vgl_selftest(int device_id, int64_t* n_mismatch, uint32_t* first_mismatch_bits);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Input path: VCF text records -> packed true genotypes, on the device.
+ *
+ * Replaces, for the records of a batch, what the reference's driver loop does per record before the hot path:
+ *   bcf_read -> vcf_parse / vcf_parse_format (GT vector)      htslib/vcf.c:3041-3110, 2425-2790
+ *   bcf_get_genotypes + check_rec_alleles()                   vcfgl.cpp:75-163
+ * The host keeps the header (it supplies record lines only) and everything dictionary-shaped (CHROM -> rid, ID, FILTER,
+ * INFO); per record the device returns POS, the allele map, the skip decision of --rm-invar-sites bits 1 / 2 and the
+ * byte ranges of the line the host may still want to look at, and leaves the record's genotypes as one row of packed
+ * bytes in HBM.  vgl_place_rows() then builds a slot's genotype matrix from those rows -- dropping skipped records and
+ * inserting the all-hom-ref sites of -explode 1 (vcfgl.cpp:1480-1538, 1567-1611) -- and the batch is submitted with
+ * VGL_SUBMIT_GT_ON_DEVICE: genotypes never exist on the host in unpacked form.
+ */
+enum { VGL_SOURCE_BINARY = 0, /* --source 0: REF=0 ALT=1, simulated as A / C (vcfgl.cpp:103-127) */
+       VGL_SOURCE_ACGT = 1 }; /* --source 1: alleles are bases (vcfgl.cpp:98-101) */
+
+/* per-record status: where the reference would exit (ERROR / ASSERT) the parser reports a code; if a line has several
+ * defects the smallest code wins */
+typedef enum vgl_in_status {
+    VGL_IN_OK = 0,
+    VGL_IN_ENCOLS = 1,     /* fewer than 10 columns */
+    VGL_IN_EPOS = 2,       /* POS beyond int32 */
+    VGL_IN_ENALLELE = 3,   /* > 5 alleles (vcfgl.cpp:90-92) or > 2 with --source 0 (vcfgl.cpp:123-125) */
+    VGL_IN_EALLELE = 4,    /* allele not a base (vcfgl.cpp:99-101) / not 0 or 1 (vcfgl.cpp:113-115) */
+    VGL_IN_ENOGT = 5,      /* no GT in FORMAT (vcfgl.cpp:83-85) */
+    VGL_IN_ENSAMPLES = 6,  /* fewer sample columns than n_samples (htslib/vcf.c:2777-2783) */
+    VGL_IN_EGTCHAR = 7,    /* GT not a number or '.', or an invalid character after it (htslib/vcf.c:2666-2669, 2729-2737) */
+    VGL_IN_EPLOIDY = 8,    /* a sample is not diploid (the reference reads gt_arr as [2 * n_samples], vcfgl.cpp:131-146) */
+    VGL_IN_EALLELEIDX = 9, /* GT allele index >= n_allele (vcfgl.cpp:144) */
+    VGL_IN_ESYMBOLIC = 10  /* GT points at <*> / <NON_REF> */
+} vgl_in_status;
+
+typedef struct vgl_in_site {
+    int32_t status;        /* vgl_in_status */
+    int32_t skip_code;     /* 0; -1 all true genotypes hom-ref, -2 all hom-alt (check_rec_alleles, vcfgl.cpp:150-160) */
+    int64_t pos;           /* bcf1_t::pos, 0-based */
+    int64_t allele_sum;    /* sum of the GT allele indices (vcfgl.cpp:145) */
+    uint64_t line_off;     /* the record's line in the text chunk ... */
+    uint32_t line_len;     /* ... without its LF (and CR) */
+    int32_t n_allele;      /* bcf1_t::n_allele */
+    int8_t allele_acgt[8]; /* [5] used: rec_alleles[] of check_rec_alleles (4 = <*> / <NON_REF>, -1 = none / invalid) */
+    uint32_t id_off, fmt_off, samples_off; /* start of the ID, FORMAT and first sample column, relative to line_off */
+    uint32_t _pad;
+} vgl_in_site;
+
+typedef struct vgl_parser vgl_parser;
+
+/* a parser belongs to a context (device, n_samples, --rm-invar-sites); it owns a pinned text staging buffer, the device
+ * copy of the text, the record index and the genotype rows [max_records][n_samples], and its own stream */
+int vgl_parser_create(vgl_ctx* ctx, int64_t max_text_bytes /* < 4 GiB */, int32_t max_records, vgl_parser** out);
+void vgl_parser_destroy(vgl_parser* ps);
+int vgl_parser_text_buffer(vgl_parser* ps, uint8_t** text, int64_t* capacity);
+
+enum { VGL_PARSE_FINAL = 1 << 0,           /* last chunk of the file: a tail without LF is a record too */
+       VGL_PARSE_TEXT_ON_DEVICE = 1 << 1 }; /* reuse the text already on the device (skips the H2D copy) */
+
+typedef struct vgl_parse_out {
+    int32_t n_records;           /* complete lines parsed (at most max_records) */
+    int32_t n_errors;            /* records with status != VGL_IN_OK */
+    int32_t first_error_record;  /* -1 if none */
+    int32_t n_kept;              /* records with status OK and skip_code 0 */
+    int64_t bytes_consumed;      /* text bytes covered by those records: carry the rest over to the next chunk */
+    const vgl_in_site* sites;    /* [n_records], pinned host memory owned by the parser */
+    float ms_h2d, ms_kernels;    /* CUDA events on the parser's stream */
+} vgl_parse_out;
+
+/* synchronous: H2D of the text, k_vcf_lines (record index), k_vcf_gt (columns, alleles, genotypes), D2H of the site records */
+int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source, uint32_t flags, vgl_parse_out* out);
+
+/* copies genotype rows of the last parse to host memory (tests, debugging): host_dst [n_records][n_samples] */
+int vgl_parser_rows(vgl_parser* ps, int32_t first_record, int32_t n_records, uint8_t* host_dst);
+
+/* builds slot `slot`'s device genotype matrix: site r takes the row of record row_map[r], or fill_gt in every sample when
+ * row_map[r] < 0 (an -explode 1 site: the blank record's GT is 0|0, i.e. VGL_GT_PACK(ref, ref)).  row_map == NULL selects
+ * records first_record .. first_record + n_sites - 1.  Asynchronous on the slot's stream; follow with
+ * vgl_submit(..., VGL_SUBMIT_GT_ON_DEVICE). */
+int vgl_place_rows(vgl_ctx* ctx, int slot, vgl_parser* ps, const int32_t* row_map, int32_t first_record, int32_t n_sites, uint8_t fill_gt);
 
 const char* vgl_strerror(int status);
 const char* vgl_last_error(const vgl_ctx* ctx);

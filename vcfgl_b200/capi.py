@@ -20,7 +20,7 @@ if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same AB
     LIB_PATH = os.environ["VGL_LIB"]
 
 VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
-ABI_VERSION = 3
+ABI_VERSION = 4
 HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF = 0, 1, 2, 3
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
@@ -29,7 +29,22 @@ I32_MISSING = -(2 ** 31)
 
 EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_bcf_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
            "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
-           "vgl_last_error", "vgl_abi_version", "vgl_native_kernels"]
+           "vgl_last_error", "vgl_abi_version", "vgl_native_kernels",
+           "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parser_rows", "vgl_place_rows"]
+
+SOURCE_BINARY, SOURCE_ACGT = 0, 1
+PARSE_FINAL, PARSE_TEXT_ON_DEVICE = 1, 2
+(IN_OK, IN_ENCOLS, IN_EPOS, IN_ENALLELE, IN_EALLELE, IN_ENOGT, IN_ENSAMPLES, IN_EGTCHAR, IN_EPLOIDY, IN_EALLELEIDX,
+ IN_ESYMBOLIC) = range(11)
+IN_SITE_DTYPE = np.dtype([("status", "<i4"), ("skip_code", "<i4"), ("pos", "<i8"), ("allele_sum", "<i8"), ("line_off", "<u8"),
+                          ("line_len", "<u4"), ("n_allele", "<i4"), ("allele_acgt", "i1", (8,)), ("id_off", "<u4"),
+                          ("fmt_off", "<u4"), ("samples_off", "<u4"), ("_pad", "<u4")])
+assert IN_SITE_DTYPE.itemsize == 64
+
+
+class VglParseOut(C.Structure):
+    _fields_ = [("n_records", C.c_int32), ("n_errors", C.c_int32), ("first_error_record", C.c_int32), ("n_kept", C.c_int32),
+                ("bytes_consumed", C.c_int64), ("sites", C.c_void_p), ("ms_h2d", C.c_float), ("ms_kernels", C.c_float)]
 
 
 class VglBcfDict(C.Structure):
@@ -139,6 +154,13 @@ def load():
     L.vgl_last_error.argtypes = [C.c_void_p]
     L.vgl_last_error.restype = C.c_char_p
     L.vgl_abi_version.restype = C.c_int
+    L.vgl_parser_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
+    L.vgl_parser_destroy.argtypes = [C.c_void_p]
+    L.vgl_parser_destroy.restype = None
+    L.vgl_parser_text_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.vgl_parse_vcf.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.POINTER(VglParseOut)]
+    L.vgl_parser_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.vgl_place_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint8]
     _lib = L
     return L
 
@@ -404,3 +426,74 @@ class Context:
         C.memmove(C.byref(raw), C.byref(batch.raw), C.sizeof(raw))
         raw.sites = C.cast(batch.sites.ctypes.data, C.POINTER(VglSiteOut))
         return int(self.L.vgl_algorithmic_bytes(C.byref(raw), self.params.tag_mask))
+
+
+    def parser(self, max_text_bytes: int, max_records: int) -> "Parser":
+        return Parser(self, max_text_bytes, max_records)
+
+    def place_rows(self, slot: int, parser: "Parser", n_sites: int, row_map=None, first_record: int = 0, fill_gt: int = 0):
+        """slot genotype matrix <- parsed rows (vgl_place_rows); follow with submit(..., flags=SUBMIT_GT_ON_DEVICE)"""
+        mp = None
+        if row_map is not None:
+            row_map = np.ascontiguousarray(row_map, np.int32)
+            assert len(row_map) == n_sites
+            mp = row_map.ctypes.data
+        self._ck(self.L.vgl_place_rows(self.h, slot, parser.h, mp, first_record, n_sites, fill_gt))
+
+
+class ParseResult:
+    def __init__(self, out: VglParseOut):
+        self.n_records, self.n_errors, self.first_error_record = out.n_records, out.n_errors, out.first_error_record
+        self.n_kept, self.bytes_consumed = out.n_kept, out.bytes_consumed
+        self.ms_h2d, self.ms_kernels = out.ms_h2d, out.ms_kernels
+        if out.n_records:
+            self.sites = np.ctypeslib.as_array(C.cast(out.sites, C.POINTER(C.c_uint8)),
+                                               shape=(out.n_records * IN_SITE_DTYPE.itemsize,)).view(IN_SITE_DTYPE)
+        else:
+            self.sites = np.zeros(0, IN_SITE_DTYPE)
+
+
+class Parser:
+    """Device-side VCF text -> packed-genotype parser of a context (include/vgl.h, "Input path")."""
+
+    def __init__(self, ctx: Context, max_text_bytes: int, max_records: int):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        ctx._ck(self.L.vgl_parser_create(ctx.h, max_text_bytes, max_records, C.byref(self.h)))
+        ptr, cap = C.c_void_p(), C.c_int64()
+        ctx._ck(self.L.vgl_parser_text_buffer(self.h, C.byref(ptr), C.byref(cap)))
+        self.text = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(cap.value,))
+        self.S = ctx.S
+
+    def close(self):
+        if self.h:
+            self.L.vgl_parser_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def parse(self, data=None, gt_source: int = SOURCE_BINARY, flags: int = 0, n_bytes: Optional[int] = None) -> ParseResult:
+        """`data` (bytes / uint8 array) is staged into the pinned text buffer first; pass None with n_bytes when the
+        caller filled `self.text` itself (or with PARSE_TEXT_ON_DEVICE)."""
+        if data is not None:
+            a = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data
+            n_bytes = len(a)
+            self.text[:n_bytes] = a
+        out = VglParseOut()
+        rc = self.L.vgl_parse_vcf(self.h, int(n_bytes), gt_source, flags, C.byref(out))
+        if rc != VGL_OK:
+            raise VglError(rc, self.L.vgl_strerror(rc).decode())
+        return ParseResult(out)
+
+    def rows(self, first_record: int, n_records: int) -> np.ndarray:
+        out = np.empty((n_records, self.S), np.uint8)
+        if n_records == 0:
+            return out
+        rc = self.L.vgl_parser_rows(self.h, first_record, n_records, out.ctypes.data)
+        if rc != VGL_OK:
+            raise VglError(rc, self.L.vgl_strerror(rc).decode())
+        return out

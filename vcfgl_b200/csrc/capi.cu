@@ -480,6 +480,45 @@ extern "C" int vgl_set_stream(vgl_ctx* ctx, int slot, void* cuda_stream)
     return VGL_OK;
 }
 
+// ---- input path (vcfin.cu) ----
+extern "C" int vgl_parser_create(vgl_ctx* ctx, int64_t max_text_bytes, int32_t max_records, vgl_parser** out)
+{
+    if (!ctx || !out) return VGL_EINVAL;
+    const int rc = parser_create(ctx->prm.device_id, ctx->prm.n_samples, ctx->prm.rm_invar_sites, ctx->n_sms, max_text_bytes, max_records, out, ctx->err);
+    return rc;
+}
+
+extern "C" int vgl_place_rows(vgl_ctx* ctx, int slot, vgl_parser* ps, const int32_t* row_map, int32_t first_record, int32_t n_sites, uint8_t fill_gt)
+{
+    if (!ctx || !ps || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    if (ps->S != ctx->prm.n_samples || ps->device != ctx->prm.device_id) return fail(ctx, VGL_EINVAL, "vgl_place_rows: parser belongs to another context geometry");
+    if (n_sites < 1 || n_sites > ctx->prm.max_batch_sites) return fail(ctx, VGL_EINVAL, "vgl_place_rows: n_sites out of range");
+    Slot& s = ctx->slots[slot];
+    if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight: call vgl_wait first");
+    if (row_map) {
+        if (n_sites > ps->max_records) return fail(ctx, VGL_EINVAL, "vgl_place_rows: a row map holds at most the parser's max_records entries");
+        for (int32_t i = 0; i < n_sites; ++i)
+            if (row_map[i] >= ps->n_records) return fail(ctx, VGL_EINVAL, "vgl_place_rows: row_map entry beyond the parsed records");
+    } else if (first_record < 0 || first_record + n_sites > ps->n_records)
+        return fail(ctx, VGL_EINVAL, "vgl_place_rows: record range beyond the parsed records");
+    CK(cudaSetDevice(ctx->prm.device_id));
+    cudaStream_t st = s.stream;
+    CK(cudaStreamWaitEvent(st, ps->ev_done, 0));
+    if (ps->placed) CK(cudaStreamWaitEvent(st, ps->ev_placed, 0)); // the shared row-map buffer may still be read by the previous placement
+    const int32_t* d_map = nullptr;
+    if (row_map) {
+        CK(cudaMemcpyAsync(ps->d_row_map, row_map, (size_t)n_sites * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st)); // row_map is the caller's (pageable) memory
+        d_map = ps->d_row_map;
+    }
+    launch_place_rows(ps->d_rows, d_map, first_record, n_sites, ctx->prm.n_samples, fill_gt, s.d_gt, st, ctx->n_sms);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ps->ev_placed, st));
+    ps->placed = true;
+    return VGL_OK;
+}
+
 template <typename T>
 static int stage_replay(vgl_ctx* ctx, DevBuf& b, const T* h, size_t n, cudaStream_t st, const T** d_out)
 {

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "../../include/vgl.h"
 
 namespace vgl {
@@ -154,4 +156,30 @@ size_t tile_m1f_scratch_words(int S, int n_sms);
 void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
                   uint8_t* adjqs, uint8_t* tails, double* eprob);
 
+// input path (vcfin.cu)
+void launch_place_rows(const uint8_t* rows, const int32_t* d_row_map, int32_t first_record, int32_t n_sites, int32_t S, uint8_t fill, uint8_t* gt,
+                       cudaStream_t st, int n_sms);
+int parser_create(int device, int S, int rm_invar, int n_sms, int64_t max_text, int32_t max_records, vgl_parser** out, std::string& err);
+void parser_destroy(vgl_parser* ps);
+
 } // namespace vgl
+
+// VCF text parser object of the input path (include/vgl.h); owned by the caller, tied to a context's device and geometry
+struct vgl_parser {
+    int device = 0, S = 0, rm_invar = 0, n_sms = 148;
+    int32_t max_records = 0, n_records = 0;
+    size_t text_cap = 0, d_text_bytes = 0;
+    uint32_t max_tiles = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {};
+    cudaEvent_t ev_done = nullptr; // rows of the last parse are complete
+    cudaEvent_t ev_placed = nullptr; // the last vgl_place_rows() that read them has run
+    bool placed = false;
+    uint8_t *h_text = nullptr, *d_text = nullptr, *d_rows = nullptr;
+    uint32_t *d_line_end = nullptr, *d_counters = nullptr, *h_counters = nullptr;
+    unsigned long long* d_tile_state = nullptr;
+    vgl_in_site *d_sites = nullptr, *h_sites = nullptr;
+    int32_t* d_row_map = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};

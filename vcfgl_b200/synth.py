@@ -54,12 +54,19 @@ def positions(n_sites: int, length: int, seed: int) -> np.ndarray:
     return np.sort(rng.choice(pos, size=n_sites, replace=False))
 
 
-def write_vcf(path: str, hap: np.ndarray, pos: np.ndarray, length: int, contig: str = "1",
-              ref: str = "0", alt: str = "1") -> None:
-    """Write binary haplotypes as a tskit-style VCF (for the reference CPU binary)."""
+def vcf_header(n_samples: int, length: int, contig: str = "1") -> bytes:
+    return ("##fileformat=VCFv4.2\n##source=vcfgl_b200.synth\n"
+            "##FILTER=<ID=PASS,Description=\"All filters passed\">\n"
+            "##contig=<ID=%s,length=%d>\n"
+            "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n"
+            % (contig, length, "\t".join("tsk_%d" % i for i in range(n_samples)))).encode()
+
+
+def vcf_body(hap: np.ndarray, pos: np.ndarray, contig: str = "1", ref: str = "0", alt: str = "1") -> bytes:
+    """the record lines of a tskit-style VCF: one 4-byte column per sample, "a|b\t" (".|.\t" when missing)"""
     n_sites, H = hap.shape
     S = H // 2
-    # one 4-byte field per sample: "a|b\t" (".|.\t" when missing)
     ch = np.where(hap < 0, ord("."), hap + ord("0")).astype(np.uint8)
     body = np.empty((n_sites, S, 4), np.uint8)
     body[:, :, 0] = ch[:, 0::2]
@@ -68,13 +75,16 @@ def write_vcf(path: str, hap: np.ndarray, pos: np.ndarray, length: int, contig: 
     body[:, :, 3] = ord("\t")
     body = body.reshape(n_sites, S * 4)
     body[:, -1] = ord("\n")
+    out = []
+    for i in range(n_sites):
+        out.append(("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t" % (contig, pos[i], ref, alt)).encode())
+        out.append(body[i].tobytes())
+    return b"".join(out)
+
+
+def write_vcf(path: str, hap: np.ndarray, pos: np.ndarray, length: int, contig: str = "1",
+              ref: str = "0", alt: str = "1") -> None:
+    """Write binary haplotypes as a tskit-style VCF (for the reference CPU binary)."""
     with open(path, "wb") as fh:
-        fh.write(("##fileformat=VCFv4.2\n##source=vcfgl_b200.synth\n"
-                  "##FILTER=<ID=PASS,Description=\"All filters passed\">\n"
-                  "##contig=<ID=%s,length=%d>\n"
-                  "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
-                  "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n"
-                  % (contig, length, "\t".join("tsk_%d" % i for i in range(S)))).encode())
-        for i in range(n_sites):
-            fh.write(("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t" % (contig, pos[i], ref, alt)).encode())
-            fh.write(body[i].tobytes())
+        fh.write(vcf_header(hap.shape[1] // 2, length, contig))
+        fh.write(vcf_body(hap, pos, contig, ref, alt))
