@@ -109,29 +109,36 @@ def fuzz_body(rng, n_lines, S, source):
     keys = [b"GT", b"DP", b"GQ", b"PL", b"AD"]
     lines = []
     for _ in range(n_lines):
-        n_alt = int(rng.choice([0, 1, 1, 1, 2, 3, 4, 5]))
-        good = rng.random() < 0.8
+        clean = rng.random() < 0.6          # a record without defects (whatever its shape)
+        n_alt = int(rng.choice([0, 1, 1, 1, 2, 3, 4] if clean else [0, 1, 1, 1, 2, 3, 4, 5]))
+        good = clean or rng.random() < 0.8
         pool = alleles[:4] if (good and source) else alleles[:2] if good else alleles
         ref = pool[rng.integers(len(pool))]
         alt = b",".join(pool[rng.integers(len(pool))] for _ in range(n_alt)) if n_alt else b"."
         if not source and good and n_alt > 1:
             alt = alt.split(b",")[0]
+        if clean and rng.random() < 0.3:      # the tskit shape: FORMAT "GT", every column "a|b"
+            line = b"\t".join([b"1", str(int(rng.integers(1, 10 ** 9))).encode(), b".", ref, alt, b".", b"PASS", b".", b"GT"] +
+                              [rng.choice([b"0", b"1", b"."], p=[0.6, 0.3, 0.1]) + rng.choice([b"|", b"/"]) +
+                               (b"1" if alt != b"." and rng.random() < 0.4 else b"0") for _ in range(S)])
+            lines.append(line + (b"\r" if rng.random() < 0.1 else b""))
+            continue
         n_al = 1 + (len(alt.split(b",")) if alt != b"." else 0)
         fmt = [keys[i] for i in rng.permutation(len(keys))[:rng.integers(1, 4)]]
-        if rng.random() < 0.9 and b"GT" not in fmt:
+        if (clean or rng.random() < 0.9) and b"GT" not in fmt:
             fmt[rng.integers(len(fmt))] = b"GT"
         if rng.random() < 0.7 and b"GT" in fmt:
             fmt.remove(b"GT")
             fmt.insert(0, b"GT")
         cols = []
-        n_cols = S if rng.random() < 0.95 else int(rng.integers(0, S + 3))
+        n_cols = S if (clean or rng.random() < 0.95) else int(rng.integers(0, S + 3))
         for _s in range(n_cols):
             sub = []
             for k in fmt:
                 if k != b"GT":
                     sub.append(rng.choice([b"3", b"17", b".", b"1,2,3", b""]))
                     continue
-                r = rng.random()
+                r = rng.random() * (0.8 if clean else 1.0)
                 if r < 0.8:
                     a = [str(int(rng.integers(0, max(n_al, 1)))).encode() if rng.random() < 0.93 else b"." for _ in range(2)]
                     sub.append(a[0] + rng.choice([b"|", b"/"]) + a[1])
@@ -141,15 +148,15 @@ def fuzz_body(rng, n_lines, S, source):
                     sub.append(str(int(rng.integers(0, 12))).encode() + b"|" + b"0" * int(rng.integers(1, 3)) + str(int(rng.integers(0, 3))).encode())
                 else:
                     sub.append(str(int(rng.integers(0, n_al + 1))).encode() + b"/" + str(int(rng.integers(0, n_al + 1))).encode())
-            if rng.random() < 0.03:
+            if not clean and rng.random() < 0.03:
                 sub = sub[:rng.integers(0, len(sub) + 1)]
             cols.append(b":".join(sub))
         pos = rng.choice([str(int(rng.integers(0, 10 ** 6))).encode(), b"+12", b"0", b"12x", b"99999999999", b"18446744073709551616000"],
-                         p=[0.9, 0.02, 0.02, 0.02, 0.02, 0.02])
+                         p=[0.94, 0.02, 0.02, 0.02, 0, 0] if clean else [0.9, 0.02, 0.02, 0.02, 0.02, 0.02])
         fixed = [rng.choice([b"1", b"chr2", b"c"]), pos, rng.choice([b".", b"rs7", b"a;b"]), ref, alt,
                  rng.choice([b".", b"30", b"1e3"]), rng.choice([b".", b"PASS", b"q10;s50"]),
                  rng.choice([b".", b"NS=3;DP=14", b"X" * int(rng.integers(1, 700))]), b":".join(fmt)]
-        if rng.random() < 0.03:
+        if not clean and rng.random() < 0.03:
             fixed = fixed[:rng.integers(0, 9)]
             cols = []
         line = b"\t".join(fixed + cols)
@@ -276,5 +283,52 @@ def test_text_to_tags_large_explode():
             assert same_site(b.site(i), ref[k + i]) is None, (k + i, same_site(b.site(i), ref[k + i]))
         k += b.n_sites
     assert k == L
+    ps.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("cid", ["in_acgt_explode", "in_acgt_rm3", "in_binary_plain", "in_binary_rm3_explode"])
+def test_cpp_host_driver(cid, tmp_path):
+    """vcfgl_b200/host/vgl_host.hpp VcfTextSimulator (the C++ mirror of the reference's driver loop) reads the VCF file itself:
+    same site sequence as the reference capture, same DP / AD as the Python host path on the same parameters"""
+    import gzip
+    import os
+    import subprocess
+    exe = os.path.join(vo.ROOT, "vcfgl_b200", "host", "example_driver")
+    if not os.path.exists(exe):
+        pytest.skip("example_driver not built")
+    c = vo.in_cases()[cid]
+    buf = vo.load_input(c["input"])
+    path = tmp_path / "in.vcf"
+    path.write_bytes(buf)
+    env = dict(os.environ, VGL_VCF_IN=str(path), VGL_SOURCE=str(c["source"]), VGL_EXPLODE=str(c["explode"]),
+               VGL_RM_INVAR=str(c["rm_invar_sites"]), VGL_BATCH="4")
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = [l.split("\t") for l in r.stdout.splitlines()]
+    assert [int(l[1]) - 1 for l in lines] == [p for p, _ in c["sites"]]
+    # the same sites through the Python host path with the driver's parameters
+    hdr = vcfinput.read_header(buf)
+    S = len(hdr.samples)
+    a = vargs.parse_args("--seed 42 -d 4 -e 0.01 -GL 1 -doUnobserved 1 -addGL 1 -addPL 1 -addFormatAD 1 -addInfoDP 1".split())
+    a.rm_invar_sites = c["rm_invar_sites"]
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=4, n_slots=2))
+    ps = ctx.parser(1 << 16, 16)
+    k = 0
+    for run, b in vcfinput.simulate_vcf_text(ctx, ps, buf[hdr.body_offset:], gt_source=c["source"], explode=c["explode"],
+                                             contigs=hdr.contigs):
+        for i in range(b.n_sites):
+            o, l = b.site(i), lines[k]
+            k += 1
+            if o["skip_code"] != 0:
+                assert l[2].startswith("skipped(%d)" % o["skip_code"])
+                continue
+            assert l[3] == "DP=%d" % o["info_dp"]
+            A = o["n_alleles"]
+            for s in range(S):
+                dp, ad = l[6 + s].split(":")
+                assert int(dp) == o["fmt_dp"][s]
+                assert [int(x) for x in ad.split(",")] == o["fmt_ad"].reshape(S, A)[s].tolist()
+    assert k == len(lines)
     ps.close()
     ctx.close()

@@ -1,7 +1,6 @@
 // Input path (include/vgl.h "Input path"): VCF text records -> packed true genotypes.
 //
-//   k_vcf_lines   one pass over the text: positions of the line feeds (record index), chained scan with decoupled
-//                 look-back so the text is read once
+//   k_vcf_count / k_vcf_scan / k_vcf_index   positions of the line feeds = the record index
 //   k_vcf_gt      one warp per record: the nine fixed columns (POS, REF/ALT -> allele map, FORMAT -> GT index), then every
 //                 sample column's GT sub-field -> one packed byte; skip decision of --rm-invar-sites bits 1 / 2
 //   k_place_rows  genotype rows -> a slot's genotype matrix (drops skipped records, inserts -explode sites)
@@ -21,9 +20,12 @@ namespace vgl {
 
 namespace {
 
-constexpr int LINES_THREADS = 256;
-constexpr int LINES_BYTES_PER_THREAD = 32;
-constexpr int LINES_TILE = LINES_THREADS * LINES_BYTES_PER_THREAD; // 8 KiB of text per tile
+// record index: the text is cut into warp tiles of 4 KiB (8 x 16 bytes per lane, interleaved so that every load is coalesced)
+constexpr int WT_CHUNKS = 8;
+constexpr int WT_BYTES = WT_CHUNKS * 32 * 16;
+constexpr int IDX_WARPS = 8;          // warps per block of k_vcf_count / k_vcf_index
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_PER_THREAD = 16;   // consecutive tile counts per thread of k_vcf_scan
 
 // counters (device words, mirrored to pinned host memory after a parse)
 enum { C_NEWLINES = 0, C_TICKET = 1, C_NRECORDS = 2, C_NERRORS = 3, C_FIRSTERR = 4, C_NKEPT = 5, C_CONSUMED = 6, C_COUNT = 8 };
@@ -41,30 +43,62 @@ __device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4)
 }
 
 // ---- record index --------------------------------------------------------------------------------------------------
-// tile_state word: bits 63..62 = 0 not ready, 1 = tile aggregate, 2 = inclusive prefix; low 32 bits = count
-__global__ void __launch_bounds__(LINES_THREADS) k_vcf_lines(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles,
-                                                               uint32_t max_records, uint32_t* __restrict__ line_end,
-                                                               unsigned long long* tile_state, uint32_t* counters)
+// line_end[i] = byte offset of the i-th line feed.  Three small launches instead of one chained scan (a decoupled
+// look-back over ~7000 tiles that each take < 1 us to load spends its time waiting on predecessors: 120 us for 56 MB):
+//   k_vcf_count  line feeds per warp tile          (streams the text once from HBM)
+//   k_vcf_scan   exclusive scan of the tile counts (one block; 16 K tiles per pass)
+//   k_vcf_index  positions of the line feeds       (the text comes from L2 when it is smaller than L2)
+__device__ __forceinline__ void load_warp_tile(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t tile, int lane, uint32_t (&m)[WT_CHUNKS])
 {
-    __shared__ uint32_t s_tile, s_base, s_warp[LINES_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(&counters[C_TICKET], 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= n_tiles) return;
-        const uint32_t off = tile * (uint32_t)LINES_TILE + (uint32_t)tid * LINES_BYTES_PER_THREAD;
-        uint32_t m = 0;
-        if (off < n_bytes) { // the buffer is padded to a whole tile
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(text + off));
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(text + off + 16));
-            m = eq_mask16(a, 0x0A0A0A0Au) | (eq_mask16(b, 0x0A0A0A0Au) << 16);
+    const uint32_t base = tile * (uint32_t)WT_BYTES + (uint32_t)lane * 16u;
+#pragma unroll
+    for (int j = 0; j < WT_CHUNKS; ++j) {
+        const uint32_t off = base + (uint32_t)j * 512u;
+        uint32_t mm = 0;
+        if (off < n_bytes) { // the buffer is padded beyond n_bytes
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + off));
+            mm = eq_mask16(v, 0x0A0A0A0Au);
             const uint32_t left = n_bytes - off;
-            if (left < 32) m &= (1u << left) - 1u;
+            if (left < 16) mm &= (1u << left) - 1u;
         }
-        const uint32_t cnt = __popc(m);
-        uint32_t incl = cnt;
+        m[j] = mm;
+    }
+}
+
+__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_count(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles,
+                                                              uint32_t* __restrict__ tile_count)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp0 = blockIdx.x * IDX_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * IDX_WARPS;
+    for (uint32_t tile = warp0; tile < n_tiles; tile += n_warps) {
+        uint32_t m[WT_CHUNKS];
+        load_warp_tile(text, n_bytes, tile, lane, m);
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < WT_CHUNKS; ++j) c += __popc(m[j]);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) tile_count[tile] = c;
+    }
+}
+
+// in place: tile_count[t] becomes the number of line feeds before tile t; counters[C_NEWLINES] = total
+__global__ void __launch_bounds__(SCAN_THREADS) k_vcf_scan(uint32_t* __restrict__ tile_count, uint32_t n_tiles, uint32_t* counters)
+{
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += SCAN_THREADS * SCAN_PER_THREAD) {
+        const uint32_t i0 = base + (uint32_t)tid * SCAN_PER_THREAD;
+        uint32_t v[SCAN_PER_THREAD];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+            v[k] = i0 + k < n_tiles ? tile_count[i0 + k] : 0;
+            sum += v[k];
+        }
+        uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -74,36 +108,56 @@ __global__ void __launch_bounds__(LINES_THREADS) k_vcf_lines(const uint8_t* __re
         __syncthreads();
         uint32_t wbase = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < LINES_THREADS / 32; ++w) {
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
             const uint32_t c = s_warp[w];
             if (w < wid) wbase += c;
             total += c;
         }
-        if (tid == 0) {
-            uint32_t base = 0;
-            if (tile > 0) {
-                atomicExch(&tile_state[tile], (1ull << 62) | total);
-                for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
-                    unsigned long long w;
-                    do {
-                        w = atomicAdd(&tile_state[t], 0ull);
-                    } while ((w >> 62) == 0);
-                    base += (uint32_t)w;
-                    if ((w >> 62) == 2) break;
-                }
-            }
-            __threadfence();
-            atomicExch(&tile_state[tile], (2ull << 62) | (unsigned long long)(base + total));
-            s_base = base;
-            if (tile == n_tiles - 1) counters[C_NEWLINES] = base + total;
+        uint32_t run = s_carry + wbase + incl - sum;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+            if (i0 + k < n_tiles) tile_count[i0 + k] = run;
+            run += v[k];
         }
         __syncthreads();
-        uint32_t idx = s_base + wbase + incl - cnt;
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            if (idx < max_records) line_end[idx] = off + b;
-            ++idx;
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) counters[C_NEWLINES] = s_carry;
+}
+
+__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_index(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles,
+                                                              const uint32_t* __restrict__ tile_base, uint32_t max_records,
+                                                              uint32_t* __restrict__ line_end)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp0 = blockIdx.x * IDX_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * IDX_WARPS;
+    for (uint32_t tile = warp0; tile < n_tiles; tile += n_warps) {
+        uint32_t idx = tile_base[tile];
+        if (idx >= max_records) return; // tiles are visited in increasing order by every warp
+        uint32_t m[WT_CHUNKS];
+        load_warp_tile(text, n_bytes, tile, lane, m);
+#pragma unroll
+        for (int j = 0; j < WT_CHUNKS; ++j) {
+            const uint32_t any = __ballot_sync(0xffffffffu, m[j] != 0);
+            if (!any) continue;
+            const uint32_t cnt = __popc(m[j]);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            uint32_t k = idx + incl - cnt;
+            uint32_t mm = m[j];
+            const uint32_t off = tile * (uint32_t)WT_BYTES + (uint32_t)j * 512u + (uint32_t)lane * 16u;
+            while (mm) {
+                const int b = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (k < max_records) line_end[k] = off + b;
+                ++k;
+            }
+            idx += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
@@ -274,6 +328,76 @@ __device__ __forceinline__ Hdr parse_header(const uint8_t* __restrict__ text, co
     return h;
 }
 
+__constant__ uint32_t c_pow10[9] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u};
+
+// The common shape of a record: REF and ALT one character each, FORMAT exactly "GT", POS of 1..9 digits.  Same results as
+// parse_header(); anything else (and every defect) returns false and takes the general parser.  Warp-uniform.
+__device__ __forceinline__ bool fast_header(const uint8_t* __restrict__ text, const uint32_t* tab, int gt_source, int lane, Hdr& h)
+{
+    const uint32_t plen = tab[1] - tab[0] - 1;
+    if (tab[3] - tab[2] != 2 || tab[4] - tab[3] != 2 || tab[8] - tab[7] != 3 || plen - 1u > 8u) return false;
+    const uint32_t ref = text[tab[2] + 1], alt = text[tab[3] + 1], f0 = text[tab[7] + 1], f1 = text[tab[7] + 2];
+    const uint32_t c = (uint32_t)lane < plen ? (uint32_t)text[tab[0] + 1 + lane] - '0' : 0u; // one POS digit per lane
+    uint32_t cr, ca;
+    if (gt_source == VGL_SOURCE_BINARY) {
+        cr = ref - '0';
+        ca = alt - '0';
+        if (cr > 1u) cr = 0xE;
+        if (ca > 1u) ca = 0xE;
+    } else {
+        cr = ref == 'A' ? 0 : ref == 'C' ? 1 : ref == 'G' ? 2 : ref == 'T' ? 3 : 0xE;
+        ca = alt == 'A' ? 0 : alt == 'C' ? 1 : alt == 'G' ? 2 : alt == 'T' ? 3 : 0xE;
+    }
+    const bool no_alt = alt == '.';
+    const bool good = f0 == 'G' && f1 == 'T' && cr != 0xE && (no_alt || ca != 0xE) && c <= 9u;
+    if (!__all_sync(0xffffffffu, good)) return false;
+    const uint32_t v = __reduce_add_sync(0xffffffffu, (uint32_t)lane < plen ? c * c_pow10[plen - 1 - lane] : 0u);
+    h.pos = (long long)v - 1;
+    h.n_allele = no_alt ? 1 : 2;
+    h.amap = 0xEEEEEE00u | cr | ((no_alt ? 0xEu : ca) << 4);
+    h.gt_idx = 0;
+    h.st = 99;
+    return true;
+}
+
+// Sample columns of fixed width, "a|b" + tab, S times (tskit / msprime VCFs): four samples per lane and step, taken as aligned
+// words and validated with word compares; returns false (warp-uniform) if any column is not of that form -- the general parser
+// then redoes the line.  sum = this lane's share of the allele-index sum.
+__device__ __forceinline__ bool fixed_width_row(const uint8_t* __restrict__ text, uint32_t p0, int S, int lane, const Hdr& h, uint8_t* __restrict__ row,
+                                                int& sum)
+{
+    bool ok = true;
+    const uint32_t sh = (p0 & 3u) * 8u, nal = (uint32_t)h.n_allele, amap = h.amap;
+    const bool row_al = (reinterpret_cast<uintptr_t>(row) & 3u) == 0;
+    for (int s0 = lane * 4; s0 < S; s0 += 128) {
+        const uint32_t q = p0 + 4u * (uint32_t)s0;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(text + (q & ~3u));
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = sh ? __ldg(w + 4) : 0u;
+        const uint32_t x[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int s = s0 + k;
+            if (s >= S) break;
+            uint32_t xv = x[k];
+            if (s == S - 1) xv = (xv & 0x00FFFFFFu) | 0x09000000u; // the line end closes the last column
+            const uint32_t sep = xv & 0xFF00FF00u;
+            const uint32_t c0 = xv & 0xFFu, c2 = (xv >> 16) & 0xFFu;
+            const uint32_t d0 = c0 - '0', d1 = c2 - '0';
+            const bool m0 = c0 == '.', m1 = c2 == '.', v0 = d0 < nal, v1 = d1 < nal;
+            const uint32_t n0 = m0 ? 0xFu : (amap >> (4u * (d0 & 7u))) & 0xFu;
+            const uint32_t n1 = m1 ? 0xFu : (amap >> (4u * (d1 & 7u))) & 0xFu;
+            ok = ok && (sep == 0x09007C00u || sep == 0x09002F00u) && (m0 || v0) && (m1 || v1) && n0 != 4u && n1 != 4u;
+            sum += (v0 ? (int)d0 : 0) + (v1 ? (int)d1 : 0);
+            out |= (n0 | (n1 << 4)) << (8 * k);
+        }
+        if (row_al && s0 + 3 < S) *reinterpret_cast<uint32_t*>(row + s0) = out;
+        else
+            for (int k = 0; k < 4 && s0 + k < S; ++k) row[s0 + k] = (uint8_t)(out >> (8 * k));
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
 constexpr int GT_WARPS = 8;
 
 __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restrict__ text, uint32_t n_bytes, const uint32_t* __restrict__ line_end,
@@ -331,9 +455,18 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
                     ntab += total;
                     continue;
                 }
-                h = parse_header(text, tab, gt_source);
+                if (!fast_header(text, tab, gt_source, lane, h)) h = parse_header(text, tab, gt_source);
                 have_hdr = true;
                 __syncwarp();
+                const uint32_t p0 = tab[8] + 1;
+                if (h.st == 99 && h.gt_idx == 0 && le - p0 == 4u * (uint32_t)S - 1u) { // "a|b\t" x S ?
+                    int fsum = 0;
+                    if (fixed_width_row(text, p0, S, lane, h, row, fsum)) {
+                        asum = fsum;
+                        ntab = 8 + S;
+                        break;
+                    }
+                }
             }
             // sample columns: the tab with ordinal o >= 8 starts sample o - 8
             uint32_t m = tm;
@@ -471,8 +604,8 @@ int parser_create(int device, int S, int rm_invar, int n_sms, int64_t max_text, 
     ps->device = device, ps->S = S, ps->rm_invar = rm_invar & 3, ps->n_sms = n_sms;
     ps->max_records = max_records;
     ps->text_cap = (size_t)max_text;
-    const size_t padded = ((ps->text_cap + 1 + LINES_TILE - 1) / LINES_TILE) * LINES_TILE + 1024;
-    ps->max_tiles = (uint32_t)(padded / LINES_TILE);
+    const size_t padded = ((ps->text_cap + 1 + WT_BYTES - 1) / WT_BYTES) * WT_BYTES + 1024;
+    ps->max_tiles = (uint32_t)(padded / WT_BYTES);
 #define PCK(call)                                                             \
     do {                                                                      \
         cudaError_t e_ = (call);                                              \
@@ -491,7 +624,7 @@ int parser_create(int device, int S, int rm_invar, int n_sms, int64_t max_text, 
     PCK(cudaMalloc((void**)&ps->d_text, padded));
     PCK(cudaMemset(ps->d_text, 0, padded));
     PCK(cudaMalloc((void**)&ps->d_line_end, ((size_t)max_records + 1) * sizeof(uint32_t)));
-    PCK(cudaMalloc((void**)&ps->d_tile_state, (size_t)ps->max_tiles * sizeof(unsigned long long)));
+    PCK(cudaMalloc((void**)&ps->d_tile_count, (size_t)ps->max_tiles * sizeof(uint32_t)));
     PCK(cudaMalloc((void**)&ps->d_counters, C_COUNT * sizeof(uint32_t)));
     PCK(cudaHostAlloc((void**)&ps->h_counters, C_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
     PCK(cudaMalloc((void**)&ps->d_sites, (size_t)max_records * sizeof(vgl_in_site)));
@@ -511,7 +644,7 @@ void parser_destroy(vgl_parser* ps)
     cudaFreeHost(ps->h_text);
     cudaFree(ps->d_text);
     cudaFree(ps->d_line_end);
-    cudaFree(ps->d_tile_state);
+    cudaFree(ps->d_tile_count);
     cudaFree(ps->d_counters);
     cudaFreeHost(ps->h_counters);
     cudaFree(ps->d_sites);
@@ -577,16 +710,16 @@ extern "C" int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source,
         ps->d_text_bytes = n;
     }
     PCK(cudaEventRecord(ps->ev[1], st));
-    const uint32_t n_tiles = (uint32_t)((n + LINES_TILE - 1) / LINES_TILE);
-    PCK(cudaMemsetAsync(ps->d_tile_state, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
+    const uint32_t n_tiles = (uint32_t)((n + WT_BYTES - 1) / WT_BYTES);
     static const uint32_t init[C_COUNT] = {0, 0, 0, 0, 0xFFFFFFFFu, 0, 0, 0};
     PCK(cudaMemcpyAsync(ps->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
-    const uint32_t lines_grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ps->n_sms * 8);
-    k_vcf_lines<<<lines_grid, LINES_THREADS, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, (uint32_t)ps->max_records, ps->d_line_end, ps->d_tile_state,
-                                                     ps->d_counters);
+    const uint32_t idx_grid = (uint32_t)std::min<uint64_t>((n_tiles + IDX_WARPS - 1) / IDX_WARPS, (uint64_t)ps->n_sms * 8);
+    k_vcf_count<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, ps->d_tile_count);
+    k_vcf_scan<<<1, SCAN_THREADS, 0, st>>>(ps->d_tile_count, n_tiles, ps->d_counters);
+    k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, ps->d_tile_count, (uint32_t)ps->max_records, ps->d_line_end);
     k_vcf_gt<<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, ps->d_line_end, ps->S, gt_source, ps->rm_invar, (uint32_t)ps->max_records,
                                                      ps->d_sites, ps->d_rows, ps->d_counters);
-    ps->launches += 2;
+    ps->launches += 4;
     PCK(cudaGetLastError());
     PCK(cudaEventRecord(ps->ev[2], st));
     PCK(cudaMemcpyAsync(ps->h_counters, ps->d_counters, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -177,7 +177,7 @@ struct vgl_parser {
     bool placed = false;
     uint8_t *h_text = nullptr, *d_text = nullptr, *d_rows = nullptr;
     uint32_t *d_line_end = nullptr, *d_counters = nullptr, *h_counters = nullptr;
-    unsigned long long* d_tile_state = nullptr;
+    uint32_t* d_tile_count = nullptr;
     vgl_in_site *d_sites = nullptr, *h_sites = nullptr;
     int32_t* d_row_map = nullptr;
     int64_t launches = 0;

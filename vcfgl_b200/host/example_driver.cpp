@@ -26,6 +26,32 @@ int main(int argc, char** argv)
     p.max_batch_sites = 4;
     p.n_slots = 2;
     p.host_output = getenv("VGL_NARROW") ? VGL_HOST_NARROW : VGL_HOST_I32; // same records either way
+    if (const char* vcf = getenv("VGL_VCF_IN")) { // input path: VCF text file -> device parser -> simulation, one line per site
+        FILE* f = fopen(vcf, "rb");
+        if (!f) { perror(vcf); return 1; }
+        p.n_samples = 0; // from the #CHROM line
+        p.max_batch_sites = getenv("VGL_BATCH") ? atoi(getenv("VGL_BATCH")) : 4;
+        p.rm_invar_sites = getenv("VGL_RM_INVAR") ? atoi(getenv("VGL_RM_INVAR")) : 0;
+        const int source = getenv("VGL_SOURCE") ? atoi(getenv("VGL_SOURCE")) : 0, explode = getenv("VGL_EXPLODE") ? atoi(getenv("VGL_EXPLODE")) : 0;
+        try {
+            vgl::VcfTextSimulator sim(p, source, explode, [&](const vgl::SimRecordView& r, const vgl::VcfTextSimulator::Site& st) {
+                if (r.ret < 0) { printf("%s\t%ld\tskipped(%d)\n", st.contig.c_str(), (long)st.pos + 1, r.ret); return; }
+                printf("%s\t%ld\t%s\tDP=%d\trec=%ld\tDP:AD", st.contig.c_str(), (long)st.pos + 1, r.alleles.c_str(), r.info_dp_arr[0], (long)st.record);
+                for (int s = 0; s < r.nSamples; ++s) {
+                    printf("\t%d:", r.fmt_dp_arr[s]);
+                    for (int a = 0; a < r.nAlleles; ++a) printf("%s%d", a ? "," : "", r.fmt_ad_arr[s * r.nAlleles + a]);
+                }
+                printf("\n");
+            });
+            sim.run(f);
+            fclose(f);
+            fprintf(stderr, "sites simulated: %ld, input-side skips: %ld\n", (long)sim.n_sites(), (long)sim.n_skipped_input());
+            return 0;
+        } catch (const vgl::Error& e) {
+            fprintf(stderr, "vgl error %d: %s\n", e.status, e.what());
+            return e.status == VGL_ENODEV ? 3 : 1;
+        }
+    }
     if (const char* path = getenv("VGL_BCF_OUT")) { // VGL_HOST_BCF: write an uncompressed BCF file, records serialised on the device
         try {
             std::string hdr = "##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\",IDX=0>\n##contig=<ID=1,length=1000,IDX=0>\n";

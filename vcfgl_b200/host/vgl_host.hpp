@@ -16,7 +16,11 @@
 
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -110,6 +114,26 @@ public:
         pending_[cur_].users.push_back(user);
         if (++fill_ == prm_.max_batch_sites) submit_current();
     }
+
+    // Input path (include/vgl.h): a whole batch whose genotypes were parsed on the device by vgl_parse_vcf().  Site k takes the
+    // row of parsed record row_map[k], or fill_gt in every sample when row_map[k] < 0 (an -explode 1 site).  Not to be mixed
+    // with push_site() inside one batch: a partially filled host batch is submitted first.
+    void push_device_sites(vgl_parser* ps, const int32_t* row_map, int32_t n, uint8_t fill_gt, void* const* users = nullptr)
+    {
+        if (fill_ > 0) submit_current();
+        check(vgl_place_rows(ctx_, cur_, ps, row_map, 0, n, fill_gt), "vgl_place_rows");
+        Pending& p = pending_[cur_];
+        p.users.assign((size_t)n, nullptr);
+        if (users) p.users.assign(users, users + n);
+        p.first = next_site_;
+        check(vgl_submit(ctx_, cur_, next_site_, n, nullptr, VGL_SUBMIT_GT_ON_DEVICE), "vgl_submit");
+        p.in_flight = true;
+        next_site_ += n;
+        cur_ = (cur_ + 1) % prm_.n_slots;
+        open_slot();
+    }
+    vgl_ctx* context() { return ctx_; }
+    const vgl_params& params() const { return prm_; }
 
     // end of input: run the partial batch and deliver everything outstanding
     void finish()
@@ -343,6 +367,213 @@ private:
     int cur_ = 0;
     int32_t fill_ = 0;
     int64_t next_site_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Input path: VCF text in, one callback per simulated site out -- the reference's main_simulate_record_values()
+// (vcfgl.cpp:1469-1620) with the per-record work (vcf_parse, bcf_get_genotypes, check_rec_alleles) done on the device.
+//
+//   reference                                            here
+//   ---------                                            ----
+//   bcf_hdr_read: samples, ##contig lengths              VcfTextSimulator::read_header()
+//   bcf_read + check_rec_alleles per record              vgl_parse_vcf() per chunk of text (k_vcf_lines, k_vcf_gt)
+//   -explode 1 blank records (vcfgl.cpp:1489-1538)       row_map entries < 0 (vgl_place_rows fills REF|REF)
+//   skip codes -1 / -2 (--rm-invar-sites 1|2)            vgl_in_site::skip_code, such records never become sites
+//   ERROR()/ASSERT() on a malformed record               vgl::Error(VGL_EINVAL) naming the record and the vgl_in_status
+class VcfTextSimulator {
+public:
+    struct Site { // what the callback gets besides the tags
+        std::string contig;
+        int64_t pos = 0;     // 0-based
+        int64_t record = -1; // >= 0: n-th record of the input; -1: -explode site
+    };
+    using Callback = std::function<void(const SimRecordView&, const Site&)>;
+
+    // params.n_samples may be 0: it is taken from the #CHROM line
+    VcfTextSimulator(vgl_params params, int gt_source, int explode, Callback cb)
+        : prm_(params), source_(gt_source), explode_(explode), cb_(std::move(cb))
+    {
+    }
+    ~VcfTextSimulator()
+    {
+        if (ps_) vgl_parser_destroy(ps_);
+    }
+    VcfTextSimulator(const VcfTextSimulator&) = delete;
+    VcfTextSimulator& operator=(const VcfTextSimulator&) = delete;
+
+    int64_t n_sites() const { return n_sites_; }
+    int64_t n_skipped_input() const { return n_skipped_; }
+    const std::vector<std::string>& samples() const { return samples_; }
+
+    void run(FILE* in)
+    {
+        const std::string carry = read_header(in);
+        if (prm_.n_samples == 0) prm_.n_samples = (int32_t)samples_.size();
+        if ((size_t)prm_.n_samples != samples_.size()) throw Error(VGL_EINVAL, "n_samples does not match the #CHROM line");
+        BatchSimulator sim(prm_, [&](const SimRecordView& v) { cb_(v, *static_cast<const Site*>(v.user)); });
+        const int32_t cap = sim.params().max_batch_sites;
+        const int64_t text_cap = (int64_t)cap * (4 * (int64_t)prm_.n_samples + 64) + (1 << 16);
+        int rc = vgl_parser_create(sim.context(), text_cap, cap, &ps_);
+        if (rc != VGL_OK) throw Error(rc, std::string("vgl_parser_create: ") + vgl_last_error(sim.context()));
+        uint8_t* text = nullptr;
+        int64_t tcap = 0;
+        vgl_parser_text_buffer(ps_, &text, &tcap);
+        // Site records of the batches in flight: a batch's entries must outlive its delivery, which happens at the
+        // latest when its slot comes round again (n_slots submissions later)
+        ring_.assign((size_t)sim.params().n_slots + 1, std::vector<Site>());
+        ring_at_ = 0;
+        size_t have = carry.size();
+        if ((int64_t)have > tcap) throw Error(VGL_EINVAL, "header tail larger than the text buffer");
+        memcpy(text, carry.data(), have);
+        bool eof = false;
+        int64_t n_records_total = 0;
+        int last_acgt0 = -1;
+        for (;;) {
+            if (!eof && (int64_t)have < tcap) {
+                const size_t got = fread(text + have, 1, (size_t)tcap - have, in);
+                have += got;
+                if (got == 0) eof = true;
+            }
+            if (have == 0) break;
+            vgl_parse_out po;
+            rc = vgl_parse_vcf(ps_, (int64_t)have, source_, eof ? VGL_PARSE_FINAL : 0, &po);
+            if (rc != VGL_OK) throw Error(rc, "vgl_parse_vcf failed");
+            if (po.n_errors) {
+                const vgl_in_site& b = po.sites[po.first_error_record];
+                throw Error(VGL_EINVAL, "malformed record at position " + std::to_string(b.pos + 1) + " (vgl_in_status " +
+                                            std::to_string(b.status) + "): " +
+                                            std::string((const char*)text + b.line_off, std::min<size_t>(b.line_len, 80)));
+            }
+            if (po.n_records == 0) {
+                if ((int64_t)have == tcap) throw Error(VGL_EINVAL, "a record does not fit the text buffer");
+                if (eof) break;
+                continue;
+            }
+            // the sites of this chunk (vcfgl.cpp:1479-1565), submitted batch by batch
+            begin_batch(cap);
+            for (int32_t i = 0; i < po.n_records; ++i) {
+                const vgl_in_site& r = po.sites[i];
+                const char* line = (const char*)text + r.line_off;
+                const char* tab = (const char*)memchr(line, '\t', r.line_len);
+                const size_t clen = tab ? (size_t)(tab - line) : r.line_len;
+                if (contig_.size() != clen || memcmp(contig_.data(), line, clen) != 0) { // contig change (vcfgl.cpp:1484-1488)
+                    contig_.assign(line, clen);
+                    n_in_contig_ = 0;
+                }
+                last_acgt0 = r.allele_acgt[0];
+                if (explode_) {
+                    if (r.pos < n_in_contig_) throw Error(VGL_EINVAL, "-explode 1 needs increasing positions within a contig");
+                    if (r.pos != n_in_contig_ && fill_acgt_ < 0) fill_acgt_ = r.allele_acgt[0]; // explode_rec: blank copy of THIS record
+                    for (; n_in_contig_ < r.pos; ++n_in_contig_) {
+                        if (prm_.rm_invar_sites & 1) ++n_skipped_; // all hom-ref: check_rec_alleles returns -1
+                        else add_site(sim, cap, n_in_contig_, -1, -1);
+                    }
+                }
+                if (r.skip_code != 0) ++n_skipped_;
+                else add_site(sim, cap, r.pos, i, n_records_total + i);
+                ++n_in_contig_;
+            }
+            flush(sim, cap); // the next parse overwrites the rows
+            n_records_total += po.n_records;
+            const size_t used = (size_t)po.bytes_consumed;
+            memmove(text, text + used, have - used);
+            have -= used;
+        }
+        if (explode_ && !contig_.empty()) { // to the end of the LAST contig (vcfgl.cpp:1567-1611)
+            const auto it = contigs_.find(contig_);
+            const int64_t size = it == contigs_.end() ? 0 : it->second;
+            if (fill_acgt_ < 0) fill_acgt_ = last_acgt0;
+            if (prm_.rm_invar_sites & 1) {
+                n_skipped_ += std::max<int64_t>(0, size - n_in_contig_);
+            } else {
+                begin_batch(cap);
+                for (; n_in_contig_ < size; ++n_in_contig_) add_site(sim, cap, n_in_contig_, -1, -1);
+                flush(sim, cap);
+            }
+        }
+        sim.finish();
+        vgl_parser_destroy(ps_);
+        ps_ = nullptr;
+    }
+
+private:
+    void begin_batch(int32_t cap)
+    {
+        map_.clear();
+        ring_[ring_at_].clear();
+        ring_[ring_at_].reserve((size_t)cap); // pointers into it are handed out: no reallocation afterwards
+    }
+    void add_site(BatchSimulator& sim, int32_t cap, int64_t pos, int32_t src, int64_t rec_no)
+    {
+        Site st;
+        st.contig = contig_;
+        st.pos = pos;
+        st.record = rec_no;
+        ring_[ring_at_].push_back(std::move(st));
+        map_.push_back(src);
+        if ((int32_t)map_.size() == cap) flush(sim, cap);
+    }
+    void flush(BatchSimulator& sim, int32_t cap)
+    {
+        if (map_.empty()) return;
+        std::vector<Site>& sites = ring_[ring_at_];
+        std::vector<void*> users(map_.size());
+        for (size_t k = 0; k < map_.size(); ++k) users[k] = &sites[k];
+        const uint8_t fill = fill_acgt_ >= 0 ? (uint8_t)(fill_acgt_ * 0x11) : 0;
+        sim.push_device_sites(ps_, map_.data(), (int32_t)map_.size(), fill, users.data());
+        n_sites_ += (int64_t)map_.size();
+        ring_at_ = (ring_at_ + 1) % ring_.size();
+        begin_batch(cap);
+    }
+
+    // header lines up to #CHROM; returns the bytes already read past it
+    std::string read_header(FILE* in)
+    {
+        std::string buf, line;
+        std::vector<char> tmp(1 << 16);
+        size_t off = 0;
+        for (;;) {
+            size_t nl;
+            while ((nl = buf.find('\n', off)) == std::string::npos) {
+                const size_t got = fread(tmp.data(), 1, tmp.size(), in);
+                if (got == 0) throw Error(VGL_EINVAL, "no #CHROM line in the VCF header");
+                buf.append(tmp.data(), got);
+            }
+            line.assign(buf, off, nl - off);
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            off = nl + 1;
+            if (line.rfind("##contig=<", 0) == 0) {
+                const size_t id = line.find("ID="), len = line.find("length=");
+                if (id != std::string::npos) {
+                    const size_t e = line.find_first_of(",>", id);
+                    contigs_[line.substr(id + 3, e - id - 3)] = len == std::string::npos ? 0 : atoll(line.c_str() + len + 7);
+                }
+            } else if (line.rfind("#CHROM", 0) == 0) {
+                size_t p = 0;
+                for (int col = 0; p != std::string::npos; ++col) {
+                    const size_t e = line.find('\t', p);
+                    if (col >= 9) samples_.push_back(line.substr(p, e == std::string::npos ? e : e - p));
+                    p = e == std::string::npos ? e : e + 1;
+                }
+                if (samples_.empty()) throw Error(VGL_EINVAL, "the VCF has no sample columns");
+                return buf.substr(off);
+            } else if (line.rfind("##", 0) != 0)
+                throw Error(VGL_EINVAL, "record before the #CHROM line");
+        }
+    }
+
+    vgl_params prm_;
+    int source_, explode_;
+    Callback cb_;
+    vgl_parser* ps_ = nullptr;
+    std::vector<std::string> samples_;
+    std::map<std::string, int64_t> contigs_;
+    std::string contig_;
+    int64_t n_in_contig_ = 0, n_sites_ = 0, n_skipped_ = 0;
+    int fill_acgt_ = -1;
+    std::vector<std::vector<Site>> ring_;
+    size_t ring_at_ = 0;
+    std::vector<int32_t> map_;
 };
 
 } // namespace vgl
