@@ -1,7 +1,9 @@
 // Input path (include/vgl.h "Input path"): VCF text records -> packed true genotypes.
 //
 //   k_vcf_count / k_vcf_scan / k_vcf_index   positions of the line feeds = the record index
-//   k_vcf_gt      one warp per record: the nine fixed columns (POS, REF/ALT -> allele map, FORMAT -> GT index), then every
+//   k_vcf_hdr     one thread per record: the nine fixed columns of records whose sample columns can be fixed-width ("a|b" + tab)
+//   k_vcf_cells   one thread per four samples of those records: word compares, a 4-entry byte table, aligned 32-bit stores
+//   k_vcf_gt      every other record, one warp per record: the nine fixed columns (POS, REF/ALT -> allele map, FORMAT -> GT index), then every
 //                 sample column's GT sub-field -> one packed byte; skip decision of --rm-invar-sites bits 1 / 2
 //   k_place_rows  genotype rows -> a slot's genotype matrix (drops skipped records, inserts -explode sites)
 //
@@ -360,49 +362,157 @@ __device__ __forceinline__ bool fast_header(const uint8_t* __restrict__ text, co
     return true;
 }
 
-// Sample columns of fixed width, "a|b" + tab, S times (tskit / msprime VCFs): four samples per lane and step, taken as aligned
-// words and validated with word compares; returns false (warp-uniform) if any column is not of that form -- the general parser
-// then redoes the line.  sum = this lane's share of the allele-index sum.
-__device__ __forceinline__ bool fixed_width_row(const uint8_t* __restrict__ text, uint32_t p0, int S, int lane, const Hdr& h, uint8_t* __restrict__ row,
-                                                int& sum)
+// ---- msprime / tskit shaped records: FORMAT "GT", every sample column "a|b" + tab -----------------------------------------
+// Per record a 16-byte descriptor, written by k_vcf_hdr (one THREAD per record: the nine fixed columns are ~40 bytes, a warp
+// per record spends most of its issue slots idle on them), consumed by k_vcf_cells (one thread per four samples, records
+// back to back: no per-record cost at all) and by k_vcf_gt, which finishes such records and parses every other one.
+struct __align__(16) RecMeta {
+    uint32_t p0;    // text offset of the first sample column
+    uint32_t lut;   // FLAG_BIALLELIC: byte i = packed genotype of haplotypes (i & 1, i >> 1); else the allele nibble map
+    uint32_t flags; // FLAG_*, n_allele << 8
+    int32_t asum;   // allele-index sum, accumulated by k_vcf_cells
+};
+enum { FLAG_FIXED = 1,     // candidate: header clean, GT first, sample columns 4 * S - 1 bytes
+       FLAG_FAILED = 2,    // some column was not "a|b": the general parser redoes the record
+       FLAG_BIALLELIC = 4 };
+
+__device__ __forceinline__ uint32_t slow_cell(uint32_t xv, uint32_t nal, uint32_t amap, bool& ok, int& sum)
 {
-    bool ok = true;
-    const uint32_t sh = (p0 & 3u) * 8u, nal = (uint32_t)h.n_allele, amap = h.amap;
-    const bool row_al = (reinterpret_cast<uintptr_t>(row) & 3u) == 0;
-    for (int s0 = lane * 4; s0 < S; s0 += 128) {
-        const uint32_t q = p0 + 4u * (uint32_t)s0;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(text + (q & ~3u));
-        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = sh ? __ldg(w + 4) : 0u;
-        const uint32_t x[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
-        uint32_t out = 0;
+    const uint32_t sep = xv & 0xFF00FF00u;
+    const uint32_t c0 = xv & 0xFFu, c2 = (xv >> 16) & 0xFFu;
+    const uint32_t d0 = c0 - '0', d1 = c2 - '0';
+    const bool m0 = c0 == '.', m1 = c2 == '.', v0 = d0 < nal, v1 = d1 < nal;
+    const uint32_t n0 = m0 ? 0xFu : (amap >> (4u * (d0 & 7u))) & 0xFu;
+    const uint32_t n1 = m1 ? 0xFu : (amap >> (4u * (d1 & 7u))) & 0xFu;
+    ok = ok && (sep == 0x09007C00u || sep == 0x09002F00u) && (m0 || v0) && (m1 || v1) && n0 < 4u + 12u * m0 && n1 < 4u + 12u * m1;
+    sum += (v0 ? (int)d0 : 0) + (v1 ? (int)d1 : 0);
+    return n0 | (n1 << 4);
+}
+
+__global__ void __launch_bounds__(128) k_vcf_hdr(const uint8_t* __restrict__ text, const uint32_t* __restrict__ line_end, int32_t S, int32_t gt_source,
+                                                 uint32_t max_records, const uint32_t* __restrict__ counters, RecMeta* __restrict__ meta,
+                                                 vgl_in_site* __restrict__ sites)
+{
+    const uint32_t n_rec = min(counters[C_NEWLINES], max_records);
+    for (uint32_t line = blockIdx.x * blockDim.x + threadIdx.x; line < n_rec; line += gridDim.x * blockDim.x) {
+        const uint32_t ls = line ? line_end[line - 1] + 1 : 0;
+        uint32_t le = line_end[line];
+        if (le > ls && text[le - 1] == '\r') --le;
+        RecMeta m;
+        m.p0 = 0, m.lut = 0, m.flags = 0, m.asum = 0;
+        // the sample columns of a candidate are 4 * S - 1 bytes: the ninth tab must sit right before them
+        const uint32_t body = 4u * (uint32_t)S - 1u;
+        if (le - ls > body + 16u && text[le - body - 1] == '\t') {
+            uint32_t tab[9];
+            int nt = 0;
+            const uint32_t p0 = le - body;
+            for (uint32_t p = ls; p < p0 && nt < 9; ++p)
+                if (text[p] == '\t') tab[nt++] = p;
+            if (nt == 9 && tab[8] == p0 - 1) {
+                const Hdr h = parse_header(text, tab, gt_source);
+                bool sym = false;
+                for (int i = 0; i < 5; ++i) sym = sym || (i < h.n_allele && ((h.amap >> (4 * i)) & 0xFu) == 4u);
+                if (h.st == 99 && h.gt_idx == 0 && !sym) {
+                    m.p0 = p0;
+                    m.flags = FLAG_FIXED | ((uint32_t)h.n_allele << 8);
+                    if (h.n_allele <= 2) {
+                        const uint32_t r = h.amap & 0xFu, a = (h.amap >> 4) & 0xFu;
+                        m.lut = (r | (r << 4)) | ((a | (r << 4)) << 8) | ((r | (a << 4)) << 16) | ((a | (a << 4)) << 24);
+                        m.flags |= FLAG_BIALLELIC;
+                    } else m.lut = h.amap;
+                    vgl_in_site o;
+                    o.status = VGL_IN_OK, o.skip_code = 0, o.pos = h.pos, o.allele_sum = 0, o.line_off = ls, o.line_len = le - ls;
+                    o.n_allele = h.n_allele;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int s = s0 + k;
-            if (s >= S) break;
-            uint32_t xv = x[k];
-            if (s == S - 1) xv = (xv & 0x00FFFFFFu) | 0x09000000u; // the line end closes the last column
-            const uint32_t sep = xv & 0xFF00FF00u;
-            const uint32_t c0 = xv & 0xFFu, c2 = (xv >> 16) & 0xFFu;
-            const uint32_t d0 = c0 - '0', d1 = c2 - '0';
-            const bool m0 = c0 == '.', m1 = c2 == '.', v0 = d0 < nal, v1 = d1 < nal;
-            const uint32_t n0 = m0 ? 0xFu : (amap >> (4u * (d0 & 7u))) & 0xFu;
-            const uint32_t n1 = m1 ? 0xFu : (amap >> (4u * (d1 & 7u))) & 0xFu;
-            ok = ok && (sep == 0x09007C00u || sep == 0x09002F00u) && (m0 || v0) && (m1 || v1) && n0 != 4u && n1 != 4u;
-            sum += (v0 ? (int)d0 : 0) + (v1 ? (int)d1 : 0);
-            out |= (n0 | (n1 << 4)) << (8 * k);
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t c = i < 5 && i < h.n_allele ? (h.amap >> (4 * i)) & 0xFu : 0xEu;
+                        o.allele_acgt[i] = c == 0xEu ? -1 : (int8_t)c;
+                    }
+                    o.id_off = tab[1] + 1 - ls, o.fmt_off = tab[7] + 1 - ls, o.samples_off = p0 - ls, o._pad = 0;
+                    sites[line] = o;
+                }
+            }
         }
-        if (row_al && s0 + 3 < S) *reinterpret_cast<uint32_t*>(row + s0) = out;
-        else
-            for (int k = 0; k < 4 && s0 + k < S; ++k) row[s0 + k] = (uint8_t)(out >> (8 * k));
+        meta[line] = m;
     }
-    return __all_sync(0xffffffffu, ok);
+}
+
+// one thread per four samples of a candidate record; groups of all records laid end to end (G = ceil(S / 4) per record)
+__global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ text, int32_t S, uint32_t G, uint32_t magic, uint32_t max_records,
+                                                   const uint32_t* __restrict__ counters, RecMeta* meta, uint8_t* __restrict__ rows)
+{
+    const uint32_t n_rec = min(counters[C_NEWLINES], max_records);
+    const unsigned long long total = (unsigned long long)n_rec * G;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warp0 = ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32ull;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const bool rows_al = (S & 3) == 0;
+    for (unsigned long long g0 = warp0; g0 < total; g0 += stride) {
+        const uint32_t line0 = (uint32_t)(g0 / G);                      // warp-uniform
+        const uint32_t r = (uint32_t)(g0 - (unsigned long long)line0 * G) + (uint32_t)lane;
+        const uint32_t dl = G == 1 ? r : __umulhi(r, magic);           // r / G, exact for r < G + 32
+        const uint32_t line = line0 + dl, g = r - dl * G;
+        const bool valid = g0 + (unsigned long long)lane < total;
+        RecMeta m;
+        m.p0 = 0, m.lut = 0, m.flags = 0, m.asum = 0;
+        if (valid) m = *reinterpret_cast<const RecMeta*>(__builtin_assume_aligned(&meta[line], 16));
+        const bool fixed = valid && (m.flags & FLAG_FIXED);
+        bool ok = true;
+        int sum = 0;
+        if (fixed) {
+            const int s0 = 4 * (int)g;
+            const uint32_t q = m.p0 + 16u * g, sh = (q & 3u) * 8u;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(text + (q & ~3u));
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = sh ? __ldg(w + 4) : 0u;
+            const uint32_t x[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+            const int n = min(4, S - s0);
+            const int last = S - 1 - s0; // the line end closes the last column
+            const uint32_t nal = m.flags >> 8;
+            uint32_t out = 0;
+            if (m.flags & FLAG_BIALLELIC) {
+                const uint32_t dmask = nal == 2 ? 0xFFFEFFFEu : 0xFFFFFFFFu;
+                const uint32_t amap = 0xEEEEEE00u | (m.lut & 0xFu) | (((m.lut >> 8) & 0xFu) << 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k >= n) break;
+                    const uint32_t xv = k == last ? (x[k] & 0x00FFFFFFu) | 0x09000000u : x[k];
+                    const uint32_t sep = xv & 0xFF00FF00u, d = (xv & 0x00FF00FFu) - 0x00300030u;
+                    uint32_t byte;
+                    if ((sep == 0x09007C00u || sep == 0x09002F00u) && (d & dmask) == 0) {
+                        byte = __byte_perm(m.lut, 0, (d | (d >> 15)) & 3u) & 0xFFu;
+                        sum += __popc(d);
+                    } else byte = slow_cell(xv, nal, amap, ok, sum);
+                    out |= byte << (8 * k);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k >= n) break;
+                    out |= slow_cell(k == last ? (x[k] & 0x00FFFFFFu) | 0x09000000u : x[k], nal, m.lut, ok, sum) << (8 * k);
+                }
+            }
+            uint8_t* dst = rows + (size_t)line * S + s0;
+            if (rows_al) *reinterpret_cast<uint32_t*>(dst) = out;
+            else
+                for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(out >> (8 * k));
+        }
+        // per-record totals: the lanes of one record are contiguous
+        const uint32_t grp = __match_any_sync(0xffffffffu, fixed ? line : 0xFFFFFFFFu);
+        const int tot = __reduce_add_sync(grp, sum);
+        const uint32_t all_ok = __reduce_and_sync(grp, ok ? 1u : 0u);
+        if (fixed && lane == __ffs(grp) - 1) {
+            if (tot) atomicAdd(&meta[line].asum, tot);
+            if (!all_ok) atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED);
+        }
+    }
 }
 
 constexpr int GT_WARPS = 8;
 
 __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restrict__ text, uint32_t n_bytes, const uint32_t* __restrict__ line_end,
                                                          int32_t S, int32_t gt_source, int32_t rm_invar, uint32_t max_records,
-                                                         vgl_in_site* __restrict__ sites, uint8_t* __restrict__ rows, uint32_t* counters)
+                                                         vgl_in_site* __restrict__ sites, uint8_t* __restrict__ rows, uint32_t* counters,
+                                                         const RecMeta* __restrict__ meta)
 {
     __shared__ uint32_t s_tab[GT_WARPS][12];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -413,7 +523,25 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
         counters[C_CONSUMED] = n_rec ? line_end[n_rec - 1] + 1 : 0;
     }
     uint32_t* tab = s_tab[wid];
+    uint32_t n_kept = 0, n_err = 0, first_err = 0xFFFFFFFFu; // lane 0's tallies, posted once per warp
     for (uint32_t line = warp0; line < n_rec; line += n_warps) {
+        {   // a fixed-width record that k_vcf_cells converted completely: only the totals are left to do
+            const RecMeta m = meta[line];
+            if ((m.flags & (FLAG_FIXED | FLAG_FAILED)) == FLAG_FIXED) {
+                if (lane == 0) {
+                    int skip = 0;
+                    const int nal = (int)(m.flags >> 8);
+                    if ((rm_invar & 1) && m.asum == 0) skip = -1;
+                    else if (rm_invar & 2)
+                        for (int al = 1; al < nal; ++al)
+                            if ((long long)al * S * 2 == (long long)m.asum) skip = -2;
+                    sites[line].skip_code = skip;
+                    sites[line].allele_sum = m.asum;
+                    n_kept += skip == 0;
+                }
+                continue;
+            }
+        }
         const uint32_t ls = line ? line_end[line - 1] + 1 : 0;
         uint32_t le = line_end[line];
         if (le > ls && text[le - 1] == '\r') --le; // KS_SEP_LINE strips the CR of a CRLF
@@ -458,15 +586,6 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
                 if (!fast_header(text, tab, gt_source, lane, h)) h = parse_header(text, tab, gt_source);
                 have_hdr = true;
                 __syncwarp();
-                const uint32_t p0 = tab[8] + 1;
-                if (h.st == 99 && h.gt_idx == 0 && le - p0 == 4u * (uint32_t)S - 1u) { // "a|b\t" x S ?
-                    int fsum = 0;
-                    if (fixed_width_row(text, p0, S, lane, h, row, fsum)) {
-                        asum = fsum;
-                        ntab = 8 + S;
-                        break;
-                    }
-                }
             }
             // sample columns: the tab with ordinal o >= 8 starts sample o - 8
             uint32_t m = tm;
@@ -550,11 +669,18 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
             o._pad = 0;
             sites[line] = o;
             if (o.status != VGL_IN_OK) {
-                atomicAdd(&counters[C_NERRORS], 1u);
-                atomicMin(&counters[C_FIRSTERR], line);
-            } else if (o.skip_code == 0) atomicAdd(&counters[C_NKEPT], 1u);
+                ++n_err;
+                first_err = min(first_err, line);
+            } else if (o.skip_code == 0) ++n_kept;
         }
         __syncwarp();
+    }
+    if (lane == 0) {
+        if (n_kept) atomicAdd(&counters[C_NKEPT], n_kept);
+        if (n_err) {
+            atomicAdd(&counters[C_NERRORS], n_err);
+            atomicMin(&counters[C_FIRSTERR], first_err);
+        }
     }
 }
 
@@ -631,6 +757,7 @@ int parser_create(int device, int S, int rm_invar, int n_sms, int64_t max_text, 
     PCK(cudaHostAlloc((void**)&ps->h_sites, (size_t)max_records * sizeof(vgl_in_site), cudaHostAllocDefault));
     PCK(cudaMalloc((void**)&ps->d_rows, (size_t)max_records * S + 16));
     PCK(cudaMalloc((void**)&ps->d_row_map, (size_t)max_records * sizeof(int32_t)));
+    PCK(cudaMalloc((void**)&ps->d_meta, (size_t)max_records * sizeof(RecMeta)));
 #undef PCK
     *out = ps;
     return VGL_OK;
@@ -651,6 +778,7 @@ void parser_destroy(vgl_parser* ps)
     cudaFreeHost(ps->h_sites);
     cudaFree(ps->d_rows);
     cudaFree(ps->d_row_map);
+    cudaFree(ps->d_meta);
     for (auto& e : ps->ev)
         if (e) cudaEventDestroy(e);
     if (ps->ev_done) cudaEventDestroy(ps->ev_done);
@@ -717,9 +845,18 @@ extern "C" int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source,
     k_vcf_count<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, ps->d_tile_count);
     k_vcf_scan<<<1, SCAN_THREADS, 0, st>>>(ps->d_tile_count, n_tiles, ps->d_counters);
     k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, ps->d_tile_count, (uint32_t)ps->max_records, ps->d_line_end);
+    RecMeta* meta = reinterpret_cast<RecMeta*>(ps->d_meta);
+    k_vcf_hdr<<<ps->n_sms * 8, 128, 0, st>>>(ps->d_text, ps->d_line_end, ps->S, gt_source, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_sites);
+    {   // k_vcf_cells: one thread per four samples of every record that can be fixed-width (each is at least 4 * S bytes long)
+        const uint32_t G = ((uint32_t)ps->S + 3u) / 4u;
+        const uint32_t magic = G > 1 ? (uint32_t)((0x100000000ull + G - 1) / G) : 0u;
+        const uint64_t max_groups = std::min<uint64_t>((uint64_t)ps->max_records, n / (4ull * (uint64_t)ps->S) + 1) * G;
+        const uint32_t cells_grid = (uint32_t)std::min<uint64_t>((max_groups + 255) / 256, (uint64_t)ps->n_sms * 16);
+        k_vcf_cells<<<std::max(cells_grid, 1u), 256, 0, st>>>(ps->d_text, ps->S, G, magic, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_rows);
+    }
     k_vcf_gt<<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, ps->d_line_end, ps->S, gt_source, ps->rm_invar, (uint32_t)ps->max_records,
-                                                     ps->d_sites, ps->d_rows, ps->d_counters);
-    ps->launches += 4;
+                                                     ps->d_sites, ps->d_rows, ps->d_counters, meta);
+    ps->launches += 6;
     PCK(cudaGetLastError());
     PCK(cudaEventRecord(ps->ev[2], st));
     PCK(cudaMemcpyAsync(ps->h_counters, ps->d_counters, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -180,6 +180,7 @@ struct vgl_parser {
     uint32_t* d_tile_count = nullptr;
     vgl_in_site *d_sites = nullptr, *h_sites = nullptr;
     int32_t* d_row_map = nullptr;
+    void* d_meta = nullptr; // RecMeta [max_records] (vcfin.cu)
     int64_t launches = 0;
     std::string err;
 };
