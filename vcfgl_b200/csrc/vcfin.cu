@@ -26,11 +26,9 @@ namespace {
 constexpr int WT_CHUNKS = 8;
 constexpr int WT_BYTES = WT_CHUNKS * 32 * 16;
 constexpr int IDX_WARPS = 8;          // warps per block of k_vcf_count / k_vcf_index
-constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_PER_THREAD = 16;   // consecutive tile counts per thread of k_vcf_scan
 
 // counters (device words, mirrored to pinned host memory after a parse)
-enum { C_NEWLINES = 0, C_TICKET = 1, C_NRECORDS = 2, C_NERRORS = 3, C_FIRSTERR = 4, C_NKEPT = 5, C_CONSUMED = 6, C_COUNT = 8 };
+enum { C_NEWLINES = 0, C_NWORK = 1, C_NRECORDS = 2, C_NERRORS = 3, C_FIRSTERR = 4, C_NKEPT = 5, C_CONSUMED = 6, C_DONE = 7, C_COUNT = 8 };
 
 // bit i of the result = byte i of w equals c
 __device__ __forceinline__ uint32_t eq_nibble(uint32_t w, uint32_t c4)
@@ -45,11 +43,10 @@ __device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4)
 }
 
 // ---- record index --------------------------------------------------------------------------------------------------
-// line_end[i] = byte offset of the i-th line feed.  Three small launches instead of one chained scan (a decoupled
+// line_end[i] = byte offset of the i-th line feed.  Two launches instead of one chained scan (a decoupled
 // look-back over ~7000 tiles that each take < 1 us to load spends its time waiting on predecessors: 120 us for 56 MB):
-//   k_vcf_count  line feeds per warp tile          (streams the text once from HBM)
-//   k_vcf_scan   exclusive scan of the tile counts (one block; 16 K tiles per pass)
-//   k_vcf_index  positions of the line feeds       (the text comes from L2 when it is smaller than L2)
+//   k_vcf_count  line feeds per warp tile and per block (streams the text once from HBM); the last block scans the block totals
+//   k_vcf_index  positions of the line feeds (the text comes from L2 when it is smaller than L2)
 __device__ __forceinline__ void load_warp_tile(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t tile, int lane, uint32_t (&m)[WT_CHUNKS])
 {
     const uint32_t base = tile * (uint32_t)WT_BYTES + (uint32_t)lane * 16u;
@@ -67,12 +64,20 @@ __device__ __forceinline__ void load_warp_tile(const uint8_t* __restrict__ text,
     }
 }
 
-__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_count(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles,
-                                                              uint32_t* __restrict__ tile_count)
+// Block b owns the warp tiles [b * tpb, (b + 1) * tpb).  k_vcf_count leaves the line feeds of every warp tile in tile_count and
+// of every block in block_base; the last block to finish turns block_base into an exclusive prefix (at most MAX_IDX_BLOCKS
+// values: no separate scan launch) and posts the total.
+constexpr int MAX_IDX_BLOCKS = 2048;
+
+__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_count(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles, uint32_t tpb,
+                                                              uint32_t* __restrict__ tile_count, uint32_t* block_base, uint32_t* counters)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp0 = blockIdx.x * IDX_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * IDX_WARPS;
-    for (uint32_t tile = warp0; tile < n_tiles; tile += n_warps) {
+    __shared__ uint32_t s_part[IDX_WARPS];
+    __shared__ uint32_t s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t t0 = blockIdx.x * tpb, t1 = min(t0 + tpb, n_tiles);
+    uint32_t mine = 0;
+    for (uint32_t tile = t0 + wid; tile < t1; tile += IDX_WARPS) {
         uint32_t m[WT_CHUNKS];
         load_warp_tile(text, n_bytes, tile, lane, m);
         uint32_t c = 0;
@@ -80,63 +85,69 @@ __global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_count(const uint8_t* __r
         for (int j = 0; j < WT_CHUNKS; ++j) c += __popc(m[j]);
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0) tile_count[tile] = c;
+        mine += c;
     }
-}
-
-// in place: tile_count[t] becomes the number of line feeds before tile t; counters[C_NEWLINES] = total
-__global__ void __launch_bounds__(SCAN_THREADS) k_vcf_scan(uint32_t* __restrict__ tile_count, uint32_t n_tiles, uint32_t* counters)
-{
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    __shared__ uint32_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    if (lane == 0) s_part[wid] = mine;
     __syncthreads();
-    for (uint32_t base = 0; base < n_tiles; base += SCAN_THREADS * SCAN_PER_THREAD) {
-        const uint32_t i0 = base + (uint32_t)tid * SCAN_PER_THREAD;
-        uint32_t v[SCAN_PER_THREAD];
-        uint32_t sum = 0;
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
 #pragma unroll
-        for (int k = 0; k < SCAN_PER_THREAD; ++k) {
-            v[k] = i0 + k < n_tiles ? tile_count[i0 + k] : 0;
-            sum += v[k];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        uint32_t wbase = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-            const uint32_t c = s_warp[w];
-            if (w < wid) wbase += c;
-            total += c;
-        }
-        uint32_t run = s_carry + wbase + incl - sum;
-#pragma unroll
-        for (int k = 0; k < SCAN_PER_THREAD; ++k) {
-            if (i0 + k < n_tiles) tile_count[i0 + k] = run;
-            run += v[k];
-        }
-        __syncthreads();
-        if (tid == 0) s_carry += total;
-        __syncthreads();
+        for (int w = 0; w < IDX_WARPS; ++w) tot += s_part[w];
+        block_base[blockIdx.x] = tot;
+        __threadfence();
+        s_last = atomicAdd(&counters[C_DONE], 1u) == gridDim.x - 1;
     }
-    if (tid == 0) counters[C_NEWLINES] = s_carry;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // exclusive scan of gridDim.x <= MAX_IDX_BLOCKS block totals by this block's 256 threads (8 consecutive values each)
+    __shared__ uint32_t s_warp[IDX_WARPS];
+    constexpr int PER = MAX_IDX_BLOCKS / (IDX_WARPS * 32);
+    const uint32_t i0 = threadIdx.x * PER;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        v[k] = i0 + k < gridDim.x ? __ldcg(&block_base[i0 + k]) : 0u;
+        sum += v[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < IDX_WARPS; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < wid) wbase += c;
+        total += c;
+    }
+    uint32_t run = wbase + incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        if (i0 + k < gridDim.x) block_base[i0 + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 0) counters[C_NEWLINES] = total;
 }
 
-__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_index(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles,
-                                                              const uint32_t* __restrict__ tile_base, uint32_t max_records,
-                                                              uint32_t* __restrict__ line_end)
+__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_index(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles, uint32_t tpb,
+                                                              const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ block_base,
+                                                              uint32_t max_records, uint32_t* __restrict__ line_end)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp0 = blockIdx.x * IDX_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * IDX_WARPS;
-    for (uint32_t tile = warp0; tile < n_tiles; tile += n_warps) {
-        uint32_t idx = tile_base[tile];
-        if (idx >= max_records) return; // tiles are visited in increasing order by every warp
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t t0 = blockIdx.x * tpb, t1 = min(t0 + tpb, n_tiles);
+    const uint32_t bbase = block_base[blockIdx.x];
+    if (bbase >= max_records) return;
+    for (uint32_t tile = t0 + wid; tile < t1; tile += IDX_WARPS) {
+        // line feeds of this block's tiles before `tile`
+        uint32_t before = 0;
+        for (uint32_t t = t0 + lane; t < tile; t += 32) before += tile_count[t];
+        uint32_t idx = bbase + __reduce_add_sync(0xffffffffu, before);
+        if (idx >= max_records) return;
         uint32_t m[WT_CHUNKS];
         load_warp_tile(text, n_bytes, tile, lane, m);
 #pragma unroll
@@ -390,8 +401,8 @@ __device__ __forceinline__ uint32_t slow_cell(uint32_t xv, uint32_t nal, uint32_
 }
 
 __global__ void __launch_bounds__(128) k_vcf_hdr(const uint8_t* __restrict__ text, const uint32_t* __restrict__ line_end, int32_t S, int32_t gt_source,
-                                                 uint32_t max_records, const uint32_t* __restrict__ counters, RecMeta* __restrict__ meta,
-                                                 vgl_in_site* __restrict__ sites)
+                                                 uint32_t max_records, uint32_t* counters, RecMeta* __restrict__ meta,
+                                                 vgl_in_site* __restrict__ sites, uint32_t* __restrict__ work)
 {
     const uint32_t n_rec = min(counters[C_NEWLINES], max_records);
     for (uint32_t line = blockIdx.x * blockDim.x + threadIdx.x; line < n_rec; line += gridDim.x * blockDim.x) {
@@ -434,12 +445,13 @@ __global__ void __launch_bounds__(128) k_vcf_hdr(const uint8_t* __restrict__ tex
             }
         }
         meta[line] = m;
+        if (!(m.flags & FLAG_FIXED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line; // for the general parser (k_vcf_gt)
     }
 }
 
 // one thread per four samples of a candidate record; groups of all records laid end to end (G = ceil(S / 4) per record)
 __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ text, int32_t S, uint32_t G, uint32_t magic, uint32_t max_records,
-                                                   const uint32_t* __restrict__ counters, RecMeta* meta, uint8_t* __restrict__ rows)
+                                                   uint32_t* counters, RecMeta* meta, uint8_t* __restrict__ rows, uint32_t* __restrict__ work)
 {
     const uint32_t n_rec = min(counters[C_NEWLINES], max_records);
     const unsigned long long total = (unsigned long long)n_rec * G;
@@ -447,10 +459,11 @@ __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ t
     const unsigned long long warp0 = ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32ull;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const bool rows_al = (S & 3) == 0;
+    const int n_seg = G >= 8 ? (int)(31u / G) + 2 : 0; // records a warp step can touch (0: too many, per-lane atomics instead)
     for (unsigned long long g0 = warp0; g0 < total; g0 += stride) {
-        const uint32_t line0 = (uint32_t)(g0 / G);                      // warp-uniform
+        const uint32_t line0 = total >> 32 ? (uint32_t)(g0 / G) : (uint32_t)g0 / G;   // warp-uniform
         const uint32_t r = (uint32_t)(g0 - (unsigned long long)line0 * G) + (uint32_t)lane;
-        const uint32_t dl = G == 1 ? r : __umulhi(r, magic);           // r / G, exact for r < G + 32
+        const uint32_t dl = G == 1 ? r : __umulhi(r, magic);                            // r / G, exact for r < G + 32
         const uint32_t line = line0 + dl, g = r - dl * G;
         const bool valid = g0 + (unsigned long long)lane < total;
         RecMeta m;
@@ -464,45 +477,56 @@ __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ t
             const uint32_t q = m.p0 + 16u * g, sh = (q & 3u) * 8u;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(text + (q & ~3u));
             const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = sh ? __ldg(w + 4) : 0u;
-            const uint32_t x[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+            uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = __funnelshift_r(w2, w3, sh), x3 = __funnelshift_r(w3, w4, sh);
             const int n = min(4, S - s0);
-            const int last = S - 1 - s0; // the line end closes the last column
+            if (s0 + 4 >= S) { // the record's last group: the line end closes the last column, columns beyond it read as "0|0"
+                const int last = S - 1 - s0;
+                x0 = last == 0 ? (x0 & 0x00FFFFFFu) | 0x09000000u : x0;
+                x1 = last == 1 ? (x1 & 0x00FFFFFFu) | 0x09000000u : last < 1 ? 0x09307C30u : x1;
+                x2 = last == 2 ? (x2 & 0x00FFFFFFu) | 0x09000000u : last < 2 ? 0x09307C30u : x2;
+                x3 = last == 3 ? (x3 & 0x00FFFFFFu) | 0x09000000u : last < 3 ? 0x09307C30u : x3;
+            }
             const uint32_t nal = m.flags >> 8;
-            uint32_t out = 0;
-            if (m.flags & FLAG_BIALLELIC) {
-                const uint32_t dmask = nal == 2 ? 0xFFFEFFFEu : 0xFFFFFFFFu;
-                const uint32_t amap = 0xEEEEEE00u | (m.lut & 0xFu) | (((m.lut >> 8) & 0xFu) << 4);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k >= n) break;
-                    const uint32_t xv = k == last ? (x[k] & 0x00FFFFFFu) | 0x09000000u : x[k];
-                    const uint32_t sep = xv & 0xFF00FF00u, d = (xv & 0x00FF00FFu) - 0x00300030u;
-                    uint32_t byte;
-                    if ((sep == 0x09007C00u || sep == 0x09002F00u) && (d & dmask) == 0) {
-                        byte = __byte_perm(m.lut, 0, (d | (d >> 15)) & 3u) & 0xFFu;
-                        sum += __popc(d);
-                    } else byte = slow_cell(xv, nal, amap, ok, sum);
-                    out |= byte << (8 * k);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k >= n) break;
-                    out |= slow_cell(k == last ? (x[k] & 0x00FFFFFFu) | 0x09000000u : x[k], nal, m.lut, ok, sum) << (8 * k);
-                }
+            uint32_t out;
+            const uint32_t dmask = nal == 2 ? 0xFFFEFFFEu : 0xFFFFFFFFu;
+            const uint32_t d0 = (x0 & 0x00FF00FFu) - 0x00300030u, d1 = (x1 & 0x00FF00FFu) - 0x00300030u;
+            const uint32_t d2 = (x2 & 0x00FF00FFu) - 0x00300030u, d3 = (x3 & 0x00FF00FFu) - 0x00300030u;
+            // all four columns "a|b" + tab with a, b in {0, 1} (0 only without an ALT allele)?  one test, one table look-up each
+            const uint32_t bad = ((x0 ^ 0x09007C00u) | (x1 ^ 0x09007C00u) | (x2 ^ 0x09007C00u) | (x3 ^ 0x09007C00u)) & 0xFF00FF00u;
+            const uint32_t badd = (d0 | d1 | d2 | d3) & dmask;
+            if ((m.flags & FLAG_BIALLELIC) && (bad | badd) == 0) {
+                const uint32_t b0 = __byte_perm(m.lut, 0, ((d0 | (d0 >> 15)) & 3u) | 0x4440u);
+                const uint32_t b1 = __byte_perm(m.lut, 0, ((d1 | (d1 >> 15)) & 3u) | 0x4440u);
+                const uint32_t b2 = __byte_perm(m.lut, 0, ((d2 | (d2 >> 15)) & 3u) | 0x4440u);
+                const uint32_t b3 = __byte_perm(m.lut, 0, ((d3 | (d3 >> 15)) & 3u) | 0x4440u);
+                out = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+                sum = __popc(d0 | (d1 << 1) | (d2 << 2) | (d3 << 3));
+            } else { // '/' separators, missing alleles, more than two alleles, or a defect
+                const uint32_t amap = (m.flags & FLAG_BIALLELIC) ? 0xEEEEEE00u | (m.lut & 0xFu) | (((m.lut >> 8) & 0xFu) << 4) : m.lut;
+                out = slow_cell(x0, nal, amap, ok, sum);
+                if (n > 1) out |= slow_cell(x1, nal, amap, ok, sum) << 8;
+                if (n > 2) out |= slow_cell(x2, nal, amap, ok, sum) << 16;
+                if (n > 3) out |= slow_cell(x3, nal, amap, ok, sum) << 24;
             }
             uint8_t* dst = rows + (size_t)line * S + s0;
             if (rows_al) *reinterpret_cast<uint32_t*>(dst) = out;
             else
                 for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(out >> (8 * k));
         }
-        // per-record totals: the lanes of one record are contiguous
-        const uint32_t grp = __match_any_sync(0xffffffffu, fixed ? line : 0xFFFFFFFFu);
-        const int tot = __reduce_add_sync(grp, sum);
-        const uint32_t all_ok = __reduce_and_sync(grp, ok ? 1u : 0u);
-        if (fixed && lane == __ffs(grp) - 1) {
-            if (tot) atomicAdd(&meta[line].asum, tot);
-            if (!all_ok) atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED);
+        // per-record totals (allele-index sum, any defect): the lanes of one record are contiguous
+        const int v = fixed ? sum + (ok ? 0 : 1 << 20) : 0;
+        if (n_seg) {
+            for (int j = 0; j < n_seg; ++j) {
+                const int tot = __reduce_add_sync(0xffffffffu, dl == (uint32_t)j ? v : 0);
+                const uint32_t lanes = __ballot_sync(0xffffffffu, fixed && dl == (uint32_t)j);
+                if (tot && lane == __ffs(lanes) - 1) {
+                    if (tot & 0xFFFFF) atomicAdd(&meta[line].asum, tot & 0xFFFFF);
+                    if ((tot >> 20) && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line;
+                }
+            }
+        } else if (v) {
+            if (v & 0xFFFFF) atomicAdd(&meta[line].asum, v & 0xFFFFF);
+            if ((v >> 20) && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line;
         }
     }
 }
@@ -512,7 +536,7 @@ constexpr int GT_WARPS = 8;
 __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restrict__ text, uint32_t n_bytes, const uint32_t* __restrict__ line_end,
                                                          int32_t S, int32_t gt_source, int32_t rm_invar, uint32_t max_records,
                                                          vgl_in_site* __restrict__ sites, uint8_t* __restrict__ rows, uint32_t* counters,
-                                                         const RecMeta* __restrict__ meta)
+                                                         const RecMeta* __restrict__ meta, const uint32_t* __restrict__ work)
 {
     __shared__ uint32_t s_tab[GT_WARPS][12];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -524,24 +548,29 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
     }
     uint32_t* tab = s_tab[wid];
     uint32_t n_kept = 0, n_err = 0, first_err = 0xFFFFFFFFu; // lane 0's tallies, posted once per warp
-    for (uint32_t line = warp0; line < n_rec; line += n_warps) {
-        {   // a fixed-width record that k_vcf_cells converted completely: only the totals are left to do
+    // (a) fixed-width records that k_vcf_cells converted completely: only the totals are left, one thread per record
+    {
+        uint32_t kept = 0;
+        for (uint32_t line = blockIdx.x * blockDim.x + threadIdx.x; line < n_rec; line += gridDim.x * blockDim.x) {
             const RecMeta m = meta[line];
-            if ((m.flags & (FLAG_FIXED | FLAG_FAILED)) == FLAG_FIXED) {
-                if (lane == 0) {
-                    int skip = 0;
-                    const int nal = (int)(m.flags >> 8);
-                    if ((rm_invar & 1) && m.asum == 0) skip = -1;
-                    else if (rm_invar & 2)
-                        for (int al = 1; al < nal; ++al)
-                            if ((long long)al * S * 2 == (long long)m.asum) skip = -2;
-                    sites[line].skip_code = skip;
-                    sites[line].allele_sum = m.asum;
-                    n_kept += skip == 0;
-                }
-                continue;
-            }
+            if ((m.flags & (FLAG_FIXED | FLAG_FAILED)) != FLAG_FIXED) continue;
+            int skip = 0;
+            const int nal = (int)(m.flags >> 8);
+            if ((rm_invar & 1) && m.asum == 0) skip = -1;
+            else if (rm_invar & 2)
+                for (int al = 1; al < nal; ++al)
+                    if ((long long)al * S * 2 == (long long)m.asum) skip = -2;
+            sites[line].skip_code = skip;
+            sites[line].allele_sum = m.asum;
+            kept += skip == 0;
         }
+        kept = __reduce_add_sync(0xffffffffu, kept);
+        n_kept += kept;
+    }
+    // (b) every other record: one warp per record, from the work list k_vcf_hdr and k_vcf_cells left
+    const uint32_t n_work = counters[C_NWORK];
+    for (uint32_t wi = warp0; wi < n_work; wi += n_warps) {
+        const uint32_t line = work[wi];
         const uint32_t ls = line ? line_end[line - 1] + 1 : 0;
         uint32_t le = line_end[line];
         if (le > ls && text[le - 1] == '\r') --le; // KS_SEP_LINE strips the CR of a CRLF
@@ -751,6 +780,8 @@ int parser_create(int device, int S, int rm_invar, int n_sms, int64_t max_text, 
     PCK(cudaMemset(ps->d_text, 0, padded));
     PCK(cudaMalloc((void**)&ps->d_line_end, ((size_t)max_records + 1) * sizeof(uint32_t)));
     PCK(cudaMalloc((void**)&ps->d_tile_count, (size_t)ps->max_tiles * sizeof(uint32_t)));
+    PCK(cudaMalloc((void**)&ps->d_block_base, (size_t)MAX_IDX_BLOCKS * sizeof(uint32_t)));
+    PCK(cudaMalloc((void**)&ps->d_work, (size_t)max_records * sizeof(uint32_t)));
     PCK(cudaMalloc((void**)&ps->d_counters, C_COUNT * sizeof(uint32_t)));
     PCK(cudaHostAlloc((void**)&ps->h_counters, C_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
     PCK(cudaMalloc((void**)&ps->d_sites, (size_t)max_records * sizeof(vgl_in_site)));
@@ -772,6 +803,8 @@ void parser_destroy(vgl_parser* ps)
     cudaFree(ps->d_text);
     cudaFree(ps->d_line_end);
     cudaFree(ps->d_tile_count);
+    cudaFree(ps->d_block_base);
+    cudaFree(ps->d_work);
     cudaFree(ps->d_counters);
     cudaFreeHost(ps->h_counters);
     cudaFree(ps->d_sites);
@@ -841,22 +874,23 @@ extern "C" int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source,
     const uint32_t n_tiles = (uint32_t)((n + WT_BYTES - 1) / WT_BYTES);
     static const uint32_t init[C_COUNT] = {0, 0, 0, 0, 0xFFFFFFFFu, 0, 0, 0};
     PCK(cudaMemcpyAsync(ps->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
-    const uint32_t idx_grid = (uint32_t)std::min<uint64_t>((n_tiles + IDX_WARPS - 1) / IDX_WARPS, (uint64_t)ps->n_sms * 8);
-    k_vcf_count<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, ps->d_tile_count);
-    k_vcf_scan<<<1, SCAN_THREADS, 0, st>>>(ps->d_tile_count, n_tiles, ps->d_counters);
-    k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, ps->d_tile_count, (uint32_t)ps->max_records, ps->d_line_end);
+    const uint32_t idx_grid = (uint32_t)std::min<uint64_t>((n_tiles + IDX_WARPS - 1) / IDX_WARPS, (uint64_t)std::min(ps->n_sms * 8, (int)MAX_IDX_BLOCKS));
+    const uint32_t tpb = (n_tiles + idx_grid - 1) / idx_grid; // warp tiles per block, contiguous
+    k_vcf_count<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, tpb, ps->d_tile_count, ps->d_block_base, ps->d_counters);
+    k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, tpb, ps->d_tile_count, ps->d_block_base, (uint32_t)ps->max_records,
+                                                       ps->d_line_end);
     RecMeta* meta = reinterpret_cast<RecMeta*>(ps->d_meta);
-    k_vcf_hdr<<<ps->n_sms * 8, 128, 0, st>>>(ps->d_text, ps->d_line_end, ps->S, gt_source, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_sites);
+    k_vcf_hdr<<<ps->n_sms * 8, 128, 0, st>>>(ps->d_text, ps->d_line_end, ps->S, gt_source, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_sites, ps->d_work);
     {   // k_vcf_cells: one thread per four samples of every record that can be fixed-width (each is at least 4 * S bytes long)
         const uint32_t G = ((uint32_t)ps->S + 3u) / 4u;
         const uint32_t magic = G > 1 ? (uint32_t)((0x100000000ull + G - 1) / G) : 0u;
         const uint64_t max_groups = std::min<uint64_t>((uint64_t)ps->max_records, n / (4ull * (uint64_t)ps->S) + 1) * G;
         const uint32_t cells_grid = (uint32_t)std::min<uint64_t>((max_groups + 255) / 256, (uint64_t)ps->n_sms * 16);
-        k_vcf_cells<<<std::max(cells_grid, 1u), 256, 0, st>>>(ps->d_text, ps->S, G, magic, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_rows);
+        k_vcf_cells<<<std::max(cells_grid, 1u), 256, 0, st>>>(ps->d_text, ps->S, G, magic, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_rows, ps->d_work);
     }
     k_vcf_gt<<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, ps->d_line_end, ps->S, gt_source, ps->rm_invar, (uint32_t)ps->max_records,
-                                                     ps->d_sites, ps->d_rows, ps->d_counters, meta);
-    ps->launches += 6;
+                                                     ps->d_sites, ps->d_rows, ps->d_counters, meta, ps->d_work);
+    ps->launches += 5;
     PCK(cudaGetLastError());
     PCK(cudaEventRecord(ps->ev[2], st));
     PCK(cudaMemcpyAsync(ps->h_counters, ps->d_counters, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
