@@ -319,7 +319,8 @@ typedef struct vgl_in_site {
     int32_t status;        /* vgl_in_status */
     int32_t skip_code;     /* 0; -1 all true genotypes hom-ref, -2 all hom-alt (check_rec_alleles, vcfgl.cpp:150-160) */
     int64_t pos;           /* bcf1_t::pos, 0-based */
-    int64_t allele_sum;    /* sum of the GT allele indices (vcfgl.cpp:145) */
+    int64_t allele_sum;    /* sum of the GT allele indices (vcfgl.cpp:145); computed only when --rm-invar-sites has bit 1 or 2
+                            * set (its only use, vcfgl.cpp:150-160), else 0 */
     uint64_t line_off;     /* the record's line in the text chunk ... */
     uint32_t line_len;     /* ... without its LF (and CR) */
     int32_t n_allele;      /* bcf1_t::n_allele */

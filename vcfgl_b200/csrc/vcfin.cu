@@ -449,23 +449,34 @@ __global__ void __launch_bounds__(128) k_vcf_hdr(const uint8_t* __restrict__ tex
     }
 }
 
-// one thread per four samples of a candidate record; groups of all records laid end to end (G = ceil(S / 4) per record)
+// One thread per four samples of a candidate record; the groups of all records are laid end to end (G = ceil(S / 4) per
+// record) and every warp takes a contiguous run of them, so its (record, group) position advances without divisions.
+// SUM: also accumulate the allele-index sum per record (only --rm-invar-sites 1 / 2 needs it, vcfgl.cpp:150-160).
+template <bool SUM>
 __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ text, int32_t S, uint32_t G, uint32_t magic, uint32_t max_records,
                                                    uint32_t* counters, RecMeta* meta, uint8_t* __restrict__ rows, uint32_t* __restrict__ work)
 {
     const uint32_t n_rec = min(counters[C_NEWLINES], max_records);
-    const unsigned long long total = (unsigned long long)n_rec * G;
+    const uint32_t total = n_rec * G; // the host guarantees max_records * G < 2^32
     const int lane = threadIdx.x & 31;
-    const unsigned long long warp0 = ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32ull;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t per_warp = ((total + n_warps - 1) / n_warps + 31u) & ~31u; // groups per warp, whole steps of 32
+    const unsigned long long first = (unsigned long long)warp * per_warp;
+    if (first >= total) return;
+    const uint32_t g_end = (uint32_t)min((unsigned long long)total, first + per_warp);
+    uint32_t line0 = (uint32_t)first / G, r0 = (uint32_t)first - line0 * G; // record and group of lane 0
     const bool rows_al = (S & 3) == 0;
     const int n_seg = G >= 8 ? (int)(31u / G) + 2 : 0; // records a warp step can touch (0: too many, per-lane atomics instead)
-    for (unsigned long long g0 = warp0; g0 < total; g0 += stride) {
-        const uint32_t line0 = total >> 32 ? (uint32_t)(g0 / G) : (uint32_t)g0 / G;   // warp-uniform
-        const uint32_t r = (uint32_t)(g0 - (unsigned long long)line0 * G) + (uint32_t)lane;
-        const uint32_t dl = G == 1 ? r : __umulhi(r, magic);                            // r / G, exact for r < G + 32
+    for (uint32_t g0 = (uint32_t)first; g0 < g_end; g0 += 32) {
+        const uint32_t r = r0 + (uint32_t)lane;
+        const uint32_t dl = G == 1 ? r : __umulhi(r, magic); // r / G, exact for r < G + 32
         const uint32_t line = line0 + dl, g = r - dl * G;
-        const bool valid = g0 + (unsigned long long)lane < total;
+        const bool valid = g0 + (uint32_t)lane < g_end;
+        {   // lane 0's position for the next step
+            const uint32_t rn = r0 + 32u, q = G == 1 ? rn : __umulhi(rn, magic);
+            line0 += q;
+            r0 = rn - q * G;
+        }
         RecMeta m;
         m.p0 = 0, m.lut = 0, m.flags = 0, m.asum = 0;
         if (valid) m = *reinterpret_cast<const RecMeta*>(__builtin_assume_aligned(&meta[line], 16));
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ t
                 const uint32_t b2 = __byte_perm(m.lut, 0, ((d2 | (d2 >> 15)) & 3u) | 0x4440u);
                 const uint32_t b3 = __byte_perm(m.lut, 0, ((d3 | (d3 >> 15)) & 3u) | 0x4440u);
                 out = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-                sum = __popc(d0 | (d1 << 1) | (d2 << 2) | (d3 << 3));
+                if (SUM) sum = __popc(d0 | (d1 << 1) | (d2 << 2) | (d3 << 3));
             } else { // '/' separators, missing alleles, more than two alleles, or a defect
                 const uint32_t amap = (m.flags & FLAG_BIALLELIC) ? 0xEEEEEE00u | (m.lut & 0xFu) | (((m.lut >> 8) & 0xFu) << 4) : m.lut;
                 out = slow_cell(x0, nal, amap, ok, sum);
@@ -513,20 +524,16 @@ __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ t
             else
                 for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(out >> (8 * k));
         }
-        // per-record totals (allele-index sum, any defect): the lanes of one record are contiguous
-        const int v = fixed ? sum + (ok ? 0 : 1 << 20) : 0;
-        if (n_seg) {
-            for (int j = 0; j < n_seg; ++j) {
-                const int tot = __reduce_add_sync(0xffffffffu, dl == (uint32_t)j ? v : 0);
-                const uint32_t lanes = __ballot_sync(0xffffffffu, fixed && dl == (uint32_t)j);
-                if (tot && lane == __ffs(lanes) - 1) {
-                    if (tot & 0xFFFFF) atomicAdd(&meta[line].asum, tot & 0xFFFFF);
-                    if ((tot >> 20) && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line;
+        if (!ok && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line; // rare
+        if (SUM) { // per-record allele-index sums: the lanes of one record are contiguous
+            const int v = fixed ? sum : 0;
+            if (n_seg) {
+                for (int j = 0; j < n_seg; ++j) {
+                    const int tot = __reduce_add_sync(0xffffffffu, dl == (uint32_t)j ? v : 0);
+                    const uint32_t lanes = __ballot_sync(0xffffffffu, fixed && dl == (uint32_t)j);
+                    if (tot && lane == __ffs(lanes) - 1) atomicAdd(&meta[line].asum, tot);
                 }
-            }
-        } else if (v) {
-            if (v & 0xFFFFF) atomicAdd(&meta[line].asum, v & 0xFFFFF);
-            if ((v >> 20) && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line;
+            } else if (v) atomicAdd(&meta[line].asum, v);
         }
     }
 }
@@ -683,7 +690,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
                         if ((long long)al * S * 2 == (long long)asum) o.skip_code = -2;
             }
             o.pos = have_hdr ? h.pos : 0;
-            o.allele_sum = asum;
+            o.allele_sum = (rm_invar & 3) ? asum : 0; // only --rm-invar-sites 1 / 2 uses it
             o.line_off = ls;
             o.line_len = le - ls;
             o.n_allele = have_hdr ? h.n_allele : 0;
@@ -752,6 +759,10 @@ int parser_create(int device, int S, int rm_invar, int n_sms, int64_t max_text, 
     *out = nullptr;
     if (max_text < 1 || max_text >= (int64_t)0xFFFF0000ll || max_records < 1 || S < 1) {
         err = "vgl_parser_create: max_text_bytes must be in [1, 4 GiB), max_records >= 1";
+        return VGL_EINVAL;
+    }
+    if ((uint64_t)max_records * (((uint64_t)S + 3) / 4) >= 0xFFFFFFFFull) {
+        err = "vgl_parser_create: max_records * n_samples / 4 must stay below 2^32";
         return VGL_EINVAL;
     }
     vgl_parser* ps = new (std::nothrow) vgl_parser();
@@ -885,8 +896,11 @@ extern "C" int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source,
         const uint32_t G = ((uint32_t)ps->S + 3u) / 4u;
         const uint32_t magic = G > 1 ? (uint32_t)((0x100000000ull + G - 1) / G) : 0u;
         const uint64_t max_groups = std::min<uint64_t>((uint64_t)ps->max_records, n / (4ull * (uint64_t)ps->S) + 1) * G;
-        const uint32_t cells_grid = (uint32_t)std::min<uint64_t>((max_groups + 255) / 256, (uint64_t)ps->n_sms * 16);
-        k_vcf_cells<<<std::max(cells_grid, 1u), 256, 0, st>>>(ps->d_text, ps->S, G, magic, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_rows, ps->d_work);
+        const uint32_t cells_grid = std::max(1u, (uint32_t)std::min<uint64_t>((max_groups + 255) / 256, (uint64_t)ps->n_sms * 16));
+        if (ps->rm_invar & 3)
+            k_vcf_cells<true><<<cells_grid, 256, 0, st>>>(ps->d_text, ps->S, G, magic, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_rows, ps->d_work);
+        else
+            k_vcf_cells<false><<<cells_grid, 256, 0, st>>>(ps->d_text, ps->S, G, magic, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_rows, ps->d_work);
     }
     k_vcf_gt<<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, ps->d_line_end, ps->S, gt_source, ps->rm_invar, (uint32_t)ps->max_records,
                                                      ps->d_sites, ps->d_rows, ps->d_counters, meta, ps->d_work);
