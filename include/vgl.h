@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 4
+#define VGL_ABI_VERSION 5
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -361,6 +361,45 @@ int vgl_parser_rows(vgl_parser* ps, int32_t first_record, int32_t n_records, uin
  * records first_record .. first_record + n_sites - 1.  Asynchronous on the slot's stream; follow with
  * vgl_submit(..., VGL_SUBMIT_GT_ON_DEVICE). */
 int vgl_place_rows(vgl_ctx* ctx, int slot, vgl_parser* ps, const int32_t* row_map, int32_t first_record, int32_t n_sites, uint8_t fill_gt);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * gVCF block merging on the device: what prepare_gvcf_block() (bcf_utils.cpp:662-942) decides
+ * and accumulates while write_record_values() (vcfgl.cpp:165-207) walks the written sites of a -doGVCF 1 run.
+ *
+ * Call after vgl_wait() on a slot (its planes are still in HBM): the device classifies every written site (skip_code 0)
+ * as a block member or not (one observed allele and min FORMAT/DP inside a --gvcf-dps range, bcf_utils.cpp:692, 741-765),
+ * cuts the site sequence into records (a member joins the block before it iff same contig, pos <= end + 1, same range:
+ * bcf_utils.cpp:711, 719, 790) and reduces each block: MIN_DP, DP[s] = min over members, PL[s] = the founder's PL[3s] and the
+ * lexicographic minimum of (PL[3s+1], PL[3s+2]) (bcf_utils.cpp:838-866).  The host writes regular records as before and
+ * block records from the founder's alleles / QS plus these arrays (bcf_utils.cpp:876-905).  A batch's first block may
+ * continue the previous batch's last one: same three conditions, the same minima (vgl_host.hpp GvcfStitcher).
+ * Needs -doUnobserved 1 or 2 (members then have REF + <*>, three genotypes), FORMAT/DP and int32 planes on the device
+ * (any host_output except VGL_HOST_BCF).
+ */
+#define VGL_MAX_GVCF_DPS 16
+
+typedef struct vgl_gvcf_site_in {
+    int32_t rid, pos; /* bcf1_t::rid, ::pos of every site of the batch, written or not */
+} vgl_gvcf_site_in;
+
+typedef struct vgl_gvcf_rec {
+    int32_t first_site, last_site; /* batch indices of the first / last member; a regular record: both the site itself */
+    int32_t n_members;             /* 0: write the site as it is (GVCF_WRITE_SIMREC); >= 1: a block of that many written sites */
+    int32_t min_dp;                /* INFO/MIN_DP of a block (a regular record: the site's minimum FORMAT/DP) */
+    int32_t dp_range;              /* 1-based --gvcf-dps range of a block, 0 for a regular record */
+    int32_t plane;                 /* block: its DP at dp + plane * n_samples, its PL at pl + plane * 3 * n_samples; else -1 */
+} vgl_gvcf_rec;
+
+typedef struct vgl_gvcf_out {
+    int32_t n_recs, n_blocks;
+    const vgl_gvcf_rec* recs; /* [n_recs] in output order, pinned host memory owned by the context */
+    const int32_t* dp;        /* [n_blocks][n_samples] */
+    const int32_t* pl;        /* [n_blocks][n_samples][3], NULL without the PL tag */
+    float ms_kernels;
+} vgl_gvcf_out;
+
+/* synchronous; sites: host array [n_sites of the slot's last batch]; gvcf_dps: ascending thresholds of --gvcf-dps */
+int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* sites, const int32_t* gvcf_dps, int32_t n_gvcf_dps, vgl_gvcf_out* out);
 
 const char* vgl_strerror(int status);
 const char* vgl_last_error(const vgl_ctx* ctx);

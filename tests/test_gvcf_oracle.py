@@ -32,7 +32,6 @@ def test_blocks_equal_reference_output(cid):
         assert np.array_equal(r["fmt"]["DP"], o["dp"])
         assert np.array_equal(r["fmt"]["PL"], o["pl"])
         assert len(r["alleles"]) == 2      # REF, <*> / <NON_REF>
-    return n_blocks
 
 
 def test_dp_range():

@@ -20,7 +20,7 @@ if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same AB
     LIB_PATH = os.environ["VGL_LIB"]
 
 VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
-ABI_VERSION = 4
+ABI_VERSION = 5
 HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF = 0, 1, 2, 3
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
@@ -30,7 +30,7 @@ I32_MISSING = -(2 ** 31)
 EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_bcf_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
            "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
            "vgl_last_error", "vgl_abi_version", "vgl_native_kernels",
-           "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parser_rows", "vgl_place_rows"]
+           "vgl_gvcf_merge", "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parser_rows", "vgl_place_rows"]
 
 SOURCE_BINARY, SOURCE_ACGT = 0, 1
 PARSE_FINAL, PARSE_TEXT_ON_DEVICE = 1, 2
@@ -40,6 +40,16 @@ IN_SITE_DTYPE = np.dtype([("status", "<i4"), ("skip_code", "<i4"), ("pos", "<i8"
                           ("line_len", "<u4"), ("n_allele", "<i4"), ("allele_acgt", "i1", (8,)), ("id_off", "<u4"),
                           ("fmt_off", "<u4"), ("samples_off", "<u4"), ("_pad", "<u4")])
 assert IN_SITE_DTYPE.itemsize == 64
+
+
+GVCF_SITE_IN_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4")])
+GVCF_REC_DTYPE = np.dtype([("first_site", "<i4"), ("last_site", "<i4"), ("n_members", "<i4"), ("min_dp", "<i4"), ("dp_range", "<i4"),
+                           ("plane", "<i4")])
+
+
+class VglGvcfOut(C.Structure):
+    _fields_ = [("n_recs", C.c_int32), ("n_blocks", C.c_int32), ("recs", C.c_void_p), ("dp", C.c_void_p), ("pl", C.c_void_p),
+                ("ms_kernels", C.c_float)]
 
 
 class VglParseOut(C.Structure):
@@ -154,6 +164,7 @@ def load():
     L.vgl_last_error.argtypes = [C.c_void_p]
     L.vgl_last_error.restype = C.c_char_p
     L.vgl_abi_version.restype = C.c_int
+    L.vgl_gvcf_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(VglGvcfOut)]
     L.vgl_parser_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
     L.vgl_parser_destroy.argtypes = [C.c_void_p]
     L.vgl_parser_destroy.restype = None
@@ -427,6 +438,24 @@ class Context:
         raw.sites = C.cast(batch.sites.ctypes.data, C.POINTER(VglSiteOut))
         return int(self.L.vgl_algorithmic_bytes(C.byref(raw), self.params.tag_mask))
 
+
+    def gvcf_merge(self, slot: int, rid, pos, gvcf_dps) -> dict:
+        """gVCF block merger over the slot's last (waited) batch: -> dict(recs structured array [n_recs], dp [n_blocks, S],
+        pl [n_blocks, S, 3] or None, ms_kernels); arrays are copies"""
+        sin = np.zeros(len(rid), GVCF_SITE_IN_DTYPE)
+        sin["rid"], sin["pos"] = rid, pos
+        dps = np.ascontiguousarray(gvcf_dps, np.int32)
+        out = VglGvcfOut()
+        self._ck(self.L.vgl_gvcf_merge(self.h, slot, sin.ctypes.data, dps.ctypes.data, len(dps), C.byref(out)))
+
+        def arr(ptr, n, dt):
+            if not ptr or n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt).copy()
+        S = self.S
+        return dict(recs=arr(out.recs, out.n_recs, GVCF_REC_DTYPE), dp=arr(out.dp, out.n_blocks * S, np.int32).reshape(-1, S),
+                    pl=arr(out.pl, out.n_blocks * S * 3, np.int32).reshape(-1, S, 3) if out.pl else None,
+                    n_blocks=out.n_blocks, ms_kernels=out.ms_kernels)
 
     def parser(self, max_text_bytes: int, max_records: int) -> "Parser":
         return Parser(self, max_text_bytes, max_records)

@@ -58,6 +58,13 @@ struct Slot {
     unsigned long long* d_tile_state = nullptr; // fused: [max tiles] look-back words, then the ticket
     float *d_gl = nullptr, *d_gp = nullptr;
     int32_t *d_pl = nullptr, *d_ad = nullptr, *d_adf = nullptr, *d_adr = nullptr;
+    // vgl_gvcf_merge(): allocated on first use
+    vgl_gvcf_site_in* g_sin = nullptr;
+    int2* g_key = nullptr;
+    vgl_gvcf_rec *g_recs = nullptr, *hg_recs = nullptr;
+    int32_t *g_prev = nullptr, *g_kidx = nullptr, *g_counts = nullptr, *hg_counts = nullptr;
+    int32_t *g_dp = nullptr, *g_pl = nullptr, *hg_dp = nullptr, *hg_pl = nullptr;
+    cudaEvent_t g_ev[2] = {};
     // replay uploads (grown on demand)
     DevBuf r_depths, r_off, r_bases, r_strands, r_qs, r_adjqs, r_eprob, r_tails, r_deep_cells, r_deep_codes;
     float ms[VGL_T_COUNT] = {};
@@ -210,6 +217,10 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
     for (Slot& s : ctx->slots) {
         if (s.own_stream) cudaStreamSynchronize(s.own_stream);
         for (auto& e : s.ev)
+            if (e) cudaEventDestroy(e);
+        cudaFree(s.g_sin); cudaFree(s.g_key); cudaFree(s.g_recs); cudaFreeHost(s.hg_recs); cudaFree(s.g_prev); cudaFree(s.g_kidx);
+        cudaFree(s.g_counts); cudaFreeHost(s.hg_counts); cudaFree(s.g_dp); cudaFree(s.g_pl); cudaFreeHost(s.hg_dp); cudaFreeHost(s.hg_pl);
+        for (auto& e : s.g_ev)
             if (e) cudaEventDestroy(e);
         cudaFreeHost(s.h_gt); cudaFreeHost(s.h_sites); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_dp);
         cudaFreeHost(s.h_gl); cudaFreeHost(s.h_gp); cudaFreeHost(s.h_pl);
@@ -477,6 +488,69 @@ extern "C" int vgl_set_stream(vgl_ctx* ctx, int slot, void* cuda_stream)
     Slot& s = ctx->slots[slot];
     if (s.submitted && !s.waited) return VGL_ESTATE;
     s.stream = cuda_stream ? (cudaStream_t)cuda_stream : s.own_stream;
+    return VGL_OK;
+}
+
+// ---- gVCF block merger (gvcf.cu) ----
+extern "C" int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* sites, const int32_t* gvcf_dps, int32_t n_gvcf_dps, vgl_gvcf_out* out)
+{
+    if (!ctx || !sites || !gvcf_dps || !out || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    const vgl_params& prm = ctx->prm;
+    if (n_gvcf_dps < 1 || n_gvcf_dps > VGL_MAX_GVCF_DPS) return fail(ctx, VGL_EINVAL, "vgl_gvcf_merge: 1..16 --gvcf-dps thresholds");
+    for (int i = 0; i < n_gvcf_dps; ++i)
+        if (gvcf_dps[i] < 1 || (i && gvcf_dps[i] <= gvcf_dps[i - 1])) return fail(ctx, VGL_EINVAL, "vgl_gvcf_merge: --gvcf-dps must be >= 1 and ascending");
+    if (prm.do_unobserved != 1 && prm.do_unobserved != 2) return fail(ctx, VGL_EINVAL, "vgl_gvcf_merge: needs -doUnobserved 1 or 2 (block members carry REF + one unobserved allele)");
+    if (!(prm.tag_mask & VGL_TAG_FMT_DP) || prm.host_output == VGL_HOST_BCF) return fail(ctx, VGL_EINVAL, "vgl_gvcf_merge: needs FORMAT/DP and the tag planes on the device");
+    Slot& s = ctx->slots[slot];
+    if (!s.submitted || !s.waited) return fail(ctx, VGL_ESTATE, "vgl_gvcf_merge: call vgl_wait on the slot first");
+    if (s.n_sites >= (1 << 21)) return fail(ctx, VGL_EINVAL, "vgl_gvcf_merge: at most 2^21 - 1 sites per batch");
+    CK(cudaSetDevice(prm.device_id));
+    const size_t B = (size_t)prm.max_batch_sites, S = (size_t)prm.n_samples;
+    if (!s.g_sin) {
+        CK(cudaMalloc((void**)&s.g_sin, B * sizeof(vgl_gvcf_site_in)));
+        CK(cudaMalloc((void**)&s.g_key, B * sizeof(int2)));
+        CK(cudaMalloc((void**)&s.g_recs, B * sizeof(vgl_gvcf_rec)));
+        CK(cudaHostAlloc((void**)&s.hg_recs, B * sizeof(vgl_gvcf_rec), cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&s.g_prev, B * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&s.g_kidx, B * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&s.g_counts, 4 * sizeof(int32_t)));
+        CK(cudaHostAlloc((void**)&s.hg_counts, 4 * sizeof(int32_t), cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&s.g_dp, B * S * sizeof(int32_t)));
+        CK(cudaHostAlloc((void**)&s.hg_dp, B * S * sizeof(int32_t), cudaHostAllocDefault));
+        if (s.d_pl) {
+            CK(cudaMalloc((void**)&s.g_pl, B * S * 3 * sizeof(int32_t)));
+            CK(cudaHostAlloc((void**)&s.hg_pl, B * S * 3 * sizeof(int32_t), cudaHostAllocDefault));
+        }
+        for (auto& e : s.g_ev) CK(cudaEventCreate(&e));
+    }
+    cudaStream_t st = s.stream;
+    const int32_t n = s.n_sites;
+    CK(cudaMemcpyAsync(s.g_sin, sites, (size_t)n * sizeof(vgl_gvcf_site_in), cudaMemcpyHostToDevice, st));
+    GvcfArgs a;
+    memset(&a, 0, sizeof a);
+    a.S = (int32_t)S, a.n_sites = n;
+    a.dps.n = n_gvcf_dps;
+    for (int i = 0; i < n_gvcf_dps; ++i) a.dps.v[i] = gvcf_dps[i];
+    a.sites = s.d_sites, a.dp = s.d_dp, a.pl = s.d_pl, a.sin = s.g_sin, a.key = s.g_key, a.recs = s.g_recs;
+    a.prev_kept = s.g_prev, a.kept_idx = s.g_kidx, a.counts = s.g_counts, a.out_dp = s.g_dp, a.out_pl = s.g_pl;
+    CK(cudaEventRecord(s.g_ev[0], st));
+    launch_gvcf(a, st, ctx->n_sms);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s.g_ev[1], st));
+    CK(cudaMemcpyAsync(s.hg_counts, s.g_counts, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int32_t n_recs = s.hg_counts[0], n_blocks = s.hg_counts[1];
+    if (n_recs) CK(cudaMemcpyAsync(s.hg_recs, s.g_recs, (size_t)n_recs * sizeof(vgl_gvcf_rec), cudaMemcpyDeviceToHost, st));
+    if (n_blocks) {
+        CK(cudaMemcpyAsync(s.hg_dp, s.g_dp, (size_t)n_blocks * S * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (s.g_pl) CK(cudaMemcpyAsync(s.hg_pl, s.g_pl, (size_t)n_blocks * S * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof *out);
+    out->n_recs = n_recs, out->n_blocks = n_blocks;
+    out->recs = s.hg_recs, out->dp = s.hg_dp, out->pl = s.g_pl ? s.hg_pl : nullptr;
+    cudaEventElapsedTime(&out->ms_kernels, s.g_ev[0], s.g_ev[1]);
     return VGL_OK;
 }
 

@@ -156,6 +156,24 @@ size_t tile_m1f_scratch_words(int S, int n_sms);
 void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
                   uint8_t* adjqs, uint8_t* tails, double* eprob);
 
+// gVCF block merger (gvcf.cu)
+struct GvcfDps {
+    int32_t n;
+    int32_t v[VGL_MAX_GVCF_DPS];
+};
+struct GvcfArgs {
+    int32_t S, n_sites;
+    GvcfDps dps;
+    const vgl_site_out* sites;
+    const int32_t *dp, *pl;
+    const vgl_gvcf_site_in* sin;
+    int2* key;
+    vgl_gvcf_rec* recs;
+    int32_t *prev_kept, *kept_idx, *counts;
+    int32_t *out_dp, *out_pl;
+};
+void launch_gvcf(const GvcfArgs& a, cudaStream_t st, int n_sms);
+
 // input path (vcfin.cu)
 void launch_place_rows(const uint8_t* rows, const int32_t* d_row_map, int32_t first_record, int32_t n_sites, int32_t S, uint8_t fill, uint8_t* gt,
                        cudaStream_t st, int n_sms);
