@@ -88,7 +88,7 @@ NATIVE = {
     "lowdepth_gaps": ("--seed 5 -d 2 -e 0.01 -GL 1 -doUnobserved 2 -doGVCF 1 --gvcf-dps 1,2,3 -addPL 1 --rm-empty-sites 1", 3, 5000, [1, 2, 3], 0.9, 37, 1500),
     "s1": ("--seed 6 -d 4 -e 0.01 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 2,4 -addPL 1", 1, 4000, [2, 4], 0.8, 0, 0),
     "s33_gl2": ("--seed 7 -d 6 -e 0.01 -GL 2 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,3 -addPL 1", 33, 3000, [1, 3], 0.95, 211, 0),
-    "s1000": ("--seed 8 -d 12 -e 0.001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,2,4 -addPL 1", 1000, 300, [1, 2, 4], 0.97, 0, 0),
+    "s300": ("--seed 8 -d 12 -e 0.00001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,2,4 -addPL 1", 300, 1200, [1, 2, 4], 0.97, 0, 0),
 }
 
 

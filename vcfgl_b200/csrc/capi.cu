@@ -62,7 +62,8 @@ struct Slot {
     vgl_gvcf_site_in* g_sin = nullptr;
     int2* g_key = nullptr;
     vgl_gvcf_rec *g_recs = nullptr, *hg_recs = nullptr;
-    int32_t *g_prev = nullptr, *g_kidx = nullptr, *g_counts = nullptr, *hg_counts = nullptr;
+    int32_t *g_prev = nullptr, *g_kidx = nullptr, *g_counts = nullptr, *hg_counts = nullptr, *g_blast = nullptr;
+    unsigned long long *g_local = nullptr, *g_bsum = nullptr;
     int32_t *g_dp = nullptr, *g_pl = nullptr, *hg_dp = nullptr, *hg_pl = nullptr;
     cudaEvent_t g_ev[2] = {};
     // replay uploads (grown on demand)
@@ -219,7 +220,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         for (auto& e : s.ev)
             if (e) cudaEventDestroy(e);
         cudaFree(s.g_sin); cudaFree(s.g_key); cudaFree(s.g_recs); cudaFreeHost(s.hg_recs); cudaFree(s.g_prev); cudaFree(s.g_kidx);
-        cudaFree(s.g_counts); cudaFreeHost(s.hg_counts); cudaFree(s.g_dp); cudaFree(s.g_pl); cudaFreeHost(s.hg_dp); cudaFreeHost(s.hg_pl);
+        cudaFree(s.g_counts); cudaFreeHost(s.hg_counts); cudaFree(s.g_blast); cudaFree(s.g_local); cudaFree(s.g_bsum); cudaFree(s.g_dp); cudaFree(s.g_pl); cudaFreeHost(s.hg_dp); cudaFreeHost(s.hg_pl);
         for (auto& e : s.g_ev)
             if (e) cudaEventDestroy(e);
         cudaFreeHost(s.h_gt); cudaFreeHost(s.h_sites); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_dp);
@@ -514,6 +515,9 @@ extern "C" int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* si
         CK(cudaMalloc((void**)&s.g_prev, B * sizeof(int32_t)));
         CK(cudaMalloc((void**)&s.g_kidx, B * sizeof(int32_t)));
         CK(cudaMalloc((void**)&s.g_counts, 4 * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&s.g_blast, B * sizeof(int32_t))); // block ordinal -> record
+        CK(cudaMalloc((void**)&s.g_bsum, (B / 1024 + 2) * sizeof(unsigned long long)));
+        CK(cudaMalloc((void**)&s.g_local, B * sizeof(unsigned long long)));
         CK(cudaHostAlloc((void**)&s.hg_counts, 4 * sizeof(int32_t), cudaHostAllocDefault));
         CK(cudaMalloc((void**)&s.g_dp, B * S * sizeof(int32_t)));
         CK(cudaHostAlloc((void**)&s.hg_dp, B * S * sizeof(int32_t), cudaHostAllocDefault));
@@ -533,9 +537,10 @@ extern "C" int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* si
     for (int i = 0; i < n_gvcf_dps; ++i) a.dps.v[i] = gvcf_dps[i];
     a.sites = s.d_sites, a.dp = s.d_dp, a.pl = s.d_pl, a.sin = s.g_sin, a.key = s.g_key, a.recs = s.g_recs;
     a.prev_kept = s.g_prev, a.kept_idx = s.g_kidx, a.counts = s.g_counts, a.out_dp = s.g_dp, a.out_pl = s.g_pl;
+    a.blk_rec = s.g_blast, a.local = s.g_local, a.block_sum = s.g_bsum;
     CK(cudaEventRecord(s.g_ev[0], st));
     launch_gvcf(a, st, ctx->n_sms);
-    ctx->launches += 4;
+    ctx->launches += 5;
     CK(cudaGetLastError());
     CK(cudaEventRecord(s.g_ev[1], st));
     CK(cudaMemcpyAsync(s.hg_counts, s.g_counts, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

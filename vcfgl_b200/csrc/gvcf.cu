@@ -8,7 +8,8 @@
 // So the machine is a segmented min-reduction over sites:
 //
 //   k_gvcf_key     warp per site: min FORMAT/DP over the samples -> dp range, member flag
-//   k_gvcf_plan    one block: head flags from neighbouring written sites, record ids / block ordinals by scan
+//   k_gvcf_plan_local / _global   blocks of 1024 sites: head flags from neighbouring written sites, record ids / block
+//                  ordinals by a two-level scan
 //   k_gvcf_fin     thread per record: last member, number of members
 //   k_gvcf_reduce  warp per (block, 32 samples): per-sample minima over the members, MIN_DP
 //
@@ -20,6 +21,7 @@ namespace vgl {
 namespace {
 
 enum { K_KEPT = 1, K_MEMBER = 2 };
+constexpr int PLAN_THREADS = 1024;
 
 __global__ void __launch_bounds__(256) k_gvcf_key(const vgl_site_out* __restrict__ sites, const int32_t* __restrict__ dp, int32_t S, int32_t n_sites,
                                                   GvcfDps dps, int2* __restrict__ key)
@@ -43,8 +45,6 @@ __global__ void __launch_bounds__(256) k_gvcf_key(const vgl_site_out* __restrict
         if (lane == 0) key[i] = make_int2(m, K_KEPT | (member ? K_MEMBER : 0) | (r << 8));
     }
 }
-
-constexpr int PLAN_THREADS = 1024;
 
 // inclusive block scans over PLAN_THREADS values (sum of a packed 64-bit word, max of an int)
 __device__ __forceinline__ void block_scan(unsigned long long& sum, int& mx, unsigned long long* s_sum, int* s_max)
@@ -75,72 +75,108 @@ __device__ __forceinline__ void block_scan(unsigned long long& sum, int& mx, uns
     __syncthreads();
 }
 
-// packed sums: bits 0..20 records (heads), 21..41 blocks (member heads), 42..62 written sites
-__global__ void __launch_bounds__(PLAN_THREADS) k_gvcf_plan(const int2* __restrict__ key, const vgl_gvcf_site_in* __restrict__ sin, int32_t n_sites,
-                                                            vgl_gvcf_rec* __restrict__ recs, int32_t* __restrict__ prev_kept,
-                                                            int32_t* __restrict__ kept_idx, int32_t* __restrict__ counts)
+// last written site before `end` (exclusive), found by the whole block, PLAN_THREADS sites per step (skipped sites are rare:
+// one step; bounded for the all-skipped worst case).  Every thread of the block must call it.
+__device__ __forceinline__ int block_last_kept_before(const int2* __restrict__ key, int end, int* s_red)
+{
+    for (int hi = end; hi > 0; hi -= PLAN_THREADS) {
+        const int i = hi - 1 - (int)threadIdx.x;
+        int v = (i >= 0 && (key[i].y & K_KEPT)) ? i : -1;
+        v = __reduce_max_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        int m = -1;
+        for (int w = 0; w < PLAN_THREADS / 32; ++w) m = max(m, s_red[w]);
+        __syncthreads();
+        if (m >= 0) return m;
+    }
+    return -1;
+}
+
+// The plan in two parallel steps over blocks of PLAN_THREADS sites.
+// packed sums: bits 0..20 records (heads), 21..41 blocks (member heads), 42..62 written sites; bit 63 of local[]: head flag
+__global__ void __launch_bounds__(PLAN_THREADS) k_gvcf_plan_local(const int2* __restrict__ key, const vgl_gvcf_site_in* __restrict__ sin, int32_t n_sites,
+                                                                  int32_t* __restrict__ prev_kept,
+                                                                  unsigned long long* __restrict__ local, unsigned long long* __restrict__ block_sum)
 {
     __shared__ unsigned long long s_sum[PLAN_THREADS / 32];
     __shared__ int s_max[PLAN_THREADS / 32];
     __shared__ int s_incl[PLAN_THREADS];
-    __shared__ unsigned long long s_carry_sum;
-    __shared__ int s_carry_max;
+    const int s_before = block_last_kept_before(key, (int)blockIdx.x * PLAN_THREADS, s_max); // last written site before this block
+    const int i = blockIdx.x * PLAN_THREADS + threadIdx.x;
+    const bool in = i < n_sites;
+    const int2 k = in ? key[i] : make_int2(0, 0);
+    const bool kept = (k.y & K_KEPT) != 0, member = (k.y & K_MEMBER) != 0;
+    unsigned long long dummy = 0;
+    int mx = kept ? i : -1;
+    block_scan(dummy, mx, s_sum, s_max);
+    s_incl[threadIdx.x] = max(mx, s_before);
+    __syncthreads();
+    const int p = threadIdx.x ? s_incl[threadIdx.x - 1] : s_before; // last written site before i
+    bool head = false;
+    if (kept) {
+        head = true;
+        if (member && p >= 0) {
+            const int2 kp = key[p];
+            const vgl_gvcf_site_in a = sin[p], b = sin[i];
+            if ((kp.y & K_MEMBER) && (kp.y >> 8) == (k.y >> 8) && a.rid == b.rid && b.pos <= a.pos + 1) head = false;
+        }
+    }
+    unsigned long long sum = (head ? 1ull : 0ull) | ((head && member) ? 1ull << 21 : 0ull) | (kept ? 1ull << 42 : 0ull);
+    int dummy_max = -1;
+    block_scan(sum, dummy_max, s_sum, s_max);
+    if (in) {
+        prev_kept[i] = p;
+        local[i] = sum | (head ? 1ull << 63 : 0ull);
+    }
+    if (threadIdx.x == PLAN_THREADS - 1) block_sum[blockIdx.x] = sum;
+}
+
+__global__ void __launch_bounds__(PLAN_THREADS) k_gvcf_plan_global(const int2* __restrict__ key, int32_t n_sites, int32_t* __restrict__ blk_rec,
+                                                                   const unsigned long long* __restrict__ local,
+                                                                   const unsigned long long* __restrict__ block_sum, vgl_gvcf_rec* __restrict__ recs,
+                                                                   int32_t* __restrict__ kept_idx, int32_t* __restrict__ counts)
+{
+    __shared__ unsigned long long s_part[PLAN_THREADS / 32];
+    __shared__ unsigned long long s_off;
+    __shared__ int s_red[PLAN_THREADS / 32];
+    int last_written = -1;
+    if (blockIdx.x == gridDim.x - 1) last_written = block_last_kept_before(key, n_sites, s_red); // the whole block takes part
+    unsigned long long part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += PLAN_THREADS) part += block_sum[b];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        s_carry_sum = 0;
-        s_carry_max = -1;
+        unsigned long long t = 0;
+        for (int w = 0; w < PLAN_THREADS / 32; ++w) t += s_part[w];
+        s_off = t;
     }
     __syncthreads();
-    for (int base = 0; base < n_sites; base += PLAN_THREADS) {
-        const int i = base + threadIdx.x;
-        const bool in = i < n_sites;
-        const int2 k = in ? key[i] : make_int2(0, 0);
-        const bool kept = (k.y & K_KEPT) != 0, member = (k.y & K_MEMBER) != 0;
-        // index of the last written site before i
-        unsigned long long dummy = 0;
-        int mx = kept ? i : -1;
-        block_scan(dummy, mx, s_sum, s_max);
-        const int incl_max = max(mx, s_carry_max);
-        s_incl[threadIdx.x] = incl_max;
-        __syncthreads();
-        const int p = threadIdx.x ? s_incl[threadIdx.x - 1] : s_carry_max; // exclusive maximum
-        bool head = false;
-        if (kept) {
-            head = true;
-            if (member && p >= 0) {
-                const int2 kp = key[p];
-                const vgl_gvcf_site_in a = sin[p], b = sin[i];
-                if ((kp.y & K_MEMBER) && (kp.y >> 8) == (k.y >> 8) && a.rid == b.rid && b.pos <= a.pos + 1) head = false;
-            }
+    const int i = blockIdx.x * PLAN_THREADS + threadIdx.x;
+    if (i < n_sites) {
+        const unsigned long long l = local[i];
+        const unsigned long long sum = (l & ~(1ull << 63)) + s_off;
+        const int2 k = key[i];
+        const bool kept = (k.y & K_KEPT) != 0, member = (k.y & K_MEMBER) != 0, head = (l >> 63) != 0;
+        kept_idx[i] = (int)((sum >> 42) & 0x1FFFFF) - (kept ? 1 : 0);
+        if (head) {
+            vgl_gvcf_rec r;
+            r.first_site = i;
+            r.last_site = i;
+            r.n_members = member ? 1 : 0;
+            r.min_dp = k.x;
+            r.dp_range = member ? (k.y >> 8) : 0;
+            r.plane = member ? (int)((sum >> 21) & 0x1FFFFF) - 1 : -1;
+            recs[(int)(sum & 0x1FFFFF) - 1] = r;
+            if (member) blk_rec[r.plane] = (int)(sum & 0x1FFFFF) - 1;
         }
-        unsigned long long sum = (head ? 1ull : 0ull) | ((head && member) ? 1ull << 21 : 0ull) | (kept ? 1ull << 42 : 0ull);
-        int dummy_max = -1;
-        block_scan(sum, dummy_max, s_sum, s_max);
-        sum += s_carry_sum;
-        if (in) {
-            prev_kept[i] = p;
-            kept_idx[i] = (int)((sum >> 42) & 0x1FFFFF) - (kept ? 1 : 0);
-            if (head) {
-                vgl_gvcf_rec r;
-                r.first_site = i;
-                r.last_site = i;
-                r.n_members = member ? 1 : 0;
-                r.min_dp = k.x;
-                r.dp_range = member ? (k.y >> 8) : 0;
-                r.plane = member ? (int)((sum >> 21) & 0x1FFFFF) - 1 : -1;
-                recs[(int)(sum & 0x1FFFFF) - 1] = r;
-            }
+        if (i == n_sites - 1) {
+            counts[0] = (int)(sum & 0x1FFFFF);         // records
+            counts[1] = (int)((sum >> 21) & 0x1FFFFF); // blocks
+            counts[2] = last_written;                  // last written site (-1: none)
         }
-        __syncthreads();
-        if (threadIdx.x == PLAN_THREADS - 1) {
-            s_carry_sum = sum;
-            s_carry_max = incl_max;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        counts[0] = (int)(s_carry_sum & 0x1FFFFF);         // records
-        counts[1] = (int)((s_carry_sum >> 21) & 0x1FFFFF); // blocks
-        counts[2] = s_carry_max;                           // last written site (-1: none)
     }
 }
 
@@ -157,20 +193,20 @@ __global__ void k_gvcf_fin(vgl_gvcf_rec* __restrict__ recs, const int32_t* __res
     }
 }
 
-__global__ void __launch_bounds__(256) k_gvcf_reduce(vgl_gvcf_rec* recs, const int32_t* __restrict__ counts, const int2* __restrict__ key,
+__global__ void __launch_bounds__(256) k_gvcf_reduce(vgl_gvcf_rec* recs, const int32_t* __restrict__ counts, const int32_t* __restrict__ blk_rec, const int2* __restrict__ key,
                                                      const vgl_site_out* __restrict__ sites, const int32_t* __restrict__ dp,
                                                      const int32_t* __restrict__ pl, int32_t S, int32_t* __restrict__ out_dp,
                                                      int32_t* __restrict__ out_pl)
 {
     const int lane = threadIdx.x & 31;
-    const int n = counts[0];
+    const int n_blocks = counts[1];
     const int chunks = (S + 31) / 32;
-    const long long total = (long long)n * chunks;
-    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long w = warp; w < total; w += n_warps) {
-        const int r = (int)(w / chunks), c = (int)(w - (long long)r * chunks);
+    const unsigned total = (unsigned)n_blocks * (unsigned)chunks; // < 2^21 * chunks: the API bounds sites * samples
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned w = warp; w < total; w += n_warps) {
+        const int blk = (int)(w / (unsigned)chunks), c = (int)(w - (unsigned)blk * (unsigned)chunks);
+        const int r = blk_rec[blk];
         const vgl_gvcf_rec rec = recs[r];
-        if (rec.n_members == 0) continue;
         const int s = c * 32 + lane;
         int d = 0x7FFFFFFF, p0 = 0, p1 = 0x7FFFFFFF, p2 = 0x7FFFFFFF, md = 0x7FFFFFFF;
         for (int i = rec.first_site; i <= rec.last_site; ++i) {
@@ -205,10 +241,12 @@ __global__ void __launch_bounds__(256) k_gvcf_reduce(vgl_gvcf_rec* recs, const i
 
 void launch_gvcf(const GvcfArgs& a, cudaStream_t st, int n_sms)
 {
+    const int nb = (a.n_sites + PLAN_THREADS - 1) / PLAN_THREADS;
     k_gvcf_key<<<n_sms * 8, 256, 0, st>>>(a.sites, a.dp, a.S, a.n_sites, a.dps, a.key);
-    k_gvcf_plan<<<1, PLAN_THREADS, 0, st>>>(a.key, a.sin, a.n_sites, a.recs, a.prev_kept, a.kept_idx, a.counts);
+    k_gvcf_plan_local<<<nb, PLAN_THREADS, 0, st>>>(a.key, a.sin, a.n_sites, a.prev_kept, a.local, a.block_sum);
+    k_gvcf_plan_global<<<nb, PLAN_THREADS, 0, st>>>(a.key, a.n_sites, a.blk_rec, a.local, a.block_sum, a.recs, a.kept_idx, a.counts);
     k_gvcf_fin<<<n_sms * 2, 256, 0, st>>>(a.recs, a.prev_kept, a.kept_idx, a.counts);
-    k_gvcf_reduce<<<n_sms * 8, 256, 0, st>>>(a.recs, a.counts, a.key, a.sites, a.dp, a.pl, a.S, a.out_dp, a.out_pl);
+    k_gvcf_reduce<<<n_sms * 8, 256, 0, st>>>(a.recs, a.counts, a.blk_rec, a.key, a.sites, a.dp, a.pl, a.S, a.out_dp, a.out_pl);
 }
 
 } // namespace vgl

@@ -169,7 +169,8 @@ struct GvcfArgs {
     const vgl_gvcf_site_in* sin;
     int2* key;
     vgl_gvcf_rec* recs;
-    int32_t *prev_kept, *kept_idx, *counts;
+    int32_t *prev_kept, *kept_idx, *counts, *blk_rec;
+    unsigned long long *local, *block_sum;
     int32_t *out_dp, *out_pl;
 };
 void launch_gvcf(const GvcfArgs& a, cudaStream_t st, int n_sms);
