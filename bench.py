@@ -285,6 +285,22 @@ def gpu_arm(opt):
     ctx.copy_sites(d, last)
     alg_bytes = ctx.algorithmic_bytes(last)           # of one step (last batch)
     g_share = float((last.sites["n_genotypes"] == 15).mean())
+    gvcf_leg = None
+    if a.do_gvcf and a.do_unobserved in (1, 2) and rank == 0:
+        # the gVCF block merger (bcf_utils.cpp:662-942) over the batch still resident in HBM
+        dps = [int(x) for x in a.gvcf_dps.split(",")]
+        rid0, pos0 = np.zeros(B, np.int32), np.arange(B, dtype=np.int32)
+        gm = [ctx.gvcf_merge(d, rid0, pos0, dps) for _ in range(4)]
+        g_ms = min(x["ms_kernels"] for x in gm[1:])
+        members = int(gm[-1]["recs"]["n_members"].sum())
+        g_alg = 4 * B * S + 16 * members * S + 16 * gm[-1]["n_blocks"] * S      # DP plane in; DP + 3 PL per member cell in; per block out
+        pk, pk_src = measured_peak()
+        gvcf_leg = {"what": "k_gvcf_key / plan_local / plan_global / fin / reduce on one step (sites at consecutive positions of one contig)",
+                    "kernel_ms": g_ms, "gpu_launches": 5, "records": int(len(gm[-1]["recs"])), "blocks": int(gm[-1]["n_blocks"]),
+                    "member_sites": members, "sites_per_s": B / (g_ms * 1e-3),
+                    "roofline": {"bound": "hbm", "achieved": g_alg / (g_ms * 1e-3) / 1e9, "peak": pk, "unit": "GB/s",
+                                 "frac": g_alg / (g_ms * 1e-3) / 1e9 / pk, "peak_source": pk_src, "traffic": None,
+                                 "algorithmic_bytes_per_step": g_alg}}
     ctx.close()
     t_max = ms
     if dist is not None:
@@ -428,7 +444,7 @@ def gpu_arm(opt):
                 "i32_planes": {"value": e2e_i32, "d2h_bytes_per_step": d2h_i32,
                                "planes": "VGL_HOST_I32: every plane int32/float32 as add_tags() hands them to htslib"},
                 "bcf_records": e2e_bcf},
-        "input_path": input_path,
+        "input_path": input_path, "gvcf_merge": gvcf_leg,
         "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(line))
     if dist is not None:

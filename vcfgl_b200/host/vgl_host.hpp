@@ -576,4 +576,83 @@ private:
     std::vector<int32_t> map_;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// gVCF (-doGVCF 1): the record sequence of a run from the device's per-batch merge (vgl_gvcf_merge).  What is left of
+// prepare_gvcf_block() (bcf_utils.cpp:662-942) on the host is the seam between batches: a batch's first block continues
+// the block still open from the batch before under the reference's own three conditions (same contig, pos <= end + 1,
+// same dp range: bcf_utils.cpp:711, 719, 790), with the same minima (:838-866).
+//
+//   reference                                            here
+//   ---------                                            ----
+//   write_record_values(sim) per site (vcfgl.cpp:165)    feed() once per batch, after vgl_wait + vgl_gvcf_merge
+//   GVCF_WRITE_SIMREC                                    on_site(global site index): write the site's own record
+//   GVCF_FLUSH_BLOCK + grec (bcf_utils.cpp:876-905)      on_block(Block): alleles / QS from site `first`, END, MIN_DP, DP, PL
+//   write_record_values(NULL) at the end (vcfgl.cpp:169) finish()
+class GvcfStitcher {
+public:
+    struct Block {
+        int64_t first = 0;   // global index of the founder site
+        int32_t rid = 0;
+        int64_t start = 0, end = 0; // 0-based positions of the first / last member
+        int32_t min_dp = 0, dp_range = 0, n_members = 0;
+        std::vector<int32_t> dp, pl; // [S], [S * 3] (empty without PL)
+    };
+    GvcfStitcher(int n_samples, std::function<void(int64_t)> on_site, std::function<void(const Block&)> on_block)
+        : S_(n_samples), on_site_(std::move(on_site)), on_block_(std::move(on_block))
+    {
+    }
+
+    void feed(const vgl_gvcf_out& o, const vgl_gvcf_site_in* sites, int32_t n_sites)
+    {
+        for (int32_t k = 0; k < o.n_recs; ++k) {
+            const vgl_gvcf_rec& r = o.recs[k];
+            if (r.n_members == 0) {
+                flush();
+                on_site_(base_ + r.first_site);
+                continue;
+            }
+            const vgl_gvcf_site_in &f = sites[r.first_site], &l = sites[r.last_site];
+            const int32_t* dp = o.dp + (size_t)r.plane * S_;
+            const int32_t* pl = o.pl ? o.pl + (size_t)r.plane * S_ * 3 : nullptr;
+            if (open_ && k == 0 && cur_.rid == f.rid && f.pos <= cur_.end + 1 && cur_.dp_range == r.dp_range) {
+                cur_.end = l.pos;
+                cur_.min_dp = std::min(cur_.min_dp, r.min_dp);
+                cur_.n_members += r.n_members;
+                for (int s = 0; s < S_; ++s) {
+                    cur_.dp[s] = std::min(cur_.dp[s], dp[s]);
+                    if (pl && !cur_.pl.empty()) {
+                        int32_t* g = &cur_.pl[3 * (size_t)s];
+                        const int32_t* m = pl + 3 * (size_t)s;
+                        if (m[1] < g[1] || (m[1] == g[1] && m[2] < g[2])) g[1] = m[1], g[2] = m[2];
+                    }
+                }
+                continue;
+            }
+            flush();
+            cur_.first = base_ + r.first_site;
+            cur_.rid = f.rid, cur_.start = f.pos, cur_.end = l.pos;
+            cur_.min_dp = r.min_dp, cur_.dp_range = r.dp_range, cur_.n_members = r.n_members;
+            cur_.dp.assign(dp, dp + S_);
+            if (pl) cur_.pl.assign(pl, pl + 3 * (size_t)S_);
+            else cur_.pl.clear();
+            open_ = true;
+        }
+        base_ += n_sites;
+    }
+    void finish() { flush(); }
+
+private:
+    void flush()
+    {
+        if (open_) on_block_(cur_);
+        open_ = false;
+    }
+    int S_;
+    std::function<void(int64_t)> on_site_;
+    std::function<void(const Block&)> on_block_;
+    Block cur_;
+    bool open_ = false;
+    int64_t base_ = 0;
+};
+
 } // namespace vgl
