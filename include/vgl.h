@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 5
+#define VGL_ABI_VERSION 6
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -61,7 +61,8 @@ typedef enum vgl_status {
     VGL_ESTATE = -4,  /* slot busy / not submitted */
     VGL_ERANGE = -5,  /* a quality score fell outside every --qs-bins range (vcfgl.cpp:63) */
     VGL_ENODEV = -6,  /* no CUDA device: there is no CPU path */
-    VGL_EOVERFLOW = -7 /* batch status with VGL_HOST_NARROW: a depth / allelic depth did not fit narrow_bits (values were saturated) */
+    VGL_EOVERFLOW = -7, /* batch status with VGL_HOST_NARROW: a depth / allelic depth did not fit narrow_bits (values were saturated) */
+    VGL_EMISSING = -8   /* batch status with VGL_DEPTH_INF: a true genotype is missing (the reference asserts, vcfgl.cpp:1196) */
 } vgl_status;
 
 /* vgl_params.tag_mask: which tags add_tags() would emit (io.h:90-102) */
@@ -74,7 +75,10 @@ enum {
 
 enum { VGL_DEPTH_POISSON = 0,            /* --depth x        rng.h:284 */
        VGL_DEPTH_POISSON_PER_SAMPLE = 1, /* --depths-file    rng.h:318 */
-       VGL_DEPTH_FIXED = 2 };            /* every cell gets exactly (int)depth_mean reads */
+       VGL_DEPTH_FIXED = 2,              /* every cell gets exactly (int)depth_mean reads */
+       VGL_DEPTH_INF = 3 };              /* --depth inf: no reads; GL / GP / PL state the true genotype (vcfgl.cpp:1089-1262).
+                                          * Only those three tags; vgl_site_out::info_dp is -1; not with replay, -doGVCF or
+                                          * --rm-invar-sites 4 (io.cpp:783-800, 1012-1019) */
 
 /* vgl_params.host_output: what vgl_wait() brings to pinned host memory */
 enum { VGL_HOST_NONE = 0,    /* nothing but the totals and the status word: results stay in HBM */

@@ -20,7 +20,7 @@ TAG_FMT_AD, TAG_INFO_AD = 1 << 7, 1 << 8
 TAG_FMT_ADF, TAG_INFO_ADF = 1 << 9, 1 << 10
 TAG_FMT_ADR, TAG_INFO_ADR = 1 << 11, 1 << 12
 
-DEPTH_POISSON, DEPTH_POISSON_PER_SAMPLE, DEPTH_FIXED = 0, 1, 2
+DEPTH_POISSON, DEPTH_POISSON_PER_SAMPLE, DEPTH_FIXED, DEPTH_INF = 0, 1, 2, 3
 
 
 class ArgError(ValueError):
@@ -222,6 +222,17 @@ def validate(a: SimArgs) -> None:
             raise ArgError("--error-qs 1 or 2 requires --error-rate > 0")
         if not a.beta_variance > 0.0:
             raise ArgError("--error-qs 1 or 2 requires --beta-variance > 0")
+    if math.isinf(a.depth):       # io.cpp:783-800, 1012-1019
+        if a.rm_invar_sites:
+            raise ArgError("--rm-invar-sites cannot be used with --depth inf")
+        if a.add_fmt_dp:
+            raise ArgError("(-addFormatDP 1) FORMAT/DP tag cannot be added when --depth inf is set")
+        if a.do_gvcf:
+            raise ArgError("[-doGVCF 1] Cannot output gVCF when --depth inf is set")
+        if a.error_rate != 0:
+            raise ArgError("Cannot simulate true values (--depth inf) with --error-rate %s: set it to 0 (io.cpp:847-853)" % a.error_rate)
+        if a.tag_mask & ~(TAG_GL | TAG_GP | TAG_PL):
+            raise ArgError("--depth inf: only GL, GP and PL can be added (io.cpp:796-846)")
     if a.do_gvcf:
         if not a.add_fmt_dp or a.rm_invar_sites or a.gvcf_dps is None or not a.add_pl \
                 or a.do_unobserved not in (1, 2, 4, 5):

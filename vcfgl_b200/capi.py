@@ -19,8 +19,8 @@ LIB_PATH = os.path.join(_HERE, "libvgl.so")
 if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same ABI (tools/gpu_variants.sh)
     LIB_PATH = os.environ["VGL_LIB"]
 
-VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
-ABI_VERSION = 5
+VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW, VGL_EMISSING = 0, -1, -2, -3, -4, -5, -6, -7, -8
+ABI_VERSION = 6
 HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF = 0, 1, 2, 3
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
@@ -193,6 +193,8 @@ def params_from_args(a: vargs.SimArgs, n_samples: int, max_batch_sites: int, n_s
     else:
         p.depth_mode = vargs.DEPTH_FIXED if fixed_depth else vargs.DEPTH_POISSON
         p.depth_mean = a.depth
+        if a.depth == float("inf"):      # --depth inf: truth mode (vcfgl.cpp:1089-1262)
+            p.depth_mode, p.depth_mean = vargs.DEPTH_INF, 0.0
     p.error_rate = a.error_rate
     p.error_qs = a.error_qs
     p.beta_variance = a.beta_variance

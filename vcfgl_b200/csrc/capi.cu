@@ -135,6 +135,7 @@ extern "C" const char* vgl_strerror(int s)
     case VGL_ERANGE: return "quality score outside every --qs-bins range";
     case VGL_ENODEV: return "no CUDA device available (libvgl has no CPU path)";
     case VGL_EOVERFLOW: return "a depth did not fit the narrow planes (VGL_HOST_NARROW)";
+    case VGL_EMISSING: return "missing true genotype with --depth inf";
     default: return "unknown status";
     }
 }
@@ -146,6 +147,7 @@ extern "C" int64_t vgl_launch_count(const vgl_ctx* ctx) { return ctx ? ctx->laun
 extern "C" const char* vgl_native_kernels(const vgl_ctx* ctx)
 {
     if (!ctx) return "";
+    if (ctx->prm.depth_mode == VGL_DEPTH_INF) return "k_truth_site+k_scan+k_truth_emit";
     return ctx->use_tile ? "k_tile_m1f" : ctx->use_tile_m2 ? "k_tile_m2" : ctx->use_fused ? "k_fused_m1f" : "k_sim+k_site+k_scan+k_emit";
 }
 
@@ -175,9 +177,15 @@ static int validate(const vgl_params* p, std::string& why)
     if (p->abi_version != VGL_ABI_VERSION) { why = "abi_version mismatch"; return VGL_EINVAL; }
     if (p->n_samples < 1) { why = "n_samples < 1"; return VGL_EINVAL; }
     if (p->max_batch_sites < 1 || p->n_slots < 1 || p->n_slots > 8) { why = "bad max_batch_sites / n_slots"; return VGL_EINVAL; }
-    if (p->depth_mode < 0 || p->depth_mode > 2) { why = "bad depth_mode"; return VGL_EINVAL; }
+    if (p->depth_mode < 0 || p->depth_mode > 3) { why = "bad depth_mode"; return VGL_EINVAL; }
+    if (p->depth_mode == VGL_DEPTH_INF) { // io.cpp:783-800, 1012-1019
+        if (p->tag_mask & ~(uint32_t)(VGL_TAG_GL | VGL_TAG_GP | VGL_TAG_PL)) { why = "--depth inf: only GL, GP and PL exist (no reads: -addFormatDP 0 etc.)"; return VGL_EINVAL; }
+        if (p->do_gvcf || (p->rm_invar_sites & 4)) { why = "--depth inf cannot be used with -doGVCF 1 or --rm-invar-sites 4"; return VGL_EINVAL; }
+        if (p->error_rate != 0.0) { why = "--depth inf requires --error-rate 0 (io.cpp:847-853)"; return VGL_EINVAL; }
+        if (p->host_output == VGL_HOST_BCF || p->host_output == VGL_HOST_NARROW) { why = "--depth inf: host_output must be VGL_HOST_NONE or VGL_HOST_I32"; return VGL_EINVAL; }
+    }
     if (p->depth_mode == VGL_DEPTH_POISSON_PER_SAMPLE && !p->depth_means) { why = "depth_means missing"; return VGL_EINVAL; }
-    if (p->depth_mode != VGL_DEPTH_POISSON_PER_SAMPLE && !(p->depth_mean >= 0.0 && p->depth_mean <= 500.0)) { why = "--depth out of [0,500]"; return VGL_EINVAL; }
+    if (p->depth_mode != VGL_DEPTH_POISSON_PER_SAMPLE && p->depth_mode != VGL_DEPTH_INF && !(p->depth_mean >= 0.0 && p->depth_mean <= 500.0)) { why = "--depth out of [0,500]"; return VGL_EINVAL; }
     if (!(p->error_rate >= 0.0 && p->error_rate < 1.0)) { why = "--error-rate out of [0,1)"; return VGL_EINVAL; }
     if (p->error_qs < 0 || p->error_qs > 2) { why = "--error-qs out of [0,2]"; return VGL_EINVAL; }
     if (p->gl_model < 1 || p->gl_model > 2) { why = "--gl-model out of [1,2]"; return VGL_EINVAL; }
@@ -348,6 +356,7 @@ static int create_impl(vgl_ctx* ctx)
             ctx->use_tile_m2 = 0; // e.g. --precise-gl 1 with --error-rate 0 (homT = 0): the per-read kernels
         }
     }
+    if (p.depth_mode == VGL_DEPTH_INF) ctx->use_fused = ctx->use_tile = ctx->use_tile_m2 = ctx->tile_aux = 0; // truth.cu
     // narrow host planes: 8 bits when no cell can hold more than 255 reads (the truncated tail of the Poisson law is below 2^-64)
     if (p.host_output == VGL_HOST_NARROW) ctx->narrow_bits = alias_ok ? 8 : 16;
     if (ctx->use_tile || ctx->use_tile_m2) {
@@ -775,6 +784,16 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         else launch_fused_m1f(p, st, ctx->n_sms);
         CK(cudaEventRecord(s.ev[EV_EMIT], st));
         ctx->launches += 1;
+    } else if (prm.depth_mode == VGL_DEPTH_INF) { // truth.cu: no reads, the tags state the true genotypes
+        if (rp) return fail(ctx, VGL_EINVAL, "--depth inf has no draws to replay");
+        CK(cudaEventRecord(s.ev[EV_SIM], st));
+        launch_truth_site(p, st, ctx->n_sms);
+        CK(cudaEventRecord(s.ev[EV_SITE], st));
+        launch_scan(p, st);
+        CK(cudaEventRecord(s.ev[EV_SCAN], st));
+        launch_truth_emit(p, st, ctx->n_sms);
+        CK(cudaEventRecord(s.ev[EV_EMIT], st));
+        ctx->launches += 3;
     } else {
         launch_sim(p, st);
         CK(cudaEventRecord(s.ev[EV_SIM], st));

@@ -156,6 +156,10 @@ size_t tile_m1f_scratch_words(int S, int n_sms);
 void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8_t* bases, uint8_t* strands, uint8_t* qs,
                   uint8_t* adjqs, uint8_t* tails, double* eprob);
 
+// --depth inf (truth.cu)
+void launch_truth_site(const DevParams& p, cudaStream_t st, int n_sms);
+void launch_truth_emit(const DevParams& p, cudaStream_t st, int n_sms);
+
 // gVCF block merger (gvcf.cu)
 struct GvcfDps {
     int32_t n;
