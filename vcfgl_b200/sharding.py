@@ -37,3 +37,32 @@ def merge_order(ranges: List[Tuple[int, int]]) -> List[int]:
             raise ValueError("shards do not tile the site range: %r" % (ranges,))
         pos = hi
     return order
+
+
+def shard_text(body, world: int, rank: int) -> Tuple[int, int]:
+    """Byte range [lo, hi) of a VCF body (record lines) for rank: cut at the first line start at or after rank * len / world,
+    so that the ranges tile the body and every record belongs to exactly one rank.  `body`: bytes-like with .find()."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    n = len(body)
+
+    def line_start_at_or_after(p: int) -> int:
+        if p <= 0:
+            return 0
+        if p >= n:
+            return n
+        nl = body.find(b"\n", p - 1)
+        return n if nl < 0 else nl + 1
+    return line_start_at_or_after(rank * n // world), line_start_at_or_after((rank + 1) * n // world)
+
+
+def site_id_offsets(n_sites_per_rank: List[int]) -> List[int]:
+    """first global site id of every rank = the sites of the ranks before it (what one all_gather of a single integer per rank
+    gives; the only exchange of the sharded input path, and it is host metadata, not on the data path).  Without -explode the
+    sites of a rank are the records it keeps; with -explode 1 the positions between two ranks' records belong to the later rank,
+    which needs the earlier rank's last (contig, position) as its planner's start state -- pass it the same way."""
+    out, acc = [], 0
+    for k in n_sites_per_rank:
+        out.append(acc)
+        acc += int(k)
+    return out
