@@ -261,7 +261,8 @@ __device__ __noinline__ uint32_t parse_sample_general(const uint8_t* __restrict_
 }
 
 // the nine fixed columns; tab[] = positions of the first nine tabs of the line.  Executed uniformly by the whole warp.
-__device__ __forceinline__ Hdr parse_header(const uint8_t* __restrict__ text, const uint32_t* tab, int gt_source)
+template <class Text>
+__device__ __forceinline__ Hdr parse_header(const Text& text, const uint32_t* tab, int gt_source)
 {
     Hdr h;
     h.st = 99;
@@ -400,10 +401,25 @@ __device__ __forceinline__ uint32_t slow_cell(uint32_t xv, uint32_t nal, uint32_
     return n0 | (n1 << 4);
 }
 
-__global__ void __launch_bounds__(128) k_vcf_hdr(const uint8_t* __restrict__ text, const uint32_t* __restrict__ line_end, int32_t S, int32_t gt_source,
+// the head of a record line, held in shared memory by the thread that parses the record
+constexpr int HDR_THREADS = 128;
+struct LineBuf {
+    static constexpr int BYTES = 64;
+    const uint8_t* g;
+    uint32_t base; // text offset of word 0, 16-byte aligned
+    uint32_t* w;   // word k at w[k * HDR_THREADS]
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const
+    {
+        const uint32_t o = i - base;
+        return o < (uint32_t)BYTES ? (w[(o >> 2) * HDR_THREADS] >> ((o & 3u) * 8u)) & 0xFFu : (uint32_t)g[i];
+    }
+};
+
+__global__ void __launch_bounds__(HDR_THREADS) k_vcf_hdr(const uint8_t* __restrict__ text, const uint32_t* __restrict__ line_end, int32_t S, int32_t gt_source,
                                                  uint32_t max_records, uint32_t* counters, RecMeta* __restrict__ meta,
                                                  vgl_in_site* __restrict__ sites, uint32_t* __restrict__ work)
 {
+    __shared__ uint32_t s_head[LineBuf::BYTES / 4 * HDR_THREADS];
     const uint32_t n_rec = min(counters[C_NEWLINES], max_records);
     for (uint32_t line = blockIdx.x * blockDim.x + threadIdx.x; line < n_rec; line += gridDim.x * blockDim.x) {
         const uint32_t ls = line ? line_end[line - 1] + 1 : 0;
@@ -417,10 +433,30 @@ __global__ void __launch_bounds__(128) k_vcf_hdr(const uint8_t* __restrict__ tex
             uint32_t tab[9];
             int nt = 0;
             const uint32_t p0 = le - body;
-            for (uint32_t p = ls; p < p0 && nt < 9; ++p)
+            // the head of the line goes to shared memory in one round trip (independent 16-byte loads); every later look at it is
+            // a shared-memory read instead of a byte load from a line no other lane touches
+            LineBuf buf;
+            buf.g = text;
+            buf.base = ls & ~15u;
+            buf.w = s_head + threadIdx.x; // word k of this thread at s_head[k * HDR_THREADS + tid]: conflict-free
+#pragma unroll
+            for (int k = 0; k < LineBuf::BYTES / 16; ++k) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + buf.base) + k);
+                buf.w[(4 * k) * HDR_THREADS] = v.x, buf.w[(4 * k + 1) * HDR_THREADS] = v.y;
+                buf.w[(4 * k + 2) * HDR_THREADS] = v.z, buf.w[(4 * k + 3) * HDR_THREADS] = v.w;
+                uint32_t tm = eq_mask16(v, 0x09090909u);
+                const uint32_t a = buf.base + 16u * k;
+                if (a < ls) tm &= ~((1u << (ls - a)) - 1u);
+                while (tm && nt < 9) {
+                    const uint32_t p = a + (uint32_t)__ffs(tm) - 1u;
+                    tm &= tm - 1;
+                    if (p < p0) tab[nt++] = p;
+                }
+            }
+            for (uint32_t p = buf.base + LineBuf::BYTES; p < p0 && nt < 9; ++p)
                 if (text[p] == '\t') tab[nt++] = p;
             if (nt == 9 && tab[8] == p0 - 1) {
-                const Hdr h = parse_header(text, tab, gt_source);
+                const Hdr h = parse_header(buf, tab, gt_source);
                 bool sym = false;
                 for (int i = 0; i < 5; ++i) sym = sym || (i < h.n_allele && ((h.amap >> (4 * i)) & 0xFu) == 4u);
                 if (h.st == 99 && h.gt_idx == 0 && !sym) {
@@ -891,7 +927,7 @@ extern "C" int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source,
     k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, tpb, ps->d_tile_count, ps->d_block_base, (uint32_t)ps->max_records,
                                                        ps->d_line_end);
     RecMeta* meta = reinterpret_cast<RecMeta*>(ps->d_meta);
-    k_vcf_hdr<<<ps->n_sms * 8, 128, 0, st>>>(ps->d_text, ps->d_line_end, ps->S, gt_source, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_sites, ps->d_work);
+    k_vcf_hdr<<<ps->n_sms * 8, HDR_THREADS, 0, st>>>(ps->d_text, ps->d_line_end, ps->S, gt_source, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_sites, ps->d_work);
     {   // k_vcf_cells: one thread per four samples of every record that can be fixed-width (each is at least 4 * S bytes long)
         const uint32_t G = ((uint32_t)ps->S + 3u) / 4u;
         const uint32_t magic = G > 1 ? (uint32_t)((0x100000000ull + G - 1) / G) : 0u;
