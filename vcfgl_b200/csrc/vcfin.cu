@@ -46,7 +46,8 @@ __device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4)
 // line_end[i] = byte offset of the i-th line feed.  Two launches instead of one chained scan (a decoupled
 // look-back over ~7000 tiles that each take < 1 us to load spends its time waiting on predecessors: 120 us for 56 MB):
 //   k_vcf_count  line feeds per warp tile and per block (streams the text once from HBM); the last block scans the block totals
-//   k_vcf_index  positions of the line feeds (the text comes from L2 when it is smaller than L2)
+//                (it also leaves one 16-bit line-feed mask per 16 bytes of text, in text order)
+//   k_vcf_index  positions of the line feeds from those masks (1/8 of the text's size; the text is not read again)
 __device__ __forceinline__ void load_warp_tile(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t tile, int lane, uint32_t (&m)[WT_CHUNKS])
 {
     const uint32_t base = tile * (uint32_t)WT_BYTES + (uint32_t)lane * 16u;
@@ -70,7 +71,7 @@ __device__ __forceinline__ void load_warp_tile(const uint8_t* __restrict__ text,
 constexpr int MAX_IDX_BLOCKS = 2048;
 
 __global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_count(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles, uint32_t tpb,
-                                                              uint32_t* __restrict__ tile_count, uint32_t* block_base, uint32_t* counters)
+                                                              uint32_t* __restrict__ tile_count, uint16_t* __restrict__ tile_masks, uint32_t* block_base, uint32_t* counters)
 {
     __shared__ uint32_t s_part[IDX_WARPS];
     __shared__ uint32_t s_last;
@@ -82,7 +83,10 @@ __global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_count(const uint8_t* __r
         load_warp_tile(text, n_bytes, tile, lane, m);
         uint32_t c = 0;
 #pragma unroll
-        for (int j = 0; j < WT_CHUNKS; ++j) c += __popc(m[j]);
+        for (int j = 0; j < WT_CHUNKS; ++j) {
+            c += __popc(m[j]);
+            tile_masks[(size_t)tile * (WT_CHUNKS * 32) + j * 32 + lane] = (uint16_t)m[j]; // in text order: k_vcf_index never reads the text
+        }
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0) tile_count[tile] = c;
         mine += c;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_count(const uint8_t* __r
     if (threadIdx.x == 0) counters[C_NEWLINES] = total;
 }
 
-__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_index(const uint8_t* __restrict__ text, uint32_t n_bytes, uint32_t n_tiles, uint32_t tpb,
+__global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_index(const uint16_t* __restrict__ tile_masks, uint32_t n_tiles, uint32_t tpb,
                                                               const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ block_base,
                                                               uint32_t max_records, uint32_t* __restrict__ line_end)
 {
@@ -146,31 +150,30 @@ __global__ void __launch_bounds__(IDX_WARPS * 32) k_vcf_index(const uint8_t* __r
         // line feeds of this block's tiles before `tile`
         uint32_t before = 0;
         for (uint32_t t = t0 + lane; t < tile; t += 32) before += tile_count[t];
-        uint32_t idx = bbase + __reduce_add_sync(0xffffffffu, before);
+        const uint32_t idx = bbase + __reduce_add_sync(0xffffffffu, before);
         if (idx >= max_records) return;
-        uint32_t m[WT_CHUNKS];
-        load_warp_tile(text, n_bytes, tile, lane, m);
+        // this lane's eight 16-byte chunks are contiguous in the text: masks [8 * lane, 8 * lane + 8) of the tile
+        const uint4 mk = __ldg(reinterpret_cast<const uint4*>(tile_masks + (size_t)tile * (WT_CHUNKS * 32)) + lane);
+        const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+        const uint32_t cnt = __popc(mk.x) + __popc(mk.y) + __popc(mk.z) + __popc(mk.w);
+        if (!__ballot_sync(0xffffffffu, cnt != 0)) continue;
+        uint32_t incl = cnt;
 #pragma unroll
-        for (int j = 0; j < WT_CHUNKS; ++j) {
-            const uint32_t any = __ballot_sync(0xffffffffu, m[j] != 0);
-            if (!any) continue;
-            const uint32_t cnt = __popc(m[j]);
-            uint32_t incl = cnt;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        uint32_t k = idx + incl - cnt;
+        const uint32_t off = tile * (uint32_t)WT_BYTES + (uint32_t)lane * 128u;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            uint32_t k = idx + incl - cnt;
-            uint32_t mm = m[j];
-            const uint32_t off = tile * (uint32_t)WT_BYTES + (uint32_t)j * 512u + (uint32_t)lane * 16u;
+        for (int q = 0; q < 4; ++q) {
+            uint32_t mm = w[q];
             while (mm) {
                 const int b = __ffs(mm) - 1;
                 mm &= mm - 1;
-                if (k < max_records) line_end[k] = off + b;
+                if (k < max_records) line_end[k] = off + (uint32_t)q * 32u + (uint32_t)b;
                 ++k;
             }
-            idx += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
@@ -827,6 +830,7 @@ int parser_create(int device, int S, int rm_invar, int n_sms, int64_t max_text, 
     PCK(cudaMemset(ps->d_text, 0, padded));
     PCK(cudaMalloc((void**)&ps->d_line_end, ((size_t)max_records + 1) * sizeof(uint32_t)));
     PCK(cudaMalloc((void**)&ps->d_tile_count, (size_t)ps->max_tiles * sizeof(uint32_t)));
+    PCK(cudaMalloc((void**)&ps->d_tile_masks, (size_t)ps->max_tiles * (WT_CHUNKS * 32) * sizeof(uint16_t)));
     PCK(cudaMalloc((void**)&ps->d_block_base, (size_t)MAX_IDX_BLOCKS * sizeof(uint32_t)));
     PCK(cudaMalloc((void**)&ps->d_work, (size_t)max_records * sizeof(uint32_t)));
     PCK(cudaMalloc((void**)&ps->d_counters, C_COUNT * sizeof(uint32_t)));
@@ -851,6 +855,7 @@ void parser_destroy(vgl_parser* ps)
     cudaFree(ps->d_line_end);
     cudaFree(ps->d_tile_count);
     cudaFree(ps->d_block_base);
+    cudaFree(ps->d_tile_masks);
     cudaFree(ps->d_work);
     cudaFree(ps->d_counters);
     cudaFreeHost(ps->h_counters);
@@ -923,9 +928,8 @@ extern "C" int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source,
     PCK(cudaMemcpyAsync(ps->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     const uint32_t idx_grid = (uint32_t)std::min<uint64_t>((n_tiles + IDX_WARPS - 1) / IDX_WARPS, (uint64_t)std::min(ps->n_sms * 8, (int)MAX_IDX_BLOCKS));
     const uint32_t tpb = (n_tiles + idx_grid - 1) / idx_grid; // warp tiles per block, contiguous
-    k_vcf_count<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, tpb, ps->d_tile_count, ps->d_block_base, ps->d_counters);
-    k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, tpb, ps->d_tile_count, ps->d_block_base, (uint32_t)ps->max_records,
-                                                       ps->d_line_end);
+    k_vcf_count<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_text, (uint32_t)n, n_tiles, tpb, ps->d_tile_count, ps->d_tile_masks, ps->d_block_base, ps->d_counters);
+    k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_tile_masks, n_tiles, tpb, ps->d_tile_count, ps->d_block_base, (uint32_t)ps->max_records, ps->d_line_end);
     RecMeta* meta = reinterpret_cast<RecMeta*>(ps->d_meta);
     k_vcf_hdr<<<ps->n_sms * 8, HDR_THREADS, 0, st>>>(ps->d_text, ps->d_line_end, ps->S, gt_source, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_sites, ps->d_work);
     {   // k_vcf_cells: one thread per four samples of every record that can be fixed-width (each is at least 4 * S bytes long)

@@ -201,6 +201,7 @@ struct vgl_parser {
     uint8_t *h_text = nullptr, *d_text = nullptr, *d_rows = nullptr;
     uint32_t *d_line_end = nullptr, *d_counters = nullptr, *h_counters = nullptr;
     uint32_t *d_tile_count = nullptr, *d_block_base = nullptr, *d_work = nullptr;
+    uint16_t* d_tile_masks = nullptr; // one line-feed mask per 16 bytes of text
     vgl_in_site *d_sites = nullptr, *h_sites = nullptr;
     int32_t* d_row_map = nullptr;
     void* d_meta = nullptr; // RecMeta [max_records] (vcfin.cu)
