@@ -43,7 +43,8 @@ def test_ctypes_mirror_has_the_compiled_layout(tmp_path):
 #include <stddef.h>
 #include "vgl.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vgl_params), offsetof(vgl_params, host_output), offsetof(vgl_params, bcf_dict),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vgl_in_site), offsetof(vgl_in_site, allele_acgt),
+         sizeof(vgl_parse_out), offsetof(vgl_parse_out, sites), sizeof(vgl_gvcf_rec), sizeof(vgl_gvcf_out), sizeof(vgl_params), offsetof(vgl_params, host_output), offsetof(vgl_params, bcf_dict),
          offsetof(vgl_params, bcf_blob_bytes_per_site), sizeof(vgl_batch_out), offsetof(vgl_batch_out, bcf), offsetof(vgl_batch_out, bcf_bytes),
          sizeof(vgl_bcf_site_in), sizeof(vgl_site_out));
   return 0; }
@@ -52,7 +53,8 @@ int main(void) {
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     P, B = capi.VglParams, capi.VglBatchOut
-    want = [C.sizeof(P), P.host_output.offset, P.bcf_dict.offset, P.bcf_blob_bytes_per_site.offset, C.sizeof(B), B.bcf.offset,
+    want = [capi.IN_SITE_DTYPE.itemsize, capi.IN_SITE_DTYPE.fields["allele_acgt"][1], C.sizeof(capi.VglParseOut), capi.VglParseOut.sites.offset,
+            capi.GVCF_REC_DTYPE.itemsize, C.sizeof(capi.VglGvcfOut), C.sizeof(P), P.host_output.offset, P.bcf_dict.offset, P.bcf_blob_bytes_per_site.offset, C.sizeof(B), B.bcf.offset,
             B.bcf_bytes.offset, C.sizeof(capi.VglBcfSiteIn), C.sizeof(capi.VglSiteOut)]
     assert got == want
 
