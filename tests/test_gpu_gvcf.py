@@ -148,3 +148,61 @@ def test_batches_stitched_equal_one_piece():
                 (idx[o["first"]], o["start"], o["end"], o["min_dp"], o["range"], len(o["members"]))
             assert np.array_equal(g["dp"], o["dp"]) and np.array_equal(g["pl"].reshape(-1), o["pl"])
     ctx.close()
+
+
+def test_cpp_host_driver_gvcf(tmp_path):
+    """the C++ mirror (vgl::VcfTextSimulator + BatchSimulator::enable_gvcf + GvcfStitcher) reads a VCF, explodes it, merges on the
+    device and stitches across batches of 4 sites: same record sequence and block values as the Python host path"""
+    import os
+    import subprocess
+    from vcfgl_b200 import vcfinput
+    exe = os.path.join(gu.ROOT, "vcfgl_b200", "host", "example_driver")
+    if not os.path.exists(exe):
+        pytest.skip("example_driver not built")
+    S, n_rec, L = 4, 12, 90
+    hap = synth.sfs_genotypes(n_rec, S, 31)
+    pos = synth.positions(n_rec, L, 31)
+    path = tmp_path / "in.vcf"
+    synth.write_vcf(str(path), hap, pos, L)
+    env = dict(os.environ, VGL_VCF_IN=str(path), VGL_EXPLODE="1", VGL_GVCF_DPS="1,2,4", VGL_BATCH="4")
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = [l.split("\t") for l in r.stdout.splitlines() if "skipped(" not in l]
+    # Python host path on the driver's parameters
+    a = vargs.parse_args("--seed 42 -d 4 -e 0.01 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,2,4 -addGL 1 -addPL 1 -addFormatAD 1 -addInfoDP 1".split())
+    buf = path.read_bytes()
+    hdr = vcfinput.read_header(buf)
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=4, n_slots=2))
+    ps = ctx.parser(1 << 16, 16)
+    st = gvcf.GvcfStitcher()
+    want = []
+
+    def emit(rec, sites_of):
+        if rec["kind"] == "site":
+            p, o = sites_of[rec["site"]]
+            A = o["n_alleles"]
+            want.append(["1", str(p + 1), "DP=%d" % o["info_dp"]] +
+                        ["%d:%s" % (o["fmt_dp"][s], ",".join(str(x) for x in o["fmt_ad"].reshape(S, A)[s])) for s in range(S)])
+        else:
+            want.append(["1", str(rec["start"] + 1), "BLOCK", "END=%d" % (rec["end"] + 1), "MIN_DP=%d" % rec["min_dp"], "n=%d" % rec["n_members"]] +
+                        ["%d:%d,%d,%d" % (rec["dp"][s], *rec["pl"][s]) for s in range(S)])
+    sites_of, base = {}, 0
+    for run, b in vcfinput.simulate_vcf_text(ctx, ps, buf[hdr.body_offset:], gt_source=0, explode=1, contigs=hdr.contigs):
+        for i in range(b.n_sites):
+            o = b.site(i)
+            sites_of[base + i] = (int(run.pos[i]), {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in o.items()})
+        rid = np.zeros(b.n_sites, np.int32)
+        for rec in st.feed(ctx.gvcf_merge(run.slot, rid, run.pos.astype(np.int32), [1, 2, 4]), rid, run.pos):
+            emit(rec, sites_of)
+        base += b.n_sites
+    for rec in st.finish():
+        emit(rec, sites_of)
+    assert base == L and any(w[2] == "BLOCK" for w in want)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        if w[2] == "BLOCK":
+            assert [g[0], g[1], g[3], g[4], g[5], g[6]] + g[8:] == w, (g, w)
+        else:
+            assert [g[0], g[1], g[3]] + g[6:] == w, (g, w)
+    ps.close()
+    ctx.close()

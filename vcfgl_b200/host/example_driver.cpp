@@ -22,6 +22,7 @@ int main(int argc, char** argv)
     p.adjust_by = 0.499;
     p.do_unobserved = 1;
     p.tag_mask = VGL_TAG_GL | VGL_TAG_PL | VGL_TAG_FMT_DP | VGL_TAG_FMT_AD | VGL_TAG_INFO_DP;
+    if (getenv("VGL_GVCF_DPS")) p.do_gvcf = 1;
     p.i16_mapq = 20;
     p.max_batch_sites = 4;
     p.n_slots = 2;
@@ -43,6 +44,21 @@ int main(int argc, char** argv)
                 }
                 printf("\n");
             });
+            if (const char* dps = getenv("VGL_GVCF_DPS")) { // -doGVCF 1 --gvcf-dps a,b,c: blocks merged on the device
+                std::vector<int32_t> v;
+                for (const char* q = dps; *q;) {
+                    v.push_back(atoi(q));
+                    while (*q && *q != ',') ++q;
+                    if (*q == ',') ++q;
+                }
+                sim.enable_gvcf(v, [&](const vgl::GvcfStitcher::Block& b) {
+                    const vgl::VcfTextSimulator::Site* st = static_cast<const vgl::VcfTextSimulator::Site*>(b.user);
+                    printf("%s\t%ld\t%s\tBLOCK\tEND=%ld\tMIN_DP=%d\tn=%d\tDP:PL", st->contig.c_str(), (long)b.start + 1, b.alleles.c_str(), (long)b.end + 1, b.min_dp,
+                           b.n_members);
+                    for (int s = 0; s < (int)b.dp.size(); ++s) printf("\t%d:%d,%d,%d", b.dp[s], b.pl[3 * s], b.pl[3 * s + 1], b.pl[3 * s + 2]);
+                    printf("\n");
+                });
+            }
             sim.run(f);
             fclose(f);
             fprintf(stderr, "sites simulated: %ld, input-side skips: %ld\n", (long)sim.n_sites(), (long)sim.n_skipped_input());

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <functional>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -53,6 +54,91 @@ struct SimRecordView {
     // current_size_bcf_tag_number[] equivalents (bcf_utils.h:25-36)
     int size_fmt_G() const { return nSamples * nGenotypes; }
     int size_fmt_R() const { return nSamples * nAlleles; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// gVCF (-doGVCF 1): the record sequence of a run from the device's per-batch merge (vgl_gvcf_merge).  What is left of
+// prepare_gvcf_block() (bcf_utils.cpp:662-942) on the host is the seam between batches: a batch's first block continues
+// the block still open from the batch before under the reference's own three conditions (same contig, pos <= end + 1,
+// same dp range: bcf_utils.cpp:711, 719, 790), with the same minima (:838-866).
+//
+//   reference                                            here
+//   ---------                                            ----
+//   write_record_values(sim) per site (vcfgl.cpp:165)    feed() once per batch, after vgl_wait + vgl_gvcf_merge
+//   GVCF_WRITE_SIMREC                                    on_site(global site index): write the site's own record
+//   GVCF_FLUSH_BLOCK + grec (bcf_utils.cpp:876-905)      on_block(Block): alleles / QS from site `first`, END, MIN_DP, DP, PL
+//   write_record_values(NULL) at the end (vcfgl.cpp:169) finish()
+class GvcfStitcher {
+public:
+    struct Block {
+        int64_t first = 0;   // global index of the founder site
+        int32_t rid = 0;
+        int64_t start = 0, end = 0; // 0-based positions of the first / last member
+        int32_t min_dp = 0, dp_range = 0, n_members = 0;
+        std::vector<int32_t> dp, pl; // [S], [S * 3] (empty without PL)
+        std::string alleles;         // founder's allele string and INFO/QS, filled by the annotate hook of feed()
+        std::vector<float> qs;
+        void* user = nullptr;        // founder's user pointer
+    };
+    GvcfStitcher(int n_samples, std::function<void(int64_t)> on_site, std::function<void(const Block&)> on_block)
+        : S_(n_samples), on_site_(std::move(on_site)), on_block_(std::move(on_block))
+    {
+    }
+
+    // annotate(block, founder's site index in this batch): called when a block is opened, to copy what the block record takes
+    // from its founder (bcf_utils.cpp:817-832) while the batch is still in memory
+    void feed(const vgl_gvcf_out& o, const vgl_gvcf_site_in* sites, int32_t n_sites, const std::function<void(Block&, int32_t)>& annotate = nullptr)
+    {
+        for (int32_t k = 0; k < o.n_recs; ++k) {
+            const vgl_gvcf_rec& r = o.recs[k];
+            if (r.n_members == 0) {
+                flush();
+                on_site_(base_ + r.first_site);
+                continue;
+            }
+            const vgl_gvcf_site_in &f = sites[r.first_site], &l = sites[r.last_site];
+            const int32_t* dp = o.dp + (size_t)r.plane * S_;
+            const int32_t* pl = o.pl ? o.pl + (size_t)r.plane * S_ * 3 : nullptr;
+            if (open_ && k == 0 && cur_.rid == f.rid && f.pos <= cur_.end + 1 && cur_.dp_range == r.dp_range) {
+                cur_.end = l.pos;
+                cur_.min_dp = std::min(cur_.min_dp, r.min_dp);
+                cur_.n_members += r.n_members;
+                for (int s = 0; s < S_; ++s) {
+                    cur_.dp[s] = std::min(cur_.dp[s], dp[s]);
+                    if (pl && !cur_.pl.empty()) {
+                        int32_t* g = &cur_.pl[3 * (size_t)s];
+                        const int32_t* m = pl + 3 * (size_t)s;
+                        if (m[1] < g[1] || (m[1] == g[1] && m[2] < g[2])) g[1] = m[1], g[2] = m[2];
+                    }
+                }
+                continue;
+            }
+            flush();
+            cur_.first = base_ + r.first_site;
+            cur_.rid = f.rid, cur_.start = f.pos, cur_.end = l.pos;
+            cur_.min_dp = r.min_dp, cur_.dp_range = r.dp_range, cur_.n_members = r.n_members;
+            cur_.dp.assign(dp, dp + S_);
+            if (pl) cur_.pl.assign(pl, pl + 3 * (size_t)S_);
+            else cur_.pl.clear();
+            if (annotate) annotate(cur_, r.first_site);
+            open_ = true;
+        }
+        base_ += n_sites;
+    }
+    void finish() { flush(); }
+
+private:
+    void flush()
+    {
+        if (open_) on_block_(cur_);
+        open_ = false;
+    }
+    int S_;
+    std::function<void(int64_t)> on_site_;
+    std::function<void(const Block&)> on_block_;
+    Block cur_;
+    bool open_ = false;
+    int64_t base_ = 0;
 };
 
 // allele string of a simulated site; no-reads sites follow simulate_site_with_no_reads (vcfgl.cpp:228-315)
@@ -135,11 +221,25 @@ public:
     vgl_ctx* context() { return ctx_; }
     const vgl_params& params() const { return prm_; }
 
+    // -doGVCF 1 (write_record_values + prepare_gvcf_block, vcfgl.cpp:165-207, bcf_utils.cpp:662-942): every finished batch is
+    // merged on the device (vgl_gvcf_merge) and stitched to the batch before it.  `where(user)` gives a site's (rid, pos).
+    // Sites that end up inside a block are not delivered through the record callback; the block is, through on_block, in
+    // output order between the regular records (its alleles / qs / user are the founder's).  Call before the first push.
+    void enable_gvcf(std::vector<int32_t> gvcf_dps, std::function<vgl_gvcf_site_in(void*)> where,
+                     std::function<void(const GvcfStitcher::Block&)> on_block)
+    {
+        gvcf_dps_ = std::move(gvcf_dps);
+        where_ = std::move(where);
+        stitch_.reset(new GvcfStitcher(prm_.n_samples, [this](int64_t g) { deliver(*cur_out_, *cur_pending_, (int)(g - cur_pending_->first)); },
+                                       std::move(on_block)));
+    }
+
     // end of input: run the partial batch and deliver everything outstanding
     void finish()
     {
         if (fill_ > 0) submit_current();
         for (int k = 0; k < prm_.n_slots; ++k) drain((cur_ + k) % prm_.n_slots);
+        if (stitch_) stitch_->finish(); // the block still open at the end (vcfgl.cpp:169-177)
     }
 
     int64_t sites_pushed() const { return next_site_; }
@@ -183,10 +283,34 @@ private:
         vgl_batch_out out;
         check(vgl_wait(ctx_, slot, &out), "vgl_wait");
         if (out.status != VGL_OK) throw Error(out.status, vgl_strerror(out.status));
+        if (stitch_) {
+            std::vector<vgl_gvcf_site_in> sin((size_t)out.n_sites);
+            for (int i = 0; i < out.n_sites; ++i) sin[(size_t)i] = where_(p.users[(size_t)i]);
+            vgl_gvcf_out g;
+            check(vgl_gvcf_merge(ctx_, slot, sin.data(), gvcf_dps_.data(), (int32_t)gvcf_dps_.size(), &g), "vgl_gvcf_merge");
+            cur_out_ = &out;
+            cur_pending_ = &p;
+            stitch_->feed(g, sin.data(), out.n_sites, [&](GvcfStitcher::Block& b, int32_t site) {
+                const vgl_site_out& so = out.sites[site];
+                b.alleles = alleles_string(so, prm_.do_unobserved, prm_.do_gvcf);
+                b.qs.assign(so.qs, so.qs + so.n_alleles);
+                b.user = p.users[(size_t)site];
+            });
+            for (int i = 0; i < out.n_sites; ++i) // skipped sites are reported as before
+                if (out.sites[i].skip_code != 0) deliver(out, p, i);
+        } else {
+            for (int i = 0; i < out.n_sites; ++i) deliver(out, p, i);
+        }
+        p.in_flight = false;
+    }
+
+    // one site's results -> the record callback
+    void deliver(const vgl_batch_out& out, const Pending& p, int i)
+    {
         SimRecordView v;
         v.nSamples = out.n_samples;
         const int S = out.n_samples;
-        for (int i = 0; i < out.n_sites; ++i) {
+        {
             const vgl_site_out& s = out.sites[i];
             v.site_id = p.first + i;
             v.user = p.users[(size_t)i];
@@ -233,7 +357,6 @@ private:
             v.i16_arr = s.i16;
             cb_(v);
         }
-        p.in_flight = false;
     }
 
     static const int32_t* widen(std::vector<int32_t>& dst, const void* src, int bits, size_t off, size_t n)
@@ -249,6 +372,11 @@ private:
     Callback cb_;
     vgl_ctx* ctx_ = nullptr;
     std::vector<Pending> pending_;
+    std::unique_ptr<GvcfStitcher> stitch_;
+    std::vector<int32_t> gvcf_dps_;
+    std::function<vgl_gvcf_site_in(void*)> where_;
+    const vgl_batch_out* cur_out_ = nullptr;
+    const Pending* cur_pending_ = nullptr;
     uint8_t* in_ = nullptr;
     int cur_ = 0;
     int32_t fill_ = 0;
@@ -386,6 +514,7 @@ public:
         std::string contig;
         int64_t pos = 0;     // 0-based
         int64_t record = -1; // >= 0: n-th record of the input; -1: -explode site
+        int32_t rid = 0;     // running number of the contig (changes when CHROM changes)
     };
     using Callback = std::function<void(const SimRecordView&, const Site&)>;
 
@@ -401,6 +530,13 @@ public:
     VcfTextSimulator(const VcfTextSimulator&) = delete;
     VcfTextSimulator& operator=(const VcfTextSimulator&) = delete;
 
+    // -doGVCF 1: blocks through on_block, regular records through the constructor's callback (BatchSimulator::enable_gvcf)
+    void enable_gvcf(std::vector<int32_t> gvcf_dps, std::function<void(const GvcfStitcher::Block&)> on_block)
+    {
+        gvcf_dps_ = std::move(gvcf_dps);
+        on_block_ = std::move(on_block);
+    }
+
     int64_t n_sites() const { return n_sites_; }
     int64_t n_skipped_input() const { return n_skipped_; }
     const std::vector<std::string>& samples() const { return samples_; }
@@ -411,6 +547,8 @@ public:
         if (prm_.n_samples == 0) prm_.n_samples = (int32_t)samples_.size();
         if ((size_t)prm_.n_samples != samples_.size()) throw Error(VGL_EINVAL, "n_samples does not match the #CHROM line");
         BatchSimulator sim(prm_, [&](const SimRecordView& v) { cb_(v, *static_cast<const Site*>(v.user)); });
+        if (!gvcf_dps_.empty())
+            sim.enable_gvcf(gvcf_dps_, [](void* u) { const Site* st = static_cast<const Site*>(u); return vgl_gvcf_site_in{st->rid, (int32_t)st->pos}; }, on_block_);
         const int32_t cap = sim.params().max_batch_sites;
         const int64_t text_cap = (int64_t)cap * (4 * (int64_t)prm_.n_samples + 64) + (1 << 16);
         int rc = vgl_parser_create(sim.context(), text_cap, cap, &ps_);
@@ -459,6 +597,7 @@ public:
                 if (contig_.size() != clen || memcmp(contig_.data(), line, clen) != 0) { // contig change (vcfgl.cpp:1484-1488)
                     contig_.assign(line, clen);
                     n_in_contig_ = 0;
+                    ++rid_;
                 }
                 last_acgt0 = r.allele_acgt[0];
                 if (explode_) {
@@ -509,6 +648,7 @@ private:
         st.contig = contig_;
         st.pos = pos;
         st.record = rec_no;
+        st.rid = rid_;
         ring_[ring_at_].push_back(std::move(st));
         map_.push_back(src);
         if ((int32_t)map_.size() == cap) flush(sim, cap);
@@ -571,88 +711,12 @@ private:
     std::string contig_;
     int64_t n_in_contig_ = 0, n_sites_ = 0, n_skipped_ = 0;
     int fill_acgt_ = -1;
+    int32_t rid_ = -1;
+    std::vector<int32_t> gvcf_dps_;
+    std::function<void(const GvcfStitcher::Block&)> on_block_;
     std::vector<std::vector<Site>> ring_;
     size_t ring_at_ = 0;
     std::vector<int32_t> map_;
-};
-
-// ---------------------------------------------------------------------------------------------------------------
-// gVCF (-doGVCF 1): the record sequence of a run from the device's per-batch merge (vgl_gvcf_merge).  What is left of
-// prepare_gvcf_block() (bcf_utils.cpp:662-942) on the host is the seam between batches: a batch's first block continues
-// the block still open from the batch before under the reference's own three conditions (same contig, pos <= end + 1,
-// same dp range: bcf_utils.cpp:711, 719, 790), with the same minima (:838-866).
-//
-//   reference                                            here
-//   ---------                                            ----
-//   write_record_values(sim) per site (vcfgl.cpp:165)    feed() once per batch, after vgl_wait + vgl_gvcf_merge
-//   GVCF_WRITE_SIMREC                                    on_site(global site index): write the site's own record
-//   GVCF_FLUSH_BLOCK + grec (bcf_utils.cpp:876-905)      on_block(Block): alleles / QS from site `first`, END, MIN_DP, DP, PL
-//   write_record_values(NULL) at the end (vcfgl.cpp:169) finish()
-class GvcfStitcher {
-public:
-    struct Block {
-        int64_t first = 0;   // global index of the founder site
-        int32_t rid = 0;
-        int64_t start = 0, end = 0; // 0-based positions of the first / last member
-        int32_t min_dp = 0, dp_range = 0, n_members = 0;
-        std::vector<int32_t> dp, pl; // [S], [S * 3] (empty without PL)
-    };
-    GvcfStitcher(int n_samples, std::function<void(int64_t)> on_site, std::function<void(const Block&)> on_block)
-        : S_(n_samples), on_site_(std::move(on_site)), on_block_(std::move(on_block))
-    {
-    }
-
-    void feed(const vgl_gvcf_out& o, const vgl_gvcf_site_in* sites, int32_t n_sites)
-    {
-        for (int32_t k = 0; k < o.n_recs; ++k) {
-            const vgl_gvcf_rec& r = o.recs[k];
-            if (r.n_members == 0) {
-                flush();
-                on_site_(base_ + r.first_site);
-                continue;
-            }
-            const vgl_gvcf_site_in &f = sites[r.first_site], &l = sites[r.last_site];
-            const int32_t* dp = o.dp + (size_t)r.plane * S_;
-            const int32_t* pl = o.pl ? o.pl + (size_t)r.plane * S_ * 3 : nullptr;
-            if (open_ && k == 0 && cur_.rid == f.rid && f.pos <= cur_.end + 1 && cur_.dp_range == r.dp_range) {
-                cur_.end = l.pos;
-                cur_.min_dp = std::min(cur_.min_dp, r.min_dp);
-                cur_.n_members += r.n_members;
-                for (int s = 0; s < S_; ++s) {
-                    cur_.dp[s] = std::min(cur_.dp[s], dp[s]);
-                    if (pl && !cur_.pl.empty()) {
-                        int32_t* g = &cur_.pl[3 * (size_t)s];
-                        const int32_t* m = pl + 3 * (size_t)s;
-                        if (m[1] < g[1] || (m[1] == g[1] && m[2] < g[2])) g[1] = m[1], g[2] = m[2];
-                    }
-                }
-                continue;
-            }
-            flush();
-            cur_.first = base_ + r.first_site;
-            cur_.rid = f.rid, cur_.start = f.pos, cur_.end = l.pos;
-            cur_.min_dp = r.min_dp, cur_.dp_range = r.dp_range, cur_.n_members = r.n_members;
-            cur_.dp.assign(dp, dp + S_);
-            if (pl) cur_.pl.assign(pl, pl + 3 * (size_t)S_);
-            else cur_.pl.clear();
-            open_ = true;
-        }
-        base_ += n_sites;
-    }
-    void finish() { flush(); }
-
-private:
-    void flush()
-    {
-        if (open_) on_block_(cur_);
-        open_ = false;
-    }
-    int S_;
-    std::function<void(int64_t)> on_site_;
-    std::function<void(const Block&)> on_block_;
-    Block cur_;
-    bool open_ = false;
-    int64_t base_ = 0;
 };
 
 } // namespace vgl

@@ -78,6 +78,7 @@ class SiteRun:
     contig: str
     pos: np.ndarray
     src: np.ndarray
+    slot: int = -1       # set by simulate_vcf_text: the slot the batch ran on (valid until the consumer asks for the next batch)
 
 
 @dataclass
@@ -205,6 +206,7 @@ def simulate_vcf_text(ctx: capi.Context, parser: capi.Parser, body: bytes, *, gt
     def drain(keep: int):
         while len(pending) > keep:
             sl, run = pending.pop(0)
+            run.slot = sl
             yield run, ctx.wait(sl)
 
     def submit(run: SiteRun):
