@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 6
+#define VGL_ABI_VERSION 7
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -404,6 +404,17 @@ typedef struct vgl_gvcf_out {
 
 /* synchronous; sites: host array [n_sites of the slot's last batch]; gvcf_dps: ascending thresholds of --gvcf-dps */
 int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* sites, const int32_t* gvcf_dps, int32_t n_gvcf_dps, vgl_gvcf_out* out);
+
+/* On-device genotype-call discordance of the slot's last (waited) batch: the hom / het comparison of
+ * misc/gtDiscordance.cpp:11-15 between the call implied by the simulated likelihoods -- the genotype with the single largest
+ * GL; a tie is no call and counts as discordant -- and the true genotype, over the cells of written sites with INFO/DP > 0 and
+ * FORMAT/DP > 0.  Needs the GL tag and FORMAT/DP.  Synchronous; 60 bytes read per cell, 32 bytes returned. */
+typedef struct vgl_discordance_out {
+    int64_t n_hom, n_hom_discordant; /* cells whose true genotype is homozygous / of those, calls that differ */
+    int64_t n_het, n_het_discordant;
+    float ms_kernel;
+} vgl_discordance_out;
+int vgl_discordance(vgl_ctx* ctx, int slot, vgl_discordance_out* out);
 
 const char* vgl_strerror(int status);
 const char* vgl_last_error(const vgl_ctx* ctx);

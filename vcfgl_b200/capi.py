@@ -20,7 +20,7 @@ if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same AB
     LIB_PATH = os.environ["VGL_LIB"]
 
 VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW, VGL_EMISSING = 0, -1, -2, -3, -4, -5, -6, -7, -8
-ABI_VERSION = 6
+ABI_VERSION = 7
 HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF = 0, 1, 2, 3
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
@@ -30,7 +30,7 @@ I32_MISSING = -(2 ** 31)
 EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_bcf_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
            "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
            "vgl_last_error", "vgl_abi_version", "vgl_native_kernels",
-           "vgl_gvcf_merge", "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parser_rows", "vgl_place_rows"]
+           "vgl_gvcf_merge", "vgl_discordance", "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parser_rows", "vgl_place_rows"]
 
 SOURCE_BINARY, SOURCE_ACGT = 0, 1
 PARSE_FINAL, PARSE_TEXT_ON_DEVICE = 1, 2
@@ -50,6 +50,11 @@ GVCF_REC_DTYPE = np.dtype([("first_site", "<i4"), ("last_site", "<i4"), ("n_memb
 class VglGvcfOut(C.Structure):
     _fields_ = [("n_recs", C.c_int32), ("n_blocks", C.c_int32), ("recs", C.c_void_p), ("dp", C.c_void_p), ("pl", C.c_void_p),
                 ("ms_kernels", C.c_float)]
+
+
+class VglDiscordanceOut(C.Structure):
+    _fields_ = [("n_hom", C.c_int64), ("n_hom_discordant", C.c_int64), ("n_het", C.c_int64), ("n_het_discordant", C.c_int64),
+                ("ms_kernel", C.c_float)]
 
 
 class VglParseOut(C.Structure):
@@ -165,6 +170,7 @@ def load():
     L.vgl_last_error.restype = C.c_char_p
     L.vgl_abi_version.restype = C.c_int
     L.vgl_gvcf_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(VglGvcfOut)]
+    L.vgl_discordance.argtypes = [C.c_void_p, C.c_int, C.POINTER(VglDiscordanceOut)]
     L.vgl_parser_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
     L.vgl_parser_destroy.argtypes = [C.c_void_p]
     L.vgl_parser_destroy.restype = None
@@ -458,6 +464,12 @@ class Context:
         return dict(recs=arr(out.recs, out.n_recs, GVCF_REC_DTYPE), dp=arr(out.dp, out.n_blocks * S, np.int32).reshape(-1, S),
                     pl=arr(out.pl, out.n_blocks * S * 3, np.int32).reshape(-1, S, 3) if out.pl else None,
                     n_blocks=out.n_blocks, ms_kernels=out.ms_kernels)
+
+    def discordance(self, slot: int) -> dict:
+        """genotype-call discordance of the slot's last (waited) batch: {"hom": [cells, discordant], "het": [...], "ms_kernel"}"""
+        out = VglDiscordanceOut()
+        self._ck(self.L.vgl_discordance(self.h, slot, C.byref(out)))
+        return dict(hom=[out.n_hom, out.n_hom_discordant], het=[out.n_het, out.n_het_discordant], ms_kernel=out.ms_kernel)
 
     def parser(self, max_text_bytes: int, max_records: int) -> "Parser":
         return Parser(self, max_text_bytes, max_records)

@@ -66,6 +66,7 @@ struct Slot {
     unsigned long long *g_local = nullptr, *g_bsum = nullptr;
     int32_t *g_dp = nullptr, *g_pl = nullptr, *hg_dp = nullptr, *hg_pl = nullptr;
     cudaEvent_t g_ev[2] = {};
+    unsigned long long *d_disc = nullptr, *h_disc = nullptr; // vgl_discordance()
     // replay uploads (grown on demand)
     DevBuf r_depths, r_off, r_bases, r_strands, r_qs, r_adjqs, r_eprob, r_tails, r_deep_cells, r_deep_codes;
     float ms[VGL_T_COUNT] = {};
@@ -231,6 +232,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         cudaFree(s.g_counts); cudaFreeHost(s.hg_counts); cudaFree(s.g_blast); cudaFree(s.g_local); cudaFree(s.g_bsum); cudaFree(s.g_dp); cudaFree(s.g_pl); cudaFreeHost(s.hg_dp); cudaFreeHost(s.hg_pl);
         for (auto& e : s.g_ev)
             if (e) cudaEventDestroy(e);
+        cudaFree(s.d_disc); cudaFreeHost(s.h_disc);
         cudaFreeHost(s.h_gt); cudaFreeHost(s.h_sites); cudaFreeHost(s.h_totals); cudaFreeHost(s.h_dp);
         cudaFreeHost(s.h_gl); cudaFreeHost(s.h_gp); cudaFreeHost(s.h_pl);
         cudaFreeHost(s.h_ad); cudaFreeHost(s.h_adf); cudaFreeHost(s.h_adr);
@@ -501,6 +503,36 @@ extern "C" int vgl_set_stream(vgl_ctx* ctx, int slot, void* cuda_stream)
     return VGL_OK;
 }
 
+// ---- discordance summary (discord.cu) ----
+extern "C" int vgl_discordance(vgl_ctx* ctx, int slot, vgl_discordance_out* out)
+{
+    if (!ctx || !out || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
+    const vgl_params& prm = ctx->prm;
+    Slot& s = ctx->slots[slot];
+    if (!s.submitted || !s.waited) return fail(ctx, VGL_ESTATE, "vgl_discordance: call vgl_wait on the slot first");
+    if (!s.d_gl || !(prm.tag_mask & VGL_TAG_FMT_DP) || prm.depth_mode == VGL_DEPTH_INF)
+        return fail(ctx, VGL_EINVAL, "vgl_discordance: needs the GL tag and FORMAT/DP of a simulated batch");
+    CK(cudaSetDevice(prm.device_id));
+    cudaStream_t st = s.stream;
+    if (!s.g_ev[0]) for (auto& e : s.g_ev) CK(cudaEventCreate(&e));
+    if (!s.d_disc) {
+        CK(cudaMalloc((void**)&s.d_disc, 4 * sizeof(unsigned long long)));
+        CK(cudaHostAlloc((void**)&s.h_disc, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    }
+    CK(cudaMemsetAsync(s.d_disc, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaEventRecord(s.g_ev[0], st));
+    launch_discordance(s.d_sites, s.d_gt, s.d_dp, s.d_gl, prm.n_samples, s.n_sites, s.d_disc, st, ctx->n_sms);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s.g_ev[1], st));
+    CK(cudaMemcpyAsync(s.h_disc, s.d_disc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->n_hom = (int64_t)s.h_disc[0], out->n_hom_discordant = (int64_t)s.h_disc[1];
+    out->n_het = (int64_t)s.h_disc[2], out->n_het_discordant = (int64_t)s.h_disc[3];
+    cudaEventElapsedTime(&out->ms_kernel, s.g_ev[0], s.g_ev[1]);
+    return VGL_OK;
+}
+
 // ---- gVCF block merger (gvcf.cu) ----
 extern "C" int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* sites, const int32_t* gvcf_dps, int32_t n_gvcf_dps, vgl_gvcf_out* out)
 {
@@ -534,8 +566,8 @@ extern "C" int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* si
             CK(cudaMalloc((void**)&s.g_pl, B * S * 3 * sizeof(int32_t)));
             CK(cudaHostAlloc((void**)&s.hg_pl, B * S * 3 * sizeof(int32_t), cudaHostAllocDefault));
         }
-        for (auto& e : s.g_ev) CK(cudaEventCreate(&e));
     }
+    if (!s.g_ev[0]) for (auto& e : s.g_ev) CK(cudaEventCreate(&e));
     cudaStream_t st = s.stream;
     const int32_t n = s.n_sites;
     CK(cudaMemcpyAsync(s.g_sin, sites, (size_t)n * sizeof(vgl_gvcf_site_in), cudaMemcpyHostToDevice, st));

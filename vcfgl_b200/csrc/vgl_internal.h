@@ -160,6 +160,10 @@ void launch_draws(const DevParams& p, cudaStream_t st, const int64_t* off, uint8
 void launch_truth_site(const DevParams& p, cudaStream_t st, int n_sms);
 void launch_truth_emit(const DevParams& p, cudaStream_t st, int n_sms);
 
+// discordance summary (discord.cu)
+void launch_discordance(const vgl_site_out* sites, const uint8_t* gt, const int32_t* dp, const float* gl, int32_t S, int32_t n_sites,
+                        unsigned long long* counts, cudaStream_t st, int n_sms);
+
 // gVCF block merger (gvcf.cu)
 struct GvcfDps {
     int32_t n;
