@@ -2,7 +2,7 @@
 //
 //   k_vcf_count / k_vcf_scan / k_vcf_index   positions of the line feeds = the record index
 //   k_vcf_hdr     one thread per record: the nine fixed columns of records whose sample columns can be fixed-width ("a|b" + tab)
-//   k_vcf_cells   one thread per four samples of those records: word compares, a 4-entry byte table, aligned 32-bit stores
+//   k_vcf_cells   one thread per eight samples of those records: word compares, a 4-entry byte table, aligned 64-bit stores
 //   k_vcf_gt      every other record, one warp per record: the nine fixed columns (POS, REF/ALT -> allele map, FORMAT -> GT index), then every
 //                 sample column's GT sub-field -> one packed byte; skip decision of --rm-invar-sites bits 1 / 2
 //   k_place_rows  genotype rows -> a slot's genotype matrix (drops skipped records, inserts -explode sites)
@@ -488,7 +488,43 @@ __global__ void __launch_bounds__(HDR_THREADS) k_vcf_hdr(const uint8_t* __restri
     }
 }
 
-// One thread per four samples of a candidate record; the groups of all records are laid end to end (G = ceil(S / 4) per
+// four columns of a candidate record (samples s0 .. s0 + 3) -> four packed bytes
+template <bool SUM>
+__device__ __forceinline__ uint32_t cells4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, int s0, int S, const RecMeta& m, bool& ok, int& sum)
+{
+    const int n = min(4, S - s0);
+    if (s0 + 4 >= S) { // the record's last columns: the line end closes the last one, columns beyond it read as "0|0"
+        const int last = S - 1 - s0;
+        x0 = last == 0 ? (x0 & 0x00FFFFFFu) | 0x09000000u : x0;
+        x1 = last == 1 ? (x1 & 0x00FFFFFFu) | 0x09000000u : last < 1 ? 0x09307C30u : x1;
+        x2 = last == 2 ? (x2 & 0x00FFFFFFu) | 0x09000000u : last < 2 ? 0x09307C30u : x2;
+        x3 = last == 3 ? (x3 & 0x00FFFFFFu) | 0x09000000u : last < 3 ? 0x09307C30u : x3;
+    }
+    const uint32_t nal = m.flags >> 8;
+    const uint32_t dmask = nal == 2 ? 0xFFFEFFFEu : 0xFFFFFFFFu;
+    const uint32_t d0 = (x0 & 0x00FF00FFu) - 0x00300030u, d1 = (x1 & 0x00FF00FFu) - 0x00300030u;
+    const uint32_t d2 = (x2 & 0x00FF00FFu) - 0x00300030u, d3 = (x3 & 0x00FF00FFu) - 0x00300030u;
+    // all four columns "a|b" + tab with a, b in {0, 1} (0 only without an ALT allele)?  one test, one table look-up each
+    const uint32_t bad = ((x0 ^ 0x09007C00u) | (x1 ^ 0x09007C00u) | (x2 ^ 0x09007C00u) | (x3 ^ 0x09007C00u)) & 0xFF00FF00u;
+    const uint32_t badd = (d0 | d1 | d2 | d3) & dmask;
+    if ((m.flags & FLAG_BIALLELIC) && (bad | badd) == 0) {
+        const uint32_t b0 = __byte_perm(m.lut, 0, ((d0 | (d0 >> 15)) & 3u) | 0x4440u);
+        const uint32_t b1 = __byte_perm(m.lut, 0, ((d1 | (d1 >> 15)) & 3u) | 0x4440u);
+        const uint32_t b2 = __byte_perm(m.lut, 0, ((d2 | (d2 >> 15)) & 3u) | 0x4440u);
+        const uint32_t b3 = __byte_perm(m.lut, 0, ((d3 | (d3 >> 15)) & 3u) | 0x4440u);
+        if (SUM) sum += __popc(d0 | (d1 << 1) | (d2 << 2) | (d3 << 3));
+        return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    // '/' separators, missing alleles, more than two alleles, or a defect
+    const uint32_t amap = (m.flags & FLAG_BIALLELIC) ? 0xEEEEEE00u | (m.lut & 0xFu) | (((m.lut >> 8) & 0xFu) << 4) : m.lut;
+    uint32_t out = slow_cell(x0, nal, amap, ok, sum);
+    if (n > 1) out |= slow_cell(x1, nal, amap, ok, sum) << 8;
+    if (n > 2) out |= slow_cell(x2, nal, amap, ok, sum) << 16;
+    if (n > 3) out |= slow_cell(x3, nal, amap, ok, sum) << 24;
+    return out;
+}
+
+// One thread per eight samples of a candidate record; the groups of all records are laid end to end (G = ceil(S / 8) per
 // record) and every warp takes a contiguous run of them, so its (record, group) position advances without divisions.
 // SUM: also accumulate the allele-index sum per record (only --rm-invar-sites 1 / 2 needs it, vcfgl.cpp:150-160).
 template <bool SUM>
@@ -504,7 +540,7 @@ __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ t
     if (first >= total) return;
     const uint32_t g_end = (uint32_t)min((unsigned long long)total, first + per_warp);
     uint32_t line0 = (uint32_t)first / G, r0 = (uint32_t)first - line0 * G; // record and group of lane 0
-    const bool rows_al = (S & 3) == 0;
+    const bool rows_al = (S & 3) == 0, rows_al8 = (S & 7) == 0;
     const int n_seg = G >= 8 ? (int)(31u / G) + 2 : 0; // records a warp step can touch (0: too many, per-lane atomics instead)
     for (uint32_t g0 = (uint32_t)first; g0 < g_end; g0 += 32) {
         const uint32_t r = r0 + (uint32_t)lane;
@@ -523,45 +559,29 @@ __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ t
         bool ok = true;
         int sum = 0;
         if (fixed) {
-            const int s0 = 4 * (int)g;
-            const uint32_t q = m.p0 + 16u * g, sh = (q & 3u) * 8u;
+            const int s0 = 8 * (int)g;
+            const uint32_t q = m.p0 + 32u * g, sh = (q & 3u) * 8u;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(text + (q & ~3u));
-            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = sh ? __ldg(w + 4) : 0u;
-            uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = __funnelshift_r(w2, w3, sh), x3 = __funnelshift_r(w3, w4, sh);
-            const int n = min(4, S - s0);
-            if (s0 + 4 >= S) { // the record's last group: the line end closes the last column, columns beyond it read as "0|0"
-                const int last = S - 1 - s0;
-                x0 = last == 0 ? (x0 & 0x00FFFFFFu) | 0x09000000u : x0;
-                x1 = last == 1 ? (x1 & 0x00FFFFFFu) | 0x09000000u : last < 1 ? 0x09307C30u : x1;
-                x2 = last == 2 ? (x2 & 0x00FFFFFFu) | 0x09000000u : last < 2 ? 0x09307C30u : x2;
-                x3 = last == 3 ? (x3 & 0x00FFFFFFu) | 0x09000000u : last < 3 ? 0x09307C30u : x3;
-            }
-            const uint32_t nal = m.flags >> 8;
-            uint32_t out;
-            const uint32_t dmask = nal == 2 ? 0xFFFEFFFEu : 0xFFFFFFFFu;
-            const uint32_t d0 = (x0 & 0x00FF00FFu) - 0x00300030u, d1 = (x1 & 0x00FF00FFu) - 0x00300030u;
-            const uint32_t d2 = (x2 & 0x00FF00FFu) - 0x00300030u, d3 = (x3 & 0x00FF00FFu) - 0x00300030u;
-            // all four columns "a|b" + tab with a, b in {0, 1} (0 only without an ALT allele)?  one test, one table look-up each
-            const uint32_t bad = ((x0 ^ 0x09007C00u) | (x1 ^ 0x09007C00u) | (x2 ^ 0x09007C00u) | (x3 ^ 0x09007C00u)) & 0xFF00FF00u;
-            const uint32_t badd = (d0 | d1 | d2 | d3) & dmask;
-            if ((m.flags & FLAG_BIALLELIC) && (bad | badd) == 0) {
-                const uint32_t b0 = __byte_perm(m.lut, 0, ((d0 | (d0 >> 15)) & 3u) | 0x4440u);
-                const uint32_t b1 = __byte_perm(m.lut, 0, ((d1 | (d1 >> 15)) & 3u) | 0x4440u);
-                const uint32_t b2 = __byte_perm(m.lut, 0, ((d2 | (d2 >> 15)) & 3u) | 0x4440u);
-                const uint32_t b3 = __byte_perm(m.lut, 0, ((d3 | (d3 >> 15)) & 3u) | 0x4440u);
-                out = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-                if (SUM) sum = __popc(d0 | (d1 << 1) | (d2 << 2) | (d3 << 3));
-            } else { // '/' separators, missing alleles, more than two alleles, or a defect
-                const uint32_t amap = (m.flags & FLAG_BIALLELIC) ? 0xEEEEEE00u | (m.lut & 0xFu) | (((m.lut >> 8) & 0xFu) << 4) : m.lut;
-                out = slow_cell(x0, nal, amap, ok, sum);
-                if (n > 1) out |= slow_cell(x1, nal, amap, ok, sum) << 8;
-                if (n > 2) out |= slow_cell(x2, nal, amap, ok, sum) << 16;
-                if (n > 3) out |= slow_cell(x3, nal, amap, ok, sum) << 24;
-            }
+            // nine independent loads: 32 bytes of columns per lane in flight
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
+            const bool second = s0 + 4 < S;
+            const uint32_t w5 = second ? __ldg(w + 5) : 0u, w6 = second ? __ldg(w + 6) : 0u, w7 = second ? __ldg(w + 7) : 0u;
+            const uint32_t w8 = second && sh ? __ldg(w + 8) : 0u;
+            const uint32_t lo = cells4<SUM>(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh),
+                                            s0, S, m, ok, sum);
+            uint32_t hi = 0;
+            if (second)
+                hi = cells4<SUM>(__funnelshift_r(w4, w5, sh), __funnelshift_r(w5, w6, sh), __funnelshift_r(w6, w7, sh), __funnelshift_r(w7, w8, sh),
+                                 s0 + 4, S, m, ok, sum);
             uint8_t* dst = rows + (size_t)line * S + s0;
-            if (rows_al) *reinterpret_cast<uint32_t*>(dst) = out;
-            else
-                for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(out >> (8 * k));
+            if (rows_al8) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+            else if (rows_al) {
+                *reinterpret_cast<uint32_t*>(dst) = lo;
+                if (second) *reinterpret_cast<uint32_t*>(dst + 4) = hi;
+            } else {
+                const int n = min(8, S - s0);
+                for (int k = 0; k < n; ++k) dst[k] = (uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)));
+            }
         }
         if (!ok && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line; // rare
         if (SUM) { // per-record allele-index sums: the lanes of one record are contiguous
@@ -932,8 +952,8 @@ extern "C" int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source,
     k_vcf_index<<<idx_grid, IDX_WARPS * 32, 0, st>>>(ps->d_tile_masks, n_tiles, tpb, ps->d_tile_count, ps->d_block_base, (uint32_t)ps->max_records, ps->d_line_end);
     RecMeta* meta = reinterpret_cast<RecMeta*>(ps->d_meta);
     k_vcf_hdr<<<ps->n_sms * 8, HDR_THREADS, 0, st>>>(ps->d_text, ps->d_line_end, ps->S, gt_source, (uint32_t)ps->max_records, ps->d_counters, meta, ps->d_sites, ps->d_work);
-    {   // k_vcf_cells: one thread per four samples of every record that can be fixed-width (each is at least 4 * S bytes long)
-        const uint32_t G = ((uint32_t)ps->S + 3u) / 4u;
+    {   // k_vcf_cells: one thread per eight samples of every record that can be fixed-width (each is at least 4 * S bytes long)
+        const uint32_t G = ((uint32_t)ps->S + 7u) / 8u;
         const uint32_t magic = G > 1 ? (uint32_t)((0x100000000ull + G - 1) / G) : 0u;
         const uint64_t max_groups = std::min<uint64_t>((uint64_t)ps->max_records, n / (4ull * (uint64_t)ps->S) + 1) * G;
         const uint32_t cells_grid = std::max(1u, (uint32_t)std::min<uint64_t>((max_groups + 255) / 256, (uint64_t)ps->n_sms * 16));
