@@ -7,11 +7,11 @@
 // values are minima over its members (MIN_DP :838-842, DP[s] :844-848, lexicographic (PL[3s+1], PL[3s+2]) :858-866).
 // So the machine is a segmented min-reduction over sites:
 //
-//   k_gvcf_key     warp per site: min FORMAT/DP over the samples -> dp range, member flag
+//   k_gvcf_key     eight lanes per site: min FORMAT/DP over the samples -> dp range, member flag
 //   k_gvcf_plan_local / _global   blocks of 1024 sites: head flags from neighbouring written sites, record ids / block
 //                  ordinals by a two-level scan
 //   k_gvcf_fin     thread per record: last member, number of members
-//   k_gvcf_reduce  warp per (block, 32 samples): per-sample minima over the members, MIN_DP
+//   k_gvcf_reduce  warp per (block, 128 samples): per-sample minima over the members, MIN_DP
 //
 // Bound: HBM -- k_gvcf_reduce reads 16 bytes (DP + 3 PL) per member cell, k_gvcf_key 4.
 #include "vgl_internal.h"
@@ -23,26 +23,39 @@ namespace {
 enum { K_KEPT = 1, K_MEMBER = 2 };
 constexpr int PLAN_THREADS = 1024;
 
+// eight lanes per site, four sites per warp at a time: a warp that walks its sites one after the other waits two dependent
+// round trips (site record, then DP row) per site, which is what bounded the first version (34 us for 131072 sites)
 __global__ void __launch_bounds__(256) k_gvcf_key(const vgl_site_out* __restrict__ sites, const int32_t* __restrict__ dp, int32_t S, int32_t n_sites,
                                                   GvcfDps dps, int2* __restrict__ key)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = gridDim.x * (blockDim.x >> 5);
-    for (int i = warp; i < n_sites; i += n_warps) {
+    const int l8 = threadIdx.x & 7;
+    const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_grp = (gridDim.x * blockDim.x) >> 3;
+    const uint32_t gmask = 0xFFu << (threadIdx.x & 24); // this group's lanes within the warp
+    for (int i = grp; i < n_sites; i += n_grp) {
         const vgl_site_out& so = sites[i];
         if (so.skip_code != 0) { // not written at all (vcfgl.cpp:1553-1558): invisible to the merger
-            if (lane == 0) key[i] = make_int2(0, 0);
+            if (l8 == 0) key[i] = make_int2(0, 0);
             continue;
         }
         int m = 0x7FFFFFFF;
         const int32_t* row = dp + (size_t)i * S;
-        for (int s = lane; s < S; s += 32) m = min(m, row[s]);
-        m = __reduce_min_sync(0xffffffffu, m);
+        if ((S & 3) == 0) { // rows are 16-byte aligned: four samples per load
+            const int4* row4 = reinterpret_cast<const int4*>(row);
+            for (int s = l8; s < (S >> 2); s += 8) {
+                const int4 v = __ldg(row4 + s);
+                m = min(m, min(min(v.x, v.y), min(v.z, v.w)));
+            }
+        } else {
+            for (int s = l8; s < S; s += 8) m = min(m, row[s]);
+        }
+        m = min(m, __shfl_xor_sync(gmask, m, 1));
+        m = min(m, __shfl_xor_sync(gmask, m, 2));
+        m = min(m, __shfl_xor_sync(gmask, m, 4));
         int r = 0;
 #pragma unroll
         for (int k = 0; k < VGL_MAX_GVCF_DPS; ++k) r += (k < dps.n && m >= dps.v[k]) ? 1 : 0; // thresholds ascend (bcf_utils.cpp:752-757)
         const bool member = so.n_alleles_observed == 1 && r >= 1 && so.n_genotypes == 3;
-        if (lane == 0) key[i] = make_int2(m, K_KEPT | (member ? K_MEMBER : 0) | (r << 8));
+        if (l8 == 0) key[i] = make_int2(m, K_KEPT | (member ? K_MEMBER : 0) | (r << 8));
     }
 }
 
@@ -193,6 +206,10 @@ __global__ void k_gvcf_fin(vgl_gvcf_rec* __restrict__ recs, const int32_t* __res
     }
 }
 
+// warp per (block, 128 samples): four independent 32-sample slices per lane keep four times the loads in flight per dependent
+// step (record -> member key -> plane offset -> values), which is what bounds this kernel
+constexpr int RED_U = 4;
+
 __global__ void __launch_bounds__(256) k_gvcf_reduce(vgl_gvcf_rec* recs, const int32_t* __restrict__ counts, const int32_t* __restrict__ blk_rec, const int2* __restrict__ key,
                                                      const vgl_site_out* __restrict__ sites, const int32_t* __restrict__ dp,
                                                      const int32_t* __restrict__ pl, int32_t S, int32_t* __restrict__ out_dp,
@@ -200,37 +217,52 @@ __global__ void __launch_bounds__(256) k_gvcf_reduce(vgl_gvcf_rec* recs, const i
 {
     const int lane = threadIdx.x & 31;
     const int n_blocks = counts[1];
-    const int chunks = (S + 31) / 32;
-    const unsigned total = (unsigned)n_blocks * (unsigned)chunks; // < 2^21 * chunks: the API bounds sites * samples
+    const int chunks = (S + 32 * RED_U - 1) / (32 * RED_U);
+    const unsigned total = (unsigned)n_blocks * (unsigned)chunks;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = gridDim.x * (blockDim.x >> 5);
     for (unsigned w = warp; w < total; w += n_warps) {
         const int blk = (int)(w / (unsigned)chunks), c = (int)(w - (unsigned)blk * (unsigned)chunks);
         const int r = blk_rec[blk];
         const vgl_gvcf_rec rec = recs[r];
-        const int s = c * 32 + lane;
-        int d = 0x7FFFFFFF, p0 = 0, p1 = 0x7FFFFFFF, p2 = 0x7FFFFFFF, md = 0x7FFFFFFF;
+        int d[RED_U], p0[RED_U], p1[RED_U], p2[RED_U], md = 0x7FFFFFFF;
+#pragma unroll
+        for (int u = 0; u < RED_U; ++u) d[u] = p1[u] = p2[u] = 0x7FFFFFFF, p0[u] = 0;
+        const int sbase = c * 32 * RED_U + lane;
         for (int i = rec.first_site; i <= rec.last_site; ++i) {
             const int2 k = key[i];
             if (!(k.y & K_KEPT)) continue;
             md = min(md, k.x);
-            if (s < S) {
-                d = min(d, dp[(size_t)i * S + s]);
-                if (pl) {
-                    const int32_t* q = pl + sites[i].g_off + 3 * (size_t)s;
-                    const int a = q[1], b = q[2];
-                    if (i == rec.first_site) p0 = q[0];
-                    if (a < p1 || (a == p1 && b < p2)) { // bcf_utils.cpp:858-866 = lexicographic minimum
-                        p1 = a;
-                        p2 = b;
-                    }
+            const int32_t* drow = dp + (size_t)i * S;
+            const int32_t* prow = pl ? pl + sites[i].g_off : nullptr;
+            int dv[RED_U], a[RED_U], b[RED_U], z[RED_U];
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) { // all loads first
+                const int s = sbase + 32 * u;
+                const bool in = s < S;
+                dv[u] = in ? drow[s] : 0x7FFFFFFF;
+                z[u] = in && prow ? prow[3 * (size_t)s] : 0;
+                a[u] = in && prow ? prow[3 * (size_t)s + 1] : 0x7FFFFFFF;
+                b[u] = in && prow ? prow[3 * (size_t)s + 2] : 0x7FFFFFFF;
+            }
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+                d[u] = min(d[u], dv[u]);
+                if (i == rec.first_site) p0[u] = z[u];
+                if (a[u] < p1[u] || (a[u] == p1[u] && b[u] < p2[u])) { // bcf_utils.cpp:858-866 = lexicographic minimum
+                    p1[u] = a[u];
+                    p2[u] = b[u];
                 }
             }
         }
-        if (s < S) {
-            out_dp[(size_t)rec.plane * S + s] = d;
-            if (pl) {
-                int32_t* o = out_pl + ((size_t)rec.plane * S + s) * 3;
-                o[0] = p0, o[1] = p1, o[2] = p2;
+#pragma unroll
+        for (int u = 0; u < RED_U; ++u) {
+            const int s = sbase + 32 * u;
+            if (s < S) {
+                out_dp[(size_t)rec.plane * S + s] = d[u];
+                if (pl) {
+                    int32_t* o = out_pl + ((size_t)rec.plane * S + s) * 3;
+                    o[0] = p0[u], o[1] = p1[u], o[2] = p2[u];
+                }
             }
         }
         if (c == 0 && lane == 0) recs[r].min_dp = md;
