@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 7
+#define VGL_ABI_VERSION 8
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -356,6 +356,16 @@ typedef struct vgl_parse_out {
 
 /* synchronous: H2D of the text, k_vcf_lines (record index), k_vcf_gt (columns, alleles, genotypes), D2H of the site records */
 int vgl_parse_vcf(vgl_parser* ps, int64_t n_bytes, int32_t gt_source, uint32_t flags, vgl_parse_out* out);
+
+/* The same for uncompressed BCF records (the reference reads VCF and BCF through the same bcf_read, vcfgl.cpp:1479): the text
+ * buffer holds the records' bytes as they follow the BCF header (BGZF already inflated by the host), rec_off[0 .. n_records]
+ * their byte offsets (record i = [rec_off[i], rec_off[i + 1]); the host finds them by hopping l_shared + l_indiv + 8), gt_key the
+ * dictionary id of FORMAT/GT in the input header (bcf_hdr_id2int(hdr, BCF_DT_ID, "GT")).  k_bcf_gt decodes the fixed fields, the
+ * allele strings and the typed GT vector (htslib/vcf.c:1535-1600 bcf_unpack, bcf_get_genotypes) and applies
+ * check_rec_alleles (vcfgl.cpp:75-163).  vgl_in_site: line_off / line_len = the record's bytes, id_off = 32,
+ * fmt_off = start of the FORMAT block, samples_off = start of the GT values; everything else as for text. */
+int vgl_parse_bcf(vgl_parser* ps, int64_t n_bytes, const uint32_t* rec_off, int32_t n_records, int32_t gt_source, int32_t gt_key, uint32_t flags,
+                  vgl_parse_out* out);
 
 /* copies genotype rows of the last parse to host memory (tests, debugging): host_dst [n_records][n_samples] */
 int vgl_parser_rows(vgl_parser* ps, int32_t first_record, int32_t n_records, uint8_t* host_dst);

@@ -20,7 +20,7 @@ if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same AB
     LIB_PATH = os.environ["VGL_LIB"]
 
 VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW, VGL_EMISSING = 0, -1, -2, -3, -4, -5, -6, -7, -8
-ABI_VERSION = 7
+ABI_VERSION = 8
 HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF = 0, 1, 2, 3
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
@@ -30,7 +30,7 @@ I32_MISSING = -(2 ** 31)
 EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_bcf_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
            "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
            "vgl_last_error", "vgl_abi_version", "vgl_native_kernels",
-           "vgl_gvcf_merge", "vgl_discordance", "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parser_rows", "vgl_place_rows"]
+           "vgl_gvcf_merge", "vgl_discordance", "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parse_bcf", "vgl_parser_rows", "vgl_place_rows"]
 
 SOURCE_BINARY, SOURCE_ACGT = 0, 1
 PARSE_FINAL, PARSE_TEXT_ON_DEVICE = 1, 2
@@ -176,6 +176,7 @@ def load():
     L.vgl_parser_destroy.restype = None
     L.vgl_parser_text_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.vgl_parse_vcf.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.POINTER(VglParseOut)]
+    L.vgl_parse_bcf.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(VglParseOut)]
     L.vgl_parser_rows.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     L.vgl_place_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint8]
     _lib = L
@@ -528,6 +529,17 @@ class Parser:
             self.text[:n_bytes] = a
         out = VglParseOut()
         rc = self.L.vgl_parse_vcf(self.h, int(n_bytes), gt_source, flags, C.byref(out))
+        if rc != VGL_OK:
+            raise VglError(rc, self.L.vgl_strerror(rc).decode())
+        return ParseResult(out)
+
+    def parse_bcf(self, data, rec_off, gt_key: int, gt_source: int = SOURCE_BINARY, flags: int = 0) -> ParseResult:
+        """uncompressed BCF records (bytes after the header) + their offsets [n + 1] (vgl_parse_bcf)"""
+        a = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data
+        self.text[:len(a)] = a
+        off = np.ascontiguousarray(rec_off, np.uint32)
+        out = VglParseOut()
+        rc = self.L.vgl_parse_bcf(self.h, len(a), off.ctypes.data, len(off) - 1, gt_source, gt_key, flags, C.byref(out))
         if rc != VGL_OK:
             raise VglError(rc, self.L.vgl_strerror(rc).decode())
         return ParseResult(out)

@@ -779,6 +779,159 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
     }
 }
 
+// ---- BCF records (binary input) -------------------------------------------------------------------------------------
+// The same per-record work for uncompressed BCF records (what bcf_read + bcf_unpack + bcf_get_genotypes + check_rec_alleles
+// do with them, htslib/vcf.c:1535-1600, vcfgl.cpp:75-163): fixed fields, allele strings -> allele map, the FORMAT block
+// whose key is GT -> typed integer vector [n_sample][ploidy] -> packed bytes.  One warp per record; the genotype vector is
+// contiguous, so the lanes read it coalesced.  Record offsets come from the host (a chain of l_shared + l_indiv hops).
+__device__ __forceinline__ uint32_t rd_u32(const uint8_t* __restrict__ t, uint32_t p)
+{
+    return (uint32_t)t[p] | ((uint32_t)t[p + 1] << 8) | ((uint32_t)t[p + 2] << 16) | ((uint32_t)t[p + 3] << 24);
+}
+
+// typed scalar / descriptor at p: returns (count, type) and advances p past the descriptor (BCF2 spec 6.3.3)
+__device__ __forceinline__ void rd_desc(const uint8_t* __restrict__ t, uint32_t& p, uint32_t& n, uint32_t& type)
+{
+    const uint32_t b = t[p++];
+    type = b & 0xFu;
+    n = b >> 4;
+    if (n == 15) { // the count follows as a typed integer
+        const uint32_t tb = t[p++] & 0xFu;
+        if (tb == 1) n = t[p], p += 1;
+        else if (tb == 2) n = (uint32_t)t[p] | ((uint32_t)t[p + 1] << 8), p += 2;
+        else n = rd_u32(t, p), p += 4;
+    }
+}
+
+__global__ void __launch_bounds__(GT_WARPS * 32) k_bcf_gt(const uint8_t* __restrict__ text, const uint32_t* __restrict__ rec_off, uint32_t n_rec, int32_t S,
+                                                         int32_t gt_source, int32_t gt_key, int32_t rm_invar, vgl_in_site* __restrict__ sites,
+                                                         uint8_t* __restrict__ rows, uint32_t* counters)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp0 = blockIdx.x * GT_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * GT_WARPS;
+    uint32_t n_kept = 0, n_err = 0, first_err = 0xFFFFFFFFu;
+    for (uint32_t r = warp0; r < n_rec; r += n_warps) {
+        const uint32_t o = rec_off[r], rec_len = rec_off[r + 1] - o;
+        int st = 99, asum = 0;
+        const uint32_t l_shared = rd_u32(text, o);
+        const int32_t pos = (int32_t)rd_u32(text, o + 12);
+        const uint32_t nai = rd_u32(text, o + 24), nfs = rd_u32(text, o + 28);
+        const int n_allele = (int)(nai >> 16), n_fmt = (int)(nfs >> 24);
+        const uint32_t n_sample = nfs & 0xFFFFFFu;
+        uint32_t p = o + 32, n, type;
+        rd_desc(text, p, n, type); // ID
+        p += n;
+        uint32_t amap = 0xEEEEEEEEu;
+        for (int a = 0; a < n_allele; ++a) {
+            rd_desc(text, p, n, type);
+            if (a < 5) {
+                uint32_t code = 0xE;
+                const uint32_t c0 = n ? text[p] : 0;
+                if (gt_source == VGL_SOURCE_BINARY) {
+                    if (c0 == '0') code = 0;
+                    else if (c0 == '1') code = 1;
+                } else if (n == 1) {
+                    code = c0 == 'A' ? 0 : c0 == 'C' ? 1 : c0 == 'G' ? 2 : c0 == 'T' ? 3 : 0xE;
+                } else if (n == 3) {
+                    if (c0 == '<' && text[p + 1] == '*' && text[p + 2] == '>') code = 4;
+                } else if (n == 9) {
+                    const char* nr = "<NON_REF>";
+                    bool eq = true;
+                    for (int k = 0; k < 9; ++k) eq = eq && text[p + k] == (uint8_t)nr[k];
+                    if (eq) code = 4;
+                }
+                if (code == 0xE) raise(st, VGL_IN_EALLELE);
+                amap = (amap & ~(0xFu << (4 * a))) | (code << (4 * a));
+            }
+            p += n;
+        }
+        if (n_allele > 5 || (gt_source == VGL_SOURCE_BINARY && n_allele > 2)) raise(st, VGL_IN_ENALLELE);
+        if ((int)n_sample != S) raise(st, VGL_IN_ENSAMPLES);
+        // FORMAT blocks: key, (values per sample, type), values
+        p = o + 8 + l_shared;
+        uint32_t gt_at = 0, gt_n = 0, gt_w = 0;
+        bool have_gt = false;
+        for (int f = 0; f < n_fmt && !have_gt; ++f) {
+            rd_desc(text, p, n, type); // the key: one typed integer
+            int key = type == 1 ? (int)(int8_t)text[p] : type == 2 ? (int)(int16_t)((uint32_t)text[p] | ((uint32_t)text[p + 1] << 8)) : (int)rd_u32(text, p);
+            p += type == 1 ? 1 : type == 2 ? 2 : 4;
+            rd_desc(text, p, n, type);
+            const uint32_t w = type == 1 || type == 7 ? 1u : type == 2 ? 2u : 4u;
+            if (key == gt_key) have_gt = true, gt_at = p, gt_n = n, gt_w = type == 7 ? 0u : w;
+            p += n * w * n_sample;
+        }
+        uint8_t* const row = rows + (size_t)r * S;
+        if (!have_gt || gt_w == 0) raise(st, VGL_IN_ENOGT);
+        else if (gt_n != 2) raise(st, VGL_IN_EPLOIDY); // the reference reads gt_arr as [2 * n_samples] (vcfgl.cpp:131-146)
+        else if ((int)n_sample == S) {
+            for (int s = lane; s < S; s += 32) {
+                uint32_t byte = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t q = gt_at + (2u * (uint32_t)s + h) * gt_w;
+                    int v;
+                    bool end, missing_sentinel;
+                    if (gt_w == 1) v = (int8_t)text[q], end = v == -127, missing_sentinel = v == -128;
+                    else if (gt_w == 2) v = (int16_t)((uint32_t)text[q] | ((uint32_t)text[q + 1] << 8)), end = v == -32767, missing_sentinel = v == -32768;
+                    else v = (int)rd_u32(text, q), end = v == (int)0x80000001, missing_sentinel = v == (int)0x80000000;
+                    uint32_t nib = 0xF;
+                    if (end) raise(st, VGL_IN_EPLOIDY);          // a haploid sample in a diploid record: vector_end
+                    else if (missing_sentinel) raise(st, VGL_IN_EALLELEIDX); // not a GT value; the reference asserts a >= 0
+                    else if ((v >> 1) != 0) {                    // bcf_gt_is_missing: (v >> 1) == 0
+                        const int a = (v >> 1) - 1;
+                        if (a < 0 || a >= n_allele) raise(st, VGL_IN_EALLELEIDX);
+                        else {
+                            asum += a;
+                            const uint32_t mc = a < 5 ? (amap >> (4 * a)) & 0xF : 0xE;
+                            if (mc == 4) raise(st, VGL_IN_ESYMBOLIC);
+                            else if (mc < 4) nib = mc;
+                        }
+                    }
+                    byte |= nib << (4 * h);
+                }
+                row[s] = (uint8_t)byte;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            st = min(st, __shfl_xor_sync(0xffffffffu, st, d));
+            asum += __shfl_xor_sync(0xffffffffu, asum, d);
+        }
+        if (lane == 0) {
+            vgl_in_site out;
+            out.status = st == 99 ? VGL_IN_OK : st;
+            out.skip_code = 0;
+            if (out.status == VGL_IN_OK) {
+                if ((rm_invar & 1) && asum == 0) out.skip_code = -1;
+                else if (rm_invar & 2)
+                    for (int al = 1; al < n_allele; ++al)
+                        if ((long long)al * S * 2 == (long long)asum) out.skip_code = -2;
+            }
+            out.pos = pos;
+            out.allele_sum = (rm_invar & 3) ? asum : 0;
+            out.line_off = o;
+            out.line_len = rec_len;
+            out.n_allele = n_allele;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t c = i < 5 && i < n_allele ? (amap >> (4 * i)) & 0xF : 0xE;
+                out.allele_acgt[i] = c == 0xE ? -1 : (int8_t)c;
+            }
+            out.id_off = 32, out.fmt_off = 8 + l_shared, out.samples_off = have_gt ? gt_at - o : 0, out._pad = 0;
+            sites[r] = out;
+            if (out.status != VGL_IN_OK) ++n_err, first_err = min(first_err, r);
+            else if (out.skip_code == 0) ++n_kept;
+        }
+    }
+    if (lane == 0) {
+        if (n_kept) atomicAdd(&counters[C_NKEPT], n_kept);
+        if (n_err) {
+            atomicAdd(&counters[C_NERRORS], n_err);
+            atomicMin(&counters[C_FIRSTERR], first_err);
+        }
+    }
+}
+
 // ---- rows -> slot genotype matrix ----------------------------------------------------------------------------------
 __global__ void k_place_rows(const uint8_t* __restrict__ rows, const int32_t* __restrict__ row_map, int32_t first_record, int32_t n_sites,
                              int32_t S, uint32_t fill, uint8_t* __restrict__ gt)
@@ -993,5 +1146,52 @@ extern "C" int vgl_parser_rows(vgl_parser* ps, int32_t first_record, int32_t n_r
     PCK(cudaSetDevice(ps->device));
     PCK(cudaMemcpyAsync(host_dst, ps->d_rows + (size_t)first_record * ps->S, (size_t)n_records * ps->S, cudaMemcpyDeviceToHost, ps->stream));
     PCK(cudaStreamSynchronize(ps->stream));
+    return VGL_OK;
+}
+
+extern "C" int vgl_parse_bcf(vgl_parser* ps, int64_t n_bytes, const uint32_t* rec_off, int32_t n_records, int32_t gt_source, int32_t gt_key, uint32_t flags,
+                             vgl_parse_out* out)
+{
+    if (!ps || !out || !rec_off || n_bytes < 0 || (size_t)n_bytes > ps->text_cap || n_records < 0 || n_records > ps->max_records || gt_source < 0 || gt_source > 1)
+        return VGL_EINVAL;
+    for (int32_t i = 0; i < n_records; ++i) // offsets ascend, every record holds its 32 fixed bytes, the last one ends inside the buffer
+        if (rec_off[i + 1] < rec_off[i] + 32u || (int64_t)rec_off[i + 1] > n_bytes) {
+            ps->err = "vgl_parse_bcf: record offsets must ascend, leave 32 bytes per record and stay inside n_bytes";
+            return VGL_EINVAL;
+        }
+    memset(out, 0, sizeof *out);
+    out->first_error_record = -1;
+    out->sites = ps->h_sites;
+    ps->n_records = 0;
+    if (n_records == 0) return VGL_OK;
+    PCK(cudaSetDevice(ps->device));
+    cudaStream_t st = ps->stream;
+    if (ps->placed) PCK(cudaStreamWaitEvent(st, ps->ev_placed, 0));
+    PCK(cudaEventRecord(ps->ev[0], st));
+    if (!(flags & VGL_PARSE_TEXT_ON_DEVICE)) {
+        PCK(cudaMemcpyAsync(ps->d_text, ps->h_text, (size_t)n_bytes, cudaMemcpyHostToDevice, st));
+        ps->d_text_bytes = (size_t)n_bytes;
+    }
+    PCK(cudaMemcpyAsync(ps->d_line_end, rec_off, ((size_t)n_records + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    PCK(cudaEventRecord(ps->ev[1], st));
+    static const uint32_t init[C_COUNT] = {0, 0, 0, 0, 0xFFFFFFFFu, 0, 0, 0};
+    PCK(cudaMemcpyAsync(ps->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    k_bcf_gt<<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, ps->d_line_end, (uint32_t)n_records, ps->S, gt_source, gt_key, ps->rm_invar, ps->d_sites,
+                                                     ps->d_rows, ps->d_counters);
+    ps->launches += 1;
+    PCK(cudaGetLastError());
+    PCK(cudaEventRecord(ps->ev[2], st));
+    PCK(cudaMemcpyAsync(ps->h_counters, ps->d_counters, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    PCK(cudaMemcpyAsync(ps->h_sites, ps->d_sites, (size_t)n_records * sizeof(vgl_in_site), cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    PCK(cudaEventRecord(ps->ev_done, st));
+    ps->n_records = n_records;
+    out->n_records = n_records;
+    out->n_errors = (int32_t)ps->h_counters[C_NERRORS];
+    out->first_error_record = out->n_errors ? (int32_t)ps->h_counters[C_FIRSTERR] : -1;
+    out->n_kept = (int32_t)ps->h_counters[C_NKEPT];
+    out->bytes_consumed = rec_off[n_records];
+    cudaEventElapsedTime(&out->ms_h2d, ps->ev[0], ps->ev[1]);
+    cudaEventElapsedTime(&out->ms_kernels, ps->ev[1], ps->ev[2]);
     return VGL_OK;
 }
