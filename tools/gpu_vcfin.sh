@@ -15,6 +15,6 @@ timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1
 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; tail -c 3000 $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
 fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_vcfin_$TAG.csv python tools/prof_vcfin.py 100 131072 3 > $OUT/ncu_launches_vcfin_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_vcf_cells -s 2 -c 1 -f -o $OUT/prof_vcfcells_$TAG python tools/prof_vcfin.py 100 131072 3 > $OUT/ncu_vcfgt_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_vcf_cells -s 2 -c 1 -f -o $OUT/prof_vcfcells_$TAG python tools/prof_vcfin.py 100 131072 3 > $OUT/ncu_vcflines_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_vcf_hdr -s 2 -c 1 -f -o $OUT/prof_vcfhdr_$TAG python tools/prof_vcfin.py 100 131072 3 > $OUT/ncu_vcfgt_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_vcf_hdr -s 2 -c 1 -f -o $OUT/prof_vcfhdr_$TAG python tools/prof_vcfin.py 100 131072 3 > $OUT/ncu_vcflines_$TAG.log 2>&1
 ls -la $OUT | tail -12

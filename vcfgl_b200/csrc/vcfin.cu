@@ -404,6 +404,40 @@ __device__ __forceinline__ uint32_t slow_cell(uint32_t xv, uint32_t nal, uint32_
     return n0 | (n1 << 4);
 }
 
+// The common shape of a record for ONE thread (k_vcf_hdr): REF and ALT one character each, FORMAT exactly "GT", POS of 1..9
+// digits.  Same results as parse_header(); anything else returns false and takes the general parser.
+template <class Text>
+__device__ __forceinline__ bool thread_fast_header(const Text& text, const uint32_t* tab, int gt_source, Hdr& h)
+{
+    const uint32_t plen = tab[1] - tab[0] - 1;
+    if (tab[3] - tab[2] != 2 || tab[4] - tab[3] != 2 || tab[8] - tab[7] != 3 || plen - 1u > 8u) return false;
+    const uint32_t ref = text[tab[2] + 1], alt = text[tab[3] + 1];
+    if (text[tab[7] + 1] != 'G' || text[tab[7] + 2] != 'T') return false;
+    uint32_t cr, ca;
+    if (gt_source == VGL_SOURCE_BINARY) {
+        cr = ref - '0', ca = alt - '0';
+        if (cr > 1u) cr = 0xE;
+        if (ca > 1u) ca = 0xE;
+    } else {
+        cr = ref == 'A' ? 0 : ref == 'C' ? 1 : ref == 'G' ? 2 : ref == 'T' ? 3 : 0xE;
+        ca = alt == 'A' ? 0 : alt == 'C' ? 1 : alt == 'G' ? 2 : alt == 'T' ? 3 : 0xE;
+    }
+    const bool no_alt = alt == '.';
+    if (cr == 0xE || (!no_alt && ca == 0xE)) return false;
+    uint32_t v = 0;
+    for (uint32_t p = tab[0] + 1; p < tab[1]; ++p) {
+        const uint32_t d = text[p] - '0';
+        if (d > 9u) return false;
+        v = v * 10u + d;
+    }
+    h.pos = (long long)v - 1;
+    h.n_allele = no_alt ? 1 : 2;
+    h.amap = 0xEEEEEE00u | cr | ((no_alt ? 0xEu : ca) << 4);
+    h.gt_idx = 0;
+    h.st = 99;
+    return true;
+}
+
 // the head of a record line, held in shared memory by the thread that parses the record
 constexpr int HDR_THREADS = 128;
 struct LineBuf {
@@ -427,24 +461,28 @@ __global__ void __launch_bounds__(HDR_THREADS) k_vcf_hdr(const uint8_t* __restri
     for (uint32_t line = blockIdx.x * blockDim.x + threadIdx.x; line < n_rec; line += gridDim.x * blockDim.x) {
         const uint32_t ls = line ? line_end[line - 1] + 1 : 0;
         uint32_t le = line_end[line];
-        if (le > ls && text[le - 1] == '\r') --le;
+        // the head of the line: its address depends on ls only, so the loads go out before anything that waits on le
+        LineBuf buf;
+        buf.g = text;
+        buf.base = ls & ~15u;
+        buf.w = s_head + threadIdx.x; // word k of this thread at s_head[k * HDR_THREADS + tid]: conflict-free
+        uint4 hv[LineBuf::BYTES / 16];
+#pragma unroll
+        for (int k = 0; k < LineBuf::BYTES / 16; ++k) hv[k] = __ldg(reinterpret_cast<const uint4*>(text + buf.base) + k);
+        const uint32_t body = 4u * (uint32_t)S - 1u;
+        const uint32_t c_cr = le > ls ? text[le - 1] : 0u, c_tab = le > body + 1u ? text[le - body - 1u] : 0u, c_tab_cr = le > body + 2u ? text[le - body - 2u] : 0u;
+        bool tab_ok = c_tab == '\t';
+        if (c_cr == '\r') --le, tab_ok = c_tab_cr == '\t'; // KS_SEP_LINE strips the CR of a CRLF
         RecMeta m;
         m.p0 = 0, m.lut = 0, m.flags = 0, m.asum = 0;
         // the sample columns of a candidate are 4 * S - 1 bytes: the ninth tab must sit right before them
-        const uint32_t body = 4u * (uint32_t)S - 1u;
-        if (le - ls > body + 16u && text[le - body - 1] == '\t') {
+        if (le - ls > body + 16u && tab_ok) {
             uint32_t tab[9];
             int nt = 0;
             const uint32_t p0 = le - body;
-            // the head of the line goes to shared memory in one round trip (independent 16-byte loads); every later look at it is
-            // a shared-memory read instead of a byte load from a line no other lane touches
-            LineBuf buf;
-            buf.g = text;
-            buf.base = ls & ~15u;
-            buf.w = s_head + threadIdx.x; // word k of this thread at s_head[k * HDR_THREADS + tid]: conflict-free
 #pragma unroll
             for (int k = 0; k < LineBuf::BYTES / 16; ++k) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + buf.base) + k);
+                const uint4 v = hv[k];
                 buf.w[(4 * k) * HDR_THREADS] = v.x, buf.w[(4 * k + 1) * HDR_THREADS] = v.y;
                 buf.w[(4 * k + 2) * HDR_THREADS] = v.z, buf.w[(4 * k + 3) * HDR_THREADS] = v.w;
                 uint32_t tm = eq_mask16(v, 0x09090909u);
@@ -459,7 +497,8 @@ __global__ void __launch_bounds__(HDR_THREADS) k_vcf_hdr(const uint8_t* __restri
             for (uint32_t p = buf.base + LineBuf::BYTES; p < p0 && nt < 9; ++p)
                 if (text[p] == '\t') tab[nt++] = p;
             if (nt == 9 && tab[8] == p0 - 1) {
-                const Hdr h = parse_header(buf, tab, gt_source);
+                Hdr h;
+                if (!thread_fast_header(buf, tab, gt_source, h)) h = parse_header(buf, tab, gt_source);
                 bool sym = false;
                 for (int i = 0; i < 5; ++i) sym = sym || (i < h.n_allele && ((h.amap >> (4 * i)) & 0xFu) == 4u);
                 if (h.st == 99 && h.gt_idx == 0 && !sym) {
