@@ -19,6 +19,11 @@ hot path over one batch of 131072 sites (13.1 M cells, ~1.9 GB of tag planes -- 
   cpu_baseline  the reference binary itself (oracle/_ref/vcfgl_ref, built from /root/reference)
                 on a bounded sample of the same workload on this box's host, 1 thread.
 
+  input_path    (N=1) SURVEY.md 8(f) row 1: one step's worth of msprime-shaped VCF text through k_vcf_* -- kernel-side
+                throughput with its own roofline, end to end from pinned host text (to narrowed arrays and to finished BCF
+                records), and the oracle's single-threaded C parser as CPU baseline.
+  gvcf_merge    (workloads with -doGVCF) SURVEY.md 8(f) row 3: the block merger on the batch resident in HBM.
+
 `--impl reference` times the reference CPU binary with one process per host core on contiguous
 site shards (the reference cannot thread its simulation).
 
