@@ -111,3 +111,37 @@ def test_bcf_to_tags_equals_packed_submit():
                 assert v == w[k], (i, k)
     ps.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("name,source,explode", [("data7.bcf", 1, 1), ("in_acgt.bcf", 1, 1), ("in_binary.bcf", 0, 0), ("s8.in.bcf", 0, 1)])
+def test_bcf_driver_equals_text_driver(name, source, explode):
+    """the whole driver loop (contigs from rid, -explode, batches of 5 sites) from BCF records gives the sites and tags of the
+    same loop from the VCF text"""
+    body, off, m = bu.load(name)
+    buf = vo.load_input(m["vcf"])
+    hdr = vcfinput.read_header(buf)
+    S = len(hdr.samples)
+    a = vargs.parse_args(ARGV.split())
+
+    def collect(gen):
+        out = []
+        for run, b in gen:
+            for i in range(b.n_sites):
+                o = b.site(i)
+                out.append((run.contig, int(run.pos[i]), {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in o.items()}))
+        return out
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=5, n_slots=2))
+    ps = ctx.parser(max(len(body), len(buf)) + 64, 16)
+    text = collect(vcfinput.simulate_vcf_text(ctx, ps, buf[hdr.body_offset:], gt_source=source, explode=explode, contigs=hdr.contigs))
+    bcf = collect(vcfinput.simulate_bcf_records(ctx, ps, body, gt_key=m["gt_key"], gt_source=source, explode=explode,
+                                                contig_names=list(hdr.contigs), contig_lengths=hdr.contigs, max_records_per_chunk=3))
+    assert len(text) == len(bcf) > 0
+    for (c1, p1, o1), (c2, p2, o2) in zip(text, bcf):
+        assert (c1, p1) == (c2, p2)
+        for k, v in o1.items():
+            if isinstance(v, np.ndarray):
+                assert np.array_equal(v.view(np.uint8), o2[k].view(np.uint8)), (p1, k)
+            else:
+                assert v == o2[k], (p1, k)
+    ps.close()
+    ctx.close()

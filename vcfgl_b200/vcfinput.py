@@ -120,6 +120,21 @@ class SitePlanner:
             yield from self._run(sites[i:j], i)
             i = j
 
+    def feed_rids(self, rids: np.ndarray, names: List[str], sites: np.ndarray) -> Iterator[SiteRun]:
+        """the same for BCF records: the contig of a record is its rid (bcf1_t::rid), names[rid] its name"""
+        n = len(sites)
+        i = 0
+        while i < n:
+            name = names[int(rids[i])].encode()
+            if self.contig != name:
+                self.contig = name
+                self.n_in_contig = 0
+            j = i + 1
+            while j < n and rids[j] == rids[i]:
+                j += 1
+            yield from self._run(sites[i:j], i)
+            i = j
+
     def _run(self, recs: np.ndarray, first_index: int) -> Iterator[SiteRun]:
         contig = self.contig.decode()
         pos = recs["pos"].astype(np.int64)
@@ -238,4 +253,69 @@ def simulate_vcf_text(ctx: capi.Context, parser: capi.Parser, body: bytes, *, gt
         if (run.src >= 0).any():
             raise AssertionError("tail sites cannot reference records")
         yield from submit(run)
+    yield from drain(0)
+
+
+def bcf_record_offsets(body) -> np.ndarray:
+    """offsets [n + 1] of the records in the bytes after a BCF header: hop l_shared + l_indiv + 8 (htslib/vcf.c:1456-1500)"""
+    import struct
+    off, o, n = [0], 0, len(body)
+    while o + 8 <= n:
+        l_shared, l_indiv = struct.unpack_from("<II", body, o)
+        if o + 8 + l_shared + l_indiv > n:
+            break                                   # incomplete record: carry it over to the next chunk
+        o += 8 + l_shared + l_indiv
+        off.append(o)
+    return np.array(off, np.uint32)
+
+
+def simulate_bcf_records(ctx: capi.Context, parser: capi.Parser, body: bytes, *, gt_key: int, gt_source: int, explode: int,
+                         contig_names: List[str], contig_lengths: Dict[str, int], first_site_id: int = 0,
+                         max_records_per_chunk: Optional[int] = None) -> Iterator[Tuple[SiteRun, capi.Batch]]:
+    """simulate_vcf_text for uncompressed BCF records (the bytes after the header, BGZF already inflated)."""
+    assert parser.S == ctx.S
+    rm_invar = int(ctx.params.rm_invar_sites) & 3
+    planner = SitePlanner(explode, rm_invar, contig_lengths, ctx.cap)
+    n_slots = int(ctx.params.n_slots)
+    pending: List[Tuple[int, SiteRun]] = []
+    site_id, slot = first_site_id, 0
+    mv = np.frombuffer(body, np.uint8)
+    off = bcf_record_offsets(body)
+    per = max_records_per_chunk or ctx.cap
+    last_acgt0 = -1
+
+    def drain(keep: int):
+        while len(pending) > keep:
+            sl, run = pending.pop(0)
+            run.slot = sl
+            yield run, ctx.wait(sl)
+
+    for r0 in range(0, len(off) - 1, per):
+        r1 = min(r0 + per, len(off) - 1)
+        lo, hi = int(off[r0]), int(off[r1])
+        res = parser.parse_bcf(mv[lo:hi], off[r0:r1 + 1] - off[r0], gt_key, gt_source)
+        if res.n_errors:
+            s = res.sites[res.first_error_record]
+            raise VcfInputError("%s at position %d (record %d)" % (IN_STATUS_TEXT.get(int(s["status"]), "status %d" % s["status"]),
+                                                                    int(s["pos"]) + 1, r0 + res.first_error_record))
+        sites = res.sites.copy()
+        last_acgt0 = int(sites["allele_acgt"][-1][0])
+        rids = mv[lo:hi].view(np.uint8)
+        rid = np.array([int.from_bytes(rids[int(o) + 8:int(o) + 12].tobytes(), "little", signed=True) for o in sites["line_off"]], np.int32)
+        for run in planner.feed_rids(rid, contig_names, sites):
+            yield from drain(n_slots - 1)
+            fill = (planner.fill_acgt & 0xF) * 0x11 if planner.fill_acgt >= 0 else 0
+            ctx.place_rows(slot, parser, len(run.src), row_map=run.src, fill_gt=fill)
+            ctx.submit(slot, site_id, len(run.src), flags=capi.SUBMIT_GT_ON_DEVICE)
+            pending.append((slot, run))
+            site_id += len(run.src)
+            slot = (slot + 1) % n_slots
+    for run in planner.finish(last_acgt0):
+        yield from drain(n_slots - 1)
+        fill = (planner.fill_acgt & 0xF) * 0x11 if planner.fill_acgt >= 0 else 0
+        ctx.place_rows(slot, parser, len(run.src), row_map=run.src, fill_gt=fill)
+        ctx.submit(slot, site_id, len(run.src), flags=capi.SUBMIT_GT_ON_DEVICE)
+        pending.append((slot, run))
+        site_id += len(run.src)
+        slot = (slot + 1) % n_slots
     yield from drain(0)
