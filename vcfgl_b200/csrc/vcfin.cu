@@ -821,7 +821,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
 // ---- BCF records (binary input) -------------------------------------------------------------------------------------
 // The same per-record work for uncompressed BCF records (what bcf_read + bcf_unpack + bcf_get_genotypes + check_rec_alleles
 // do with them, htslib/vcf.c:1535-1600, vcfgl.cpp:75-163): fixed fields, allele strings -> allele map, the FORMAT block
-// whose key is GT -> typed integer vector [n_sample][ploidy] -> packed bytes.  One warp per record; the genotype vector is
+// whose key is GT -> typed integer vector [n_sample][ploidy] -> packed bytes.  Eight lanes per record; the genotype vector is
 // contiguous, so the lanes read it coalesced.  Record offsets come from the host (a chain of l_shared + l_indiv hops).
 __device__ __forceinline__ uint32_t rd_u32(const uint8_t* __restrict__ t, uint32_t p)
 {
@@ -842,14 +842,18 @@ __device__ __forceinline__ void rd_desc(const uint8_t* __restrict__ t, uint32_t&
     }
 }
 
+template <int LANES> // lanes per record: 8 (four records per warp in flight) for narrow records, 32 for wide ones
 __global__ void __launch_bounds__(GT_WARPS * 32) k_bcf_gt(const uint8_t* __restrict__ text, const uint32_t* __restrict__ rec_off, uint32_t n_rec, int32_t S,
                                                          int32_t gt_source, int32_t gt_key, int32_t rm_invar, vgl_in_site* __restrict__ sites,
                                                          uint8_t* __restrict__ rows, uint32_t* counters)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp0 = blockIdx.x * GT_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * GT_WARPS;
+    // eight lanes per record, four records per warp in flight: a record's fixed fields are a chain of dependent byte loads, and a
+    // warp walking its records one after the other would wait on every link (cf. k_gvcf_key)
+    const int lane = threadIdx.x & (LANES - 1);
+    const uint32_t gmask = LANES == 32 ? 0xFFFFFFFFu : 0xFFu << (threadIdx.x & 24);
+    const uint32_t grp0 = (blockIdx.x * blockDim.x + threadIdx.x) / LANES, n_grp = (gridDim.x * blockDim.x) / LANES;
     uint32_t n_kept = 0, n_err = 0, first_err = 0xFFFFFFFFu;
-    for (uint32_t r = warp0; r < n_rec; r += n_warps) {
+    for (uint32_t r = grp0; r < n_rec; r += n_grp) {
         const uint32_t o = rec_off[r], rec_len = rec_off[r + 1] - o;
         int st = 99, asum = 0;
         const uint32_t l_shared = rd_u32(text, o);
@@ -903,7 +907,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_bcf_gt(const uint8_t* __restr
         if (!have_gt || gt_w == 0) raise(st, VGL_IN_ENOGT);
         else if (gt_n != 2) raise(st, VGL_IN_EPLOIDY); // the reference reads gt_arr as [2 * n_samples] (vcfgl.cpp:131-146)
         else if ((int)n_sample == S) {
-            for (int s = lane; s < S; s += 32) {
+            for (int s = lane; s < S; s += LANES) {
                 uint32_t byte = 0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -932,9 +936,9 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_bcf_gt(const uint8_t* __restr
             }
         }
 #pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            st = min(st, __shfl_xor_sync(0xffffffffu, st, d));
-            asum += __shfl_xor_sync(0xffffffffu, asum, d);
+        for (int d = LANES / 2; d; d >>= 1) {
+            st = min(st, __shfl_xor_sync(gmask, st, d));
+            asum += __shfl_xor_sync(gmask, asum, d);
         }
         if (lane == 0) {
             vgl_in_site out;
@@ -1215,8 +1219,12 @@ extern "C" int vgl_parse_bcf(vgl_parser* ps, int64_t n_bytes, const uint32_t* re
     PCK(cudaEventRecord(ps->ev[1], st));
     static const uint32_t init[C_COUNT] = {0, 0, 0, 0, 0xFFFFFFFFu, 0, 0, 0};
     PCK(cudaMemcpyAsync(ps->d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
-    k_bcf_gt<<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, ps->d_line_end, (uint32_t)n_records, ps->S, gt_source, gt_key, ps->rm_invar, ps->d_sites,
-                                                     ps->d_rows, ps->d_counters);
+    if (ps->S <= 256)
+        k_bcf_gt<8><<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, ps->d_line_end, (uint32_t)n_records, ps->S, gt_source, gt_key, ps->rm_invar, ps->d_sites,
+                                                            ps->d_rows, ps->d_counters);
+    else
+        k_bcf_gt<32><<<ps->n_sms * 8, GT_WARPS * 32, 0, st>>>(ps->d_text, ps->d_line_end, (uint32_t)n_records, ps->S, gt_source, gt_key, ps->rm_invar, ps->d_sites,
+                                                             ps->d_rows, ps->d_counters);
     ps->launches += 1;
     PCK(cudaGetLastError());
     PCK(cudaEventRecord(ps->ev[2], st));
