@@ -145,3 +145,30 @@ def test_bcf_driver_equals_text_driver(name, source, explode):
                 assert v == o2[k], (p1, k)
     ps.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("name,source,explode,dps", [("data7.bcf", 1, 1, None), ("in_binary.bcf", 0, 0, None), ("s8.in.bcf", 0, 1, "1,2")])
+def test_cpp_host_driver_bcf(name, source, explode, dps, tmp_path):
+    """vgl::VcfTextSimulator::run_bcf (C++: BCF header, record hops, vgl_parse_bcf, site plan) prints exactly what ::run prints
+    for the VCF the BCF was made from"""
+    import gzip
+    import os
+    import subprocess
+    exe = os.path.join(bu.ROOT, "vcfgl_b200", "host", "example_driver")
+    if not os.path.exists(exe):
+        pytest.skip("example_driver not built")
+    m = bu.MANIFEST[name]
+    pb, pv = tmp_path / "in.bcf", tmp_path / "in.vcf"
+    pb.write_bytes(gzip.open(os.path.join(bu.INPUTS, name + ".gz"), "rb").read())
+    pv.write_bytes(vo.load_input(m["vcf"]))
+    outs = []
+    for path, is_bcf in ((pv, False), (pb, True)):
+        env = dict(os.environ, VGL_VCF_IN=str(path), VGL_SOURCE=str(source), VGL_EXPLODE=str(explode), VGL_BATCH="5")
+        if dps:
+            env["VGL_GVCF_DPS"] = dps
+        if is_bcf:
+            env["VGL_INPUT_IS_BCF"] = "1"
+        r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) >= m["n_records"]

@@ -59,7 +59,8 @@ int main(int argc, char** argv)
                     printf("\n");
                 });
             }
-            sim.run(f);
+            if (getenv("VGL_INPUT_IS_BCF")) sim.run_bcf(f); // uncompressed BCF (-O u)
+            else sim.run(f);
             fclose(f);
             fprintf(stderr, "sites simulated: %ld, input-side skips: %ld\n", (long)sim.n_sites(), (long)sim.n_skipped_input());
             return 0;

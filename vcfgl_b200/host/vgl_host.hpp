@@ -635,6 +635,149 @@ public:
         ps_ = nullptr;
     }
 
+    // The same driver loop for an uncompressed BCF stream (what `bcftools view -Ou` or the reference's own -O u writes; a BGZF
+    // stream must be inflated by the caller): header -> samples, contig names in rid order, the dictionary id of FORMAT/GT;
+    // records -> vgl_parse_bcf() (k_bcf_gt) chunk by chunk.
+    void run_bcf(FILE* in)
+    {
+        char magic[5];
+        uint32_t l_text = 0;
+        if (fread(magic, 1, 5, in) != 5 || memcmp(magic, "BCF\2\2", 5) != 0 || fread(&l_text, 4, 1, in) != 1) throw Error(VGL_EINVAL, "not an uncompressed BCF2 stream");
+        std::string text(l_text, '\0');
+        if (fread(&text[0], 1, l_text, in) != l_text) throw Error(VGL_EINVAL, "truncated BCF header");
+        std::vector<std::string> rid_names;
+        int gt_key = -1;
+        {   // dictionary of FILTER / INFO / FORMAT ids: PASS = 0, then first appearance, IDX= overrides (htslib/vcf.c bcf_hdr_sync)
+            std::map<std::string, int> ids;
+            ids["PASS"] = 0;
+            int next = 1;
+            size_t p = 0;
+            while (p < text.size()) {
+                size_t e = text.find('\n', p);
+                if (e == std::string::npos) e = text.size();
+                const std::string line = text.substr(p, e - p);
+                p = e + 1;
+                const bool dict = line.rfind("##FILTER=<", 0) == 0 || line.rfind("##INFO=<", 0) == 0 || line.rfind("##FORMAT=<", 0) == 0;
+                if (dict || line.rfind("##contig=<", 0) == 0) {
+                    const size_t id = line.find("ID=");
+                    if (id == std::string::npos) continue;
+                    const std::string name = line.substr(id + 3, line.find_first_of(",>", id) - id - 3);
+                    if (!dict) {
+                        const size_t len = line.find("length=");
+                        contigs_[name] = len == std::string::npos ? 0 : atoll(line.c_str() + len + 7);
+                        rid_names.push_back(name);
+                        continue;
+                    }
+                    const size_t idx = line.find("IDX=");
+                    if (idx != std::string::npos) ids[name] = atoi(line.c_str() + idx + 4), next = std::max(next, ids[name] + 1);
+                    else if (!ids.count(name)) ids[name] = next++;
+                    if (line.rfind("##FORMAT=<", 0) == 0 && name == "GT") gt_key = ids[name];
+                } else if (line.rfind("#CHROM", 0) == 0) {
+                    size_t q = 0;
+                    for (int col = 0; q != std::string::npos; ++col) {
+                        const size_t t = line.find('\t', q);
+                        if (col >= 9) samples_.push_back(line.substr(q, t == std::string::npos ? t : t - q));
+                        q = t == std::string::npos ? t : t + 1;
+                    }
+                }
+            }
+        }
+        if (samples_.empty()) throw Error(VGL_EINVAL, "the BCF has no samples");
+        if (gt_key < 0) throw Error(VGL_EINVAL, "Could not find GT tag in the BCF header");
+        if (prm_.n_samples == 0) prm_.n_samples = (int32_t)samples_.size();
+        if ((size_t)prm_.n_samples != samples_.size()) throw Error(VGL_EINVAL, "n_samples does not match the BCF header");
+        BatchSimulator sim(prm_, [&](const SimRecordView& v) { cb_(v, *static_cast<const Site*>(v.user)); });
+        if (!gvcf_dps_.empty())
+            sim.enable_gvcf(gvcf_dps_, [](void* u) { const Site* st = static_cast<const Site*>(u); return vgl_gvcf_site_in{st->rid, (int32_t)st->pos}; }, on_block_);
+        const int32_t cap = sim.params().max_batch_sites;
+        const int64_t text_cap = (int64_t)cap * (2 * (int64_t)prm_.n_samples + 256) + (1 << 16);
+        int rc = vgl_parser_create(sim.context(), text_cap, cap, &ps_);
+        if (rc != VGL_OK) throw Error(rc, std::string("vgl_parser_create: ") + vgl_last_error(sim.context()));
+        uint8_t* buf = nullptr;
+        int64_t tcap = 0;
+        vgl_parser_text_buffer(ps_, &buf, &tcap);
+        ring_.assign((size_t)sim.params().n_slots + 1, std::vector<Site>());
+        ring_at_ = 0;
+        size_t have = 0;
+        bool eof = false;
+        int64_t n_records_total = 0;
+        int last_acgt0 = -1, last_rid = -1;
+        std::vector<uint32_t> off;
+        for (;;) {
+            if (!eof && (int64_t)have < tcap) {
+                const size_t got = fread(buf + have, 1, (size_t)tcap - have, in);
+                have += got;
+                if (got == 0) eof = true;
+            }
+            if (have == 0) break;
+            off.assign(1, 0u);
+            for (size_t o = 0; o + 8 <= have && (int32_t)off.size() <= cap;) { // hop l_shared + l_indiv + 8
+                uint32_t ls, li;
+                memcpy(&ls, buf + o, 4);
+                memcpy(&li, buf + o + 4, 4);
+                if (o + 8 + ls + li > have) break;
+                o += 8 + (size_t)ls + li;
+                off.push_back((uint32_t)o);
+            }
+            const int32_t n = (int32_t)off.size() - 1;
+            if (n == 0) {
+                if (eof || (int64_t)have == tcap) throw Error(VGL_EINVAL, "truncated BCF record (or one that does not fit the buffer)");
+                continue;
+            }
+            vgl_parse_out po;
+            rc = vgl_parse_bcf(ps_, (int64_t)off[(size_t)n], off.data(), n, source_, gt_key, 0, &po);
+            if (rc != VGL_OK) throw Error(rc, "vgl_parse_bcf failed");
+            if (po.n_errors) {
+                const vgl_in_site& b = po.sites[po.first_error_record];
+                throw Error(VGL_EINVAL, "malformed record at position " + std::to_string(b.pos + 1) + " (vgl_in_status " + std::to_string(b.status) + ")");
+            }
+            begin_batch(cap);
+            for (int32_t i = 0; i < n; ++i) {
+                const vgl_in_site& r = po.sites[i];
+                int32_t rid;
+                memcpy(&rid, buf + r.line_off + 8, 4);
+                if (rid != last_rid) { // contig change (vcfgl.cpp:1484-1488)
+                    if (rid < 0 || (size_t)rid >= rid_names.size()) throw Error(VGL_EINVAL, "record with a contig id that is not in the header");
+                    contig_ = rid_names[(size_t)rid];
+                    last_rid = rid;
+                    n_in_contig_ = 0;
+                    ++rid_;
+                }
+                last_acgt0 = r.allele_acgt[0];
+                if (explode_) {
+                    if (r.pos < n_in_contig_) throw Error(VGL_EINVAL, "-explode 1 needs increasing positions within a contig");
+                    if (r.pos != n_in_contig_ && fill_acgt_ < 0) fill_acgt_ = r.allele_acgt[0];
+                    for (; n_in_contig_ < r.pos; ++n_in_contig_) {
+                        if (prm_.rm_invar_sites & 1) ++n_skipped_;
+                        else add_site(sim, cap, n_in_contig_, -1, -1);
+                    }
+                }
+                if (r.skip_code != 0) ++n_skipped_;
+                else add_site(sim, cap, r.pos, i, n_records_total + i);
+                ++n_in_contig_;
+            }
+            flush(sim, cap);
+            n_records_total += n;
+            const size_t used = off[(size_t)n];
+            memmove(buf, buf + used, have - used);
+            have -= used;
+        }
+        if (explode_ && !contig_.empty()) { // to the end of the LAST contig (vcfgl.cpp:1567-1611)
+            const auto it = contigs_.find(contig_);
+            const int64_t size = it == contigs_.end() ? 0 : it->second;
+            if (fill_acgt_ < 0) fill_acgt_ = last_acgt0;
+            if (prm_.rm_invar_sites & 1) n_skipped_ += std::max<int64_t>(0, size - n_in_contig_);
+            else {
+                begin_batch(cap);
+                for (; n_in_contig_ < size; ++n_in_contig_) add_site(sim, cap, n_in_contig_, -1, -1);
+                flush(sim, cap);
+            }
+        }
+        sim.finish();
+        vgl_parser_destroy(ps_);
+        ps_ = nullptr;
+    }
+
 private:
     void begin_batch(int32_t cap)
     {
