@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 8
+#define VGL_ABI_VERSION 8 /* 2: VGL_HOST_NARROW; 3: VGL_HOST_BCF; 4: input path (vgl_parser_*, vgl_parse_vcf, vgl_place_rows); 5: vgl_gvcf_merge;
+                          * 6: VGL_DEPTH_INF; 7: vgl_discordance; 8: vgl_parse_bcf */
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
