@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(HDR_THREADS) k_vcf_hdr(const uint8_t* __restri
 {
     __shared__ uint32_t s_head[LineBuf::BYTES / 4 * HDR_THREADS];
     const uint32_t n_rec = min(counters[C_NEWLINES], max_records);
+    uint32_t n_fixed = 0;
     for (uint32_t line = blockIdx.x * blockDim.x + threadIdx.x; line < n_rec; line += gridDim.x * blockDim.x) {
         const uint32_t ls = line ? line_end[line - 1] + 1 : 0;
         uint32_t le = line_end[line];
@@ -523,8 +524,12 @@ __global__ void __launch_bounds__(HDR_THREADS) k_vcf_hdr(const uint8_t* __restri
             }
         }
         meta[line] = m;
-        if (!(m.flags & FLAG_FIXED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line; // for the general parser (k_vcf_gt)
+        if (m.flags & FLAG_FIXED) ++n_fixed;
+        else work[atomicAdd(&counters[C_NWORK], 1u)] = line; // for the general parser (k_vcf_gt)
     }
+    // candidates count as kept records up front (k_vcf_cells takes a failed one back, k_vcf_gt applies --rm-invar-sites 1 | 2)
+    n_fixed = __reduce_add_sync(0xffffffffu, n_fixed);
+    if ((threadIdx.x & 31) == 0 && n_fixed) atomicAdd(&counters[C_NKEPT], n_fixed);
 }
 
 // four columns of a candidate record (samples s0 .. s0 + 3) -> four packed bytes
@@ -622,7 +627,10 @@ __global__ void __launch_bounds__(256) k_vcf_cells(const uint8_t* __restrict__ t
                 for (int k = 0; k < n; ++k) dst[k] = (uint8_t)((k < 4 ? lo : hi) >> (8 * (k & 3)));
             }
         }
-        if (!ok && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) work[atomicAdd(&counters[C_NWORK], 1u)] = line; // rare
+        if (!ok && !(atomicOr(&meta[line].flags, (uint32_t)FLAG_FAILED) & FLAG_FAILED)) { // rare: back to the general parser
+            work[atomicAdd(&counters[C_NWORK], 1u)] = line;
+            atomicSub(&counters[C_NKEPT], 1u);
+        }
         if (SUM) { // per-record allele-index sums: the lanes of one record are contiguous
             const int v = fixed ? sum : 0;
             if (n_seg) {
@@ -653,9 +661,10 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
     }
     uint32_t* tab = s_tab[wid];
     uint32_t n_kept = 0, n_err = 0, first_err = 0xFFFFFFFFu; // lane 0's tallies, posted once per warp
-    // (a) fixed-width records that k_vcf_cells converted completely: only the totals are left, one thread per record
-    {
-        uint32_t kept = 0;
+    // (a) fixed-width records that k_vcf_cells converted completely are finished (k_vcf_hdr wrote their site records and counted
+    //     them as kept) unless --rm-invar-sites 1 | 2 asks for the skip decision: then one thread per record applies it
+    uint32_t n_dropped = 0;
+    if (rm_invar & 3) {
         for (uint32_t line = blockIdx.x * blockDim.x + threadIdx.x; line < n_rec; line += gridDim.x * blockDim.x) {
             const RecMeta m = meta[line];
             if ((m.flags & (FLAG_FIXED | FLAG_FAILED)) != FLAG_FIXED) continue;
@@ -667,10 +676,9 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
                     if ((long long)al * S * 2 == (long long)m.asum) skip = -2;
             sites[line].skip_code = skip;
             sites[line].allele_sum = m.asum;
-            kept += skip == 0;
+            n_dropped += skip != 0;
         }
-        kept = __reduce_add_sync(0xffffffffu, kept);
-        n_kept += kept;
+        n_dropped = __reduce_add_sync(0xffffffffu, n_dropped);
     }
     // (b) every other record: one warp per record, from the work list k_vcf_hdr and k_vcf_cells left
     const uint32_t n_work = counters[C_NWORK];
@@ -811,6 +819,7 @@ __global__ void __launch_bounds__(GT_WARPS * 32) k_vcf_gt(const uint8_t* __restr
     }
     if (lane == 0) {
         if (n_kept) atomicAdd(&counters[C_NKEPT], n_kept);
+        if (n_dropped) atomicSub(&counters[C_NKEPT], n_dropped);
         if (n_err) {
             atomicAdd(&counters[C_NERRORS], n_err);
             atomicMin(&counters[C_FIRSTERR], first_err);
