@@ -560,10 +560,16 @@ def input_path_leg(a, gt, hap, B, S, first_site, local, peak_of):
                "sample": "oracle/vcf_in_oracle.c on the first %d records (%.1f MB of text), %.3f s" % (n_cpu, cut / 1e6, dt)}
     except Exception as e:      # the oracle is test infrastructure; its absence must not break the bench line
         cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %s" % e}
+    traffic, traffic_src = None, None
+    try:    # DRAM bytes of the path's kernels from their ncu --set full captures (profiles/traffic.json), when this shape was profiled
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["input_path_%dx%d" % (B, S)]
+        traffic, traffic_src = tr["dram_bytes_per_step"], tr["source"]
+    except Exception:
+        pass
     return {"what": "VCF text -> packed genotypes on the device (k_vcf_count, k_vcf_index, k_vcf_hdr, k_vcf_cells, k_vcf_gt), %d records x %d samples, %.1f MB of text per step" % (B, S, n_text / 1e6),
             "value": B * S / (k_ms * 1e-3), "unit": UNIT, "kernel_ms": k_ms, "gpu_launches_per_step": 5,
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_step": alg, "bytes_per_cell": alg / (B * S)},
             "e2e": {"value": n_e2e * B * S / wall, "unit": UNIT, "h2d_bytes_per_step": n_text, "steps": n_e2e,
                     "note": "pinned host text -> H2D -> k_vcf_* -> k_place_rows -> simulate -> D2H (VGL_HOST_NARROW); host wall clock, two slots"},
