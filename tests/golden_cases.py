@@ -24,3 +24,20 @@ def case_sites(cid):
     if cid not in _cache:
         _cache[cid] = vgl_dump.read_dump(os.path.join(GOLD, cid + ".vgld.gz"))
     return _cache[cid]
+
+
+# ---- tests/golden/fuzz: captures of seeded random configurations (tools/make_golden_fuzz.py, tests/fuzz_cases.py)
+FUZZ = os.path.join(GOLD, "fuzz")
+FUZZ_MANIFEST = json.load(open(os.path.join(FUZZ, "manifest.json"))) if os.path.exists(os.path.join(FUZZ, "manifest.json")) else {}
+FUZZ_IDS = sorted(FUZZ_MANIFEST)
+
+
+def fuzz_args(cid) -> vargs.SimArgs:
+    m = FUZZ_MANIFEST[cid]
+    return vargs.parse_args(m["argv"], qs_bins=m.get("qs_bins"), depths=m.get("depths"))
+
+
+def fuzz_sites(cid):
+    if cid not in _cache:
+        _cache[cid] = vgl_dump.read_dump(os.path.join(FUZZ, cid + ".vgld.gz"))
+    return _cache[cid]

@@ -36,6 +36,14 @@ def batch_from_dump(sites, args):
         codes, n_deep = [], 0
         for d in sites:
             o = 0
+            n_site_deep = int((d.fmt_dp > 255).sum())
+            if len(d.em_n) == 0 and n_site_deep:
+                # the site returned before calculate_gls (--rm-invar-sites, vcfgl.cpp:677): the reference drew no
+                # subsample, the ABI still takes one block per deep cell (ignored for a skipped site)
+                codes += [np.zeros(255, np.uint16)] * n_site_deep
+                n_deep += n_site_deep
+                continue
+            assert len(d.em_n) == n_site_deep, (len(d.em_n), n_site_deep)
             for k in range(len(d.em_n)):
                 m = int(d.em_n[k])
                 codes.append(d.em_codes[o:o + 255])

@@ -19,8 +19,16 @@ def bits(x):
 
 @pytest.mark.parametrize("cid", gc.CASE_IDS)
 def test_oracle_reproduces_reference_dump(cid):
-    a = gc.case_args(cid)
-    sites = gc.case_sites(cid)
+    check_oracle_on_dump(cid, gc.case_args(cid), gc.case_sites(cid))
+
+
+@pytest.mark.parametrize("cid", gc.FUZZ_IDS)
+def test_oracle_reproduces_fuzz_dump(cid):
+    """32 seeded random configurations captured from the reference (tests/golden/fuzz, tools/make_golden_fuzz.py)"""
+    check_oracle_on_dump(cid, gc.fuzz_args(cid), gc.fuzz_sites(cid), need_values=False)
+
+
+def check_oracle_on_dump(cid, a, sites, need_values=True):
     assert sites, "empty dump"
     orc = oracle_lib.Oracle(a, sites[0].S)
     n_checked = 0
@@ -42,7 +50,7 @@ def test_oracle_reproduces_reference_dump(cid):
                 assert got.shape == want.shape, (cid, k, key)
                 assert np.array_equal(got, want), (cid, k, key, o[key], d.out[key])
                 n_checked += got.size
-    assert n_checked > 0
+    assert n_checked > 0 or not need_values
 
 
 def test_precalc_anchor_values():
