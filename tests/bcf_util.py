@@ -23,7 +23,15 @@ BCF_CASES = [c for c in gc.CASE_IDS if not is_gvcf(c)]
 
 
 def reference_bcf(cid):
-    return bo.read_bcf(os.path.join(BCF_DIR, cid + ".bcf.gz"))
+    return bo.read_bcf(os.path.join(gc.FUZZ if cid in gc.FUZZ_MANIFEST else BCF_DIR, cid + ".bcf.gz"))
+
+
+def any_args(cid):
+    return gc.fuzz_args(cid) if cid in gc.FUZZ_MANIFEST else gc.case_args(cid)
+
+
+def any_sites(cid):
+    return gc.fuzz_sites(cid) if cid in gc.FUZZ_MANIFEST else gc.case_sites(cid)
 
 
 def enabled_tags(a):

@@ -59,10 +59,10 @@ def assert_records_close(got, want, where):
     return False
 
 
-@pytest.mark.parametrize("cid", bu.BCF_CASES)
+@pytest.mark.parametrize("cid", bu.BCF_CASES + gc.FUZZ_IDS)
 def test_replay_records_equal_the_reference_file(cid):
-    a = gc.case_args(cid)
-    sites = gc.case_sites(cid)
+    a = bu.any_args(cid)
+    sites = bu.any_sites(cid)
     S = sites[0].S
     _, ids, recs = bu.reference_bcf(cid)
     gt, rp = replay_util.batch_from_dump(sites, a)

@@ -3,7 +3,7 @@
 
 Draws N seeded random hot-path configurations (tests/fuzz_cases.py), runs each through the unmodified
 and the instrumented reference binary (their VCF outputs must agree), and stores the replay captures as
-tests/golden/fuzz/fz<NN>.vgld.gz with a manifest of the arguments (file arguments inlined), so the GPU
+tests/golden/fuzz/fz<NN>.vgld.gz (+ the `-O u` file of the same run, fz<NN>.bcf.gz) with a manifest of the arguments (file arguments inlined), so the GPU
 box can check the CUDA path against them without /root/reference."""
 import gzip
 import json
@@ -55,6 +55,13 @@ def main():
             continue
         with gzip.GzipFile(os.path.join(OUT, cid + ".vgld.gz"), "wb", compresslevel=9, mtime=0) as g:
             g.write(open(dump, "rb").read())
+        # the same run with -O u: the records the output-path tests compare with (tests/test_bcf_oracle.py, tests/test_gpu_bcf.py)
+        u_argv = [("u" if i and ref_argv[i - 1] == "-O" else x) for i, x in enumerate(ref_argv)]
+        ru = subprocess.run([BIN, "-i", vcf, "-o", os.path.join(tmp, cid + ".u")] + u_argv, capture_output=True, text=True)
+        if ru.returncode:
+            raise SystemExit("reference -O u failed on %s: %s" % (u_argv, ru.stderr[-800:]))
+        with gzip.GzipFile(os.path.join(OUT, cid + ".bcf.gz"), "wb", compresslevel=9, mtime=0) as g:
+            g.write(open(os.path.join(tmp, cid + ".u.bcf"), "rb").read())
         manifest[cid] = dict(entry, source="tools/make_golden_fuzz.py (seed %d, draw %d)" % (SEED, k),
                              pinned_by="unmodified reference binary run in the build container")
         print(cid, " ".join(entry["argv"]), "| dump", os.path.getsize(dump))
