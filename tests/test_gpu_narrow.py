@@ -81,12 +81,14 @@ def test_narrow_equals_int32_native(name):
             assert np.array_equal(miss.all(1), s["fmt_dp"] == 0) and np.array_equal(miss.any(1), miss.all(1))
 
 
-@pytest.mark.parametrize("cid", ["x_s40_gl1_cfg2", "x_s40_cfg4tags", "x_gl2_eq2_bins", "test13"])
+@pytest.mark.parametrize("cid", ["x_s40_gl1_cfg2", "x_s40_cfg4tags", "x_gl2_eq2_bins", "test13"] + gc.FUZZ_IDS)
 def test_narrow_equals_int32_replay(cid):
-    if cid not in gc.CASE_IDS:
+    if cid in gc.FUZZ_MANIFEST:       # the random-configuration captures (tests/golden/fuzz)
+        a, sites = gc.fuzz_args(cid), gc.fuzz_sites(cid)
+    elif cid in gc.CASE_IDS:
+        a, sites = gc.case_args(cid), gc.case_sites(cid)
+    else:
         pytest.skip("no such capture")
-    a = gc.case_args(cid)
-    sites = gc.case_sites(cid)
     S = sites[0].S
     gt, rp = replay_util.batch_from_dump(sites, a)
     wide = run(a, S, gt, len(sites), capi.HOST_I32, replay=rp)
