@@ -9,9 +9,15 @@ import gvcf_util as gu
 
 @pytest.mark.parametrize("cid", gu.CASES)
 def test_blocks_equal_reference_output(cid):
-    a, kept, (text, ids, recs) = gu.load(cid)
+    a, kept, bcf = gu.load(cid)
+    check_blocks(a, kept, bcf, where=cid)
+
+
+def check_blocks(a, kept, bcf, where=None):
+    """the oracle's merge of the captured sites `kept` == the records of the reference's output `bcf`; -> number of blocks"""
+    text, ids, recs = bcf
     out = gu.go.merge(gu.oracle_input(kept), gu.dps_of(a))
-    assert len(out) == len(recs), (len(out), len(recs))
+    assert len(out) == len(recs), (where, len(out), len(recs))
     n_blocks = 0
     for o, rec in zip(out, recs):
         r = gu.decode(rec, ids)
@@ -32,6 +38,7 @@ def test_blocks_equal_reference_output(cid):
         assert np.array_equal(r["fmt"]["DP"], o["dp"])
         assert np.array_equal(r["fmt"]["PL"], o["pl"])
         assert len(r["alleles"]) == 2      # REF, <*> / <NON_REF>
+    return n_blocks
 
 
 def test_dp_range():
