@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 from fuzz_cases import draw_case, reference_exited
+from vcfgl_b200 import args as vargs
 import oracle_lib
 import vgl_dump
 from test_oracle_golden import OUT_KEYS, bits
@@ -31,7 +32,10 @@ def test_oracle_equals_live_reference_on_random_configurations(block, tmp_path):
     rnd = random.Random(7100 + block)
     n_sites_checked = n_values = 0
     for k in range(12):
-        ref_argv, a, vcf, _ = draw_case(rnd, str(tmp_path), k)
+        ref_argv, a, vcf, entry = draw_case(rnd, str(tmp_path), k)
+        if "-addFormatDP" not in ref_argv and k % 2:      # FORMAT/DP is on by default (io.cpp): also run without it
+            ref_argv += ["-addFormatDP", "0"]
+            a = vargs.parse_args(entry["argv"] + ["-addFormatDP", "0"], qs_bins=entry["qs_bins"], depths=entry["depths"])
         dump = str(tmp_path / ("c%d.vgld" % k))
         r = subprocess.run([BIN_DUMP, "-i", vcf, "-o", str(tmp_path / ("c%d" % k))] + ref_argv,
                            capture_output=True, text=True, env=dict(os.environ, VGL_DUMP_PATH=dump))
