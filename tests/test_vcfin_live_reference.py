@@ -29,7 +29,7 @@ HDR = ("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed
        "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n")
 
 
-def random_vcf(rnd, acgt):
+def random_vcf(rnd, acgt, extra_values=(".", "3", "17", "250")):
     S = rnd.choice([1, 2, 3, 5, 8])
     n_rec = rnd.randrange(4, 40)
     p_alt = rnd.choice([0.0, 0.05, 0.3, 0.6, 1.0])     # 0 / 1: runs of invariant records for --rm-invar-sites
@@ -58,7 +58,7 @@ def random_vcf(rnd, acgt):
                 g = rnd.choice(["." + sep + h, h + sep + "."])
             else:
                 g = sep.join(str(rnd.randrange(1, n_real + 1) if rnd.random() < p_alt else 0) for _h in range(2))
-            cols.append(":".join([g] + [rnd.choice([".", "3", "17", "250"]) for _x in range(n_extra)]))
+            cols.append(":".join([g] + [rnd.choice(extra_values) for _x in range(n_extra)]))
         recs.append(["chrA", str(pos), rnd.choice([".", ".", "rs%d" % pos, "a;b"]), ref, ",".join(alts),
                      rnd.choice([".", "30", "12.5"]), rnd.choice([".", "PASS", "q10"]),
                      rnd.choice([".", "NS=3"]), ":".join(["GT", "DP", "GQ"][:1 + n_extra])] + cols)
