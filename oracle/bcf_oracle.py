@@ -109,12 +109,15 @@ def alleles_of_site(n_alleles, alleles2acgt, info_dp, do_unobserved, do_gvcf):
     return out
 
 
-def encode_record(rid, pos, qual_bits, id_bytes, filter_info_bytes, n_info_in, alleles, n_samples, dict_ids, fmt, info):
+def encode_record(rid, pos, qual_bits, id_bytes, filter_info_bytes, n_info_in, alleles, n_samples, dict_ids, fmt, info, in_fmt=()):
     """One BCF record exactly as bcf_write() emits it after the reference's edits.
 
     id_bytes / filter_info_bytes: the input record's typed ID string and its FILTER vector followed by its own INFO
     pairs -- bytes bcf1_sync copies unchanged (vcf.c:1802-1838).  fmt / info: dicts tag -> array for the enabled
     tags (FORMAT arrays hold n_samples * k values).  dict_ids: {"FORMAT/GL": id, "INFO/DP": id, ...}.
+    in_fmt: the FORMAT blocks the INPUT record carried besides GT, in its order, as (dictionary id, block bytes): the
+    reference removes only GT (bcf_update_genotypes(NULL), vcfgl.cpp:793); bcf_update_format replaces a block whose key a
+    simulated tag has IN PLACE (vcf.c: the fmt slot is kept) and appends the other simulated tags behind the input's.
     """
     shared = bytearray(id_bytes)
     for al in alleles:
@@ -130,17 +133,29 @@ def encode_record(rid, pos, qual_bits, id_bytes, filter_info_bytes, n_info_in, a
         n_info += 1
     indiv = bytearray()
     n_fmt = 0
-    for tag in FORMAT_ORDER:
-        if tag not in fmt:
-            continue
+
+    def put(tag):
         v = np.asarray(fmt[tag])
         nps = v.size // n_samples
         assert nps * n_samples == v.size and nps > 0
-        indiv += enc_int1(dict_ids["FORMAT/" + tag])
+        out = enc_int1(dict_ids["FORMAT/" + tag])
         if tag in ("GL", "GP"):
-            indiv += enc_size(nps, BT_FLOAT) + np.ascontiguousarray(v, dtype="<f4").tobytes()
+            return out + enc_size(nps, BT_FLOAT) + np.ascontiguousarray(v, dtype="<f4").tobytes()
+        return out + enc_vint(v, nps)
+
+    by_id = {dict_ids["FORMAT/" + tag]: tag for tag in FORMAT_ORDER if tag in fmt}
+    placed = set()
+    for key, block in in_fmt:
+        if key in by_id:            # the simulated tag takes the input block's slot
+            indiv += put(by_id[key])
+            placed.add(by_id[key])
         else:
-            indiv += enc_vint(v, nps)
+            indiv += block
+        n_fmt += 1
+    for tag in FORMAT_ORDER:
+        if tag not in fmt or tag in placed:
+            continue
+        indiv += put(tag)
         n_fmt += 1
     rlen = len(alleles[0]) if alleles else 0  # _bcf1_sync_alleles, no INFO/END on these records
     head = struct.pack("<IIiiiIHHI", len(shared) + 24, len(indiv), rid, pos, rlen, qual_bits, n_info, len(alleles),
