@@ -101,8 +101,13 @@ def test_cli_mirror_validation():
                 "-d 1 -e 0.01 -bv 1e-5",               # beta variance without error-qs
                 "-d 1 -e 0.01 --adjust-qs 2",          # needs -addQS
                 "-d 501 -e 0.01",                      # depth range
+                "-d 1 -e 0.01 --gvcf-dps 1,5",         # io.cpp:986-989: needs -doGVCF 1
+                "-d 1 -e 0.01 --adjust-qs 4",          # io.cpp:891: needs -printPileup 1
+                "-d 1 -e 0.01 --adjust-qs 8",          # io.cpp:894: needs -printQScores 1
+                "-d 1 -e 0.01 --adjust-qs 16",         # io.cpp:897: needs -printGlError 1
                 "-d 1 -e 0.01 -doGVCF 1"):             # gVCF requirements
         with pytest.raises(vargs.ArgError):
             vargs.parse_args(bad.split())
+    assert vargs.parse_args("-d 1 -e 0.01 --adjust-qs 12 -printPileup 1 -printQScores 1".split()).adjust_qs == 12
     al, be = vargs.beta_shape(0.01, 1e-5)
     assert abs(al - 9.89) < 1e-9 and abs(be - 979.11) < 1e-9

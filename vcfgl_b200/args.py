@@ -213,6 +213,13 @@ def validate(a: SimArgs) -> None:
         raise ArgError("--adjust-qs 1 requires --precise-gl 0")
     if (a.adjust_qs & 2) and not a.add_qs:
         raise ArgError("--adjust-qs 2 requires -addQS 1")
+    other = {k.lower(): v for k, v in a.other.items()}       # the print flags are accepted, not on the hot path
+    for bit, flag, on in ((4, "--printPileup", a.print_pileup), (8, "--printQScores", int(other.get("-printqscores", 0))),
+                          (16, "--printGlError", int(other.get("-printglerror", 0)))):
+        if (a.adjust_qs & bit) and not on:
+            raise ArgError("--adjust-qs %d requires %s 1 (io.cpp:891-899)" % (bit, flag))
+    if int(other.get("-printglerror", 0)) and a.gl_model == 1:
+        raise ArgError("-printGlError 1 is not supported with --gl-model 1 (io.cpp:993-995)")
     if a.precise_gl and a.gl_model == 1:
         raise ArgError("--precise-gl 1 is not supported with --gl-model 1")
     if a.beta_variance >= 0 and a.error_qs == 0:
@@ -237,6 +244,8 @@ def validate(a: SimArgs) -> None:
         if not a.add_fmt_dp or a.rm_invar_sites or a.gvcf_dps is None or not a.add_pl \
                 or a.do_unobserved not in (1, 2, 4, 5):
             raise ArgError("-doGVCF 1 requirements not met (io.cpp:958-985)")
+    if a.gvcf_dps is not None and not a.do_gvcf:
+        raise ArgError("--gvcf-dps requires -doGVCF 1 (io.cpp:986-989)")
     if not a.add_i16 and a.i16_mapq != 20:
         raise ArgError("--i16-mapq requires -addI16 1")
 
