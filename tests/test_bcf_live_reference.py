@@ -45,10 +45,11 @@ def test_records_with_input_format_blocks(block, tmp_path):
         assert len(kept) == len(recs)
         # FORMAT keys of the input record at each position (no -explode here: one record per site)
         in_keys = {}
+        names = [l.split("ID=")[1].split(",")[0] for l in buf.decode().splitlines() if l.startswith("##contig")]
         for line in buf.decode().splitlines():
             if line and not line.startswith("#"):
                 f = line.split("\t")
-                in_keys[int(f[1]) - 1] = f[8].split(":")[1:]
+                in_keys[(names.index(f[0]), int(f[1]) - 1)] = f[8].split(":")[1:]
         ftags, itags = bu.enabled_tags(a)
         sim_ids = {ids["FORMAT/" + t] for t in ftags}
         for d, rec in zip(kept, recs):
@@ -57,7 +58,7 @@ def test_records_with_input_format_blocks(block, tmp_path):
             passthrough = r["filter_bytes"] + b"".join(b for _, b in r["infos"][:n_in])
             raw = {key: blk for key, n, t, blk in r["fmts"] if key not in sim_ids}     # blocks the reference copied from the input
             in_fmt = []
-            for name in in_keys[d.pos]:
+            for name in in_keys[(d.rid, d.pos)]:
                 key = ids["FORMAT/" + name]
                 in_fmt.append((key, raw.get(key)))
                 n_in_place += key in sim_ids
@@ -65,6 +66,6 @@ def test_records_with_input_format_blocks(block, tmp_path):
             alleles = bo.alleles_of_site(d.n_alleles, d.alleles2acgt, d.info_dp, a.do_unobserved, a.do_gvcf)
             fmt, info = bu.site_arrays(a, d)
             got = bo.encode_record(d.rid, d.pos, r["qual_bits"], r["id_bytes"], passthrough, n_in, alleles, d.S, ids, fmt, info, in_fmt=in_fmt)
-            assert got == rec, (argv, d.pos, in_keys[d.pos], [k_ for k_, *_ in r["fmts"]])
+            assert got == rec, (argv, d.pos, in_keys[(d.rid, d.pos)], [k_ for k_, *_ in r["fmts"]])
         n_records += len(recs)
     assert n_records > 50 and n_passed_through > 20 and n_in_place > 20, (n_records, n_passed_through, n_in_place)

@@ -22,7 +22,7 @@ BIN_DUMP = os.path.join(ROOT, "oracle", "_ref", "vcfgl_ref_dump")
 pytestmark = pytest.mark.skipif(not os.path.exists(BIN_DUMP), reason="oracle/_ref not built (needs /root/reference)")
 
 HDR = ("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n##FILTER=<ID=q10,Description=\"low\">\n"
-       "##contig=<ID=chrA,length=%d>\n"
+       "%s"
        "##INFO=<ID=NS,Number=1,Type=Integer,Description=\"n\">\n##INFO=<ID=AF,Number=A,Type=Float,Description=\"af\">\n"
        "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
        "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n##FORMAT=<ID=GQ,Number=1,Type=Integer,Description=\"q\">\n"
@@ -36,7 +36,15 @@ def random_vcf(rnd, acgt, extra_values=(".", "3", "17", "250")):
     p_miss = rnd.choice([0.0, 0.0, 0.1, 0.5])
     pos = 0
     recs = []
+    # one, two or three contigs; the records move on to the next contig at a random record (possibly never: a contig without records)
+    contigs = ["chrA", "chrB", "chrC"][:rnd.choice([1, 1, 2, 3])]
+    lengths = []
+    ci = 0
     for _ in range(n_rec):
+        if ci + 1 < len(contigs) and rnd.random() < 0.08:
+            lengths.append(pos + rnd.choice([0, 0, 3, 11]))
+            ci += 1
+            pos = 0
         pos += rnd.choice([1, 1, 1, 2, 3, 7])
         if acgt:
             ref = rnd.choice("ACGT")
@@ -59,11 +67,14 @@ def random_vcf(rnd, acgt, extra_values=(".", "3", "17", "250")):
             else:
                 g = sep.join(str(rnd.randrange(1, n_real + 1) if rnd.random() < p_alt else 0) for _h in range(2))
             cols.append(":".join([g] + [rnd.choice(extra_values) for _x in range(n_extra)]))
-        recs.append(["chrA", str(pos), rnd.choice([".", ".", "rs%d" % pos, "a;b"]), ref, ",".join(alts),
+        recs.append([contigs[ci], str(pos), rnd.choice([".", ".", "rs%d" % pos, "a;b"]), ref, ",".join(alts),
                      rnd.choice([".", "30", "12.5"]), rnd.choice([".", "PASS", "q10"]),
                      rnd.choice([".", "NS=3"]), ":".join(["GT", "DP", "GQ"][:1 + n_extra])] + cols)
-    length = pos + rnd.choice([0, 0, 3, 11])
-    text = HDR % (length, "\t".join("s%d" % i for i in range(S))) + "".join("\t".join(r) + "\n" for r in recs)
+    lengths.append(pos + rnd.choice([0, 0, 3, 11]))
+    while len(lengths) < len(contigs):
+        lengths.append(rnd.choice([1, 4, 9]))
+    ctg = "".join("##contig=<ID=%s,length=%d>\n" % cl for cl in zip(contigs, lengths))
+    text = HDR % (ctg, "\t".join("s%d" % i for i in range(S))) + "".join("\t".join(r) + "\n" for r in recs)
     return S, text.encode()
 
 
