@@ -73,7 +73,10 @@ def draw_case(rnd, tmp, k):
 #   ASSERT(adjqScore_i != -1), vcfgl.cpp:558 -- --error-qs 2 with --adjust-qs: a beta draw of exactly 0.0 (tiny alpha) leaves the
 #       adjusted score unset (vcfgl.cpp:499-506)
 #   bcf_enc_vfloat: Assertion `n >= 0' (htslib/vcf.c:2339) -- -doGVCF 1 with -addQS 1 on some low-depth runs (a crash of the reference)
-REFERENCE_EXITS = ("Could not find a range for qs value", "sim->nAlleles > 1", "adjqScore_i != -1", "bcf_enc_vfloat: Assertion")
+#   bcf_update_format: Assertion `nps && nps*line->n_sample==n' (htslib/vcf.c:4452) -- -doGVCF 1 on some multi-allelic / missing-genotype
+#       inputs (the reference itself warns that gVCF mode is under development, io.cpp:964)
+REFERENCE_EXITS = ("Could not find a range for qs value", "sim->nAlleles > 1", "adjqScore_i != -1", "bcf_enc_vfloat: Assertion",
+                   "bcf_update_format: Assertion")
 
 
 def reference_exited(stderr: str) -> bool:

@@ -62,3 +62,34 @@ def test_gvcf_oracle_equals_live_reference(block, tmp_path):
         n_blocks += nb
         n_records += len(bcf[2])
     assert n_blocks > 10 and n_records > 50, (n_blocks, n_records)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_gvcf_oracle_on_multi_contig_inputs(block, tmp_path):
+    """the same on the random texts of tests/test_vcfin_live_reference.py: one to three contigs (a block never spans two), ACGT or
+    binary alleles, missing genotypes, gaps"""
+    from test_vcfin_live_reference import random_vcf
+    rnd = random.Random(8400 + 2 * block)
+    n_blocks = n_records = 0
+    for k in range(10):
+        acgt = rnd.random() < 0.5
+        S, buf = random_vcf(rnd, acgt)
+        _, _, _, _, argv = draw(rnd)
+        argv += ["--source", str(int(acgt))]
+        a = vargs.parse_args(argv)
+        vcf = str(tmp_path / ("in%d.vcf" % k))
+        open(vcf, "wb").write(buf)
+        dump = str(tmp_path / ("c%d.vgld" % k))
+        u_argv = [("u" if i and argv[i - 1] == "-O" else x) for i, x in enumerate(argv)]
+        exited = False
+        for binary, av, env in ((BIN_DUMP, argv, dict(os.environ, VGL_DUMP_PATH=dump)), (BIN, u_argv, dict(os.environ))):
+            r = subprocess.run([binary, "-i", vcf, "-o", str(tmp_path / ("o%d" % k))] + av, capture_output=True, text=True, env=env)
+            exited = exited or (r.returncode != 0 and reference_exited(r.stderr))
+            assert r.returncode == 0 or exited, (av, r.stderr[-1500:])
+        if exited:
+            continue
+        kept = [d for d in vgl_dump.read_dump(dump) if d.ret == 0] if os.path.exists(dump) and os.path.getsize(dump) else []
+        bcf = gu.bo.read_bcf(str(tmp_path / ("o%d.bcf" % k)))
+        n_blocks += check_blocks(a, kept, bcf, where=(argv, buf.decode()))
+        n_records += len(bcf[2])
+    assert n_blocks > 5 and n_records > 50, (n_blocks, n_records)
