@@ -1,31 +1,32 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the vcfgl simulate-and-score hot path on B200.
+"""bench.py -- benchmark of the vcfgl simulate-and-score hot path on B200.
 
-Metric (BASELINE.json): simulate+GL throughput in site x sample cells/s.
-Workload (configs[1]): synthetic msprime-shaped genotypes, 100 diploid samples x 1M biallelic
-sites, Poisson depth 10, error 0.01, GL model 1, tags GL+PL+AD(+DP).  One STEP = one pass of the
-hot path over one batch of 131072 sites (13.1 M cells, ~1.9 GB of tag planes -- larger than the
-126 MB L2, so no L2 flush is needed between steps); 8 steps = 1,048,576 sites.
+Metric (BASELINE.json): simulate+GL throughput in site x sample cells/s, and the fraction of the HBM roofline.
+Headline workload: the scaling config (configs[4]): 10 000 diploid samples, Poisson depth 30, error 0.01, GL model 1,
+tags GL+PL+AD(+DP) on synthetic msprime-shaped genotypes.  The other BASELINE configs (cfg2, cfg3(i), cfg3(ii), cfg4) run
+as sub-legs of the same JSON line (`configs`), each with its kernel time, throughput and roofline fraction.
 
-  value  kernel-side throughput: genotypes resident in HBM, results left in HBM, CUDA events
-         on the launching stream (torch's current stream, handed to libvgl).
-  e2e    the same metric through the C ABI with HOST buffers: pinned H2D of the packed
-         genotypes and D2H of every tag plane inside the timed region, two slots in flight.
-         Planes cross PCIe in the ABI's VGL_HOST_NARROW form (GL float32; PL / AD / DP as the
-         8-bit values BCF stores, narrowed on the device); `e2e.i32_planes` is the same loop
-         with the int32 planes of VGL_HOST_I32 (add_tags() layout) for comparison.
-  roofline      algorithmic bytes / device time of the kernels, against the
-                measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline  the reference binary itself (oracle/_ref/vcfgl_ref, built from /root/reference)
-                on a bounded sample of the same workload on this box's host, 1 thread.
+One STEP = `launches_per_step` batches of `batch_sites` sites pushed through the hot path back to back (>= 50 ms of device
+work; four slots in flight so the stream never waits for the host).  Each batch writes more than the 126 MB L2 holds, so no
+L2 flush is needed between launches.
 
-  input_path    (N=1) SURVEY.md 8(f) row 1: one step's worth of msprime-shaped VCF text through k_vcf_* -- kernel-side
-                throughput with its own roofline, end to end from pinned host text (to narrowed arrays and to finished BCF
-                records), and the oracle's single-threaded C parser as CPU baseline.
-  gvcf_merge    (workloads with -doGVCF) SURVEY.md 8(f) row 3: the block merger on the batch resident in HBM.
+  value  kernel-side throughput: genotypes resident in HBM, results left in HBM, CUDA events on the launching stream
+         (torch's current stream, handed to libvgl); max over ranks.
+  e2e    the same metric through the C ABI with HOST buffers: pinned H2D of the packed genotypes and D2H of every tag plane
+         inside the timed region.  Planes cross PCIe in the ABI's VGL_HOST_NARROW form (GL float32; PL / AD / DP as the
+         8-bit values BCF stores, narrowed on the device); `e2e.i32_planes` is the same loop with the int32 planes of
+         VGL_HOST_I32 (add_tags() layout), `e2e.bcf_records` with finished BCF records (VGL_HOST_BCF).
+  roofline      algorithmic bytes of one launch / the kernel's average launch duration (CUDA events inside
+                the timed region), against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference binary itself (oracle/_ref/vcfgl_ref, built from /root/reference) on a bounded sample of the
+                same workload on this box's host, 1 thread.
+  configs       (N=1) the other BASELINE.json configs, kernel side: value, kernel_ms, roofline {frac, traffic}.
+  input_path    (N=1) SURVEY.md 8(f) row 1: one batch of msprime-shaped VCF text through k_vcf_*.
+  gvcf_merge    (cfg4) SURVEY.md 8(f) row 3: the block merger on the batch resident in HBM.
 
-`--impl reference` times the reference CPU binary with one process per host core on contiguous
-site shards (the reference cannot thread its simulation).
+`--impl reference` times the reference CPU binary with one process per host core on contiguous site shards (the reference
+cannot thread its simulation); each process runs long enough (>= 65 536 sites at 100 samples, the same
+number of cells at other sample counts) that its start-up cost is below 3 % of its run.
 
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 via torch.distributed.run.
 """
@@ -44,44 +45,56 @@ sys.path.insert(0, ROOT)
 
 METRIC = "sim+GL site x sample cells/s"
 UNIT = "cells/s"
-N_SAMPLES = 100
-BATCH_SITES = 131072
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "vcfgl_ref")
-VCFGL_ARGS = "-d 10 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1".split()
-WORKLOAD = ("cfg2: 100 samples x 1M sites (steps of %d sites), Poisson depth 10, e=0.01, GL model 1, "
-            "tags GL+PL+AD+DP, seed 42" % BATCH_SITES)
+RTA3_BINS = [(0, 2, 2), (3, 14, 12), (15, 30, 23), (31, 63, 37)]   # test/data/rta3_qs_bins.csv, last range opened to 63
+
+# name -> samples, sites per batch (launch), launches per >= 50 ms step, launches of a sub-leg, reference-arm sites per process,
+#         vcfgl options, --qs-bins, share of invariant sites, description
+WORKLOADS = {
+    "cfg5": dict(S=10000, B=4440, L=32, sub=64, ref_sites=256,
+                 args="-d 30 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1",
+                 text="cfg5 shape: 10000 samples, Poisson depth 30, e=0.01, GL model 1, tags GL+PL+AD+DP, seed 42"),
+    "cfg2": dict(S=100, B=131072, L=110, sub=220, ref_sites=65536,
+                 args="-d 10 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1",
+                 text="cfg2: 100 samples x 1M sites, Poisson depth 10, e=0.01, GL model 1, tags GL+PL+AD+DP, seed 42"),
+    "cfg3a": dict(S=1000, B=8192, L=64, sub=128, ref_sites=6554,
+                  args="-d 10 -e 0.01 -GL 2 -eq 1 -bv 1e-5 -addGL 1 -addPL 1",
+                  text="cfg3(i): 1000 samples, Poisson depth 10, GL model 2, per-site beta error (mean 0.01, var 1e-5), "
+                       "tags GL+PL+DP, seed 42"),
+    "cfg3b": dict(S=1000, B=8192, L=48, sub=96, ref_sites=2048, bins=RTA3_BINS,
+                  args="-d 10 -e 0.01 -GL 2 -eq 2 -bv 1e-5 -addGL 1 -addPL 1",
+                  text="cfg3(ii): 1000 samples, Poisson depth 10, GL model 2, per-read beta error (mean 0.01, var 1e-5) + RTA3 "
+                       "qs bins, tags GL+PL+DP, seed 42"),
+    "cfg4": dict(S=100, B=131072, L=48, sub=96, ref_sites=65536, invariant=0.99,
+                 args="-d 10 -e 0.001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,5,10 -addGL 1 -addPL 1 -addI16 1 -addQS 1",
+                 text="cfg4: 100 samples, 99% invariant sites (-explode), Poisson depth 10, e=0.001, GL model 1, <*> allele, gVCF, "
+                      "tags GL+PL+DP+I16+QS, seed 42"),
+}
+N_SLOTS = 4
 
 
-QS_BINS = None          # --qs-bins ranges of the workload (start, end, value)
-INVARIANT_SHARE = 0.0   # share of all-hom-ref sites in the synthetic genotypes (gVCF / -explode runs)
+class Workload:
+    def __init__(self, name):
+        w = WORKLOADS[name]
+        self.name, self.S, self.B, self.L, self.sub = name, w["S"], w["B"], w["L"], w["sub"]
+        self.ref_sites = w["ref_sites"]
+        self.argv = w["args"].split()
+        self.bins = w.get("bins")
+        self.invariant = w.get("invariant", 0.0)
+        self.text = "%s (launches of %d sites)" % (w["text"], self.B)
 
+    def sim_args(self):
+        from vcfgl_b200 import args as vargs
+        return vargs.parse_args(["--seed", "42"] + self.argv, qs_bins=self.bins)
 
-def set_workload(name):
-    """cfg2 is the bench line (BASELINE.json configs[1]).  The others are the remaining BASELINE.json configs at a
-    per-step size that fits one GPU; they are measured with `--workload` for DESIGN.md and never replace the cfg2 line."""
-    global N_SAMPLES, BATCH_SITES, VCFGL_ARGS, WORKLOAD, QS_BINS, INVARIANT_SHARE
-    if name == "cfg5":
-        N_SAMPLES, BATCH_SITES = 10000, 4440   # 5 x (148 SMs x 6 resident CTAs) tiles
-        VCFGL_ARGS = "-d 30 -e 0.01 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1".split()
-        WORKLOAD = ("cfg5 shape: 10000 samples, steps of %d sites, Poisson depth 30, e=0.01, GL model 1, "
-                    "tags GL+PL+AD+DP, seed 42" % BATCH_SITES)
-    elif name == "cfg3a":
-        N_SAMPLES, BATCH_SITES = 1000, 8192
-        VCFGL_ARGS = "-d 10 -e 0.01 -GL 2 -eq 1 -bv 1e-5 -addGL 1 -addPL 1".split()
-        WORKLOAD = ("cfg3(i): 1000 samples, steps of %d sites, Poisson depth 10, GL model 2, per-site beta error "
-                    "(mean 0.01, var 1e-5), tags GL+PL+DP, seed 42" % BATCH_SITES)
-    elif name == "cfg3b":
-        N_SAMPLES, BATCH_SITES = 1000, 8192
-        VCFGL_ARGS = "-d 10 -e 0.01 -GL 2 -eq 2 -bv 1e-5 -addGL 1 -addPL 1".split()
-        QS_BINS = [(0, 2, 2), (3, 14, 12), (15, 30, 23), (31, 63, 37)]   # RTA3 bins, last range opened to 63
-        WORKLOAD = ("cfg3(ii): 1000 samples, steps of %d sites, Poisson depth 10, GL model 2, per-read beta error "
-                    "(mean 0.01, var 1e-5) + RTA3 qs bins, tags GL+PL+DP, seed 42" % BATCH_SITES)
-    elif name == "cfg4":
-        N_SAMPLES, BATCH_SITES = 100, 131072
-        VCFGL_ARGS = "-d 10 -e 0.001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,5,10 -addGL 1 -addPL 1 -addI16 1 -addQS 1".split()
-        INVARIANT_SHARE = 0.99
-        WORKLOAD = ("cfg4: 100 samples, steps of %d sites of which 99%% invariant (-explode), Poisson depth 10, e=0.001, "
-                    "GL model 1, <*> allele, tags GL+PL+DP+I16+QS, seed 42" % BATCH_SITES)
+    def genotypes(self, seed):
+        """packed genotypes of one batch [B, S] and the haplotype matrix they came from"""
+        import numpy as np
+        from vcfgl_b200 import synth
+        hap = synth.sfs_genotypes(self.B, self.S, seed)
+        if self.invariant > 0:      # positions absent from the input VCF: hom-ref records synthesised by -explode
+            hap[np.random.default_rng(7 + seed).random(self.B) < self.invariant] = 0
+        return synth.pack_gt(hap), hap      # binary source: REF=0 -> A, ALT=1 -> C (vcfgl.cpp:103-128)
 
 
 def measured_peak():
@@ -137,24 +150,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def sim_args():
-    from vcfgl_b200 import args as vargs
-    return vargs.parse_args(["--seed", "42"] + VCFGL_ARGS, qs_bins=QS_BINS)
-
-
 # --------------------------------------------------------------------------- reference CPU arm
-def run_reference_shards(n_proc, sites_per_proc, seed, tmp):
+def run_reference_shards(wl, n_proc, sites_per_proc, seed, tmp):
     """P processes of the unmodified reference on P contiguous site shards; returns (cells, wall_s)"""
+    import numpy as np
     from vcfgl_b200 import synth
     paths = []
     for r in range(n_proc):
-        hap = synth.sfs_genotypes(sites_per_proc, N_SAMPLES, seed + r)
+        hap = synth.sfs_genotypes(sites_per_proc, wl.S, seed + r)
+        if wl.invariant > 0:
+            hap[np.random.default_rng(7 + seed + r).random(sites_per_proc) < wl.invariant] = 0
         pos = synth.positions(sites_per_proc, sites_per_proc * 10, seed + r)
         path = os.path.join(tmp, "shard%d.vcf" % r)
         synth.write_vcf(path, hap, pos, sites_per_proc * 10)
         paths.append(path)
+    argv = list(wl.argv)
+    if wl.bins:
+        bins_path = os.path.join(tmp, "qs_bins.csv")
+        with open(bins_path, "w") as fh:
+            fh.write("".join("%d,%d,%d\n" % b for b in wl.bins))
+        argv += ["--qs-bins", bins_path]
     t0 = time.perf_counter()
-    procs = [subprocess.Popen([REF_BIN, "-i", path, "-o", path + ".out", "-O", "u", "--seed", "42"] + VCFGL_ARGS,
+    procs = [subprocess.Popen([REF_BIN, "-i", path, "-o", path + ".out", "-O", "u", "--seed", "42"] + argv,
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for path in paths]
     rcs = [p.wait() for p in procs]
     wall = time.perf_counter() - t0
@@ -166,7 +183,7 @@ def run_reference_shards(n_proc, sites_per_proc, seed, tmp):
                 os.remove(path + ext)
             except OSError:
                 pass
-    return n_proc * sites_per_proc * N_SAMPLES, wall
+    return n_proc * sites_per_proc * wl.S, wall
 
 
 def reference_arm(opt):
@@ -176,38 +193,168 @@ def reference_arm(opt):
     if not os.path.exists(REF_BIN):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/vcfgl_ref was not built (needs /root/reference at build time)"}))
         return
+    wl = Workload(opt.workload)
     cores = os.cpu_count() or 1
-    sites_per_proc = 8192
+    sites_per_proc = wl.ref_sites
     tmp = tempfile.mkdtemp(prefix="vgl_refbench_")
     try:
         for w in range(opt.warmup):
-            run_reference_shards(cores, 1024, 1000 + w, tmp)
+            run_reference_shards(wl, cores, max(2, sites_per_proc // 64), 1000 + w, tmp)
         cells = 0
         wall = 0.0
         for k in range(opt.steps):
-            c, t = run_reference_shards(cores, sites_per_proc, 2000 + 97 * k, tmp)
+            c, t = run_reference_shards(wl, cores, sites_per_proc, 2000 + 97 * k, tmp)
             cells += c
             wall += t
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     value = cells / wall
     sample = "%d steps x %d processes x %d sites x %d samples, -O u, one process per host core" % (
-        opt.steps, cores, sites_per_proc, N_SAMPLES)
+        opt.steps, cores, sites_per_proc, wl.S)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": opt.gpus, "steps": opt.steps,
         "warmup": opt.warmup, "ms_per_step": 1e3 * wall / opt.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU binary (vcfgl v1.3.0 da6a334), whole program: VCF parse + simulate + BCF -O u"},
+        "config": {"workload": wl.text, "note": "reference CPU binary (vcfgl v1.3.0 da6a334), whole program: VCF parse + simulate + BCF -O u"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 # --------------------------------------------------------------------------- GPU arm
+def load_traffic(name):
+    """DRAM bytes of one launch from the last `ncu --set full` capture of this workload (profiles/traffic.json)"""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[name]
+        return tr["dram_bytes_per_launch"], tr["source"], tr.get("cells_per_launch")
+    except Exception:
+        return None, None, None
+
+
+class KernelLeg:
+    """The hot path of one workload with genotypes resident in HBM and results left in HBM: N_SLOTS slots of one context
+    on one stream, every launch on its own range of global site ids."""
+
+    def __init__(self, wl, local, rank, stream, site0):
+        from vcfgl_b200 import capi
+        self.capi, self.wl, self.stream = capi, wl, stream
+        self.a = wl.sim_args()
+        self.gt, self.hap = wl.genotypes(20260002 + rank)
+        self.ctx = capi.Context(capi.params_from_args(self.a, wl.S, max_batch_sites=wl.B, n_slots=N_SLOTS, device_id=local, host_output=False))
+        self.kernels = self.ctx.native_kernels()
+        self.site = site0
+        for s in range(N_SLOTS):
+            self.ctx.set_stream(s, stream.cuda_stream)
+            self.ctx.input_buffer(s)[:] = self.gt
+            self.ctx.submit(s, self.site, wl.B)          # uploads the genotypes once (untimed)
+            self.ctx.sync(s)
+            self.site += wl.B
+        self.i = 0
+
+    def run(self, n_launches, kern_ms=None):
+        """n launches, N_SLOTS in flight; adds the per-launch device times (libvgl's CUDA events around the kernels) to kern_ms"""
+        ctx, capi, B = self.ctx, self.capi, self.wl.B
+        pend = []
+        for _ in range(n_launches):
+            s = self.i % N_SLOTS
+            if len(pend) == N_SLOTS:
+                d = pend.pop(0)
+                ctx.sync(d)
+                if kern_ms is not None:
+                    kern_ms += ctx.timing(d)
+            ctx.submit(s, self.site, B, flags=capi.SUBMIT_GT_ON_DEVICE)
+            pend.append(s)
+            self.site += B
+            self.i += 1
+        for d in pend:
+            ctx.sync(d)
+            if kern_ms is not None:
+                kern_ms += ctx.timing(d)
+        return d
+
+    def roofline(self, last_slot, kern_ms_per_launch):
+        """algorithmic bytes of the last launch / the kernels' average launch duration"""
+        capi, ctx = self.capi, self.ctx
+        b = ctx.wait(last_slot)
+        ctx.copy_sites(last_slot, b)
+        alg = ctx.algorithmic_bytes(b)
+        fused = "+" not in self.kernels      # one kernel does the whole path; libvgl reports its time in the T_EMIT interval
+        k = kern_ms_per_launch
+        dev_ms = float(k[capi.T_EMIT]) if fused else float(k[capi.T_SIM] + k[capi.T_SITE] + k[capi.T_SCAN] + k[capi.T_EMIT])
+        peak, peak_src = measured_peak()
+        achieved = alg / (dev_ms * 1e-3) / 1e9
+        traffic, traffic_src, traffic_cells = load_traffic(self.wl.name)
+        cells = self.wl.B * self.wl.S
+        if traffic is not None and traffic_cells and traffic_cells != cells:      # captured at another batch size: scale per cell
+            traffic = int(traffic * cells / traffic_cells)
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": "%s (%s per batch; algorithmic bytes of the whole path / its average launch duration, CUDA events on the "
+                          "launching stream)" % (self.kernels, "one launch" if fused else "four launches"),
+                "algorithmic_bytes_per_launch": alg, "bytes_per_cell": alg / cells,
+                "kernel_ms": {self.kernels: dev_ms} if fused else
+                             {"k_sim": float(k[capi.T_SIM]), "k_site": float(k[capi.T_SITE]),
+                              "k_scan": float(k[capi.T_SCAN]), "k_emit": float(k[capi.T_EMIT])}}
+        g15 = float((b.sites["n_genotypes"] == 15).mean())
+        return roof, dev_ms, alg, g15, b
+
+    def gvcf_leg(self, slot):
+        """the gVCF block merger (bcf_utils.cpp:662-942) over the batch still resident in HBM"""
+        import numpy as np
+        a, ctx, B, S = self.a, self.ctx, self.wl.B, self.wl.S
+        if not (a.do_gvcf and a.do_unobserved in (1, 2)):
+            return None
+        dps = [int(x) for x in a.gvcf_dps.split(",")]
+        rid0, pos0 = np.zeros(B, np.int32), np.arange(B, dtype=np.int32)
+        gm = [ctx.gvcf_merge(slot, rid0, pos0, dps) for _ in range(4)]
+        g_ms = min(x["ms_kernels"] for x in gm[1:])
+        members = int(gm[-1]["recs"]["n_members"].sum())
+        g_alg = 4 * B * S + 16 * members * S + 16 * gm[-1]["n_blocks"] * S      # DP plane in; DP + 3 PL per member cell in; per block out
+        pk, pk_src = measured_peak()
+        return {"what": "gVCF block merger on one batch (sites at consecutive positions of one contig)",
+                "kernel_ms": g_ms, "records": int(len(gm[-1]["recs"])), "blocks": int(gm[-1]["n_blocks"]),
+                "member_sites": members, "sites_per_s": B / (g_ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": g_alg / (g_ms * 1e-3) / 1e9, "peak": pk, "unit": "GB/s",
+                             "frac": g_alg / (g_ms * 1e-3) / 1e9 / pk, "peak_source": pk_src, "traffic": None,
+                             "algorithmic_bytes_per_launch": g_alg}}
+
+    def close(self):
+        self.ctx.close()
+
+
+def sub_leg(name, local, stream):
+    """one of the other BASELINE configs, kernel side (N=1): `sub` launches timed by CUDA events on the launching stream"""
+    import numpy as np
+    import torch
+    from vcfgl_b200 import capi
+    wl = Workload(name)
+    leg = KernelLeg(wl, local, 0, stream, 0)
+    leg.run(8)
+    torch.cuda.synchronize()
+    l0 = leg.ctx.launch_count()
+    kern_ms = np.zeros(capi.T_COUNT)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    last = leg.run(wl.sub, kern_ms)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = leg.ctx.launch_count() - l0
+    roof, dev_ms, alg, g15, _ = leg.roofline(last, kern_ms / wl.sub)
+    out = {"workload": wl.text, "value": wl.sub * wl.B * wl.S / (ms * 1e-3), "unit": UNIT, "launches": wl.sub, "gpu_launches": int(launches),
+           "cells_per_launch": wl.B * wl.S, "ms_per_launch": ms / wl.sub, "kernel_ms": dev_ms, "kernels": leg.kernels,
+           "timed_region_ms": ms, "sites_with_15_genotypes": g15, "roofline": roof}
+    g = leg.gvcf_leg(last)
+    if g is not None:
+        out["gvcf_merge"] = g
+    leg.close()
+    return out
+
+
 def gpu_arm(opt):
     import numpy as np
     import torch
-    from vcfgl_b200 import capi, synth
+    from vcfgl_b200 import capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,112 +372,78 @@ def gpu_arm(opt):
             dist.barrier()
         torch.cuda.synchronize()
 
-    a = sim_args()
-    B, S, K, W = BATCH_SITES, N_SAMPLES, opt.steps, opt.warmup
-    cells_per_step = B * S
-    # contiguous site range of this rank (weak scaling: every rank simulates K + W batches of its own)
-    site0 = rank * (K + W + 4) * B
-    hap = synth.sfs_genotypes(B, S, 20260002 + rank)
-    if INVARIANT_SHARE > 0:      # positions absent from the input VCF: hom-ref records synthesised by -explode
-        inv = np.random.default_rng(7 + rank).random(B) < INVARIANT_SHARE
-        hap[inv] = 0
-    gt = synth.pack_gt(hap)      # binary source: REF=0 -> A, ALT=1 -> C (vcfgl.cpp:103-128)
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = Workload(opt.workload)
+    B, S, L, K, W = wl.B, wl.S, wl.L, opt.steps, opt.warmup
+    cells_per_step = B * S * L
+    # contiguous site range of this rank (weak scaling: every rank simulates (K + W) * L + spare batches of its own)
+    per_rank_sites = ((K + W) * L + 64) * B
+    site0 = rank * per_rank_sites
     stream = torch.cuda.Stream()   # an explicit stream: libvgl treats a NULL stream as "use the slot's own"
 
     # ---------------- value: genotypes resident in HBM, results stay in HBM
-    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=False))
-    kernels = ctx.native_kernels()
-    for s in (0, 1):
-        ctx.set_stream(s, stream.cuda_stream)
-        ctx.input_buffer(s)[:] = gt
-        ctx.submit(s, site0, B)          # uploads the genotypes once (untimed)
-        ctx.wait(s)
-    step = [0]
-
-    def run_steps(n, flags):
-        # two slots in flight on one stream keeps the GPU queue non-empty
-        pend = []
-        for _ in range(n):
-            s = step[0] & 1
-            if len(pend) == 2:
-                ctx.wait(pend.pop(0))
-            ctx.submit(s, site0 + step[0] * B, B, flags=flags)
-            pend.append(s)
-            step[0] += 1
-        for s in pend:
-            ctx.wait(s)
-
-    run_steps(W, capi.SUBMIT_GT_ON_DEVICE)
+    leg = KernelLeg(wl, local, rank, stream, site0)
+    a, gt, hap, kernels = leg.a, leg.gt, leg.hap, leg.kernels
+    leg.run(W * L)
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
         clocks.start()
-    l0 = ctx.launch_count()
+    l0 = leg.ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = np.zeros(capi.T_COUNT)
     ev0.record(stream)
-    pend = []
-    for _ in range(K):
-        s = step[0] & 1
-        if len(pend) == 2:
-            d = pend.pop(0)
-            ctx.wait(d)
-            kern_ms += ctx.timing(d)
-        ctx.submit(s, site0 + step[0] * B, B, flags=capi.SUBMIT_GT_ON_DEVICE)
-        pend.append(s)
-        step[0] += 1
-    for d in pend:
-        last = ctx.wait(d)
-        kern_ms += ctx.timing(d)
+    last = leg.run(K * L, kern_ms)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count() - l0
+    launches = leg.ctx.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
-    ctx.copy_sites(d, last)
-    alg_bytes = ctx.algorithmic_bytes(last)           # of one step (last batch)
-    g_share = float((last.sites["n_genotypes"] == 15).mean())
-    gvcf_leg = None
-    if a.do_gvcf and a.do_unobserved in (1, 2) and rank == 0:
-        # the gVCF block merger (bcf_utils.cpp:662-942) over the batch still resident in HBM
-        dps = [int(x) for x in a.gvcf_dps.split(",")]
-        rid0, pos0 = np.zeros(B, np.int32), np.arange(B, dtype=np.int32)
-        gm = [ctx.gvcf_merge(d, rid0, pos0, dps) for _ in range(4)]
-        g_ms = min(x["ms_kernels"] for x in gm[1:])
-        members = int(gm[-1]["recs"]["n_members"].sum())
-        g_alg = 4 * B * S + 16 * members * S + 16 * gm[-1]["n_blocks"] * S      # DP plane in; DP + 3 PL per member cell in; per block out
-        pk, pk_src = measured_peak()
-        gvcf_leg = {"what": "k_gvcf_key / plan_local / plan_global / fin / reduce on one step (sites at consecutive positions of one contig)",
-                    "kernel_ms": g_ms, "gpu_launches": 5, "records": int(len(gm[-1]["recs"])), "blocks": int(gm[-1]["n_blocks"]),
-                    "member_sites": members, "sites_per_s": B / (g_ms * 1e-3),
-                    "roofline": {"bound": "hbm", "achieved": g_alg / (g_ms * 1e-3) / 1e9, "peak": pk, "unit": "GB/s",
-                                 "frac": g_alg / (g_ms * 1e-3) / 1e9 / pk, "peak_source": pk_src, "traffic": None,
-                                 "algorithmic_bytes_per_step": g_alg}}
-    ctx.close()
-    t_max = ms
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_max = float(t.item())
+    roof, dev_ms, alg_bytes, g_share, _ = leg.roofline(last, kern_ms / (K * L))
+    gvcf_leg = leg.gvcf_leg(last) if rank == 0 else None
+    site_next = leg.site
+    leg.close()
+    t_max = max_over_ranks(ms)
     value = world * K * cells_per_step / (t_max * 1e-3)
 
     # ---------------- e2e: host buffers, H2D + kernels + D2H inside the timed region
     if opt.skip_e2e:     # profiling runs only (ncu); such a line is not a bench result
         if rank == 0:
-            print(json.dumps({"profiling_only": True, "value": value, "kernel_ms": (kern_ms / K).tolist()}))
+            print(json.dumps({"profiling_only": True, "value": value, "kernel_ms": dev_ms}))
         return
     Ke = max(2, min(K, 4))
-    s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+    Le = max(2, min(L, int(opt.e2e_launches)))       # batches per e2e step
+    E_SLOTS = 3
+    streams = [torch.cuda.Stream() for _ in range(E_SLOTS)]
 
-    def e2e_steps(ctx, bufs, n, first, bcf_in=None):
-        pend = []
-        d2h = 0
+    def out_bytes(b):
+        """bytes the D2H copies of one batch moved (spans as libvgl copies them)"""
+        r = b.raw
+        if b.bcf_off is not None:   # VGL_HOST_BCF: the record stream, its offsets, the per-site records
+            return int(b.bcf_bytes + 8 * (b.n_sites + 1) + b.n_sites * capi.SITE_DTYPE.itemsize)
+        w = (b.narrow_bits // 8) if b.narrow_bits else 4          # DP / AD element width
+        g_up, r_up = b.n_sites * ((S * 15 + 3) & ~3), b.n_sites * ((S * 5 + 3) & ~3)   # tile kernels: whole spans
+        if "k_tile" not in kernels:
+            g_up, r_up = b.g_elems, b.r_elems
+        n = b.n_sites * S * w + b.n_sites * capi.SITE_DTYPE.itemsize
+        n += 4 * g_up * sum(bool(x) for x in (r.gl, r.gp))
+        n += g_up * (4 * bool(r.pl) + bool(r.pl_u8))
+        n += w * r_up * sum(bool(x) for x in ((r.ad_n, r.adf_n, r.adr_n) if b.narrow_bits else (r.ad, r.adf, r.adr)))
+        return int(n)
+
+    def e2e_batches(ctx, bufs, n, first, bcf_in=None):
+        pend, d2h = [], 0
         for i in range(n):
-            s = i & 1
-            if len(pend) == 2:
-                b = ctx.wait(pend.pop(0))
-                d2h = out_bytes(b)
-            bufs[s][:] = gt                       # the caller packs this step's genotypes into pinned memory
+            s = i % E_SLOTS
+            if len(pend) == E_SLOTS:
+                d2h = out_bytes(ctx.wait(pend.pop(0)))
+            bufs[s][:] = gt                       # the caller packs this batch's genotypes into pinned memory
             if bcf_in is not None:                # ... and the fields its input records pass through (CHROM, POS; ID ".", FILTER ".")
                 sin = bcf_in[s]
                 sin["pos"][:B] = np.arange(first + i * B, first + (i + 1) * B, dtype=np.int64) % (1 << 30)
@@ -338,86 +451,52 @@ def gpu_arm(opt):
             ctx.submit(s, first + i * B, B)
             pend.append(s)
         for s in pend:
-            b = ctx.wait(s)
-            d2h = out_bytes(b)
+            d2h = out_bytes(ctx.wait(s))
         return d2h
 
-    def out_bytes(b):
-        r = b.raw
-        if b.bcf_off is not None:   # VGL_HOST_BCF: the record stream, its offsets, the per-site records
-            return int(b.bcf_bytes + 8 * (b.n_sites + 1) + b.n_sites * capi.SITE_DTYPE.itemsize)
-        w = (b.narrow_bits // 8) if b.narrow_bits else 4          # DP / AD element width
-        n = b.n_sites * S * w + b.n_sites * capi.SITE_DTYPE.itemsize
-        n += 4 * b.g_elems * sum(bool(x) for x in (r.gl, r.gp))
-        n += b.g_elems * (4 * bool(r.pl) + bool(r.pl_u8))
-        n += w * b.r_elems * sum(bool(x) for x in ((r.ad_n, r.adf_n, r.adr_n) if b.narrow_bits else (r.ad, r.adf, r.adr)))
-        return int(n)
-
     def e2e_run(mode):
-        ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=mode,
+        ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=E_SLOTS, device_id=local, host_output=mode,
                                                  bcf_dict=dict(DP=1, GL=2, PL=3, GP=4, AD=5, ADF=6, ADR=7, QS=8, I16=9)))
-        ctx.set_stream(0, s_a.cuda_stream)
-        ctx.set_stream(1, s_b.cuda_stream)
-        bufs = [ctx.input_buffer(0), ctx.input_buffer(1)]
-        bcf_in = [ctx.bcf_input(0)[0], ctx.bcf_input(1)[0]] if mode == capi.HOST_BCF else None
-        e2e_steps(ctx, bufs, 2, site0 + (K + W) * B, bcf_in)
+        for s in range(E_SLOTS):
+            ctx.set_stream(s, streams[s].cuda_stream)
+        bufs = [ctx.input_buffer(s) for s in range(E_SLOTS)]
+        bcf_in = [ctx.bcf_input(s)[0] for s in range(E_SLOTS)] if mode == capi.HOST_BCF else None
+        e2e_batches(ctx, bufs, E_SLOTS, site_next, bcf_in)
         barrier()
         l0 = ctx.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(s_a)
-        d2h = e2e_steps(ctx, bufs, Ke, site0 + (K + W) * B, bcf_in)
-        s_a.wait_stream(s_b)
-        e1.record(s_a)
+        t0 = time.perf_counter()
+        d2h = e2e_batches(ctx, bufs, Ke * Le, site_next, bcf_in)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3     # host wall clock around the user-facing calls (every wait has returned)
         barrier()
-        ms = e0.elapsed_time(e1)
         n_launch = ctx.launch_count() - l0
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms)
         ctx.close()
-        return world * Ke * cells_per_step / (ms * 1e-3), d2h, n_launch
+        return world * Ke * Le * B * S / (ms * 1e-3), d2h, n_launch
 
     e2e_i32, d2h_i32, _ = e2e_run(capi.HOST_I32)
     e2e_value, d2h_bytes, e2e_launches = e2e_run(capi.HOST_NARROW)
     e2e_bcf = None
     if not a.do_gvcf:   # serialised BCF records (the gVCF block merger consumes arrays)
         v, nb, nl = e2e_run(capi.HOST_BCF)
-        e2e_bcf = {"value": v, "d2h_bytes_per_step": nb, "gpu_launches": int(nl),
+        e2e_bcf = {"value": v, "d2h_bytes_per_step": nb * Le, "gpu_launches": int(nl),
                    "planes": "VGL_HOST_BCF: complete BCF records serialised on the device (k_bcf_plan/scan/emit), byte-identical to "
                              "the reference's -O u stream; the host only appends the buffer to the output"}
 
-    # ---------------- input path: VCF text -> packed genotypes on the device -> the same kernels
-    input_path = None
+    # ---------------- the other BASELINE configs, kernel side; the input path
+    configs, input_path = None, None
+    if world == 1 and not opt.no_configs:
+        configs = {}
+        for name in ("cfg2", "cfg3a", "cfg3b", "cfg4", "cfg5"):
+            if name != wl.name:
+                configs[name] = sub_leg(name, local, stream)
     if world == 1 and not opt.no_input_path:
-        input_path = input_path_leg(a, gt, hap, B, S, site0 + (K + W + 2) * B, local, peak_of=measured_peak)
+        input_path = input_path_leg(a, gt, hap, B, S, site_next + 64 * B, local, peak_of=measured_peak)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-
-    # ---------------- roofline of the kernels (device time inside the timed region)
-    peak, peak_src = measured_peak()
-    kern_ms /= K
-    fused = "+" not in kernels       # one kernel does the whole path; libvgl reports its time in the T_EMIT interval
-    dev_ms = float(kern_ms[capi.T_EMIT]) if fused else \
-        float(kern_ms[capi.T_SIM] + kern_ms[capi.T_SITE] + kern_ms[capi.T_SCAN] + kern_ms[capi.T_EMIT])
-    achieved = alg_bytes / (dev_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    try:    # DRAM bytes of one launch from the last `ncu --set full` capture of this workload (profiles/README.md)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[opt.workload]
-        traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
-    except Exception:
-        pass
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-            "kernel": "%s (%s per step; algorithmic bytes of the whole path / its average launch duration, CUDA events "
-                      "on the launching stream)" % (kernels, "one launch" if fused else "four launches"),
-            "algorithmic_bytes_per_step": alg_bytes, "bytes_per_cell": alg_bytes / cells_per_step,
-            "kernel_ms": {kernels: dev_ms} if fused else
-                         {"k_sim": float(kern_ms[capi.T_SIM]), "k_site": float(kern_ms[capi.T_SITE]),
-                          "k_scan": float(kern_ms[capi.T_SCAN]), "k_emit": float(kern_ms[capi.T_EMIT])}}
 
     # ---------------- CPU baseline: the reference binary, 1 thread, bounded sample
     cpu = None
@@ -425,8 +504,8 @@ def gpu_arm(opt):
         if os.path.exists(REF_BIN):
             tmp = tempfile.mkdtemp(prefix="vgl_cpubase_")
             try:
-                n_sites = 196608
-                cells, wall = run_reference_shards(1, n_sites, 4242, tmp)
+                n_sites = wl.ref_sites * 2
+                cells, wall = run_reference_shards(wl, 1, n_sites, 4242, tmp)
                 cpu = {"value": cells / wall, "unit": UNIT, "cores": 1, "kind": "reference",
                        "sample": "%d sites x %d samples of the same workload, reference binary -O u, wall %.1f s" % (n_sites, S, wall)}
             finally:
@@ -438,18 +517,19 @@ def gpu_arm(opt):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_sites": B, "cells_per_step": cells_per_step,
-                   "l2": "no flush: each step writes %.2f GB of tag planes (> 126 MB L2)" % (alg_bytes / 1e9),
-                   "n_samples": S,
+        "config": {"workload": wl.text, "batch_sites": B, "launches_per_step": L, "cells_per_step": cells_per_step,
+                   "slots_in_flight": N_SLOTS,
+                   "l2": "no flush: each launch writes %.2f GB of tag planes (> 126 MB L2)" % (alg_bytes / 1e9),
+                   "n_samples": S, "timed_region_s": t_max * 1e-3,
                    "sites_with_15_genotypes": g_share, "sharding": "contiguous site ranges per GPU, no collective"},
         "roofline": roof, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * S), "d2h_bytes_per_step": d2h_bytes,
-                "steps": Ke, "gpu_launches": int(e2e_launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * S * Le), "d2h_bytes_per_step": d2h_bytes * Le,
+                "steps": Ke, "launches_per_step": Le, "gpu_launches": int(e2e_launches), "timer": "host wall clock, max over ranks",
                 "planes": "VGL_HOST_NARROW: GL float32, PL/AD/DP narrowed on the device to the 8-bit values BCF stores",
-                "i32_planes": {"value": e2e_i32, "d2h_bytes_per_step": d2h_i32,
+                "i32_planes": {"value": e2e_i32, "d2h_bytes_per_step": d2h_i32 * Le,
                                "planes": "VGL_HOST_I32: every plane int32/float32 as add_tags() hands them to htslib"},
                 "bcf_records": e2e_bcf},
-        "input_path": input_path, "gvcf_merge": gvcf_leg,
+        "configs": configs, "input_path": input_path, "gvcf_merge": gvcf_leg,
         "gpu_launches": int(launches), "clocks": clk}
     print(json.dumps(line))
     if dist is not None:
@@ -584,10 +664,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-input-path", action="store_true", help="skip the VCF-text input-path leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-legs of the other BASELINE configs")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: stop after the kernel-side loop")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3a", "cfg3b", "cfg4", "cfg5"])
+    ap.add_argument("--e2e-launches", type=int, default=6, help="batches per end-to-end step")
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     opt = ap.parse_args()
-    set_workload(opt.workload)
     opt.warmup = max(opt.warmup, 3) if opt.impl == "b200" else opt.warmup
     if opt.impl == "reference":
         reference_arm(opt)

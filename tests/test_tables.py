@@ -121,10 +121,10 @@ def test_qs_class_table_is_the_beta_law(shim, mean, var, shift, bins):
         for lo, hi, val in ((0, 2, 2), (3, 14, 12), (15, 30, 23), (31, 40 if bins == "rta3_40" else 63, 37)):
             lut[lo:hi + 1] = val
             bin_max = hi
-    words = np.zeros(512, np.uint32)
+    words = np.zeros(768, np.uint32)
     prob = np.zeros(257, np.float64)
     n = shim.shim_qs_classes(a, b, shift, int(bins is not None), lut.ctypes.data, bin_max, words.ctypes.data, prob.ctypes.data)
-    assert n == 512
+    assert n == 768
     assert abs(prob.sum() - 1.0) < 1e-9
     want = np.zeros(257)
     d = stats.beta(a, b)
@@ -142,7 +142,7 @@ def test_qs_class_table_is_the_beta_law(shim, mean, var, shift, bins):
         assert prob[256] > 0        # the reference would exit on such a read; the kernel raises VGL_ERANGE
     # the alias table: exact column arithmetic
     alias, thr = words[:256] & 0xFF, (words[:256] >> 8).astype(np.int64)
-    info = words[256:]
+    info = words[256:512]
     mass = np.zeros(256, np.int64)
     for k in range(256):
         if alias[k] == k:
@@ -154,3 +154,23 @@ def test_qs_class_table_is_the_beta_law(shim, mean, var, shift, bins):
         if mass[c]:
             q, oob = int(info[c] & 0xFF), int((info[c] >> 9) & 1)
             assert mass[c] == round(prob[256 if oob else q] * 2 ** 32), (c, q)
+    # words 512..767: the conditional law of the classes other than the heaviest one (the tile kernel draws the number of
+    # such reads per cell, then their classes from this table)
+    dom = int(np.argmax(mass))
+    alias2, thr2 = words[512:] & 0xFF, (words[512:] >> 8).astype(np.int64)
+    m2 = np.zeros(256, np.int64)
+    for k in range(256):
+        if alias2[k] == k:
+            m2[k] += 1 << 24
+        else:
+            m2[k] += thr2[k]
+            m2[alias2[k]] += (1 << 24) - thr2[k]
+    assert m2.sum() == 2 ** 32
+    rest = 2 ** 32 - mass[dom]
+    if rest == 0:
+        assert m2[dom] == 2 ** 32
+    else:
+        assert m2[dom] == 0
+        for c in range(256):
+            if c != dom:
+                assert abs(m2[c] / 2 ** 32 - mass[c] / rest) < 1e-9, (c, m2[c], mass[c])

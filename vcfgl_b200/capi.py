@@ -403,6 +403,12 @@ class Context:
         self._ck(self.L.vgl_wait(self.h, slot, C.byref(out)))
         return Batch(out, self.params.tag_mask, bool(self.params.host_output))
 
+    def sync(self, slot: int) -> int:
+        """vgl_wait without building the numpy views: blocks until the slot's batch is complete, returns its status"""
+        out = VglBatchOut()
+        self._ck(self.L.vgl_wait(self.h, slot, C.byref(out)))
+        return int(out.status)
+
     def copy_sites(self, slot: int, batch: Batch) -> np.ndarray:
         """host_output=0: fetch the per-site records of a waited slot (also stored on `batch.sites`)"""
         arr = np.zeros(batch.n_sites, SITE_DTYPE)

@@ -71,6 +71,7 @@ struct Slot {
     DevBuf r_depths, r_off, r_bases, r_strands, r_qs, r_adjqs, r_eprob, r_tails, r_deep_cells, r_deep_codes;
     float ms[VGL_T_COUNT] = {};
     bool had_d2h = false;
+    bool early_d2h = false; // the plane copies were enqueued by vgl_submit (tile kernels: the spans are known on the host)
     // vgl_native_draws() results (host)
     std::vector<int32_t> dr_depths;
     std::vector<int64_t> dr_off;
@@ -393,12 +394,18 @@ static int create_impl(vgl_ctx* ctx)
             CK(cudaMemset(s.d_tile_state, 0, (B + 2) * sizeof(unsigned long long)));
         }
         CK(cudaMemset(s.d_totals, 0, 4 * sizeof(int64_t)));
-        if (t & VGL_TAG_GL) CK(cudaMalloc((void**)&s.d_gl, ctx->g_cap * 4));
-        if (t & VGL_TAG_GP) CK(cudaMalloc((void**)&s.d_gp, ctx->g_cap * 4));
-        if (t & VGL_TAG_PL) CK(cudaMalloc((void**)&s.d_pl, ctx->g_cap * 4));
-        if (t & VGL_TAG_FMT_AD) CK(cudaMalloc((void**)&s.d_ad, ctx->r_cap * 4));
-        if (t & VGL_TAG_FMT_ADF) CK(cudaMalloc((void**)&s.d_adf, ctx->r_cap * 4));
-        if (t & VGL_TAG_FMT_ADR) CK(cudaMalloc((void**)&s.d_adr, ctx->r_cap * 4));
+        // planes are zeroed once: words the kernels never write (block padding of the general path, tile-end holes) must not
+        // hold another allocation's bits when a whole span is narrowed or copied to the host
+        auto plane = [&](void** d, size_t bytes) -> cudaError_t {
+            cudaError_t e = cudaMalloc(d, bytes);
+            return e != cudaSuccess ? e : cudaMemset(*d, 0, bytes);
+        };
+        if (t & VGL_TAG_GL) CK(plane((void**)&s.d_gl, ctx->g_cap * 4));
+        if (t & VGL_TAG_GP) CK(plane((void**)&s.d_gp, ctx->g_cap * 4));
+        if (t & VGL_TAG_PL) CK(plane((void**)&s.d_pl, ctx->g_cap * 4));
+        if (t & VGL_TAG_FMT_AD) CK(plane((void**)&s.d_ad, ctx->r_cap * 4));
+        if (t & VGL_TAG_FMT_ADF) CK(plane((void**)&s.d_adf, ctx->r_cap * 4));
+        if (t & VGL_TAG_FMT_ADR) CK(plane((void**)&s.d_adr, ctx->r_cap * 4));
         if (p.host_output == VGL_HOST_NARROW) {
             const size_t w = (size_t)ctx->narrow_bits / 8, cells4 = (cells + 3) & ~(size_t)3;
             CK(cudaMalloc(&s.d_dpn, cells4 * w));
@@ -701,6 +708,7 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.need_cellq = ctx->need_cellq;
     p.need_tail = ctx->need_tail;
     p.fast_div = ctx->fast_div;
+    p.zero_holes = prm.host_output == VGL_HOST_I32 || prm.host_output == VGL_HOST_NARROW;
     p.lut_log10 = ctx->d_lut;
     p.m1_bsum = ctx->d_m1_bsum;
     p.m1_het = ctx->d_m1_het;
@@ -869,6 +877,30 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     else if (bcf) {}
     else if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[EV_META], st));
+    s.early_d2h = false;
+    if (tile_launch && (prm.host_output == VGL_HOST_I32 || narrow)) {
+        // tile kernels lay tiles out at a fixed stride: the spans are n_sites x (padded 15-genotype / 5-allele block) whatever the
+        // sites turn out to be (holes are zeroed, tile_zero_holes), so the plane copies queue up behind the kernels right away
+        // instead of waiting for the host to come back for the totals
+        const size_t g_up = (size_t)n_sites * (((size_t)S * 15 + 3) & ~(size_t)3), r_up = (size_t)n_sites * (((size_t)S * 5 + 3) & ~(size_t)3);
+        CK(cudaEventRecord(s.ev[EV_D2H0], st));
+        if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, g_up * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, g_up * 4, cudaMemcpyDeviceToHost, st));
+        if (narrow) {
+            const size_t w = (size_t)ctx->narrow_bits / 8;
+            if (s.d_pl8) CK(cudaMemcpyAsync(s.h_pl8, s.d_pl8, g_up, cudaMemcpyDeviceToHost, st));
+            if (s.d_adn) CK(cudaMemcpyAsync(s.h_adn, s.d_adn, r_up * w, cudaMemcpyDeviceToHost, st));
+            if (s.d_adfn) CK(cudaMemcpyAsync(s.h_adfn, s.d_adfn, r_up * w, cudaMemcpyDeviceToHost, st));
+            if (s.d_adrn) CK(cudaMemcpyAsync(s.h_adrn, s.d_adrn, r_up * w, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (s.d_pl) CK(cudaMemcpyAsync(s.h_pl, s.d_pl, g_up * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_ad) CK(cudaMemcpyAsync(s.h_ad, s.d_ad, r_up * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_adf) CK(cudaMemcpyAsync(s.h_adf, s.d_adf, r_up * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_adr) CK(cudaMemcpyAsync(s.h_adr, s.d_adr, r_up * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaEventRecord(s.ev[EV_D2H1], st));
+        s.early_d2h = true;
+    }
     s.submitted = true;
     s.waited = false;
     s.n_sites = n_sites;
@@ -886,7 +918,10 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
     CK(cudaEventSynchronize(s.ev[EV_META]));
     const int64_t g_elems = s.h_totals[0], r_elems = s.h_totals[1];
     const int32_t status = *reinterpret_cast<int32_t*>(s.h_totals + 2);
-    if (prm.host_output && !s.waited) {
+    if (prm.host_output && !s.waited && s.early_d2h) {
+        CK(cudaEventSynchronize(s.ev[EV_D2H1]));
+        s.had_d2h = true;
+    } else if (prm.host_output && !s.waited) {
         cudaStream_t st = s.stream;
         CK(cudaEventRecord(s.ev[EV_D2H0], st));
         if (prm.host_output == VGL_HOST_BCF) {

@@ -581,7 +581,8 @@ __global__ void __launch_bounds__(VGL_BLOCK) k_emit(const __grid_constant__ DevP
                     for (int i = 0; i < n; ++i) {
                         const Read r = cs.read(p, i);
                         if (n > 255 && !sub.keep()) continue;
-                        const int q = gl_adj ? r.adjqs : r.qs;
+                        int q = gl_adj ? r.adjqs : r.qs;
+                        if (q < 0) { atomicExch(p.status, (int)VGL_ERANGE); q = 0; } // the reference stops on ASSERT(qs >= 0) (zero beta draw / negative --adjust-by)
                         codes[nn++] = (uint16_t)(q << 5 | r.base);
                     }
                 }
@@ -634,7 +635,8 @@ __global__ void __launch_bounds__(VGL_BLOCK) k_emit(const __grid_constant__ DevP
                     if (MODE == GL_M2_FIXED) {
                         c2 = p.homT; c1 = p.het; c0 = p.homF;
                     } else if (MODE == GL_M2_LUT) {
-                        const int q = gl_adj ? r.adjqs : r.qs;
+                        int q = gl_adj ? r.adjqs : r.qs;
+                        if (q < 0) { atomicExch(p.status, (int)VGL_ERANGE); q = 0; } // vcfgl.cpp:558 ASSERT(adjqScore_i != -1)
                         c2 = __ldg(p.lut_log10 + q); c1 = __ldg(p.lut_log10 + 257 + q); c0 = __ldg(p.lut_log10 + 514 + q);
                     } else {
                         const double e = r.eprob;

@@ -186,8 +186,37 @@ double inc_beta(double a, double b, double x)
     return flip ? 1.0 - v : v;
 }
 
+// Walker alias over 256 columns of capacity 2^24 each for integer weights that sum to 2^32 (exact integer arithmetic):
+// entry = stay24 << 8 | alias; a draw keeps its column when its low 24 bits are below stay24
+static std::vector<uint32_t> walker_alias24(const std::vector<unsigned long long>& w)
+{
+    typedef unsigned long long u64;
+    const int K = 256;
+    const u64 cap = 1ull << 24;
+    std::vector<u64> m(K, 0);
+    for (size_t i = 0; i < w.size() && i < (size_t)K; ++i) m[i] = w[i];
+    std::vector<int> small, large, alias(K);
+    std::vector<u64> stay(K, cap);
+    for (int k = 0; k < K; ++k) { alias[k] = k; (m[k] < cap ? small : large).push_back(k); }
+    while (!small.empty() && !large.empty()) {
+        const int s = small.back(), l = large.back();
+        small.pop_back();
+        stay[s] = m[s];
+        alias[s] = l;
+        m[l] -= cap - m[s];
+        if (m[l] < cap) { large.pop_back(); small.push_back(l); }
+    }
+    // leftovers hold exactly one column each (integer arithmetic): alias = itself, any threshold
+    std::vector<uint32_t> out(K, 0u);
+    for (int k = 0; k < K; ++k) {
+        if (alias[k] == k) out[k] = (uint32_t)((cap - 1) << 8) | (uint32_t)k;
+        else out[k] = (uint32_t)(stay[k] << 8) | (uint32_t)alias[k];
+    }
+    return out;
+}
+
 std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_bins, const uint8_t* bin_lut, int bin_max,
-                                     std::vector<double>* prob, std::vector<int>* q_values)
+                                     std::vector<double>* prob, std::vector<int>* q_values, int* dominant, double* p_minor)
 {
     typedef unsigned long long u64;
     if (!(shift >= 0.0)) return {};
@@ -233,27 +262,35 @@ std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_
         prob->assign(257, 0.0);
         for (size_t i = 0; i < wq.size(); ++i) (*prob)[((cls_info[i] >> 9) & 1) ? 256 : (cls_info[i] & 0xFF)] = (double)wq[i] / 4294967296.0;
     }
-    // Walker alias over K columns of capacity 2^24 each (K * 2^24 = 2^32: exact integer arithmetic)
-    const u64 cap = 1ull << 24;
-    std::vector<u64> m(K, 0);
-    for (size_t i = 0; i < wq.size(); ++i) m[i] = wq[i];
-    std::vector<int> small, large, alias(K);
-    std::vector<u64> stay(K, cap);
-    for (int k = 0; k < K; ++k) { alias[k] = k; (m[k] < cap ? small : large).push_back(k); }
-    while (!small.empty() && !large.empty()) {
-        const int s = small.back(), l = large.back();
-        small.pop_back();
-        stay[s] = m[s];
-        alias[s] = l;
-        m[l] -= cap - m[s];
-        if (m[l] < cap) { large.pop_back(); small.push_back(l); }
+    std::vector<uint32_t> out(768, 0u);
+    {
+        const std::vector<uint32_t> al = walker_alias24(wq);
+        for (int k = 0; k < K; ++k) out[k] = al[k];
     }
-    // leftovers hold exactly one column each (integer arithmetic): alias = itself, any threshold
-    std::vector<uint32_t> out(512, 0u);
-    for (int k = 0; k < K; ++k) {
-        if (alias[k] == k) out[k] = (uint32_t)((cap - 1) << 8) | (uint32_t)k;
-        else out[k] = (uint32_t)(stay[k] << 8) | (uint32_t)alias[k]; // keep the column when the low 24 bits of the draw < stay
+    // the conditional law of the classes other than the heaviest one ("minor" classes), quantised to 2^-32 again:
+    // the tile kernel draws how many reads of a cell are minor, then their classes from this table
+    {
+        std::vector<u64> wm(wq.size(), 0);
+        const u64 rest = one32 - wq[heavy];
+        if (rest == 0) {
+            wm[heavy] = one32; // a single class: the table is never consulted
+        } else {
+            u64 s2 = 0;
+            int big = -1;
+            for (size_t i = 0; i < wq.size(); ++i) {
+                if ((int)i == heavy) continue;
+                wm[i] = (u64)((long double)wq[i] / (long double)rest * 4294967296.0L + 0.5L);
+                s2 += wm[i];
+                if (big < 0 || wm[i] > wm[big]) big = (int)i;
+            }
+            if (s2 > one32) wm[big] -= s2 - one32;
+            else wm[big] += one32 - s2;
+        }
+        const std::vector<uint32_t> al = walker_alias24(wm);
+        for (int k = 0; k < K; ++k) out[512 + k] = al[k];
     }
+    if (dominant) *dominant = heavy;
+    if (p_minor) *p_minor = (double)((long double)(one32 - wq[heavy]) / 4294967296.0L);
     // dense index of the quality scores in use (ascending)
     std::vector<int> qidx(256, -1), qv;
     for (int q = 0; q < 256; ++q)
@@ -283,6 +320,27 @@ std::vector<double> m2_const_table(const std::vector<double>& c)
         for (int i = 0; i < 6; ++i) { tc[i] = ry[i]; tc[8 + i] = rx[i]; }
     }
     return t;
+}
+
+bool m2_pure_table(const std::vector<double>& c, std::vector<float>* out)
+{
+    const size_t nq = c.size() / 3;
+    out->assign(nq * 65 * 2, 0.0f);
+    for (size_t q = 0; q < nq; ++q) {
+        const double c2 = c[3 * q], c1 = c[3 * q + 1], c0 = c[3 * q + 2];
+        if (!(c2 >= c1 && c2 >= c0)) return false; // the matching homozygote would not be the running maximum
+        float v2 = -0.0f, v1 = -0.0f, v0 = -0.0f; // bcf_utils.h:310
+        for (int n = 0; n <= 64; ++n) {
+            (*out)[(q * 65 + n) * 2] = v1;
+            (*out)[(q * 65 + n) * 2 + 1] = v0;
+            // one more read of x (gl_methods.cpp:27-58): float += double, then the maximum is subtracted in float
+            const float a2 = (float)((double)v2 + c2), a1 = (float)((double)v1 + c1), a0 = (float)((double)v0 + c0);
+            v2 = a2 - a2;
+            v1 = a1 - a2;
+            v0 = a0 - a2;
+        }
+    }
+    return true;
 }
 
 std::vector<uint32_t> m2_class_map()
@@ -352,6 +410,7 @@ int precalc(double error_rate, int error_qs, int gl_model, int precise_gl, int a
         if (qs > 63) qs = 63;
         if (adjust_qs && adj > 63) adj = 63;
     }
+    if (qs < 0 || (adjust_qs && adj < 0)) return -1; // a negative --adjust-by can push the score below 0: the tables have no such row
     out->qs = qs;
     if (adjust_qs) out->adj_qs = adj;
     if (gl_model == 2) {

@@ -44,13 +44,16 @@ double inc_beta(double a, double b, double x);
 // is Beta(a, b), phred = -10 log10 p, q = (int)(phred + shift) (shift = --adjust-by when the GL uses the adjusted score,
 // else 0), then --qs-bins or the cap at 63; P(q) = I(p_hi) - I(p_lo).  (The read is mis-called with the run-constant
 // --error-rate, independently of its quality score: vcfgl.cpp:485 draws before and apart from :495.)
-// Returned: 512 words = a Walker alias table over 256 columns (threshold24 << 8 | alias; probabilities quantised to
+// Returned: 768 words = a Walker alias table over 256 columns (threshold24 << 8 | alias; probabilities quantised to
 // 2^-32) followed by the class info words: q | out-of-range << 9 | dense index of q << 16 (ascending q; `q_values`
 // receives the scores).  Scores beyond the last --qs-bins range (the reference exits when it draws one, vcfgl.cpp:63)
 // form a class of their own (score 0, bit 9) so that the kernel can raise VGL_ERANGE.  `prob` receives the quantised
 // probabilities ([q], out of range at [256]; for tests).  Empty when the classes do not fit 256 columns.
+// Words 512..767: the Walker alias table of the conditional law of the classes other than the heaviest ("dominant") one;
+// `dominant` receives that class's index (into the info words), `p_minor` the probability that a read is not of it.
 std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_bins, const uint8_t* bin_lut, int bin_max,
-                                     std::vector<double>* prob = nullptr, std::vector<int>* q_values = nullptr);
+                                     std::vector<double>* prob = nullptr, std::vector<int>* q_values = nullptr, int* dominant = nullptr,
+                                     double* p_minor = nullptr);
 
 // Constant tables of the model-2 tile kernel for each (homT, het, homF) triple: per triple M2_TAB_DOUBLES doubles =
 // [4 read bases][17] the constant each of the 15 base pairs (k*(k+1)/2 + j, 4 = unobserved allele) receives from a
@@ -58,6 +61,12 @@ std::vector<uint32_t> qs_class_table(double a, double b, double shift, bool use_
 // a cell whose reads show two bases x, y for a read of y ([0]) or x ([1]).
 enum { M2_TAB_DOUBLES = 84 };
 std::vector<double> m2_const_table(const std::vector<double>& homT_het_homF);
+// GL of a cell whose n <= 64 reads all show the same base x and share one quality score ("pure" cell): the matching
+// homozygote is the maximum after every read, so the vector is a function of n alone: out[(q * 65 + n) * 2 + {0, 1}] = the
+// value of the base pairs that contain x once / not at all (the pair xx holds +0), computed with the reference's
+// float += double, float -= max sequence (gl_methods.cpp:27-58).  False when a triple does not have homT >= het, homF
+// (error rates >= 0.5): the shortcut is then not valid.
+bool m2_pure_table(const std::vector<double>& homT_het_homF, std::vector<float>* out);
 // [16 = x*4+y][8 words]: words 0..2 = six 16-bit masks of the base pairs in each class, words 4,5 = the class of
 // every base pair (3 bits each, pair k at bits 3k)
 std::vector<uint32_t> m2_class_map();

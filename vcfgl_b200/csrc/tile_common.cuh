@@ -243,6 +243,8 @@ __device__ __forceinline__ void tile_phase_b(const DevParams& p, const int lane,
     if (lane == 0) {
         s_base[0] = bg;
         s_base[1] = br;
+        s_base[2] = tile_g; // used elements of the tile's spans (the rest up to nsl * padded block size is a hole)
+        s_base[3] = tile_r;
         s_ctr[1] = 0u;
         if (tile == p.n_tiles - 1) {
             p.totals[0] = p.totals_host[0] = bg + tile_g;
@@ -252,6 +254,26 @@ __device__ __forceinline__ void tile_phase_b(const DevParams& p, const int lane,
     if (lane < nsl) {
         p.sites[site0 + lane].g_off = bg + (ig - my_g);
         p.sites[site0 + lane].r_off = br + (ir - my_r);
+    }
+}
+
+// VGL_HOST_I32 / VGL_HOST_NARROW copy the planes to the host as whole spans: the hole at the end of a tile (behind sites with
+// fewer than five alleles or skipped ones) is zeroed so that the spans are deterministic and the narrowing pass never sees
+// stale words.  Spans and holes are multiples of four elements (blocks are padded to 16 B).
+__device__ __forceinline__ void tile_zero_holes(const DevParams& p, const int tid, const int nsl, const int S, const int64_t* s_base)
+{
+    const int g_full = nsl * ((S * 15 + 3) & ~3), r_full = nsl * ((S * 5 + 3) & ~3);
+    const int g_used = (int)s_base[2], r_used = (int)s_base[3];
+    const int4 z = make_int4(0, 0, 0, 0);
+    for (int i = g_used + tid * 4; i < g_full; i += TILE_BLOCK * 4) {
+        if (p.gl) *reinterpret_cast<int4*>(p.gl + s_base[0] + i) = z;
+        if (p.pl) *reinterpret_cast<int4*>(p.pl + s_base[0] + i) = z;
+        if (p.gp) *reinterpret_cast<int4*>(p.gp + s_base[0] + i) = z;
+    }
+    for (int i = r_used + tid * 4; i < r_full; i += TILE_BLOCK * 4) {
+        if (p.ad) *reinterpret_cast<int4*>(p.ad + s_base[1] + i) = z;
+        if (p.adf) *reinterpret_cast<int4*>(p.adf + s_base[1] + i) = z;
+        if (p.adr) *reinterpret_cast<int4*>(p.adr + s_base[1] + i) = z;
     }
 }
 

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
     TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
     int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
     TAux* aux = reinterpret_cast<TAux*>(tile_smem + OFF_AUX);
-    __shared__ int64_t s_base[2];
+    __shared__ int64_t s_base[4];
     __shared__ int s_next;
     __shared__ uint32_t s_ctr[2];
     __shared__ uint32_t s_zero[32];
@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
             tile_phase_b(p, lane, nsl, site0, tile, S, T, tot, st, explode, add_unobs, s_base, s_ctr, AUX ? aux : nullptr);
         }
         __syncthreads();
+        if (p.zero_holes) tile_zero_holes(p, tid, nsl, S, s_base);
 
         // ---------------- phase AUX: QS (thread per site and base; float sums in sample order, vcfgl.cpp:845-898) and
         // I16 (thread per site, vcfgl.cpp:982-1074) from the cached counts and the site totals

@@ -28,6 +28,13 @@ namespace vgl {
 #define M2_TAB_BYTES (M2_TAB_DOUBLES * 8) // per quality score: pair table [4][17] doubles, then class table [2][8]
 #define M2_TAB_MAXQ 8                     // scores whose tables fit the shared-memory copy
 #define M2_TAB_CLS 544                    // byte offset of the class table
+#define M2_SCR_BYTES 2048                 // per-warp scratch: 16 words per lane (the quality classes of up to 64 reads, LUT mode)
+#ifndef M2_MIN_CTAS
+#define M2_MIN_CTAS 5
+#endif
+
+// BIG variant: words of a CTA's global row = counts [S4] | mixed-cell list [S4] | chunk records [S4 / 32 + 1] x 4
+__host__ __device__ inline size_t m2_big_row_words(int S4) { return (size_t)2 * S4 + (size_t)4 * (S4 / 32 + 1); }
 
 struct __align__(16) M2SiteE {
     double e;  // base-picking error probability of the site
@@ -285,6 +292,43 @@ struct M2Reads {
     }
 };
 
+// ---- per-read quality-score classes of a LUT-mode cell of at most 64 reads, drawn at count level: the number of reads M whose
+// class is not the dominant one (M ~ Binomial(n, p_minor): threshold table, exact inversion beyond it), their positions
+// (uniform without replacement) and their classes (alias table of the conditional law) -- the joint law of n iid draws
+// from the class law.  Words of the cell's P_QS stream: word 0 = M, then per minor read one word for the position
+// (+ one per re-draw of an occupied position) and one for the class.  Cells deeper than 64 reads draw every read's
+// class on its own (m2_lut_qs).
+__device__ __forceinline__ int m2_qs_minor_count(const DevParams& p, int n, uint32_t u)
+{
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(p.qm_cdf) + n);
+    int M = (u >= c.x) + (u >= c.y) + (u >= c.z);
+    if (u >= c.w) M = binom_inversion(n, p.q_minor, u01_32(u));
+    return M;
+}
+// calls put(position, class) for each of the cell's minor reads; returns their number
+template <typename PUT>
+__device__ __forceinline__ int m2_qs_minor_reads(const DevParams& p, const M2Rng& R, unsigned long long site, uint32_t sample, int n, PUT put)
+{
+    Stream st;
+    Key key;
+    key.k0 = p.k0; key.k1 = p.k1;
+    st.init(key, (int64_t)site, sample, 0, P_QS);
+    const int M = m2_qs_minor_count(p, n, st.next());
+    unsigned long long hit = 0ull;
+    for (int j = 0; j < M; ++j) {
+        uint32_t pos;
+        for (;;) {
+            pos = mulhi32(st.next(), (uint32_t)n);
+            if (!((hit >> pos) & 1ull)) break;
+        }
+        hit |= 1ull << pos;
+        const uint32_t r = st.next(), col = r >> 24;
+        const uint32_t en = lds32(R.s_qcls + col * 4u); // conditional alias table
+        put(pos, (r & 0xFFFFFFu) < (en >> 8) ? col : (en & 0xFFu));
+    }
+    return M;
+}
+
 // final GL / PL of a cell, scattered into the warp's stage slice in allele order (vcfgl.cpp:907-939)
 __device__ __forceinline__ void m2_emit_cell(const float (&gl)[15], const uint4 slot, uint32_t cell_g, bool has_gl, bool has_pl)
 {
@@ -303,26 +347,50 @@ __device__ __forceinline__ void m2_emit_cell(const float (&gl)[15], const uint4 
     }
 }
 
+// base pairs (bit k = pair k) that hold base b twice / exactly once
+__device__ __forceinline__ uint32_t m2_hom_bit(int b) { return 1u << ((b * (b + 3)) >> 1); }
+__device__ __forceinline__ uint32_t m2_het_mask(int b)
+{
+    // pairs (j, k), j < k <= 4, with j == b or k == b
+    return b == 0 ? 0x044Au : (b == 1 ? 0x0892u : (b == 2 ? 0x1118u : 0x21C0u));
+}
+
+struct __align__(16) M2Chunk { // per chunk of 32 virtual cells, written in phase A
+    uint32_t base2, base15; // first list position of the chunk's two-base / general mixed cells (the latter counted from the end)
+    uint32_t mask2, mask15; // lanes of those cells
+};
+
 // MODE 0: FIXED with the run-constant error rate, 1: FIXED with a per-site error rate, 2: LUT (per-read qs)
 // TAB: the constants of every quality score in use fit the shared-memory tables (always in FIXED mode) -> table-driven
-// updates and the six-class form for warps whose cells all show at most two bases
+// updates, the six-class form for cells whose reads show at most two bases, and (PURE) the closed form of cells whose
+// reads all agree.
+//
+// Phase C is split in two.  Model 2 renormalises after every read, so a cell costs one dependent update chain per read --
+// but most cells are "pure" (every read shows the same base with the same quality score), and their vector depends on
+// the depth alone (m2_pure_table).  Phase A lists the other ("mixed") cells of the tile; phase M walks that list densely
+// (every lane a mixed cell), runs the per-read chains and parks the 15 results per cell in a per-CTA scratch row in
+// global memory (L2-resident); phase C then only assembles: table values for pure cells, parked values for mixed ones.
 template <int MODE, bool BIG, bool TAB>
-__global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant__ DevParams p)
+__global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     // layout: alias [256] u64 | cdf_e [256] uint4 | stage | st [sites] | tot [sites][4] | site_e [sites] |
-    //         constant tables [M2_TAB_MAXQ] | class map [16][8] | class scratch [warps][6][32] | qs alias + info [512] | cnt [cap]
+    //         constant tables [nq] | class map [16][8] | per-warp scratch [warps][2 KB] | qs tables [512] (LUT) |
+    //         chunk records | cnt [cap]
     constexpr int WST = 2 * TILE_WST_G + TILE_WST_R;
+    constexpr int NQ_SMEM = MODE == 2 ? M2_TAB_MAXQ : 1;
     constexpr uint32_t OFF_STAGE = 2048 + 4096, OFF_ST = OFF_STAGE + TILE_WARPS * WST * 4, OFF_TOT = OFF_ST + TILE_MAX_SITES * sizeof(TSite),
                        OFF_SE = OFF_TOT + TILE_MAX_SITES * 16, OFF_TAB = OFF_SE + TILE_MAX_SITES * sizeof(M2SiteE),
-                       OFF_CMAP = OFF_TAB + M2_TAB_MAXQ * M2_TAB_BYTES, OFF_SCR = OFF_CMAP + 512, OFF_QCLS = OFF_SCR + TILE_WARPS * 768,
-                       OFF_CNT = OFF_QCLS + 2048;
+                       OFF_CMAP = OFF_TAB + NQ_SMEM * M2_TAB_BYTES, OFF_SCR = OFF_CMAP + 512, OFF_QCLS = OFF_SCR + TILE_WARPS * M2_SCR_BYTES,
+                       OFF_CHK = OFF_QCLS + (MODE == 2 ? 2048 : 0), OFF_CNT = OFF_CHK + (BIG ? 0 : (TILE_CELLS / 32) * sizeof(M2Chunk)),
+                       OFF_LIST = OFF_CNT + (BIG ? 0 : TILE_CELLS * 4);
     TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
     int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
     M2SiteE* site_e = reinterpret_cast<M2SiteE*>(tile_smem + OFF_SE);
-    __shared__ int64_t s_base[2];
+    __shared__ int64_t s_base[4];
     __shared__ int s_next;
-    __shared__ uint32_t s_ctr[2];
+    __shared__ uint32_t s_ctr[4];
+    __shared__ uint32_t s_mix[2];
     __shared__ uint32_t s_zero[32];
 
     int tid, S;
@@ -334,7 +402,10 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
     for (int i = tid; i < 256; i += TILE_BLOCK) {
         reinterpret_cast<uint2*>(tile_smem)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
         reinterpret_cast<uint4*>(tile_smem + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
-        if (MODE == 2) reinterpret_cast<uint2*>(tile_smem + OFF_QCLS)[i] = reinterpret_cast<const uint2*>(p.qcls)[i]; // 512 words
+        if (MODE == 2) { // words 0..255: the conditional alias table of the minor classes, 256..511: class info words
+            reinterpret_cast<uint32_t*>(tile_smem + OFF_QCLS)[i] = p.qcls[512 + i];
+            reinterpret_cast<uint32_t*>(tile_smem + OFF_QCLS)[256 + i] = p.qcls[256 + i];
+        }
     }
     for (int i = tid; i < TILE_MAX_SITES * 4; i += TILE_BLOCK) tot[i] = 0;
     if (TAB) {
@@ -343,10 +414,12 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
     }
     if (tid == 0) {
         s_next = (int)atomicAdd(p.ticket, 1u);
-        s_ctr[0] = s_ctr[1] = 0u;
+        s_ctr[0] = s_ctr[1] = s_ctr[2] = s_ctr[3] = 0u;
+        s_mix[0] = s_mix[1] = 0u;
     }
     if (tid < 32) s_zero[tid] = 0u;
-    const uint32_t s_tab = s_smem + OFF_TAB, s_cmap = s_smem + OFF_CMAP, s_scr = s_smem + OFF_SCR + warp * 768 + lane * 4;
+    const uint32_t s_tab = s_smem + OFF_TAB, s_cmap = s_smem + OFF_CMAP;
+    const uint32_t s_scrw = s_smem + OFF_SCR + warp * M2_SCR_BYTES + lane * 4; // this lane's column of the warp's scratch: word w at + 128 w
     M2Rng R;
     R.s_alias = s_smem;
     R.s_cdf_e = s_smem + 2048;
@@ -357,18 +430,35 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
     const bool explode = p.do_unobserved >= 3;
     const bool add_unobs = p.do_unobserved == 1 || p.do_unobserved == 2 || p.do_unobserved == 4 || p.do_unobserved == 5;
     const bool has_gl = p.gl != nullptr, has_pl = p.pl != nullptr, has_ad = p.ad != nullptr;
+    const bool pure_ok = TAB && p.m2_pure != nullptr;
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4;
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
-    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST;
-    uint32_t* const cnt_g = BIG ? p.cnt_scratch + (size_t)blockIdx.x * S4 : nullptr;
-    uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]);
+    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST, s_chk = s_smem + OFF_CHK, s_list = s_smem + OFF_LIST;
+    // BIG: per-CTA rows in global memory: counts [S4] | list [S4] | chunk records [S4 / 32 + 1]
+    uint32_t* const cnt_g = BIG ? p.cnt_scratch + (size_t)blockIdx.x * m2_big_row_words(S4) : nullptr;
+    uint32_t* const list_g = BIG ? cnt_g + S4 : nullptr;
+    M2Chunk* const chk_g = BIG ? reinterpret_cast<M2Chunk*>(cnt_g + 2 * S4) : nullptr;
+    const int list_cap = BIG ? S4 : TILE_CELLS;
+    float* const park = p.m2_park + (size_t)blockIdx.x * (size_t)list_cap * 16; // 16 floats per mixed cell
+    uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]), s_ctrM = smem_u32(&s_ctr[2]), s_ctrN = smem_u32(&s_ctr[3]);
     bool first_tile = true;
     M2SiteE run_e;
     run_e.e = p.error_rate;
     run_e.l2 = 0.0f;
     run_e.er = 0.0f;
-    const bool gl_adj = (p.adjust_qs & 1) != 0;
-    (void)gl_adj;
+    const uint32_t dom_cls = (uint32_t)p.q_dom;          // LUT mode: the dominant class and its table offset
+    const uint32_t dom_qoff = MODE == 2 ? ((lds32(0u + 0u) & 0u) + (uint32_t)p.q_dom_idx * (uint32_t)M2_TAB_BYTES) : 0u;
+
+    auto list_put = [&](uint32_t pos, uint32_t iv) {
+        if (BIG) list_g[pos] = iv;
+        else asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_list + pos * 2u), "h"((unsigned short)iv) : "memory");
+    };
+    auto list_get = [&](uint32_t pos) -> uint32_t {
+        if (BIG) return list_g[pos];
+        unsigned short v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(s_list + pos * 2u));
+        return (uint32_t)v;
+    };
 
     for (;;) {
         __syncthreads();
@@ -378,6 +468,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
             const uint32_t opaque_zero = lds32(smem_u32(&s_zero[lane]));
             s_ctrA += opaque_zero;
             s_ctrC += opaque_zero;
+            s_ctrM += opaque_zero;
+            s_ctrN += opaque_zero;
             first_tile = false;
         }
         const int site0 = tile * T;
@@ -405,7 +497,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
             __syncthreads();
         }
 
-        // ---------------- phase A: counts, FORMAT/DP, per-site base totals
+        // ---------------- phase A: counts, FORMAT/DP, per-site base totals, the list of mixed cells
         {
             int cur = tile_ticket_get(tile_ticket_issue(s_ctrA, lane));
             while (cur < nchunk) {
@@ -416,8 +508,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
                 uint32_t gt = 0xFFu;
                 if (real) gt = gt_t[(uint32_t)(iv - sl * PAD)];
                 uint32_t ad = 0u;
+                int n = 0;
                 if (real) {
-                    int n;
                     uint32_t wseq[4];
                     ad = m2_cell_fixed<false, MODE == 1>(p, R, site_base + (uint32_t)sl, (uint32_t)v, gt, MODE == 1 ? site_e[sl] : run_e, n, wseq);
                     dp_t[(uint32_t)(iv - sl * PAD)] = n;
@@ -425,6 +517,33 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
                 if (iv < nv) {
                     if (BIG) cnt_g[iv] = ad;
                     else sts32(s_cnt + (uint32_t)iv * 4u, ad);
+                }
+                // cell kind: pure (closed form), two-base mixed (six classes), general mixed (15 base pairs)
+                {
+                    const int nb = __popc(nonzero_bytes(ad));
+                    bool pure = pure_ok && nb == 1 && n <= 64;
+                    if (MODE == 2 && pure) { // every read of the dominant quality class?
+                        const u32x4 q0 = philox_rk(p, (uint32_t)(site_base + (uint32_t)sl), (uint32_t)((site_base + (uint32_t)sl) >> 32) & 0xFFu, (uint32_t)v,
+                                                   (uint32_t)P_QS << 24);
+                        pure = m2_qs_minor_count(p, n, q0.x) == 0;
+                    }
+                    const bool mixed = n > 0 && !pure;
+                    const bool two = mixed && TAB && nb <= 2 && n <= 64;
+                    const uint32_t m2 = __ballot_sync(0xffffffffu, two), m15 = __ballot_sync(0xffffffffu, mixed && !two);
+                    uint32_t b2 = 0u, b15 = 0u;
+                    if (lane == 0) {
+                        if (m2) b2 = atomicAdd(&s_mix[0], (uint32_t)__popc(m2));
+                        if (m15) b15 = atomicAdd(&s_mix[1], (uint32_t)__popc(m15));
+                        M2Chunk c;
+                        c.base2 = b2; c.base15 = b15; c.mask2 = m2; c.mask15 = m15;
+                        if (BIG) chk_g[cur] = c;
+                        else *reinterpret_cast<M2Chunk*>(tile_smem + OFF_CHK + (size_t)cur * sizeof(M2Chunk)) = c;
+                    }
+                    b2 = __shfl_sync(0xffffffffu, b2, 0);
+                    b15 = __shfl_sync(0xffffffffu, b15, 0);
+                    const uint32_t lt = low_bits(lane);
+                    if (two) list_put(b2 + (uint32_t)__popc(m2 & lt), (uint32_t)iv);
+                    else if (mixed) list_put((uint32_t)list_cap - 1u - (b15 + (uint32_t)__popc(m15 & lt)), (uint32_t)iv);
                 }
                 // site totals (counts of one chunk stay below 2^16 per base: 32 cells x 255 reads)
                 const int first = __shfl_sync(0xffffffffu, sl, 0);
@@ -457,8 +576,159 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
             tile_phase_b(p, lane, nsl, site0, tile, S, T, tot, st, explode, add_unobs, s_base, s_ctr);
         }
         __syncthreads();
+        if (p.zero_holes) tile_zero_holes(p, tid, nsl, S, s_base);
 
-        // ---------------- phase C: score + emit, one warp per chunk of 32 virtual cells
+        // ---------------- phase M: the mixed cells, one per lane, in list order
+        const int n_two = (int)s_mix[0], n_gen = (int)s_mix[1];
+        auto cell_setup = [&](uint32_t iv, M2Reads<MODE>& rd, uint32_t& c4, uint32_t& pv, int& n) {
+            const int sl = (int)__umulhi(iv, inv_s4), v = (int)iv - sl * S4;
+            c4 = BIG ? cnt_g[iv] : lds32(s_cnt + iv * 4u);
+            n = (int)__vsadu4(c4, 0u);
+            const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
+            pv = (nonzero_bytes(~slot.x) | (nonzero_bytes(~slot.y) << 4) | (nonzero_bytes(~slot.z) << 8) | (nonzero_bytes(~slot.w) << 12)) & 0x7FFFu;
+            const uint32_t gt = gt_t[(uint32_t)((int)iv - sl * PAD)];
+            rd.g0 = gt & 0x3;
+            rd.g1 = (gt >> 4) & 0x3;
+            rd.site = site_base + (uint32_t)sl;
+            rd.sample = (uint32_t)v;
+            rd.e = MODE == 1 ? site_e[sl].e : run_e.e;
+            rd.deep = n > 64;
+            rd.w0 = rd.w1 = rd.w2 = rd.w3 = rd.cur = 0u;
+            if (!rd.deep) {
+                int nn;
+                uint32_t wseq[4];
+                m2_cell_fixed<true, MODE == 1>(p, R, rd.site, (uint32_t)v, gt, MODE == 1 ? site_e[sl] : run_e, nn, wseq);
+                rd.w0 = wseq[0]; rd.w1 = wseq[1]; rd.w2 = wseq[2]; rd.w3 = wseq[3];
+            }
+        };
+        // LUT mode: the quality class of every read of the lane's cell (<= 64 reads) as bytes in the lane's scratch column
+        auto qs_classes = [&](const M2Reads<MODE>& rd, int n, int nmax) {
+            if (MODE != 2) return;
+            const uint32_t fill = dom_cls * 0x01010101u;
+            for (int w = 0; w * 4 < nmax && w < 16; ++w) sts32(s_scrw + 128u * (uint32_t)w, fill);
+            if (n > 0 && n <= 64)
+                m2_qs_minor_reads(p, R, rd.site, rd.sample, n, [&](uint32_t pos, uint32_t cls) {
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(s_scrw + 128u * (pos >> 2) + (pos & 3u)), "r"(cls) : "memory");
+                });
+        };
+        auto read_qoff = [&](M2Reads<MODE>& rd, int i, int& qs) -> uint32_t { // table offset (and score) of read i's quality class
+            qs = 0;
+            if (MODE != 2) return 0u;
+            uint32_t info;
+            if (rd.deep) {
+                info = m2_lut_qs(p, R, rd.site, rd.sample, i, rd.qblk);
+            } else {
+                uint32_t cls;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cls) : "r"(s_scrw + 128u * ((uint32_t)i >> 2) + ((uint32_t)i & 3u)));
+                info = lds32(R.s_qcls + 1024u + cls * 4u);
+                if (info & 0x200u) atomicExch(p.status, (int)VGL_ERANGE); // apply_qs_bins() -> ERROR, vcfgl.cpp:63
+            }
+            qs = (int)(info & 0xFFu);
+            return ((info >> 16) & 0xFFu) * (uint32_t)M2_TAB_BYTES;
+        };
+        if (TAB) { // two-base cells: six classes {xx, xy, yy, x., y., ..}
+            int g = tile_ticket_get(tile_ticket_issue(s_ctrM, lane));
+            while (g * 32 < n_two) {
+                const int raw = tile_ticket_issue(s_ctrM, lane);
+                const int j = g * 32 + lane;
+                const bool act = j < n_two;
+                M2Reads<MODE> rd;
+                uint32_t c4 = 0u, pv = 0u;
+                int n = 0;
+                if (act) cell_setup(list_get((uint32_t)j), rd, c4, pv, n);
+                else { rd.deep = false; rd.w0 = rd.w1 = rd.w2 = rd.w3 = rd.cur = 0u; rd.site = 0; rd.sample = 0; rd.g0 = rd.g1 = 0; rd.e = 0.0; }
+                const int nmax = __reduce_max_sync(0xffffffffu, n);
+                qs_classes(rd, n, nmax);
+                const uint32_t seen = nonzero_bytes(c4);
+                const int x = __ffs(seen | 16u) - 1, rest = seen & (seen - 1u);
+                const int y = rest ? __ffs(rest) - 1 : ((x + 1) & 3);
+                const uint32_t ent = s_cmap + (uint32_t)(((x & 3) * 4 + y) * 32);
+                const uint4 cm = lds128(ent);
+                const uint2 ids = lds64(ent + 16u);
+                float gc[6];
+                gc[0] = (pv & cm.x & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
+                gc[1] = (pv & (cm.x >> 16)) ? -0.0f : -CUDART_INF_F;
+                gc[2] = (pv & cm.y & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
+                gc[3] = (pv & (cm.y >> 16)) ? -0.0f : -CUDART_INF_F;
+                gc[4] = (pv & cm.z & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
+                gc[5] = (pv & (cm.z >> 16)) ? -0.0f : -CUDART_INF_F;
+                for (int i = 0; i < nmax; ++i) {
+                    if (i < n) {
+                        uint32_t dq;
+                        int dqs;
+                        const int b = rd.get(p, R, i, dq, dqs);
+                        int qs;
+                        const uint32_t qoff = read_qoff(rd, i, qs);
+                        m2_update_classes(gc, s_tab + qoff + M2_TAB_CLS + (b == x ? 64u : 0u));
+                    }
+                }
+                if (act) { // the 15 base pairs from the six classes, parked for phase C
+                    const unsigned long long id64 = ((unsigned long long)ids.y << 32) | ids.x;
+                    float gl[16];
+#pragma unroll
+                    for (int k = 0; k < 15; ++k) {
+                        const uint32_t c = (uint32_t)((id64 >> (3 * k)) & 7ull);
+                        gl[k] = c == 0 ? gc[0] : (c == 1 ? gc[1] : (c == 2 ? gc[2] : (c == 3 ? gc[3] : (c == 4 ? gc[4] : gc[5]))));
+                    }
+                    gl[15] = 0.0f;
+                    float4* dst = reinterpret_cast<float4*>(park + (size_t)j * 16);
+                    dst[0] = make_float4(gl[0], gl[1], gl[2], gl[3]);
+                    dst[1] = make_float4(gl[4], gl[5], gl[6], gl[7]);
+                    dst[2] = make_float4(gl[8], gl[9], gl[10], gl[11]);
+                    dst[3] = make_float4(gl[12], gl[13], gl[14], gl[15]);
+                }
+                g = tile_ticket_get(raw);
+            }
+        }
+        { // general cells: all 15 base pairs
+            int g = tile_ticket_get(tile_ticket_issue(s_ctrN, lane));
+            while (g * 32 < n_gen) {
+                const int raw = tile_ticket_issue(s_ctrN, lane);
+                const int j = g * 32 + lane;
+                const bool act = j < n_gen;
+                const uint32_t pos = (uint32_t)list_cap - 1u - (uint32_t)j;
+                M2Reads<MODE> rd;
+                uint32_t c4 = 0u, pv = 0u;
+                int n = 0;
+                if (act) cell_setup(list_get(pos), rd, c4, pv, n);
+                else { rd.deep = false; rd.w0 = rd.w1 = rd.w2 = rd.w3 = rd.cur = 0u; rd.site = 0; rd.sample = 0; rd.g0 = rd.g1 = 0; rd.e = 0.0; }
+                const int nmax = __reduce_max_sync(0xffffffffu, n);
+                qs_classes(rd, n, min(nmax, 64));
+                float gl[16];
+#pragma unroll
+                for (int k = 0; k < 15; ++k) gl[k] = ((pv >> k) & 1u) ? -0.0f : -CUDART_INF_F; // bcf_utils.h:310
+                gl[15] = 0.0f;
+                for (int i = 0; i < nmax; ++i) {
+                    if (i < n) {
+                        uint32_t dq;
+                        int dqs;
+                        const int b = rd.get(p, R, i, dq, dqs);
+                        int qs;
+                        const uint32_t qoff = read_qoff(rd, i, qs);
+                        float (&g15)[15] = *reinterpret_cast<float (*)[15]>(gl);
+                        if (TAB) {
+                            m2_update_pairs(g15, s_tab + qoff + (uint32_t)b * 136u);
+                        } else if (MODE == 2) {
+                            m2_update(g15, b, __ldg(p.lut_log10 + qs), __ldg(p.lut_log10 + 257 + qs), __ldg(p.lut_log10 + 514 + qs));
+                        } else {
+                            m2_update(g15, b, p.homT, p.het, p.homF);
+                        }
+                    }
+                }
+                if (act) {
+                    float4* dst = reinterpret_cast<float4*>(park + (size_t)pos * 16);
+                    dst[0] = make_float4(gl[0], gl[1], gl[2], gl[3]);
+                    dst[1] = make_float4(gl[4], gl[5], gl[6], gl[7]);
+                    dst[2] = make_float4(gl[8], gl[9], gl[10], gl[11]);
+                    dst[3] = make_float4(gl[12], gl[13], gl[14], gl[15]);
+                }
+                g = tile_ticket_get(raw);
+            }
+        }
+        __syncthreads(); // parked values are visible to the CTA (global memory, same CTA: the barrier orders them)
+        if (tid == 0) { s_ctr[2] = s_ctr[3] = 0u; s_mix[0] = s_mix[1] = 0u; }
+
+        // ---------------- phase C: assemble + emit, one warp per chunk of 32 virtual cells
         float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
         int32_t* const pl_t = has_pl ? p.pl + s_base[0] : nullptr;
         int32_t* const ad_t = has_ad ? p.ad + s_base[1] : nullptr;
@@ -467,6 +737,22 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
             const int raw = tile_ticket_issue(s_ctrC, lane);
             const int iv = cur * 32 + lane;
             const uint32_t c4 = iv < nv ? (BIG ? cnt_g[iv] : lds32(s_cnt + (uint32_t)iv * 4u)) : 0u;
+            M2Chunk ck;
+            if (BIG) ck = chk_g[cur];
+            else {
+                const uint4 t = lds128(s_chk + (uint32_t)cur * 16u);
+                ck.base2 = t.x; ck.base15 = t.y; ck.mask2 = t.z; ck.mask15 = t.w;
+            }
+            // parked values of a mixed cell: issue the loads first
+            const uint32_t lt = low_bits(lane);
+            const bool is2 = (ck.mask2 >> lane) & 1u, is15 = (ck.mask15 >> lane) & 1u;
+            float4 pk0, pk1, pk2, pk3;
+            pk0 = pk1 = pk2 = pk3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (is2 || is15) {
+                const uint32_t pos = is2 ? ck.base2 + (uint32_t)__popc(ck.mask2 & lt) : (uint32_t)list_cap - 1u - (ck.base15 + (uint32_t)__popc(ck.mask15 & lt));
+                const float4* src = reinterpret_cast<const float4*>(park + (size_t)pos * 16);
+                pk0 = __ldcg(src); pk1 = __ldcg(src + 1); pk2 = __ldcg(src + 2); pk3 = __ldcg(src + 3);
+            }
             int sl = (int)__umulhi((uint32_t)iv, inv_s4);
             int v = iv - sl * S4;
             if (sl >= nsl) { sl = nsl - 1; v = S4; }
@@ -483,80 +769,20 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
             const uint32_t cell_g = live ? s_wg + (uint32_t)(gpos - g_lo) * 4u : s_wg + TILE_G_TRASH * 4u;
             const uint32_t cell_r = live ? s_wr + (uint32_t)(rpos - r_lo) * 4u : s_wr + TILE_R_TRASH * 4u;
             const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
-            // ---- the cell's reads, in order
-            float gl[15];
             const int n = (int)__vsadu4(c4, 0u);
-            const bool work = live && n > 0;
-            // base pairs that are genotypes of the site (bit k)
-            const uint32_t pv = (nonzero_bytes(~slot.x) | (nonzero_bytes(~slot.y) << 4) | (nonzero_bytes(~slot.z) << 8) | (nonzero_bytes(~slot.w) << 12)) & 0x7FFFu;
-            M2Reads<MODE> rd;
-            rd.deep = false;
-            rd.w0 = rd.w1 = rd.w2 = rd.w3 = rd.cur = 0u;
-            if (work) {
-                const uint32_t gt = gt_t[(uint32_t)(iv - sl * PAD)];
-                rd.g0 = gt & 0x3;
-                rd.g1 = (gt >> 4) & 0x3;
-                rd.site = site_base + (uint32_t)sl;
-                rd.sample = (uint32_t)v;
-                rd.e = MODE == 1 ? site_e[sl].e : run_e.e;
-                if (n > 64) {
-                    rd.deep = true;
-                } else {
-                    int nn;
-                    uint32_t wseq[4];
-                    m2_cell_fixed<true, MODE == 1>(p, R, rd.site, (uint32_t)v, gt, MODE == 1 ? site_e[sl] : run_e, nn, wseq);
-                    rd.w0 = wseq[0]; rd.w1 = wseq[1]; rd.w2 = wseq[2]; rd.w3 = wseq[3];
-                }
-            }
-            const uint32_t seen = nonzero_bytes(c4); // bases this cell's reads show
-            const bool two = TAB && __all_sync(0xffffffffu, !work || (__popc(seen) <= 2 && !rd.deep));
-            if (two) {
-                // at most two bases x, y in every cell of the warp: the 15 base pairs fall into six classes with
-                // identical histories {xx, xy, yy, x., y., ..} ('.' = any other allele); a class takes part in the
-                // max when one of its pairs is a genotype of the site
-                const int x = __ffs(seen | 16u) - 1, rest = seen & (seen - 1u);
-                const int y = rest ? __ffs(rest) - 1 : ((x + 1) & 3);
-                const uint32_t ent = s_cmap + (uint32_t)(((x & 3) * 4 + y) * 32);
-                const uint4 cm = lds128(ent);
-                const uint2 ids = lds64(ent + 16u);
-                float gc[6];
-                gc[0] = (pv & cm.x & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
-                gc[1] = (pv & (cm.x >> 16)) ? -0.0f : -CUDART_INF_F;
-                gc[2] = (pv & cm.y & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
-                gc[3] = (pv & (cm.y >> 16)) ? -0.0f : -CUDART_INF_F;
-                gc[4] = (pv & cm.z & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
-                gc[5] = (pv & (cm.z >> 16)) ? -0.0f : -CUDART_INF_F;
-                if (work) {
-                    for (int i = 0; i < n; ++i) {
-                        uint32_t qoff;
-                        int qs;
-                        const int b = rd.get(p, R, i, qoff, qs);
-                        m2_update_classes(gc, s_tab + qoff + M2_TAB_CLS + (b == x ? 64u : 0u));
-                    }
-                }
-                __syncwarp();
+            float gl[15];
+            if (is2 || is15) {
+                gl[0] = pk0.x; gl[1] = pk0.y; gl[2] = pk0.z; gl[3] = pk0.w;
+                gl[4] = pk1.x; gl[5] = pk1.y; gl[6] = pk1.z; gl[7] = pk1.w;
+                gl[8] = pk2.x; gl[9] = pk2.y; gl[10] = pk2.z; gl[11] = pk2.w;
+                gl[12] = pk3.x; gl[13] = pk3.y; gl[14] = pk3.z;
+            } else { // pure cell (or no reads: overwritten below): +0 for xx, the table's two values for x? and ??
+                const int x = __ffs(nonzero_bytes(c4) | 16u) - 1;
+                float2 tv = make_float2(0.f, 0.f);
+                if (pure_ok) tv = __ldg(reinterpret_cast<const float2*>(p.m2_pure) + (MODE == 2 ? p.q_dom_idx * 65 : 0) + min(n, 64));
+                const uint32_t hom = m2_hom_bit(x & 3), het = m2_het_mask(x & 3);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) sts32(s_scr + 128u * k, __float_as_uint(gc[k]));
-                const unsigned long long id64 = ((unsigned long long)ids.y << 32) | ids.x;
-#pragma unroll
-                for (int k = 0; k < 15; ++k) gl[k] = __uint_as_float(lds32(s_scr + 128u * (uint32_t)((id64 >> (3 * k)) & 7ull)));
-            } else {
-#pragma unroll
-                for (int k = 0; k < 15; ++k) gl[k] = ((pv >> k) & 1u) ? -0.0f : -CUDART_INF_F; // bcf_utils.h:310
-                if (work) {
-                    for (int i = 0; i < n; ++i) {
-                        uint32_t qoff;
-                        int qs;
-                        const int b = rd.get(p, R, i, qoff, qs);
-                        if (TAB) {
-                            m2_update_pairs(gl, s_tab + qoff + (uint32_t)b * 136u);
-                        } else if (MODE == 2) {
-                            m2_update(gl, b, __ldg(p.lut_log10 + qs), __ldg(p.lut_log10 + 257 + qs), __ldg(p.lut_log10 + 514 + qs));
-                        } else {
-                            m2_update(gl, b, p.homT, p.het, p.homF);
-                        }
-                    }
-                }
+                for (int k = 0; k < 15; ++k) gl[k] = ((hom >> k) & 1u) ? 0.0f : (((het >> k) & 1u) ? tv.x : tv.y);
             }
             bulk_wait_read();
             __syncwarp();
@@ -609,23 +835,32 @@ __global__ void __launch_bounds__(TILE_BLOCK, 4) k_tile_m2(const __grid_constant
     }
 }
 
+template <int MODE>
 static size_t tile_m2_dyn_smem(bool big)
 {
     return 2048 + 4096 + (size_t)TILE_WARPS * (2 * TILE_WST_G + TILE_WST_R) * 4 + TILE_MAX_SITES * sizeof(TSite) + TILE_MAX_SITES * 16 +
-           TILE_MAX_SITES * sizeof(M2SiteE) + M2_TAB_MAXQ * M2_TAB_BYTES + 512 + TILE_WARPS * 768 + 2048 + (big ? 0 : (size_t)TILE_CELLS * 4);
+           TILE_MAX_SITES * sizeof(M2SiteE) + (MODE == 2 ? M2_TAB_MAXQ : 1) * M2_TAB_BYTES + 512 + TILE_WARPS * M2_SCR_BYTES +
+           (MODE == 2 ? 2048 : 0) + (big ? 0 : (size_t)(TILE_CELLS / 32) * sizeof(M2Chunk) + (size_t)TILE_CELLS * 4 + (size_t)TILE_CELLS * 2);
 }
 
 template <int MODE, bool BIG, bool TAB>
-static void launch_tile_m2_t(const DevParams& p, cudaStream_t st, int n_sms)
+static int tile_m2_ctas_per_sm()
 {
-    const size_t dyn = tile_m2_dyn_smem(BIG);
+    const size_t dyn = tile_m2_dyn_smem<MODE>(BIG);
     cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m2<MODE, BIG, TAB>, TILE_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
-    int grid = n_sms * per_sm;
+    return per_sm;
+}
+
+template <int MODE, bool BIG, bool TAB>
+static void launch_tile_m2_t(const DevParams& p, cudaStream_t st, int n_sms)
+{
+    const size_t dyn = tile_m2_dyn_smem<MODE>(BIG);
+    int grid = n_sms * tile_m2_ctas_per_sm<MODE, BIG, TAB>();
     if (grid > p.n_tiles) grid = p.n_tiles;
     k_tile_m2<MODE, BIG, TAB><<<grid, TILE_BLOCK, dyn, st>>>(p);
 }
@@ -638,6 +873,19 @@ void launch_tile_m2(const DevParams& p, cudaStream_t st, int n_sms, int mode)
     else if (mode == 1) { if (big) launch_tile_m2_t<1, true, true>(p, st, n_sms); else launch_tile_m2_t<1, false, true>(p, st, n_sms); }
     else if (tab) { if (big) launch_tile_m2_t<2, true, true>(p, st, n_sms); else launch_tile_m2_t<2, false, true>(p, st, n_sms); }
     else { if (big) launch_tile_m2_t<2, true, false>(p, st, n_sms); else launch_tile_m2_t<2, false, false>(p, st, n_sms); }
+}
+
+// global scratch of the model-2 tile kernel for S samples on n_sms SMs: 32-bit words of the per-CTA rows (counts, list, chunk
+// records; 0 unless a site exceeds the shared-memory tile) and floats of the parked results (16 per cell of a tile)
+size_t tile_m2_row_words(int S, int n_sms)
+{
+    const int S4 = (S + 3) & ~3;
+    return S4 > TILE_CELLS ? m2_big_row_words(S4) * TILE_SCRATCH_CTAS_PER_SM * (size_t)n_sms : 0;
+}
+size_t tile_m2_park_floats(int S, int n_sms)
+{
+    const int S4 = (S + 3) & ~3;
+    return (size_t)(S4 > TILE_CELLS ? S4 : TILE_CELLS) * 16 * TILE_SCRATCH_CTAS_PER_SM * (size_t)n_sms;
 }
 
 // ---- the sampler's per-read draws in the replay layout (vgl_native_draws): pass 0 writes the depths, pass 1 the reads

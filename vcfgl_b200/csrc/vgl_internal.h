@@ -63,6 +63,7 @@ struct DevParams {
     int32_t sample_strand;      // shared.h:160 PROGRAM_WILL_SAMPLE_STRAND
     int32_t need_cellq, need_tail;
     int32_t fast_div;           // table-derived proof that the 3-instruction /10 is exact for every score
+    int32_t zero_holes;         // tile kernels: zero the unused tail of every tile's plane span (planes that cross PCIe whole)
     // tables
     const double* lut_log10;  // [3*257]
     const double* m1_bsum;    // [256*256] fixed-qs running sums
