@@ -96,7 +96,10 @@ struct vgl_ctx {
     int use_tile_m2 = 0, tile_m2_mode = 0; // tile_m2.cu; mode 0 / 1 / 2 = --error-qs
     int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
     size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
-    uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr;
+    uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr, *d_qm_cdf = nullptr;
+    float *d_m2_pure = nullptr, *d_m2_park = nullptr;
+    int q_dom = 0, q_dom_idx = 0;
+    double q_minor = 0.0;
     double* d_m2_tab = nullptr;
     int m2_nq = 0;
     unsigned long long *d_pois = nullptr, *d_alias = nullptr;
@@ -249,7 +252,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park);
     delete ctx;
 }
 
@@ -341,9 +344,15 @@ static int create_impl(vgl_ctx* ctx)
         if (p.error_qs == 2) {
             const bool gl_adj = (p.adjust_qs & 1) != 0;
             std::vector<int> qv;
-            const std::vector<uint32_t> qc = qs_class_table(ctx->beta_a, ctx->beta_b, gl_adj ? p.adjust_by : 0.0, p.n_qs_bins > 0, ctx->bin_lut, ctx->bin_max, nullptr, &qv);
+            int dom = 0;
+            const std::vector<uint32_t> qc = qs_class_table(ctx->beta_a, ctx->beta_b, gl_adj ? p.adjust_by : 0.0, p.n_qs_bins > 0, ctx->bin_lut, ctx->bin_max, nullptr, &qv, &dom, &ctx->q_minor);
             if (qc.empty()) ctx->use_tile_m2 = 0; // classes outside the bins / too many: the per-read kernels keep the reference's behaviour
-            else CK(upload(&ctx->d_qcls, qc));
+            else {
+                CK(upload(&ctx->d_qcls, qc));
+                ctx->q_dom = dom;
+                ctx->q_dom_idx = (int)((qc[256 + dom] >> 16) & 0xFFu);
+                CK(upload(&ctx->d_qm_cdf, binomial_cdf4_u32(ctx->q_minor)));
+            }
             for (int q : qv) { consts.push_back(kLutLog10Gl[0][q]); consts.push_back(kLutLog10Gl[1][q]); consts.push_back(kLutLog10Gl[2][q]); }
         } else {
             consts = {ctx->pre.homT, ctx->pre.het, ctx->pre.homF};
@@ -355,6 +364,8 @@ static int create_impl(vgl_ctx* ctx)
             ctx->m2_nq = (int)consts.size() / 3;
             CK(upload(&ctx->d_m2_tab, m2_const_table(consts)));
             CK(upload(&ctx->d_m2_cmap, m2_class_map()));
+            std::vector<float> pure;
+            if (m2_pure_table(consts, &pure)) CK(upload(&ctx->d_m2_pure, pure));
         } else if (p.error_qs != 2) {
             ctx->use_tile_m2 = 0; // e.g. --precise-gl 1 with --error-rate 0 (homT = 0): the per-read kernels
         }
@@ -365,8 +376,9 @@ static int create_impl(vgl_ctx* ctx)
     if (ctx->use_tile || ctx->use_tile_m2) {
         CK(upload(&ctx->d_alias, alias));
         CK(upload(&ctx->d_errcdf, binomial_cdf4_u32(p.error_rate)));
-        const size_t words = tile_m1f_scratch_words(p.n_samples, ctx->n_sms);
+        const size_t words = ctx->use_tile_m2 ? tile_m2_row_words(p.n_samples, ctx->n_sms) : tile_m1f_scratch_words(p.n_samples, ctx->n_sms);
         if (words) CK(cudaMalloc((void**)&ctx->d_cnt_scratch, words * 4));
+        if (ctx->use_tile_m2) CK(cudaMalloc((void**)&ctx->d_m2_park, tile_m2_park_floats(p.n_samples, ctx->n_sms) * sizeof(float)));
     }
 
     // ---- slots
@@ -732,6 +744,12 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.m2_tab = ctx->d_m2_tab;
     p.m2_nq = ctx->m2_nq;
     p.m2_cmap = ctx->d_m2_cmap;
+    p.qm_cdf = ctx->d_qm_cdf;
+    p.q_minor = ctx->q_minor;
+    p.q_dom = ctx->q_dom;
+    p.q_dom_idx = ctx->q_dom_idx;
+    p.m2_pure = ctx->d_m2_pure;
+    p.m2_park = ctx->d_m2_park;
     {
         int T = 1024 / (int)S;
         T = T < 1 ? 1 : (T > 128 ? 128 : T);

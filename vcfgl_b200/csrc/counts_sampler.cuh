@@ -47,16 +47,19 @@ __device__ __forceinline__ int binom_half(int n, uint32_t first_word, Stream& st
     return k;
 }
 
-// Binomial(n, e) by CDF inversion from the smaller tail; u in (0,1)
+// Binomial(n, e) by CDF inversion, non-decreasing in u (callers combine it with threshold tables of the same CDF for the
+// first few outcomes); u in (0,1).  For e > 1/2 the walk runs over the mirrored law from the other end (n - K', K' ~
+// Binomial(n, 1 - e) at 1 - u), which keeps the map monotone and the starting term away from underflow.
 __device__ __forceinline__ int binom_inversion(int n, double e, double u)
 {
     if (e <= 0.0) return 0;
     const bool flip = e > 0.5;
     const double pe = flip ? 1.0 - e : e;
+    const double uu = flip ? 1.0 - u : u;
     const double ratio = pe / (1.0 - pe);
     double p = exp2((double)n * log2(1.0 - pe)), cdf = p;
     int k = 0;
-    while (u > cdf && k < n) {
+    while (uu > cdf && k < n) {
         p *= (double)(n - k) / (double)(k + 1) * ratio;
         cdf += p;
         ++k;

@@ -33,8 +33,8 @@ namespace vgl {
 #define M2_MIN_CTAS 5
 #endif
 
-// BIG variant: words of a CTA's global row = counts [S4] | mixed-cell list [S4] | chunk records [S4 / 32 + 1] x 4
-__host__ __device__ inline size_t m2_big_row_words(int S4) { return (size_t)2 * S4 + (size_t)4 * (S4 / 32 + 1); }
+// BIG variant: words of a CTA's global row = counts [S4] | chunk records [S4 / 32 + 1] x 4
+__host__ __device__ inline size_t m2_big_row_words(int S4) { return (size_t)S4 + (size_t)4 * (S4 / 32 + 1); }
 
 struct __align__(16) M2SiteE {
     double e;  // base-picking error probability of the site
@@ -45,7 +45,7 @@ struct __align__(16) M2SiteE {
 struct M2Rng {
     uint32_t s_alias; // shared address: Poisson alias table
     uint32_t s_cdf_e; // shared address: [256] uint4 P(E <= j | n) * 2^32 (run-constant error rate)
-    uint32_t s_qcls;  // shared address: LUT mode, [256] (threshold24 << 8 | alias) then [256] class info words
+    uint32_t s_qcls;  // shared address: LUT mode, [256] (threshold24 << 8 | alias) of the minor classes' conditional law, then [256] class info words
     int fixed_depth;
     bool has_err;
 };
@@ -173,14 +173,15 @@ __device__ __forceinline__ uint32_t m2_cell_fixed(const DevParams& p, const M2Rn
     return ad;
 }
 
-// LUT mode: the quality score of read i from word i&3 of block i>>2 of the cell's P_QS counter -> alias draw.
+// LUT mode, cells deeper than 64 reads: the quality score of read i from word i&3 of block 0x10000 + (i>>2) of the cell's
+// P_QS counter -> alias draw from the full class law.
 // Returns the class info word (q | out-of-range << 9 | dense index << 16).
 __device__ __forceinline__ uint32_t m2_lut_qs(const DevParams& p, const M2Rng& R, unsigned long long site, uint32_t sample, int i, u32x4& qblk)
 {
-    if ((i & 3) == 0) qblk = philox_rk(p, (uint32_t)site, (uint32_t)(site >> 32) & 0xFFu, sample, ((uint32_t)P_QS << 24) | (uint32_t)(i >> 2));
+    if ((i & 3) == 0) qblk = philox_rk(p, (uint32_t)site, (uint32_t)(site >> 32) & 0xFFu, sample, ((uint32_t)P_QS << 24) | (uint32_t)(0x10000 + (i >> 2)));
     const uint32_t r = (i & 3) == 0 ? qblk.x : ((i & 3) == 1 ? qblk.y : ((i & 3) == 2 ? qblk.z : qblk.w));
     const uint32_t col = r >> 24;
-    const uint32_t en = lds32(R.s_qcls + col * 4u);
+    const uint32_t en = __ldg(p.qcls + col); // the full class law (deep cells only: global memory)
     const uint32_t cls = (r & 0xFFFFFFu) < (en >> 8) ? col : (en & 0xFFu);
     const uint32_t info = lds32(R.s_qcls + 1024u + cls * 4u);
     if (info & 0x200u) atomicExch(p.status, (int)VGL_ERANGE); // apply_qs_bins() -> ERROR, vcfgl.cpp:63
@@ -274,16 +275,9 @@ struct M2Reads {
     int g0, g1;
     double e;
     u32x4 qblk;
-    // returns the base of read i (reads must be asked in order); qoff / qs: LUT mode
-    __device__ __forceinline__ int get(const DevParams& p, const M2Rng& R, int i, uint32_t& qoff, int& qs)
+    // returns the base of read i (reads must be asked in order)
+    __device__ __forceinline__ int base(const DevParams& p, int i)
     {
-        qoff = 0u;
-        qs = 0;
-        if (MODE == 2) {
-            const uint32_t info = m2_lut_qs(p, R, site, sample, i, qblk);
-            qs = (int)(info & 0xFFu);
-            qoff = ((info >> 16) & 0xFFu) * (uint32_t)M2_TAB_BYTES;
-        }
         if (deep) return m2_deep_base(p, site, sample, i, g0, g1, e);
         if ((i & 15) == 0) cur = (i >> 4) == 0 ? w0 : ((i >> 4) == 1 ? w1 : ((i >> 4) == 2 ? w2 : w3));
         const int b = (int)(cur & 3u);
@@ -381,9 +375,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
     constexpr int NQ_SMEM = MODE == 2 ? M2_TAB_MAXQ : 1;
     constexpr uint32_t OFF_STAGE = 2048 + 4096, OFF_ST = OFF_STAGE + TILE_WARPS * WST * 4, OFF_TOT = OFF_ST + TILE_MAX_SITES * sizeof(TSite),
                        OFF_SE = OFF_TOT + TILE_MAX_SITES * 16, OFF_TAB = OFF_SE + TILE_MAX_SITES * sizeof(M2SiteE),
-                       OFF_CMAP = OFF_TAB + NQ_SMEM * M2_TAB_BYTES, OFF_SCR = OFF_CMAP + 512, OFF_QCLS = OFF_SCR + TILE_WARPS * M2_SCR_BYTES,
-                       OFF_CHK = OFF_QCLS + (MODE == 2 ? 2048 : 0), OFF_CNT = OFF_CHK + (BIG ? 0 : (TILE_CELLS / 32) * sizeof(M2Chunk)),
-                       OFF_LIST = OFF_CNT + (BIG ? 0 : TILE_CELLS * 4);
+                       OFF_CMAP = OFF_TAB + NQ_SMEM * M2_TAB_BYTES, OFF_SCR = OFF_CMAP + 512, OFF_QCLS = OFF_SCR + (MODE == 2 ? TILE_WARPS * M2_SCR_BYTES : 0),
+                       OFF_CHK = OFF_QCLS + (MODE == 2 ? 2048 : 0), OFF_CNT = OFF_CHK + (BIG ? 0 : (TILE_CELLS / 32) * sizeof(M2Chunk));
     TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
     int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
     M2SiteE* site_e = reinterpret_cast<M2SiteE*>(tile_smem + OFF_SE);
@@ -433,13 +426,14 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
     const bool pure_ok = TAB && p.m2_pure != nullptr;
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4;
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
-    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST, s_chk = s_smem + OFF_CHK, s_list = s_smem + OFF_LIST;
-    // BIG: per-CTA rows in global memory: counts [S4] | list [S4] | chunk records [S4 / 32 + 1]
+    const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST, s_chk = s_smem + OFF_CHK;
+    // BIG: per-CTA rows in global memory: counts [S4] | chunk records [S4 / 32 + 1]
     uint32_t* const cnt_g = BIG ? p.cnt_scratch + (size_t)blockIdx.x * m2_big_row_words(S4) : nullptr;
-    uint32_t* const list_g = BIG ? cnt_g + S4 : nullptr;
-    M2Chunk* const chk_g = BIG ? reinterpret_cast<M2Chunk*>(cnt_g + 2 * S4) : nullptr;
+    M2Chunk* const chk_g = BIG ? reinterpret_cast<M2Chunk*>(cnt_g + S4) : nullptr;
+    // every variant: the CTA's row of parked results (16 floats per mixed cell) followed by the list of mixed cells (L2-resident)
     const int list_cap = BIG ? S4 : TILE_CELLS;
-    float* const park = p.m2_park + (size_t)blockIdx.x * (size_t)list_cap * 16; // 16 floats per mixed cell
+    float* const park = p.m2_park + (size_t)blockIdx.x * (size_t)list_cap * 17;
+    uint32_t* const list_g = reinterpret_cast<uint32_t*>(park + (size_t)list_cap * 16);
     uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]), s_ctrM = smem_u32(&s_ctr[2]), s_ctrN = smem_u32(&s_ctr[3]);
     bool first_tile = true;
     M2SiteE run_e;
@@ -447,18 +441,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
     run_e.l2 = 0.0f;
     run_e.er = 0.0f;
     const uint32_t dom_cls = (uint32_t)p.q_dom;          // LUT mode: the dominant class and its table offset
-    const uint32_t dom_qoff = MODE == 2 ? ((lds32(0u + 0u) & 0u) + (uint32_t)p.q_dom_idx * (uint32_t)M2_TAB_BYTES) : 0u;
 
-    auto list_put = [&](uint32_t pos, uint32_t iv) {
-        if (BIG) list_g[pos] = iv;
-        else asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_list + pos * 2u), "h"((unsigned short)iv) : "memory");
-    };
-    auto list_get = [&](uint32_t pos) -> uint32_t {
-        if (BIG) return list_g[pos];
-        unsigned short v;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(s_list + pos * 2u));
-        return (uint32_t)v;
-    };
+    auto list_put = [&](uint32_t pos, uint32_t iv) { __stcg(list_g + pos, iv); };
+    auto list_get = [&](uint32_t pos) -> uint32_t { return __ldcg(list_g + pos); };
 
     for (;;) {
         __syncthreads();
@@ -654,9 +639,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
                 gc[5] = (pv & (cm.z >> 16)) ? -0.0f : -CUDART_INF_F;
                 for (int i = 0; i < nmax; ++i) {
                     if (i < n) {
-                        uint32_t dq;
-                        int dqs;
-                        const int b = rd.get(p, R, i, dq, dqs);
+                        const int b = rd.base(p, i);
                         int qs;
                         const uint32_t qoff = read_qoff(rd, i, qs);
                         m2_update_classes(gc, s_tab + qoff + M2_TAB_CLS + (b == x ? 64u : 0u));
@@ -700,9 +683,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
                 gl[15] = 0.0f;
                 for (int i = 0; i < nmax; ++i) {
                     if (i < n) {
-                        uint32_t dq;
-                        int dqs;
-                        const int b = rd.get(p, R, i, dq, dqs);
+                        const int b = rd.base(p, i);
                         int qs;
                         const uint32_t qoff = read_qoff(rd, i, qs);
                         float (&g15)[15] = *reinterpret_cast<float (*)[15]>(gl);
@@ -839,8 +820,8 @@ template <int MODE>
 static size_t tile_m2_dyn_smem(bool big)
 {
     return 2048 + 4096 + (size_t)TILE_WARPS * (2 * TILE_WST_G + TILE_WST_R) * 4 + TILE_MAX_SITES * sizeof(TSite) + TILE_MAX_SITES * 16 +
-           TILE_MAX_SITES * sizeof(M2SiteE) + (MODE == 2 ? M2_TAB_MAXQ : 1) * M2_TAB_BYTES + 512 + TILE_WARPS * M2_SCR_BYTES +
-           (MODE == 2 ? 2048 : 0) + (big ? 0 : (size_t)(TILE_CELLS / 32) * sizeof(M2Chunk) + (size_t)TILE_CELLS * 4 + (size_t)TILE_CELLS * 2);
+           TILE_MAX_SITES * sizeof(M2SiteE) + (MODE == 2 ? M2_TAB_MAXQ : 1) * M2_TAB_BYTES + 512 + (MODE == 2 ? TILE_WARPS * M2_SCR_BYTES : 0) +
+           (MODE == 2 ? 2048 : 0) + (big ? 0 : (size_t)(TILE_CELLS / 32) * sizeof(M2Chunk) + (size_t)TILE_CELLS * 4);
 }
 
 template <int MODE, bool BIG, bool TAB>
@@ -885,7 +866,7 @@ size_t tile_m2_row_words(int S, int n_sms)
 size_t tile_m2_park_floats(int S, int n_sms)
 {
     const int S4 = (S + 3) & ~3;
-    return (size_t)(S4 > TILE_CELLS ? S4 : TILE_CELLS) * 16 * TILE_SCRATCH_CTAS_PER_SM * (size_t)n_sms;
+    return (size_t)(S4 > TILE_CELLS ? S4 : TILE_CELLS) * 17 * TILE_SCRATCH_CTAS_PER_SM * (size_t)n_sms; // + one list word per cell
 }
 
 // ---- the sampler's per-read draws in the replay layout (vgl_native_draws): pass 0 writes the depths, pass 1 the reads
@@ -895,7 +876,10 @@ __global__ void k_tile_m2_draws(const DevParams p, int mode, int pass, int32_t* 
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         reinterpret_cast<uint2*>(sm)[i] = reinterpret_cast<const uint2*>(p.pois_alias)[i];
         reinterpret_cast<uint4*>(sm + 2048)[i] = reinterpret_cast<const uint4*>(p.err_cdf)[i];
-        if (mode == 2) reinterpret_cast<uint2*>(sm + 6144)[i] = reinterpret_cast<const uint2*>(p.qcls)[i];
+        if (mode == 2) {
+            reinterpret_cast<uint32_t*>(sm + 6144)[i] = p.qcls[512 + i];
+            reinterpret_cast<uint32_t*>(sm + 6144)[256 + i] = p.qcls[256 + i];
+        }
     }
     __syncthreads();
     M2Rng R;
@@ -936,8 +920,21 @@ __global__ void k_tile_m2_draws(const DevParams p, int mode, int pass, int32_t* 
         bases[off[c] + i] = (uint8_t)b;
     }
     if (mode == 2) {
-        u32x4 qblk;
-        for (int i = 0; i < n; ++i) qs[off[c] + i] = (uint8_t)(m2_lut_qs(p, R, site, sample, i, qblk) & 0xFFu);
+        if (n > 64) {
+            u32x4 qblk;
+            for (int i = 0; i < n; ++i) qs[off[c] + i] = (uint8_t)(m2_lut_qs(p, R, site, sample, i, qblk) & 0xFFu);
+        } else {
+            const uint8_t qd = (uint8_t)(lds32(R.s_qcls + 1024u + (uint32_t)p.q_dom * 4u) & 0xFFu);
+            for (int i = 0; i < n; ++i) qs[off[c] + i] = qd;
+            uint8_t* const q0 = qs + off[c];
+            const uint32_t s_info = R.s_qcls + 1024u;
+            int32_t* const status = p.status;
+            m2_qs_minor_reads(p, R, site, sample, n, [&](uint32_t pos, uint32_t cls) {
+                const uint32_t info = lds32(s_info + cls * 4u);
+                if (info & 0x200u) atomicExch(status, (int)VGL_ERANGE);
+                q0[pos] = (uint8_t)(info & 0xFFu);
+            });
+        }
     }
 }
 

@@ -100,6 +100,11 @@ struct DevParams {
     const double* m2_tab;                 // [m2_nq][M2_TAB_DOUBLES] constants per quality score in use, tables.h m2_const_table(); null: none
     int32_t m2_nq;
     const uint32_t* m2_cmap;              // [16][8], tables.h m2_class_map()
+    const uint32_t* qm_cdf;               // [256][4] P(M <= j | n) * 2^32: reads of a cell whose quality class is not the dominant one
+    double q_minor;                       // P(a read is not of the dominant class)
+    int32_t q_dom, q_dom_idx;             // the dominant class (index into the info words) and the dense index of its score
+    const float* m2_pure;                 // [m2_nq][65][2] tables.h m2_pure_table(); null: no closed form for pure cells
+    float* m2_park;                       // per-CTA rows of parked results of mixed cells (16 floats each)
     // replay
     int32_t replay;
     const int32_t* rp_depths;
@@ -147,6 +152,8 @@ void launch_tile_m1f_draws(const DevParams& p, cudaStream_t st, int pass, int32_
                            uint8_t* tails);
 uint32_t tile_m1f_aux_tags();
 void launch_tile_m2(const DevParams& p, cudaStream_t st, int n_sms, int mode);
+size_t tile_m2_row_words(int S, int n_sms);
+size_t tile_m2_park_floats(int S, int n_sms);
 void launch_tile_m2_draws(const DevParams& p, cudaStream_t st, int mode, int pass, int32_t* depths, const int64_t* off, uint8_t* bases,
                           uint8_t* qs);
 void launch_narrow(const int32_t* src, void* dst, int bits, bool is_pl, const int64_t* n_dev, int64_t n_fixed, int64_t cap, int32_t* status,
