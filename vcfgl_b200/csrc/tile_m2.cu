@@ -42,6 +42,17 @@ struct __align__(16) M2SiteE {
     float er;  // e / (1 - e)
 };
 
+// rare paths kept out of line (the kernel's hot loops should stay within the instruction cache)
+__device__ __noinline__ int m2_binom_inversion(int n, double e, uint32_t u) { return binom_inversion(n, e, u01_32(u)); }
+__device__ __noinline__ double m2_site_beta(const DevParams& p, unsigned long long site)
+{
+    Stream bs;
+    Key key;
+    key.k0 = p.k0; key.k1 = p.k1;
+    bs.init(key, (int64_t)site, 0xFFFFFFFFu, 0, P_SITE);
+    return beta_draw(bs, p.beta_a, p.beta_b);
+}
+
 struct M2Rng {
     uint32_t s_alias; // shared address: Poisson alias table
     uint32_t s_cdf_e; // shared address: [256] uint4 P(E <= j | n) * 2^32 (run-constant error rate)
@@ -61,7 +72,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x)
 }
 
 // read i of a cell deeper than 64 reads: one Philox block per read, as CellSource::read (cell_source.cuh)
-__device__ __forceinline__ int m2_deep_base(const DevParams& p, unsigned long long site, uint32_t sample, int i, int g0, int g1, double e)
+__device__ __noinline__ int m2_deep_base(const DevParams& p, unsigned long long site, uint32_t sample, int i, int g0, int g1, double e)
 {
     const u32x4 w = philox_rk(p, (uint32_t)site, ((uint32_t)(site >> 32) & 0xFFu) | ((uint32_t)i << 8), sample, (uint32_t)P_READ << 24);
     const int truth = (w.y >> 31) ? g1 : g0;
@@ -98,6 +109,7 @@ __device__ __forceinline__ uint32_t m2_cell_fixed(const DevParams& p, const M2Rn
     const int g0 = gt & 0x3, g1 = (gt >> 4) & 0x3;
     const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
     const u32x4 b0 = philox_rk(p, c0, c1, sample, (uint32_t)P_COUNTS << 24);
+    const u32x4 b1 = philox_rk(p, c0, c1, sample, ((uint32_t)P_COUNTS << 24) | 1u); // independent of b0: the two chains overlap
     const int n = m2_depth(R, b0, gt);
     n_out = n;
     if (SEQ) w[0] = w[1] = w[2] = w[3] = 0u;
@@ -107,7 +119,6 @@ __device__ __forceinline__ uint32_t m2_cell_fixed(const DevParams& p, const M2Rn
         for (int i = 0; i < n; ++i) ad += 1u << (8 * m2_deep_base(p, site, sample, i, g0, g1, se.e));
         return ad;
     }
-    const u32x4 b1 = philox_rk(p, c0, c1, sample, ((uint32_t)P_COUNTS << 24) | 1u);
     const unsigned long long h = ((unsigned long long)b1.x << 32) | b0.w;
     const unsigned long long hm = h & (n >= 64 ? ~0ull : ((1ull << n) - 1ull));
     const bool het = g0 != g1;
@@ -133,13 +144,13 @@ __device__ __forceinline__ uint32_t m2_cell_fixed(const DevParams& p, const M2Rn
                     ++E;
                 }
             } else {
-                E = binom_inversion(n, se.e, u01_32(b0.z));
+                E = m2_binom_inversion(n, se.e, b0.z);
             }
         }
     } else if (R.has_err) {
         const uint4 c = lds128(R.s_cdf_e + (uint32_t)n * 16u);
         E = (b0.z >= c.x) + (b0.z >= c.y) + (b0.z >= c.z);
-        if (b0.z >= c.w) E = binom_inversion(n, se.e, u01_32(b0.z));
+        if (b0.z >= c.w) E = m2_binom_inversion(n, se.e, b0.z);
     }
     if (E > 0) {
         unsigned long long hit = 0ull;
@@ -296,7 +307,7 @@ __device__ __forceinline__ int m2_qs_minor_count(const DevParams& p, int n, uint
 {
     const uint4 c = __ldg(reinterpret_cast<const uint4*>(p.qm_cdf) + n);
     int M = (u >= c.x) + (u >= c.y) + (u >= c.z);
-    if (u >= c.w) M = binom_inversion(n, p.q_minor, u01_32(u));
+    if (u >= c.w) M = m2_binom_inversion(n, p.q_minor, u);
     return M;
 }
 // calls put(position, class) for each of the cell's minor reads; returns their number
@@ -364,7 +375,7 @@ struct __align__(16) M2Chunk { // per chunk of 32 virtual cells, written in phas
 // the depth alone (m2_pure_table).  Phase A lists the other ("mixed") cells of the tile; phase M walks that list densely
 // (every lane a mixed cell), runs the per-read chains and parks the 15 results per cell in a per-CTA scratch row in
 // global memory (L2-resident); phase C then only assembles: table values for pure cells, parked values for mixed ones.
-template <int MODE, bool BIG, bool TAB>
+template <int MODE, bool BIG, bool TAB, bool GLPL>
 __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -384,6 +395,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
     __shared__ int s_next;
     __shared__ uint32_t s_ctr[4];
     __shared__ uint32_t s_mix[2];
+    __shared__ uint32_t s_hist[72]; // two-base mixed cells per depth (0..64), then the running offsets of the counting sort
     __shared__ uint32_t s_zero[32];
 
     int tid, S;
@@ -410,6 +422,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
         s_ctr[0] = s_ctr[1] = s_ctr[2] = s_ctr[3] = 0u;
         s_mix[0] = s_mix[1] = 0u;
     }
+    if (tid < 72) s_hist[tid] = 0u;
     if (tid < 32) s_zero[tid] = 0u;
     const uint32_t s_tab = s_smem + OFF_TAB, s_cmap = s_smem + OFF_CMAP;
     const uint32_t s_scrw = s_smem + OFF_SCR + warp * M2_SCR_BYTES + lane * 4; // this lane's column of the warp's scratch: word w at + 128 w
@@ -422,7 +435,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
     const uint32_t inv_s4 = (uint32_t)(((1ull << 32) + S4 - 1) / S4);
     const bool explode = p.do_unobserved >= 3;
     const bool add_unobs = p.do_unobserved == 1 || p.do_unobserved == 2 || p.do_unobserved == 4 || p.do_unobserved == 5;
-    const bool has_gl = p.gl != nullptr, has_pl = p.pl != nullptr, has_ad = p.ad != nullptr;
+    // GLPL: both the GL and the PL plane exist (compile time); else the plane tests are pinned in registers (the compiler would
+    // otherwise re-read the kernel parameters for every one of the 15 stores of a cell)
+    uint32_t plane_flags = (p.gl != nullptr ? 1u : 0u) | (p.pl != nullptr ? 2u : 0u) | (p.ad != nullptr ? 4u : 0u);
+    asm volatile("mov.u32 %0, %0;" : "+r"(plane_flags));
+    const bool has_gl = GLPL || (plane_flags & 1u), has_pl = GLPL || (plane_flags & 2u), has_ad = (plane_flags & 4u) != 0u;
     const bool pure_ok = TAB && p.m2_pure != nullptr;
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4;
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
@@ -432,8 +449,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
     M2Chunk* const chk_g = BIG ? reinterpret_cast<M2Chunk*>(cnt_g + S4) : nullptr;
     // every variant: the CTA's row of parked results (16 floats per mixed cell) followed by the list of mixed cells (L2-resident)
     const int list_cap = BIG ? S4 : TILE_CELLS;
-    float* const park = p.m2_park + (size_t)blockIdx.x * (size_t)list_cap * 17;
+    float* const park = p.m2_park + (size_t)blockIdx.x * (size_t)list_cap * 18;
     uint32_t* const list_g = reinterpret_cast<uint32_t*>(park + (size_t)list_cap * 16);
+    uint32_t* const sorted_g = list_g + list_cap; // the two-base cells ordered by depth: list position << 16 | virtual cell
     uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]), s_ctrM = smem_u32(&s_ctr[2]), s_ctrN = smem_u32(&s_ctr[3]);
     bool first_tile = true;
     M2SiteE run_e;
@@ -468,11 +486,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
 
         if (MODE == 1) { // per-site beta-distributed base-picking error rate (vcfgl.cpp:425-437), same draw as cell_source.cuh
             if (tid < nsl) {
-                Stream bs;
-                Key key;
-                key.k0 = p.k0; key.k1 = p.k1;
-                bs.init(key, (int64_t)(site_base + (unsigned)tid), 0xFFFFFFFFu, 0, P_SITE);
-                const double e = beta_draw(bs, p.beta_a, p.beta_b);
+                const double e = m2_site_beta(p, site_base + (unsigned)tid);
                 M2SiteE se;
                 se.e = e;
                 se.l2 = (e > 0.0 && e <= 0.5) ? log2f((float)(1.0 - e)) : 0.0f;
@@ -527,7 +541,10 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
                     b2 = __shfl_sync(0xffffffffu, b2, 0);
                     b15 = __shfl_sync(0xffffffffu, b15, 0);
                     const uint32_t lt = low_bits(lane);
-                    if (two) list_put(b2 + (uint32_t)__popc(m2 & lt), (uint32_t)iv);
+                    if (two) {
+                        list_put(b2 + (uint32_t)__popc(m2 & lt), (uint32_t)iv);
+                        atomicAdd(&s_hist[n], 1u);
+                    }
                     else if (mixed) list_put((uint32_t)list_cap - 1u - (b15 + (uint32_t)__popc(m15 & lt)), (uint32_t)iv);
                 }
                 // site totals (counts of one chunk stay below 2^16 per base: 32 cells x 255 reads)
@@ -559,6 +576,18 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
                 s_next = (int)atomicAdd(p.ticket, 1u);
             }
             tile_phase_b(p, lane, nsl, site0, tile, S, T, tot, st, explode, add_unobs, s_base, s_ctr);
+        } else if (warp == 1) { // counting sort of the two-base cells by depth: histogram -> exclusive offsets
+            const uint32_t h0 = s_hist[lane], h1 = s_hist[32 + lane], h2 = lane == 0 ? s_hist[64] : 0u;
+            uint32_t i0 = h0, i1 = h1;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, off), t1 = __shfl_up_sync(0xffffffffu, i1, off);
+                if (lane >= off) { i0 += t0; i1 += t1; }
+            }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+            s_hist[lane] = i0 - h0;
+            s_hist[32 + lane] = tot0 + i1 - h1;
+            if (lane == 0) s_hist[64] = tot0 + tot1 + 0u * h2;
         }
         __syncthreads();
         if (p.zero_holes) tile_zero_holes(p, tid, nsl, S, s_base);
@@ -611,25 +640,35 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
             qs = (int)(info & 0xFFu);
             return ((info >> 16) & 0xFFu) * (uint32_t)M2_TAB_BYTES;
         };
+        if (TAB) { // order the two-base cells by depth, so that the 32 cells a warp takes run read loops of (nearly) equal length
+            for (int j = tid; j < n_two; j += TILE_BLOCK) {
+                const uint32_t iv = list_get((uint32_t)j);
+                const uint32_t c4 = BIG ? cnt_g[iv] : lds32(s_cnt + iv * 4u);
+                const uint32_t pos = atomicAdd(&s_hist[__vsadu4(c4, 0u)], 1u);
+                __stcg(sorted_g + pos, ((uint32_t)j << 16) | iv);
+            }
+            __syncthreads();
+        }
         if (TAB) { // two-base cells: six classes {xx, xy, yy, x., y., ..}
             int g = tile_ticket_get(tile_ticket_issue(s_ctrM, lane));
             while (g * 32 < n_two) {
                 const int raw = tile_ticket_issue(s_ctrM, lane);
-                const int j = g * 32 + lane;
-                const bool act = j < n_two;
+                const bool act = g * 32 + lane < n_two;
+                const uint32_t ent = act ? __ldcg(sorted_g + g * 32 + lane) : 0u;
+                const int j = (int)(ent >> 16);
                 M2Reads<MODE> rd;
                 uint32_t c4 = 0u, pv = 0u;
                 int n = 0;
-                if (act) cell_setup(list_get((uint32_t)j), rd, c4, pv, n);
+                if (act) cell_setup(ent & 0xFFFFu, rd, c4, pv, n);
                 else { rd.deep = false; rd.w0 = rd.w1 = rd.w2 = rd.w3 = rd.cur = 0u; rd.site = 0; rd.sample = 0; rd.g0 = rd.g1 = 0; rd.e = 0.0; }
                 const int nmax = __reduce_max_sync(0xffffffffu, n);
                 qs_classes(rd, n, nmax);
                 const uint32_t seen = nonzero_bytes(c4);
                 const int x = __ffs(seen | 16u) - 1, rest = seen & (seen - 1u);
                 const int y = rest ? __ffs(rest) - 1 : ((x + 1) & 3);
-                const uint32_t ent = s_cmap + (uint32_t)(((x & 3) * 4 + y) * 32);
-                const uint4 cm = lds128(ent);
-                const uint2 ids = lds64(ent + 16u);
+                const uint32_t cm_ent = s_cmap + (uint32_t)(((x & 3) * 4 + y) * 32);
+                const uint4 cm = lds128(cm_ent);
+                const uint2 ids = lds64(cm_ent + 16u);
                 float gc[6];
                 gc[0] = (pv & cm.x & 0xFFFFu) ? -0.0f : -CUDART_INF_F;
                 gc[1] = (pv & (cm.x >> 16)) ? -0.0f : -CUDART_INF_F;
@@ -708,6 +747,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
         }
         __syncthreads(); // parked values are visible to the CTA (global memory, same CTA: the barrier orders them)
         if (tid == 0) { s_ctr[2] = s_ctr[3] = 0u; s_mix[0] = s_mix[1] = 0u; }
+        if (tid < 72) s_hist[tid] = 0u;
 
         // ---------------- phase C: assemble + emit, one warp per chunk of 32 virtual cells
         float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
@@ -824,26 +864,32 @@ static size_t tile_m2_dyn_smem(bool big)
            (MODE == 2 ? 2048 : 0) + (big ? 0 : (size_t)(TILE_CELLS / 32) * sizeof(M2Chunk) + (size_t)TILE_CELLS * 4);
 }
 
-template <int MODE, bool BIG, bool TAB>
+template <int MODE, bool BIG, bool TAB, bool GLPL>
 static int tile_m2_ctas_per_sm()
 {
     const size_t dyn = tile_m2_dyn_smem<MODE>(BIG);
-    cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB, GLPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m2<MODE, BIG, TAB, GLPL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m2<MODE, BIG, TAB>, TILE_BLOCK, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m2<MODE, BIG, TAB, GLPL>, TILE_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
     return per_sm;
 }
 
+template <int MODE, bool BIG, bool TAB, bool GLPL>
+static void launch_tile_m2_g(const DevParams& p, cudaStream_t st, int n_sms)
+{
+    const size_t dyn = tile_m2_dyn_smem<MODE>(BIG);
+    int grid = n_sms * tile_m2_ctas_per_sm<MODE, BIG, TAB, GLPL>();
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    k_tile_m2<MODE, BIG, TAB, GLPL><<<grid, TILE_BLOCK, dyn, st>>>(p);
+}
 template <int MODE, bool BIG, bool TAB>
 static void launch_tile_m2_t(const DevParams& p, cudaStream_t st, int n_sms)
 {
-    const size_t dyn = tile_m2_dyn_smem<MODE>(BIG);
-    int grid = n_sms * tile_m2_ctas_per_sm<MODE, BIG, TAB>();
-    if (grid > p.n_tiles) grid = p.n_tiles;
-    k_tile_m2<MODE, BIG, TAB><<<grid, TILE_BLOCK, dyn, st>>>(p);
+    if (p.gl && p.pl) launch_tile_m2_g<MODE, BIG, TAB, true>(p, st, n_sms);
+    else launch_tile_m2_g<MODE, BIG, TAB, false>(p, st, n_sms);
 }
 
 // mode: 0 FIXED / run-constant error rate, 1 FIXED / per-site error rate, 2 LUT (per-read quality scores)
@@ -866,7 +912,7 @@ size_t tile_m2_row_words(int S, int n_sms)
 size_t tile_m2_park_floats(int S, int n_sms)
 {
     const int S4 = (S + 3) & ~3;
-    return (size_t)(S4 > TILE_CELLS ? S4 : TILE_CELLS) * 17 * TILE_SCRATCH_CTAS_PER_SM * (size_t)n_sms; // + one list word per cell
+    return (size_t)(S4 > TILE_CELLS ? S4 : TILE_CELLS) * 18 * TILE_SCRATCH_CTAS_PER_SM * (size_t)n_sms; // + two list words per cell
 }
 
 // ---- the sampler's per-read draws in the replay layout (vgl_native_draws): pass 0 writes the depths, pass 1 the reads
@@ -899,11 +945,7 @@ __global__ void k_tile_m2_draws(const DevParams p, int mode, int pass, int32_t* 
     se.e = p.error_rate;
     se.l2 = se.er = 0.0f;
     if (mode == 1) {
-        Stream bs;
-        Key key;
-        key.k0 = p.k0; key.k1 = p.k1;
-        bs.init(key, (int64_t)site, 0xFFFFFFFFu, 0, P_SITE);
-        const double e = beta_draw(bs, p.beta_a, p.beta_b);
+        const double e = m2_site_beta(p, site);
         se.e = e;
         se.l2 = (e > 0.0 && e <= 0.5) ? log2f((float)(1.0 - e)) : 0.0f;
         se.er = (float)(e / (1.0 - e));
