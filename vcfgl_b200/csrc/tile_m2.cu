@@ -499,13 +499,19 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
         // ---------------- phase A: counts, FORMAT/DP, per-site base totals, the list of mixed cells
         {
             int cur = tile_ticket_get(tile_ticket_issue(s_ctrA, lane));
+            int nxt = tile_ticket_get(tile_ticket_issue(s_ctrA, lane));
+            int iv = cur * 32 + lane;
+            int sl = (int)__umulhi((uint32_t)iv, inv_s4), v = iv - sl * S4;
+            bool real = iv < nv && v < S;
+            uint32_t gt = 0xFFu;
+            if (real) gt = gt_t[(uint32_t)(iv - sl * PAD)];
             while (cur < nchunk) {
-                const int raw = tile_ticket_issue(s_ctrA, lane);
-                const int iv = cur * 32 + lane;
-                const int sl = (int)__umulhi((uint32_t)iv, inv_s4), v = iv - sl * S4;
-                const bool real = iv < nv && v < S;
-                uint32_t gt = 0xFFu;
-                if (real) gt = gt_t[(uint32_t)(iv - sl * PAD)];
+                const int raw = tile_ticket_issue(s_ctrA, lane); // the chunk after next
+                const int iv2 = nxt * 32 + lane;
+                const int sl2 = (int)__umulhi((uint32_t)iv2, inv_s4), v2 = iv2 - sl2 * S4;
+                const bool real2 = iv2 < nv && v2 < S;
+                uint32_t gt2 = 0xFFu;
+                if (real2) gt2 = gt_t[(uint32_t)(iv2 - sl2 * PAD)];
                 uint32_t ad = 0u;
                 int n = 0;
                 if (real) {
@@ -564,7 +570,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
                         if (val) atomicAdd(&tot[sl * 4 + b], val);
                     }
                 }
-                cur = tile_ticket_get(raw);
+                cur = nxt; iv = iv2; sl = sl2; v = v2; real = real2; gt = gt2;
+                nxt = tile_ticket_get(raw);
             }
         }
         __syncthreads();
@@ -574,6 +581,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
             if (lane == 0) {
                 s_ctr[0] = 0u;
                 s_next = (int)atomicAdd(p.ticket, 1u);
+            }
+            { // pull the next tile's genotypes into L2 while this tile is scored
+                const int nt = __shfl_sync(0xffffffffu, lane == 0 ? s_next : 0, 0);
+                const int64_t lo = (int64_t)nt * T * S + lane * 128;
+                if (nt < p.n_tiles && lane * 128 < T * S && lo < p.n_cells) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gt + lo));
             }
             tile_phase_b(p, lane, nsl, site0, tile, S, T, tot, st, explode, add_unobs, s_base, s_ctr);
         } else if (warp == 1) { // counting sort of the two-base cells by depth: histogram -> exclusive offsets
