@@ -98,6 +98,7 @@ struct vgl_ctx {
     size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr, *d_qm_cdf = nullptr;
     float *d_m2_pure = nullptr, *d_m2_park = nullptr;
+    void* d_m1_pure = nullptr;
     int q_dom = 0, q_dom_idx = 0;
     double q_minor = 0.0;
     double* d_m2_tab = nullptr;
@@ -252,7 +253,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park); cudaFree(ctx->d_m1_pure);
     delete ctx;
 }
 
@@ -371,6 +372,16 @@ static int create_impl(vgl_ctx* ctx)
         }
     }
     if (p.depth_mode == VGL_DEPTH_INF) ctx->use_fused = ctx->use_tile = ctx->use_tile_m2 = ctx->tile_aux = 0; // truth.cu
+    // closed form of cells whose reads all show one base: worth its branch when most 32-cell chunks hold no mis-called read
+    // (expected mis-called reads per chunk = 32 x depth x error rate below ~1/2; heterozygous cells are the input's business)
+    const double exp_depth = p.depth_mode == VGL_DEPTH_POISSON || p.depth_mode == VGL_DEPTH_FIXED ? p.depth_mean : 0.0;
+    if (ctx->use_tile && 32.0 * exp_depth * p.error_rate < 0.5 && !getenv("VGL_NO_PURE")) {
+        CK(cudaMalloc(&ctx->d_m1_pure, 256 * sizeof(M1Pure)));
+        if (!build_m1f_pure_table(ctx->d_m1_bsum, ctx->d_m1_het, ctx->d_m1_pure, nullptr)) {
+            cudaFree(ctx->d_m1_pure);
+            ctx->d_m1_pure = nullptr;
+        }
+    }
     // narrow host planes: 8 bits when no cell can hold more than 255 reads (the truncated tail of the Poisson law is below 2^-64)
     if (p.host_output == VGL_HOST_NARROW) ctx->narrow_bits = alias_ok ? 8 : 16;
     if (ctx->use_tile || ctx->use_tile_m2) {
@@ -740,6 +751,7 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.pois_alias = ctx->d_alias;
     p.err_cdf = ctx->d_errcdf;
     p.cnt_scratch = ctx->d_cnt_scratch;
+    p.m1_pure = ctx->d_m1_pure;
     p.qcls = ctx->d_qcls;
     p.m2_tab = ctx->d_m2_tab;
     p.m2_nq = ctx->m2_nq;

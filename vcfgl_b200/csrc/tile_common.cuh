@@ -32,6 +32,7 @@ struct __align__(16) TSite {
     uint32_t sel4;        // PRMT selector of allele 4 (see sel01)
     uint32_t sel01, sel23; // 16-bit PRMT selectors of alleles 0..3: byte (base) of the packed counts, 4 = reads 0
     int32_t g_end, r_end; // g_rel / r_rel + the padded block size
+    uint32_t cls[4];      // per base x: bits 0..14 = genotype slots that hold x exactly once, bits 16..19 = the slot of xx
 };
 
 // per-site scratch of the AUX variant of k_tile_m1f (QS / I16 / INFO ADF, ADR)
@@ -212,6 +213,21 @@ __device__ __forceinline__ void tile_phase_b(const DevParams& p, const int lane,
         ts.sel23 = sel[2] | (sel[3] << 16);
         ts.sel4 = sel[4];
         ts.AG = keep ? ((uint32_t)o.n_alleles | ((uint32_t)o.n_genotypes << 8) | ((all15 && dp > 0) ? 1u << 16 : 0u)) : 0u;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { // slot classes of a cell whose reads all show base x (pure cells: closed-form GL / PL)
+            uint32_t m = 0u;
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+#pragma unroll
+                for (int j = 0; j <= k; ++j) {
+                    const uint32_t sl_ = (uint32_t)((pm >> (4 * (k * (k + 1) / 2 + j))) & 0xF);
+                    if (sl_ != 0xFu) {
+                        if ((j == x) != (k == x)) m |= 1u << sl_;
+                        if (j == x && k == x) m |= sl_ << 16;
+                    }
+                }
+            ts.cls[x] = m;
+        }
         if (keep) {
             my_g = (S * o.n_genotypes + 3) & ~3;
             my_r = (S * o.n_alleles + 3) & ~3;

@@ -21,6 +21,9 @@
 
 namespace vgl {
 
+// BIG variant: words of a CTA's global row = counts [S4] | AUX chunk masks [S4 / 32 + 1][8]
+__host__ __device__ inline size_t tile_m1f_row_words(int S4) { return (size_t)S4 + (size_t)8 * (S4 / 32 + 1); }
+
 // One cell of the count-level sampler: returns the four 8-bit base counts (A | C << 8 | G << 16 | T << 24).
 // Draws (same counter layout as draw() in philox.cuh, purpose P_COUNTS): block 0 = {x,y: depth; z: number of
 // errors; w: haplotype bits 0..31}, block 1 = {x: haplotype bits 32..63; y,z,w: placement of errors 1..3};
@@ -167,9 +170,10 @@ __device__ __forceinline__ void tile_tail_sums(const DevParams& p, unsigned long
         const u32x4 blk = philox_rk(p, c0, c1, sample, ((uint32_t)P_TAIL << 24) | (uint32_t)kb);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            const int r = kb * 12 + j * 3;
+            if (r >= nmax) break; // uniform: no cell of the warp has a read left for this word
             int t0, t1, t2;
             tile_tail3(tile_word(blk, j), t0, t1, t2);
-            const int r = kb * 12 + j * 3;
             t0 = r < n ? t0 : 0;
             t1 = r + 1 < n ? t1 : 0;
             t2 = r + 2 < n ? t2 : 0;
@@ -209,13 +213,32 @@ __device__ __forceinline__ float tile_add_const_times(float v, int c, int k)
     return v;
 }
 
-// I16 of one site (vcfgl.cpp:982-1074) from the site totals.  Every accumulator of the reference is a float that
-// adds small non-negative integers in (sample, read) order; while the total stays below 2^24 every partial sum is an
-// exactly representable integer and the float equals the integer total.  Beyond that (deep, many samples) the sums
-// are redone in the reference's order from the cached counts (SEQ path, one thread: rare and slow, but exact).
+// acc + 1.0f, k times, as the reference's float accumulator would round it (vcfgl.cpp:845-898: a cell whose reads all show the
+// base adds the term 1.0f).  Within a binade adding 1 is exact (acc sits on the binade's grid, ulp <= 1), so the run jumps
+// to the last value below the next power of two in one exact step and takes only the crossing add through the rounder.
+__device__ __forceinline__ float tile_add_ones(float acc, int k)
+{
+    while (k > 0) {
+        if (acc < 1.0f || acc >= 8388608.0f) { // below 1 the grid is finer than the result's; above 2^23 every add may round
+            acc = __fadd_rn(acc, 1.0f);
+            --k;
+            continue;
+        }
+        const float top = __uint_as_float((__float_as_uint(acc) & 0x7F800000u) + 0x00800000u); // next power of two above acc
+        const float d = __fsub_rn(top, acc);                                                  // exact (Sterbenz)
+        const int m = min(k, (int)ceilf(d) - 1);                                              // adds that stay below `top`
+        acc = __fadd_rn(acc, (float)m);                                                       // exact: same binade, on the grid
+        k -= m;
+        if (k > 0) { acc = __fadd_rn(acc, 1.0f); --k; }                                       // the crossing add rounds like the reference's
+    }
+    return acc;
+}
+
+// I16 of one site when a float accumulator overflows its exact range (vcfgl.cpp:982-1074; deep sites with many samples): the
+// sums are redone in the reference's order from the cached counts.  One thread, rare and slow, but exact.
 template <bool BIG>
-__device__ __noinline__ void tile_site_i16(const DevParams& p, const TAux& ax, const unsigned long long site, const int S, const uint32_t s_cnt_site,
-                                           const uint32_t* cnt_g, float* out)
+__device__ __noinline__ void tile_site_i16_seq(const DevParams& p, const TAux& ax, const unsigned long long site, const int S, const uint32_t s_cnt_site,
+                                               const uint32_t* cnt_g, float* out)
 {
     float v[16];
 #pragma unroll
@@ -234,61 +257,40 @@ __device__ __noinline__ void tile_site_i16(const DevParams& p, const TAux& ax, c
     const int refb = a2b[0];
     const int q = (p.adjust_qs & 2) ? p.pre_adj_qs : p.pre_qs, q2 = qs_squared(q), mq = p.i16_mapq, mq2 = mq * mq;
     auto cnt = [&](int s) -> uint32_t { return BIG ? cnt_g[s] : lds32(s_cnt_site + 4u * (uint32_t)s); };
-    // the site's last read (stale r_base)
     int stale = -1;
     if (ax.last >= 0) {
         const uint32_t c4 = cnt(ax.last);
         stale = tile_base_of_read(c4, tile_last_read(p, site, (uint32_t)ax.last, (int)__vsadu4(c4, 0u)));
     }
-    long long nonref = 0;
+    float tsum = 0.0f, tsq = 0.0f;
+    for (int s = 0; s < S; ++s) {
+        const uint32_t c4 = cnt(s);
+        const int n = (int)__vsadu4(c4, 0u);
+        for (int i = 0; i < n; ++i) {
+            const int t = tile_tail_of_read(p, site, (uint32_t)s, i);
+            tsum = __fadd_rn(tsum, (float)t);
+            tsq = __fadd_rn(tsq, (float)(t * t));
+        }
+        const int cr = (int)((c4 >> (8 * refb)) & 0xFFu);
+        v[4] = __fadd_rn(v[4], (float)(q * cr));
+        v[5] = __fadd_rn(v[5], (float)(q2 * cr));
+        for (int a = 0; a < A; ++a) {
+            if (a == n_obs) continue;
+            const int b = a2b[a];
+            if (b < 0 || b == 4) continue;
+            const int k = (int)((c4 >> (8 * b)) & 0xFFu);
+            if (a == 0) { v[8] = tile_add_const_times(v[8], mq, k); v[9] = tile_add_const_times(v[9], mq2, k); }
+            else        { v[10] = tile_add_const_times(v[10], mq, k); v[11] = tile_add_const_times(v[11], mq2, k); }
+        }
+    }
     for (int a = 1; a < A; ++a) {
         if (a == n_obs) continue;
         const int b = a2b[a];
         if (b < 0 || b == 4) continue;
-        nonref += ax.tot[b];
-    }
-    const long long ref = refb >= 0 && refb < 4 ? ax.tot[refb] : 0;
-    const long long qmax = max(max(q2, q), max(mq2, mq));
-    const bool exact = qmax * max(ref, nonref) < 16777216ll && ax.tq < 16777216ull;
-    float tsum, tsq;
-    if (exact) {
-        tsum = (float)ax.ts;
-        tsq = (float)ax.tq;
-        v[4] = (float)(q * ref); v[5] = (float)(q2 * ref);
-        v[8] = (float)(mq * ref); v[9] = (float)(mq2 * ref);
-        v[6] = (float)(q * nonref); v[7] = (float)(q2 * nonref);
-        v[10] = (float)(mq * nonref); v[11] = (float)(mq2 * nonref);
-    } else {
-        tsum = tsq = 0.0f;
         for (int s = 0; s < S; ++s) {
-            const uint32_t c4 = cnt(s);
-            const int n = (int)__vsadu4(c4, 0u);
-            for (int i = 0; i < n; ++i) {
-                const int t = tile_tail_of_read(p, site, (uint32_t)s, i);
-                tsum = __fadd_rn(tsum, (float)t);
-                tsq = __fadd_rn(tsq, (float)(t * t));
-            }
-            const int cr = (int)((c4 >> (8 * refb)) & 0xFFu);
-            v[4] = __fadd_rn(v[4], (float)(q * cr));
-            v[5] = __fadd_rn(v[5], (float)(q2 * cr));
-            for (int a = 0; a < A; ++a) {
-                if (a == n_obs) continue;
-                const int b = a2b[a];
-                if (b < 0 || b == 4) continue;
-                const int k = (int)((c4 >> (8 * b)) & 0xFFu);
-                if (a == 0) { v[8] = tile_add_const_times(v[8], mq, k); v[9] = tile_add_const_times(v[9], mq2, k); }
-                else        { v[10] = tile_add_const_times(v[10], mq, k); v[11] = tile_add_const_times(v[11], mq2, k); }
-            }
-        }
-        for (int a = 1; a < A; ++a) {
-            if (a == n_obs) continue;
-            const int b = a2b[a];
-            if (b < 0 || b == 4) continue;
-            for (int s = 0; s < S; ++s) {
-                const int k = (int)((cnt(s) >> (8 * b)) & 0xFFu);
-                v[6] = __fadd_rn(v[6], (float)(q * k));
-                v[7] = __fadd_rn(v[7], (float)(q2 * k));
-            }
+            const int k = (int)((cnt(s) >> (8 * b)) & 0xFFu);
+            v[6] = __fadd_rn(v[6], (float)(q * k));
+            v[7] = __fadd_rn(v[7], (float)(q2 * k));
         }
     }
     v[0] = (float)ax.fw[refb];
@@ -308,25 +310,56 @@ __device__ __noinline__ void tile_site_i16(const DevParams& p, const TAux& ax, c
     for (int i = 0; i < 16; ++i) out[i] = v[i];
 }
 
-// GL / PL of one cell from its scores, scattered into the warp's stage slice in allele order
-// (gl_methods.cpp:338-357, vcfgl.cpp:907-939).  ALL15: every base pair is a genotype of the site.
-// With w = q/10 >= 0: GL = (-w) - max(-w) = min(w) - w, the same float as the reference's subtraction.
+// I16 of one site (vcfgl.cpp:982-1074) from the site totals.  Every accumulator of the reference is a float that adds small
+// non-negative integers in (sample, read) order; while the total stays below 2^24 every partial sum is an exactly
+// representable integer and the float equals the integer total.  Beyond that: tile_site_i16_seq.
+template <bool BIG>
+__device__ __forceinline__ void tile_site_i16(const DevParams& p, const TAux& ax, const unsigned long long site, const int S, const uint32_t s_cnt_site,
+                                              const uint32_t* cnt_g, float* out)
+{
+    const int A = (int)(ax.info & 0xFFu), n_obs = (int)((ax.info >> 8) & 0xFFu);
+    const int q = (p.adjust_qs & 2) ? p.pre_adj_qs : p.pre_qs, q2 = qs_squared(q), mq = p.i16_mapq, mq2 = mq * mq;
+    // the site's last read (stale r_base)
+    int stale = -1;
+    if (ax.last >= 0) {
+        const uint32_t c4 = BIG ? cnt_g[ax.last] : lds32(s_cnt_site + 4u * (uint32_t)ax.last);
+        stale = tile_base_of_read(c4, tile_last_read(p, site, (uint32_t)ax.last, (int)__vsadu4(c4, 0u)));
+    }
+    int ref = 0, ref_fw = 0, nonref = 0, nonref_fw = 0;
+    bool stale_ref = false, stale_nonref = false;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int a = (int)((ax.b2a >> (4 * b)) & 0xFu);
+        if (a == 0) { ref = ax.tot[b]; ref_fw = ax.fw[b]; stale_ref = b == stale; }
+        else if (a != 0xF && a < A && a != n_obs) { nonref += ax.tot[b]; nonref_fw += ax.fw[b]; stale_nonref = stale_nonref || b == stale; }
+    }
+    const long long qmax = max(max(q2, q), max(mq2, mq));
+    if (!(qmax * (long long)max(ref, nonref) < 16777216ll && ax.tq < 16777216ull)) {
+        tile_site_i16_seq<BIG>(p, ax, site, S, s_cnt_site, cnt_g, out);
+        return;
+    }
+    const float tsum = (float)ax.ts, tsq = (float)ax.tq;
+    out[0] = (float)ref_fw; out[1] = (float)(ref - ref_fw); out[2] = (float)nonref_fw; out[3] = (float)(nonref - nonref_fw);
+    out[4] = (float)(q * ref); out[5] = (float)(q2 * ref); out[6] = (float)(q * nonref); out[7] = (float)(q2 * nonref);
+    out[8] = (float)(mq * ref); out[9] = (float)(mq2 * ref); out[10] = (float)(mq * nonref); out[11] = (float)(mq2 * nonref);
+    out[12] = stale_ref ? tsum : 0.0f; out[13] = stale_ref ? tsq : 0.0f;
+    out[14] = stale_nonref ? tsum : 0.0f; out[15] = stale_nonref ? tsq : 0.0f;
+}
+
+// GL and the mantissa-encoded PL of one cell from its scores (gl_methods.cpp:338-357, vcfgl.cpp:907-939).  ALL15: every base
+// pair is a genotype of the site.  With w = q/10 >= 0: GL = (-w) - max(-w) = min(w) - w, the same float as the reference's
+// subtraction.
 template <bool ALL15>
-__device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const uint4 slot, uint32_t cell_g, bool has_gl, bool has_pl)
+__device__ __forceinline__ void tile_cell_values(const float (&q)[15], const uint32_t (&off)[15], float (&g)[16], float (&u)[16])
 {
     float w[16];
 #pragma unroll
     for (int k = 0; k < 14; k += 2) unpack2(div10_fast2(pack2(q[k], q[k + 1])), w[k], w[k + 1]);
     w[14] = -neg_div10_fast(q[14]);
-    const uint32_t sw[4] = {slot.x, slot.y, slot.z, slot.w};
-    uint32_t off[15];
-#pragma unroll
-    for (int k = 0; k < 15; ++k) off[k] = __byte_perm(sw[k >> 2], 0u, 0x4440u | (k & 3));
     float mn = CUDART_INF_F;
 #pragma unroll
     for (int k = 0; k < 15; ++k) mn = fminf(mn, (ALL15 || off[k] != 0xFFu) ? w[k] : CUDART_INF_F);
     const f32x2 mn2 = pack2(mn, mn);
-    float g[16], u[16];
 #pragma unroll
     for (int k = 0; k < 14; k += 2) {
         const f32x2 g2 = sub2(mn2, pack2(w[k], w[k + 1]));
@@ -335,6 +368,18 @@ __device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const uint4
     }
     g[14] = __fsub_rn(mn, w[14]);
     u[14] = __fadd_rz(__fadd_rz(__fmul_rn(-10.0f, g[14]), 0.5f), 8388608.0f);
+}
+
+// ... scattered into the warp's stage slice in allele order
+template <bool ALL15>
+__device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const uint4 slot, uint32_t cell_g, bool has_gl, bool has_pl)
+{
+    const uint32_t sw[4] = {slot.x, slot.y, slot.z, slot.w};
+    uint32_t off[15];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) off[k] = __byte_perm(sw[k >> 2], 0u, 0x4440u | (k & 3));
+    float g[16], u[16];
+    tile_cell_values<ALL15>(q, off, g, u);
 #pragma unroll
     for (int k = 0; k < 15; ++k) {
         if (ALL15 || off[k] != 0xFFu) {
@@ -345,11 +390,76 @@ __device__ __forceinline__ void tile_emit_cell(const float (&q)[15], const uint4
     }
 }
 
+// ---- "pure" cells: every read shows the same base x.  The 15 scores then fall into three classes -- xx (score 0), the pairs
+// that hold x once, the pairs without x -- and GL / PL are functions of the depth alone.  The table is built on the device by
+// the scoring code itself (so it is bit-identical by construction) for every base and depth, and is only used when the
+// classes really collapse for all four bases (`ok` stays 1).
+__global__ void k_m1f_pure_table(const double* __restrict__ bsum, const double* __restrict__ het, M1Pure* __restrict__ out, int* ok)
+{
+    const int n = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (n > 255) return;
+    M1Pure r;
+    r.gl1 = r.gl0 = 0.0f;
+    r.pl1 = r.pl0 = 0;
+    bool good = true;
+    if (n >= 1) {
+        for (int x = 0; x < 4; ++x) {
+            float q[15];
+            m1f_scores_noclamp(n, x == 0 ? n : 0, x == 1 ? n : 0, x == 2 ? n : 0, x == 3 ? n : 0, bsum, het, q);
+            uint32_t off[15];
+#pragma unroll
+            for (int k = 0; k < 15; ++k) off[k] = 0u;
+            float g[16], u[16];
+            tile_cell_values<true>(q, off, g, u);
+            M1Pure c;
+            c.gl1 = c.gl0 = 0.0f;
+            c.pl1 = c.pl0 = 0;
+            bool have1 = false, have0 = false;
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+#pragma unroll
+                for (int j = 0; j <= k; ++j) {
+                    const int pair = k * (k + 1) / 2 + j, hits = (j == x) + (k == x);
+                    const float gv = g[pair];
+                    const int pv = pl_from_magic_bits(u[pair]);
+                    if (hits == 2) good = good && __float_as_uint(gv) == 0u && pv == 0;
+                    else if (hits == 1) {
+                        if (!have1) { c.gl1 = gv; c.pl1 = pv; have1 = true; }
+                        good = good && __float_as_uint(gv) == __float_as_uint(c.gl1) && pv == c.pl1;
+                    } else {
+                        if (!have0) { c.gl0 = gv; c.pl0 = pv; have0 = true; }
+                        good = good && __float_as_uint(gv) == __float_as_uint(c.gl0) && pv == c.pl0;
+                    }
+                }
+            if (x == 0) r = c;
+            good = good && __float_as_uint(c.gl1) == __float_as_uint(r.gl1) && __float_as_uint(c.gl0) == __float_as_uint(r.gl0) &&
+                   c.pl1 == r.pl1 && c.pl0 == r.pl0;
+        }
+    }
+    out[n] = r;
+    if (!good) atomicExch(ok, 0);
+}
+
+// builds the table into `out` ([256] M1Pure, device); returns 1 when pure cells may use it
+int build_m1f_pure_table(const double* d_bsum, const double* d_het, void* out, cudaStream_t st)
+{
+    int* d_ok = nullptr;
+    int ok = 1;
+    if (cudaMalloc((void**)&d_ok, sizeof(int)) != cudaSuccess) return 0;
+    cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, st);
+    k_m1f_pure_table<<<2, 128, 0, st>>>(d_bsum, d_het, reinterpret_cast<M1Pure*>(out), d_ok);
+    cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) ok = 0;
+    cudaFree(d_ok);
+    return ok;
+}
 
 // GEN: any subset of the GL / PL / AD planes (else all three); BIG: a site's counts do not fit the shared-memory
 // cache -> they pass through a per-CTA scratch row in global memory (L2-resident), read one chunk ahead;
 // AUX: QS / I16 / INFO ADF, ADR (strand and tail-distance draws in phase A, per-site sums in an extra phase after B)
-template <bool GEN, bool BIG, bool AUX>
+// PURE: chunks whose cells all show a single base take the closed form (m1_pure table); compiled in only for runs where such
+// chunks are the rule (low depth x error rate), because the extra branch costs the general path ~10 %
+template <bool GEN, bool BIG, bool AUX, bool PURE>
 __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -357,7 +467,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
     //         aux [sites] (AUX only) | cnt [cap]
     constexpr int WST = 2 * TILE_WST_G + TILE_WST_R; // words per warp
     constexpr uint32_t OFF_STAGE = 2048 + 4096, OFF_ST = OFF_STAGE + TILE_WARPS * WST * 4, OFF_TOT = OFF_ST + TILE_MAX_SITES * sizeof(TSite),
-                       OFF_AUX = OFF_TOT + TILE_MAX_SITES * 16, OFF_CNT = OFF_AUX + (AUX ? TILE_MAX_SITES * sizeof(TAux) : 0);
+                       OFF_AUX = OFF_TOT + TILE_MAX_SITES * 16, OFF_MSK = OFF_AUX + (AUX ? TILE_MAX_SITES * sizeof(TAux) : 0),
+                       OFF_CNT = OFF_MSK + ((AUX && !BIG) ? (TILE_CELLS / 32) * 32 : 0);
     TSite* st = reinterpret_cast<TSite*>(tile_smem + OFF_ST);
     int* tot = reinterpret_cast<int*>(tile_smem + OFF_TOT);
     TAux* aux = reinterpret_cast<TAux*>(tile_smem + OFF_AUX);
@@ -407,7 +518,10 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4; // this warp's GL slice; PL at +TILE_WST_G words, AD at +2*TILE_WST_G
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
     const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST;
-    uint32_t* const cnt_g = BIG ? p.cnt_scratch + (size_t)blockIdx.x * S4 : nullptr;
+    // BIG: per-CTA row in global memory = counts [S4], then (AUX) the chunk masks [S4 / 32 + 1][8]
+    uint32_t* const cnt_g = BIG ? p.cnt_scratch + (size_t)blockIdx.x * tile_m1f_row_words(S4) : nullptr;
+    uint32_t* const msk_g = BIG ? cnt_g + S4 : nullptr;
+    const uint32_t s_msk = s_smem + OFF_MSK;
     uint32_t s_ctrA = smem_u32(&s_ctr[0]), s_ctrC = smem_u32(&s_ctr[1]);
     bool first_tile = true;
 
@@ -480,6 +594,24 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
                         if (val) atomicAdd(&tot[sl * 4 + b], val);
                     }
                 }
+                if (AUX) { // per base: which cells of the chunk show only that base / that base among others (the QS terms 1 / fractional)
+                    const int n_ = (int)__vsadu4(ad, 0u);
+                    const uint32_t nz = __vcmpne4(ad, 0u), eqn = __vcmpeq4(ad, (uint32_t)n_ * 0x01010101u);
+                    const uint32_t full = nz & eqn, frac = nz & ~eqn;
+                    uint32_t mk[8];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        mk[b] = __ballot_sync(0xffffffffu, (full >> (8 * b)) & 1u);
+                        mk[4 + b] = __ballot_sync(0xffffffffu, (frac >> (8 * b)) & 1u);
+                    }
+                    if (lane < 8) {
+                        uint32_t mine = mk[0];
+#pragma unroll
+                        for (int k = 1; k < 8; ++k) mine = lane == k ? mk[k] : mine;
+                        if (BIG) msk_g[(size_t)cur * 8 + lane] = mine;
+                        else sts32(s_msk + (uint32_t)cur * 32u + 4u * (uint32_t)lane, mine);
+                    }
+                }
                 if (AUX) { // strand and tail-distance draws, summed per site
                     const int n = (int)__vsadu4(ad, 0u);
                     const int nmax = __reduce_max_sync(0xffffffffu, n);
@@ -550,21 +682,41 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
         if (AUX) {
             const int sl = tid >> 2, b = tid & 3;
             if (sl < nsl && (aux[sl].info >> 16)) {
-                const TAux ax = aux[sl];
+                const uint32_t b2a_ = aux[sl].b2a;
                 const uint32_t s_cnt_site = s_cnt + (uint32_t)(sl * S4) * 4u;
                 vgl_site_out* const rec = p.sites + site0 + sl;
-                const int a = (int)((ax.b2a >> (4 * b)) & 0xFu);
+                const int a = (int)((b2a_ >> (4 * b)) & 0xFu);
                 if ((p.tag_mask & VGL_TAG_QS) && a != 0xF) {
+                    // QS[a] = sum over samples, in order, of (float)(q c_b) / (float)(q n) (vcfgl.cpp:845-898).  Cells without the
+                    // base add +0 (identity), cells with nothing but the base add exactly 1 (tile_add_ones runs them in bulk);
+                    // only the cells that mix the base with others take a division.  The chunk masks of phase A say which is which.
                     const int q = (p.adjust_qs & 2) ? p.pre_adj_qs : p.pre_qs;
                     float acc = 0.0f;
-                    for (int s = 0; s < S; ++s) {
-                        const uint32_t c4 = BIG ? cnt_g[s] : lds32(s_cnt_site + 4u * (uint32_t)s);
-                        const float sum = (float)(q * (int)__vsadu4(c4, 0u));
-                        if (sum != 0.0f) acc = __fadd_rn(acc, __fdiv_rn((float)(q * (int)((c4 >> (8 * b)) & 0xFFu)), sum));
+                    const int v_lo = sl * S4, v_hi = v_lo + S; // the site's virtual cells
+                    for (int c = v_lo >> 5; c <= (v_hi - 1) >> 5; ++c) {
+                        const int lo = max(v_lo - c * 32, 0), hi = min(v_hi - c * 32, 32);
+                        const uint32_t range = low_bits(hi) & ~low_bits(lo);
+                        uint32_t fullm = (BIG ? msk_g[(size_t)c * 8 + b] : lds32(s_msk + (uint32_t)c * 32u + 4u * (uint32_t)b)) & range;
+                        uint32_t fracm = (BIG ? msk_g[(size_t)c * 8 + 4 + b] : lds32(s_msk + (uint32_t)c * 32u + 16u + 4u * (uint32_t)b)) & range;
+                        while (fracm) {
+                            const int pos = __ffs(fracm) - 1;
+                            const uint32_t before = low_bits(pos);
+                            acc = tile_add_ones(acc, __popc(fullm & before));
+                            fullm &= ~before;
+                            const int iv = c * 32 + pos;
+                            const uint32_t c4 = BIG ? cnt_g[iv] : lds32(s_cnt + 4u * (uint32_t)iv);
+                            const float sum = (float)(q * (int)__vsadu4(c4, 0u));
+                            acc = __fadd_rn(acc, __fdiv_rn((float)(q * (int)((c4 >> (8 * b)) & 0xFFu)), sum));
+                            fracm &= fracm - 1u;
+                        }
+                        acc = tile_add_ones(acc, __popc(fullm));
                     }
                     rec->qs[a] = acc;
                 }
-                if ((p.tag_mask & VGL_TAG_I16) && b == 0) tile_site_i16<BIG>(p, ax, site_base + (uint32_t)sl, S, s_cnt_site, cnt_g, rec->i16);
+            }
+            if ((p.tag_mask & VGL_TAG_I16) && tid < nsl && (aux[tid].info >> 16)) { // a thread per site (one warp)
+                const TAux ax = aux[tid];
+                tile_site_i16<BIG>(p, ax, site_base + (uint32_t)tid, S, s_cnt + (uint32_t)(tid * S4) * 4u, cnt_g, p.sites[site0 + tid].i16);
             }
             __syncthreads();
             if (tid < nsl) { // clear the phase-A accumulators for the next tile
@@ -578,6 +730,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
         float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
         int32_t* const pl_t = has_pl ? p.pl + s_base[0] : nullptr;
         int32_t* const ad_t = has_ad ? p.ad + s_base[1] : nullptr;
+        const uint4* const pure_tab = reinterpret_cast<const uint4*>(p.m1_pure);
         // chunk tickets run two ahead and the counts of the next chunk are fetched before the current one is scored
         auto load_counts = [&](int chunk) -> uint32_t {
             const int i = chunk * 32 + lane;
@@ -594,8 +747,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
             int sl = (int)__umulhi((uint32_t)iv, inv_s4);
             int v = iv - sl * S4;
             if (sl >= nsl) { sl = nsl - 1; v = S4; } // past the tile: sits at the end of the last block
-            const uint4 t1 = lds128(s_st + (uint32_t)sl * 48u + 16u); // g_rel, r_rel, AG, sel4
-            const uint4 t2 = lds128(s_st + (uint32_t)sl * 48u + 32u); // sel01, sel23, g_end, r_end
+            const uint4 t1 = lds128(s_st + (uint32_t)sl * 64u + 16u); // g_rel, r_rel, AG, sel4
+            const uint4 t2 = lds128(s_st + (uint32_t)sl * 64u + 32u); // sel01, sel23, g_end, r_end
             const int A = (int)(t1.z & 0xFF), G = (int)__byte_perm(t1.z, 0u, 0x4441);
             const bool live = v < S && G > 0;
             const int vv = min(v, S);
@@ -607,16 +760,44 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
             // cells that emit nothing (padding slots, skipped sites, past the tile) compute along and store into a scratch cell
             const uint32_t cell_g = live ? s_wg + (uint32_t)(gpos - g_lo) * 4u : s_wg + TILE_G_TRASH * 4u;
             const uint32_t cell_r = live ? s_wr + (uint32_t)(rpos - r_lo) * 4u : s_wr + TILE_R_TRASH * 4u;
-            const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
+            const uint4 slot = lds128(s_st + (uint32_t)sl * 64u);
             bulk_wait_read(); // this warp's previous copies (issued by lane 0) must have finished reading the slice
             __syncwarp();
             const int c0 = (int)__byte_perm(c4, 0u, 0x4440), c1 = (int)__byte_perm(c4, 0u, 0x4441);
             const int c2 = (int)__byte_perm(c4, 0u, 0x4442), c3 = (int)__byte_perm(c4, 0u, 0x4443);
             const int n = (int)__vsadu4(c4, 0u);
-            float q[15];
-            m1f_scores_noclamp(n, c0, c1, c2, c3, p.m1_bsum, p.m1_het, q);
-            if (__all_sync(0xffffffffu, !live || (t1.z >> 16))) tile_emit_cell<true>(q, slot, cell_g, has_gl, has_pl);
-            else tile_emit_cell<false>(q, slot, cell_g, has_gl, has_pl);
+            const uint32_t seen4 = __vcmpne4(c4, 0u);
+            if (PURE && __all_sync(0xffffffffu, !live || __popc(seen4) <= 8)) {
+                // every cell of the chunk is pure (or empty): GL / PL by class from the depth table, written slot by slot
+                const int x = ((__ffs(seen4 | 0x80000000u) - 1) >> 3) & 3;
+                M1Pure tv;
+                {
+                    const uint4 t = __ldg(pure_tab + n);
+                    tv.gl1 = __uint_as_float(t.x); tv.gl0 = __uint_as_float(t.y); tv.pl1 = (int32_t)t.z; tv.pl0 = (int32_t)t.w;
+                }
+                const uint32_t cm = lds32(s_st + (uint32_t)sl * 64u + 48u + 4u * (uint32_t)x);
+                const int gmax = __reduce_max_sync(0xffffffffu, live ? G : 0);
+                const uint32_t dstb = cell_g;
+#pragma unroll
+                for (int g = 0; g < 15; ++g) {
+                    if (g >= gmax) break;
+                    const bool one = (cm >> g) & 1u;
+                    if (g < G && live) {
+                        if (has_gl) sts32(dstb + 4u * g, __float_as_uint(one ? tv.gl1 : tv.gl0));
+                        if (has_pl) sts32(dstb + 4u * g + TILE_WST_G * 4, (uint32_t)(one ? tv.pl1 : tv.pl0));
+                    }
+                }
+                if (live) { // the slot of xx
+                    const uint32_t hs = dstb + ((cm >> 16) & 0xFu) * 4u;
+                    if (has_gl) sts32(hs, 0u);
+                    if (has_pl) sts32(hs + TILE_WST_G * 4, 0u);
+                }
+            } else {
+                float q[15];
+                m1f_scores_noclamp(n, c0, c1, c2, c3, p.m1_bsum, p.m1_het, q);
+                if (__all_sync(0xffffffffu, !live || (t1.z >> 16))) tile_emit_cell<true>(q, slot, cell_g, has_gl, has_pl);
+                else tile_emit_cell<false>(q, slot, cell_g, has_gl, has_pl);
+            }
             if (has_ad) { // AD in allele order (vcfgl.cpp:806-831): byte permute, selector 4 reads 0
                 sts32(cell_r, __byte_perm(c4, 0u, t2.x));
                 if (A > 1) sts32(cell_r + 4, __byte_perm(c4, 0u, t2.x >> 16));
@@ -674,19 +855,25 @@ static size_t tile_dyn_smem(bool big)
            (big ? 0 : (size_t)TILE_CELLS * 4);
 }
 
-template <bool GEN, bool BIG, bool AUX>
-static void launch_tile_t(const DevParams& p, cudaStream_t st, int n_sms)
+template <bool GEN, bool BIG, bool AUX, bool PURE>
+static void launch_tile_p(const DevParams& p, cudaStream_t st, int n_sms)
 {
-    const size_t dyn = tile_dyn_smem(BIG) + (AUX ? TILE_MAX_SITES * sizeof(TAux) : 0);
-    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const size_t dyn = tile_dyn_smem(BIG) + (AUX ? TILE_MAX_SITES * sizeof(TAux) + (BIG ? 0 : (TILE_CELLS / 32) * 32) : 0);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX, PURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX, PURE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN, BIG, AUX>, TILE_BLOCK, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN, BIG, AUX, PURE>, TILE_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
     int grid = n_sms * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    k_tile_m1f<GEN, BIG, AUX><<<grid, TILE_BLOCK, dyn, st>>>(p);
+    k_tile_m1f<GEN, BIG, AUX, PURE><<<grid, TILE_BLOCK, dyn, st>>>(p);
+}
+template <bool GEN, bool BIG, bool AUX>
+static void launch_tile_t(const DevParams& p, cudaStream_t st, int n_sms)
+{
+    if (p.m1_pure != nullptr) launch_tile_p<GEN, BIG, AUX, true>(p, st, n_sms);
+    else launch_tile_p<GEN, BIG, AUX, false>(p, st, n_sms);
 }
 
 // aux: QS / I16 / INFO ADF, ADR wanted (tile_m1f_aux_tags)
@@ -778,7 +965,7 @@ int tile_m1f_sites_per_tile(int S)
 size_t tile_m1f_scratch_words(int S, int n_sms)
 {
     const int S4 = (S + 3) & ~3;
-    return S4 > TILE_CELLS ? (size_t)S4 * TILE_SCRATCH_CTAS_PER_SM * n_sms : 0;
+    return S4 > TILE_CELLS ? tile_m1f_row_words(S4) * TILE_SCRATCH_CTAS_PER_SM * n_sms : 0;
 }
 
 } // namespace vgl

@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
             const int sl = (int)__umulhi(iv, inv_s4), v = (int)iv - sl * S4;
             c4 = BIG ? cnt_g[iv] : lds32(s_cnt + iv * 4u);
             n = (int)__vsadu4(c4, 0u);
-            const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
+            const uint4 slot = lds128(s_st + (uint32_t)sl * 64u);
             pv = (nonzero_bytes(~slot.x) | (nonzero_bytes(~slot.y) << 4) | (nonzero_bytes(~slot.z) << 8) | (nonzero_bytes(~slot.w) << 12)) & 0x7FFFu;
             const uint32_t gt = gt_t[(uint32_t)((int)iv - sl * PAD)];
             rd.g0 = gt & 0x3;
@@ -789,8 +789,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
             int sl = (int)__umulhi((uint32_t)iv, inv_s4);
             int v = iv - sl * S4;
             if (sl >= nsl) { sl = nsl - 1; v = S4; }
-            const uint4 t1 = lds128(s_st + (uint32_t)sl * 48u + 16u); // g_rel, r_rel, AG, sel4
-            const uint4 t2 = lds128(s_st + (uint32_t)sl * 48u + 32u); // sel01, sel23, g_end, r_end
+            const uint4 t1 = lds128(s_st + (uint32_t)sl * 64u + 16u); // g_rel, r_rel, AG, sel4
+            const uint4 t2 = lds128(s_st + (uint32_t)sl * 64u + 32u); // sel01, sel23, g_end, r_end
             const int A = (int)(t1.z & 0xFF), G = (int)__byte_perm(t1.z, 0u, 0x4441);
             const bool live = v < S && G > 0;
             const int vv = min(v, S);
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __gri
             const int r_lo = __shfl_sync(0xffffffffu, rpos, 0), r_hi = __shfl_sync(0xffffffffu, rend, 31);
             const uint32_t cell_g = live ? s_wg + (uint32_t)(gpos - g_lo) * 4u : s_wg + TILE_G_TRASH * 4u;
             const uint32_t cell_r = live ? s_wr + (uint32_t)(rpos - r_lo) * 4u : s_wr + TILE_R_TRASH * 4u;
-            const uint4 slot = lds128(s_st + (uint32_t)sl * 48u);
+            const uint4 slot = lds128(s_st + (uint32_t)sl * 64u);
             const int n = (int)__vsadu4(c4, 0u);
             float gl[15];
             if (is2 || is15) {

@@ -36,6 +36,12 @@ struct __align__(16) CellTail {
     uint32_t _pad;
 };
 
+// GL / PL of the two non-trivial classes of a pure cell (tile_m1f.cu): base pairs that hold the cell's base once / not at all
+struct __align__(16) M1Pure {
+    float gl1, gl0;
+    int32_t pl1, pl0;
+};
+
 struct DevParams {
     // geometry
     int32_t S, n_sites;
@@ -95,6 +101,7 @@ struct DevParams {
     const unsigned long long* pois_alias; // [256] Walker alias table of the depth distribution: t56 << 8 | alias
     const uint32_t* err_cdf;              // [256][4] P(E <= j | n reads) * 2^32, j = 0..3
     uint32_t* cnt_scratch;                // per-CTA rows of packed counts when a site does not fit shared memory
+    const void* m1_pure;                  // [256] M1Pure: GL / PL of a cell whose reads all show one base, by depth; null: not usable
     // model-2 tile kernel (tile_m2.cu), --error-qs 2: alias table + info words of the per-read (quality score, error) classes
     const uint32_t* qcls;                 // [512], tables.h qs_class_table()
     const double* m2_tab;                 // [m2_nq][M2_TAB_DOUBLES] constants per quality score in use, tables.h m2_const_table(); null: none
@@ -148,6 +155,7 @@ void launch_emit(const DevParams& p, cudaStream_t st);
 int run_selftest(unsigned long long* n_bad, unsigned int* first_bad);
 void launch_fused_m1f(const DevParams& p, cudaStream_t st, int n_sms);
 void launch_tile_m1f(const DevParams& p, cudaStream_t st, int n_sms, bool aux);
+int build_m1f_pure_table(const double* d_bsum, const double* d_het, void* out, cudaStream_t st);
 void launch_tile_m1f_draws(const DevParams& p, cudaStream_t st, int pass, int32_t* depths, const int64_t* off, uint8_t* bases, uint8_t* strands,
                            uint8_t* tails);
 uint32_t tile_m1f_aux_tags();
