@@ -513,7 +513,10 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
     const uint32_t inv_s4 = (uint32_t)(((1ull << 32) + S4 - 1) / S4);
     const bool explode = p.do_unobserved >= 3;
     const bool add_unobs = p.do_unobserved == 1 || p.do_unobserved == 2 || p.do_unobserved == 4 || p.do_unobserved == 5;
-    const bool has_gl = GEN ? p.gl != nullptr : true, has_pl = GEN ? p.pl != nullptr : true, has_ad = GEN ? p.ad != nullptr : true;
+    // GEN: the plane tests are pinned in a register (the compiler would otherwise re-read the kernel parameters at every store)
+    uint32_t plane_flags = (p.gl != nullptr ? 1u : 0u) | (p.pl != nullptr ? 2u : 0u) | (p.ad != nullptr ? 4u : 0u);
+    asm volatile("mov.u32 %0, %0;" : "+r"(plane_flags));
+    const bool has_gl = GEN ? (plane_flags & 1u) != 0u : true, has_pl = GEN ? (plane_flags & 2u) != 0u : true, has_ad = GEN ? (plane_flags & 4u) != 0u : true;
     const bool want_tail = AUX && (p.tag_mask & VGL_TAG_I16) != 0;
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4; // this warp's GL slice; PL at +TILE_WST_G words, AD at +2*TILE_WST_G
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
