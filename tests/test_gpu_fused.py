@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from test_gpu_native import ALPHA, PAIRS, STATS, chi2_two_sample, u32
+from test_gpu_native import ALPHA, PAIRS, STATS, chi2_two_sample, ks_two_sample, u32
 from scipy import stats
 from vcfgl_b200 import args as vargs
 from vcfgl_b200 import capi, synth
@@ -118,55 +118,71 @@ def test_fused_tags_match_oracle_on_own_counts(name):
             assert np.array_equal(u32(d["gl"]), u32(e["gl"])) and np.array_equal(d["fmt_ad"], e["fmt_ad"])
 
 
-@pytest.mark.parametrize("name", ["gl1_d10", "gl1_d30"])
-def test_count_sampler_distributions_match_reference(name):
+@pytest.mark.parametrize("name,no_tile,kernels", [("gl1_d10", False, "k_fused_m1f"), ("gl1_d30", True, "k_fused_m1f"),
+                                                  ("gl1_d30", False, "k_tile_m1f"), ("gl1_df", False, "k_fused_m1f")])
+def test_count_sampler_distributions_match_reference(name, no_tile, kernels, monkeypatch):
+    """the count-level sampler against the reference's captures (>= 1e6 cells each), from the AD / ADF planes alone (the
+    fused kernel has no per-read draws to export); the kernel set is asserted"""
     st = STATS[name]
-    a = vargs.parse_args(st["argv"])
+    a = vargs.parse_args(st["argv"], depths=st.get("depths"))
     S, n_sites = st["S"], st["n_sites"]
-    hap = synth.sfs_genotypes(n_sites, S, st["gt_seed"])
-    gt = synth.pack_gt(hap)
-    sites, _ = run(a, S, gt, 0, n_sites)
-    pvals = {}
-    dp = np.concatenate([d["fmt_dp"] for d in sites])
-    depth_hist = np.bincount(np.minimum(dp, 199), minlength=200)
-    pvals["depth"] = chi2_two_sample(depth_hist, st["depth_hist"])
-    pvals["depth_vs_poisson"] = chi2_two_sample(depth_hist, stats.poisson.pmf(np.arange(200), a.depth) * len(dp) * 1e3)
+    if no_tile:
+        monkeypatch.setenv("VGL_NO_TILE", "1")
+    hap_all = synth.sfs_genotypes(n_sites, S, st["gt_seed"])
+    batch = 2000
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=batch, n_slots=1, sampler=2))
+    assert ctx.native_kernels() == kernels, ctx.native_kernels()
+    depth_hist = np.zeros(200, np.int64)
+    depth_by_sample = np.zeros((S, 64), np.int64)
     conf = np.zeros((4, 4), np.int64)
     het_reads = np.zeros(2, np.int64)
     strand = np.zeros(2, np.int64)
     disc = {"hom": [0, 0], "het": [0, 0]}
-    for i, d in enumerate(sites):
-        if d["skip_code"] != 0 or d["info_dp"] == 0:
-            continue
-        A, G = d["n_alleles"], d["n_genotypes"]
-        a2b = d["alleles2acgt"]
-        ad = d["fmt_ad"].reshape(S, A)
-        acgt = np.zeros((S, 4), np.int64)
-        for al in range(A):
-            if 0 <= a2b[al] < 4:
-                acgt[:, a2b[al]] = ad[:, al]
-        g0, g1 = hap[i, 0::2], hap[i, 1::2]
-        hom = g0 == g1
-        for t in range(4):
-            conf[t] += acgt[hom & (g0 == t)].sum(axis=0)
-        het = ~hom
-        het_reads[0] += acgt[het, g0[het]].sum()
-        het_reads[1] += acgt[het, g1[het]].sum()
-        if d.get("fmt_adf") is not None:
-            f = int(d["fmt_adf"].sum())
-            strand += [f, int(ad.sum()) - f]
-        gl = d["gl"].reshape(S, G)
-        mx = gl.max(axis=1)
-        for s in np.flatnonzero(d["fmt_dp"] > 0):
-            best = np.flatnonzero(gl[s] == mx[s])
-            call = None
-            if len(best) == 1:
-                a1, a2 = PAIRS[best[0]]
-                call = tuple(sorted((int(a2b[a1]), int(a2b[a2]))))
-            truth = tuple(sorted((int(g0[s]), int(g1[s]))))
-            k = "hom" if truth[0] == truth[1] else "het"
-            disc[k][0] += 1
-            disc[k][1] += int(call != truth)
+    for lo in range(0, n_sites, batch):
+        nb = min(batch, n_sites - lo)
+        hap = hap_all[lo:lo + nb]
+        ctx.input_buffer(0)[:nb] = synth.pack_gt(hap)
+        ctx.submit(0, lo, nb)
+        b = ctx.wait(0)
+        assert b.status == 0
+        depth_hist += np.bincount(np.minimum(b.dp[:nb * S], 199), minlength=200)
+        np.add.at(depth_by_sample, (np.tile(np.arange(S), nb), np.minimum(b.dp[:nb * S], 63)), 1)
+        dd = ctx.discordance(0)
+        for k in ("hom", "het"):
+            disc[k][0] += dd[k][0]
+            disc[k][1] += dd[k][1]
+        for i in range(nb):
+            d = b.site(i)
+            if d["skip_code"] != 0 or d["info_dp"] == 0:
+                continue
+            A = d["n_alleles"]
+            a2b = d["alleles2acgt"]
+            ad = d["fmt_ad"].reshape(S, A)
+            acgt = np.zeros((S, 4), np.int64)
+            for al in range(A):
+                if 0 <= a2b[al] < 4:
+                    acgt[:, a2b[al]] = ad[:, al]
+            g0, g1 = hap[i, 0::2], hap[i, 1::2]
+            hom = g0 == g1
+            for t in range(4):
+                conf[t] += acgt[hom & (g0 == t)].sum(axis=0)
+            het = ~hom
+            het_reads[0] += acgt[het, g0[het]].sum()
+            het_reads[1] += acgt[het, g1[het]].sum()
+            if d.get("fmt_adf") is not None:
+                f = int(d["fmt_adf"].sum())
+                strand += [f, int(ad.sum()) - f]
+    ctx.close()
+    pvals = {}
+    pvals["depth"] = chi2_two_sample(depth_hist, st["depth_hist"])
+    pvals["depth_ks"] = ks_two_sample(depth_hist, st["depth_hist"])
+    if st.get("depths") is None:
+        pvals["depth_vs_poisson"] = chi2_two_sample(depth_hist, stats.poisson.pmf(np.arange(200), a.depth) * depth_hist.sum() * 1e3)
+    else:   # --depths-file: each group of samples that share a mean against the reference's same group
+        ref_by, means = np.array(st["depth_by_sample"]), np.array(st["depths"])
+        for m in sorted(set(means)):
+            pvals["depth_mean_%g" % m] = chi2_two_sample(depth_by_sample[means == m].sum(axis=0), ref_by[means == m].sum(axis=0))
+            pvals["depth_ks_mean_%g" % m] = ks_two_sample(depth_by_sample[means == m].sum(axis=0), ref_by[means == m].sum(axis=0))
     ref_conf = np.array(st["confusion"])
     for t in range(4):
         if ref_conf[t].sum() > 0:
@@ -182,4 +198,4 @@ def test_count_sampler_distributions_match_reference(name):
             z = (x1 / n1 - x2 / n2) / np.sqrt(pp * (1 - pp) * (1 / n1 + 1 / n2))
             pvals["discordance_" + k] = 2 * stats.norm.sf(abs(z))
     bad = {k: v for k, v in pvals.items() if not (v >= ALPHA)}
-    assert not bad, (name, bad, pvals)
+    assert not bad, (name, kernels, bad, pvals)

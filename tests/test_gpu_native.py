@@ -4,9 +4,12 @@
     the replay path, must reproduce the native run's tags bit-exactly -- this checks the whole native
     pipeline at sizes where no reference capture exists, and that results do not depend on batch size.
 (2) statistical parity with the reference (tests/golden/stats.json, made by
-    tools/make_stats_golden.py from the instrumented reference): two-sample chi-square on the
-    per-cell depth histogram, the true-base -> read-base matrix, the strand split and the per-read
-    qs histogram; two-proportion z-test on genotype-call discordance; alpha = 0.001 each.
+    tools/make_stats_golden.py from the instrumented reference, >= 1e6 cells per fixture): two-sample
+    chi-square on the per-cell depth histogram (per group of samples with --depths-file), the true-base ->
+    read-base matrix, the haplotype pick, the strand split, the tail distances and the side of a site's tail
+    mass, the per-read qs histogram and the mis-called reads per site (--error-qs 1); two-sample
+    Kolmogorov-Smirnov on depth, quality score and tail distance; two-proportion z-test on genotype-call
+    discordance; alpha = 0.001 each.  Every fixture runs on each native kernel set that takes its flags.
 """
 import json
 import os
@@ -139,82 +142,145 @@ def chi2_two_sample(a, b, min_expected=5):
     return stats.chi2_contingency(np.stack([a, b]))[1]
 
 
-@pytest.mark.parametrize("name", sorted(STATS))
-def test_native_distributions_match_reference(name):
-    distributions(name, 1)
+def ks_two_sample(h1, h2):
+    """two-sample Kolmogorov-Smirnov test from two histograms over the same ordered support (asymptotic p-value; for a
+    discrete law the test is conservative)"""
+    h1, h2 = np.asarray(h1, float).ravel(), np.asarray(h2, float).ravel()
+    n1, n2 = h1.sum(), h2.sum()
+    d = np.abs(np.cumsum(h1) / n1 - np.cumsum(h2) / n2).max()
+    return float(stats.kstwobign.sf(d * np.sqrt(n1 * n2 / (n1 + n2))))
 
 
-def distributions(name, sampler, kernels=None, strand=True):
+# every fixture runs on each native kernel set that takes its flags; the kernel set is asserted, so that a dispatch change
+# in vgl_create cannot silently move a test to another kernel.  (fixture, sampler, kernels, drop the strand flags?)
+PER_READ = "k_sim+k_site+k_scan+k_emit"
+DIST_RUNS = [
+    ("gl1_d10", 1, PER_READ, False),
+    ("gl1_d10", 0, "k_tile_m1f", True),            # without FORMAT/ADF the headline kernel takes it
+    ("gl1_d30", 1, PER_READ, False),
+    ("gl1_d30", 0, "k_tile_m1f", False),
+    ("gl1_aux", 1, PER_READ, False),
+    ("gl1_aux", 0, "k_tile_m1f", False),           # the AUX variant (QS / I16 / INFO ADF, ADR)
+    ("gl1_df", 1, PER_READ, False),                # --depths-file: per-sample Poisson means (k_fused_m1f: tests/test_gpu_fused.py)
+    ("gl2_d2_e02", 1, PER_READ, False),
+    ("gl2_d2_e02", 0, "k_tile_m2", True),
+    ("gl2_eq2", 1, PER_READ, False),
+    ("gl2_eq2", 0, "k_tile_m2", False),
+    ("gl2_eq2_bins", 1, PER_READ, False),
+    ("gl2_eq2_bins", 0, "k_tile_m2", False),
+    ("gl2_eq1", 1, PER_READ, False),
+    ("gl2_eq1", 0, "k_tile_m2", False),
+]
+
+
+@pytest.mark.parametrize("name,sampler,kernels,drop_strand", DIST_RUNS, ids=["%s-%s" % (r[0], r[2].split("+")[0]) for r in DIST_RUNS])
+def test_native_distributions_match_reference(name, sampler, kernels, drop_strand):
+    distributions(name, sampler, kernels=kernels, strand=not drop_strand)
+
+
+def test_fixed_depth_has_the_reference_read_laws():
+    """VGL_DEPTH_FIXED (north_star: "Poisson/fixed"; the reference CLI has no such option): every cell has exactly the
+    depth, the read-level laws (mis-calls, haplotype pick) are those of the reference's gl1_d10 capture"""
+    distributions("gl1_d10", 0, kernels="k_tile_m1f", strand=False, fixed_depth=True)
+
+
+def distributions(name, sampler, kernels=None, strand=True, fixed_depth=False, batch=2000):
     st = STATS[name]
     argv = list(st["argv"])
     if not strand:   # kernels without strand tags: drop the ADF/ADR flags of the fixture's command line
-        for flag in ("-addFormatADF", "-addFormatADR", "-addInfoADF", "-addInfoADR"):
+        for flag in ("-addFormatADF", "-addFormatADR"):
             while flag in argv:
                 i = argv.index(flag)
                 del argv[i:i + 2]
-    a = vargs.parse_args(argv, qs_bins=st.get("qs_bins"))
+    a = vargs.parse_args(argv, qs_bins=st.get("qs_bins"), depths=st.get("depths"))
     S, n_sites = st["S"], st["n_sites"]
-    hap = synth.sfs_genotypes(n_sites, S, st["gt_seed"])
-    gt = synth.pack_gt(hap)
-    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=n_sites, n_slots=1, sampler=sampler))
+    hap_all = synth.sfs_genotypes(n_sites, S, st["gt_seed"])
+    batch = min(batch * 100 // S, n_sites)
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=batch, n_slots=1, sampler=sampler, fixed_depth=fixed_depth))
     if kernels:
-        assert ctx.native_kernels() == kernels, ctx.native_kernels()
-    ctx.input_buffer(0)[:n_sites] = gt
-    ctx.submit(0, 0, n_sites)
-    b = ctx.wait(0)
-    rp = ctx.native_draws(0, 0, n_sites)
-    pvals = {}
-    # depth
-    depth_hist = np.bincount(np.minimum(b.dp, 199), minlength=200)
-    pvals["depth"] = chi2_two_sample(depth_hist, st["depth_hist"])
-    lam = a.depth
-    expected = stats.poisson.pmf(np.arange(200), lam) * len(b.dp)
-    pvals["depth_vs_poisson"] = chi2_two_sample(depth_hist, expected * 1e3)  # vs (almost) exact expectation
-    # read-level draws
-    cell_of_read = np.repeat(np.arange(n_sites * S), np.diff(rp["read_offsets"]))
-    g0 = hap.reshape(-1, 2)[cell_of_read, 0]
-    g1 = hap.reshape(-1, 2)[cell_of_read, 1]
-    hom = g0 == g1
+        assert ctx.native_kernels() == kernels, (ctx.native_kernels(), kernels)
+    depth_hist = np.zeros(200, np.int64)
+    depth_by_sample = np.zeros((S, 64), np.int64)
     conf = np.zeros((4, 4), np.int64)
-    np.add.at(conf, (g0[hom], rp["bases"][hom]), 1)
+    het_reads = np.zeros(2, np.int64)
+    strand_n = np.zeros(2, np.int64)
+    qs_hist = np.zeros(256, np.int64)
+    tail_hist = np.zeros(32, np.int64)
+    tail_side = np.zeros(2, np.int64)
+    site_err_hist = np.zeros(64, np.int64)
+    disc = {"hom": [0, 0], "het": [0, 0]}
+    for lo in range(0, n_sites, batch):
+        nb = min(batch, n_sites - lo)
+        hap = hap_all[lo:lo + nb]
+        ctx.input_buffer(0)[:nb] = synth.pack_gt(hap)
+        ctx.submit(0, lo, nb)
+        b = ctx.wait(0)
+        dpl = b.dp[:nb * S].reshape(nb, S)
+        depth_hist += np.bincount(np.minimum(dpl.ravel(), 199), minlength=200)
+        np.add.at(depth_by_sample, (np.tile(np.arange(S), nb), np.minimum(dpl.ravel(), 63)), 1)
+        dd = ctx.discordance(0)     # on-device summary (tests/test_gpu_discordance.py pins it to the definition)
+        for k in ("hom", "het"):
+            disc[k][0] += dd[k][0]
+            disc[k][1] += dd[k][1]
+        sites = b.sites[:nb]
+        if a.add_i16:
+            keep = (sites["skip_code"] == 0) & (sites["info_dp"] > 0)
+            tail_side += [int((sites["i16"][keep][:, 12] > 0).sum()), int((sites["i16"][keep][:, 14] > 0).sum())]
+        rp = ctx.native_draws(0, lo, nb)
+        assert np.array_equal(rp["depths"], dpl.ravel())
+        cell_of_read = np.repeat(np.arange(nb * S), np.diff(rp["read_offsets"]))
+        g0 = hap.reshape(-1, 2)[cell_of_read, 0]
+        g1 = hap.reshape(-1, 2)[cell_of_read, 1]
+        hom = g0 == g1
+        np.add.at(conf, (g0[hom], rp["bases"][hom]), 1)
+        err_site = np.bincount(cell_of_read[hom] // S, weights=(rp["bases"][hom] != g0[hom]), minlength=nb).astype(np.int64)
+        site_err_hist += np.bincount(np.minimum(err_site, 63), minlength=64)
+        het = ~hom
+        het_reads += [(rp["bases"][het] == g0[het]).sum(), (rp["bases"][het] == g1[het]).sum()]
+        if strand:
+            strand_n += np.bincount(rp["strands"], minlength=2)[:2]
+        if a.error_qs == 2:
+            qs_hist += np.bincount(rp["qs"], minlength=256)
+        if a.add_i16:
+            tail_hist += np.bincount(np.minimum(rp["tail_dists"], 31), minlength=32)
+    ctx.close()
+    pvals = {}
+    if fixed_depth:
+        assert depth_hist[int(a.depth)] == depth_hist.sum(), "fixed depth: every cell must hold exactly --depth reads"
+    else:
+        pvals["depth"] = chi2_two_sample(depth_hist, st["depth_hist"])
+        pvals["depth_ks"] = ks_two_sample(depth_hist, st["depth_hist"])
+        if st.get("depths") is None:
+            pvals["depth_vs_poisson"] = chi2_two_sample(depth_hist, stats.poisson.pmf(np.arange(200), a.depth) * depth_hist.sum() * 1e3)
+        else:   # per-sample means: each group of samples that share a mean against the reference's same group
+            ref_by = np.array(st["depth_by_sample"])
+            means = np.array(st["depths"])
+            for m in sorted(set(means)):
+                pvals["depth_mean_%g" % m] = chi2_two_sample(depth_by_sample[means == m].sum(axis=0), ref_by[means == m].sum(axis=0))
+                pvals["depth_ks_mean_%g" % m] = ks_two_sample(depth_by_sample[means == m].sum(axis=0), ref_by[means == m].sum(axis=0))
     ref_conf = np.array(st["confusion"])
     for t in range(4):
         if ref_conf[t].sum() > 0:
             pvals["confusion_true%d" % t] = chi2_two_sample(conf[t], ref_conf[t])
-    het = ~hom
-    pvals["het_hap_pick"] = chi2_two_sample([(rp["bases"][het] == g0[het]).sum(), (rp["bases"][het] == g1[het]).sum()],
-                                            st["het_reads"])
-    if strand and sum(st["strand"][1:]) > 0:
-        pvals["strand"] = chi2_two_sample(np.bincount(rp["strands"], minlength=2), st["strand"])
+    pvals["het_hap_pick"] = chi2_two_sample(het_reads, st["het_reads"])
+    if a.error_qs == 1 and not fixed_depth:   # the per-site beta draw shows as over-dispersion of the mis-called reads per site
+        pvals["site_errors"] = chi2_two_sample(site_err_hist, st["site_err_hist"])
+    if strand and sum(st["strand"][1:]) > 0 and strand_n.sum() > 0:
+        pvals["strand"] = chi2_two_sample(strand_n, st["strand"])
     if a.error_qs == 2:
-        pvals["qs"] = chi2_two_sample(np.bincount(rp["qs"], minlength=256), st["qs_hist"])
-    # genotype-call discordance (argmax GL vs truth), misc/gtDiscordance.cpp semantics
-    disc = {"hom": [0, 0], "het": [0, 0]}
-    for i in range(n_sites):
-        d = b.site(i)
-        if d["skip_code"] != 0 or d["info_dp"] == 0:
-            continue
-        G = d["n_genotypes"]
-        gl = d["gl"].reshape(S, G)
-        a2b = d["alleles2acgt"]
-        mx = gl.max(axis=1)
-        for s in np.flatnonzero(d["fmt_dp"] > 0):
-            best = np.flatnonzero(gl[s] == mx[s])
-            call = None
-            if len(best) == 1:
-                a1, a2 = PAIRS[best[0]]
-                call = tuple(sorted((int(a2b[a1]), int(a2b[a2]))))
-            truth = tuple(sorted((int(hap[i, 2 * s]), int(hap[i, 2 * s + 1]))))
-            k = "hom" if truth[0] == truth[1] else "het"
-            disc[k][0] += 1
-            disc[k][1] += int(call != truth)
-    for k in ("hom", "het"):
-        n1, x1 = disc[k]
-        n2, x2 = st["discordance"][k]
-        pp = (x1 + x2) / (n1 + n2)
-        if 0 < pp < 1:
-            z = (x1 / n1 - x2 / n2) / np.sqrt(pp * (1 - pp) * (1 / n1 + 1 / n2))
-            pvals["discordance_" + k] = 2 * stats.norm.sf(abs(z))
+        pvals["qs"] = chi2_two_sample(qs_hist, st["qs_hist"])
+        pvals["qs_ks"] = ks_two_sample(qs_hist, st["qs_hist"])
+    if a.add_i16:
+        pvals["tail"] = chi2_two_sample(tail_hist, st["tail_hist"])
+        pvals["tail_ks"] = ks_two_sample(tail_hist, st["tail_hist"])
+        pvals["tail_side"] = chi2_two_sample(tail_side, st["tail_side"])   # the stale r_base of vcfgl.cpp:657
+    if not fixed_depth:
+        for k in ("hom", "het"):   # genotype-call discordance (argmax GL vs truth), misc/gtDiscordance.cpp strata
+            n1, x1 = disc[k]
+            n2, x2 = st["discordance"][k]
+            pp = (x1 + x2) / (n1 + n2)
+            if 0 < pp < 1:
+                z = (x1 / n1 - x2 / n2) / np.sqrt(pp * (1 - pp) * (1 / n1 + 1 / n2))
+                pvals["discordance_" + k] = 2 * stats.norm.sf(abs(z))
     bad = {k: v for k, v in pvals.items() if not (v >= ALPHA)}
-    assert not bad, (name, bad, pvals)
-    ctx.close()
+    assert not bad, (name, kernels, bad, pvals)

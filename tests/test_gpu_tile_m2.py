@@ -4,12 +4,12 @@ GL model 2 depends on the ORDER of a cell's reads, so the kernel's own read sequ
 (vgl_native_draws) and
 (1) the CPU oracle and the replay kernels (pinned bit-exactly to the reference's captures) re-derive every tag from
     that sequence -> bit-exact; results do not depend on batch boundaries;
-(2) the sampler has the reference's distributions (same fixtures and tests as the per-read sampler): depth,
-    true-base -> read-base matrix, haplotype pick, per-read quality scores, genotype-call discordance.
+(2) the sampler has the reference's distributions: tests/test_gpu_native.py runs every gl2 fixture on k_tile_m2 (depth,
+    true-base -> read-base matrix, haplotype pick, per-read quality scores, per-site error counts, genotype-call discordance).
 """
 import pytest
 
-from test_gpu_native import STATS, distributions, self_replay
+from test_gpu_native import self_replay
 
 pytestmark = pytest.mark.gpu
 
@@ -40,8 +40,3 @@ CASES = {
 def test_tile_m2_tags_match_oracle_on_own_reads(name):
     argv, S, n_sites, bins = CASES[name]
     self_replay(name.replace("deep", "d70"), argv, 0, S, n_sites, kernels="k_tile_m2", qs_bins=bins)
-
-
-@pytest.mark.parametrize("name", sorted(k for k in STATS if k.startswith("gl2")))
-def test_tile_m2_distributions_match_reference(name):
-    distributions(name, 0, kernels="k_tile_m2", strand=False)

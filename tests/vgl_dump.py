@@ -59,13 +59,17 @@ class _R:
 
 
 def read_dump(path) -> List[SiteDump]:
+    return list(iter_dump(path))
+
+
+def iter_dump(path):
+    """the sites of a capture one at a time (large captures: tools/make_stats_golden.py)"""
     if str(path).endswith(".gz"):
         import gzip
         buf = gzip.open(path, "rb").read()
     else:
-        buf = open(path, "rb").read()
+        buf = np.memmap(path, dtype=np.uint8, mode="r") if __import__("os").path.getsize(path) > 0 else b""
     r = _R(buf)
-    sites = []
     while r.o < len(buf):
         magic = r.s("I")
         assert magic == MAGIC, "bad magic at %d" % r.o
@@ -102,7 +106,6 @@ def read_dump(path) -> List[SiteDump]:
         for bit, name, dt, n in spec:
             if flags & (1 << bit):
                 out[name] = r.a(dt, n)
-        sites.append(SiteDump(ret, pos, rid, S, stale, site_e if has_e else None, nA, nAo, nG, a_un,
-                              a2b, b2a, flags, gts, depths, fmt_dp, info_dp, rs, rb, rst, rq, raq, re,
-                              tails, ems, emn, emc, out))
-    return sites
+        yield SiteDump(ret, pos, rid, S, stale, site_e if has_e else None, nA, nAo, nG, a_un,
+                       a2b, b2a, flags, gts, depths, fmt_dp, info_dp, rs, rb, rst, rq, raq, re,
+                       tails, ems, emn, emc, out)
