@@ -37,8 +37,9 @@
 extern "C" {
 #endif
 
-#define VGL_ABI_VERSION 8 /* 2: VGL_HOST_NARROW; 3: VGL_HOST_BCF; 4: input path (vgl_parser_*, vgl_parse_vcf, vgl_place_rows); 5: vgl_gvcf_merge;
-                          * 6: VGL_DEPTH_INF; 7: vgl_discordance; 8: vgl_parse_bcf */
+#define VGL_ABI_VERSION 9 /* 2: VGL_HOST_NARROW; 3: VGL_HOST_BCF; 4: input path (vgl_parser_*, vgl_parse_vcf, vgl_place_rows); 5: vgl_gvcf_merge;
+                          * 6: VGL_DEPTH_INF; 7: vgl_discordance; 8: vgl_parse_bcf 
+                          * 9: VGL_HOST_BGZF (device-side BGZF compression of the record stream) */
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -86,10 +87,12 @@ enum { VGL_HOST_NONE = 0,    /* nothing but the totals and the status word: resu
        VGL_HOST_I32 = 1,     /* every plane exactly as add_tags() hands it to htslib (int32 / float32, bcf_utils.cpp:426-507) */
        VGL_HOST_NARROW = 2,  /* GL / GP as float32; PL, AD, ADF, ADR and DP narrowed on the device to the width BCF stores them
                               * in anyway (htslib/vcf.c:2249-2294 bcf_enc_vint): 1.8x fewer bytes over PCIe (see vgl_batch_out) */
-       VGL_HOST_BCF = 3 };   /* complete uncompressed BCF records, serialised on the device byte-for-byte as the reference's
+       VGL_HOST_BCF = 3,     /* complete uncompressed BCF records, serialised on the device byte-for-byte as the reference's
                               * add_tags() + bcf_write() would (bcf_utils.cpp:426-507, htslib/vcf.c:1773-1917, 1951-2001): the
                               * host appends vgl_batch_out.bcf to the output stream (see vgl_bcf_site_in).  Not with -doGVCF:
                               * the block merger (bcf_utils.cpp:662-942) consumes arrays. */
+       VGL_HOST_BGZF = 4 };  /* the same records, compressed on the device into BGZF blocks (the reference's default output,
+                              * -O b; htslib/bgzf.c, vcfgl.cpp:1791-1803): vgl_batch_out.bgzf.  Input as for VGL_HOST_BCF. */
 
 /* VGL_HOST_BCF: dictionary ids of the simulator's tags in the OUTPUT header, bcf_hdr_id2int(hdr, BCF_DT_ID, "DP") etc.
  * (FORMAT and INFO tags of the same name share one id).  Only ids of tags enabled in tag_mask are read. */
@@ -221,6 +224,14 @@ typedef struct vgl_batch_out {
     const uint8_t* bcf;
     const int64_t* bcf_off;    /* [n_sites + 1] */
     int64_t bcf_bytes;         /* = bcf_off[n_sites] */
+    /* VGL_HOST_BGZF only: the same record stream compressed on the device into BGZF blocks (htslib/bgzf.c; the reference's
+     * default container, -O b), each block a gzip member holding 32 KiB of the stream.  `bgzf` holds the blocks back to back:
+     * the host appends the bytes to the output file after its own (BGZF-compressed) header and closes the file with the 28-byte
+     * BGZF EOF block.  `bcf` is NULL in this mode; bcf_off / bcf_bytes still describe the UNCOMPRESSED stream (record i starts at
+     * uncompressed offset bcf_off[i], e.g. for an index), bgzf_bytes the compressed one. */
+    const uint8_t* bgzf;
+    int64_t bgzf_bytes;
+    int32_t bgzf_blocks;
 } vgl_batch_out;
 
 /* timing of a slot's last completed submit, CUDA events on the slot's stream (ms) */

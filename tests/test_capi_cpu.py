@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libvgl.so does not export %s" % n
     assert sorted(capi.EXPORTS) == names
-    assert lib.vgl_abi_version() == capi.ABI_VERSION == 8
+    assert lib.vgl_abi_version() == capi.ABI_VERSION == 9
 
 
 def test_struct_layouts_match_header():

@@ -20,8 +20,8 @@ if os.environ.get("VGL_LIB"):      # development only: A/B builds of the same AB
     LIB_PATH = os.environ["VGL_LIB"]
 
 VGL_OK, VGL_EINVAL, VGL_ENOMEM, VGL_ECUDA, VGL_ESTATE, VGL_ERANGE, VGL_ENODEV, VGL_EOVERFLOW, VGL_EMISSING = 0, -1, -2, -3, -4, -5, -6, -7, -8
-ABI_VERSION = 8
-HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF = 0, 1, 2, 3
+ABI_VERSION = 9
+HOST_NONE, HOST_I32, HOST_NARROW, HOST_BCF, HOST_BGZF = 0, 1, 2, 3, 4
 T_H2D, T_SIM, T_SITE, T_SCAN, T_EMIT, T_D2H, T_TOTAL, T_COUNT = range(8)
 SUBMIT_GT_ON_DEVICE = 1
 F32_MISSING_BITS = 0x7F800001
@@ -118,7 +118,8 @@ class VglBatchOut(C.Structure):
                 ("g_elems", C.c_int64), ("r_elems", C.c_int64), ("status", C.c_int32),
                 ("narrow_bits", C.c_int32), ("pl_u8", C.c_void_p), ("dp_n", C.c_void_p), ("ad_n", C.c_void_p),
                 ("adf_n", C.c_void_p), ("adr_n", C.c_void_p),
-                ("bcf", C.c_void_p), ("bcf_off", C.c_void_p), ("bcf_bytes", C.c_int64)]
+                ("bcf", C.c_void_p), ("bcf_off", C.c_void_p), ("bcf_bytes", C.c_int64),
+                ("bgzf", C.c_void_p), ("bgzf_bytes", C.c_int64), ("bgzf_blocks", C.c_int32)]
 
 
 class VglDraws(C.Structure):
@@ -268,10 +269,15 @@ class Batch:
         # HOST_BCF: the serialised records and their byte offsets (views over pinned memory)
         self.bcf = self.bcf_off = None
         self.bcf_bytes = int(out.bcf_bytes)
+        self.bgzf, self.bgzf_bytes, self.bgzf_blocks = None, int(out.bgzf_bytes), int(out.bgzf_blocks)
         if out.bcf_off and host:
             self.bcf_off = np.ctypeslib.as_array(C.cast(out.bcf_off, C.POINTER(C.c_int64)), shape=(out.n_sites + 1,))
-            self.bcf = (np.ctypeslib.as_array(C.cast(out.bcf, C.POINTER(C.c_uint8)), shape=(self.bcf_bytes,))
-                        if self.bcf_bytes > 0 else np.zeros(0, np.uint8))
+            if out.bcf:
+                self.bcf = (np.ctypeslib.as_array(C.cast(out.bcf, C.POINTER(C.c_uint8)), shape=(self.bcf_bytes,))
+                            if self.bcf_bytes > 0 else np.zeros(0, np.uint8))
+            if out.bgzf:      # HOST_BGZF: the record stream as BGZF blocks (views over pinned memory)
+                self.bgzf = (np.ctypeslib.as_array(C.cast(out.bgzf, C.POINTER(C.c_uint8)), shape=(self.bgzf_bytes,))
+                             if self.bgzf_bytes > 0 else np.zeros(0, np.uint8))
         self.pl_u8 = self.dp_n = self.ad_n = self.adf_n = self.adr_n = None
         if self.narrow_bits and host:
             ct, dt = (C.c_uint8, np.uint8) if self.narrow_bits == 8 else (C.c_uint16, np.uint16)

@@ -36,6 +36,7 @@ struct Builder {
     uint32_t* seg_start;
     uint32_t* seg_kind;
     unsigned long long* seg_src;
+    BcfRecPlanes* planes = nullptr; // receives the FORMAT plane layout
     int nseg = 0;
     uint32_t pos = 0;  // bytes of the record so far
     uint32_t nlit = 0;
@@ -166,11 +167,13 @@ __device__ uint32_t bcf_layout(const BcfArgs& a, int i, const vgl_site_out& s, c
         b.int1(key);
         const int ty = int_type(mm.mn[which], mm.mx[which]);
         b.size(nps, ty);
+        if (b.planes && b.planes->n < 7) { b.planes->off[b.planes->n] = b.pos; b.planes->cell[b.planes->n] = (uint16_t)(nps * type_width(ty)); ++b.planes->n; }
         b.ext(ty == BT_INT8 ? SEG_I8 : (ty == BT_INT16 ? SEG_I16 : SEG_VERB), src, (uint32_t)S * nps * type_width(ty));
     };
     auto fmt_float = [&](int32_t key, const float* src, int nps) {
         b.int1(key);
         b.size(nps, BT_FLOAT);
+        if (b.planes && b.planes->n < 7) { b.planes->off[b.planes->n] = b.pos; b.planes->cell[b.planes->n] = (uint16_t)(nps * 4); ++b.planes->n; }
         b.ext(SEG_VERB, src, (uint32_t)S * nps * 4u);
     };
     if (t & VGL_TAG_FMT_DP) fmt_int(a.dict.dp, a.dp + (size_t)i * S, 1, 0);
@@ -329,7 +332,12 @@ __global__ void __launch_bounds__(256) k_bcf_emit(const BcfArgs a)
         s = a.sites[i];
         Builder b;
         b.lit = lit; b.seg_start = seg_start; b.seg_kind = seg_kind; b.seg_src = seg_src;
+        BcfRecPlanes pl;
+        pl.n = 0;
+        for (int k = 0; k < 7; ++k) { pl.off[k] = 0u; pl.cell[k] = 0; }
+        if (a.planes) b.planes = &pl;
         const uint32_t got = bcf_layout(a, i, s, a.minmax[i], b);
+        if (a.planes) a.planes[i] = pl;
         nseg_s = b.nseg;
         seg_start[b.nseg] = got;
     }

@@ -4,6 +4,7 @@
 #include "tables.h"
 #include "vgl_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -32,7 +33,7 @@ struct Slot {
     // host (pinned)
     uint8_t* h_gt = nullptr;
     vgl_site_out* h_sites = nullptr;
-    int64_t* h_totals = nullptr; // [2] + status in [2]
+    int64_t* h_totals = nullptr; // [0..1] plane extents, [2] status, [3] record-stream bytes, [4] BGZF bytes, [5] BGZF blocks
     int32_t* h_dp = nullptr;
     float *h_gl = nullptr, *h_gp = nullptr;
     int32_t *h_pl = nullptr, *h_ad = nullptr, *h_adf = nullptr, *h_adr = nullptr;
@@ -46,6 +47,11 @@ struct Slot {
     BcfSiteMinMax* d_minmax = nullptr;
     uint32_t* d_rec_len = nullptr;
     long long *d_rec_off = nullptr, *h_rec_off = nullptr;
+    // VGL_HOST_BGZF: plane layout of every record, block staging, block sizes / offsets, the compressed stream (device + pinned)
+    BcfRecPlanes* d_planes = nullptr;
+    uint8_t *d_stage = nullptr, *d_bgzf = nullptr, *h_bgzf = nullptr;
+    uint32_t* d_blk_size = nullptr;
+    long long* d_blk_off = nullptr;
     // device
     uint8_t* d_gt = nullptr;
     int32_t* d_dp = nullptr;
@@ -96,6 +102,8 @@ struct vgl_ctx {
     int use_tile_m2 = 0, tile_m2_mode = 0; // tile_m2.cu; mode 0 / 1 / 2 = --error-qs
     int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
     size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
+    int64_t bgzf_max_blocks = 0;           // VGL_HOST_BGZF: blocks a full record stream makes
+    uint32_t* d_crc_pow = nullptr;
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr, *d_qm_cdf = nullptr;
     float *d_m2_pure = nullptr, *d_m2_park = nullptr;
     void* d_m1_pure = nullptr;
@@ -188,7 +196,7 @@ static int validate(const vgl_params* p, std::string& why)
         if (p->tag_mask & ~(uint32_t)(VGL_TAG_GL | VGL_TAG_GP | VGL_TAG_PL)) { why = "--depth inf: only GL, GP and PL exist (no reads: -addFormatDP 0 etc.)"; return VGL_EINVAL; }
         if (p->do_gvcf || (p->rm_invar_sites & 4)) { why = "--depth inf cannot be used with -doGVCF 1 or --rm-invar-sites 4"; return VGL_EINVAL; }
         if (p->error_rate != 0.0) { why = "--depth inf requires --error-rate 0 (io.cpp:847-853)"; return VGL_EINVAL; }
-        if (p->host_output == VGL_HOST_BCF || p->host_output == VGL_HOST_NARROW) { why = "--depth inf: host_output must be VGL_HOST_NONE or VGL_HOST_I32"; return VGL_EINVAL; }
+        if (p->host_output == VGL_HOST_BCF || p->host_output == VGL_HOST_BGZF || p->host_output == VGL_HOST_NARROW) { why = "--depth inf: host_output must be VGL_HOST_NONE or VGL_HOST_I32"; return VGL_EINVAL; }
     }
     if (p->depth_mode == VGL_DEPTH_POISSON_PER_SAMPLE && !p->depth_means) { why = "depth_means missing"; return VGL_EINVAL; }
     if (p->depth_mode != VGL_DEPTH_POISSON_PER_SAMPLE && p->depth_mode != VGL_DEPTH_INF && !(p->depth_mean >= 0.0 && p->depth_mean <= 500.0)) { why = "--depth out of [0,500]"; return VGL_EINVAL; }
@@ -209,9 +217,9 @@ static int validate(const vgl_params* p, std::string& why)
     if (p->i16_mapq < 0 || p->i16_mapq > 60) { why = "--i16-mapq out of [0,60]"; return VGL_EINVAL; }
     if (p->n_qs_bins < 0 || p->n_qs_bins > 255) { why = "bad n_qs_bins"; return VGL_EINVAL; }
     if (p->sampler < 0 || p->sampler > 2) { why = "bad sampler"; return VGL_EINVAL; }
-    if (p->host_output < 0 || p->host_output > 3) { why = "bad host_output"; return VGL_EINVAL; }
-    if (p->host_output == VGL_HOST_BCF && p->do_gvcf) { why = "VGL_HOST_BCF does not take -doGVCF (the block merger consumes arrays)"; return VGL_EINVAL; }
-    if (p->host_output == VGL_HOST_BCF && (p->bcf_blob_bytes_per_site < 0 || p->bcf_blob_bytes_per_site > 65536)) { why = "bad bcf_blob_bytes_per_site"; return VGL_EINVAL; }
+    if (p->host_output < 0 || p->host_output > 4) { why = "bad host_output"; return VGL_EINVAL; }
+    if ((p->host_output == VGL_HOST_BCF || p->host_output == VGL_HOST_BGZF) && p->do_gvcf) { why = "VGL_HOST_BCF does not take -doGVCF (the block merger consumes arrays)"; return VGL_EINVAL; }
+    if ((p->host_output == VGL_HOST_BCF || p->host_output == VGL_HOST_BGZF) && (p->bcf_blob_bytes_per_site < 0 || p->bcf_blob_bytes_per_site > 65536)) { why = "bad bcf_blob_bytes_per_site"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && !(p->gl_model == 1 && p->error_qs != 2)) { why = "count-level sampler needs --gl-model 1 and --error-qs 0|1"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && (p->tag_mask & (VGL_TAG_QS | VGL_TAG_I16))) { why = "count-level sampler does not produce QS / I16 (use VGL_SAMPLER_PER_READ)"; return VGL_EINVAL; }
     return VGL_OK;
@@ -244,6 +252,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         cudaFreeHost(s.h_pl8); cudaFreeHost(s.h_dpn); cudaFreeHost(s.h_adn); cudaFreeHost(s.h_adfn); cudaFreeHost(s.h_adrn);
         cudaFreeHost(s.h_bcf_in); cudaFreeHost(s.h_blob); cudaFreeHost(s.h_bcf); cudaFreeHost(s.h_rec_off);
         cudaFree(s.d_bcf_in); cudaFree(s.d_blob); cudaFree(s.d_bcf); cudaFree(s.d_minmax); cudaFree(s.d_rec_len); cudaFree(s.d_rec_off);
+        cudaFree(s.d_planes); cudaFree(s.d_stage); cudaFree(s.d_bgzf); cudaFreeHost(s.h_bgzf); cudaFree(s.d_blk_size); cudaFree(s.d_blk_off);
         cudaFree(s.d_pl8); cudaFree(s.d_dpn); cudaFree(s.d_adn); cudaFree(s.d_adfn); cudaFree(s.d_adrn);
         cudaFree(s.d_gt); cudaFree(s.d_dp); cudaFree(s.d_cell); cudaFree(s.d_cellq); cudaFree(s.d_celltail);
         cudaFree(s.d_sites); cudaFree(s.d_totals); cudaFree(s.d_pairmap); cudaFree(s.d_tile_state);
@@ -253,7 +262,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park); cudaFree(ctx->d_m1_pure);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park); cudaFree(ctx->d_m1_pure); cudaFree(ctx->d_crc_pow);
     delete ctx;
 }
 
@@ -403,20 +412,20 @@ static int create_impl(vgl_ctx* ctx)
         for (auto& e : s.ev) CK(cudaEventCreate(&e));
         CK(cudaHostAlloc((void**)&s.h_gt, cells, cudaHostAllocDefault));
         CK(cudaHostAlloc((void**)&s.h_sites, B * sizeof(vgl_site_out), cudaHostAllocDefault));
-        CK(cudaHostAlloc((void**)&s.h_totals, 4 * sizeof(int64_t), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&s.h_totals, 8 * sizeof(int64_t), cudaHostAllocDefault));
         CK(cudaMalloc((void**)&s.d_gt, cells));
         CK(cudaMalloc((void**)&s.d_dp, cells * sizeof(int32_t)));
         CK(cudaMalloc((void**)&s.d_cell, cells * sizeof(CellRec)));
         if (ctx->need_cellq) CK(cudaMalloc((void**)&s.d_cellq, cells * sizeof(CellQ)));
         if (ctx->need_tail) CK(cudaMalloc((void**)&s.d_celltail, cells * sizeof(CellTail)));
         CK(cudaMalloc((void**)&s.d_sites, B * sizeof(vgl_site_out)));
-        CK(cudaMalloc((void**)&s.d_totals, 4 * sizeof(int64_t)));
+        CK(cudaMalloc((void**)&s.d_totals, 8 * sizeof(int64_t)));
         CK(cudaMalloc((void**)&s.d_pairmap, B * sizeof(uint64_t)));
         if (ctx->use_fused || ctx->use_tile_m2) {
             CK(cudaMalloc((void**)&s.d_tile_state, (B + 2) * sizeof(unsigned long long)));
             CK(cudaMemset(s.d_tile_state, 0, (B + 2) * sizeof(unsigned long long)));
         }
-        CK(cudaMemset(s.d_totals, 0, 4 * sizeof(int64_t)));
+        CK(cudaMemset(s.d_totals, 0, 8 * sizeof(int64_t)));
         // planes are zeroed once: words the kernels never write (block padding of the general path, tile-end holes) must not
         // hold another allocation's bits when a whole span is narrowed or copied to the host
         auto plane = [&](void** d, size_t bytes) -> cudaError_t {
@@ -442,7 +451,8 @@ static int create_impl(vgl_ctx* ctx)
             if (t & VGL_TAG_FMT_AD) { CK(cudaMalloc(&s.d_adn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adn, ctx->r_cap * w, cudaHostAllocDefault)); }
             if (t & VGL_TAG_FMT_ADF) { CK(cudaMalloc(&s.d_adfn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adfn, ctx->r_cap * w, cudaHostAllocDefault)); }
             if (t & VGL_TAG_FMT_ADR) { CK(cudaMalloc(&s.d_adrn, ctx->r_cap * w)); CK(cudaHostAlloc(&s.h_adrn, ctx->r_cap * w, cudaHostAllocDefault)); }
-        } else if (p.host_output == VGL_HOST_BCF) {
+        } else if (p.host_output == VGL_HOST_BCF || p.host_output == VGL_HOST_BGZF) {
+            const bool bgzf = p.host_output == VGL_HOST_BGZF;
             // worst case per record: every integer tag at the widest type its values can need (PL <= 255 -> int16; depths
             // bounded by 255 reads under the alias-table law -> int16, else int32) + literals + the pass-through bytes
             const size_t wc = alias_ok ? 2 : 4, per_site_blob = p.bcf_blob_bytes_per_site ? (size_t)p.bcf_blob_bytes_per_site : 16;
@@ -452,7 +462,22 @@ static int create_impl(vgl_ctx* ctx)
             ctx->blob_cap = B * per_site_blob;
             CK(cudaHostAlloc((void**)&s.h_bcf_in, B * sizeof(vgl_bcf_site_in), cudaHostAllocDefault));
             CK(cudaHostAlloc((void**)&s.h_blob, ctx->blob_cap, cudaHostAllocDefault));
-            CK(cudaHostAlloc((void**)&s.h_bcf, ctx->bcf_cap, cudaHostAllocDefault));
+            if (!bgzf) CK(cudaHostAlloc((void**)&s.h_bcf, ctx->bcf_cap, cudaHostAllocDefault));
+            else { // the record stream stays on the device; the host receives the compressed blocks
+                ctx->bgzf_max_blocks = bgzf_blocks_for((int64_t)ctx->bcf_cap);
+                const size_t worst = (size_t)ctx->bgzf_max_blocks * BGZF_STRIDE;
+                CK(cudaMalloc((void**)&s.d_planes, B * sizeof(BcfRecPlanes)));
+                CK(cudaMalloc((void**)&s.d_stage, worst));
+                CK(cudaMalloc((void**)&s.d_bgzf, worst));
+                CK(cudaHostAlloc((void**)&s.h_bgzf, worst, cudaHostAllocDefault));
+                CK(cudaMalloc((void**)&s.d_blk_size, (size_t)ctx->bgzf_max_blocks * sizeof(uint32_t)));
+                CK(cudaMalloc((void**)&s.d_blk_off, (size_t)ctx->bgzf_max_blocks * sizeof(long long)));
+                if (!ctx->d_crc_pow) {
+                    std::vector<uint32_t> pw(1024);
+                    bgzf_crc_pow_table(pw.data());
+                    CK(upload(&ctx->d_crc_pow, pw));
+                }
+            }
             CK(cudaHostAlloc((void**)&s.h_rec_off, (B + 1) * sizeof(long long), cudaHostAllocDefault));
             memset(s.h_bcf_in, 0, B * sizeof(vgl_bcf_site_in));
             CK(cudaMalloc((void**)&s.d_bcf_in, B * sizeof(vgl_bcf_site_in)));
@@ -517,7 +542,7 @@ extern "C" int vgl_input_buffer(vgl_ctx* ctx, int slot, uint8_t** gt, int64_t* c
 extern "C" int vgl_bcf_input_buffer(vgl_ctx* ctx, int slot, vgl_bcf_site_in** sites, uint8_t** blob, int64_t* blob_capacity)
 {
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
-    if (ctx->prm.host_output != VGL_HOST_BCF) return fail(ctx, VGL_ESTATE, "vgl_bcf_input_buffer: the context was not created with VGL_HOST_BCF");
+    if (ctx->prm.host_output != VGL_HOST_BCF && ctx->prm.host_output != VGL_HOST_BGZF) return fail(ctx, VGL_ESTATE, "vgl_bcf_input_buffer: the context was not created with VGL_HOST_BCF");
     if (sites) *sites = ctx->slots[slot].h_bcf_in;
     if (blob) *blob = ctx->slots[slot].h_blob;
     if (blob_capacity) *blob_capacity = (int64_t)ctx->blob_cap;
@@ -793,7 +818,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     CK(cudaEventRecord(s.ev[EV_START], st));
     if (!(flags & VGL_SUBMIT_GT_ON_DEVICE)) CK(cudaMemcpyAsync(s.d_gt, s.h_gt, (size_t)cells, cudaMemcpyHostToDevice, st));
     const bool tile_launch = (ctx->use_tile || ctx->use_tile_m2) && !rp; // the tile kernel rearms its own ticket and writes the totals itself
-    if (!tile_launch) CK(cudaMemsetAsync(s.d_totals, 0, 4 * sizeof(int64_t), st));
+    if (!tile_launch) CK(cudaMemsetAsync(s.d_totals, 0, 8 * sizeof(int64_t), st));
     if (rp) {
         if (!rp->depths || !rp->read_offsets || (rp->n_reads > 0 && !rp->bases)) return fail(ctx, VGL_EINVAL, "replay: depths/read_offsets/bases required");
         if (prm.error_qs == 2 && rp->n_reads > 0 && !rp->qs) return fail(ctx, VGL_EINVAL, "replay: per-read qs required with --error-qs 2");
@@ -829,7 +854,8 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     // status word: only the model-2 tile kernel in per-read-qs mode can raise a device-side error (a quality score outside
     // the --qs-bins ranges); it goes through the device word, cleared and copied back in stream order
     const bool narrow = prm.host_output == VGL_HOST_NARROW; // the narrowing pass can raise VGL_EOVERFLOW
-    const bool bcf = prm.host_output == VGL_HOST_BCF;       // the serialiser posts its byte total (and VGL_EOVERFLOW) in the device words
+    const bool bgzf = prm.host_output == VGL_HOST_BGZF;
+    const bool bcf = prm.host_output == VGL_HOST_BCF || bgzf; // the serialiser posts its byte total (and VGL_EOVERFLOW) in the device words
     const bool tile_status = tile_launch && ((ctx->use_tile_m2 && ctx->tile_m2_mode == 2) || narrow || bcf);
     if (bcf) {
         for (int32_t i = 0; i < n_sites; ++i) { // byte ranges must lie inside the blob
@@ -895,14 +921,26 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         b.minmax = s.d_minmax; b.rec_len = s.d_rec_len; b.rec_off = s.d_rec_off;
         b.out = s.d_bcf; b.out_cap = (long long)ctx->bcf_cap;
         b.totals = s.d_totals; b.status = reinterpret_cast<int32_t*>(s.d_totals + 2);
+        b.planes = s.d_planes;
         launch_bcf(b, st);
         ctx->launches += 3;
+        if (bgzf) {
+            BgzfArgs z;
+            memset(&z, 0, sizeof z);
+            z.S = (int32_t)S; z.n_sites = n_sites; z.in = s.d_bcf; z.in_cap = (long long)ctx->bcf_cap;
+            z.rec_off = s.d_rec_off; z.planes = s.d_planes; z.crc_pow = ctx->d_crc_pow;
+            z.stage = s.d_stage; z.blk_size = s.d_blk_size; z.blk_off = s.d_blk_off; z.out = s.d_bgzf; z.totals = s.d_totals;
+            // blocks this batch can make at most (its worst-case record bytes), not the slot's capacity
+            const int64_t nb_max = std::min<int64_t>(ctx->bgzf_max_blocks, bgzf_blocks_for((int64_t)((double)ctx->bcf_cap * n_sites / prm.max_batch_sites) + 65536));
+            launch_bgzf(z, nb_max, st, ctx->n_sms);
+            ctx->launches += 3;
+        }
         CK(cudaMemcpyAsync(s.h_rec_off, s.d_rec_off, ((size_t)n_sites + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaGetLastError());
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
     if (tile_launch && !tile_status) s.h_totals[2] = 0; // the kernel posts the totals into the pinned words itself and raises no errors
-    else CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    else CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (narrow) CK(cudaMemcpyAsync(s.h_dpn, s.d_dpn, (size_t)cells * (ctx->narrow_bits / 8), cudaMemcpyDeviceToHost, st));
     else if (bcf) {}
     else if (prm.host_output) CK(cudaMemcpyAsync(s.h_dp, s.d_dp, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
@@ -957,6 +995,9 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
         if (prm.host_output == VGL_HOST_BCF) {
             const int64_t nb = s.h_totals[3];
             if (nb > 0 && nb <= (int64_t)ctx->bcf_cap) CK(cudaMemcpyAsync(s.h_bcf, s.d_bcf, (size_t)nb, cudaMemcpyDeviceToHost, st));
+        } else if (prm.host_output == VGL_HOST_BGZF) {
+            const int64_t nb = s.h_totals[4];
+            if (nb > 0 && nb <= ctx->bgzf_max_blocks * (int64_t)BGZF_STRIDE) CK(cudaMemcpyAsync(s.h_bgzf, s.d_bgzf, (size_t)nb, cudaMemcpyDeviceToHost, st));
         } else {
         if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
         if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
@@ -1013,9 +1054,14 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
         out->adf_n = s.h_adfn;
         out->adr_n = s.h_adrn;
     }
-    if (prm.host_output == VGL_HOST_BCF) { // the planes stay on the device; the host gets the serialised records
+    if (prm.host_output == VGL_HOST_BCF || prm.host_output == VGL_HOST_BGZF) { // the planes stay on the device; the host gets the serialised records
         out->dp = nullptr; out->pl = out->ad = out->adf = out->adr = nullptr;
         out->gl = out->gp = nullptr;
+        if (prm.host_output == VGL_HOST_BGZF) {
+            out->bgzf = s.h_bgzf;
+            out->bgzf_bytes = s.h_totals[4];
+            out->bgzf_blocks = (int32_t)s.h_totals[5];
+        }
         out->bcf = s.h_bcf;
         out->bcf_off = reinterpret_cast<const int64_t*>(s.h_rec_off);
         out->bcf_bytes = s.h_totals[3];

@@ -145,8 +145,34 @@ struct BcfArgs {
     long long out_cap;
     int64_t* totals;       // [3] receives the total
     int32_t* status;
+    struct BcfRecPlanes* planes; // [n_sites] or null: FORMAT plane layout of every record (for the BGZF compressor)
 };
 void launch_bcf(const BcfArgs& a, cudaStream_t st);
+
+// VGL_HOST_BGZF (bgzf.cu): the record stream compressed into BGZF blocks on the device
+struct BcfRecPlanes { // where the FORMAT planes of a serialised record lie (written by k_bcf_emit)
+    uint32_t off[7];  // byte offset of the plane's first value within the record
+    uint16_t cell[7]; // bytes per sample
+    uint16_t n;       // planes
+};
+enum { BGZF_STRIDE = 36992 }; // bytes of a block's slot in the staging buffer (>= 18 + 32768 * 9 / 8 + 2 + 8)
+struct BgzfArgs {
+    int32_t S, n_sites;
+    const uint8_t* in;          // the uncompressed record stream
+    long long in_cap;
+    const long long* rec_off;   // [n_sites + 1]
+    const BcfRecPlanes* planes; // [n_sites]
+    const uint32_t* crc_pow;    // [1024] x^(256 k) mod P
+    uint8_t* stage;             // [max blocks][BGZF_STRIDE]
+    uint32_t* blk_size;         // [max blocks]
+    long long* blk_off;         // [max blocks]
+    uint8_t* out;               // the compressed stream, blocks back to back
+    int64_t* totals;            // [3] bytes of the record stream (in); [4] compressed bytes, [5] blocks (out)
+};
+size_t bgzf_dyn_smem();
+int64_t bgzf_blocks_for(int64_t bytes);
+void bgzf_crc_pow_table(uint32_t* t);
+void launch_bgzf(const BgzfArgs& a, int64_t max_blocks, cudaStream_t st, int n_sms);
 
 void launch_sim(const DevParams& p, cudaStream_t st);
 void launch_site(const DevParams& p, cudaStream_t st);
