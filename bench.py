@@ -12,10 +12,12 @@ L2 flush is needed between launches.
 
   value  kernel-side throughput: genotypes resident in HBM, results left in HBM, CUDA events on the launching stream
          (torch's current stream, handed to libvgl); max over ranks.
-  e2e    the same metric through the C ABI with HOST buffers: pinned H2D of the packed genotypes and D2H of every tag plane
-         inside the timed region.  Planes cross PCIe in the ABI's VGL_HOST_NARROW form (GL float32; PL / AD / DP as the
-         8-bit values BCF stores, narrowed on the device); `e2e.i32_planes` is the same loop with the int32 planes of
-         VGL_HOST_I32 (add_tags() layout), `e2e.bcf_records` with finished BCF records (VGL_HOST_BCF).
+  e2e    the same metric through the C ABI with HOST buffers: pinned H2D of the packed genotypes and D2H of the results
+         inside the timed region.  Headline: VGL_HOST_BGZF -- finished BCF records, BGZF-compressed on the device (what the
+         reference writes by default); `e2e.bcf_records` the same records uncompressed (VGL_HOST_BCF), `e2e.narrow_planes`
+         the tag planes (GL float32; PL / AD / DP as the 8-bit values BCF stores, narrowed on the device), `e2e.i32_planes`
+         the int32 planes of VGL_HOST_I32 (add_tags() layout).  gVCF workloads: the narrowed planes (the block merger
+         consumes arrays).
   roofline      algorithmic bytes of one launch / the kernel's average launch duration (CUDA events inside
                 the timed region), against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the reference binary itself (oracle/_ref/vcfgl_ref, built from /root/reference) on a bounded sample of the
@@ -425,6 +427,8 @@ def gpu_arm(opt):
     def out_bytes(b):
         """bytes the D2H copies of one batch moved (spans as libvgl copies them)"""
         r = b.raw
+        if b.bgzf is not None:      # VGL_HOST_BGZF: the compressed record stream, the record offsets, the per-site records
+            return int(b.bgzf_bytes + 8 * (b.n_sites + 1) + b.n_sites * capi.SITE_DTYPE.itemsize)
         if b.bcf_off is not None:   # VGL_HOST_BCF: the record stream, its offsets, the per-site records
             return int(b.bcf_bytes + 8 * (b.n_sites + 1) + b.n_sites * capi.SITE_DTYPE.itemsize)
         w = (b.narrow_bits // 8) if b.narrow_bits else 4          # DP / AD element width
@@ -460,7 +464,7 @@ def gpu_arm(opt):
         for s in range(E_SLOTS):
             ctx.set_stream(s, streams[s].cuda_stream)
         bufs = [ctx.input_buffer(s) for s in range(E_SLOTS)]
-        bcf_in = [ctx.bcf_input(s)[0] for s in range(E_SLOTS)] if mode == capi.HOST_BCF else None
+        bcf_in = [ctx.bcf_input(s)[0] for s in range(E_SLOTS)] if mode in (capi.HOST_BCF, capi.HOST_BGZF) else None
         e2e_batches(ctx, bufs, E_SLOTS, site_next, bcf_in)
         barrier()
         l0 = ctx.launch_count()
@@ -475,13 +479,21 @@ def gpu_arm(opt):
         return world * Ke * Le * B * S / (ms * 1e-3), d2h, n_launch
 
     e2e_i32, d2h_i32, _ = e2e_run(capi.HOST_I32)
-    e2e_value, d2h_bytes, e2e_launches = e2e_run(capi.HOST_NARROW)
+    e2e_nar, d2h_nar, nl_nar = e2e_run(capi.HOST_NARROW)
+    e2e_narrow = {"value": e2e_nar, "d2h_bytes_per_step": d2h_nar * Le, "gpu_launches": int(nl_nar),
+                  "planes": "VGL_HOST_NARROW: GL float32, PL/AD/DP narrowed on the device to the 8-bit values BCF stores"}
+    e2e_value, d2h_bytes, e2e_launches = e2e_nar, d2h_nar, nl_nar
+    e2e_planes = e2e_narrow["planes"]
     e2e_bcf = None
     if not a.do_gvcf:   # serialised BCF records (the gVCF block merger consumes arrays)
         v, nb, nl = e2e_run(capi.HOST_BCF)
         e2e_bcf = {"value": v, "d2h_bytes_per_step": nb * Le, "gpu_launches": int(nl),
                    "planes": "VGL_HOST_BCF: complete BCF records serialised on the device (k_bcf_plan/scan/emit), byte-identical to "
                              "the reference's -O u stream; the host only appends the buffer to the output"}
+        # the headline: finished records as BGZF blocks (the reference's default container, -O b), compressed on the device
+        e2e_value, d2h_bytes, e2e_launches = e2e_run(capi.HOST_BGZF)
+        e2e_planes = ("VGL_HOST_BGZF: complete BCF records serialised and BGZF-compressed on the device (k_bcf_* + k_bgzf_*); inflating "
+                      "the blocks gives the reference's -O u stream byte for byte; the host only appends the buffer to the output")
 
     # ---------------- the other BASELINE configs, kernel side; the input path
     configs, input_path = None, None
@@ -525,7 +537,7 @@ def gpu_arm(opt):
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * S * Le), "d2h_bytes_per_step": d2h_bytes * Le,
                 "steps": Ke, "launches_per_step": Le, "gpu_launches": int(e2e_launches), "timer": "host wall clock, max over ranks",
-                "planes": "VGL_HOST_NARROW: GL float32, PL/AD/DP narrowed on the device to the 8-bit values BCF stores",
+                "planes": e2e_planes, "narrow_planes": e2e_narrow,
                 "i32_planes": {"value": e2e_i32, "d2h_bytes_per_step": d2h_i32 * Le,
                                "planes": "VGL_HOST_I32: every plane int32/float32 as add_tags() hands them to htslib"},
                 "bcf_records": e2e_bcf},

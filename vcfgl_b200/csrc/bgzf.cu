@@ -16,11 +16,17 @@
 //                   per segment -> CTA-wide prefix sum -> every segment ORs its bits into the block image in shared memory.
 //                   CRC32: 32-byte chunks per thread, combined by multiplication with x^(8 n) mod P (the identity zlib's
 //                   crc32_combine uses).
+//   k_bgzf_first    thread per block: the first record that reaches into it (binary search over the record offsets)
 //   k_bgzf_scan     exclusive prefix of the compressed block sizes
-//   k_bgzf_pack     blocks moved back to back into the stream the host receives
+//   k_bgzf_pack     blocks moved back to back into the stream the host receives -- written straight into the slot's pinned host
+//                   buffer (mapped memory), so the transfer is part of the stream's work and needs no size known to the host
 //
 // Parity: inflating the blocks gives back the VGL_HOST_BCF stream byte for byte (tests/test_gpu_bgzf.py: zlib on the host).
 #include "vgl_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 namespace vgl {
 
@@ -109,6 +115,30 @@ __host__ __device__ inline uint32_t crc_mul(uint32_t a, uint32_t b)
     return p;
 }
 
+// first record whose bytes reach into block b (the last record that starts at or before the block's first byte)
+__global__ void __launch_bounds__(256) k_bgzf_first(const BgzfArgs a)
+{
+    const long long total = a.totals[3];
+    const long long nblk = total > a.in_cap ? 0 : (total + BGZF_IN - 1) / BGZF_IN;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (long long)gridDim.x * blockDim.x) {
+        const long long b0 = b * BGZF_IN;
+        int lo = 0, hi = a.n_sites; // rec_off[lo] <= b0 < rec_off[hi]; rec_off is non-decreasing
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.rec_off[mid] <= b0) lo = mid; else hi = mid;
+        }
+        a.blk_first[b] = lo;
+    }
+}
+
+// 32-bit word at byte offset `pos` of shared memory (any alignment)
+__device__ __forceinline__ uint32_t word_at(const uint8_t* base, uint32_t pos)
+{
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (pos >> 2);
+    const uint32_t sh = (pos & 3u) * 8u;
+    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+}
+
 __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs a)
 {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -118,7 +148,8 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     uint32_t* const seg_bit = reinterpret_cast<uint32_t*>(segs + MAX_SEG);        // [MAX_SEG] bit offset of every segment
     uint32_t* const htab = seg_bit + MAX_SEG;                                     // [HASH_SLOTS] tag << 16 | position
     uint32_t* const rng = htab + HASH_SLOTS;                                      // [MAX_RANGES][4]: pos, len, cell bytes (0: gap), first segment
-    __shared__ uint32_t crc_tab[256];
+    __shared__ uint32_t crc_tab[1024]; // slicing-by-four tables of CRC-32
+    __shared__ uint16_t lit_tab[256];
     __shared__ uint32_t warp_tot[32];
     __shared__ int n_rng_s, n_seg_s, lit_only_s;
     __shared__ uint32_t crc_s, total_bits_s;
@@ -129,27 +160,38 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     if (b0 >= total || total > a.in_cap) return;
     const int L = (int)min((long long)BGZF_IN, total - b0);
 
-    // ---- the block's bytes, the CRC table, cleared tables
-    for (int i = tid; i < (L + 15) / 16; i += BGZF_THREADS) reinterpret_cast<uint4*>(in)[i] = reinterpret_cast<const uint4*>(a.in + b0)[i];
-    for (int i = tid; i < OUT_WORDS; i += BGZF_THREADS) out[i] = 0u;
-    for (int i = tid; i < HASH_SLOTS; i += BGZF_THREADS) htab[i] = 0xFFFFFFFFu;
-    if (tid < 256) {
-        uint32_t c = (uint32_t)tid;
+    // ---- warps 1..: the block's bytes, the CRC and literal-code tables, cleared tables; meanwhile warp 0: the ranges
+    if (warp > 0) {
+        const int t = tid - 32, nt = BGZF_THREADS - 32;
+        for (int i = t; i < (L + 15) / 16; i += nt) reinterpret_cast<uint4*>(in)[i] = __ldcs(reinterpret_cast<const uint4*>(a.in + b0) + i);
+        for (int i = t; i < OUT_WORDS / 4; i += nt) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = t; i < HASH_SLOTS / 4; i += nt) reinterpret_cast<uint4*>(htab)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        if (t < 256) {
+            uint32_t c = (uint32_t)t;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
-        crc_tab[tid] = c;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+            crc_tab[t] = c;
+            uint32_t c1 = c;
+#pragma unroll
+            for (int lvl = 1; lvl < 4; ++lvl) { // T_lvl[i] = the CRC register after byte i and lvl zero bytes
+                uint32_t z = c1 & 0xFFu;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) z = (z & 1u) ? (z >> 1) ^ 0xEDB88320u : z >> 1;
+                c1 = z ^ (c1 >> 8);
+                crc_tab[256 * lvl + t] = c1;
+            }
+            uint32_t b;
+            int n;
+            lit_code((uint32_t)t, b, n);
+            lit_tab[t] = (uint16_t)(b | ((uint32_t)(n - 8) << 15)); // 9 code bits, bit 15: one more than 8
+        }
     }
-    if (tid == 0) { n_rng_s = 0; n_seg_s = 0; lit_only_s = 0; crc_s = 0u; }
-    __syncthreads();
 
     // ---- ranges: the part of every record that lies in the block, split at the FORMAT planes (warp 0, a lane per record)
     if (warp == 0) {
-        // first record that ends after b0
-        int lo = 0, hi = a.n_sites; // rec_off[lo] <= b0 < rec_off[hi] over the kept records; rec_off is non-decreasing
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (a.rec_off[mid] <= b0) lo = mid; else hi = mid;
-        }
+        if (lane == 0) { n_rng_s = 0; n_seg_s = 0; lit_only_s = 0; crc_s = 0u; }
+        __syncwarp();
+        const int lo = a.blk_first[blockIdx.x];
         const int r = lo + lane;
         int my_n = 0;
         uint32_t my[16][3]; // pos, len, cell
@@ -162,7 +204,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
             const long long end = min(re, b0 + L);
             for (int k = 0; k < (int)pl.n && k < 7; ++k) {
                 const long long ps = rs + pl.off[k], pe = ps + (long long)pl.cell[k] * a.S;
-                if (pl.cell[k] < 3 || pl.cell[k] > 258 || pe <= cur || ps >= end) continue; // deflate matches are 3 .. 258 bytes long
+                if (pl.cell[k] < 3 || pl.cell[k] > RUN || pe <= cur || ps >= end) continue; // deflate matches are at least 3 bytes long; segments at most RUN
                 // full cells of this plane inside [cur, end)
                 long long c_lo = ps >= cur ? 0 : (cur - ps + pl.cell[k] - 1) / pl.cell[k];
                 long long c_hi = pe <= end ? a.S : (end - ps) / pl.cell[k];
@@ -227,9 +269,11 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     __syncthreads();
 
     // ---- cells: hash of the bytes, first occurrence per hash (atomicMin on tag << 16 | position; open addressing)
-    auto cell_hash = [&](const Seg& s) -> uint32_t {
+    auto cell_hash = [&](const Seg& s) -> uint32_t { // FNV-style over 32-bit words (the tail word masked)
         uint32_t h = 2166136261u ^ s.len;
-        for (int k = 0; k < s.len; ++k) h = (h ^ in[s.pos + k]) * 16777619u;
+        const int nw = s.len >> 2;
+        for (int k = 0; k < nw; ++k) h = (h ^ word_at(in, s.pos + 4u * k)) * 16777619u;
+        if (s.len & 3) h = (h ^ (word_at(in, s.pos + 4u * nw) & ((1u << (8 * (s.len & 3))) - 1u))) * 16777619u;
         h ^= h >> 15;
         return h;
     };
@@ -237,6 +281,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         const Seg s = segs[j];
         if (!s.cell) continue;
         const uint32_t h = cell_hash(s), tag = h >> 16, mine = (tag << 16) | s.pos;
+        seg_bit[j] = h; // kept for the look-up pass
         uint32_t slot = h & (HASH_SLOTS - 1);
         for (int probe = 0; probe < 16; ++probe) {
             const uint32_t old = atomicCAS(&htab[slot], 0xFFFFFFFFu, mine);
@@ -251,7 +296,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         Seg s = segs[j];
         uint32_t nbits = 0;
         if (s.cell) {
-            const uint32_t h = cell_hash(s), tag = h >> 16;
+            const uint32_t h = seg_bit[j], tag = h >> 16;
             uint32_t slot = h & (HASH_SLOTS - 1);
             for (int probe = 0; probe < 16; ++probe) {
                 const uint32_t e = htab[slot];
@@ -260,7 +305,9 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
                     const uint32_t q = e & 0xFFFFu;
                     if (q < s.pos && q + s.len <= s.pos) { // an earlier cell (cells do not overlap)
                         bool same = true;
-                        for (int k = 0; k < s.len && same; ++k) same = in[q + k] == in[s.pos + k];
+                        const int nw = s.len >> 2;
+                        for (int k = 0; k < nw && same; ++k) same = word_at(in, q + 4u * k) == word_at(in, s.pos + 4u * k);
+                        for (int k = 4 * nw; k < s.len && same; ++k) same = in[q + k] == in[s.pos + k];
                         if (same) s.dist = (uint16_t)(s.pos - q);
                     }
                     break;
@@ -274,8 +321,24 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
             match_code(s.len, s.dist, b, n);
             nbits = (uint32_t)n;
             segs[j].dist = s.dist;
-        } else {
-            for (int k = 0; k < s.len; ++k) nbits += in[s.pos + k] < 144 ? 8u : 9u;
+            segs[j].cell = 0;
+        } else { // 8 bits per literal, 9 for the values from 144 up; the counts before quarters 1..3 go into the free cell field
+            const int ql = (s.len + 3) >> 2; // <= 16: segments are at most 64 bytes long
+            uint32_t extra = 0u, cum = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { // 9-bit literals (values from 144 up) of quarter q, four bytes at a time
+                const int k0 = q * ql, k1 = min(k0 + ql, (int)s.len);
+                uint32_t part = 0u;
+                for (int k = k0; k < k1; k += 4) {
+                    uint32_t w = __vcmpgeu4(word_at(in, s.pos + (uint32_t)k), 0x90909090u) & 0x01010101u;
+                    if (k1 - k < 4) w &= (1u << (8 * (k1 - k))) - 1u;
+                    part += __popc(w);
+                }
+                if (q < 3) cum |= part << (5 * q);
+                extra += part;
+            }
+            nbits = 8u * s.len + extra;
+            segs[j].cell = (uint16_t)(0x8000u | cum); // bit 15: literal segment
         }
         seg_bit[j] = nbits;
     }
@@ -317,34 +380,66 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         if (tid == BGZF_THREADS - 1) total_bits_s = base;
     }
     __syncthreads();
-    // ---- bits: BFINAL = 1, BTYPE = 01 (fixed Huffman), the segments, end of block (7 zero bits: already there)
+    // ---- bits: BFINAL = 1, BTYPE = 01 (fixed Huffman), the segments, end of block (7 zero bits: already there).
+    // Warps 0 .. 27 write the codes, four threads per segment (a literal segment is split into quarters, whose bit offsets
+    // follow from the bytes before them); warps 28 .. 31 compute the CRC32 of the block meanwhile.
+    constexpr int EMIT_THREADS = BGZF_THREADS - 128;
     if (tid == 0) atomicOr(&out[0], 3u);
-    for (int j = tid; j < n_seg; j += BGZF_THREADS) {
-        const Seg s = segs[j];
-        unsigned at = seg_bit[j];
-        if (s.dist) {
-            uint32_t b;
-            int n;
-            match_code(s.len, s.dist, b, n);
-            put_bits(out, at, b, n);
-        } else {
-            for (int k = 0; k < s.len; ++k) {
-                uint32_t b;
+    if (warp < 28) {
+        // a warp takes 32 consecutive segments: the matches go out one per lane, then the literal segments of the group are
+        // spread over the lanes a quarter each, so that the byte loops run on full warps
+        for (int j0 = warp * 32; j0 < n_seg; j0 += 28 * 32) {
+            const int j = j0 + lane;
+            Seg s;
+            s.pos = s.len = s.dist = s.cell = 0;
+            if (j < n_seg) s = segs[j];
+            if (s.dist) {
+                uint32_t bb;
                 int n;
-                lit_code(in[s.pos + k], b, n);
-                put_bits(out, at, b, n);
-                at += (unsigned)n;
+                match_code(s.len, s.dist, bb, n);
+                put_bits(out, seg_bit[j], bb, n);
+            }
+            const uint32_t litm = __ballot_sync(0xffffffffu, j < n_seg && (s.cell & 0x8000u));
+            const int ntask = 4 * __popc(litm);
+            for (int t = lane; t < ntask; t += 32) {
+                const int jj = j0 + (int)__fns(litm, 0u, (t >> 2) + 1), q = t & 3;
+                const Seg ls = segs[jj];
+                const int ql = (ls.len + 3) >> 2, k0 = q * ql, k1 = min(k0 + ql, (int)ls.len);
+                if (k0 >= k1) continue;
+                const unsigned c = ls.cell; // 9-bit literals in quarters 0, 1, 2: five bits each
+                const unsigned cum = (q > 0 ? c & 31u : 0u) + (q > 1 ? (c >> 5) & 31u : 0u) + (q > 2 ? (c >> 10) & 31u : 0u);
+                unsigned at = seg_bit[jj] + 8u * (unsigned)k0 + cum;
+                unsigned w = at >> 5;
+                int fill = (int)(at & 31u);
+                unsigned long long acc = 0ull;
+                for (int k = k0; k < k1; ++k) {
+                    const uint32_t e = lit_tab[in[ls.pos + k]];
+                    acc |= (unsigned long long)(e & 0x1FFu) << fill;
+                    fill += 8 + (int)(e >> 15);
+                    if (fill >= 32) {
+                        atomicOr(&out[w], (uint32_t)acc);
+                        ++w;
+                        acc >>= 32;
+                        fill -= 32;
+                    }
+                }
+                if (fill > 0) atomicOr(&out[w], (uint32_t)acc);
             }
         }
-    }
-    // ---- CRC32 of the block: 32-byte chunks from the end, each shifted across the bytes behind it
-    {
-        const int hi = L - tid * 32, lo2 = max(hi - 32, 0);
+    } else {
+        // CRC32 of the block: 256-byte chunks from the end (slicing by four), each shifted across the bytes behind it
+        const int c = tid - EMIT_THREADS; // 0 .. 127
+        const int hi = L - c * 256, lo2 = max(hi - 256, 0);
         uint32_t part = 0u;
         if (hi > 0) {
-            uint32_t c = 0xFFFFFFFFu;
-            for (int k = lo2; k < hi; ++k) c = crc_tab[(c ^ in[k]) & 0xFFu] ^ (c >> 8);
-            part = crc_mul(a.crc_pow[tid], ~c);
+            uint32_t r = 0xFFFFFFFFu;
+            int k = lo2;
+            for (; k < hi && ((hi - k) & 3); ++k) r = crc_tab[(r ^ in[k]) & 0xFFu] ^ (r >> 8); // head bytes: the rest is whole words
+            for (; k < hi; k += 4) {
+                r ^= word_at(in, (uint32_t)k);
+                r = crc_tab[768 + (r & 0xFFu)] ^ crc_tab[512 + ((r >> 8) & 0xFFu)] ^ crc_tab[256 + ((r >> 16) & 0xFFu)] ^ crc_tab[r >> 24];
+            }
+            part = crc_mul(a.crc_pow[c * 8], ~r);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
@@ -354,14 +449,17 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     // ---- the BGZF block: header, deflate data, CRC32, ISIZE -> its slot of the staging buffer
     const uint32_t nbytes = (total_bits_s + 7u + 7u) >> 3; // + the 7-bit end-of-block code, rounded up to a byte
     const uint32_t bsize = 18u + nbytes + 8u;
-    uint8_t* const dst = a.stage + (size_t)blockIdx.x * BGZF_STRIDE;
+    uint8_t* const dst = a.stage + (size_t)blockIdx.x * BGZF_STRIDE + 2; // + 2: the deflate data (at + 18) starts on a word
     if (tid < 18) {
         const uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)((bsize - 1u) & 0xFFu), (uint8_t)((bsize - 1u) >> 8)};
         dst[tid] = hdr[tid];
     }
-    // dst + 18 is 2 mod 4: bytes
-    const uint8_t* const ob = reinterpret_cast<const uint8_t*>(out);
-    for (uint32_t i = tid; i < nbytes; i += BGZF_THREADS) dst[18 + i] = ob[i];
+    {
+        uint32_t* const dw = reinterpret_cast<uint32_t*>(dst + 18);
+        const uint8_t* const ob = reinterpret_cast<const uint8_t*>(out);
+        for (uint32_t i = tid; i < (nbytes >> 2); i += BGZF_THREADS) __stcs(dw + i, out[i]);
+        if (tid < (nbytes & 3u)) dst[18 + (nbytes & ~3u) + tid] = ob[(nbytes & ~3u) + tid];
+    }
     if (tid < 8) {
         const uint32_t v = tid < 4 ? crc_s : (uint32_t)L;
         dst[18 + nbytes + tid] = (uint8_t)(v >> (8 * (tid & 3)));
@@ -417,7 +515,7 @@ __global__ void __launch_bounds__(256) k_bgzf_pack(const BgzfArgs a)
     const long long total = a.totals[3];
     const int nblk = total > a.in_cap ? 0 : (int)((total + BGZF_IN - 1) / BGZF_IN);
     for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
-        const uint8_t* src = a.stage + (size_t)b * BGZF_STRIDE;
+        const uint8_t* src = a.stage + (size_t)b * BGZF_STRIDE + 2;
         uint8_t* dst = a.out + a.blk_off[b];
         const uint32_t n = a.blk_size[b];
         // aligned words of the destination, edges by bytes
@@ -455,6 +553,7 @@ void bgzf_crc_pow_table(uint32_t* t)
 void launch_bgzf(const BgzfArgs& a, int64_t max_blocks, cudaStream_t st, int n_sms)
 {
     cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bgzf_dyn_smem()); // per device
+    k_bgzf_first<<<(unsigned)std::min<int64_t>((max_blocks + 255) / 256, 4096), 256, 0, st>>>(a);
     k_bgzf_deflate<<<(unsigned)max_blocks, BGZF_THREADS, bgzf_dyn_smem(), st>>>(a);
     k_bgzf_scan<<<1, 1024, 0, st>>>(a);
     k_bgzf_pack<<<(unsigned)(n_sms * 8), 256, 0, st>>>(a);

@@ -5,7 +5,9 @@
 #include "vgl_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,6 +54,7 @@ struct Slot {
     uint8_t *d_stage = nullptr, *d_bgzf = nullptr, *h_bgzf = nullptr;
     uint32_t* d_blk_size = nullptr;
     long long* d_blk_off = nullptr;
+    int32_t* d_blk_first = nullptr;
     // device
     uint8_t* d_gt = nullptr;
     int32_t* d_dp = nullptr;
@@ -252,7 +255,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         cudaFreeHost(s.h_pl8); cudaFreeHost(s.h_dpn); cudaFreeHost(s.h_adn); cudaFreeHost(s.h_adfn); cudaFreeHost(s.h_adrn);
         cudaFreeHost(s.h_bcf_in); cudaFreeHost(s.h_blob); cudaFreeHost(s.h_bcf); cudaFreeHost(s.h_rec_off);
         cudaFree(s.d_bcf_in); cudaFree(s.d_blob); cudaFree(s.d_bcf); cudaFree(s.d_minmax); cudaFree(s.d_rec_len); cudaFree(s.d_rec_off);
-        cudaFree(s.d_planes); cudaFree(s.d_stage); cudaFree(s.d_bgzf); cudaFreeHost(s.h_bgzf); cudaFree(s.d_blk_size); cudaFree(s.d_blk_off);
+        cudaFree(s.d_planes); cudaFree(s.d_stage); cudaFree(s.d_bgzf); cudaFreeHost(s.h_bgzf); cudaFree(s.d_blk_size); cudaFree(s.d_blk_off); cudaFree(s.d_blk_first);
         cudaFree(s.d_pl8); cudaFree(s.d_dpn); cudaFree(s.d_adn); cudaFree(s.d_adfn); cudaFree(s.d_adrn);
         cudaFree(s.d_gt); cudaFree(s.d_dp); cudaFree(s.d_cell); cudaFree(s.d_cellq); cudaFree(s.d_celltail);
         cudaFree(s.d_sites); cudaFree(s.d_totals); cudaFree(s.d_pairmap); cudaFree(s.d_tile_state);
@@ -472,6 +475,7 @@ static int create_impl(vgl_ctx* ctx)
                 CK(cudaHostAlloc((void**)&s.h_bgzf, worst, cudaHostAllocDefault));
                 CK(cudaMalloc((void**)&s.d_blk_size, (size_t)ctx->bgzf_max_blocks * sizeof(uint32_t)));
                 CK(cudaMalloc((void**)&s.d_blk_off, (size_t)ctx->bgzf_max_blocks * sizeof(long long)));
+                CK(cudaMalloc((void**)&s.d_blk_first, (size_t)ctx->bgzf_max_blocks * sizeof(int32_t)));
                 if (!ctx->d_crc_pow) {
                     std::vector<uint32_t> pw(1024);
                     bgzf_crc_pow_table(pw.data());
@@ -802,6 +806,50 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
 
 }
 
+// The result copies of a batch whose extents (plane elements, record bytes, compressed bytes) are only known once its kernels
+// have run: enqueued on the slot's stream as soon as some API call finds the totals on the host.
+static int issue_d2h(vgl_ctx* ctx, Slot& s)
+{
+    const vgl_params& prm = ctx->prm;
+    cudaStream_t st = s.stream;
+    const int64_t g_elems = s.h_totals[0], r_elems = s.h_totals[1];
+    CK(cudaEventRecord(s.ev[EV_D2H0], st));
+    if (prm.host_output == VGL_HOST_BCF) {
+        const int64_t nb = s.h_totals[3];
+        if (nb > 0 && nb <= (int64_t)ctx->bcf_cap) CK(cudaMemcpyAsync(s.h_bcf, s.d_bcf, (size_t)nb, cudaMemcpyDeviceToHost, st));
+    } else if (prm.host_output == VGL_HOST_BGZF) {
+        const int64_t nb = s.h_totals[4];
+        if (nb > 0 && nb <= ctx->bgzf_max_blocks * (int64_t)BGZF_STRIDE) CK(cudaMemcpyAsync(s.h_bgzf, s.d_bgzf, (size_t)nb, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
+        if (ctx->narrow_bits) {
+            const size_t w = (size_t)ctx->narrow_bits / 8;
+            if (s.d_pl8) CK(cudaMemcpyAsync(s.h_pl8, s.d_pl8, (size_t)g_elems, cudaMemcpyDeviceToHost, st));
+            if (s.d_adn) CK(cudaMemcpyAsync(s.h_adn, s.d_adn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
+            if (s.d_adfn) CK(cudaMemcpyAsync(s.h_adfn, s.d_adfn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
+            if (s.d_adrn) CK(cudaMemcpyAsync(s.h_adrn, s.d_adrn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (s.d_pl) CK(cudaMemcpyAsync(s.h_pl, s.d_pl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_ad) CK(cudaMemcpyAsync(s.h_ad, s.d_ad, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_adf) CK(cudaMemcpyAsync(s.h_adf, s.d_adf, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+            if (s.d_adr) CK(cudaMemcpyAsync(s.h_adr, s.d_adr, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK(cudaEventRecord(s.ev[EV_D2H1], st));
+    s.early_d2h = true;
+    return VGL_OK;
+}
+
+// every submit / wait looks at the other slots in flight: a batch whose kernels have finished gets its result copies enqueued
+// right away, so that they run under the host's work on other slots instead of inside that slot's vgl_wait
+static void progress(vgl_ctx* ctx)
+{
+    if (!ctx->prm.host_output) return;
+    for (Slot& s : ctx->slots)
+        if (s.submitted && !s.waited && !s.early_d2h && cudaEventQuery(s.ev[EV_META]) == cudaSuccess) issue_d2h(ctx, s);
+}
+
 extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_sites, const vgl_replay* rp, uint32_t flags)
 {
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
@@ -810,6 +858,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     if (s.submitted && !s.waited) return fail(ctx, VGL_ESTATE, "slot still in flight: call vgl_wait first");
     const vgl_params& prm = ctx->prm;
     CK(cudaSetDevice(prm.device_id));
+    progress(ctx);
     cudaStream_t st = s.stream;
     const int64_t S = prm.n_samples, cells = (int64_t)n_sites * S;
 
@@ -929,11 +978,11 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             memset(&z, 0, sizeof z);
             z.S = (int32_t)S; z.n_sites = n_sites; z.in = s.d_bcf; z.in_cap = (long long)ctx->bcf_cap;
             z.rec_off = s.d_rec_off; z.planes = s.d_planes; z.crc_pow = ctx->d_crc_pow;
-            z.stage = s.d_stage; z.blk_size = s.d_blk_size; z.blk_off = s.d_blk_off; z.out = s.d_bgzf; z.totals = s.d_totals;
+            z.stage = s.d_stage; z.blk_size = s.d_blk_size; z.blk_off = s.d_blk_off; z.blk_first = s.d_blk_first; z.out = s.d_bgzf; z.totals = s.d_totals;
             // blocks this batch can make at most (its worst-case record bytes), not the slot's capacity
             const int64_t nb_max = std::min<int64_t>(ctx->bgzf_max_blocks, bgzf_blocks_for((int64_t)((double)ctx->bcf_cap * n_sites / prm.max_batch_sites) + 65536));
             launch_bgzf(z, nb_max, st, ctx->n_sms);
-            ctx->launches += 3;
+            ctx->launches += 4;
         }
         CK(cudaMemcpyAsync(s.h_rec_off, s.d_rec_off, ((size_t)n_sites + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     }
@@ -983,39 +1032,27 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
     if (!s.submitted) return fail(ctx, VGL_ESTATE, "slot was not submitted");
     const vgl_params& prm = ctx->prm;
     CK(cudaSetDevice(prm.device_id));
-    CK(cudaEventSynchronize(s.ev[EV_META]));
+    // waiting polls, so that the other slots' result copies get enqueued the moment their kernels finish (progress())
+    auto wait_event = [&](cudaEvent_t ev) -> cudaError_t {
+        if (!prm.host_output || ctx->slots.size() == 1) return cudaEventSynchronize(ev);
+        for (;;) {
+            const cudaError_t e = cudaEventQuery(ev);
+            if (e != cudaErrorNotReady) return e;
+            progress(ctx);
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+    };
+    progress(ctx);
+    CK(wait_event(s.ev[EV_META]));
+    progress(ctx);
     const int64_t g_elems = s.h_totals[0], r_elems = s.h_totals[1];
     const int32_t status = *reinterpret_cast<int32_t*>(s.h_totals + 2);
-    if (prm.host_output && !s.waited && s.early_d2h) {
-        CK(cudaEventSynchronize(s.ev[EV_D2H1]));
-        s.had_d2h = true;
-    } else if (prm.host_output && !s.waited) {
-        cudaStream_t st = s.stream;
-        CK(cudaEventRecord(s.ev[EV_D2H0], st));
-        if (prm.host_output == VGL_HOST_BCF) {
-            const int64_t nb = s.h_totals[3];
-            if (nb > 0 && nb <= (int64_t)ctx->bcf_cap) CK(cudaMemcpyAsync(s.h_bcf, s.d_bcf, (size_t)nb, cudaMemcpyDeviceToHost, st));
-        } else if (prm.host_output == VGL_HOST_BGZF) {
-            const int64_t nb = s.h_totals[4];
-            if (nb > 0 && nb <= ctx->bgzf_max_blocks * (int64_t)BGZF_STRIDE) CK(cudaMemcpyAsync(s.h_bgzf, s.d_bgzf, (size_t)nb, cudaMemcpyDeviceToHost, st));
-        } else {
-        if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
-        if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
-        if (ctx->narrow_bits) {
-            const size_t w = (size_t)ctx->narrow_bits / 8;
-            if (s.d_pl8) CK(cudaMemcpyAsync(s.h_pl8, s.d_pl8, (size_t)g_elems, cudaMemcpyDeviceToHost, st));
-            if (s.d_adn) CK(cudaMemcpyAsync(s.h_adn, s.d_adn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
-            if (s.d_adfn) CK(cudaMemcpyAsync(s.h_adfn, s.d_adfn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
-            if (s.d_adrn) CK(cudaMemcpyAsync(s.h_adrn, s.d_adrn, (size_t)r_elems * w, cudaMemcpyDeviceToHost, st));
-        } else {
-            if (s.d_pl) CK(cudaMemcpyAsync(s.h_pl, s.d_pl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
-            if (s.d_ad) CK(cudaMemcpyAsync(s.h_ad, s.d_ad, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
-            if (s.d_adf) CK(cudaMemcpyAsync(s.h_adf, s.d_adf, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
-            if (s.d_adr) CK(cudaMemcpyAsync(s.h_adr, s.d_adr, (size_t)r_elems * 4, cudaMemcpyDeviceToHost, st));
+    if (prm.host_output && !s.waited) {
+        if (!s.early_d2h) { // the copies wait for the totals: enqueue them now unless an earlier call already did (progress())
+            const int rc = issue_d2h(ctx, s);
+            if (rc != VGL_OK) return rc;
         }
-        }
-        CK(cudaEventRecord(s.ev[EV_D2H1], st));
-        CK(cudaEventSynchronize(s.ev[EV_D2H1]));
+        CK(wait_event(s.ev[EV_D2H1]));
         s.had_d2h = true;
     }
     if (!s.waited) {

@@ -166,6 +166,7 @@ struct BgzfArgs {
     uint8_t* stage;             // [max blocks][BGZF_STRIDE]
     uint32_t* blk_size;         // [max blocks]
     long long* blk_off;         // [max blocks]
+    int32_t* blk_first;         // [max blocks] first record that reaches into the block
     uint8_t* out;               // the compressed stream, blocks back to back
     int64_t* totals;            // [3] bytes of the record stream (in); [4] compressed bytes, [5] blocks (out)
 };
