@@ -185,11 +185,28 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
             lit_code((uint32_t)t, b, n);
             lit_tab[t] = (uint16_t)(b | ((uint32_t)(n - 8) << 15)); // 9 code bits, bit 15: one more than 8
         }
+        if (t == 0) crc_s = 0u;
+        // CRC32 of the block while warp 0 is busy with the ranges: 32-byte chunks from the end (slicing by four), each shifted
+        // across the bytes behind it.  Barrier 1 = warps 1 .. 31 only.
+        asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
+        for (int c = t; c < 1024; c += nt) {
+            const int hi = L - c * 32, lo2 = max(hi - 32, 0);
+            if (hi <= 0) break;
+            uint32_t r = 0xFFFFFFFFu;
+            int k = lo2;
+            for (; k < hi && ((hi - k) & 3); ++k) r = crc_tab[(r ^ in[k]) & 0xFFu] ^ (r >> 8); // head bytes: the rest is whole words
+            for (; k < hi; k += 4) {
+                r ^= word_at(in, (uint32_t)k);
+                r = crc_tab[768 + (r & 0xFFu)] ^ crc_tab[512 + ((r >> 8) & 0xFFu)] ^ crc_tab[256 + ((r >> 16) & 0xFFu)] ^ crc_tab[r >> 24];
+            }
+            const uint32_t part = crc_mul(a.crc_pow[c], ~r);
+            if (part) atomicXor(&crc_s, part);
+        }
     }
 
     // ---- ranges: the part of every record that lies in the block, split at the FORMAT planes (warp 0, a lane per record)
     if (warp == 0) {
-        if (lane == 0) { n_rng_s = 0; n_seg_s = 0; lit_only_s = 0; crc_s = 0u; }
+        if (lane == 0) { n_rng_s = 0; n_seg_s = 0; lit_only_s = 0; }
         __syncwarp();
         const int lo = a.blk_first[blockIdx.x];
         const int r = lo + lane;
@@ -381,14 +398,12 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     }
     __syncthreads();
     // ---- bits: BFINAL = 1, BTYPE = 01 (fixed Huffman), the segments, end of block (7 zero bits: already there).
-    // Warps 0 .. 27 write the codes, four threads per segment (a literal segment is split into quarters, whose bit offsets
-    // follow from the bytes before them); warps 28 .. 31 compute the CRC32 of the block meanwhile.
-    constexpr int EMIT_THREADS = BGZF_THREADS - 128;
+    // A literal segment is split into quarters (their bit offsets follow from the counts kept with the segment).
     if (tid == 0) atomicOr(&out[0], 3u);
-    if (warp < 28) {
+    {
         // a warp takes 32 consecutive segments: the matches go out one per lane, then the literal segments of the group are
         // spread over the lanes a quarter each, so that the byte loops run on full warps
-        for (int j0 = warp * 32; j0 < n_seg; j0 += 28 * 32) {
+        for (int j0 = warp * 32; j0 < n_seg; j0 += (BGZF_THREADS / 32) * 32) {
             const int j = j0 + lane;
             Seg s;
             s.pos = s.len = s.dist = s.cell = 0;
@@ -426,24 +441,6 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
                 if (fill > 0) atomicOr(&out[w], (uint32_t)acc);
             }
         }
-    } else {
-        // CRC32 of the block: 256-byte chunks from the end (slicing by four), each shifted across the bytes behind it
-        const int c = tid - EMIT_THREADS; // 0 .. 127
-        const int hi = L - c * 256, lo2 = max(hi - 256, 0);
-        uint32_t part = 0u;
-        if (hi > 0) {
-            uint32_t r = 0xFFFFFFFFu;
-            int k = lo2;
-            for (; k < hi && ((hi - k) & 3); ++k) r = crc_tab[(r ^ in[k]) & 0xFFu] ^ (r >> 8); // head bytes: the rest is whole words
-            for (; k < hi; k += 4) {
-                r ^= word_at(in, (uint32_t)k);
-                r = crc_tab[768 + (r & 0xFFu)] ^ crc_tab[512 + ((r >> 8) & 0xFFu)] ^ crc_tab[256 + ((r >> 16) & 0xFFu)] ^ crc_tab[r >> 24];
-            }
-            part = crc_mul(a.crc_pow[c * 8], ~r);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0 && part) atomicXor(&crc_s, part);
     }
     __syncthreads();
     // ---- the BGZF block: header, deflate data, CRC32, ISIZE -> its slot of the staging buffer

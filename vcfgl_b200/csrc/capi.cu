@@ -81,6 +81,7 @@ struct Slot {
     float ms[VGL_T_COUNT] = {};
     bool had_d2h = false;
     bool early_d2h = false; // the plane copies were enqueued by vgl_submit (tile kernels: the spans are known on the host)
+    int64_t stream_copied = 0; // VGL_HOST_BCF / BGZF: bytes of the record stream vgl_submit already copied on a prediction
     // vgl_native_draws() results (host)
     std::vector<int32_t> dr_depths;
     std::vector<int64_t> dr_off;
@@ -106,6 +107,7 @@ struct vgl_ctx {
     int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
     size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
     int64_t bgzf_max_blocks = 0;           // VGL_HOST_BGZF: blocks a full record stream makes
+    double stream_bytes_per_site = 0.0;    // VGL_HOST_BCF / BGZF: bytes per site of the last finished batch (predicts the next copy)
     uint32_t* d_crc_pow = nullptr;
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr, *d_qm_cdf = nullptr;
     float *d_m2_pure = nullptr, *d_m2_park = nullptr;
@@ -814,12 +816,13 @@ static int issue_d2h(vgl_ctx* ctx, Slot& s)
     cudaStream_t st = s.stream;
     const int64_t g_elems = s.h_totals[0], r_elems = s.h_totals[1];
     CK(cudaEventRecord(s.ev[EV_D2H0], st));
-    if (prm.host_output == VGL_HOST_BCF) {
-        const int64_t nb = s.h_totals[3];
-        if (nb > 0 && nb <= (int64_t)ctx->bcf_cap) CK(cudaMemcpyAsync(s.h_bcf, s.d_bcf, (size_t)nb, cudaMemcpyDeviceToHost, st));
-    } else if (prm.host_output == VGL_HOST_BGZF) {
-        const int64_t nb = s.h_totals[4];
-        if (nb > 0 && nb <= ctx->bgzf_max_blocks * (int64_t)BGZF_STRIDE) CK(cudaMemcpyAsync(s.h_bgzf, s.d_bgzf, (size_t)nb, cudaMemcpyDeviceToHost, st));
+    if (prm.host_output == VGL_HOST_BCF || prm.host_output == VGL_HOST_BGZF) {
+        const bool z = prm.host_output == VGL_HOST_BGZF;
+        const int64_t nb = s.h_totals[z ? 4 : 3], cap = z ? ctx->bgzf_max_blocks * (int64_t)BGZF_STRIDE : (int64_t)ctx->bcf_cap;
+        const int64_t done = s.stream_copied; // what vgl_submit copied on its prediction
+        if (nb > done && nb <= cap)
+            CK(cudaMemcpyAsync((z ? s.h_bgzf : s.h_bcf) + done, (z ? s.d_bgzf : s.d_bcf) + done, (size_t)(nb - done), cudaMemcpyDeviceToHost, st));
+        if (nb > 0 && s.n_sites > 0) ctx->stream_bytes_per_site = (double)nb / s.n_sites;
     } else {
         if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
         if (s.d_gp) CK(cudaMemcpyAsync(s.h_gp, s.d_gp, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
@@ -985,6 +988,16 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             ctx->launches += 4;
         }
         CK(cudaMemcpyAsync(s.h_rec_off, s.d_rec_off, ((size_t)n_sites + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        // The stream's size is only known on the device, but the previous batch predicts it well: that many bytes (+ 3 %) follow
+        // the kernels right away; vgl_wait copies what is left once it knows the size (a few per cent, or nothing).
+        s.stream_copied = 0;
+        if (ctx->stream_bytes_per_site > 0.0) {
+            const size_t cap = bgzf ? (size_t)ctx->bgzf_max_blocks * BGZF_STRIDE : ctx->bcf_cap;
+            size_t pred = (size_t)(ctx->stream_bytes_per_site * n_sites * 1.03) + 65536;
+            pred = std::min(pred, cap) & ~(size_t)15;
+            CK(cudaMemcpyAsync(bgzf ? s.h_bgzf : s.h_bcf, bgzf ? s.d_bgzf : s.d_bcf, pred, cudaMemcpyDeviceToHost, st));
+            s.stream_copied = (int64_t)pred;
+        }
     }
     CK(cudaGetLastError());
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
