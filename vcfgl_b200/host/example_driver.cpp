@@ -114,7 +114,25 @@ int main(int argc, char** argv)
         }
     }
     try {
-        vgl::BatchSimulator sim(p, [&](const vgl::SimRecordView& r) {
+        // VGL_DEVICES=0,1,...: consecutive batches alternate between the listed GPUs (vgl::MultiGpuSimulator); same output
+        std::vector<int> devs;
+        if (const char* dl = getenv("VGL_DEVICES"))
+            for (const char* q = dl; *q;) {
+                devs.push_back(atoi(q));
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+        if (devs.empty()) devs.push_back(0);
+        if (getenv("VGL_BATCH")) p.max_batch_sites = atoi(getenv("VGL_BATCH"));
+        if (getenv("VGL_SAMPLES_TAGS")) p.tag_mask |= VGL_TAG_QS | VGL_TAG_I16;
+        std::vector<int32_t> gdps;
+        if (const char* dps = getenv("VGL_GVCF_DPS"))
+            for (const char* q = dps; *q;) {
+                gdps.push_back(atoi(q));
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+        vgl::MultiGpuSimulator sim(p, devs, [&](const vgl::SimRecordView& r) {
             if (r.ret < 0) { printf("site %ld skipped (%d)\n", (long)r.site_id, r.ret); return; }
             printf("1\t%ld\t.\t%s\tDP=%d\tDP:AD:PL", (long)r.site_id + 1, r.alleles.c_str(), r.info_dp_arr[0]);
             for (int s = 0; s < r.nSamples; ++s) {
@@ -129,13 +147,23 @@ int main(int argc, char** argv)
             }
             printf("\n");
         });
+        std::vector<vgl_gvcf_site_in> where((size_t)n_sites);
+        if (!gdps.empty()) { // -doGVCF 1: blocks merged on the device, stitched across batches (and devices) on the host
+            for (int i = 0; i < n_sites; ++i) { where[(size_t)i].rid = 0; where[(size_t)i].pos = i + (i >= n_sites / 2 ? 3 : 0); } // one gap in the middle
+            sim.enable_gvcf(gdps, [&](void* u) { return *static_cast<vgl_gvcf_site_in*>(u); }, [&](const vgl::GvcfStitcher::Block& b) {
+                printf("1\t%ld\t%s\tBLOCK\tEND=%ld\tMIN_DP=%d\tn=%d\tDP:PL", (long)b.start + 1, b.alleles.c_str(), (long)b.end + 1, b.min_dp, b.n_members);
+                for (int s = 0; s < (int)b.dp.size(); ++s) printf("\t%d:%d,%d,%d", b.dp[s], b.pl[3 * s], b.pl[3 * s + 1], b.pl[3 * s + 2]);
+                printf("\n");
+            });
+        }
         std::vector<int> gts(2 * S);
+        const bool invar = getenv("VGL_INVARIANT") != nullptr; // mostly hom-ref sites (gVCF blocks form)
         for (int i = 0; i < n_sites; ++i) {
             for (int s = 0; s < S; ++s) { // A = REF, C = ALT (binary source, vcfgl.cpp:103-128)
-                gts[2 * s] = (i + s) % 3 == 2 ? 1 : 0;
-                gts[2 * s + 1] = (i + s) % 3 >= 1 ? 1 : 0;
+                gts[2 * s] = (!invar || i % 7 == 0) && (i + s) % 3 == 2 ? 1 : 0;
+                gts[2 * s + 1] = (!invar || i % 7 == 0) && (i + s) % 3 >= 1 ? 1 : 0;
             }
-            sim.push_site(gts.data());
+            sim.push_site(gts.data(), gdps.empty() ? nullptr : &where[(size_t)i]);
         }
         sim.finish();
     } catch (const vgl::Error& e) {

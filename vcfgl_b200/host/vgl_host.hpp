@@ -173,17 +173,37 @@ public:
     // params: fill from the parsed argStruct (io.h:40-148); host_output is forced on.  With VGL_HOST_NARROW the
     // integer planes cross PCIe as 8/16-bit values and are widened here, one site at a time, into the int32
     // arrays bcf_update_format_int32 takes (it narrows them again itself, htslib/vcf.c:2249-2294).
-    BatchSimulator(vgl_params params, Callback on_record) : prm_(params), cb_(std::move(on_record))
+    BatchSimulator(vgl_params params, Callback on_record) : BatchSimulator(params, std::vector<int>{params.device_id}, std::move(on_record)) {}
+
+    // Several GPUs of one box: one context per device, consecutive batches -- contiguous ranges of the global
+    // site index -- go to the devices in turn, and the results come back through the one callback strictly in site order (the
+    // ordered host-side merge; the gVCF block machine runs over the merged stream, so blocks cross device boundaries like
+    // batch boundaries).  Every draw is keyed by the global site index, so the records are the same bytes for any device list.
+    // A device may be listed more than once (several contexts on one GPU).
+    BatchSimulator(vgl_params params, const std::vector<int>& device_ids, Callback on_record) : prm_(params), cb_(std::move(on_record))
     {
+        if (device_ids.empty()) throw Error(VGL_EINVAL, "BatchSimulator: empty device list");
         prm_.abi_version = VGL_ABI_VERSION;
         if (prm_.host_output != VGL_HOST_NARROW) prm_.host_output = VGL_HOST_I32;
         if (prm_.n_slots < 2) prm_.n_slots = 2;
-        const int rc = vgl_create(&prm_, &ctx_);
-        if (rc != VGL_OK) throw Error(rc, std::string("vgl_create: ") + vgl_strerror(rc));
-        pending_.resize(prm_.n_slots);
+        for (int d : device_ids) {
+            vgl_params q = prm_;
+            q.device_id = d;
+            vgl_ctx* c = nullptr;
+            const int rc = vgl_create(&q, &c);
+            if (rc != VGL_OK) {
+                for (vgl_ctx* x : ctxs_) vgl_destroy(x);
+                throw Error(rc, std::string("vgl_create: ") + vgl_strerror(rc));
+            }
+            ctxs_.push_back(c);
+        }
+        ctx_ = ctxs_[0];
+        n_lanes_ = (int)ctxs_.size() * prm_.n_slots;
+        pending_.resize(n_lanes_);
         open_slot();
     }
-    ~BatchSimulator() { vgl_destroy(ctx_); }
+    ~BatchSimulator() { for (vgl_ctx* c : ctxs_) vgl_destroy(c); }
+    int n_devices() const { return (int)ctxs_.size(); }
     BatchSimulator(const BatchSimulator&) = delete;
     BatchSimulator& operator=(const BatchSimulator&) = delete;
 
@@ -206,6 +226,7 @@ public:
     // with push_site() inside one batch: a partially filled host batch is submitted first.
     void push_device_sites(vgl_parser* ps, const int32_t* row_map, int32_t n, uint8_t fill_gt, void* const* users = nullptr)
     {
+        if (ctxs_.size() != 1) throw Error(VGL_EINVAL, "push_device_sites: the parser belongs to one device; use one context");
         if (fill_ > 0) submit_current();
         check(vgl_place_rows(ctx_, cur_, ps, row_map, 0, n, fill_gt), "vgl_place_rows");
         Pending& p = pending_[cur_];
@@ -215,7 +236,7 @@ public:
         check(vgl_submit(ctx_, cur_, next_site_, n, nullptr, VGL_SUBMIT_GT_ON_DEVICE), "vgl_submit");
         p.in_flight = true;
         next_site_ += n;
-        cur_ = (cur_ + 1) % prm_.n_slots;
+        cur_ = (cur_ + 1) % n_lanes_;
         open_slot();
     }
     vgl_ctx* context() { return ctx_; }
@@ -238,7 +259,7 @@ public:
     void finish()
     {
         if (fill_ > 0) submit_current();
-        for (int k = 0; k < prm_.n_slots; ++k) drain((cur_ + k) % prm_.n_slots);
+        for (int k = 0; k < n_lanes_; ++k) drain((cur_ + k) % n_lanes_);
         if (stitch_) stitch_->finish(); // the block still open at the end (vcfgl.cpp:169-177)
     }
 
@@ -255,12 +276,15 @@ private:
     {
         if (rc != VGL_OK) throw Error(rc, std::string(what) + ": " + vgl_strerror(rc) + " (" + vgl_last_error(ctx_) + ")");
     }
+    // lane = (device, slot): consecutive batches take consecutive lanes, i.e. alternate between the devices
+    vgl_ctx* ctx_of(int lane) const { return ctxs_[(size_t)lane % ctxs_.size()]; }
+    int slot_of(int lane) const { return lane / (int)ctxs_.size(); }
 
     void open_slot()
     {
         drain(cur_); // the slot we are about to refill must have been delivered
         int64_t cap = 0;
-        check(vgl_input_buffer(ctx_, cur_, &in_, &cap), "vgl_input_buffer");
+        check(vgl_input_buffer(ctx_of(cur_), slot_of(cur_), &in_, &cap), "vgl_input_buffer");
         fill_ = 0;
         pending_[cur_].users.clear();
     }
@@ -269,11 +293,11 @@ private:
     {
         Pending& p = pending_[cur_];
         p.first = next_site_;
-        check(vgl_submit(ctx_, cur_, next_site_, fill_, nullptr, 0), "vgl_submit");
+        check(vgl_submit(ctx_of(cur_), slot_of(cur_), next_site_, fill_, nullptr, 0), "vgl_submit");
         p.in_flight = true;
         next_site_ += fill_;
-        cur_ = (cur_ + 1) % prm_.n_slots;
-        open_slot(); // delivers the older batch while this one runs on the GPU
+        cur_ = (cur_ + 1) % n_lanes_;
+        open_slot(); // delivers the oldest batch while this one runs on its GPU
     }
 
     void drain(int slot)
@@ -281,13 +305,13 @@ private:
         Pending& p = pending_[slot];
         if (!p.in_flight) return;
         vgl_batch_out out;
-        check(vgl_wait(ctx_, slot, &out), "vgl_wait");
+        check(vgl_wait(ctx_of(slot), slot_of(slot), &out), "vgl_wait");
         if (out.status != VGL_OK) throw Error(out.status, vgl_strerror(out.status));
         if (stitch_) {
             std::vector<vgl_gvcf_site_in> sin((size_t)out.n_sites);
             for (int i = 0; i < out.n_sites; ++i) sin[(size_t)i] = where_(p.users[(size_t)i]);
             vgl_gvcf_out g;
-            check(vgl_gvcf_merge(ctx_, slot, sin.data(), gvcf_dps_.data(), (int32_t)gvcf_dps_.size(), &g), "vgl_gvcf_merge");
+            check(vgl_gvcf_merge(ctx_of(slot), slot_of(slot), sin.data(), gvcf_dps_.data(), (int32_t)gvcf_dps_.size(), &g), "vgl_gvcf_merge");
             cur_out_ = &out;
             cur_pending_ = &p;
             stitch_->feed(g, sin.data(), out.n_sites, [&](GvcfStitcher::Block& b, int32_t site) {
@@ -370,7 +394,9 @@ private:
     std::vector<int32_t> w_dp_, w_pl_, w_ad_, w_adf_, w_adr_;
     vgl_params prm_;
     Callback cb_;
-    vgl_ctx* ctx_ = nullptr;
+    vgl_ctx* ctx_ = nullptr;      // = ctxs_[0]
+    std::vector<vgl_ctx*> ctxs_;  // one per device
+    int n_lanes_ = 0;             // devices x slots
     std::vector<Pending> pending_;
     std::unique_ptr<GvcfStitcher> stitch_;
     std::vector<int32_t> gvcf_dps_;
@@ -382,6 +408,9 @@ private:
     int32_t fill_ = 0;
     int64_t next_site_ = 0;
 };
+
+// the multi-GPU driver is the batch simulator with a device list (see its second constructor)
+using MultiGpuSimulator = BatchSimulator;
 
 // ---------------------------------------------------------------------------------------------------------------
 // VGL_HOST_BCF: the reference's whole write path for a site -- add_tags() (bcf_utils.cpp:426-507) and bcf_write()
