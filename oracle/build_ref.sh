@@ -7,6 +7,7 @@
 #
 #   oracle/_ref/vcfgl_ref        the reference CLI, unmodified
 #   oracle/_ref/vcfgl_ref_dump   same + replay-capture hooks (ref_dump_hooks.h)
+#   oracle/_ref/vcfgl_ref_vgl    same + the hot path answered by libvgl.so (ref_vgl_binding.h; INTEGRATION.md compiled)
 #   oracle/_ref/libref_errmod.so htslib errmod.c alone (errmod_init/errmod_cal)
 #
 # The reference's own build systems are NOT run (its Makefile does `git
@@ -93,6 +94,20 @@ g++ $CXXFLAGS -I"$HERE" -c "$TMP/vcfgl.cpp" -o "$OUT/obj/vcfgl_dump.o" &
 g++ $CXXFLAGS -I"$HERE" -c "$TMP/gl_methods.cpp" -o "$OUT/obj/gl_methods_dump.o" &
 wait
 g++ -o "$OUT/vcfgl_ref_dump" "$OUT/obj/vcfgl_dump.o" "$OUT/obj/io.o" "$OUT/obj/bcf_utils.o" "$OUT/obj/gl_methods_dump.o" "$OUT/obj/shared.o" $LIBS
+
+# (2b) the INTEGRATION.md binding compiled for real: the same instrumented copy with the hot path answered by libvgl.so
+#      (replay of the reference's own draws, oracle/ref_vgl_binding.h); needs the product library built first
+LIBVGL_DIR="$HERE/../vcfgl_b200"
+if [ -f "$LIBVGL_DIR/libvgl.so" ]; then
+  TMP2="$(mktemp -d)"
+  python3 "$HERE/patch_ref_for_dump.py" "$REF" "$TMP2" --vgl > /dev/null
+  g++ $CXXFLAGS -I"$HERE" -I"$HERE/../include" -c "$TMP2/vcfgl.cpp" -o "$OUT/obj/vcfgl_vgl.o"
+  g++ -o "$OUT/vcfgl_ref_vgl" "$OUT/obj/vcfgl_vgl.o" "$OUT/obj/io.o" "$OUT/obj/bcf_utils.o" "$OUT/obj/gl_methods_dump.o" "$OUT/obj/shared.o" $LIBS \
+      -L"$LIBVGL_DIR" -lvgl -Wl,-rpath,'$ORIGIN/../../vcfgl_b200'
+  rm -rf "$TMP2"
+else
+  echo "build_ref.sh: vcfgl_b200/libvgl.so not built yet; skipping vcfgl_ref_vgl" >&2
+fi
 
 # (3) errmod alone, for table-level cross-checks of the oracle restatement
 gcc -O2 -fPIC -shared -w -I"$GEN" -I"$H" "$H/errmod.c" "$H/hts_os.c" -o "$OUT/libref_errmod.so" -lm

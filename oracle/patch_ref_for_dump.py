@@ -11,11 +11,15 @@ Anchors are matched on exact statement text (not line numbers) and every
 anchor must match exactly the expected number of times, otherwise we abort --
 so a changed reference cannot be silently mis-instrumented.
 
-usage: patch_ref_for_dump.py REF_DIR OUT_DIR
+usage: patch_ref_for_dump.py REF_DIR OUT_DIR [--vgl]
+
+--vgl: additionally route the hot path through libvgl (oracle/ref_vgl_binding.h): the wrapper of
+simulate_record_values() replays the captured draws on the GPU and overwrites the record's arrays.
 """
 import sys, os, re
 
 ref, out = sys.argv[1], sys.argv[2]
+VGL = "--vgl" in sys.argv[3:]
 
 
 def patch(text, anchor, repl, count, mode="after"):
@@ -39,7 +43,7 @@ def patch(text, anchor, repl, count, mode="after"):
 # ---- vcfgl.cpp ----------------------------------------------------------
 src = open(os.path.join(ref, "vcfgl.cpp")).read()
 src = patch(src, '#include "gl_methods.h"',
-            '#define VGL_DUMP_NEED_SIMRECORD 1\n#include "ref_dump_hooks.h"', 1)
+            '#define VGL_DUMP_NEED_SIMRECORD 1\n#include "ref_dump_hooks.h"' + ('\n#include "ref_vgl_binding.h"' if VGL else ''), 1)
 # rename the hot-path entry and wrap it (vcfgl.cpp:327)
 a = "static int simulate_record_values(simRecord* sim) {"
 if src.count(a) != 1:
@@ -50,6 +54,7 @@ wrapper = (
     "    vgl_dump_begin(sim);\n"
     "    int vgl_ret = simulate_record_values_VGLORIG(sim);\n"
     "    vgl_dump_end(sim, vgl_ret);\n"
+    + ("    vgl_bind_replace(sim, vgl_ret);\n" if VGL else "") +
     "    return vgl_ret;\n"
     "}\n")
 src = patch(src, "static int simulate_record_true_values(simRecord* sim) {", wrapper, 1, mode="before")
