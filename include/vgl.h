@@ -39,7 +39,7 @@ extern "C" {
 
 #define VGL_ABI_VERSION 9 /* 2: VGL_HOST_NARROW; 3: VGL_HOST_BCF; 4: input path (vgl_parser_*, vgl_parse_vcf, vgl_place_rows); 5: vgl_gvcf_merge;
                           * 6: VGL_DEPTH_INF; 7: vgl_discordance; 8: vgl_parse_bcf 
-                          * 9: VGL_HOST_BGZF (device-side BGZF compression of the record stream) */
+                          * 9: VGL_HOST_BGZF (device-side BGZF compression of the record stream); vgl_bcf_site_in::fmt_off/fmt_len/n_fmt */
 
 #define VGL_MAX_ALLELES 5    /* shared.h:220 MAX_NALLELES */
 #define VGL_MAX_GENOTYPES 15 /* shared.h:228 MAX_NGTS */
@@ -112,6 +112,13 @@ typedef struct vgl_bcf_site_in {
     uint32_t n_info;              /* INFO fields the input record carries (they precede the simulator's) */
     uint32_t id_off, id_len;
     uint32_t flt_info_off, flt_info_len;
+    /* FORMAT blocks the input record carries besides GT, concatenated in the record's order (typed key, size/type descriptor,
+     * n_samples vectors each -- the bytes of in_rec->indiv.s with the GT block taken out); n_fmt of them.  The reference keeps
+     * them: bcf_update_genotypes(NULL) removes only GT (vcfgl.cpp:793), a block whose key one of the simulated tags has is
+     * replaced IN PLACE by that tag (an input FORMAT/DP), the other simulated tags follow the input's blocks
+     * (htslib/vcf.c bcf_update_format).  n_fmt = 0: the input FORMAT is GT alone. */
+    uint32_t fmt_off, fmt_len, n_fmt;
+    uint32_t _pad;
 } vgl_bcf_site_in;
 
 /* how the native simulator draws a cell (replay ignores this) */

@@ -116,7 +116,7 @@ def test_replay_records_equal_the_reference_file(cid):
     ctx.close()
 
 
-def _native_pair(argv, S, n_sites, batch, passthrough_seed=None, missing=0.0, fixed_depth=False):
+def _native_pair(argv, S, n_sites, batch, passthrough_seed=None, missing=0.0, fixed_depth=False, in_fmt_seed=None):
     """run the same native batch through VGL_HOST_I32 and VGL_HOST_BCF; returns (expected stream from the oracle, got)"""
     a = vargs.parse_args(argv.split())
     hap = synth.sfs_genotypes(n_sites, S, 4242, missing)
@@ -127,7 +127,8 @@ def _native_pair(argv, S, n_sites, batch, passthrough_seed=None, missing=0.0, fi
     rng = np.random.default_rng(passthrough_seed or 0)
     ref = capi.Context(capi.params_from_args(a, S, max_batch_sites=batch, n_slots=1, host_output=capi.HOST_I32, fixed_depth=fixed_depth))
     dev = capi.Context(capi.params_from_args(a, S, max_batch_sites=batch, n_slots=2, host_output=capi.HOST_BCF, bcf_dict=ids,
-                                             bcf_blob_bytes_per_site=64, fixed_depth=fixed_depth))
+                                             bcf_blob_bytes_per_site=64 + (12 * S + 32 if in_fmt_seed is not None else 0), fixed_depth=fixed_depth))
+    frng = np.random.default_rng(in_fmt_seed or 0)
     ftags, itags = bu.enabled_tags(a)
     want, got = [], []
     slot = 0
@@ -159,7 +160,21 @@ def _native_pair(argv, S, n_sites, batch, passthrough_seed=None, missing=0.0, fi
                 blob[o:o + len(pt)] = np.frombuffer(pt, np.uint8)
                 o += len(pt)
                 sin[k]["n_info"] = n_in
-            pts.append((idb, pt, n_in, int(sin[k]["qual_bits"])))
+            in_fmt = []
+            if in_fmt_seed is not None and frng.random() < 0.8:
+                # FORMAT blocks of the input record besides GT (the reference keeps them, vcfgl.cpp:793): an input DP (key of the
+                # simulated DP: replaced in place), GQ (int8 / int16), a float vector, a per-sample string -- in random order
+                cand = [(ids["DP"], bo.enc_int1(ids["DP"]) + bo.enc_vint(frng.integers(0, 90, S), 1)),
+                        (60, bo.enc_int1(60) + bo.enc_vint(frng.integers(0, 300 if frng.random() < 0.5 else 99, S), 1)),
+                        (61, bo.enc_int1(61) + bo.enc_size(2, bo.BT_FLOAT) + frng.random(2 * S).astype("<f4").tobytes()),
+                        (300, bo.enc_int1(300) + bo.enc_size(3, bo.BT_CHAR) + bytes(frng.integers(65, 90, 3 * S).astype(np.uint8)))]
+                pick = [cand[j] for j in frng.permutation(4)[:int(frng.integers(1, 5))]]
+                in_fmt = pick
+                fb = b"".join(x[1] for x in pick)
+                sin[k]["fmt_off"], sin[k]["fmt_len"], sin[k]["n_fmt"] = o, len(fb), len(pick)
+                blob[o:o + len(fb)] = np.frombuffer(fb, np.uint8)
+                o += len(fb)
+            pts.append((idb, pt, n_in, int(sin[k]["qual_bits"]), in_fmt))
         dev.submit(slot, s0, m)
         db = dev.wait(slot)
         assert db.status == 0 and rb.status == 0
@@ -175,8 +190,8 @@ def _native_pair(argv, S, n_sites, batch, passthrough_seed=None, missing=0.0, fi
             info = {t: {"DP": np.array([o_["info_dp"]]), "QS": o_["qs"], "I16": o_["i16"], "AD": o_["info_ad"], "ADF": o_["info_adf"],
                         "ADR": o_["info_adr"]}[t] for t in itags}
             alleles = bo.alleles_of_site(o_["n_alleles"], o_["alleles2acgt"], o_["info_dp"], a.do_unobserved, a.do_gvcf)
-            idb, pt, n_in, qb = pts[k]
-            want.append(bo.encode_record((s0 + k) % 3, 10 * (s0 + k) + 7, qb, idb, pt, n_in, alleles, S, dict_ids, fmt, info))
+            idb, pt, n_in, qb, in_fmt = pts[k]
+            want.append(bo.encode_record((s0 + k) % 3, 10 * (s0 + k) + 7, qb, idb, pt, n_in, alleles, S, dict_ids, fmt, info, in_fmt=in_fmt))
             got.append(bytes(db.bcf[lo:hi]))
         assert db.bcf_bytes == int(db.bcf_off[m])
         slot ^= 1
@@ -206,6 +221,16 @@ def test_native_all_tags_wide_vectors_and_passthrough():
     _check(want, got)
     r = bo.split_record(got[0])
     assert {t for _, _, t, _ in r["fmts"]} >= {bo.BT_INT16, bo.BT_FLOAT}
+
+
+@pytest.mark.parametrize("S,tags", [(7, "-addPL 1 -addFormatAD 1"), (33, "-addGP 1 -addPL 1 -addFormatAD 1 -addFormatADF 1 -addInfoDP 1"),
+                                    (120, "-addGL 1 -addPL 1 -addFormatDP 0")])
+def test_native_input_records_with_other_format_keys(S, tags):
+    # the input record carries FORMAT blocks besides GT (GT:DP:GQ ...): the reference keeps them in front of the simulated tags and
+    # replaces an input DP in place (layout pinned on the reference by tests/test_bcf_live_reference.py through the same oracle)
+    want, got = _native_pair("--seed 21 -d 6 -e 0.02 -GL 1 -doUnobserved 1 " + tags, S, 400, 128, passthrough_seed=3, in_fmt_seed=9)
+    _check(want, got)
+    assert any(len(bo.split_record(g)["fmts"]) > 4 for g in got)
 
 
 @pytest.mark.parametrize("S", [1, 2, 3, 5, 33])

@@ -68,11 +68,13 @@ class VglBcfDict(C.Structure):
 
 class VglBcfSiteIn(C.Structure):
     _fields_ = [("rid", C.c_int32), ("pos", C.c_int32), ("qual_bits", C.c_uint32), ("n_info", C.c_uint32),
-                ("id_off", C.c_uint32), ("id_len", C.c_uint32), ("flt_info_off", C.c_uint32), ("flt_info_len", C.c_uint32)]
+                ("id_off", C.c_uint32), ("id_len", C.c_uint32), ("flt_info_off", C.c_uint32), ("flt_info_len", C.c_uint32),
+                ("fmt_off", C.c_uint32), ("fmt_len", C.c_uint32), ("n_fmt", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 BCF_SITE_IN_DTYPE = np.dtype([("rid", "<i4"), ("pos", "<i4"), ("qual_bits", "<u4"), ("n_info", "<u4"), ("id_off", "<u4"),
-                              ("id_len", "<u4"), ("flt_info_off", "<u4"), ("flt_info_len", "<u4")])
+                              ("id_len", "<u4"), ("flt_info_off", "<u4"), ("flt_info_len", "<u4"), ("fmt_off", "<u4"), ("fmt_len", "<u4"),
+                              ("n_fmt", "<u4"), ("_pad", "<u4")])
 assert BCF_SITE_IN_DTYPE.itemsize == C.sizeof(VglBcfSiteIn)
 
 

@@ -19,7 +19,7 @@ namespace {
 
 enum { BT_NULL = 0, BT_INT8 = 1, BT_INT16 = 2, BT_INT32 = 3, BT_FLOAT = 5, BT_CHAR = 7 };
 enum { SEG_LIT = 0, SEG_BLOB = 1, SEG_VERB = 2, SEG_I8 = 3, SEG_I16 = 4 };
-constexpr int MAX_SEG = 24, LIT_CAP = 512;
+constexpr int MAX_SEG = 40, LIT_CAP = 512;
 
 using SiteMinMax = BcfSiteMinMax; // per tag: 0 dp, 1 pl, 2 ad, 3 adf, 4 adr
 
@@ -115,6 +115,29 @@ struct Builder {
     }
 };
 
+// typed integer of a BCF stream (bcf_enc_int1's output): advances p
+__device__ __forceinline__ int32_t read_typed_int(const uint8_t*& p)
+{
+    const int t = *p++ & 0xF;
+    int32_t v = 0;
+    if (t == BT_INT8) { v = (int8_t)p[0]; p += 1; }
+    else if (t == BT_INT16) { v = (int16_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8)); p += 2; }
+    else { v = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24)); p += 4; }
+    return v;
+}
+// one FORMAT block of the input record: key, values per sample x width -> bytes of the whole block
+__device__ __forceinline__ uint32_t in_fmt_block(const uint8_t* p0, int S, int32_t& key)
+{
+    const uint8_t* p = p0;
+    key = read_typed_int(p);
+    const int d = *p++;
+    int n = d >> 4;
+    const int ty = d & 0xF;
+    if (n == 15) n = read_typed_int(p);
+    const int w = ty == BT_INT8 || ty == BT_CHAR ? 1 : (ty == BT_INT16 ? 2 : (ty == BT_NULL ? 0 : 4));
+    return (uint32_t)(p - p0) + (uint32_t)S * (uint32_t)n * (uint32_t)w;
+}
+
 // Lays out site `i`'s record.  Returns its length; l_shared / l_indiv as bcf_write() counts them.
 __device__ uint32_t bcf_layout(const BcfArgs& a, int i, const vgl_site_out& s, const SiteMinMax& mm, Builder& b)
 {
@@ -123,8 +146,23 @@ __device__ uint32_t bcf_layout(const BcfArgs& a, int i, const vgl_site_out& s, c
     const uint32_t t = a.tag_mask;
     const int n_info_sim = !!(t & VGL_TAG_INFO_DP) + !!(t & VGL_TAG_QS) + !!(t & VGL_TAG_I16) + !!(t & VGL_TAG_INFO_AD) +
                            !!(t & VGL_TAG_INFO_ADF) + !!(t & VGL_TAG_INFO_ADR);
-    const int n_fmt = !!(t & VGL_TAG_FMT_DP) + !!(t & VGL_TAG_GL) + !!(t & VGL_TAG_PL) + !!(t & VGL_TAG_GP) + !!(t & VGL_TAG_FMT_AD) +
-                      !!(t & VGL_TAG_FMT_ADF) + !!(t & VGL_TAG_FMT_ADR);
+    // the simulator's FORMAT tags in add_tags() order, and which of them take the slot of an input block with the same key
+    const uint32_t fbit[7] = {VGL_TAG_FMT_DP, VGL_TAG_GL, VGL_TAG_PL, VGL_TAG_GP, VGL_TAG_FMT_AD, VGL_TAG_FMT_ADF, VGL_TAG_FMT_ADR};
+    const int32_t fkey[7] = {a.dict.dp, a.dict.gl, a.dict.pl, a.dict.gp, a.dict.ad, a.dict.adf, a.dict.adr};
+    uint32_t placed = 0u;
+    if (in.n_fmt) {
+        const uint8_t* q = a.blob + in.fmt_off;
+        for (uint32_t k = 0; k < in.n_fmt; ++k) {
+            int32_t key;
+            const uint32_t len = in_fmt_block(q, S, key);
+            for (int f = 0; f < 7; ++f)
+                if ((t & fbit[f]) && fkey[f] == key) placed |= 1u << f;
+            q += len;
+        }
+    }
+    int n_fmt = (int)in.n_fmt;
+    for (int f = 0; f < 7; ++f)
+        if ((t & fbit[f]) && !((placed >> f) & 1u)) ++n_fmt;
     // ---- the 32 fixed bytes (htslib/vcf.c:1984-1993); the two lengths are patched at the end
     b.put32(0); b.put32(0);
     b.put32((uint32_t)in.rid);
@@ -176,13 +214,32 @@ __device__ uint32_t bcf_layout(const BcfArgs& a, int i, const vgl_site_out& s, c
         if (b.planes && b.planes->n < 7) { b.planes->off[b.planes->n] = b.pos; b.planes->cell[b.planes->n] = (uint16_t)(nps * 4); ++b.planes->n; }
         b.ext(SEG_VERB, src, (uint32_t)S * nps * 4u);
     };
-    if (t & VGL_TAG_FMT_DP) fmt_int(a.dict.dp, a.dp + (size_t)i * S, 1, 0);
-    if (t & VGL_TAG_GL) fmt_float(a.dict.gl, a.gl + s.g_off, G);
-    if (t & VGL_TAG_PL) fmt_int(a.dict.pl, a.pl + s.g_off, G, 1);
-    if (t & VGL_TAG_GP) fmt_float(a.dict.gp, a.gp + s.g_off, G);
-    if (t & VGL_TAG_FMT_AD) fmt_int(a.dict.ad, a.ad + s.r_off, A, 2);
-    if (t & VGL_TAG_FMT_ADF) fmt_int(a.dict.adf, a.adf + s.r_off, A, 3);
-    if (t & VGL_TAG_FMT_ADR) fmt_int(a.dict.adr, a.adr + s.r_off, A, 4);
+    auto put_tag = [&](int f) {
+        switch (f) {
+        case 0: fmt_int(a.dict.dp, a.dp + (size_t)i * S, 1, 0); break;
+        case 1: fmt_float(a.dict.gl, a.gl + s.g_off, G); break;
+        case 2: fmt_int(a.dict.pl, a.pl + s.g_off, G, 1); break;
+        case 3: fmt_float(a.dict.gp, a.gp + s.g_off, G); break;
+        case 4: fmt_int(a.dict.ad, a.ad + s.r_off, A, 2); break;
+        case 5: fmt_int(a.dict.adf, a.adf + s.r_off, A, 3); break;
+        default: fmt_int(a.dict.adr, a.adr + s.r_off, A, 4); break;
+        }
+    };
+    if (in.n_fmt) { // the input's blocks first, in their order: a simulated tag with the same key takes the block's slot
+        const uint8_t* q = a.blob + in.fmt_off;
+        for (uint32_t k = 0; k < in.n_fmt; ++k) {
+            int32_t key;
+            const uint32_t len = in_fmt_block(q, S, key);
+            int hit = -1;
+            for (int f = 0; f < 7; ++f)
+                if ((t & fbit[f]) && fkey[f] == key) hit = f;
+            if (hit >= 0) put_tag(hit);
+            else b.ext(SEG_BLOB, q, len);
+            q += len;
+        }
+    }
+    for (int f = 0; f < 7; ++f)
+        if ((t & fbit[f]) && !((placed >> f) & 1u)) put_tag(f);
     const uint32_t l_indiv = b.pos - 8 - l_shared;
     if (b.lit) {
         const uint32_t v[2] = {l_shared, l_indiv};

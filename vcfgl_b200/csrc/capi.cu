@@ -912,8 +912,32 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     if (bcf) {
         for (int32_t i = 0; i < n_sites; ++i) { // byte ranges must lie inside the blob
             const vgl_bcf_site_in& b = s.h_bcf_in[i];
-            if ((size_t)b.id_off + b.id_len > ctx->blob_cap || (size_t)b.flt_info_off + b.flt_info_len > ctx->blob_cap)
+            if ((size_t)b.id_off + b.id_len > ctx->blob_cap || (size_t)b.flt_info_off + b.flt_info_len > ctx->blob_cap ||
+                (size_t)b.fmt_off + b.fmt_len > ctx->blob_cap)
                 return fail(ctx, VGL_EINVAL, "vgl_bcf_site_in: byte range outside the pass-through blob");
+            if (b.n_fmt > 8 || (b.n_fmt == 0) != (b.fmt_len == 0)) return fail(ctx, VGL_EINVAL, "vgl_bcf_site_in: at most 8 input FORMAT blocks, n_fmt and fmt_len both zero or both set");
+            if (b.n_fmt) { // the blocks must tile the byte range exactly
+                const uint8_t *q = s.h_blob + b.fmt_off, *end = q + b.fmt_len;
+                for (uint32_t k = 0; k < b.n_fmt && q < end; ++k) {
+                    if (end - q < 2) { q = end + 1; break; }
+                    const uint8_t* r = q;
+                    const int tk = *r & 0xF;
+                    r += 1 + (tk == 1 ? 1 : (tk == 2 ? 2 : 4));
+                    if (r >= end) { q = end + 1; break; }
+                    const int d = *r++;
+                    long n = d >> 4;
+                    const int ty = d & 0xF;
+                    if (n == 15) {
+                        if (r >= end) { q = end + 1; break; }
+                        const int tn = *r & 0xF;
+                        n = tn == 1 ? (int8_t)r[1] : (tn == 2 ? (int16_t)(r[1] | (r[2] << 8)) : (int32_t)(r[1] | (r[2] << 8) | (r[3] << 16) | ((uint32_t)r[4] << 24)));
+                        r += 1 + (tn == 1 ? 1 : (tn == 2 ? 2 : 4));
+                    }
+                    const int w = ty == 1 || ty == 7 ? 1 : (ty == 2 ? 2 : (ty == 0 ? 0 : 4));
+                    q = r + (long)S * n * w;
+                }
+                if (q != end) return fail(ctx, VGL_EINVAL, "vgl_bcf_site_in: the input FORMAT blocks do not tile fmt_len bytes");
+            }
         }
         CK(cudaMemcpyAsync(s.d_bcf_in, s.h_bcf_in, (size_t)n_sites * sizeof(vgl_bcf_site_in), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(s.d_blob, s.h_blob, ctx->blob_cap, cudaMemcpyHostToDevice, st));

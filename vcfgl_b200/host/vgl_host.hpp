@@ -445,10 +445,13 @@ public:
     // One input record (after check_rec_alleles, vcfgl.cpp:75-163).  id / flt_info: with in_rec unpacked,
     //   id       = in_rec->shared.s[0 .. unpack_size[0])                              (nullptr / 0: ".")
     //   flt_info = in_rec->shared.s[unpack_size[0] + unpack_size[1] .. shared.l)      (nullptr / 0: FILTER ".", no INFO)
+    //   fmt      = the FORMAT blocks of the input record besides GT, in its order: in_rec->indiv.s with the GT block taken out
+    //              (typed key, descriptor, n_samples vectors each), n_fmt of them                (nullptr / 0: FORMAT is GT alone)
     void push_site(const int* true_gts_acgt_int, int32_t rid, int32_t pos, float qual, const uint8_t* id, uint32_t id_len,
-                   const uint8_t* flt_info, uint32_t flt_info_len, uint32_t n_info)
+                   const uint8_t* flt_info, uint32_t flt_info_len, uint32_t n_info, const uint8_t* fmt = nullptr, uint32_t fmt_len = 0,
+                   uint32_t n_fmt = 0)
     {
-        if (blob_fill_ + id_len + flt_info_len > (size_t)blob_cap_) {
+        if (blob_fill_ + id_len + flt_info_len + fmt_len > (size_t)blob_cap_) {
             if (fill_ == 0) throw Error(VGL_EINVAL, "pass-through fields of one record exceed the blob (raise bcf_blob_bytes_per_site)");
             submit_current();
         }
@@ -470,6 +473,12 @@ public:
         r.flt_info_len = flt_info_len;
         if (flt_info_len) memcpy(blob_ + blob_fill_, flt_info, flt_info_len);
         blob_fill_ += flt_info_len;
+        r.fmt_off = (uint32_t)blob_fill_;
+        r.fmt_len = fmt_len;
+        r.n_fmt = n_fmt;
+        r._pad = 0;
+        if (fmt_len) memcpy(blob_ + blob_fill_, fmt, fmt_len);
+        blob_fill_ += fmt_len;
         if (++fill_ == prm_.max_batch_sites) submit_current();
     }
 
