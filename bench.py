@@ -429,7 +429,7 @@ def gpu_arm(opt):
         r = b.raw
         if b.bgzf is not None:      # VGL_HOST_BGZF: the compressed record stream, the record offsets, the per-site records
             return int(b.bgzf_bytes + 8 * (b.n_sites + 1) + b.n_sites * capi.SITE_DTYPE.itemsize)
-        if b.bcf_off is not None:   # VGL_HOST_BCF: the record stream, its offsets, the per-site records
+        if b.bcf_off is not None or b.bcf is not None:   # VGL_HOST_BCF: the record stream, its offsets, the per-site records
             return int(b.bcf_bytes + 8 * (b.n_sites + 1) + b.n_sites * capi.SITE_DTYPE.itemsize)
         w = (b.narrow_bits // 8) if b.narrow_bits else 4          # DP / AD element width
         g_up, r_up = b.n_sites * ((S * 15 + 3) & ~3), b.n_sites * ((S * 5 + 3) & ~3)   # tile kernels: whole spans
@@ -460,7 +460,9 @@ def gpu_arm(opt):
 
     def e2e_run(mode):
         ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=E_SLOTS, device_id=local, host_output=mode,
-                                                 bcf_dict=dict(DP=1, GL=2, PL=3, GP=4, AD=5, ADF=6, ADR=7, QS=8, I16=9)))
+                                                 bcf_dict=dict(DP=1, GL=2, PL=3, GP=4, AD=5, ADF=6, ADR=7, QS=8, I16=9, END=10, MIN_DP=11)))
+        if a.do_gvcf and mode == capi.HOST_BCF:
+            ctx.set_gvcf_dps([int(x) for x in a.gvcf_dps.split(",")])
         for s in range(E_SLOTS):
             ctx.set_stream(s, streams[s].cuda_stream)
         bufs = [ctx.input_buffer(s) for s in range(E_SLOTS)]
@@ -485,7 +487,12 @@ def gpu_arm(opt):
     e2e_value, d2h_bytes, e2e_launches = e2e_nar, d2h_nar, nl_nar
     e2e_planes = e2e_narrow["planes"]
     e2e_bcf = None
-    if not a.do_gvcf:   # serialised BCF records (the gVCF block merger consumes arrays)
+    if a.do_gvcf and a.do_unobserved in (1, 2):   # gVCF: block merger + serialisation on the device, seams stitched by vgl_wait
+        v, nb, nl = e2e_run(capi.HOST_BCF)
+        e2e_bcf = {"value": v, "d2h_bytes_per_step": nb * Le, "gpu_launches": int(nl),
+                   "planes": "VGL_HOST_BCF with -doGVCF: regular and block records serialised on the device (k_gvcf_* + k_bcf_*), byte-identical "
+                             "to the reference's -O u stream"}
+    if not a.do_gvcf:   # serialised BCF records
         v, nb, nl = e2e_run(capi.HOST_BCF)
         e2e_bcf = {"value": v, "d2h_bytes_per_step": nb * Le, "gpu_launches": int(nl),
                    "planes": "VGL_HOST_BCF: complete BCF records serialised on the device (k_bcf_plan/scan/emit), byte-identical to "

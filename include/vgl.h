@@ -98,6 +98,7 @@ enum { VGL_HOST_NONE = 0,    /* nothing but the totals and the status word: resu
  * (FORMAT and INFO tags of the same name share one id).  Only ids of tags enabled in tag_mask are read. */
 typedef struct vgl_bcf_dict {
     int32_t dp, gl, pl, gp, ad, adf, adr, qs, i16;
+    int32_t end, min_dp; /* -doGVCF 1: INFO/END and INFO/MIN_DP of the block records (bcf_utils.cpp:905-912) */
 } vgl_bcf_dict;
 
 /* VGL_HOST_BCF: what the input record passes through to the output record unchanged (the reference edits a bcf_copy of
@@ -239,6 +240,13 @@ typedef struct vgl_batch_out {
     const uint8_t* bgzf;
     int64_t bgzf_bytes;
     int32_t bgzf_blocks;
+    /* VGL_HOST_BCF with -doGVCF 1 (after vgl_set_gvcf_dps): the batch went through the block merger on the device
+     * (prepare_gvcf_block, bcf_utils.cpp:662-942) and `bcf` holds its n_recs records in output order -- regular records and
+     * block records (END, MIN_DP, the founder's alleles and QS, per-sample minima of PL and DP) -- with the seam to the
+     * neighbouring batches already stitched: a block open at the end of a batch is held back and comes out (merged, if the
+     * next batch continues it) in front of the next batch's records, or from vgl_gvcf_flush() after the last batch.  Batches
+     * must be waited in submission order; bcf_off is NULL in this mode. */
+    int32_t n_recs;
 } vgl_batch_out;
 
 /* timing of a slot's last completed submit, CUDA events on the slot's stream (ms) */
@@ -430,6 +438,12 @@ typedef struct vgl_gvcf_out {
     const int32_t* pl;        /* [n_blocks][n_samples][3], NULL without the PL tag */
     float ms_kernels;
 } vgl_gvcf_out;
+
+/* VGL_HOST_BCF with -doGVCF 1: the ascending --gvcf-dps thresholds, once, before the first vgl_submit; and, after the last
+ * vgl_wait, the block that was still open (write_record_values(NULL), vcfgl.cpp:169-177): *n_bytes = 0 when there is none.
+ * The returned bytes stay valid until the next call on the context. */
+int vgl_set_gvcf_dps(vgl_ctx* ctx, const int32_t* gvcf_dps, int32_t n_gvcf_dps);
+int vgl_gvcf_flush(vgl_ctx* ctx, const uint8_t** rec, int64_t* n_bytes);
 
 /* synchronous; sites: host array [n_sites of the slot's last batch]; gvcf_dps: ascending thresholds of --gvcf-dps */
 int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* sites, const int32_t* gvcf_dps, int32_t n_gvcf_dps, vgl_gvcf_out* out);

@@ -27,7 +27,7 @@ SUBMIT_GT_ON_DEVICE = 1
 F32_MISSING_BITS = 0x7F800001
 I32_MISSING = -(2 ** 31)
 
-EXPORTS = ["vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_bcf_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
+EXPORTS = ["vgl_set_gvcf_dps", "vgl_gvcf_flush", "vgl_create", "vgl_destroy", "vgl_input_buffer", "vgl_bcf_input_buffer", "vgl_submit", "vgl_wait", "vgl_set_stream",
            "vgl_slot_timing", "vgl_copy_sites", "vgl_native_draws", "vgl_selftest", "vgl_launch_count", "vgl_algorithmic_bytes", "vgl_strerror",
            "vgl_last_error", "vgl_abi_version", "vgl_native_kernels",
            "vgl_gvcf_merge", "vgl_discordance", "vgl_parser_create", "vgl_parser_destroy", "vgl_parser_text_buffer", "vgl_parse_vcf", "vgl_parse_bcf", "vgl_parser_rows", "vgl_place_rows"]
@@ -63,7 +63,7 @@ class VglParseOut(C.Structure):
 
 
 class VglBcfDict(C.Structure):
-    _fields_ = [(k, C.c_int32) for k in ("dp", "gl", "pl", "gp", "ad", "adf", "adr", "qs", "i16")]
+    _fields_ = [(k, C.c_int32) for k in ("dp", "gl", "pl", "gp", "ad", "adf", "adr", "qs", "i16", "end", "min_dp")]
 
 
 class VglBcfSiteIn(C.Structure):
@@ -121,7 +121,7 @@ class VglBatchOut(C.Structure):
                 ("narrow_bits", C.c_int32), ("pl_u8", C.c_void_p), ("dp_n", C.c_void_p), ("ad_n", C.c_void_p),
                 ("adf_n", C.c_void_p), ("adr_n", C.c_void_p),
                 ("bcf", C.c_void_p), ("bcf_off", C.c_void_p), ("bcf_bytes", C.c_int64),
-                ("bgzf", C.c_void_p), ("bgzf_bytes", C.c_int64), ("bgzf_blocks", C.c_int32)]
+                ("bgzf", C.c_void_p), ("bgzf_bytes", C.c_int64), ("bgzf_blocks", C.c_int32), ("n_recs", C.c_int32)]
 
 
 class VglDraws(C.Structure):
@@ -173,6 +173,8 @@ def load():
     L.vgl_last_error.restype = C.c_char_p
     L.vgl_abi_version.restype = C.c_int
     L.vgl_gvcf_merge.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(VglGvcfOut)]
+    L.vgl_set_gvcf_dps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.vgl_gvcf_flush.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.vgl_discordance.argtypes = [C.c_void_p, C.c_int, C.POINTER(VglDiscordanceOut)]
     L.vgl_parser_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
     L.vgl_parser_destroy.argtypes = [C.c_void_p]
@@ -272,8 +274,10 @@ class Batch:
         self.bcf = self.bcf_off = None
         self.bcf_bytes = int(out.bcf_bytes)
         self.bgzf, self.bgzf_bytes, self.bgzf_blocks = None, int(out.bgzf_bytes), int(out.bgzf_blocks)
-        if out.bcf_off and host:
-            self.bcf_off = np.ctypeslib.as_array(C.cast(out.bcf_off, C.POINTER(C.c_int64)), shape=(out.n_sites + 1,))
+        self.n_recs = int(out.n_recs)
+        if (out.bcf_off or out.bcf) and host:
+            if out.bcf_off:
+                self.bcf_off = np.ctypeslib.as_array(C.cast(out.bcf_off, C.POINTER(C.c_int64)), shape=(out.n_sites + 1,))
             if out.bcf:
                 self.bcf = (np.ctypeslib.as_array(C.cast(out.bcf, C.POINTER(C.c_uint8)), shape=(self.bcf_bytes,))
                             if self.bcf_bytes > 0 else np.zeros(0, np.uint8))
@@ -479,6 +483,17 @@ class Context:
         return dict(recs=arr(out.recs, out.n_recs, GVCF_REC_DTYPE), dp=arr(out.dp, out.n_blocks * S, np.int32).reshape(-1, S),
                     pl=arr(out.pl, out.n_blocks * S * 3, np.int32).reshape(-1, S, 3) if out.pl else None,
                     n_blocks=out.n_blocks, ms_kernels=out.ms_kernels)
+
+    def set_gvcf_dps(self, gvcf_dps):
+        """HOST_BCF with -doGVCF: the --gvcf-dps thresholds, before the first submit"""
+        d = np.ascontiguousarray(gvcf_dps, np.int32)
+        self._ck(self.L.vgl_set_gvcf_dps(self.h, d.ctypes.data, len(d)))
+
+    def gvcf_flush(self) -> bytes:
+        """HOST_BCF with -doGVCF: the block record still open after the last batch (b"" when there is none)"""
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.L.vgl_gvcf_flush(self.h, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value) if n.value else b""
 
     def discordance(self, slot: int) -> dict:
         """genotype-call discordance of the slot's last (waited) batch: {"hom": [cells, discordant], "het": [...], "ms_kernel"}"""

@@ -248,6 +248,52 @@ __device__ uint32_t bcf_layout(const BcfArgs& a, int i, const vgl_site_out& s, c
     return b.pos;
 }
 
+// A gVCF block record (GVCF_FLUSH_BLOCK, bcf_utils.cpp:896-925): a cleared record with the founder's contig / position /
+// alleles, rlen = END - start, INFO END (blocks longer than one position), MIN_DP, QS (the founder's), FORMAT PL then DP (the
+// per-sample minima over the members, reduced by k_gvcf_reduce).  `s` is the founder's site record.
+__device__ uint32_t bcf_layout_block(const BcfArgs& a, const vgl_gvcf_rec& r, const vgl_site_out& s, const SiteMinMax& mm, Builder& b)
+{
+    const int S = a.S;
+    const vgl_bcf_site_in first = a.site_in[r.first_site], last = a.site_in[r.last_site];
+    const int32_t end1 = last.pos + 1; // 1-based END
+    const bool has_end = end1 - first.pos >= 2, has_qs = (a.tag_mask & VGL_TAG_QS) != 0, has_pl = a.blk_pl != nullptr;
+    b.put32(0); b.put32(0);
+    b.put32((uint32_t)first.rid);
+    b.put32((uint32_t)first.pos);
+    b.put32((uint32_t)(end1 - first.pos)); // rlen
+    b.put32(VGL_F32_MISSING_BITS);         // QUAL of a cleared record
+    b.put16((uint32_t)((has_end ? 1 : 0) + 1 + (has_qs ? 1 : 0)));
+    b.put16((uint32_t)s.n_alleles);
+    b.put32(((uint32_t)((has_pl ? 1 : 0) + 1) << 24) | ((uint32_t)S & 0xFFFFFFu));
+    b.put(0x07); // ID "."
+    const bool nonref_name = a.do_unobserved == 2 || a.do_unobserved == 5;
+    for (int k = 0; k < s.n_alleles; ++k) {
+        const int code = s.alleles2acgt[k];
+        if (code == 4) { if (nonref_name) b.str("<NON_REF>", 9); else b.str("<*>", 3); }
+        else { const char c = "ACGT"[code & 3]; b.str(&c, 1); }
+    }
+    b.put(0x00); // FILTER: none
+    if (has_end) { b.int1(a.dict.end); b.int1(end1); }
+    b.int1(a.dict.min_dp); b.int1(r.min_dp);
+    if (has_qs) { b.int1(a.dict.qs); b.vfloat_small(s.qs, s.n_alleles); }
+    const uint32_t l_shared = b.pos - 8;
+    auto fmt_int = [&](int32_t key, const int32_t* src, int nps, int which) {
+        b.int1(key);
+        const int ty = int_type(mm.mn[which], mm.mx[which]);
+        b.size(nps, ty);
+        if (b.planes && b.planes->n < 7) { b.planes->off[b.planes->n] = b.pos; b.planes->cell[b.planes->n] = (uint16_t)(nps * type_width(ty)); ++b.planes->n; }
+        b.ext(ty == BT_INT8 ? SEG_I8 : (ty == BT_INT16 ? SEG_I16 : SEG_VERB), src, (uint32_t)S * nps * type_width(ty));
+    };
+    if (has_pl) fmt_int(a.dict.pl, a.blk_pl + (size_t)r.plane * S * 3, 3, 1);
+    fmt_int(a.dict.dp, a.blk_dp + (size_t)r.plane * S, 1, 0);
+    const uint32_t l_indiv = b.pos - 8 - l_shared;
+    if (b.lit) {
+        const uint32_t v[2] = {l_shared, l_indiv};
+        for (int k = 0; k < 8; ++k) b.lit[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+    }
+    return b.pos;
+}
+
 __device__ __forceinline__ void mm_update(int32_t v, int32_t& mn, int32_t& mx)
 {
     if (v != VGL_I32_MISSING && v != VGL_I32_MISSING + 1) { mn = min(mn, v); mx = max(mx, v); }
@@ -255,16 +301,54 @@ __device__ __forceinline__ void mm_update(int32_t v, int32_t& mn, int32_t& mx)
 
 __global__ void __launch_bounds__(128) k_bcf_plan(const BcfArgs a)
 {
-    const int i = blockIdx.x, tid = threadIdx.x;
+    const int rk = blockIdx.x, tid = threadIdx.x; // record index: the site itself, or (-doGVCF) the merger's k-th record
     __shared__ vgl_site_out s;
     __shared__ int32_t red[2][5][4];
-    if (tid == 0) s = a.sites[i];
-    __syncthreads();
-    if (s.skip_code != 0) {
-        if (tid == 0) a.rec_len[i] = 0u;
+    __shared__ vgl_gvcf_rec grec;
+    if (a.recs && rk >= a.rec_counts[0]) {
+        if (tid == 0) a.rec_len[rk] = 0u;
         return;
     }
+    if (tid == 0) {
+        if (a.recs) grec = a.recs[rk];
+        s = a.sites[a.recs ? a.recs[rk].first_site : rk];
+    }
+    __syncthreads();
+    const int i = a.recs ? grec.first_site : rk;
     const int S = a.S;
+    if (a.recs && grec.n_members > 0) { // block record: min / max of its DP and PL planes
+        int32_t mn[2] = {INT32_MAX, INT32_MAX}, mx[2] = {INT32_MIN, INT32_MIN};
+        const int32_t* pd = a.blk_dp + (size_t)grec.plane * S;
+        for (int k = tid; k < S; k += 128) mm_update(pd[k], mn[0], mx[0]);
+        if (a.blk_pl) {
+            const int32_t* pp = a.blk_pl + (size_t)grec.plane * S * 3;
+            for (int k = tid; k < 3 * S; k += 128) mm_update(pp[k], mn[1], mx[1]);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
+            mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+            if ((tid & 31) == 0) { red[0][k][tid >> 5] = mn[k]; red[1][k][tid >> 5] = mx[k]; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            SiteMinMax mm;
+            for (int k = 0; k < 5; ++k) { mm.mn[k] = INT32_MAX; mm.mx[k] = INT32_MIN; }
+            for (int k = 0; k < 2; ++k) {
+                mm.mn[k] = min(min(red[0][k][0], red[0][k][1]), min(red[0][k][2], red[0][k][3]));
+                mm.mx[k] = max(max(red[1][k][0], red[1][k][1]), max(red[1][k][2], red[1][k][3]));
+            }
+            a.minmax[rk] = mm;
+            Builder b;
+            b.lit = nullptr;
+            a.rec_len[rk] = bcf_layout_block(a, grec, s, mm, b);
+        }
+        return;
+    }
+    if (s.skip_code != 0) {
+        if (tid == 0) a.rec_len[rk] = 0u;
+        return;
+    }
     const int64_t nG = (int64_t)S * s.n_genotypes, nA = (int64_t)S * s.n_alleles;
     int32_t mn[5], mx[5];
 #pragma unroll
@@ -297,10 +381,10 @@ __global__ void __launch_bounds__(128) k_bcf_plan(const BcfArgs a)
             mm.mn[k] = min(min(red[0][k][0], red[0][k][1]), min(red[0][k][2], red[0][k][3]));
             mm.mx[k] = max(max(red[1][k][0], red[1][k][1]), max(red[1][k][2], red[1][k][3]));
         }
-        a.minmax[i] = mm;
+        a.minmax[rk] = mm;
         Builder b;
         b.lit = nullptr;
-        a.rec_len[i] = bcf_layout(a, i, s, mm, b);
+        a.rec_len[rk] = bcf_layout(a, i, s, mm, b);
     }
 }
 
@@ -312,7 +396,7 @@ __global__ void __launch_bounds__(1024) k_bcf_scan(const BcfArgs a)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < a.n_sites; base += 1024) {
+    for (int base = 0; base < a.n_sites; base += 1024) { // slots beyond the merger's record count hold length 0
         const int i = base + tid;
         const long long v = i < a.n_sites ? (long long)a.rec_len[i] : 0;
         long long x = v;
@@ -375,17 +459,22 @@ __device__ __forceinline__ uint32_t seg_byte(const SegView& v, int sg, uint32_t 
 
 __global__ void __launch_bounds__(256) k_bcf_emit(const BcfArgs a)
 {
-    const int i = blockIdx.x, tid = threadIdx.x;
+    const int rk = blockIdx.x, tid = threadIdx.x; // record index (see k_bcf_plan)
     __shared__ vgl_site_out s;
     __shared__ uint32_t seg_start[MAX_SEG + 1], seg_kind[MAX_SEG];
     __shared__ unsigned long long seg_src[MAX_SEG];
     __shared__ __align__(4) uint8_t lit[LIT_CAP];
     __shared__ int nseg_s;
-    const uint32_t len = a.rec_len[i];
+    const uint32_t len = a.rec_len[rk];
     if (len == 0) return;
-    const long long off = a.rec_off[i];
+    const long long off = a.rec_off[rk];
     if (off + len > a.out_cap) return; // status already raised by the scan
     if (tid == 0) {
+        vgl_gvcf_rec grec;
+        grec.n_members = 0;
+        grec.first_site = rk;
+        if (a.recs) grec = a.recs[rk];
+        const int i = grec.first_site;
         s = a.sites[i];
         Builder b;
         b.lit = lit; b.seg_start = seg_start; b.seg_kind = seg_kind; b.seg_src = seg_src;
@@ -393,8 +482,8 @@ __global__ void __launch_bounds__(256) k_bcf_emit(const BcfArgs a)
         pl.n = 0;
         for (int k = 0; k < 7; ++k) { pl.off[k] = 0u; pl.cell[k] = 0; }
         if (a.planes) b.planes = &pl;
-        const uint32_t got = bcf_layout(a, i, s, a.minmax[i], b);
-        if (a.planes) a.planes[i] = pl;
+        const uint32_t got = grec.n_members > 0 ? bcf_layout_block(a, grec, s, a.minmax[rk], b) : bcf_layout(a, i, s, a.minmax[rk], b);
+        if (a.planes) a.planes[rk] = pl;
         nseg_s = b.nseg;
         seg_start[b.nseg] = got;
     }

@@ -82,6 +82,9 @@ struct Slot {
     bool had_d2h = false;
     bool early_d2h = false; // the plane copies were enqueued by vgl_submit (tile kernels: the spans are known on the host)
     int64_t stream_copied = 0; // VGL_HOST_BCF / BGZF: bytes of the record stream vgl_submit already copied on a prediction
+    const uint8_t* seam_ptr = nullptr; // -doGVCF: the stream vgl_wait hands out after the seam was stitched
+    int64_t seam_bytes = 0;
+    int32_t seam_recs = 0;
     // vgl_native_draws() results (host)
     std::vector<int32_t> dr_depths;
     std::vector<int64_t> dr_off;
@@ -108,6 +111,18 @@ struct vgl_ctx {
     size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
     int64_t bgzf_max_blocks = 0;           // VGL_HOST_BGZF: blocks a full record stream makes
     double stream_bytes_per_site = 0.0;    // VGL_HOST_BCF / BGZF: bytes per site of the last finished batch (predicts the next copy)
+    // VGL_HOST_BCF with -doGVCF: thresholds, and the block still open at the end of the last waited batch (the seam)
+    std::vector<int32_t> gvcf_dps;
+    struct Carry {
+        bool open = false;
+        int32_t rid = 0, start = 0, end = 0, range = 0, min_dp = 0, n_alleles = 0;
+        int8_t a2b[8] = {0};
+        float qs[5] = {0};
+        std::vector<int32_t> dp, pl;
+        std::vector<uint8_t> rec; // its record as it stands
+    } carry;
+    size_t bcf_headroom = 0;               // bytes in front of a slot's pinned record stream (a re-encoded seam block goes there)
+    std::vector<uint8_t> flush_rec;
     uint32_t* d_crc_pow = nullptr;
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr, *d_qm_cdf = nullptr;
     float *d_m2_pure = nullptr, *d_m2_park = nullptr;
@@ -223,7 +238,11 @@ static int validate(const vgl_params* p, std::string& why)
     if (p->n_qs_bins < 0 || p->n_qs_bins > 255) { why = "bad n_qs_bins"; return VGL_EINVAL; }
     if (p->sampler < 0 || p->sampler > 2) { why = "bad sampler"; return VGL_EINVAL; }
     if (p->host_output < 0 || p->host_output > 4) { why = "bad host_output"; return VGL_EINVAL; }
-    if ((p->host_output == VGL_HOST_BCF || p->host_output == VGL_HOST_BGZF) && p->do_gvcf) { why = "VGL_HOST_BCF does not take -doGVCF (the block merger consumes arrays)"; return VGL_EINVAL; }
+    if (p->host_output == VGL_HOST_BCF && p->do_gvcf && ((p->do_unobserved != 1 && p->do_unobserved != 2) || !(p->tag_mask & VGL_TAG_FMT_DP))) {
+        why = "VGL_HOST_BCF with -doGVCF needs -doUnobserved 1|2 and FORMAT/DP (the block merger's requirements)";
+        return VGL_EINVAL;
+    }
+    if (p->host_output == VGL_HOST_BGZF && p->do_gvcf) { why = "VGL_HOST_BCF does not take -doGVCF (the block merger consumes arrays)"; return VGL_EINVAL; }
     if ((p->host_output == VGL_HOST_BCF || p->host_output == VGL_HOST_BGZF) && (p->bcf_blob_bytes_per_site < 0 || p->bcf_blob_bytes_per_site > 65536)) { why = "bad bcf_blob_bytes_per_site"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && !(p->gl_model == 1 && p->error_qs != 2)) { why = "count-level sampler needs --gl-model 1 and --error-qs 0|1"; return VGL_EINVAL; }
     if (p->sampler == VGL_SAMPLER_COUNTS && (p->tag_mask & (VGL_TAG_QS | VGL_TAG_I16))) { why = "count-level sampler does not produce QS / I16 (use VGL_SAMPLER_PER_READ)"; return VGL_EINVAL; }
@@ -467,7 +486,8 @@ static int create_impl(vgl_ctx* ctx)
             ctx->blob_cap = B * per_site_blob;
             CK(cudaHostAlloc((void**)&s.h_bcf_in, B * sizeof(vgl_bcf_site_in), cudaHostAllocDefault));
             CK(cudaHostAlloc((void**)&s.h_blob, ctx->blob_cap, cudaHostAllocDefault));
-            if (!bgzf) CK(cudaHostAlloc((void**)&s.h_bcf, ctx->bcf_cap, cudaHostAllocDefault));
+            ctx->bcf_headroom = (!bgzf && p.do_gvcf) ? (((size_t)4096 + 16 * S + 15) & ~(size_t)15) : 0;
+            if (!bgzf) CK(cudaHostAlloc((void**)&s.h_bcf, ctx->bcf_cap + ctx->bcf_headroom, cudaHostAllocDefault));
             else { // the record stream stays on the device; the host receives the compressed blocks
                 ctx->bgzf_max_blocks = bgzf_blocks_for((int64_t)ctx->bcf_cap);
                 const size_t worst = (size_t)ctx->bgzf_max_blocks * BGZF_STRIDE;
@@ -594,6 +614,30 @@ extern "C" int vgl_discordance(vgl_ctx* ctx, int slot, vgl_discordance_out* out)
     return VGL_OK;
 }
 
+static int ensure_gvcf_buffers(vgl_ctx* ctx, Slot& s)
+{
+    if (s.g_sin) return VGL_OK;
+    const size_t B = (size_t)ctx->prm.max_batch_sites, S = (size_t)ctx->prm.n_samples;
+    CK(cudaMalloc((void**)&s.g_sin, B * sizeof(vgl_gvcf_site_in)));
+    CK(cudaMalloc((void**)&s.g_key, B * sizeof(int2)));
+    CK(cudaMalloc((void**)&s.g_recs, B * sizeof(vgl_gvcf_rec)));
+    CK(cudaHostAlloc((void**)&s.hg_recs, B * sizeof(vgl_gvcf_rec), cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&s.g_prev, B * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&s.g_kidx, B * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&s.g_counts, 4 * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&s.g_blast, B * sizeof(int32_t))); // block ordinal -> record
+    CK(cudaMalloc((void**)&s.g_bsum, (B / 1024 + 2) * sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&s.g_local, B * sizeof(unsigned long long)));
+    CK(cudaHostAlloc((void**)&s.hg_counts, 4 * sizeof(int32_t), cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&s.g_dp, B * S * sizeof(int32_t)));
+    CK(cudaHostAlloc((void**)&s.hg_dp, B * S * sizeof(int32_t), cudaHostAllocDefault));
+    if (s.d_pl) {
+        CK(cudaMalloc((void**)&s.g_pl, B * S * 3 * sizeof(int32_t)));
+        CK(cudaHostAlloc((void**)&s.hg_pl, B * S * 3 * sizeof(int32_t), cudaHostAllocDefault));
+    }
+    return VGL_OK;
+}
+
 // ---- gVCF block merger (gvcf.cu) ----
 extern "C" int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* sites, const int32_t* gvcf_dps, int32_t n_gvcf_dps, vgl_gvcf_out* out)
 {
@@ -609,25 +653,7 @@ extern "C" int vgl_gvcf_merge(vgl_ctx* ctx, int slot, const vgl_gvcf_site_in* si
     if (s.n_sites >= (1 << 21)) return fail(ctx, VGL_EINVAL, "vgl_gvcf_merge: at most 2^21 - 1 sites per batch");
     CK(cudaSetDevice(prm.device_id));
     const size_t B = (size_t)prm.max_batch_sites, S = (size_t)prm.n_samples;
-    if (!s.g_sin) {
-        CK(cudaMalloc((void**)&s.g_sin, B * sizeof(vgl_gvcf_site_in)));
-        CK(cudaMalloc((void**)&s.g_key, B * sizeof(int2)));
-        CK(cudaMalloc((void**)&s.g_recs, B * sizeof(vgl_gvcf_rec)));
-        CK(cudaHostAlloc((void**)&s.hg_recs, B * sizeof(vgl_gvcf_rec), cudaHostAllocDefault));
-        CK(cudaMalloc((void**)&s.g_prev, B * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&s.g_kidx, B * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&s.g_counts, 4 * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&s.g_blast, B * sizeof(int32_t))); // block ordinal -> record
-        CK(cudaMalloc((void**)&s.g_bsum, (B / 1024 + 2) * sizeof(unsigned long long)));
-        CK(cudaMalloc((void**)&s.g_local, B * sizeof(unsigned long long)));
-        CK(cudaHostAlloc((void**)&s.hg_counts, 4 * sizeof(int32_t), cudaHostAllocDefault));
-        CK(cudaMalloc((void**)&s.g_dp, B * S * sizeof(int32_t)));
-        CK(cudaHostAlloc((void**)&s.hg_dp, B * S * sizeof(int32_t), cudaHostAllocDefault));
-        if (s.d_pl) {
-            CK(cudaMalloc((void**)&s.g_pl, B * S * 3 * sizeof(int32_t)));
-            CK(cudaHostAlloc((void**)&s.hg_pl, B * S * 3 * sizeof(int32_t), cudaHostAllocDefault));
-        }
-    }
+    { const int rc = ensure_gvcf_buffers(ctx, s); if (rc != VGL_OK) return rc; }
     if (!s.g_ev[0]) for (auto& e : s.g_ev) CK(cudaEventCreate(&e));
     cudaStream_t st = s.stream;
     const int32_t n = s.n_sites;
@@ -808,6 +834,116 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
 
 }
 
+extern "C" int vgl_set_gvcf_dps(vgl_ctx* ctx, const int32_t* gvcf_dps, int32_t n)
+{
+    if (!ctx || !gvcf_dps || n < 1 || n > VGL_MAX_GVCF_DPS) return VGL_EINVAL;
+    for (int i = 0; i < n; ++i)
+        if (gvcf_dps[i] < 1 || (i && gvcf_dps[i] <= gvcf_dps[i - 1])) return fail(ctx, VGL_EINVAL, "vgl_set_gvcf_dps: --gvcf-dps must be >= 1 and ascending");
+    ctx->gvcf_dps.assign(gvcf_dps, gvcf_dps + n);
+    return VGL_OK;
+}
+
+// ---- host-side encoding of ONE gVCF block record: only the block that straddles two batches is encoded here (its halves were
+// reduced on the device); same bytes as bcf_layout_block() in bcf.cu / GVCF_FLUSH_BLOCK in bcf_utils.cpp:896-925
+namespace {
+struct ByteOut {
+    std::vector<uint8_t>& v;
+    void put(uint8_t b) { v.push_back(b); }
+    void put16(uint32_t x) { put((uint8_t)x); put((uint8_t)(x >> 8)); }
+    void put32(uint32_t x) { put16(x); put16(x >> 16); }
+    void size(int n, int type)
+    {
+        if (n >= 15) {
+            put((uint8_t)(15 << 4 | type));
+            if (n >= 128) {
+                if (n >= 32768) { put(1 << 4 | 3); put32((uint32_t)n); }
+                else { put(1 << 4 | 2); put16((uint32_t)n); }
+            } else { put(1 << 4 | 1); put((uint8_t)n); }
+        } else put((uint8_t)(n << 4 | type));
+    }
+    void int1(int32_t x)
+    {
+        if (x == VGL_I32_MISSING) { size(1, 1); put(0x80); }
+        else if (x == VGL_I32_MISSING + 1) { size(1, 1); put(0x81); }
+        else if (x <= 127 && x >= -120) { size(1, 1); put((uint8_t)x); }
+        else if (x <= 32767 && x >= -32760) { size(1, 2); put16((uint32_t)x); }
+        else { size(1, 3); put32((uint32_t)x); }
+    }
+    void vint(const int32_t* a, size_t n, int nps)
+    {
+        int32_t mx = INT32_MIN, mn = INT32_MAX;
+        for (size_t i = 0; i < n; ++i) {
+            if (a[i] == VGL_I32_MISSING || a[i] == VGL_I32_MISSING + 1) continue;
+            mx = std::max(mx, a[i]);
+            mn = std::min(mn, a[i]);
+        }
+        const int t = (mx <= 127 && mn >= -120) ? 1 : ((mx <= 32767 && mn >= -32760) ? 2 : 3);
+        size(nps, t);
+        for (size_t i = 0; i < n; ++i) {
+            const int32_t x = a[i];
+            if (t == 1) put(x == VGL_I32_MISSING ? 0x80 : (x == VGL_I32_MISSING + 1 ? 0x81 : (uint8_t)x));
+            else if (t == 2) put16(x == VGL_I32_MISSING ? 0x8000u : (x == VGL_I32_MISSING + 1 ? 0x8001u : (uint32_t)x));
+            else put32((uint32_t)x);
+        }
+    }
+};
+} // namespace
+
+static void encode_gvcf_block(const vgl_ctx* ctx, const vgl_ctx::Carry& c, std::vector<uint8_t>& out)
+{
+    const vgl_params& prm = ctx->prm;
+    const int S = prm.n_samples;
+    out.clear();
+    ByteOut b{out};
+    const int32_t end1 = c.end + 1;
+    const bool has_end = end1 - c.start >= 2, has_qs = (prm.tag_mask & VGL_TAG_QS) != 0, has_pl = !c.pl.empty();
+    b.put32(0); b.put32(0);
+    b.put32((uint32_t)c.rid);
+    b.put32((uint32_t)c.start);
+    b.put32((uint32_t)(end1 - c.start));
+    b.put32(VGL_F32_MISSING_BITS);
+    b.put16((uint32_t)((has_end ? 1 : 0) + 1 + (has_qs ? 1 : 0)));
+    b.put16((uint32_t)c.n_alleles);
+    b.put32(((uint32_t)((has_pl ? 1 : 0) + 1) << 24) | ((uint32_t)S & 0xFFFFFFu));
+    b.put(0x07);
+    const bool nonref_name = prm.do_unobserved == 2 || prm.do_unobserved == 5;
+    for (int k = 0; k < c.n_alleles; ++k) {
+        const int code = c.a2b[k];
+        const char* str = code == 4 ? (nonref_name ? "<NON_REF>" : "<*>") : (code == 0 ? "A" : code == 1 ? "C" : code == 2 ? "G" : "T");
+        const int n = (int)strlen(str);
+        b.size(n, 7);
+        for (int i = 0; i < n; ++i) b.put((uint8_t)str[i]);
+    }
+    b.put(0x00);
+    if (has_end) { b.int1(prm.bcf_dict.end); b.int1(end1); }
+    b.int1(prm.bcf_dict.min_dp); b.int1(c.min_dp);
+    if (has_qs) {
+        b.int1(prm.bcf_dict.qs);
+        b.size(c.n_alleles, 5);
+        for (int k = 0; k < c.n_alleles; ++k) { uint32_t u; memcpy(&u, &c.qs[k], 4); b.put32(u); }
+    }
+    const uint32_t l_shared = (uint32_t)out.size() - 8;
+    if (has_pl) { b.int1(prm.bcf_dict.pl); b.vint(c.pl.data(), c.pl.size(), 3); }
+    b.int1(prm.bcf_dict.dp); b.vint(c.dp.data(), c.dp.size(), 1);
+    const uint32_t l_indiv = (uint32_t)out.size() - 8 - l_shared;
+    memcpy(out.data(), &l_shared, 4);
+    memcpy(out.data() + 4, &l_indiv, 4);
+}
+
+extern "C" int vgl_gvcf_flush(vgl_ctx* ctx, const uint8_t** rec, int64_t* n_bytes)
+{
+    if (!ctx || !rec || !n_bytes) return VGL_EINVAL;
+    *rec = nullptr;
+    *n_bytes = 0;
+    if (ctx->carry.open) {
+        ctx->flush_rec = ctx->carry.rec;
+        ctx->carry.open = false;
+        *rec = ctx->flush_rec.data();
+        *n_bytes = (int64_t)ctx->flush_rec.size();
+    }
+    return VGL_OK;
+}
+
 // The result copies of a batch whose extents (plane elements, record bytes, compressed bytes) are only known once its kernels
 // have run: enqueued on the slot's stream as soon as some API call finds the totals on the host.
 static int issue_d2h(vgl_ctx* ctx, Slot& s)
@@ -821,7 +957,21 @@ static int issue_d2h(vgl_ctx* ctx, Slot& s)
         const int64_t nb = s.h_totals[z ? 4 : 3], cap = z ? ctx->bgzf_max_blocks * (int64_t)BGZF_STRIDE : (int64_t)ctx->bcf_cap;
         const int64_t done = s.stream_copied; // what vgl_submit copied on its prediction
         if (nb > done && nb <= cap)
-            CK(cudaMemcpyAsync((z ? s.h_bgzf : s.h_bcf) + done, (z ? s.d_bgzf : s.d_bcf) + done, (size_t)(nb - done), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync((z ? s.h_bgzf : s.h_bcf + ctx->bcf_headroom) + done, (z ? s.d_bgzf : s.d_bcf) + done, (size_t)(nb - done), cudaMemcpyDeviceToHost, st));
+        if (prm.do_gvcf && !z) { // the merger's record list and the per-sample minima of the first and the last record (the seam)
+            const int32_t n_recs = s.hg_counts[0];
+            if (n_recs > 0) {
+                CK(cudaMemcpyAsync(s.hg_recs, s.g_recs, (size_t)n_recs * sizeof(vgl_gvcf_rec), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st)); // the planes to fetch depend on the records
+                const size_t S = (size_t)prm.n_samples;
+                for (int k : {0, n_recs - 1}) {
+                    const vgl_gvcf_rec& r = s.hg_recs[k];
+                    if (r.n_members == 0) continue;
+                    CK(cudaMemcpyAsync(s.hg_dp + (size_t)r.plane * S, s.g_dp + (size_t)r.plane * S, S * 4, cudaMemcpyDeviceToHost, st));
+                    if (s.g_pl) CK(cudaMemcpyAsync(s.hg_pl + (size_t)r.plane * S * 3, s.g_pl + (size_t)r.plane * S * 3, S * 12, cudaMemcpyDeviceToHost, st));
+                }
+            }
+        }
         if (nb > 0 && s.n_sites > 0) ctx->stream_bytes_per_site = (double)nb / s.n_sites;
     } else {
         if (s.d_gl) CK(cudaMemcpyAsync(s.h_gl, s.d_gl, (size_t)g_elems * 4, cudaMemcpyDeviceToHost, st));
@@ -998,6 +1148,24 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         b.out = s.d_bcf; b.out_cap = (long long)ctx->bcf_cap;
         b.totals = s.d_totals; b.status = reinterpret_cast<int32_t*>(s.d_totals + 2);
         b.planes = s.d_planes;
+        if (prm.do_gvcf) { // the block merger first (gvcf.cu): the records to serialise are its output, blocks included
+            if (ctx->gvcf_dps.empty()) return fail(ctx, VGL_ESTATE, "VGL_HOST_BCF with -doGVCF: call vgl_set_gvcf_dps before the first submit");
+            if (n_sites >= (1 << 21)) return fail(ctx, VGL_EINVAL, "-doGVCF: at most 2^21 - 1 sites per batch");
+            { const int rc2 = ensure_gvcf_buffers(ctx, s); if (rc2 != VGL_OK) return rc2; }
+            launch_gvcf_sin_from_bcf(s.d_bcf_in, s.g_sin, n_sites, st);
+            GvcfArgs g;
+            memset(&g, 0, sizeof g);
+            g.S = (int32_t)S, g.n_sites = n_sites;
+            g.dps.n = (int32_t)ctx->gvcf_dps.size();
+            for (int i = 0; i < g.dps.n; ++i) g.dps.v[i] = ctx->gvcf_dps[(size_t)i];
+            g.sites = s.d_sites, g.dp = s.d_dp, g.pl = s.d_pl, g.sin = s.g_sin, g.key = s.g_key, g.recs = s.g_recs;
+            g.prev_kept = s.g_prev, g.kept_idx = s.g_kidx, g.counts = s.g_counts, g.out_dp = s.g_dp, g.out_pl = s.g_pl;
+            g.blk_rec = s.g_blast, g.local = s.g_local, g.block_sum = s.g_bsum;
+            launch_gvcf(g, st, ctx->n_sms);
+            ctx->launches += 6;
+            b.recs = s.g_recs; b.rec_counts = s.g_counts; b.blk_dp = s.g_dp; b.blk_pl = s.g_pl;
+            CK(cudaMemcpyAsync(s.hg_counts, s.g_counts, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
         launch_bcf(b, st);
         ctx->launches += 3;
         if (bgzf) {
@@ -1019,7 +1187,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             const size_t cap = bgzf ? (size_t)ctx->bgzf_max_blocks * BGZF_STRIDE : ctx->bcf_cap;
             size_t pred = (size_t)(ctx->stream_bytes_per_site * n_sites * 1.03) + 65536;
             pred = std::min(pred, cap) & ~(size_t)15;
-            CK(cudaMemcpyAsync(bgzf ? s.h_bgzf : s.h_bcf, bgzf ? s.d_bgzf : s.d_bcf, pred, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(bgzf ? s.h_bgzf : s.h_bcf + ctx->bcf_headroom, bgzf ? s.d_bgzf : s.d_bcf, pred, cudaMemcpyDeviceToHost, st));
             s.stream_copied = (int64_t)pred;
         }
     }
@@ -1062,6 +1230,81 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     return VGL_OK;
 }
 
+// -doGVCF with VGL_HOST_BCF: the device serialised every record of the batch, closing every block at the batch's ends.  A block
+// may run across the seam between two batches (bcf_utils.cpp:711, 719, 790: same contig, pos <= end + 1, same dp range), so the
+// last record of a batch is held back when it is a block, and merged with the next batch's first record when that joins it --
+// the merged record is the one piece encoded on the host (encode_gvcf_block), written into the headroom in front of the stream.
+// Batches must be waited in submission order.
+static void gvcf_seam(vgl_ctx* ctx, Slot& s, vgl_batch_out* out)
+{
+    const size_t S = (size_t)ctx->prm.n_samples;
+    vgl_ctx::Carry& c = ctx->carry;
+    const int32_t n_recs = s.hg_counts[0];
+    uint8_t* base = s.h_bcf + ctx->bcf_headroom;
+    const long long* off = s.h_rec_off;
+    int64_t lo = 0, hi = n_recs > 0 ? (int64_t)off[n_recs] : 0; // bytes of the device stream that go out
+    int32_t n_out = n_recs;
+    std::vector<uint8_t> front; // what precedes them
+    auto load = [&](const vgl_gvcf_rec& r, vgl_ctx::Carry& d) {
+        const vgl_bcf_site_in &f = s.h_bcf_in[r.first_site], &l = s.h_bcf_in[r.last_site];
+        const vgl_site_out& so = s.h_sites[r.first_site];
+        d.open = true;
+        d.rid = f.rid, d.start = f.pos, d.end = l.pos, d.range = r.dp_range, d.min_dp = r.min_dp, d.n_alleles = so.n_alleles;
+        memcpy(d.a2b, so.alleles2acgt, 8);
+        memcpy(d.qs, so.qs, sizeof d.qs);
+        d.dp.assign(s.hg_dp + (size_t)r.plane * S, s.hg_dp + (size_t)r.plane * S + S);
+        if (s.hg_pl) d.pl.assign(s.hg_pl + (size_t)r.plane * S * 3, s.hg_pl + (size_t)r.plane * S * 3 + 3 * S);
+        else d.pl.clear();
+    };
+    bool merged_is_last = false;
+    if (n_recs > 0 && c.open) {
+        const vgl_gvcf_rec& r0 = s.hg_recs[0];
+        const vgl_bcf_site_in& f = s.h_bcf_in[r0.first_site];
+        if (r0.n_members > 0 && c.rid == f.rid && f.pos <= c.end + 1 && c.range == r0.dp_range) { // the batch's first block continues the carried one
+            vgl_ctx::Carry m;
+            load(r0, m);
+            c.end = m.end;
+            c.min_dp = std::min(c.min_dp, m.min_dp);
+            for (size_t k = 0; k < S; ++k) {
+                c.dp[k] = std::min(c.dp[k], m.dp[k]);
+                if (!c.pl.empty() && !m.pl.empty()) {
+                    int32_t* g = &c.pl[3 * k];
+                    const int32_t* q = &m.pl[3 * k];
+                    if (q[1] < g[1] || (q[1] == g[1] && q[2] < g[2])) g[1] = q[1], g[2] = q[2];
+                }
+            }
+            encode_gvcf_block(ctx, c, c.rec);
+            lo = (int64_t)off[1]; // the device's version of that record is dropped
+            --n_out;
+            if (n_recs == 1) merged_is_last = true; // still the open block
+            else { front = c.rec; c.open = false; ++n_out; }
+        } else {
+            front = c.rec; // the carried block ended with its batch
+            c.open = false;
+            ++n_out;
+        }
+    }
+    if (n_recs > 0 && !merged_is_last) {
+        const vgl_gvcf_rec& rl = s.hg_recs[n_recs - 1];
+        if (rl.n_members > 0 && !(n_recs == 1 && lo > 0)) { // hold the trailing block back
+            load(rl, c);
+            c.rec.assign(base + off[n_recs - 1], base + off[n_recs]);
+            hi = (int64_t)off[n_recs - 1];
+            --n_out;
+        }
+    }
+    if (hi < lo) hi = lo;
+    uint8_t* start = base + lo - (int64_t)front.size();
+    if (!front.empty()) memcpy(start, front.data(), front.size()); // headroom (lo = 0) or the dropped first record's place
+    s.seam_ptr = start;
+    s.seam_bytes = (int64_t)front.size() + (hi - lo);
+    s.seam_recs = n_out;
+    out->bcf = s.seam_ptr;
+    out->bcf_bytes = s.seam_bytes;
+    out->bcf_off = nullptr;
+    out->n_recs = s.seam_recs;
+}
+
 extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
 {
     if (!ctx || !out || slot < 0 || slot >= (int)ctx->slots.size()) return VGL_EINVAL;
@@ -1092,6 +1335,7 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
         CK(wait_event(s.ev[EV_D2H1]));
         s.had_d2h = true;
     }
+    const bool first_wait = !s.waited;
     if (!s.waited) {
         float* ms = s.ms;
         CK(cudaEventElapsedTime(&ms[VGL_T_H2D], s.ev[EV_START], s.ev[EV_H2D]));
@@ -1136,9 +1380,11 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
             out->bgzf_bytes = s.h_totals[4];
             out->bgzf_blocks = (int32_t)s.h_totals[5];
         }
-        out->bcf = s.h_bcf;
+        out->bcf = s.h_bcf ? s.h_bcf + ctx->bcf_headroom : nullptr;
         out->bcf_off = reinterpret_cast<const int64_t*>(s.h_rec_off);
         out->bcf_bytes = s.h_totals[3];
+        if (prm.do_gvcf && prm.host_output == VGL_HOST_BCF && first_wait) gvcf_seam(ctx, s, out);
+        else if (prm.do_gvcf && prm.host_output == VGL_HOST_BCF) { out->bcf = s.seam_ptr; out->bcf_bytes = s.seam_bytes; out->bcf_off = nullptr; out->n_recs = s.seam_recs; }
     }
     out->g_elems = g_elems;
     out->r_elems = r_elems;

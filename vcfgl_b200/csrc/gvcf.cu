@@ -269,7 +269,24 @@ __global__ void __launch_bounds__(256) k_gvcf_reduce(vgl_gvcf_rec* recs, const i
     }
 }
 
+__global__ void k_gvcf_sin_from_bcf(const vgl_bcf_site_in* __restrict__ in, vgl_gvcf_site_in* __restrict__ out, int32_t n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        vgl_gvcf_site_in o;
+        o.rid = in[i].rid;
+        o.pos = in[i].pos;
+        out[i] = o;
+    }
+}
+
 } // namespace
+
+// VGL_HOST_BCF with -doGVCF: the merger's (contig, position) input from the pass-through records already on the device
+void launch_gvcf_sin_from_bcf(const vgl_bcf_site_in* in, vgl_gvcf_site_in* out, int32_t n, cudaStream_t st)
+{
+    k_gvcf_sin_from_bcf<<<(n + 255) / 256, 256, 0, st>>>(in, out, n);
+}
 
 void launch_gvcf(const GvcfArgs& a, cudaStream_t st, int n_sms)
 {

@@ -146,6 +146,10 @@ struct BcfArgs {
     int64_t* totals;       // [3] receives the total
     int32_t* status;
     struct BcfRecPlanes* planes; // [n_sites] or null: FORMAT plane layout of every record (for the BGZF compressor)
+    // -doGVCF 1: the records are those of the block merger (gvcf.cu), in its order; null: one record per kept site
+    const vgl_gvcf_rec* recs;    // [counts[0]]
+    const int32_t* rec_counts;   // [0] records
+    const int32_t *blk_dp, *blk_pl; // planes of the blocks' per-sample minima
 };
 void launch_bcf(const BcfArgs& a, cudaStream_t st);
 
@@ -225,6 +229,7 @@ struct GvcfArgs {
     int32_t *out_dp, *out_pl;
 };
 void launch_gvcf(const GvcfArgs& a, cudaStream_t st, int n_sms);
+void launch_gvcf_sin_from_bcf(const vgl_bcf_site_in* in, vgl_gvcf_site_in* out, int32_t n, cudaStream_t st);
 
 // input path (vcfin.cu)
 void launch_place_rows(const uint8_t* rows, const int32_t* d_row_map, int32_t first_record, int32_t n_sites, int32_t S, uint8_t fill, uint8_t* gt,

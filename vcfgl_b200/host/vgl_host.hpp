@@ -482,10 +482,24 @@ public:
         if (++fill_ == prm_.max_batch_sites) submit_current();
     }
 
+    // -doGVCF 1: the block merger runs on the device too (vgl_set_gvcf_dps); the stream then holds regular and block records
+    // in output order, the seam between batches stitched by vgl_wait; the last open block arrives with finish()
+    void enable_gvcf(const std::vector<int32_t>& gvcf_dps)
+    {
+        check(vgl_set_gvcf_dps(ctx_, gvcf_dps.data(), (int32_t)gvcf_dps.size()), "vgl_set_gvcf_dps");
+        gvcf_ = true;
+    }
+
     void finish()
     {
         if (fill_ > 0) submit_current();
         for (int k = 0; k < prm_.n_slots; ++k) drain((cur_ + k) % prm_.n_slots);
+        if (gvcf_) {
+            const uint8_t* rec = nullptr;
+            int64_t nb = 0;
+            check(vgl_gvcf_flush(ctx_, &rec, &nb), "vgl_gvcf_flush");
+            if (nb > 0) sink_(rec, (size_t)nb, 0, 0);
+        }
     }
 
 private:
@@ -527,6 +541,7 @@ private:
     vgl_ctx* ctx_ = nullptr;
     std::vector<bool> in_flight_;
     uint8_t *gt_ = nullptr, *blob_ = nullptr;
+    bool gvcf_ = false;
     vgl_bcf_site_in* sin_ = nullptr;
     int64_t blob_cap_ = 0;
     size_t blob_fill_ = 0;
