@@ -492,6 +492,7 @@ def gpu_arm(opt):
         e2e_bcf = {"value": v, "d2h_bytes_per_step": nb * Le, "gpu_launches": int(nl),
                    "planes": "VGL_HOST_BCF with -doGVCF: regular and block records serialised on the device (k_gvcf_* + k_bcf_*), byte-identical "
                              "to the reference's -O u stream"}
+        e2e_value, d2h_bytes, e2e_launches, e2e_planes = v, nb, nl, e2e_bcf["planes"]   # the headline of a gVCF workload
     if not a.do_gvcf:   # serialised BCF records
         v, nb, nl = e2e_run(capi.HOST_BCF)
         e2e_bcf = {"value": v, "d2h_bytes_per_step": nb * Le, "gpu_launches": int(nl),
