@@ -248,11 +248,23 @@ def test_native_ten_thousand_samples():
     _check(want, got)
 
 
-def test_bcf_mode_rejects_gvcf_and_overflow_is_reported():
-    a = vargs.parse_args("--seed 1 -d 10 -e 0.001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,5,10 -addPL 1".split())
+def test_gvcf_record_modes_that_are_rejected():
+    # -doGVCF through VGL_HOST_BCF needs the block merger's requirements (-doUnobserved 1|2: tests/test_gpu_gvcf_bcf.py covers the mode);
+    # the BGZF stream cannot be spliced at batch seams, and a submit without the thresholds is a state error
+    a = vargs.parse_args("--seed 1 -d 10 -e 0.001 -GL 1 -doUnobserved 4 -doGVCF 1 --gvcf-dps 1,5,10 -addPL 1".split())
     with pytest.raises(capi.VglError) as e:
         capi.Context(capi.params_from_args(a, 4, 16, host_output=capi.HOST_BCF))
     assert e.value.code == capi.VGL_EINVAL
+    a = vargs.parse_args("--seed 1 -d 10 -e 0.001 -GL 1 -doUnobserved 1 -doGVCF 1 --gvcf-dps 1,5,10 -addPL 1".split())
+    with pytest.raises(capi.VglError) as e:
+        capi.Context(capi.params_from_args(a, 4, 16, host_output=capi.HOST_BGZF))
+    assert e.value.code == capi.VGL_EINVAL
+    ctx = capi.Context(capi.params_from_args(a, 4, 16, n_slots=1, host_output=capi.HOST_BCF, bcf_dict=dict(DP=1, GL=2, PL=3, END=4, MIN_DP=5)))
+    ctx.input_buffer(0)[:] = 0
+    with pytest.raises(capi.VglError) as e:
+        ctx.submit(0, 0, 16)
+    assert e.value.code == capi.VGL_ESTATE
+    ctx.close()
 
 
 def test_cpp_host_stream_writes_a_bcf_file_the_oracle_reads(tmp_path):

@@ -19,7 +19,7 @@ using namespace vgl;
 
 namespace {
 
-enum { EV_START = 0, EV_H2D, EV_SIM, EV_SITE, EV_SCAN, EV_EMIT, EV_META, EV_D2H0, EV_D2H1, EV_COUNT };
+enum { EV_START = 0, EV_H2D, EV_SIM, EV_SITE, EV_SCAN, EV_EMIT, EV_META, EV_D2H0, EV_D2H1, EV_KDONE, EV_COUNT };
 
 struct DevBuf {
     void* p = nullptr;
@@ -123,6 +123,7 @@ struct vgl_ctx {
     } carry;
     size_t bcf_headroom = 0;               // bytes in front of a slot's pinned record stream (a re-encoded seam block goes there)
     std::vector<uint8_t> flush_rec;
+    cudaEvent_t chain_ev = nullptr;        // kernels of the previous submit are done (see vgl_submit)
     uint32_t* d_crc_pow = nullptr;
     uint32_t *d_qcls = nullptr, *d_m2_cmap = nullptr, *d_qm_cdf = nullptr;
     float *d_m2_pure = nullptr, *d_m2_park = nullptr;
@@ -951,6 +952,12 @@ static int issue_d2h(vgl_ctx* ctx, Slot& s)
     const vgl_params& prm = ctx->prm;
     cudaStream_t st = s.stream;
     const int64_t g_elems = s.h_totals[0], r_elems = s.h_totals[1];
+    if (getenv("VGL_TRACE") && s.stream_copied > 0) {
+        float k = 0.f, c = 0.f;
+        cudaEventElapsedTime(&k, s.ev[EV_START], s.ev[EV_D2H0]);
+        cudaEventElapsedTime(&c, s.ev[EV_D2H0], s.ev[EV_D2H1]);
+        fprintf(stderr, "[vgl] slot: start -> kernels done %.2f ms, predicted copy %.2f ms (%.1f MB, %.1f GB/s)\n", k, c, s.stream_copied / 1e6, s.stream_copied / 1e6 / c);
+    }
     CK(cudaEventRecord(s.ev[EV_D2H0], st));
     if (prm.host_output == VGL_HOST_BCF || prm.host_output == VGL_HOST_BGZF) {
         const bool z = prm.host_output == VGL_HOST_BGZF;
@@ -1096,6 +1103,10 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
     const bool fused = (ctx->use_fused || ctx->use_tile_m2) && !rp;
     if (fused && !tile_launch) CK(cudaMemsetAsync(s.d_tile_state, 0, ((size_t)p.n_tiles + 1) * sizeof(unsigned long long), st));
     CK(cudaEventRecord(s.ev[EV_H2D], st));
+    // Batches run their kernels strictly one after the other, also across slots with streams of their own: left to itself the
+    // GPU interleaves the kernels of all batches in flight, they all finish together, and the result copies then run while
+    // the SMs idle.  In order, batch k's copies overlap batch k+1's kernels.
+    if (ctx->chain_ev && prm.host_output) CK(cudaStreamWaitEvent(st, ctx->chain_ev, 0));
     if (fused) {
         // one kernel does everything; its time is reported as VGL_T_EMIT (SIM / SITE / SCAN = 0)
         CK(cudaEventRecord(s.ev[EV_SIM], st));
@@ -1179,6 +1190,8 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             launch_bgzf(z, nb_max, st, ctx->n_sms);
             ctx->launches += 4;
         }
+        CK(cudaEventRecord(s.ev[EV_KDONE], st)); // the batch's last kernel: the next batch's kernels may start (its copies follow)
+        ctx->chain_ev = s.ev[EV_KDONE];
         CK(cudaMemcpyAsync(s.h_rec_off, s.d_rec_off, ((size_t)n_sites + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
         // The stream's size is only known on the device, but the previous batch predicts it well: that many bytes (+ 3 %) follow
         // the kernels right away; vgl_wait copies what is left once it knows the size (a few per cent, or nothing).
@@ -1187,11 +1200,17 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             const size_t cap = bgzf ? (size_t)ctx->bgzf_max_blocks * BGZF_STRIDE : ctx->bcf_cap;
             size_t pred = (size_t)(ctx->stream_bytes_per_site * n_sites * 1.03) + 65536;
             pred = std::min(pred, cap) & ~(size_t)15;
+            CK(cudaEventRecord(s.ev[EV_D2H0], st));
             CK(cudaMemcpyAsync(bgzf ? s.h_bgzf : s.h_bcf + ctx->bcf_headroom, bgzf ? s.d_bgzf : s.d_bcf, pred, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(s.ev[EV_D2H1], st));
             s.stream_copied = (int64_t)pred;
         }
     }
     CK(cudaGetLastError());
+    if (prm.host_output && !bcf) {
+        CK(cudaEventRecord(s.ev[EV_KDONE], st));
+        ctx->chain_ev = s.ev[EV_KDONE];
+    }
     if (prm.host_output) CK(cudaMemcpyAsync(s.h_sites, s.d_sites, (size_t)n_sites * sizeof(vgl_site_out), cudaMemcpyDeviceToHost, st));
     if (tile_launch && !tile_status) s.h_totals[2] = 0; // the kernel posts the totals into the pinned words itself and raises no errors
     else CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
