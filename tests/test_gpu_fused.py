@@ -119,7 +119,8 @@ def test_fused_tags_match_oracle_on_own_counts(name):
 
 
 @pytest.mark.parametrize("name,no_tile,kernels", [("gl1_d10", False, "k_fused_m1f"), ("gl1_d30", True, "k_fused_m1f"),
-                                                  ("gl1_d30", False, "k_tile_m1f"), ("gl1_df", False, "k_fused_m1f")])
+                                                  ("gl1_d30", False, "k_tile_m1f"), ("gl1_df", True, "k_fused_m1f"),
+                                                  ("gl1_df", False, "k_tile_m1f")])
 def test_count_sampler_distributions_match_reference(name, no_tile, kernels, monkeypatch):
     """the count-level sampler against the reference's captures (>= 1e6 cells each), from the AD / ADF planes alone (the
     fused kernel has no per-read draws to export); the kernel set is asserted"""

@@ -51,8 +51,8 @@ def test_native_tags_match_oracle_on_own_draws(name):
     self_replay(name, SELF_CASES[name], 1, S, n_sites)
 
 
-def self_replay(name, argv, sampler, S, n_sites, kernels=None, qs_bins=None):
-    a = vargs.parse_args(argv.split(), qs_bins=qs_bins)
+def self_replay(name, argv, sampler, S, n_sites, kernels=None, qs_bins=None, depths=None):
+    a = vargs.parse_args(argv.split(), qs_bins=qs_bins, depths=depths)
     hap = synth.sfs_genotypes(n_sites, S, 99, missing_rate=0.05) if S > 1 else \
         np.random.default_rng(1).integers(0, 2, (n_sites, 2)).astype(np.int8)
     gt = synth.pack_gt(hap)
@@ -162,6 +162,7 @@ DIST_RUNS = [
     ("gl1_aux", 1, PER_READ, False),
     ("gl1_aux", 0, "k_tile_m1f", False),           # the AUX variant (QS / I16 / INFO ADF, ADR)
     ("gl1_df", 1, PER_READ, False),                # --depths-file: per-sample Poisson means (k_fused_m1f: tests/test_gpu_fused.py)
+    ("gl1_df", 0, "k_tile_m1f", False),            # one alias table per distinct mean
     ("gl2_d2_e02", 1, PER_READ, False),
     ("gl2_d2_e02", 0, "k_tile_m2", True),
     ("gl2_eq2", 1, PER_READ, False),

@@ -9,7 +9,11 @@ GL model 2 depends on the ORDER of a cell's reads, so the kernel's own read sequ
 """
 import pytest
 
+import numpy as np
+
 from test_gpu_native import self_replay
+from vcfgl_b200 import args as vargs
+from vcfgl_b200 import capi
 
 pytestmark = pytest.mark.gpu
 
@@ -40,3 +44,24 @@ CASES = {
 def test_tile_m2_tags_match_oracle_on_own_reads(name):
     argv, S, n_sites, bins = CASES[name]
     self_replay(name.replace("deep", "d70"), argv, 0, S, n_sites, kernels="k_tile_m2", qs_bins=bins)
+
+
+@pytest.mark.parametrize("argv,kernels", [("--seed 31 -e 0.05 -GL 2 -addPL 1 -addFormatAD 1", "k_tile_m2"),
+                                          ("--seed 32 -e 0.01 -eq 2 -bv 1e-4 -GL 2 -addPL 1 -addFormatAD 1", "k_tile_m2"),
+                                          ("--seed 33 -e 0.02 -GL 1 -addPL 1 -addFormatAD 1", "k_tile_m1f"),
+                                          ("--seed 34 -e 0.02 -GL 1 -addPL 1 -addI16 1 -addQS 1", "k_tile_m1f")])
+def test_tile_kernels_with_per_sample_depths(argv, kernels):
+    """--depths-file (vcfgl.cpp:1093-1100: each sample its own Poisson mean): one alias table per distinct mean on the device;
+    the kernel's planes against the oracle on the kernel's own draws, and the mean depth of each sample against its mean"""
+    S, n_sites = 37, 400
+    depths = [0.5 + (i % 5) * 2.0 for i in range(S)]
+    self_replay("df", argv, 0, S, n_sites, kernels=kernels, depths=depths)
+    a = vargs.parse_args(argv.split(), depths=depths)
+    ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=4000, n_slots=1))
+    assert ctx.native_kernels() == kernels
+    ctx.input_buffer(0)[:4000] = 0
+    ctx.submit(0, 0, 4000)
+    dp = ctx.wait(0).dp.reshape(4000, S).astype(np.float64)
+    ctx.close()
+    z = (dp.mean(axis=0) - np.array(depths)) / np.sqrt(np.array(depths) / 4000)
+    assert np.abs(z).max() < 4.5, z

@@ -133,6 +133,7 @@ struct vgl_ctx {
     double* d_m2_tab = nullptr;
     int m2_nq = 0;
     unsigned long long *d_pois = nullptr, *d_alias = nullptr;
+    uint16_t* d_alias_row = nullptr; // --depths-file: each sample's row in d_alias
     uint32_t *d_errcdf = nullptr, *d_cnt_scratch = nullptr;
     int pois_n = 0;
     double *d_lut = nullptr, *d_m1_bsum = nullptr, *d_m1_het = nullptr, *d_fk = nullptr, *d_beta = nullptr, *d_depth_means = nullptr;
@@ -287,7 +288,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park); cudaFree(ctx->d_m1_pure); cudaFree(ctx->d_crc_pow);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_alias_row); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park); cudaFree(ctx->d_m1_pure); cudaFree(ctx->d_crc_pow);
     delete ctx;
 }
 
@@ -365,6 +366,26 @@ static int create_impl(vgl_ctx* ctx)
         const std::vector<unsigned long long> al = poisson_alias_u64(cdf); // empty: depth can exceed 255
         if (!al.empty()) { alias = al; alias_ok = true; }
     }
+    std::vector<uint16_t> alias_row;
+    if (p.depth_mode == VGL_DEPTH_POISSON_PER_SAMPLE) { // --depths-file: one alias table per distinct mean, a row index per sample
+        std::vector<double> means;
+        std::vector<unsigned long long> all;
+        alias_ok = true;
+        for (int sidx = 0; sidx < p.n_samples && alias_ok; ++sidx) {
+            const double m = ctx->depth_means[(size_t)sidx];
+            size_t row = 0;
+            while (row < means.size() && means[row] != m) ++row;
+            if (row == means.size()) {
+                const std::vector<unsigned long long> al = poisson_alias_u64(poisson_cdf_u64(m, 1024));
+                if (al.empty() || means.size() >= 65535) { alias_ok = false; break; }
+                means.push_back(m);
+                all.insert(all.end(), al.begin(), al.end());
+            }
+            alias_row.push_back((uint16_t)row);
+        }
+        if (alias_ok) alias = all;
+        else alias_row.clear();
+    }
     // the tile kernel (tile_m1f.cu): the fused path's headline special case; its AUX variant also takes QS / I16 / INFO ADF, ADR
     const bool tile_base = ctx->gl_mode == GL_M1_FIXED && p.sampler != VGL_SAMPLER_PER_READ && g_cap_elems < (1ull << 31) && alias_ok &&
                            p.error_qs == 0 && ctx->fast_div && !(t & (VGL_TAG_GP | VGL_TAG_FMT_ADF | VGL_TAG_FMT_ADR)) &&
@@ -408,7 +429,8 @@ static int create_impl(vgl_ctx* ctx)
     if (p.depth_mode == VGL_DEPTH_INF) ctx->use_fused = ctx->use_tile = ctx->use_tile_m2 = ctx->tile_aux = 0; // truth.cu
     // closed form of cells whose reads all show one base: worth its branch when most 32-cell chunks hold no mis-called read
     // (expected mis-called reads per chunk = 32 x depth x error rate below ~1/2; heterozygous cells are the input's business)
-    const double exp_depth = p.depth_mode == VGL_DEPTH_POISSON || p.depth_mode == VGL_DEPTH_FIXED ? p.depth_mean : 0.0;
+    double exp_depth = p.depth_mode == VGL_DEPTH_POISSON || p.depth_mode == VGL_DEPTH_FIXED ? p.depth_mean : 0.0;
+    for (double d : ctx->depth_means) exp_depth = std::max(exp_depth, d);
     if (ctx->use_tile && 32.0 * exp_depth * p.error_rate < 0.5 && !getenv("VGL_NO_PURE")) {
         CK(cudaMalloc(&ctx->d_m1_pure, 256 * sizeof(M1Pure)));
         if (!build_m1f_pure_table(ctx->d_m1_bsum, ctx->d_m1_het, ctx->d_m1_pure, nullptr)) {
@@ -420,6 +442,7 @@ static int create_impl(vgl_ctx* ctx)
     if (p.host_output == VGL_HOST_NARROW) ctx->narrow_bits = alias_ok ? 8 : 16;
     if (ctx->use_tile || ctx->use_tile_m2) {
         CK(upload(&ctx->d_alias, alias));
+        if (!alias_row.empty()) CK(upload(&ctx->d_alias_row, alias_row));
         CK(upload(&ctx->d_errcdf, binomial_cdf4_u32(p.error_rate)));
         const size_t words = ctx->use_tile_m2 ? tile_m2_row_words(p.n_samples, ctx->n_sms) : tile_m1f_scratch_words(p.n_samples, ctx->n_sms);
         if (words) CK(cudaMalloc((void**)&ctx->d_cnt_scratch, words * 4));
@@ -807,6 +830,7 @@ static void fill_params(const vgl_ctx* ctx, const Slot& s, int64_t first_site_id
     p.pois_cdf = ctx->d_pois;
     p.pois_n = ctx->pois_n;
     p.pois_alias = ctx->d_alias;
+    p.alias_row = ctx->d_alias_row;
     p.err_cdf = ctx->d_errcdf;
     p.cnt_scratch = ctx->d_cnt_scratch;
     p.m1_pure = ctx->d_m1_pure;

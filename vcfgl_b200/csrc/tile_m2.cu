@@ -82,14 +82,16 @@ __device__ __noinline__ int m2_deep_base(const DevParams& p, unsigned long long 
 }
 
 // depth of a cell from block 0 of its P_COUNTS counter
-__device__ __forceinline__ int m2_depth(const M2Rng& R, const u32x4& b0, uint32_t gt)
+__device__ __forceinline__ int m2_depth(const DevParams& p, const M2Rng& R, const u32x4& b0, uint32_t gt, uint32_t sample)
 {
     int n;
     if (R.fixed_depth >= 0) {
         n = R.fixed_depth;
     } else {
         const uint32_t col = b0.x >> 24;
-        const uint2 en = lds64(R.s_alias + col * 8u);
+        uint2 en;
+        if (p.alias_row) en = __ldg(reinterpret_cast<const uint2*>(p.pois_alias) + (size_t)__ldg(p.alias_row + sample) * 256u + col); // the sample's own mean
+        else en = lds64(R.s_alias + col * 8u);
         const unsigned long long frac = ((unsigned long long)__funnelshift_l(b0.y, b0.x, 8) << 32) | (b0.y << 8);
         const unsigned long long thr = ((unsigned long long)en.y << 32) | (en.x & 0xFFFFFF00u);
         n = frac < thr ? (int)col : (int)(en.x & 0xFFu);
@@ -110,7 +112,7 @@ __device__ __forceinline__ uint32_t m2_cell_fixed(const DevParams& p, const M2Rn
     const uint32_t c0 = (uint32_t)site, c1 = (uint32_t)(site >> 32) & 0xFFu;
     const u32x4 b0 = philox_rk(p, c0, c1, sample, (uint32_t)P_COUNTS << 24);
     const u32x4 b1 = philox_rk(p, c0, c1, sample, ((uint32_t)P_COUNTS << 24) | 1u); // independent of b0: the two chains overlap
-    const int n = m2_depth(R, b0, gt);
+    const int n = m2_depth(p, R, b0, gt, sample);
     n_out = n;
     if (SEQ) w[0] = w[1] = w[2] = w[3] = 0u;
     if (n == 0) return 0u;

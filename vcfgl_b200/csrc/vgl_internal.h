@@ -99,6 +99,7 @@ struct DevParams {
     uint32_t* ticket;                   // dynamic tile counter
     // tile kernel (tile_m1f.cu)
     const unsigned long long* pois_alias; // [256] Walker alias table of the depth distribution: t56 << 8 | alias
+    const uint16_t* alias_row;            // --depths-file: [S] row of each sample's own table in pois_alias ([rows][256]); null: one table
     const uint32_t* err_cdf;              // [256][4] P(E <= j | n reads) * 2^32, j = 0..3
     uint32_t* cnt_scratch;                // per-CTA rows of packed counts when a site does not fit shared memory
     const void* m1_pure;                  // [256] M1Pure: GL / PL of a cell whose reads all show one base, by depth; null: not usable
