@@ -29,4 +29,12 @@ int shim_qs_classes(double a, double b, double shift, int use_bins, const uint8_
     memcpy(prob512, pr.data(), 257 * 8);
     return (int)w.size();
 }
+// 640 words: lit[256], len[256], dist[32], eob, hdr_bits, hdr[94]
+void shim_bgzf_code(const uint32_t* hist, int fixed, uint32_t* out)
+{
+    vgl::BgzfCode c;
+    vgl::bgzf_build_code(hist, fixed != 0, &c);
+    memcpy(out, &c, sizeof(c));
+}
+int shim_bgzf_code_words() { return (int)(sizeof(vgl::BgzfCode) / 4); }
 }

@@ -1,6 +1,10 @@
 """VGL_HOST_BGZF: the BCF record stream of a batch compressed on the device into BGZF blocks (csrc/bgzf.cu; the reference's
 default container, -O b: htslib/bgzf.c, vcfgl.cpp:1791-1803).
 
+The blocks use one dynamic Huffman code per context (RFC 1951 3.2.7), built by vgl_submit from the symbol statistics of
+the context's first record stream (csrc/tables.cpp bgzf_build_code, pinned on zlib by tests/test_tables.py); a block the
+code would expand beyond the block image falls back to deflate's fixed code.
+
 Oracle = zlib on the host: every block must be a well-formed BGZF gzip member (magic, "BC" extra field with the block size,
 raw deflate data, CRC32 and length of the uncompressed bytes), and the inflated blocks, concatenated, must equal byte for
 byte the uncompressed record stream VGL_HOST_BCF returns for the same submit (which tests/test_gpu_bcf.py pins to the
@@ -110,3 +114,48 @@ def test_bgzf_blocks_inflate_to_the_record_stream(name):
     assert gzip.GzipFile(fileobj=io.BytesIO(blob)).read() == header + b"".join(p[0] for p in plain)
     if name == "cfg2":    # the simulated tags repeat: the stream must actually shrink
         assert tot_z < 0.5 * tot_raw, (tot_z, tot_raw)
+
+
+def inflate_all(z):
+    got = bytearray()
+    kinds = set()
+    for payload, crc, isize in split_blocks(z):
+        d = zlib.decompressobj(-15)
+        raw = d.decompress(payload)
+        assert d.eof and not d.unused_data and len(raw) == isize and zlib.crc32(raw) == crc
+        kinds.add((payload[0] >> 1) & 3)      # BTYPE of the block's only deflate block
+        got += raw
+    return bytes(got), kinds
+
+
+def test_dynamic_code_beats_the_fixed_code(monkeypatch):
+    argv, S, n_sites, batch, missing = CASES["cfg2"]
+    a = vargs.parse_args(argv.split())
+    gt = synth.pack_gt(synth.sfs_genotypes(n_sites, S, 4242, missing))
+    plain = run(capi.HOST_BCF, a, S, gt, n_sites, batch)
+    dyn = run(capi.HOST_BGZF, a, S, gt, n_sites, batch)
+    monkeypatch.setenv("VGL_BGZF_FIXED", "1")
+    fix = run(capi.HOST_BGZF, a, S, gt, n_sites, batch)
+    raw_d, kinds_d = inflate_all(dyn[0][0])
+    raw_f, kinds_f = inflate_all(fix[0][0])
+    assert raw_d == raw_f == plain[0][0]
+    assert kinds_d == {2} and kinds_f == {1}
+    assert len(dyn[0][0]) < 0.9 * len(fix[0][0]), (len(dyn[0][0]), len(fix[0][0]))
+
+
+def test_blocks_the_context_code_does_not_fit_fall_back_to_the_fixed_code():
+    """the code is built from the first batch; a first batch of missing genotypes only (no reads: constant tags) gives a
+    code under which the second batch's literals take up to 15 bits each"""
+    argv, S, n_sites = "--seed 42 -d 10 -e 0.2 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1", 100, 600
+    a = vargs.parse_args(argv.split())
+    hap = synth.sfs_genotypes(2 * n_sites, S, 77, 0.0)
+    hap[:n_sites] = -1
+    gt = synth.pack_gt(hap)
+    plain = run(capi.HOST_BCF, a, S, gt, 2 * n_sites, n_sites)
+    packed = run(capi.HOST_BGZF, a, S, gt, 2 * n_sites, n_sites)
+    kinds = set()
+    for (want, _, _, _), (z, _, _, _) in zip(plain, packed):
+        got, k = inflate_all(z)
+        assert got == want
+        kinds |= k
+    assert kinds == {1, 2}, kinds

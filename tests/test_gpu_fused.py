@@ -30,6 +30,9 @@ CASES = {
     "s2501_scratch": ("--seed 14 -d 3 -e 0.02 -GL 1 -addGL 1 -addPL 1 -addFormatAD 1", 2501, 12),
     "e_high": ("--seed 12 -d 12 -e 0.9 -GL 1 -addPL 1 -addFormatAD 1", 33, 300),
     "deep": ("--seed 13 -d 280 -e 0.01 -GL 1 -addPL 1 -addFormatAD 1", 6, 60),
+    # every third site has no reads and is dropped; its neighbours show all four bases (+ <*>: all 15 base pairs have a slot), so
+    # 32-cell chunks mix lanes of skipped sites with lanes of the unpredicated store path
+    "skipped_next_to_all15": ("--seed 15 -d 6 -e 0.6 -GL 1 -doUnobserved 1 --rm-empty-sites 1 -addPL 1 -addFormatAD 1", 6, 900),
 }
 
 
@@ -51,6 +54,8 @@ def test_fused_tags_match_oracle_on_own_counts(name):
     a = vargs.parse_args(argv.split())
     hap = synth.sfs_genotypes(n_sites, S, 4242, missing_rate=0.04) if S > 1 else \
         np.random.default_rng(1).integers(0, 2, (n_sites, 2)).astype(np.int8)
+    if name.startswith("skipped"):
+        hap[::3] = -1
     gt = synth.pack_gt(hap)
     first = 987654321
     sites, (g_off, r_off, g_elems, r_elems) = run(a, S, gt, first, n_sites)

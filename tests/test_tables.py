@@ -174,3 +174,92 @@ def test_qs_class_table_is_the_beta_law(shim, mean, var, shift, bins):
         for c in range(256):
             if c != dom:
                 assert abs(m2[c] / 2 ** 32 - mass[c] / rest) < 1e-9, (c, m2[c], mass[c])
+
+
+# ---- the prefix codes of the device's BGZF compressor (csrc/bgzf.cu): a stream put together in Python from the tables
+# (header bits, literal / length / distance codes, end of block) must inflate with zlib to the bytes it encodes
+def _bgzf_encode(code, tokens):
+    lit, ln, dist, eob, hdr_bits, hdr = code[:256], code[256:512], code[512:544], int(code[544]), int(code[545]), code[546:]
+    acc, n = 0, 0
+    for i in range((hdr_bits + 31) // 32):
+        acc |= int(hdr[i]) << (32 * i)
+    n = hdr_bits
+    for t in tokens:
+        if isinstance(t, int):
+            e = int(lit[t])
+            acc |= (e & 0xFFFF) << n
+            n += e >> 16
+        else:
+            L, D = t
+            e = int(ln[L - 3])
+            acc |= (e & 0xFFFFFF) << n
+            n += e >> 24
+            if D <= 4:
+                dc, deb, dev = D - 1, 0, 0
+            else:
+                u = D - 1
+                hb = u.bit_length() - 1
+                deb = hb - 1
+                dc = 2 * hb + ((u >> deb) & 1)
+                dev = u & ((1 << deb) - 1)
+            e = int(dist[dc])
+            acc |= (e & 0xFFFF) << n
+            n += e >> 16
+            acc |= dev << n
+            n += deb
+    acc |= (eob & 0xFFFF) << n
+    n += eob >> 16
+    return acc.to_bytes((n + 7) // 8, "little")
+
+
+@pytest.mark.parametrize("kind", ["fixed", "flat", "skewed", "one_symbol", "huge_counts"])
+def test_bgzf_prefix_codes_inflate_with_zlib(shim, kind):
+    import zlib
+    rng = np.random.default_rng(5)
+    hist = np.zeros(320, np.uint32)
+    if kind == "skewed":
+        hist[:256] = (1e6 * rng.random(256) ** 8).astype(np.uint32)
+        hist[0] = 5_000_000
+        hist[257:286] = rng.integers(0, 1000, 29)
+        hist[288:318] = rng.integers(0, 100000, 30)
+    elif kind == "one_symbol":
+        hist[7] = 123456
+    elif kind == "huge_counts":     # Fibonacci-like counts: the unlimited Huffman tree would be far deeper than 15
+        f = [1, 1]
+        while len(f) < 46:
+            f.append(f[-1] + f[-2])
+        hist[:46] = np.minimum(np.array(f), 2**32 - 1)
+        hist[288:318] = np.array(f[:30])
+    n_words = shim.shim_bgzf_code_words()
+    assert n_words == 640
+    code = np.zeros(n_words, np.uint32)
+    shim.shim_bgzf_code(hist.ctypes.data_as(C.c_void_p), int(kind == "fixed"), code.ctypes.data_as(C.c_void_p))
+    assert ((code[:256] >> 16) >= 1).all() and ((code[:256] >> 16) <= 15).all()      # every byte value codable
+    assert (code[256:512] >> 24).max() <= 20 and (code[512:542] >> 16).max() <= 15
+    if kind == "fixed":
+        assert int(code[545]) == 3 and int(code[546]) == 3 and int(code[544]) == 7 << 16
+    # a token stream with every literal, every match length and distances over the whole window
+    data, tokens = bytearray(), []
+    for v in list(range(256)) + [int(x) for x in rng.integers(0, 256, 3000)]:
+        data.append(v)
+        tokens.append(v)
+    for L in list(range(3, 259)) + [int(x) for x in rng.integers(3, 259, 300)]:
+        D = int(rng.integers(1, min(len(data), 32768) + 1))
+        for k in range(L):
+            data.append(data[len(data) - D])
+        tokens.append((L, D))
+        data.append(L & 0xFF)
+        tokens.append(L & 0xFF)
+    while len(data) < 40000:
+        data.append(0)
+        tokens.append(0)
+    for D in (1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 16, 17, 24, 25, 32, 33, 48, 49, 64, 65, 96, 97, 128, 129, 192, 193, 256, 257, 384, 385, 512, 513,
+              768, 769, 1024, 1025, 1536, 1537, 2048, 2049, 3072, 3073, 4096, 4097, 6144, 6145, 8192, 8193, 12288, 12289, 16384, 16385,
+              24576, 24577, 32768):
+        for k in range(5):
+            data.append(data[len(data) - D])
+        tokens.append((5, D))
+    z = _bgzf_encode(code, tokens)
+    d = zlib.decompressobj(-15)
+    out = d.decompress(z)
+    assert d.eof and out == bytes(data)

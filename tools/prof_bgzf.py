@@ -12,3 +12,7 @@ for i in range(3):
     ctx.submit(0, i * wl.B, wl.B)
     b = ctx.wait(0)
 print("raw", b.bcf_bytes, "bgzf", b.bgzf_bytes, "ratio", b.bcf_bytes / b.bgzf_bytes, "B/cell", b.bgzf_bytes / (wl.B * wl.S))
+try:      # the per-phase counters of the development build (make -C vcfgl_b200/csrc bgzfprof; VGL_LIB=build/variants/libvgl_bgzfprof.so)
+    capi.load().vgl_bgzf_prof_dump()
+except AttributeError:
+    pass

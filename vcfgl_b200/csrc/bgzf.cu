@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace vgl {
 
@@ -39,44 +40,20 @@ constexpr int RUN = 64;                         // bytes of a literal run segmen
 constexpr int OUT_WORDS = (BGZF_IN * 9 / 8 + 64) / 4; // fixed codes: at most 9 bits per input byte, + header bits / end of block / padding
 constexpr int HASH_SLOTS = 8192;
 constexpr int MAX_RANGES = 32 * 16;
+constexpr int CRC_CHUNK = 64;                  // bytes a thread takes in the CRC pass
 
 struct Seg { // 8 bytes
     uint16_t pos, len;   // position in the block, bytes
-    uint16_t dist;       // 0: literals; else a match of `len` bytes at this distance
-    uint16_t cell;       // 1: a cell (match candidate)
+    uint32_t info;       // SEG_MATCH | distance; SEG_LIT | bits of quarters 0, 1, 2 (8 bits each); SEG_CELL: a match candidate
 };
+constexpr uint32_t SEG_MATCH = 1u << 31, SEG_LIT = 1u << 30, SEG_CELL = 1u << 29;
+constexpr uint32_t CAP_BITS = (uint32_t)OUT_WORDS * 32u - 96u; // what the block image holds (the fixed code never needs more)
 
 __device__ __forceinline__ uint32_t rev_bits(uint32_t code, int n) { return __brev(code) >> (32 - n); }
 
-// fixed Huffman code of a literal byte, already bit-reversed (codes go into the stream most significant bit first)
-__device__ __forceinline__ void lit_code(uint32_t v, uint32_t& bits, int& n)
+// distance code, number and value of its extra bits (1 <= dist <= 32768)
+__device__ __forceinline__ void dist_code(int dist, int& dc, int& deb, uint32_t& dev)
 {
-    if (v < 144u) { bits = rev_bits(0x30u + v, 8); n = 8; }
-    else { bits = rev_bits(0x190u + (v - 144u), 9); n = 9; }
-}
-// length / distance pair (3 <= len <= 258, 1 <= dist <= 32768): up to 31 bits
-__device__ __forceinline__ void match_code(int len, int dist, uint32_t& bits, int& n)
-{
-    int idx, eb;
-    uint32_t ev;
-    const int t = len - 3;
-    if (t < 8) { idx = t; eb = 0; ev = 0u; }
-    else if (len == 258) { idx = 28; eb = 0; ev = 0u; }
-    else {
-        const int hb = 31 - __clz(t);
-        eb = hb - 2;
-        idx = 4 * (hb - 1) + ((t >> eb) & 3);
-        ev = (uint32_t)t & ((1u << eb) - 1u);
-    }
-    const int sym = 257 + idx;
-    uint32_t b;
-    int nb;
-    if (sym < 280) { b = rev_bits((uint32_t)(sym - 256), 7); nb = 7; }
-    else { b = rev_bits(0xC0u + (uint32_t)(sym - 280), 8); nb = 8; }
-    b |= ev << nb;
-    nb += eb;
-    int dc, deb;
-    uint32_t dev;
     if (dist <= 4) { dc = dist - 1; deb = 0; dev = 0u; }
     else {
         const int u = dist - 1, hb = 31 - __clz(u);
@@ -84,12 +61,29 @@ __device__ __forceinline__ void match_code(int len, int dist, uint32_t& bits, in
         dc = 2 * hb + ((u >> deb) & 1);
         dev = (uint32_t)u & ((1u << deb) - 1u);
     }
-    b |= rev_bits((uint32_t)dc, 5) << nb;
-    nb += 5;
-    b |= dev << nb;
-    nb += deb;
+}
+// length / distance pair (3 <= len <= 258) from the context's code tables: up to 20 + 15 + 13 bits
+__device__ __forceinline__ void match_code(const uint32_t* len_tab, const uint32_t* dist_tab, int len, int dist, unsigned long long& bits, int& n)
+{
+    const uint32_t le = len_tab[len - 3];
+    int dc, deb;
+    uint32_t dev;
+    dist_code(dist, dc, deb, dev);
+    const uint32_t de = dist_tab[dc];
+    int nb = (int)(le >> 24);
+    unsigned long long b = le & 0xFFFFFFu;
+    b |= (unsigned long long)(de & 0xFFFFu) << nb;
+    nb += (int)(de >> 16);
+    b |= (unsigned long long)dev << nb;
     bits = b;
-    n = nb;
+    n = nb + deb;
+}
+__device__ __forceinline__ int match_bits(const uint32_t* len_tab, const uint32_t* dist_tab, int len, int dist)
+{
+    int dc, deb;
+    uint32_t dev;
+    dist_code(dist, dc, deb, dev);
+    return (int)(len_tab[len - 3] >> 24) + (int)(dist_tab[dc] >> 16) + deb;
 }
 
 // ORs `n` (<= 32) bits into the block image at bit offset `at`
@@ -98,6 +92,16 @@ __device__ __forceinline__ void put_bits(uint32_t* out, unsigned at, uint32_t bi
     const unsigned w = at >> 5, sh = at & 31u;
     atomicOr(&out[w], bits << sh);
     if (sh + (unsigned)n > 32u) atomicOr(&out[w + 1], bits >> (32u - sh));
+}
+
+// ... up to 57 bits
+__device__ __forceinline__ void put_bits64(uint32_t* out, unsigned at, unsigned long long bits, int n)
+{
+    const unsigned w = at >> 5, sh = at & 31u;
+    atomicOr(&out[w], (uint32_t)bits << sh);
+    const unsigned long long rest = bits >> (32u - sh); // sh = 0: the upper word
+    if (sh + (unsigned)n > 32u) atomicOr(&out[w + 1], (uint32_t)rest);
+    if (sh + (unsigned)n > 64u) atomicOr(&out[w + 2], (uint32_t)(rest >> 32));
 }
 
 // a * b mod P over GF(2) in the reflected representation of CRC-32 (P = 0xEDB88320): shifts a CRC across the bytes that follow
@@ -111,6 +115,19 @@ __host__ __device__ inline uint32_t crc_mul(uint32_t a, uint32_t b)
         }
         m >>= 1;
         b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+
+// the same product, branch-free (device: every lane takes the same 32 steps)
+__device__ __forceinline__ uint32_t crc_mul_dev(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0u;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        p ^= b & (uint32_t)((int32_t)a >> 31); // bit 31 of a: the x^0 term in the reflected representation
+        a <<= 1;
+        b = (b >> 1) ^ (0xEDB88320u & (0u - (b & 1u)));
     }
     return p;
 }
@@ -139,8 +156,98 @@ __device__ __forceinline__ uint32_t word_at(const uint8_t* base, uint32_t pos)
     return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
 }
 
+// The part of every record that lies in block `blk` ([b0, b0 + L) of the stream), split at the FORMAT planes: ranges of whole
+// cells and the gaps between them (one warp, a lane per record).  rng[i] = {pos, len, cell bytes (0: gap), first segment}.
+// state: 0 = ranges written, 1 = the block goes out as literals, 2 = more than cap_rng ranges (nothing written)
+__device__ void bgzf_block_ranges(const BgzfArgs& a, int blk, long long b0, int L, int lane, uint32_t* rng, int cap_rng, int& n_rng, int& n_seg, int& state)
+{
+    const int lo = a.blk_first[blk];
+    const int r = lo + lane;
+    int my_n = 0;
+    uint32_t my[16][3]; // pos, len, cell
+    long long rs = 0, re = 0;
+    if (r < a.n_sites) { rs = a.rec_off[r]; re = a.rec_off[r + 1]; }
+    const bool has = r < a.n_sites && re > rs && rs < b0 + L && re > b0;
+    if (has) {
+        const BcfRecPlanes pl = a.planes[r];
+        long long cur = max(rs, b0); // next byte of the record not yet put into a range
+        const long long end = min(re, b0 + L);
+        for (int k = 0; k < (int)pl.n && k < 7; ++k) {
+            const long long ps = rs + pl.off[k], pe = ps + (long long)pl.cell[k] * a.S;
+            if (pl.cell[k] < 3 || pl.cell[k] > RUN || pe <= cur || ps >= end) continue; // deflate matches are at least 3 bytes long; segments at most RUN
+            // full cells of this plane inside [cur, end)
+            long long c_lo = ps >= cur ? 0 : (cur - ps + pl.cell[k] - 1) / pl.cell[k];
+            long long c_hi = pe <= end ? a.S : (end - ps) / pl.cell[k];
+            if (c_hi <= c_lo) continue;
+            const long long cs = ps + c_lo * pl.cell[k], ce = ps + c_hi * pl.cell[k];
+            if (cs > cur) { my[my_n][0] = (uint32_t)(cur - b0); my[my_n][1] = (uint32_t)(cs - cur); my[my_n][2] = 0u; ++my_n; }
+            my[my_n][0] = (uint32_t)(cs - b0); my[my_n][1] = (uint32_t)(ce - cs); my[my_n][2] = pl.cell[k]; ++my_n;
+            cur = ce;
+        }
+        if (cur < end) { my[my_n][0] = (uint32_t)(cur - b0); my[my_n][1] = (uint32_t)(end - cur); my[my_n][2] = 0u; ++my_n; }
+    }
+    // more than 32 records in one block (a handful of samples): the block goes out as literals, nothing to gain there
+    const long long last_end = __shfl_sync(0xffffffffu, has ? re : 0, 31);
+    const bool overflow = lo + 32 < a.n_sites && last_end < b0 + L && __shfl_sync(0xffffffffu, (int)has, 31);
+    int segs_mine = 0, bytes_mine = 0;
+    for (int k = 0; k < my_n; ++k) {
+        segs_mine += my[k][2] ? (int)(my[k][1] / my[k][2]) : (int)((my[k][1] + RUN - 1) / RUN);
+        bytes_mine += (int)my[k][1];
+    }
+    const bool covered = __reduce_add_sync(0xffffffffu, bytes_mine) == L; // else: records beyond the 32 lanes (skipped sites in between)
+    int inc_r = my_n, inc_s = segs_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t1 = __shfl_up_sync(0xffffffffu, inc_r, o), t2 = __shfl_up_sync(0xffffffffu, inc_s, o);
+        if (lane >= o) { inc_r += t1; inc_s += t2; }
+    }
+    const int tot_r = __shfl_sync(0xffffffffu, inc_r, 31), tot_s = __shfl_sync(0xffffffffu, inc_s, 31);
+    n_rng = tot_r;
+    n_seg = tot_s;
+    if (overflow || !covered || tot_s > MAX_SEG || tot_r > MAX_RANGES) {
+        state = 1;
+    } else if (tot_r > cap_rng) {
+        state = 2;
+    } else {
+        state = 0;
+        int r0 = inc_r - my_n, s0 = inc_s - segs_mine;
+        for (int k = 0; k < my_n; ++k) {
+            rng[(r0 + k) * 4 + 0] = my[k][0]; rng[(r0 + k) * 4 + 1] = my[k][1]; rng[(r0 + k) * 4 + 2] = my[k][2]; rng[(r0 + k) * 4 + 3] = (uint32_t)s0;
+            s0 += my[k][2] ? (int)(my[k][1] / my[k][2]) : (int)((my[k][1] + RUN - 1) / RUN);
+        }
+    }
+}
+
+// a warp per block: the block's ranges into its slot of rng_g ({ranges, segments, state, -}, then the ranges)
+__global__ void __launch_bounds__(256) k_bgzf_ranges(const BgzfArgs a)
+{
+    const long long total = a.totals[3];
+    const long long nblk = total > a.in_cap ? 0 : (total + BGZF_IN - 1) / BGZF_IN;
+    const int lane = threadIdx.x & 31;
+    const long long blk = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (blk >= nblk) return;
+    const long long b0 = blk * BGZF_IN;
+    const int L = (int)min((long long)BGZF_IN, total - b0);
+    uint32_t* const g = a.rng_g + (size_t)blk * BGZF_RNG_WORDS;
+    int n_r = 0, n_s = 0, state = 0;
+    bgzf_block_ranges(a, (int)blk, b0, L, lane, g + 4, BGZF_RNG_LIST, n_r, n_s, state);
+    if (lane == 0) { g[0] = (uint32_t)n_r; g[1] = (uint32_t)n_s; g[2] = (uint32_t)state; g[3] = 0u; }
+}
+
+#ifdef BGZF_PROF // development: cycles between the kernel's barriers, summed over blocks (make bgzfprof; tools/prof_bgzf.py)
+__device__ unsigned long long g_bgzf_prof[16];
+#define PROFW(i) do { if (threadIdx.x == 32) { const long long t_ = clock64(); atomicAdd(&g_bgzf_prof[i], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
+#define PROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_bgzf_prof[i], (unsigned long long)(t_ - prof_t)); prof_t = t_; } } while (0)
+#else
+#define PROF(i) do { } while (0)
+#define PROFW(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs a)
 {
+#ifdef BGZF_PROF
+    long long prof_t = clock64();
+#endif
     extern __shared__ __align__(16) unsigned char sm[];
     uint8_t* const in = sm;                                                       // [BGZF_IN]
     uint32_t* const out = reinterpret_cast<uint32_t*>(sm + BGZF_IN);              // [OUT_WORDS]
@@ -149,7 +256,8 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     uint32_t* const htab = seg_bit + MAX_SEG;                                     // [HASH_SLOTS] tag << 16 | position
     uint32_t* const rng = htab + HASH_SLOTS;                                      // [MAX_RANGES][4]: pos, len, cell bytes (0: gap), first segment
     __shared__ uint32_t crc_tab[1024]; // slicing-by-four tables of CRC-32
-    __shared__ uint16_t lit_tab[256];
+    __shared__ uint32_t lit_tab[256], len_tab[256], dist_tab[32]; // the context's prefix code (BgzfCode)
+    __shared__ uint32_t eob_s, hdr_bits_s;
     __shared__ uint32_t warp_tot[32];
     __shared__ int n_rng_s, n_seg_s, lit_only_s;
     __shared__ uint32_t crc_s, total_bits_s;
@@ -163,104 +271,68 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     // ---- warps 1..: the block's bytes, the CRC and literal-code tables, cleared tables; meanwhile warp 0: the ranges
     if (warp > 0) {
         const int t = tid - 32, nt = BGZF_THREADS - 32;
-        for (int i = t; i < (L + 15) / 16; i += nt) reinterpret_cast<uint4*>(in)[i] = __ldcs(reinterpret_cast<const uint4*>(a.in + b0) + i);
+        // the block's bytes are requested first and stored last: everything in between runs under the latency of the loads
+        const uint4* const src = reinterpret_cast<const uint4*>(a.in + b0);
+        const int n16 = (L + 15) / 16; // <= 2048 = 2.07 per thread
+        uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0, v2 = v0;
+        if (t < n16) v0 = __ldcs(src + t);
+        if (t + nt < n16) v1 = __ldcs(src + t + nt);
+        if (t + 2 * nt < n16) v2 = __ldcs(src + t + 2 * nt);
+        for (int i = t; i < 1024; i += nt) crc_tab[i] = __ldg(a.crc_pow + 1024 + i);
+        if (t < 256) {
+            lit_tab[t] = __ldg(a.code->lit + t);
+            len_tab[t] = __ldg(a.code->len + t);
+            if (t < 32) dist_tab[t] = __ldg(a.code->dist + t);
+        }
+        if (t == 0) { crc_s = 0u; eob_s = a.code->eob; hdr_bits_s = a.code->hdr_bits; }
         for (int i = t; i < OUT_WORDS / 4; i += nt) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = t; i < HASH_SLOTS / 4; i += nt) reinterpret_cast<uint4*>(htab)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        if (t < 256) {
-            uint32_t c = (uint32_t)t;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
-            crc_tab[t] = c;
-            uint32_t c1 = c;
-#pragma unroll
-            for (int lvl = 1; lvl < 4; ++lvl) { // T_lvl[i] = the CRC register after byte i and lvl zero bytes
-                uint32_t z = c1 & 0xFFu;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) z = (z & 1u) ? (z >> 1) ^ 0xEDB88320u : z >> 1;
-                c1 = z ^ (c1 >> 8);
-                crc_tab[256 * lvl + t] = c1;
-            }
-            uint32_t b;
-            int n;
-            lit_code((uint32_t)t, b, n);
-            lit_tab[t] = (uint16_t)(b | ((uint32_t)(n - 8) << 15)); // 9 code bits, bit 15: one more than 8
-        }
-        if (t == 0) crc_s = 0u;
-        // CRC32 of the block while warp 0 is busy with the ranges: 32-byte chunks from the end (slicing by four), each shifted
+        if (t < n16) reinterpret_cast<uint4*>(in)[t] = v0;
+        if (t + nt < n16) reinterpret_cast<uint4*>(in)[t + nt] = v1;
+        if (t + 2 * nt < n16) reinterpret_cast<uint4*>(in)[t + 2 * nt] = v2;
+        PROFW(8); // load, clear, tables issued
+        // CRC32 of the block: 64-byte chunks from the end (slicing by four), each shifted
         // across the bytes behind it.  Barrier 1 = warps 1 .. 31 only.
         asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
-        for (int c = t; c < 1024; c += nt) {
-            const int hi = L - c * 32, lo2 = max(hi - 32, 0);
+        PROFW(9); // barrier of warps 1..31 (the loads have landed)
+        if (!a.hist && t < (int)((hdr_bits_s + 31u) >> 5)) out[t] = a.code->hdr[t]; // the block header (the image is cleared)
+        for (int c = t; c < BGZF_IN / CRC_CHUNK; c += nt) {
+            const int hi = L - c * CRC_CHUNK, lo2 = max(hi - CRC_CHUNK, 0);
             if (hi <= 0) break;
             uint32_t r = 0xFFFFFFFFu;
-            int k = lo2;
-            for (; k < hi && ((hi - k) & 3); ++k) r = crc_tab[(r ^ in[k]) & 0xFFu] ^ (r >> 8); // head bytes: the rest is whole words
-            for (; k < hi; k += 4) {
-                r ^= word_at(in, (uint32_t)k);
+            auto step = [&](uint32_t w) {
+                r ^= w;
                 r = crc_tab[768 + (r & 0xFFu)] ^ crc_tab[512 + ((r >> 8) & 0xFFu)] ^ crc_tab[256 + ((r >> 16) & 0xFFu)] ^ crc_tab[r >> 24];
+            };
+            if (hi - lo2 == CRC_CHUNK && (lo2 & 15) == 0) { // a whole aligned chunk: 128-bit loads (word loads at this stride collide on four banks)
+#pragma unroll
+                for (int q = 0; q < CRC_CHUNK / 16; ++q) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(in + lo2 + 16 * q);
+                    step(v.x); step(v.y); step(v.z); step(v.w);
+                }
+            } else {
+                int k = lo2;
+                for (; k < hi && ((hi - k) & 3); ++k) r = crc_tab[(r ^ in[k]) & 0xFFu] ^ (r >> 8); // head bytes: the rest is whole words
+                for (; k < hi; k += 4) step(word_at(in, (uint32_t)k));
             }
-            const uint32_t part = crc_mul(a.crc_pow[c], ~r);
+            const uint32_t part = crc_mul_dev(__ldg(a.crc_pow + c), ~r);
             if (part) atomicXor(&crc_s, part);
         }
+        PROFW(10); // CRC (warp 1)
     }
 
-    // ---- ranges: the part of every record that lies in the block, split at the FORMAT planes (warp 0, a lane per record)
+    // ---- ranges: made by k_bgzf_ranges ahead of this kernel (on one warp they would take as long as everything else here)
     if (warp == 0) {
-        if (lane == 0) { n_rng_s = 0; n_seg_s = 0; lit_only_s = 0; }
-        __syncwarp();
-        const int lo = a.blk_first[blockIdx.x];
-        const int r = lo + lane;
-        int my_n = 0;
-        uint32_t my[16][3]; // pos, len, cell
-        long long rs = 0, re = 0;
-        if (r < a.n_sites) { rs = a.rec_off[r]; re = a.rec_off[r + 1]; }
-        const bool has = r < a.n_sites && re > rs && rs < b0 + L && re > b0;
-        if (has) {
-            const BcfRecPlanes pl = a.planes[r];
-            long long cur = max(rs, b0); // next byte of the record not yet put into a range
-            const long long end = min(re, b0 + L);
-            for (int k = 0; k < (int)pl.n && k < 7; ++k) {
-                const long long ps = rs + pl.off[k], pe = ps + (long long)pl.cell[k] * a.S;
-                if (pl.cell[k] < 3 || pl.cell[k] > RUN || pe <= cur || ps >= end) continue; // deflate matches are at least 3 bytes long; segments at most RUN
-                // full cells of this plane inside [cur, end)
-                long long c_lo = ps >= cur ? 0 : (cur - ps + pl.cell[k] - 1) / pl.cell[k];
-                long long c_hi = pe <= end ? a.S : (end - ps) / pl.cell[k];
-                if (c_hi <= c_lo) continue;
-                const long long cs = ps + c_lo * pl.cell[k], ce = ps + c_hi * pl.cell[k];
-                if (cs > cur) { my[my_n][0] = (uint32_t)(cur - b0); my[my_n][1] = (uint32_t)(cs - cur); my[my_n][2] = 0u; ++my_n; }
-                my[my_n][0] = (uint32_t)(cs - b0); my[my_n][1] = (uint32_t)(ce - cs); my[my_n][2] = pl.cell[k]; ++my_n;
-                cur = ce;
-            }
-            if (cur < end) { my[my_n][0] = (uint32_t)(cur - b0); my[my_n][1] = (uint32_t)(end - cur); my[my_n][2] = 0u; ++my_n; }
-        }
-        // more than 32 records in one block (a handful of samples): the block goes out as literals, nothing to gain there
-        const long long last_end = __shfl_sync(0xffffffffu, has ? re : 0, 31);
-        const bool overflow = lo + 32 < a.n_sites && last_end < b0 + L && __shfl_sync(0xffffffffu, (int)has, 31);
-        int segs_mine = 0, bytes_mine = 0;
-        for (int k = 0; k < my_n; ++k) {
-            segs_mine += my[k][2] ? (int)(my[k][1] / my[k][2]) : (int)((my[k][1] + RUN - 1) / RUN);
-            bytes_mine += (int)my[k][1];
-        }
-        const bool covered = __reduce_add_sync(0xffffffffu, bytes_mine) == L; // else: records beyond the 32 lanes (skipped sites in between)
-        int inc_r = my_n, inc_s = segs_mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t1 = __shfl_up_sync(0xffffffffu, inc_r, o), t2 = __shfl_up_sync(0xffffffffu, inc_s, o);
-            if (lane >= o) { inc_r += t1; inc_s += t2; }
-        }
-        const int tot_r = __shfl_sync(0xffffffffu, inc_r, 31), tot_s = __shfl_sync(0xffffffffu, inc_s, 31);
-        if (overflow || !covered || tot_s > MAX_SEG || tot_r > MAX_RANGES) {
-            if (lane == 0) lit_only_s = 1;
-        } else {
-            int r0 = inc_r - my_n, s0 = inc_s - segs_mine;
-            for (int k = 0; k < my_n; ++k) {
-                rng[(r0 + k) * 4 + 0] = my[k][0]; rng[(r0 + k) * 4 + 1] = my[k][1]; rng[(r0 + k) * 4 + 2] = my[k][2]; rng[(r0 + k) * 4 + 3] = (uint32_t)s0;
-                s0 += my[k][2] ? (int)(my[k][1] / my[k][2]) : (int)((my[k][1] + RUN - 1) / RUN);
-            }
-            if (lane == 0) { n_rng_s = tot_r; n_seg_s = tot_s; }
-        }
+        const uint32_t* const g = a.rng_g + (size_t)blockIdx.x * BGZF_RNG_WORDS;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(g)); // ranges, segments, state
+        int n_r = (int)h.x, n_s = (int)h.y, state = (int)h.z;
+        if (state == 2) bgzf_block_ranges(a, (int)blockIdx.x, b0, L, lane, rng, MAX_RANGES, n_r, n_s, state); // more than the list holds
+        else if (state == 0)
+            for (int i = lane; i < n_r; i += 32) reinterpret_cast<uint4*>(rng)[i] = __ldg(reinterpret_cast<const uint4*>(g) + 1 + i);
+        if (lane == 0) { n_rng_s = n_r; n_seg_s = n_s; lit_only_s = state != 0; }
     }
     __syncthreads();
+    PROF(0); // load + tables + CRC || ranges
     if (lit_only_s) { // one gap over the whole block
         if (tid == 0) {
             rng[0] = 0u; rng[1] = (uint32_t)L; rng[2] = 0u; rng[3] = 0u;
@@ -277,13 +349,13 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         const int n = cell ? (int)(len / cell) : (int)((len + RUN - 1) / RUN);
         for (int c = lane; c < n; c += 32) {
             Seg s;
-            if (cell) { s.pos = (uint16_t)(pos + (uint32_t)c * cell); s.len = (uint16_t)cell; s.cell = 1; }
-            else { s.pos = (uint16_t)(pos + (uint32_t)c * RUN); s.len = (uint16_t)min((uint32_t)RUN, len - (uint32_t)c * RUN); s.cell = 0; }
-            s.dist = 0;
+            if (cell) { s.pos = (uint16_t)(pos + (uint32_t)c * cell); s.len = (uint16_t)cell; s.info = SEG_CELL; }
+            else { s.pos = (uint16_t)(pos + (uint32_t)c * RUN); s.len = (uint16_t)min((uint32_t)RUN, len - (uint32_t)c * RUN); s.info = 0u; }
             segs[first + c] = s;
         }
     }
     __syncthreads();
+    PROF(1); // segment table
 
     // ---- cells: hash of the bytes, first occurrence per hash (atomicMin on tag << 16 | position; open addressing)
     auto cell_hash = [&](const Seg& s) -> uint32_t { // FNV-style over 32-bit words (the tail word masked)
@@ -296,7 +368,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     };
     for (int j = tid; j < n_seg; j += BGZF_THREADS) {
         const Seg s = segs[j];
-        if (!s.cell) continue;
+        if (!(s.info & SEG_CELL)) continue;
         const uint32_t h = cell_hash(s), tag = h >> 16, mine = (tag << 16) | s.pos;
         seg_bit[j] = h; // kept for the look-up pass
         uint32_t slot = h & (HASH_SLOTS - 1);
@@ -308,134 +380,177 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         }
     }
     __syncthreads();
-    // ---- match = the first cell of the block with the same bytes; bit length of every segment
+    PROF(2); // hash insert
+    // ---- match = the first cell of the block with the same bytes
     for (int j = tid; j < n_seg; j += BGZF_THREADS) {
-        Seg s = segs[j];
-        uint32_t nbits = 0;
-        if (s.cell) {
-            const uint32_t h = seg_bit[j], tag = h >> 16;
-            uint32_t slot = h & (HASH_SLOTS - 1);
-            for (int probe = 0; probe < 16; ++probe) {
-                const uint32_t e = htab[slot];
-                if (e == 0xFFFFFFFFu) break;
-                if ((e >> 16) == tag) {
-                    const uint32_t q = e & 0xFFFFu;
-                    if (q < s.pos && q + s.len <= s.pos) { // an earlier cell (cells do not overlap)
-                        bool same = true;
-                        const int nw = s.len >> 2;
-                        for (int k = 0; k < nw && same; ++k) same = word_at(in, q + 4u * k) == word_at(in, s.pos + 4u * k);
-                        for (int k = 4 * nw; k < s.len && same; ++k) same = in[q + k] == in[s.pos + k];
-                        if (same) s.dist = (uint16_t)(s.pos - q);
-                    }
-                    break;
+        const Seg s = segs[j];
+        if (!(s.info & SEG_CELL)) continue;
+        const uint32_t h = seg_bit[j], tag = h >> 16;
+        uint32_t slot = h & (HASH_SLOTS - 1), dist = 0u;
+        for (int probe = 0; probe < 16; ++probe) {
+            const uint32_t e = htab[slot];
+            if (e == 0xFFFFFFFFu) break;
+            if ((e >> 16) == tag) {
+                const uint32_t q = e & 0xFFFFu;
+                if (q < s.pos && q + s.len <= s.pos) { // an earlier cell (cells do not overlap)
+                    bool same = true;
+                    const int nw = s.len >> 2;
+                    for (int k = 0; k < nw && same; ++k) same = word_at(in, q + 4u * k) == word_at(in, s.pos + 4u * k);
+                    for (int k = 4 * nw; k < s.len && same; ++k) same = in[q + k] == in[s.pos + k];
+                    if (same) dist = s.pos - q;
                 }
-                slot = (slot + 1) & (HASH_SLOTS - 1);
+                break;
             }
+            slot = (slot + 1) & (HASH_SLOTS - 1);
         }
-        if (s.dist) {
-            uint32_t b;
-            int n;
-            match_code(s.len, s.dist, b, n);
-            nbits = (uint32_t)n;
-            segs[j].dist = s.dist;
-            segs[j].cell = 0;
-        } else { // 8 bits per literal, 9 for the values from 144 up; the counts before quarters 1..3 go into the free cell field
-            const int ql = (s.len + 3) >> 2; // <= 16: segments are at most 64 bytes long
-            uint32_t extra = 0u, cum = 0u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { // 9-bit literals (values from 144 up) of quarter q, four bytes at a time
-                const int k0 = q * ql, k1 = min(k0 + ql, (int)s.len);
-                uint32_t part = 0u;
-                for (int k = k0; k < k1; k += 4) {
-                    uint32_t w = __vcmpgeu4(word_at(in, s.pos + (uint32_t)k), 0x90909090u) & 0x01010101u;
-                    if (k1 - k < 4) w &= (1u << (8 * (k1 - k))) - 1u;
-                    part += __popc(w);
-                }
-                if (q < 3) cum |= part << (5 * q);
-                extra += part;
-            }
-            nbits = 8u * s.len + extra;
-            segs[j].cell = (uint16_t)(0x8000u | cum); // bit 15: literal segment
-        }
-        seg_bit[j] = nbits;
+        segs[j].info = dist ? (SEG_MATCH | dist) : 0u;
     }
-    __syncthreads();
-    // ---- exclusive prefix of the bit lengths (8 segments per thread), 3 header bits in front
-    {
-        uint32_t v[MAX_SEG / BGZF_THREADS], sum = 0u;
-#pragma unroll
-        for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
-            const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
-            v[k] = j < n_seg ? seg_bit[j] : 0u;
-            sum += v[k];
-        }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
+    if (a.hist) { // statistics pass (vgl_submit, once per context): symbol counts of this parse, nothing is written
         __syncthreads();
-        if (warp == 0) {
-            uint32_t t = warp_tot[lane];
+        uint32_t* const hist = out; // cleared above
+        for (int j = tid; j < n_seg; j += BGZF_THREADS) {
+            const Seg s = segs[j];
+            if (s.info & SEG_MATCH) {
+                const int t = s.len - 3;
+                int idx;
+                if (t < 8) idx = t;
+                else if (s.len == 258) idx = 28;
+                else { const int hb = 31 - __clz(t); idx = 4 * (hb - 1) + ((t >> (hb - 2)) & 3); }
+                int dc, deb;
+                uint32_t dev;
+                dist_code((int)(s.info & 0xFFFFu), dc, deb, dev);
+                atomicAdd(&hist[257 + idx], 1u);
+                atomicAdd(&hist[288 + dc], 1u);
+            } else {
+                for (int k = 0; k < s.len; ++k) atomicAdd(&hist[in[s.pos + k]], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < BGZF_HIST && hist[tid]) atomicAdd(&a.hist[tid], hist[tid]);
+        if (tid == 0) atomicAdd(&a.hist[256], 1u);
+        return;
+    }
+    // ---- bit length of every segment under the context's code, exclusive prefix; should the image not hold them (a code
+    // built from other statistics), once more under the fixed code, which always fits
+    for (int attempt = 0;; ++attempt) {
+        PROF(3); // match
+        for (int j = tid; j < n_seg; j += BGZF_THREADS) {
+            const Seg s = segs[j];
+            uint32_t nbits;
+            if (s.info & SEG_MATCH) {
+                nbits = (uint32_t)match_bits(len_tab, dist_tab, s.len, (int)(s.info & 0xFFFFu));
+            } else { // the bits of quarters 0..2 are kept with the segment (the emitters take a quarter each)
+                const int ql = (s.len + 3) >> 2; // <= 16: segments are at most 64 bytes long
+                uint32_t tot = 0u, cum = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k0 = q * ql, k1 = min(k0 + ql, (int)s.len);
+                    uint32_t part = 0u;
+                    for (int k = k0; k < k1; ++k) part += lit_tab[in[s.pos + k]] >> 16;
+                    if (q < 3) cum |= part << (8 * q);
+                    tot += part;
+                }
+                nbits = tot;
+                segs[j].info = SEG_LIT | cum;
+            }
+            seg_bit[j] = nbits;
+        }
+        __syncthreads();
+        PROF(4); // bit lengths
+        {
+            uint32_t v[MAX_SEG / BGZF_THREADS], sum = 0u;
+#pragma unroll
+            for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
+                const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
+                v[k] = j < n_seg ? seg_bit[j] : 0u;
+                sum += v[k];
+            }
+            uint32_t inc = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += u;
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
             }
-            warp_tot[lane] = t;
+            if (lane == 31) warp_tot[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t t = warp_tot[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, t, o);
+                    if (lane >= o) t += u;
+                }
+                warp_tot[lane] = t;
+            }
+            __syncthreads();
+            uint32_t base = hdr_bits_s + (warp ? warp_tot[warp - 1] : 0u) + inc - sum;
+#pragma unroll
+            for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
+                const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
+                if (j < n_seg) seg_bit[j] = base;
+                base += v[k];
+            }
+            if (tid == BGZF_THREADS - 1) total_bits_s = base;
         }
         __syncthreads();
-        uint32_t base = 3u + (warp ? warp_tot[warp - 1] : 0u) + inc - sum;
-#pragma unroll
-        for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
-            const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
-            if (j < n_seg) seg_bit[j] = base;
-            base += v[k];
+        PROF(5); // prefix
+        if (attempt == 1 || total_bits_s + (eob_s >> 16) <= CAP_BITS) break;
+        const uint32_t old_words = (hdr_bits_s + 31u) >> 5;
+        __syncthreads();
+        if (tid < 256) {
+            lit_tab[tid] = a.code_fixed->lit[tid];
+            len_tab[tid] = a.code_fixed->len[tid];
+            if (tid < 32) dist_tab[tid] = a.code_fixed->dist[tid];
         }
-        if (tid == BGZF_THREADS - 1) total_bits_s = base;
+        if (tid < (int)old_words) out[tid] = tid == 0 ? 3u : 0u; // BFINAL = 1, BTYPE = 01
+        if (tid == 0) { eob_s = a.code_fixed->eob; hdr_bits_s = a.code_fixed->hdr_bits; }
+        __syncthreads();
     }
-    __syncthreads();
-    // ---- bits: BFINAL = 1, BTYPE = 01 (fixed Huffman), the segments, end of block (7 zero bits: already there).
+    // ---- bits: the segments, then the end-of-block code.
     // A literal segment is split into quarters (their bit offsets follow from the counts kept with the segment).
-    if (tid == 0) atomicOr(&out[0], 3u);
+    if (tid == 0) put_bits(out, total_bits_s, eob_s & 0xFFFFu, (int)(eob_s >> 16));
     {
         // a warp takes 32 consecutive segments: the matches go out one per lane, then the literal segments of the group are
         // spread over the lanes a quarter each, so that the byte loops run on full warps
         for (int j0 = warp * 32; j0 < n_seg; j0 += (BGZF_THREADS / 32) * 32) {
             const int j = j0 + lane;
             Seg s;
-            s.pos = s.len = s.dist = s.cell = 0;
+            s.pos = s.len = 0; s.info = 0u;
             if (j < n_seg) s = segs[j];
-            if (s.dist) {
-                uint32_t bb;
+            if (s.info & SEG_MATCH) {
+                unsigned long long bb;
                 int n;
-                match_code(s.len, s.dist, bb, n);
-                put_bits(out, seg_bit[j], bb, n);
+                match_code(len_tab, dist_tab, s.len, (int)(s.info & 0xFFFFu), bb, n);
+                put_bits64(out, seg_bit[j], bb, n);
             }
-            const uint32_t litm = __ballot_sync(0xffffffffu, j < n_seg && (s.cell & 0x8000u));
+            const uint32_t litm = __ballot_sync(0xffffffffu, j < n_seg && (s.info & SEG_LIT));
             const int ntask = 4 * __popc(litm);
             for (int t = lane; t < ntask; t += 32) {
                 const int jj = j0 + (int)__fns(litm, 0u, (t >> 2) + 1), q = t & 3;
                 const Seg ls = segs[jj];
                 const int ql = (ls.len + 3) >> 2, k0 = q * ql, k1 = min(k0 + ql, (int)ls.len);
                 if (k0 >= k1) continue;
-                const unsigned c = ls.cell; // 9-bit literals in quarters 0, 1, 2: five bits each
-                const unsigned cum = (q > 0 ? c & 31u : 0u) + (q > 1 ? (c >> 5) & 31u : 0u) + (q > 2 ? (c >> 10) & 31u : 0u);
-                unsigned at = seg_bit[jj] + 8u * (unsigned)k0 + cum;
+                const unsigned c = ls.info; // bits of quarters 0, 1, 2
+                const unsigned cum = (q > 0 ? c & 255u : 0u) + (q > 1 ? (c >> 8) & 255u : 0u) + (q > 2 ? (c >> 16) & 255u : 0u);
+                unsigned at = seg_bit[jj] + cum;
                 unsigned w = at >> 5;
                 int fill = (int)(at & 31u);
                 unsigned long long acc = 0ull;
-                for (int k = k0; k < k1; ++k) {
-                    const uint32_t e = lit_tab[in[ls.pos + k]];
-                    acc |= (unsigned long long)(e & 0x1FFu) << fill;
-                    fill += 8 + (int)(e >> 15);
-                    if (fill >= 32) {
-                        atomicOr(&out[w], (uint32_t)acc);
-                        ++w;
-                        acc >>= 32;
-                        fill -= 32;
+                for (int k = k0; k < k1; k += 4) { // four look-ups in flight, the codes go in as pairs (<= 30 bits)
+                    uint32_t e[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) e[i] = k + i < k1 ? lit_tab[in[ls.pos + k + i]] : 0u; // past the end: no bits
+#pragma unroll
+                    for (int i = 0; i < 4; i += 2) {
+                        const uint32_t n0 = e[i] >> 16;
+                        acc |= (unsigned long long)((e[i] & 0xFFFFu) | ((e[i + 1] & 0xFFFFu) << n0)) << fill;
+                        fill += (int)(n0 + (e[i + 1] >> 16));
+                        if (fill >= 32) {
+                            atomicOr(&out[w], (uint32_t)acc);
+                            ++w;
+                            acc >>= 32;
+                            fill -= 32;
+                        }
                     }
                 }
                 if (fill > 0) atomicOr(&out[w], (uint32_t)acc);
@@ -443,8 +558,9 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         }
     }
     __syncthreads();
+    PROF(6); // emission
     // ---- the BGZF block: header, deflate data, CRC32, ISIZE -> its slot of the staging buffer
-    const uint32_t nbytes = (total_bits_s + 7u + 7u) >> 3; // + the 7-bit end-of-block code, rounded up to a byte
+    const uint32_t nbytes = (total_bits_s + (eob_s >> 16) + 7u) >> 3; // + the end-of-block code, rounded up to a byte
     const uint32_t bsize = 18u + nbytes + 8u;
     uint8_t* const dst = a.stage + (size_t)blockIdx.x * BGZF_STRIDE + 2; // + 2: the deflate data (at + 18) starts on a word
     if (tid < 18) {
@@ -462,6 +578,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         dst[18 + nbytes + tid] = (uint8_t)(v >> (8 * (tid & 3)));
     }
     if (tid == 0) a.blk_size[blockIdx.x] = bsize;
+    PROF(7); // copy out (thread 0's share)
 }
 
 // exclusive prefix of the block sizes; the totals for the host: [4] compressed bytes, [5] blocks
@@ -531,26 +648,56 @@ __global__ void __launch_bounds__(256) k_bgzf_pack(const BgzfArgs a)
 
 } // namespace
 
+#ifdef BGZF_PROF
+extern "C" void vgl_bgzf_prof_dump()
+{
+    unsigned long long h[16];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_bgzf_prof, sizeof h);
+    static const char* names[11] = {"load+crc||ranges", "segment table", "hash insert", "match", "bit lengths", "prefix", "emission", "copy out", "  w1: issue loads", "  w1: bar 1", "  w1: crc"};
+    unsigned long long tot = 0;
+    for (int i = 0; i < 8; ++i) tot += h[i];
+    fprintf(stderr, "bgzf cycles (thread 0, all blocks) %.4g\n", (double)tot);
+    for (int i = 0; i < 11; ++i) fprintf(stderr, "bgzf phase %-18s %6.2f %%\n", names[i], 100.0 * (double)h[i] / (double)(tot ? tot : 1));
+    memset(h, 0, sizeof h);
+    cudaMemcpyToSymbol(g_bgzf_prof, h, sizeof h);
+}
+#endif
+
 size_t bgzf_dyn_smem() { return (size_t)BGZF_IN + (size_t)OUT_WORDS * 4 + (size_t)MAX_SEG * (sizeof(Seg) + 4) + (size_t)HASH_SLOTS * 4 + (size_t)MAX_RANGES * 16; }
 
 // blocks a record stream of `bytes` bytes makes
 int64_t bgzf_blocks_for(int64_t bytes) { return (bytes + BGZF_IN - 1) / BGZF_IN; }
 
-// x^(8 * 32 * k) mod P for k = 0 .. 1023 (reflected CRC-32 representation)
+// [0..1023] x^(8 * CRC_CHUNK * k) mod P (reflected CRC-32 representation); [1024..2047] the slicing-by-four tables of CRC-32:
+// T_lvl[i] = the CRC register after byte i and lvl zero bytes
 void bgzf_crc_pow_table(uint32_t* t)
 {
     uint32_t x8 = 1u << 31; // x^0
     for (int k = 0; k < 8; ++k) x8 = crc_mul(x8, 1u << 30); // times x
-    uint32_t x256 = 1u << 31;
-    for (int k = 0; k < 32; ++k) x256 = crc_mul(x256, x8);
+    uint32_t xc = 1u << 31;
+    for (int k = 0; k < CRC_CHUNK; ++k) xc = crc_mul(xc, x8);
     t[0] = 1u << 31;
-    for (int k = 1; k < 1024; ++k) t[k] = crc_mul(t[k - 1], x256);
+    for (int k = 1; k < 1024; ++k) t[k] = crc_mul(t[k - 1], xc);
+    uint32_t* const tab = t + 1024;
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+        tab[i] = c;
+    }
+    for (int lvl = 1; lvl < 4; ++lvl)
+        for (uint32_t i = 0; i < 256; ++i) tab[256 * lvl + i] = tab[tab[256 * (lvl - 1) + i] & 0xFFu] ^ (tab[256 * (lvl - 1) + i] >> 8);
 }
 
 void launch_bgzf(const BgzfArgs& a, int64_t max_blocks, cudaStream_t st, int n_sms)
 {
     cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bgzf_dyn_smem()); // per device
     k_bgzf_first<<<(unsigned)std::min<int64_t>((max_blocks + 255) / 256, 4096), 256, 0, st>>>(a);
+    k_bgzf_ranges<<<(unsigned)((max_blocks + 7) / 8), 256, 0, st>>>(a);
+    if (a.hist) { // symbol statistics of (at most the first 8192 blocks of) this record stream
+        k_bgzf_deflate<<<(unsigned)std::min<int64_t>(max_blocks, 8192), BGZF_THREADS, bgzf_dyn_smem(), st>>>(a);
+        return;
+    }
     k_bgzf_deflate<<<(unsigned)max_blocks, BGZF_THREADS, bgzf_dyn_smem(), st>>>(a);
     k_bgzf_scan<<<1, 1024, 0, st>>>(a);
     k_bgzf_pack<<<(unsigned)(n_sms * 8), 256, 0, st>>>(a);

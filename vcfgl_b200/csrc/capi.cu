@@ -52,6 +52,7 @@ struct Slot {
     // VGL_HOST_BGZF: plane layout of every record, block staging, block sizes / offsets, the compressed stream (device + pinned)
     BcfRecPlanes* d_planes = nullptr;
     uint8_t *d_stage = nullptr, *d_bgzf = nullptr, *h_bgzf = nullptr;
+    uint32_t* d_blk_rng = nullptr;
     uint32_t* d_blk_size = nullptr;
     long long* d_blk_off = nullptr;
     int32_t* d_blk_first = nullptr;
@@ -110,6 +111,9 @@ struct vgl_ctx {
     int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
     size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
     int64_t bgzf_max_blocks = 0;           // VGL_HOST_BGZF: blocks a full record stream makes
+    BgzfCode* d_bgzf_code = nullptr;       // [2]: the context's prefix code, deflate's fixed code
+    uint32_t* d_bgzf_hist = nullptr;       // symbol counts of the statistics pass
+    bool bgzf_code_ready = false;          // [0] built from the first batch's record stream (vgl_submit)
     double stream_bytes_per_site = 0.0;    // VGL_HOST_BCF / BGZF: bytes per site of the last finished batch (predicts the next copy)
     // VGL_HOST_BCF with -doGVCF: thresholds, and the block still open at the end of the last waited batch (the seam)
     std::vector<int32_t> gvcf_dps;
@@ -278,7 +282,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         cudaFreeHost(s.h_pl8); cudaFreeHost(s.h_dpn); cudaFreeHost(s.h_adn); cudaFreeHost(s.h_adfn); cudaFreeHost(s.h_adrn);
         cudaFreeHost(s.h_bcf_in); cudaFreeHost(s.h_blob); cudaFreeHost(s.h_bcf); cudaFreeHost(s.h_rec_off);
         cudaFree(s.d_bcf_in); cudaFree(s.d_blob); cudaFree(s.d_bcf); cudaFree(s.d_minmax); cudaFree(s.d_rec_len); cudaFree(s.d_rec_off);
-        cudaFree(s.d_planes); cudaFree(s.d_stage); cudaFree(s.d_bgzf); cudaFreeHost(s.h_bgzf); cudaFree(s.d_blk_size); cudaFree(s.d_blk_off); cudaFree(s.d_blk_first);
+        cudaFree(s.d_planes); cudaFree(s.d_stage); cudaFree(s.d_bgzf); cudaFreeHost(s.h_bgzf); cudaFree(s.d_blk_size); cudaFree(s.d_blk_off); cudaFree(s.d_blk_first); cudaFree(s.d_blk_rng);
         cudaFree(s.d_pl8); cudaFree(s.d_dpn); cudaFree(s.d_adn); cudaFree(s.d_adfn); cudaFree(s.d_adrn);
         cudaFree(s.d_gt); cudaFree(s.d_dp); cudaFree(s.d_cell); cudaFree(s.d_cellq); cudaFree(s.d_celltail);
         cudaFree(s.d_sites); cudaFree(s.d_totals); cudaFree(s.d_pairmap); cudaFree(s.d_tile_state);
@@ -288,7 +292,7 @@ extern "C" void vgl_destroy(vgl_ctx* ctx)
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_m1_bsum); cudaFree(ctx->d_m1_het); cudaFree(ctx->d_fk); cudaFree(ctx->d_beta);
-    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_alias_row); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park); cudaFree(ctx->d_m1_pure); cudaFree(ctx->d_crc_pow);
+    cudaFree(ctx->d_depth_means); cudaFree(ctx->d_pois); cudaFree(ctx->d_alias); cudaFree(ctx->d_alias_row); cudaFree(ctx->d_bgzf_code); cudaFree(ctx->d_bgzf_hist); cudaFree(ctx->d_errcdf); cudaFree(ctx->d_cnt_scratch); cudaFree(ctx->d_qcls); cudaFree(ctx->d_m2_cmap); cudaFree(ctx->d_m2_tab); cudaFree(ctx->d_qm_cdf); cudaFree(ctx->d_m2_pure); cudaFree(ctx->d_m2_park); cudaFree(ctx->d_m1_pure); cudaFree(ctx->d_crc_pow);
     delete ctx;
 }
 
@@ -522,8 +526,17 @@ static int create_impl(vgl_ctx* ctx)
                 CK(cudaMalloc((void**)&s.d_blk_size, (size_t)ctx->bgzf_max_blocks * sizeof(uint32_t)));
                 CK(cudaMalloc((void**)&s.d_blk_off, (size_t)ctx->bgzf_max_blocks * sizeof(long long)));
                 CK(cudaMalloc((void**)&s.d_blk_first, (size_t)ctx->bgzf_max_blocks * sizeof(int32_t)));
+                CK(cudaMalloc((void**)&s.d_blk_rng, (size_t)ctx->bgzf_max_blocks * BGZF_RNG_WORDS * sizeof(uint32_t)));
+                if (!ctx->d_bgzf_code) {
+                    std::vector<BgzfCode> codes(2);
+                    bgzf_build_code(nullptr, true, &codes[0]);
+                    codes[1] = codes[0];
+                    CK(upload(&ctx->d_bgzf_code, codes));
+                    CK(cudaMalloc((void**)&ctx->d_bgzf_hist, BGZF_HIST * sizeof(uint32_t)));
+                    ctx->bgzf_code_ready = getenv("VGL_BGZF_FIXED") != nullptr; // development: keep the fixed code
+                }
                 if (!ctx->d_crc_pow) {
-                    std::vector<uint32_t> pw(1024);
+                    std::vector<uint32_t> pw(2048);
                     bgzf_crc_pow_table(pw.data());
                     CK(upload(&ctx->d_crc_pow, pw));
                 }
@@ -1208,11 +1221,33 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             memset(&z, 0, sizeof z);
             z.S = (int32_t)S; z.n_sites = n_sites; z.in = s.d_bcf; z.in_cap = (long long)ctx->bcf_cap;
             z.rec_off = s.d_rec_off; z.planes = s.d_planes; z.crc_pow = ctx->d_crc_pow;
-            z.stage = s.d_stage; z.blk_size = s.d_blk_size; z.blk_off = s.d_blk_off; z.blk_first = s.d_blk_first; z.out = s.d_bgzf; z.totals = s.d_totals;
+            z.stage = s.d_stage; z.blk_size = s.d_blk_size; z.blk_off = s.d_blk_off; z.blk_first = s.d_blk_first; z.rng_g = s.d_blk_rng; z.out = s.d_bgzf; z.totals = s.d_totals;
             // blocks this batch can make at most (its worst-case record bytes), not the slot's capacity
             const int64_t nb_max = std::min<int64_t>(ctx->bgzf_max_blocks, bgzf_blocks_for((int64_t)((double)ctx->bcf_cap * n_sites / prm.max_batch_sites) + 65536));
+            z.code = ctx->d_bgzf_code; z.code_fixed = ctx->d_bgzf_code + 1;
+            if (!ctx->bgzf_code_ready) {
+                // once per context: the symbol statistics of this batch's parse -> a dynamic Huffman code (RFC 1951 3.2.7)
+                // every later block starts with; the simulated tags have the same statistics from batch to batch
+                CK(cudaMemsetAsync(ctx->d_bgzf_hist, 0, BGZF_HIST * sizeof(uint32_t), st));
+                z.hist = ctx->d_bgzf_hist;
+                launch_bgzf(z, nb_max, st, ctx->n_sms);
+                ctx->launches += 3;
+                z.hist = nullptr;
+                uint32_t hist[BGZF_HIST];
+                CK(cudaMemcpyAsync(hist, ctx->d_bgzf_hist, sizeof hist, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                uint64_t seen = 0;
+                for (int i = 0; i < BGZF_HIST; ++i) seen += hist[i];
+                if (seen > 1000) { // else: an (almost) empty batch, try again on the next
+                    BgzfCode code;
+                    bgzf_build_code(hist, false, &code);
+                    CK(cudaMemcpyAsync(ctx->d_bgzf_code, &code, sizeof code, cudaMemcpyHostToDevice, st));
+                    CK(cudaStreamSynchronize(st));
+                    ctx->bgzf_code_ready = true;
+                }
+            }
             launch_bgzf(z, nb_max, st, ctx->n_sms);
-            ctx->launches += 4;
+            ctx->launches += 5;
         }
         CK(cudaEventRecord(s.ev[EV_KDONE], st)); // the batch's last kernel: the next batch's kernels may start (its copies follow)
         ctx->chain_ev = s.ev[EV_KDONE];

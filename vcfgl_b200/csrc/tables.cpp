@@ -4,8 +4,11 @@
 // of table entries.
 #include "tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 namespace vgl {
 
@@ -430,6 +433,178 @@ int precalc(double error_rate, int error_qs, int gl_model, int precise_gl, int a
         }
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Prefix codes for csrc/bgzf.cu (RFC 1951)
+namespace {
+
+// code lengths of a Huffman code over the symbols with cnt > 0, none longer than max_bits (counts are halved until the
+// tree is shallow enough: the classic fallback, a fraction of a percent from package-merge on skewed inputs)
+std::vector<int> huff_lengths(std::vector<uint64_t> cnt, int max_bits)
+{
+    const int n = (int)cnt.size();
+    std::vector<int> len(n, 0);
+    int used = 0, one = -1;
+    for (int i = 0; i < n; ++i)
+        if (cnt[i]) { ++used; one = i; }
+    if (used == 0) return len;
+    if (used == 1) { // a complete code needs two codewords (zlib rejects incomplete literal / code-length codes)
+        len[one] = 1;
+        len[one == 0 ? 1 : 0] = 1;
+        return len;
+    }
+    for (;;) {
+        // two-queue construction over the sorted leaves
+        std::vector<int> order;
+        for (int i = 0; i < n; ++i)
+            if (cnt[i]) order.push_back(i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] < cnt[b]; });
+        const int m = (int)order.size();
+        std::vector<uint64_t> w(2 * m - 1);
+        std::vector<int> parent(2 * m - 1, -1);
+        for (int i = 0; i < m; ++i) w[i] = cnt[order[i]];
+        int leaf = 0, node = m, next = m;
+        auto take = [&]() -> int {
+            if (leaf < m && (node >= next || w[leaf] <= w[node])) return leaf++;
+            return node++;
+        };
+        while (next < 2 * m - 1) {
+            const int a = take(), b = take();
+            w[next] = w[a] + w[b];
+            parent[a] = parent[b] = next;
+            ++next;
+        }
+        int deepest = 0;
+        for (int i = 0; i < m; ++i) {
+            int d = 0;
+            for (int j = i; parent[j] >= 0; j = parent[j]) ++d;
+            len[order[i]] = d;
+            deepest = std::max(deepest, d);
+        }
+        if (deepest <= max_bits) return len;
+        for (int i = 0; i < n; ++i)
+            if (cnt[i]) cnt[i] = (cnt[i] + 1) / 2;
+    }
+}
+
+// canonical codes (RFC 1951 3.2.2), bit-reversed
+std::vector<uint32_t> canon_codes(const std::vector<int>& len)
+{
+    int bl_count[17] = {0};
+    for (int l : len) ++bl_count[l];
+    bl_count[0] = 0;
+    uint32_t next[17] = {0}, code = 0;
+    for (int b = 1; b <= 16; ++b) {
+        code = (code + (uint32_t)bl_count[b - 1]) << 1;
+        next[b] = code;
+    }
+    std::vector<uint32_t> out(len.size(), 0u);
+    for (size_t i = 0; i < len.size(); ++i) {
+        if (!len[i]) continue;
+        const uint32_t c = next[len[i]]++;
+        uint32_t r = 0;
+        for (int k = 0; k < len[i]; ++k) r |= ((c >> k) & 1u) << (len[i] - 1 - k);
+        out[i] = r;
+    }
+    return out;
+}
+
+struct BitOut {
+    uint32_t* w;
+    uint32_t cap_bits, n = 0;
+    void put(uint32_t v, int bits)
+    {
+        for (int k = 0; k < bits; ++k, ++n)
+            if (n < cap_bits && ((v >> k) & 1u)) w[n >> 5] |= 1u << (n & 31);
+    }
+};
+
+} // namespace
+
+void bgzf_build_code(const uint32_t* hist, bool fixed, BgzfCode* out)
+{
+    memset(out, 0, sizeof(*out));
+    std::vector<int> ll(288, 0), dl(30, 5);
+    if (fixed) {
+        for (int i = 0; i < 288; ++i) ll[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+    } else {
+        std::vector<uint64_t> c(286), d(30);
+        for (int i = 0; i < 286; ++i) c[i] = (uint64_t)hist[i] + 1; // every byte value and length must stay codable
+        for (int i = 0; i < 30; ++i) d[i] = (uint64_t)hist[288 + i] + 1;
+        const std::vector<int> l1 = huff_lengths(c, 15);
+        std::copy(l1.begin(), l1.end(), ll.begin());
+        dl = huff_lengths(d, 15);
+    }
+    const std::vector<uint32_t> lc = canon_codes(ll);
+    std::vector<int> dl32(dl);
+    if (fixed) dl32.resize(32, 5); // the fixed distance code has 32 codewords of 5 bits
+    const std::vector<uint32_t> dc = canon_codes(dl32);
+    for (int i = 0; i < 256; ++i) out->lit[i] = lc[i] | ((uint32_t)ll[i] << 16);
+    out->eob = lc[256] | ((uint32_t)ll[256] << 16);
+    for (int L = 3; L <= 258; ++L) {
+        int idx, eb;
+        uint32_t ev;
+        const int t = L - 3;
+        if (t < 8) { idx = t; eb = 0; ev = 0; }
+        else if (L == 258) { idx = 28; eb = 0; ev = 0; }
+        else {
+            int hb = 0;
+            while ((t >> (hb + 1)) != 0) ++hb;
+            eb = hb - 2;
+            idx = 4 * (hb - 1) + ((t >> eb) & 3);
+            ev = (uint32_t)t & ((1u << eb) - 1u);
+        }
+        const int sym = 257 + idx, nb = ll[sym];
+        out->len[t] = (lc[sym] | (ev << nb)) | ((uint32_t)(nb + eb) << 24);
+    }
+    for (int i = 0; i < 30; ++i) out->dist[i] = dc[i] | ((uint32_t)dl[i] << 16);
+    BitOut bo{out->hdr, (uint32_t)(sizeof(out->hdr) * 8)};
+    bo.put(1, 1); // BFINAL: every BGZF block is one deflate block
+    if (fixed) {
+        bo.put(1, 2);
+    } else {
+        bo.put(2, 2);
+        // the 316 code lengths, run-length coded with the symbols 16 / 17 / 18 (3.2.7)
+        std::vector<int> seq(ll.begin(), ll.begin() + 286);
+        seq.insert(seq.end(), dl.begin(), dl.end());
+        std::vector<std::pair<int, int>> rle; // symbol, extra value
+        for (size_t i = 0; i < seq.size();) {
+            size_t j = i;
+            while (j < seq.size() && seq[j] == seq[i]) ++j;
+            int run = (int)(j - i);
+            const int v = seq[i];
+            if (v == 0) {
+                while (run >= 11) { const int r = std::min(run, 138); rle.push_back({18, r - 11}); run -= r; }
+                if (run >= 3) { rle.push_back({17, run - 3}); run = 0; }
+                while (run-- > 0) rle.push_back({0, 0});
+            } else {
+                rle.push_back({v, 0});
+                --run;
+                while (run >= 3) { const int r = std::min(run, 6); rle.push_back({16, r - 3}); run -= r; }
+                while (run-- > 0) rle.push_back({v, 0});
+            }
+            i = j;
+        }
+        std::vector<uint64_t> cc(19, 0);
+        for (auto& e : rle) ++cc[e.first];
+        const std::vector<int> cl = huff_lengths(cc, 7);
+        const std::vector<uint32_t> ccode = canon_codes(cl);
+        static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        int hclen = 19;
+        while (hclen > 4 && cl[order[hclen - 1]] == 0) --hclen;
+        bo.put(286 - 257, 5);
+        bo.put(30 - 1, 5);
+        bo.put((uint32_t)(hclen - 4), 4);
+        for (int i = 0; i < hclen; ++i) bo.put((uint32_t)cl[order[i]], 3);
+        for (auto& e : rle) {
+            bo.put(ccode[e.first], cl[e.first]);
+            if (e.first == 16) bo.put((uint32_t)e.second, 2);
+            else if (e.first == 17) bo.put((uint32_t)e.second, 3);
+            else if (e.first == 18) bo.put((uint32_t)e.second, 7);
+        }
+    }
+    out->hdr_bits = bo.n;
 }
 
 } // namespace vgl

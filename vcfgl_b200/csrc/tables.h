@@ -84,4 +84,20 @@ struct PreCalc {
 int precalc(double error_rate, int error_qs, int gl_model, int precise_gl, int adjust_qs, double adjust_by,
             int n_bins, const uint8_t bins[][3], PreCalc* out);
 
+// ---- the prefix codes of the device's BGZF compressor (csrc/bgzf.cu), RFC 1951.  One code per context: either deflate's fixed
+// code (3.2.6) or a "dynamic" code (3.2.7) built once from the symbol counts of the context's first record stream; every block
+// then starts with the same precomputed header bits.  All codes are stored bit-reversed (deflate packs Huffman codes most
+// significant bit first into a stream that is otherwise filled from the least significant bit).
+struct BgzfCode {
+    uint32_t lit[256];  // literal byte: code | bits << 16
+    uint32_t len[256];  // match length - 3: (code | extra bits << code bits) | total bits << 24   (<= 15 + 5 bits)
+    uint32_t dist[32];  // distance code 0..29: code | bits << 16   (the extra bits follow, computed by the kernel)
+    uint32_t eob;       // end of block: code | bits << 16
+    uint32_t hdr_bits;  // bits of the block header (BFINAL, BTYPE, and for a dynamic code the code lengths)
+    uint32_t hdr[94];   // the header bits, least significant bit first
+};
+enum { BGZF_HIST = 320 }; // symbol counts: [0..285] literal / length symbols, [288..317] distance symbols
+// fixed = deflate's fixed code; else from the counts (every symbol gets a code, whatever its count)
+void bgzf_build_code(const uint32_t* hist, bool fixed, BgzfCode* out);
+
 } // namespace vgl

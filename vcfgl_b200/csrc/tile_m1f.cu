@@ -798,9 +798,11 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
                     if (has_pl) sts32(hs + TILE_WST_G * 4, 0u);
                 }
             } else {
+                // the all-15 flag of the lane's site is 0 for a skipped site: its lanes store into the scratch cell and need the
+                // slot test (their offsets may be 0xFF)
                 float q[15];
                 m1f_scores_noclamp(n, c0, c1, c2, c3, p.m1_bsum, p.m1_het, q);
-                if (__all_sync(0xffffffffu, !live || (t1.z >> 16))) tile_emit_cell<true>(q, slot, cell_g, has_gl, has_pl);
+                if (__all_sync(0xffffffffu, (t1.z >> 16) != 0u)) tile_emit_cell<true>(q, slot, cell_g, has_gl, has_pl);
                 else tile_emit_cell<false>(q, slot, cell_g, has_gl, has_pl);
             }
             if (has_ad) { // AD in allele order (vcfgl.cpp:806-831): byte permute, selector 4 reads 0

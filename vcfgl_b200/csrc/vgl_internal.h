@@ -6,6 +6,7 @@
 #include <string>
 
 #include "../../include/vgl.h"
+#include "tables.h"
 
 namespace vgl {
 
@@ -160,20 +161,24 @@ struct BcfRecPlanes { // where the FORMAT planes of a serialised record lie (wri
     uint16_t cell[7]; // bytes per sample
     uint16_t n;       // planes
 };
-enum { BGZF_STRIDE = 36992 }; // bytes of a block's slot in the staging buffer (>= 18 + 32768 * 9 / 8 + 2 + 8)
+enum { BGZF_STRIDE = 36992, BGZF_RNG_LIST = 63, BGZF_RNG_WORDS = 4 * (1 + BGZF_RNG_LIST) }; // bytes of a block's slot in the staging buffer (>= 18 + 32768 * 9 / 8 + 2 + 8)
 struct BgzfArgs {
     int32_t S, n_sites;
     const uint8_t* in;          // the uncompressed record stream
     long long in_cap;
     const long long* rec_off;   // [n_sites + 1]
     const BcfRecPlanes* planes; // [n_sites]
-    const uint32_t* crc_pow;    // [1024] x^(256 k) mod P
+    const uint32_t* crc_pow;    // [2048] bgzf_crc_pow_table(): chunk shifts, slicing tables
     uint8_t* stage;             // [max blocks][BGZF_STRIDE]
     uint32_t* blk_size;         // [max blocks]
     long long* blk_off;         // [max blocks]
     int32_t* blk_first;         // [max blocks] first record that reaches into the block
+    uint32_t* rng_g;            // [max blocks][BGZF_RNG_WORDS] k_bgzf_ranges -> k_bgzf_deflate: {ranges, segments, state, -}, the ranges
     uint8_t* out;               // the compressed stream, blocks back to back
     int64_t* totals;            // [3] bytes of the record stream (in); [4] compressed bytes, [5] blocks (out)
+    const BgzfCode* code;       // the context's prefix code (tables.h): deflate's fixed code until the statistics pass has run
+    const BgzfCode* code_fixed; // the fixed code (blocks the context's code would expand beyond the block image)
+    uint32_t* hist;             // non-null: statistics pass -- [BGZF_HIST] symbol counts of the parse, no output
 };
 size_t bgzf_dyn_smem();
 int64_t bgzf_blocks_for(int64_t bytes);
