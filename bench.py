@@ -686,7 +686,7 @@ def main():
     ap.add_argument("--no-input-path", action="store_true", help="skip the VCF-text input-path leg")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-legs of the other BASELINE configs")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling only: stop after the kernel-side loop")
-    ap.add_argument("--e2e-launches", type=int, default=6, help="batches per end-to-end step")
+    ap.add_argument("--e2e-launches", type=int, default=12, help="batches per end-to-end step (the timed region starts and ends with an empty pipeline)")
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     opt = ap.parse_args()
     opt.warmup = max(opt.warmup, 3) if opt.impl == "b200" else opt.warmup

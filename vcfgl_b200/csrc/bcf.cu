@@ -457,7 +457,10 @@ __device__ __forceinline__ uint32_t seg_byte(const SegView& v, int sg, uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(256) k_bcf_emit(const BcfArgs a)
+// U = words per thread and round: 4 for long records (the plane loads of a round are all in flight together), 1 for short ones,
+// where the kernel is bound by thread 0's layout pass and more resident blocks matter more than longer rounds
+template <int U>
+__global__ void __launch_bounds__(256, U == 1 ? 8 : 5) k_bcf_emit(const BcfArgs a)
 {
     const int rk = blockIdx.x, tid = threadIdx.x; // record index (see k_bcf_plan)
     __shared__ vgl_site_out s;
@@ -494,40 +497,71 @@ __global__ void __launch_bounds__(256) k_bcf_emit(const BcfArgs a)
     // aligned words of the output buffer that overlap [off, off + len)
     const long long w0 = off >> 2, w1 = (off + len + 3) >> 2;
     int sg = 0;
-    for (long long w = w0 + tid; w < w1; w += 256) {
-        const long long p0 = w * 4 - off; // record-relative position of the word's first byte (may be < 0)
-        const uint32_t rfirst = p0 < 0 ? 0u : (uint32_t)p0;
-        while (sg + 1 < nseg && seg_start[sg + 1] <= rfirst) ++sg;
-        if (p0 >= 0 && (uint32_t)p0 + 4u <= seg_start[sg + 1]) { // whole word inside one segment (or the record's end is beyond it)
-            const uint32_t r = (uint32_t)p0 - seg_start[sg];
-            const unsigned long long src = seg_src[sg];
-            uint32_t word;
+    // U words per thread and round (w, w + 256, ...): the plane loads of all of them are issued before any is used -- the loop is
+    // bound by the latency of those loads, not by their number.
+    for (long long wb = w0 + tid; wb < w1; wb += U * 256) {
+        int32_t x[U][4];
+        uint32_t info[U]; // 0: not a plane word (literal bytes, pass-through bytes, or it straddles segments); else kind | r << 8 (r: low bits only)
+        int sgu[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long w = wb + 256 * u;
+            info[u] = 0u;
+            sgu[u] = sg;
+            if (w >= w1) continue;
+            const long long p0 = w * 4 - off; // record-relative position of the word's first byte (may be < 0)
+            const uint32_t rfirst = p0 < 0 ? 0u : (uint32_t)p0;
+            while (sg + 1 < nseg && seg_start[sg + 1] <= rfirst) ++sg;
+            sgu[u] = sg;
             const uint32_t kind = seg_kind[sg];
-            if (kind == SEG_VERB) {
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(src) + (r >> 2);
-                const uint32_t sh = r & 3u;
-                const uint32_t lo = __ldg(q);
-                word = sh ? __funnelshift_r(lo, __ldg(q + 1), 8 * sh) : lo;
-            } else if (kind == SEG_I8) {
-                const int32_t* q = reinterpret_cast<const int32_t*>(src) + r;
-                word = 0;
+            if (p0 >= 0 && (uint32_t)p0 + 4u <= seg_start[sg + 1] && kind >= SEG_VERB) { // whole word inside one plane segment
+                const uint32_t r = (uint32_t)p0 - seg_start[sg];
+                const int32_t* q = reinterpret_cast<const int32_t*>(seg_src[sg]);
+                int n;
+                if (kind == SEG_VERB) { q += r >> 2; n = 1 + ((r & 3u) != 0u); }
+                else if (kind == SEG_I8) { q += r; n = 4; }
+                else { q += r >> 1; n = 2 + (int)(r & 1u); }
+                info[u] = kind | ((r & 3u) << 8);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[u][k] = k < n ? __ldg(q + k) : 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long w = wb + 256 * u;
+            if (w >= w1) continue;
+            if (info[u]) {
+                const uint32_t kind = info[u] & 0xFFu, r = info[u] >> 8;
+                uint32_t word;
+                if (kind == SEG_VERB) {
+                    word = r ? __funnelshift_r((uint32_t)x[u][0], (uint32_t)x[u][1], 8 * r) : (uint32_t)x[u][0];
+                } else if (kind == SEG_I8) {
+                    word = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int32_t v8 = x[u][k];
+                        word |= (v8 == VGL_I32_MISSING ? 0x80u : (v8 == VGL_I32_MISSING + 1 ? 0x81u : (uint32_t)v8 & 0xFFu)) << (8 * k);
+                    }
+                } else {
+                    uint32_t h[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int32_t v16 = x[u][k];
+                        h[k] = v16 == VGL_I32_MISSING ? 0x8000u : (v16 == VGL_I32_MISSING + 1 ? 0x8001u : (uint32_t)v16 & 0xFFFFu);
+                    }
+                    word = (r & 1u) ? ((h[0] >> 8) | (h[1] << 8) | (h[2] << 24)) : (h[0] | (h[1] << 16));
+                }
+                *reinterpret_cast<uint32_t*>(out + w * 4) = word;
+            } else { // byte by byte, only this record's bytes
+                const long long p0 = w * 4 - off;
+                int g = sgu[u];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int32_t x = __ldg(q + k);
-                    word |= (x == VGL_I32_MISSING ? 0x80u : (x == VGL_I32_MISSING + 1 ? 0x81u : (uint32_t)x & 0xFFu)) << (8 * k);
+                    const long long p = p0 + k;
+                    if (p < 0 || p >= (long long)len) continue;
+                    while (g + 1 < nseg && seg_start[g + 1] <= (uint32_t)p) ++g;
+                    out[w * 4 + k] = (uint8_t)seg_byte(v, g, (uint32_t)p - seg_start[g]);
                 }
-            } else {
-                word = seg_byte(v, sg, r) | (seg_byte(v, sg, r + 1) << 8) | (seg_byte(v, sg, r + 2) << 16) | (seg_byte(v, sg, r + 3) << 24);
-            }
-            *reinterpret_cast<uint32_t*>(out + w * 4) = word;
-        } else { // a word that straddles segments or the record's ends: byte by byte, only this record's bytes
-            int g = sg;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long p = p0 + k;
-                if (p < 0 || p >= (long long)len) continue;
-                while (g + 1 < nseg && seg_start[g + 1] <= (uint32_t)p) ++g;
-                out[w * 4 + k] = (uint8_t)seg_byte(v, g, (uint32_t)p - seg_start[g]);
             }
         }
     }
@@ -539,7 +573,8 @@ void launch_bcf(const BcfArgs& a, cudaStream_t st)
 {
     k_bcf_plan<<<(unsigned)a.n_sites, 128, 0, st>>>(a);
     k_bcf_scan<<<1, 1024, 0, st>>>(a);
-    k_bcf_emit<<<(unsigned)a.n_sites, 256, 0, st>>>(a);
+    if (a.S >= 1000) k_bcf_emit<4><<<(unsigned)a.n_sites, 256, 0, st>>>(a);
+    else k_bcf_emit<1><<<(unsigned)a.n_sites, 256, 0, st>>>(a);
 }
 
 } // namespace vgl

@@ -37,9 +37,10 @@ constexpr int BGZF_IN = 32768;                  // uncompressed bytes per block
 constexpr int BGZF_THREADS = 1024;
 constexpr int MAX_SEG = 8192;                   // segments (cells, literal runs) of a block
 constexpr int RUN = 64;                         // bytes of a literal run segment
-constexpr int OUT_WORDS = (BGZF_IN * 9 / 8 + 64) / 4; // fixed codes: at most 9 bits per input byte, + header bits / end of block / padding
+constexpr int OUT_WORDS = 24576 / 4;               // the block image; a block that does not fit (three quarters of its input) is stored
 constexpr int HASH_SLOTS = 8192;
 constexpr int MAX_RANGES = 32 * 16;
+constexpr int WORD_BITS = 12, WORD_SLOTS = 1 << WORD_BITS; // word table of the unmatched cells (half of the cell table's memory)
 constexpr int CRC_CHUNK = 64;                  // bytes a thread takes in the CRC pass
 
 struct Seg { // 8 bytes
@@ -47,7 +48,7 @@ struct Seg { // 8 bytes
     uint32_t info;       // SEG_MATCH | distance; SEG_LIT | bits of quarters 0, 1, 2 (8 bits each); SEG_CELL: a match candidate
 };
 constexpr uint32_t SEG_MATCH = 1u << 31, SEG_LIT = 1u << 30, SEG_CELL = 1u << 29;
-constexpr uint32_t CAP_BITS = (uint32_t)OUT_WORDS * 32u - 96u; // what the block image holds (the fixed code never needs more)
+constexpr uint32_t CAP_BITS = (uint32_t)OUT_WORDS * 32u - 96u; // what the block image holds
 
 __device__ __forceinline__ uint32_t rev_bits(uint32_t code, int n) { return __brev(code) >> (32 - n); }
 
@@ -61,6 +62,15 @@ __device__ __forceinline__ void dist_code(int dist, int& dc, int& deb, uint32_t&
         dc = 2 * hb + ((u >> deb) & 1);
         dev = (uint32_t)u & ((1u << deb) - 1u);
     }
+}
+// index of the length symbol (257 + ...) of a match length
+__device__ __forceinline__ int len_symbol(int len)
+{
+    const int t = len - 3;
+    if (t < 8) return t;
+    if (len == 258) return 28;
+    const int hb = 31 - __clz(t);
+    return 4 * (hb - 1) + ((t >> (hb - 2)) & 3);
 }
 // length / distance pair (3 <= len <= 258) from the context's code tables: up to 20 + 15 + 13 bits
 __device__ __forceinline__ void match_code(const uint32_t* len_tab, const uint32_t* dist_tab, int len, int dist, unsigned long long& bits, int& n)
@@ -255,11 +265,12 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     uint32_t* const seg_bit = reinterpret_cast<uint32_t*>(segs + MAX_SEG);        // [MAX_SEG] bit offset of every segment
     uint32_t* const htab = seg_bit + MAX_SEG;                                     // [HASH_SLOTS] tag << 16 | position
     uint32_t* const rng = htab + HASH_SLOTS;                                      // [MAX_RANGES][4]: pos, len, cell bytes (0: gap), first segment
+    uint16_t* const lit_list = reinterpret_cast<uint16_t*>(rng + MAX_RANGES * 4);  // [MAX_SEG] the segments that are not matches (any order)
     __shared__ uint32_t crc_tab[1024]; // slicing-by-four tables of CRC-32
     __shared__ uint32_t lit_tab[256], len_tab[256], dist_tab[32]; // the context's prefix code (BgzfCode)
     __shared__ uint32_t eob_s, hdr_bits_s;
     __shared__ uint32_t warp_tot[32];
-    __shared__ int n_rng_s, n_seg_s, lit_only_s;
+    __shared__ int n_rng_s, n_seg_s, lit_only_s, n_lit_s;
     __shared__ uint32_t crc_s, total_bits_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -284,7 +295,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
             len_tab[t] = __ldg(a.code->len + t);
             if (t < 32) dist_tab[t] = __ldg(a.code->dist + t);
         }
-        if (t == 0) { crc_s = 0u; eob_s = a.code->eob; hdr_bits_s = a.code->hdr_bits; }
+        if (t == 0) { crc_s = 0u; n_lit_s = 0; eob_s = a.code->eob; hdr_bits_s = a.code->hdr_bits; }
         for (int i = t; i < OUT_WORDS / 4; i += nt) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = t; i < HASH_SLOTS / 4; i += nt) reinterpret_cast<uint4*>(htab)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         if (t < n16) reinterpret_cast<uint4*>(in)[t] = v0;
@@ -358,12 +369,17 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     PROF(1); // segment table
 
     // ---- cells: hash of the bytes, first occurrence per hash (atomicMin on tag << 16 | position; open addressing)
-    auto cell_hash = [&](const Seg& s) -> uint32_t { // FNV-style over 32-bit words (the tail word masked)
-        uint32_t h = 2166136261u ^ s.len;
+    auto cell_hash = [&](const Seg& s) -> uint32_t { // sum of the 32-bit words (the tail word masked) times odd constants: no chain
+        uint32_t h = 2166136261u ^ s.len, c = 0x9E3779B1u;
         const int nw = s.len >> 2;
-        for (int k = 0; k < nw; ++k) h = (h ^ word_at(in, s.pos + 4u * k)) * 16777619u;
-        if (s.len & 3) h = (h ^ (word_at(in, s.pos + 4u * nw) & ((1u << (8 * (s.len & 3))) - 1u))) * 16777619u;
+        for (int k = 0; k < nw; ++k) {
+            h += word_at(in, s.pos + 4u * k) * c;
+            c += 0x7F4A7C16u; // stays odd
+        }
+        if (s.len & 3) h += (word_at(in, s.pos + 4u * nw) & ((1u << (8 * (s.len & 3))) - 1u)) * c;
         h ^= h >> 15;
+        h *= 0x2C1B3C6Du;
+        h ^= h >> 13;
         return h;
     };
     for (int j = tid; j < n_seg; j += BGZF_THREADS) {
@@ -381,188 +397,293 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     }
     __syncthreads();
     PROF(2); // hash insert
-    // ---- match = the first cell of the block with the same bytes
-    for (int j = tid; j < n_seg; j += BGZF_THREADS) {
-        const Seg s = segs[j];
-        if (!(s.info & SEG_CELL)) continue;
-        const uint32_t h = seg_bit[j], tag = h >> 16;
-        uint32_t slot = h & (HASH_SLOTS - 1), dist = 0u;
-        for (int probe = 0; probe < 16; ++probe) {
-            const uint32_t e = htab[slot];
-            if (e == 0xFFFFFFFFu) break;
-            if ((e >> 16) == tag) {
-                const uint32_t q = e & 0xFFFFu;
-                if (q < s.pos && q + s.len <= s.pos) { // an earlier cell (cells do not overlap)
-                    bool same = true;
-                    const int nw = s.len >> 2;
-                    for (int k = 0; k < nw && same; ++k) same = word_at(in, q + 4u * k) == word_at(in, s.pos + 4u * k);
-                    for (int k = 4 * nw; k < s.len && same; ++k) same = in[q + k] == in[s.pos + k];
-                    if (same) dist = s.pos - q;
+    // ---- match = the first cell of the block with the same bytes; the other segments go on the list of literal segments
+    for (int j0 = warp * 32; j0 < n_seg; j0 += BGZF_THREADS) {
+        const int j = j0 + lane;
+        bool is_lit = false;
+        if (j < n_seg) {
+            const Seg s = segs[j];
+            is_lit = true;
+            if (s.info & SEG_CELL) {
+                const uint32_t h = seg_bit[j], tag = h >> 16;
+                uint32_t slot = h & (HASH_SLOTS - 1), dist = 0u;
+                for (int probe = 0; probe < 16; ++probe) {
+                    const uint32_t e = htab[slot];
+                    if (e == 0xFFFFFFFFu) break;
+                    if ((e >> 16) == tag) {
+                        const uint32_t q = e & 0xFFFFu;
+                        if (q < s.pos && q + s.len <= s.pos) { // an earlier cell (cells do not overlap)
+                            uint32_t diff = 0u; // all words compared, no early exit: the loads are independent
+                            const int nw = s.len >> 2;
+                            for (int k = 0; k < nw; ++k) diff |= word_at(in, q + 4u * k) ^ word_at(in, s.pos + 4u * k);
+                            for (int k = 4 * nw; k < s.len; ++k) diff |= (uint32_t)(in[q + k] ^ in[s.pos + k]);
+                            if (diff == 0u) dist = s.pos - q;
+                        }
+                        break;
+                    }
+                    slot = (slot + 1) & (HASH_SLOTS - 1);
                 }
+                if (dist) {
+                    segs[j].info = SEG_MATCH | dist;
+                    seg_bit[j] = (uint32_t)match_bits(len_tab, dist_tab, s.len, (int)dist);
+                    is_lit = false;
+                } // else: an unmatched cell stays a candidate for word matches (SEG_CELL)
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, is_lit);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&n_lit_s, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_lit) lit_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+    }
+    // ---- words: the 32-bit words of the unmatched cells against each other.  A new cell mostly differs from earlier ones in a
+    // few of its values; every word that occurred before in an unmatched cell (any matched cell is a copy of one) can go out
+    // as a match of length 4.  The cell table's memory now holds the word table (first position per value, the value is read
+    // back from the block) and, per word of the block, the distance chosen (0: literals).
+    __syncthreads();
+    PROF(3); // match
+    uint32_t* const wtab = htab;                                           // [WORD_SLOTS]
+    uint16_t* const wdist = reinterpret_cast<uint16_t*>(htab + WORD_SLOTS); // [BGZF_IN / 4]
+    for (int i = tid; i < HASH_SLOTS / 4; i += BGZF_THREADS)
+        reinterpret_cast<uint4*>(htab)[i] = i < WORD_SLOTS / 4 ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    // quarter q of a literal segment: bytes [k0, k1), the first nwb of them whole words of an unmatched cell
+    auto quarter = [&](const Seg& sg, int q, int& k0, int& k1, int& nwb) {
+        if (sg.info & SEG_CELL) {
+            const int nw = sg.len >> 2, qw = (nw + 3) >> 2, w0 = min(q * qw, nw), w1 = min(w0 + qw, nw);
+            k0 = 4 * w0;
+            k1 = q == 3 ? (int)sg.len : 4 * w1;
+            nwb = 4 * (w1 - w0);
+        } else {
+            const int ql = (sg.len + 3) >> 2;
+            k0 = min(q * ql, (int)sg.len);
+            k1 = min(k0 + ql, (int)sg.len);
+            nwb = 0;
+        }
+    };
+    const int n_lit = n_lit_s;
+    for (int task = tid; task < n_lit * 16; task += BGZF_THREADS) { // insert: a word of an unmatched cell per thread
+        const Seg ls = segs[lit_list[task >> 4]];
+        const int k = 4 * (task & 15);
+        if (!(ls.info & SEG_CELL) || k + 4 > (int)ls.len) continue;
+        const uint32_t wp = ls.pos + (uint32_t)k, v = word_at(in, wp);
+        uint32_t slot = (v * 2654435761u) >> (32 - WORD_BITS);
+        for (int probe = 0; probe < 8; ++probe) {
+            uint32_t cur = wtab[slot];
+            if (cur == 0xFFFFFFFFu) {
+                cur = atomicCAS(&wtab[slot], 0xFFFFFFFFu, wp);
+                if (cur == 0xFFFFFFFFu) break;
+            }
+            if (word_at(in, cur) == v) {
+                if (wp < cur) atomicMin(&wtab[slot], wp); // (an entry only ever moves to an earlier position of the same value)
                 break;
             }
-            slot = (slot + 1) & (HASH_SLOTS - 1);
+            slot = (slot + 1) & (WORD_SLOTS - 1);
         }
-        segs[j].info = dist ? (SEG_MATCH | dist) : 0u;
     }
-    if (a.hist) { // statistics pass (vgl_submit, once per context): symbol counts of this parse, nothing is written
-        __syncthreads();
-        uint32_t* const hist = out; // cleared above
+    __syncthreads();
+    PROF(4); // word insert
+    // ---- bit length of every segment under the context's code (the word matches are decided here: a match where it is
+    // shorter than its four literals), exclusive prefix; should the image not hold them (a code built from other statistics),
+    // once more under the fixed code, which always fits.  The statistics pass counts the symbols instead and stops.
+    uint32_t* const hist = out; // statistics pass only (the image is clear and stays unused)
+    if (a.hist) // the matches' symbols (their bit lengths are already in place)
         for (int j = tid; j < n_seg; j += BGZF_THREADS) {
             const Seg s = segs[j];
-            if (s.info & SEG_MATCH) {
-                const int t = s.len - 3;
-                int idx;
-                if (t < 8) idx = t;
-                else if (s.len == 258) idx = 28;
-                else { const int hb = 31 - __clz(t); idx = 4 * (hb - 1) + ((t >> (hb - 2)) & 3); }
-                int dc, deb;
-                uint32_t dev;
-                dist_code((int)(s.info & 0xFFFFu), dc, deb, dev);
-                atomicAdd(&hist[257 + idx], 1u);
-                atomicAdd(&hist[288 + dc], 1u);
-            } else {
-                for (int k = 0; k < s.len; ++k) atomicAdd(&hist[in[s.pos + k]], 1u);
+            if (!(s.info & SEG_MATCH)) continue;
+            int dc, deb;
+            uint32_t dev;
+            dist_code((int)(s.info & 0xFFFFu), dc, deb, dev);
+            atomicAdd(&hist[257 + len_symbol(s.len)], 1u);
+            atomicAdd(&hist[288 + dc], 1u);
+        }
+    for (int tb = 0; tb < n_lit * 4; tb += BGZF_THREADS) { // a quarter of a literal segment per thread; lanes 4 i .. 4 i + 3 share a segment
+        const int t = tb + tid;
+        uint32_t part = 0u;
+        int jj = 0;
+        const int q = t & 3;
+        if (t < n_lit * 4) {
+            jj = lit_list[t >> 2];
+            const Seg ls = segs[jj];
+            int k0, k1, nwb;
+            quarter(ls, q, k0, k1, nwb);
+            int k = k0;
+            for (; k < k0 + nwb; k += 4) {
+                const uint32_t wp = ls.pos + (uint32_t)k, v = word_at(in, wp);
+                const uint32_t e0 = lit_tab[v & 0xFFu], e1 = lit_tab[(v >> 8) & 0xFFu], e2 = lit_tab[(v >> 16) & 0xFFu], e3 = lit_tab[v >> 24];
+                uint32_t nb = (e0 >> 16) + (e1 >> 16) + (e2 >> 16) + (e3 >> 16), dsel = 0u;
+                uint32_t slot = (v * 2654435761u) >> (32 - WORD_BITS);
+                for (int probe = 0; probe < 8; ++probe) {
+                    const uint32_t cur = wtab[slot];
+                    if (cur == 0xFFFFFFFFu) break;
+                    if (word_at(in, cur) == v) {
+                        if (cur < wp) {
+                            const uint32_t mb = (uint32_t)match_bits(len_tab, dist_tab, 4, (int)(wp - cur));
+                            if (mb < nb) { nb = mb; dsel = wp - cur; }
+                        }
+                        break;
+                    }
+                    slot = (slot + 1) & (WORD_SLOTS - 1);
+                }
+                wdist[wp >> 2] = (uint16_t)dsel;
+                part += nb;
+                if (a.hist) {
+                    if (dsel) {
+                        int dc, deb;
+                        uint32_t dev;
+                        dist_code((int)dsel, dc, deb, dev);
+                        atomicAdd(&hist[257 + 1], 1u); // length 4
+                        atomicAdd(&hist[288 + dc], 1u);
+                    } else {
+                        atomicAdd(&hist[v & 0xFFu], 1u); atomicAdd(&hist[(v >> 8) & 0xFFu], 1u);
+                        atomicAdd(&hist[(v >> 16) & 0xFFu], 1u); atomicAdd(&hist[v >> 24], 1u);
+                    }
+                }
+            }
+            for (; k < k1; ++k) {
+                const uint32_t b = in[ls.pos + k];
+                part += lit_tab[b] >> 16;
+                if (a.hist) atomicAdd(&hist[b], 1u);
             }
         }
+        // bits of the quarters before this one, and of the whole segment
+        const uint32_t p1 = __shfl_up_sync(0xffffffffu, part, 1), p2 = __shfl_up_sync(0xffffffffu, part, 2), p3 = __shfl_up_sync(0xffffffffu, part, 3);
+        if (t < n_lit * 4 && q == 3) {
+            seg_bit[jj] = part + p1 + p2 + p3;
+            segs[jj].info = (segs[jj].info & SEG_CELL) | SEG_LIT | p3 | (p2 << 8) | (p1 << 16); // quarters 0, 1, 2
+        }
+    }
+    if (a.hist) { // statistics pass: the counts of this block to the context's, nothing is written
         __syncthreads();
         if (tid < BGZF_HIST && hist[tid]) atomicAdd(&a.hist[tid], hist[tid]);
         if (tid == 0) atomicAdd(&a.hist[256], 1u);
         return;
     }
-    // ---- bit length of every segment under the context's code, exclusive prefix; should the image not hold them (a code
-    // built from other statistics), once more under the fixed code, which always fits
-    for (int attempt = 0;; ++attempt) {
-        PROF(3); // match
-        for (int j = tid; j < n_seg; j += BGZF_THREADS) {
-            const Seg s = segs[j];
-            uint32_t nbits;
-            if (s.info & SEG_MATCH) {
-                nbits = (uint32_t)match_bits(len_tab, dist_tab, s.len, (int)(s.info & 0xFFFFu));
-            } else { // the bits of quarters 0..2 are kept with the segment (the emitters take a quarter each)
-                const int ql = (s.len + 3) >> 2; // <= 16: segments are at most 64 bytes long
-                uint32_t tot = 0u, cum = 0u;
+    __syncthreads();
+    PROF(5); // bit lengths
+    {
+        uint32_t v[MAX_SEG / BGZF_THREADS], sum = 0u;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k0 = q * ql, k1 = min(k0 + ql, (int)s.len);
-                    uint32_t part = 0u;
-                    for (int k = k0; k < k1; ++k) part += lit_tab[in[s.pos + k]] >> 16;
-                    if (q < 3) cum |= part << (8 * q);
-                    tot += part;
-                }
-                nbits = tot;
-                segs[j].info = SEG_LIT | cum;
-            }
-            seg_bit[j] = nbits;
+        for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
+            const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
+            v[k] = j < n_seg ? seg_bit[j] : 0u;
+            sum += v[k];
         }
-        __syncthreads();
-        PROF(4); // bit lengths
-        {
-            uint32_t v[MAX_SEG / BGZF_THREADS], sum = 0u;
+        uint32_t inc = sum;
 #pragma unroll
-            for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
-                const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
-                v[k] = j < n_seg ? seg_bit[j] : 0u;
-                sum += v[k];
-            }
-            uint32_t inc = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t t = warp_tot[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
+                const uint32_t u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
             }
-            if (lane == 31) warp_tot[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t t = warp_tot[lane];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, t, o);
-                    if (lane >= o) t += u;
-                }
-                warp_tot[lane] = t;
-            }
-            __syncthreads();
-            uint32_t base = hdr_bits_s + (warp ? warp_tot[warp - 1] : 0u) + inc - sum;
-#pragma unroll
-            for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
-                const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
-                if (j < n_seg) seg_bit[j] = base;
-                base += v[k];
-            }
-            if (tid == BGZF_THREADS - 1) total_bits_s = base;
+            warp_tot[lane] = t;
         }
         __syncthreads();
-        PROF(5); // prefix
-        if (attempt == 1 || total_bits_s + (eob_s >> 16) <= CAP_BITS) break;
-        const uint32_t old_words = (hdr_bits_s + 31u) >> 5;
-        __syncthreads();
-        if (tid < 256) {
-            lit_tab[tid] = a.code_fixed->lit[tid];
-            len_tab[tid] = a.code_fixed->len[tid];
-            if (tid < 32) dist_tab[tid] = a.code_fixed->dist[tid];
+        uint32_t base = hdr_bits_s + (warp ? warp_tot[warp - 1] : 0u) + inc - sum;
+#pragma unroll
+        for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
+            const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
+            if (j < n_seg) seg_bit[j] = base;
+            base += v[k];
         }
-        if (tid < (int)old_words) out[tid] = tid == 0 ? 3u : 0u; // BFINAL = 1, BTYPE = 01
-        if (tid == 0) { eob_s = a.code_fixed->eob; hdr_bits_s = a.code_fixed->hdr_bits; }
-        __syncthreads();
+        if (tid == BGZF_THREADS - 1) total_bits_s = base;
+    }
+    __syncthreads();
+    PROF(6); // prefix
+    uint8_t* const dst = a.stage + (size_t)blockIdx.x * BGZF_STRIDE + 2; // + 2: the deflate data (at + 18) starts on a word
+    if (total_bits_s + (eob_s >> 16) > CAP_BITS) {
+        // the image does not hold the block (it would barely shrink, or the context's code was built from other statistics):
+        // a stored block (RFC 1951 3.2.4) -- BFINAL = 1, BTYPE = 00, LEN, ~LEN, the bytes
+        const uint32_t bsize = 18u + 5u + (uint32_t)L + 8u;
+        if (tid < 18) {
+            const uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)((bsize - 1u) & 0xFFu), (uint8_t)((bsize - 1u) >> 8)};
+            dst[tid] = hdr[tid];
+        }
+        if (tid < 5) {
+            const uint8_t sb[5] = {1, (uint8_t)(L & 0xFF), (uint8_t)(L >> 8), (uint8_t)(~L & 0xFF), (uint8_t)((~L >> 8) & 0xFF)};
+            dst[18 + tid] = sb[tid];
+        }
+        for (int i = tid; i < L; i += BGZF_THREADS) dst[23 + i] = in[i];
+        if (tid < 8) {
+            const uint32_t v = tid < 4 ? crc_s : (uint32_t)L;
+            dst[23 + L + tid] = (uint8_t)(v >> (8 * (tid & 3)));
+        }
+        if (tid == 0) a.blk_size[blockIdx.x] = bsize;
+        return;
     }
     // ---- bits: the segments, then the end-of-block code.
     // A literal segment is split into quarters (their bit offsets follow from the counts kept with the segment).
     if (tid == 0) put_bits(out, total_bits_s, eob_s & 0xFFFFu, (int)(eob_s >> 16));
-    {
-        // a warp takes 32 consecutive segments: the matches go out one per lane, then the literal segments of the group are
-        // spread over the lanes a quarter each, so that the byte loops run on full warps
-        for (int j0 = warp * 32; j0 < n_seg; j0 += (BGZF_THREADS / 32) * 32) {
-            const int j = j0 + lane;
-            Seg s;
-            s.pos = s.len = 0; s.info = 0u;
-            if (j < n_seg) s = segs[j];
-            if (s.info & SEG_MATCH) {
+    for (int j = tid; j < n_seg; j += BGZF_THREADS) {
+        const Seg s = segs[j];
+        if (!(s.info & SEG_MATCH)) continue;
+        unsigned long long bb;
+        int n;
+        match_code(len_tab, dist_tab, s.len, (int)(s.info & 0xFFFFu), bb, n);
+        put_bits64(out, seg_bit[j], bb, n);
+    }
+    for (int t = tid; t < n_lit * 4; t += BGZF_THREADS) {
+        const int jj = lit_list[t >> 2], q = t & 3;
+        const Seg ls = segs[jj];
+        int k0, k1, nwb;
+        quarter(ls, q, k0, k1, nwb);
+        if (k0 >= k1) continue;
+        const unsigned c = ls.info; // bits of quarters 0, 1, 2
+        const unsigned cum = (q > 0 ? c & 255u : 0u) + (q > 1 ? (c >> 8) & 255u : 0u) + (q > 2 ? (c >> 16) & 255u : 0u);
+        unsigned at = seg_bit[jj] + cum;
+        unsigned w = at >> 5;
+        int fill = (int)(at & 31u);
+        unsigned long long acc = 0ull;
+        auto pair = [&](uint32_t ea, uint32_t eb) { // two codes (<= 30 bits) behind the pending bits
+            const uint32_t n0 = ea >> 16;
+            acc |= (unsigned long long)((ea & 0xFFFFu) | ((eb & 0xFFFFu) << n0)) << fill;
+            fill += (int)(n0 + (eb >> 16));
+            if (fill >= 32) {
+                atomicOr(&out[w], (uint32_t)acc);
+                ++w;
+                acc >>= 32;
+                fill -= 32;
+            }
+        };
+        int k = k0;
+        for (; k < k0 + nwb; k += 4) { // whole words of an unmatched cell: a match of four bytes or four literals
+            const uint32_t wp = ls.pos + (uint32_t)k, d = wdist[wp >> 2];
+            if (d) {
+                if (fill > 0) atomicOr(&out[w], (uint32_t)acc);
                 unsigned long long bb;
                 int n;
-                match_code(len_tab, dist_tab, s.len, (int)(s.info & 0xFFFFu), bb, n);
-                put_bits64(out, seg_bit[j], bb, n);
-            }
-            const uint32_t litm = __ballot_sync(0xffffffffu, j < n_seg && (s.info & SEG_LIT));
-            const int ntask = 4 * __popc(litm);
-            for (int t = lane; t < ntask; t += 32) {
-                const int jj = j0 + (int)__fns(litm, 0u, (t >> 2) + 1), q = t & 3;
-                const Seg ls = segs[jj];
-                const int ql = (ls.len + 3) >> 2, k0 = q * ql, k1 = min(k0 + ql, (int)ls.len);
-                if (k0 >= k1) continue;
-                const unsigned c = ls.info; // bits of quarters 0, 1, 2
-                const unsigned cum = (q > 0 ? c & 255u : 0u) + (q > 1 ? (c >> 8) & 255u : 0u) + (q > 2 ? (c >> 16) & 255u : 0u);
-                unsigned at = seg_bit[jj] + cum;
-                unsigned w = at >> 5;
-                int fill = (int)(at & 31u);
-                unsigned long long acc = 0ull;
-                for (int k = k0; k < k1; k += 4) { // four look-ups in flight, the codes go in as pairs (<= 30 bits)
-                    uint32_t e[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) e[i] = k + i < k1 ? lit_tab[in[ls.pos + k + i]] : 0u; // past the end: no bits
-#pragma unroll
-                    for (int i = 0; i < 4; i += 2) {
-                        const uint32_t n0 = e[i] >> 16;
-                        acc |= (unsigned long long)((e[i] & 0xFFFFu) | ((e[i + 1] & 0xFFFFu) << n0)) << fill;
-                        fill += (int)(n0 + (e[i + 1] >> 16));
-                        if (fill >= 32) {
-                            atomicOr(&out[w], (uint32_t)acc);
-                            ++w;
-                            acc >>= 32;
-                            fill -= 32;
-                        }
-                    }
-                }
-                if (fill > 0) atomicOr(&out[w], (uint32_t)acc);
+                match_code(len_tab, dist_tab, 4, (int)d, bb, n);
+                at = w * 32u + (unsigned)fill;
+                put_bits64(out, at, bb, n);
+                at += (unsigned)n;
+                w = at >> 5;
+                fill = (int)(at & 31u);
+                acc = 0ull;
+            } else {
+                const uint32_t v = word_at(in, wp);
+                pair(lit_tab[v & 0xFFu], lit_tab[(v >> 8) & 0xFFu]);
+                pair(lit_tab[(v >> 16) & 0xFFu], lit_tab[v >> 24]);
             }
         }
+        for (; k < k1; k += 2) {
+            const uint32_t ea = lit_tab[in[ls.pos + k]], eb = k + 1 < k1 ? lit_tab[in[ls.pos + k + 1]] : 0u; // past the end: no bits
+            pair(ea, eb);
+        }
+        if (fill > 0) atomicOr(&out[w], (uint32_t)acc);
     }
     __syncthreads();
-    PROF(6); // emission
+    PROF(7); // emission
     // ---- the BGZF block: header, deflate data, CRC32, ISIZE -> its slot of the staging buffer
     const uint32_t nbytes = (total_bits_s + (eob_s >> 16) + 7u) >> 3; // + the end-of-block code, rounded up to a byte
     const uint32_t bsize = 18u + nbytes + 8u;
-    uint8_t* const dst = a.stage + (size_t)blockIdx.x * BGZF_STRIDE + 2; // + 2: the deflate data (at + 18) starts on a word
     if (tid < 18) {
         const uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)((bsize - 1u) & 0xFFu), (uint8_t)((bsize - 1u) >> 8)};
         dst[tid] = hdr[tid];
@@ -578,7 +699,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         dst[18 + nbytes + tid] = (uint8_t)(v >> (8 * (tid & 3)));
     }
     if (tid == 0) a.blk_size[blockIdx.x] = bsize;
-    PROF(7); // copy out (thread 0's share)
+    PROF(11); // copy out (thread 0's share)
 }
 
 // exclusive prefix of the block sizes; the totals for the host: [4] compressed bytes, [5] blocks
@@ -654,17 +775,19 @@ extern "C" void vgl_bgzf_prof_dump()
     unsigned long long h[16];
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(h, g_bgzf_prof, sizeof h);
-    static const char* names[11] = {"load+crc||ranges", "segment table", "hash insert", "match", "bit lengths", "prefix", "emission", "copy out", "  w1: issue loads", "  w1: bar 1", "  w1: crc"};
+    static const char* names[12] = {"load+crc||ranges", "segment table", "hash insert", "match", "word insert", "bit lengths + words", "prefix", "emission",
+                                    "  w1: issue loads", "  w1: bar 1", "  w1: crc", "copy out"};
     unsigned long long tot = 0;
     for (int i = 0; i < 8; ++i) tot += h[i];
+    tot += h[11];
     fprintf(stderr, "bgzf cycles (thread 0, all blocks) %.4g\n", (double)tot);
-    for (int i = 0; i < 11; ++i) fprintf(stderr, "bgzf phase %-18s %6.2f %%\n", names[i], 100.0 * (double)h[i] / (double)(tot ? tot : 1));
+    for (int i = 0; i < 12; ++i) fprintf(stderr, "bgzf phase %-18s %6.2f %%\n", names[i], 100.0 * (double)h[i] / (double)(tot ? tot : 1));
     memset(h, 0, sizeof h);
     cudaMemcpyToSymbol(g_bgzf_prof, h, sizeof h);
 }
 #endif
 
-size_t bgzf_dyn_smem() { return (size_t)BGZF_IN + (size_t)OUT_WORDS * 4 + (size_t)MAX_SEG * (sizeof(Seg) + 4) + (size_t)HASH_SLOTS * 4 + (size_t)MAX_RANGES * 16; }
+size_t bgzf_dyn_smem() { return (size_t)BGZF_IN + (size_t)OUT_WORDS * 4 + (size_t)MAX_SEG * (sizeof(Seg) + 4 + 2) + (size_t)HASH_SLOTS * 4 + (size_t)MAX_RANGES * 16; }
 
 // blocks a record stream of `bytes` bytes makes
 int64_t bgzf_blocks_for(int64_t bytes) { return (bytes + BGZF_IN - 1) / BGZF_IN; }

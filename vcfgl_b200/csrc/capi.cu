@@ -19,7 +19,7 @@ using namespace vgl;
 
 namespace {
 
-enum { EV_START = 0, EV_H2D, EV_SIM, EV_SITE, EV_SCAN, EV_EMIT, EV_META, EV_D2H0, EV_D2H1, EV_KDONE, EV_COUNT };
+enum { EV_START = 0, EV_H2D, EV_SIM, EV_SITE, EV_SCAN, EV_EMIT, EV_META, EV_D2H0, EV_D2H1, EV_KDONE, EV_BCF, EV_COUNT };
 
 struct DevBuf {
     void* p = nullptr;
@@ -111,9 +111,9 @@ struct vgl_ctx {
     int narrow_bits = 0;                   // VGL_HOST_NARROW: width of the DP / AD planes (8 or 16), 0 = int32 planes
     size_t bcf_cap = 0, blob_cap = 0;      // VGL_HOST_BCF: bytes per slot of the record stream / the pass-through blob
     int64_t bgzf_max_blocks = 0;           // VGL_HOST_BGZF: blocks a full record stream makes
-    BgzfCode* d_bgzf_code = nullptr;       // [2]: the context's prefix code, deflate's fixed code
+    BgzfCode* d_bgzf_code = nullptr;       // the context's prefix code (deflate's fixed code until the statistics pass)
     uint32_t* d_bgzf_hist = nullptr;       // symbol counts of the statistics pass
-    bool bgzf_code_ready = false;          // [0] built from the first batch's record stream (vgl_submit)
+    bool bgzf_code_ready = false;          // built from the first batch's record stream (vgl_submit)
     double stream_bytes_per_site = 0.0;    // VGL_HOST_BCF / BGZF: bytes per site of the last finished batch (predicts the next copy)
     // VGL_HOST_BCF with -doGVCF: thresholds, and the block still open at the end of the last waited batch (the seam)
     std::vector<int32_t> gvcf_dps;
@@ -528,9 +528,8 @@ static int create_impl(vgl_ctx* ctx)
                 CK(cudaMalloc((void**)&s.d_blk_first, (size_t)ctx->bgzf_max_blocks * sizeof(int32_t)));
                 CK(cudaMalloc((void**)&s.d_blk_rng, (size_t)ctx->bgzf_max_blocks * BGZF_RNG_WORDS * sizeof(uint32_t)));
                 if (!ctx->d_bgzf_code) {
-                    std::vector<BgzfCode> codes(2);
+                    std::vector<BgzfCode> codes(1);
                     bgzf_build_code(nullptr, true, &codes[0]);
-                    codes[1] = codes[0];
                     CK(upload(&ctx->d_bgzf_code, codes));
                     CK(cudaMalloc((void**)&ctx->d_bgzf_hist, BGZF_HIST * sizeof(uint32_t)));
                     ctx->bgzf_code_ready = getenv("VGL_BGZF_FIXED") != nullptr; // development: keep the fixed code
@@ -1216,6 +1215,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
         }
         launch_bcf(b, st);
         ctx->launches += 3;
+        CK(cudaEventRecord(s.ev[EV_BCF], st));
         if (bgzf) {
             BgzfArgs z;
             memset(&z, 0, sizeof z);
@@ -1224,7 +1224,7 @@ extern "C" int vgl_submit(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t
             z.stage = s.d_stage; z.blk_size = s.d_blk_size; z.blk_off = s.d_blk_off; z.blk_first = s.d_blk_first; z.rng_g = s.d_blk_rng; z.out = s.d_bgzf; z.totals = s.d_totals;
             // blocks this batch can make at most (its worst-case record bytes), not the slot's capacity
             const int64_t nb_max = std::min<int64_t>(ctx->bgzf_max_blocks, bgzf_blocks_for((int64_t)((double)ctx->bcf_cap * n_sites / prm.max_batch_sites) + 65536));
-            z.code = ctx->d_bgzf_code; z.code_fixed = ctx->d_bgzf_code + 1;
+            z.code = ctx->d_bgzf_code;
             if (!ctx->bgzf_code_ready) {
                 // once per context: the symbol statistics of this batch's parse -> a dynamic Huffman code (RFC 1951 3.2.7)
                 // every later block starts with; the simulated tags have the same statistics from batch to batch
@@ -1426,6 +1426,22 @@ extern "C" int vgl_wait(vgl_ctx* ctx, int slot, vgl_batch_out* out)
         if (s.had_d2h) CK(cudaEventElapsedTime(&d2h, s.ev[EV_D2H0], s.ev[EV_D2H1]));
         ms[VGL_T_D2H] = meta + d2h;
         CK(cudaEventElapsedTime(&ms[VGL_T_TOTAL], s.ev[EV_START], s.had_d2h ? s.ev[EV_D2H1] : s.ev[EV_META]));
+        if (getenv("VGL_TRACE") && (prm.host_output == VGL_HOST_BCF || prm.host_output == VGL_HOST_BGZF)) { // development: the kernel chain of the batch
+            float t_bcf = 0.f, t_z = 0.f, t_wait = 0.f;
+            cudaEventElapsedTime(&t_wait, s.ev[EV_H2D], s.ev[EV_SCAN]);
+            cudaEventElapsedTime(&t_bcf, s.ev[EV_EMIT], s.ev[EV_BCF]);
+            cudaEventElapsedTime(&t_z, s.ev[EV_BCF], s.ev[EV_KDONE]);
+            fprintf(stderr, "[vgl] batch: h2d %.2f, waited for the previous batch's kernels %.2f, simulate %.2f, serialise %.2f, compress %.2f ms\n",
+                    ms[VGL_T_H2D], t_wait, ms[VGL_T_EMIT], t_bcf, t_z);
+            static cudaEvent_t base = nullptr; // absolute timeline: the first traced batch's start
+            if (!base) base = s.ev[EV_START];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            cudaEventElapsedTime(&a0, base, s.ev[EV_START]);
+            cudaEventElapsedTime(&a1, base, s.ev[EV_SCAN]);
+            cudaEventElapsedTime(&a2, base, s.ev[EV_KDONE]);
+            cudaEventElapsedTime(&a3, base, s.ev[EV_D2H1]);
+            fprintf(stderr, "[vgl] timeline: submit %.2f  kernels %.2f .. %.2f  copies done %.2f\n", a0, a1, a2, a3);
+        }
     }
     s.waited = true;
     memset(out, 0, sizeof *out);

@@ -177,7 +177,6 @@ struct BgzfArgs {
     uint8_t* out;               // the compressed stream, blocks back to back
     int64_t* totals;            // [3] bytes of the record stream (in); [4] compressed bytes, [5] blocks (out)
     const BgzfCode* code;       // the context's prefix code (tables.h): deflate's fixed code until the statistics pass has run
-    const BgzfCode* code_fixed; // the fixed code (blocks the context's code would expand beyond the block image)
     uint32_t* hist;             // non-null: statistics pass -- [BGZF_HIST] symbol counts of the parse, no output
 };
 size_t bgzf_dyn_smem();
