@@ -113,7 +113,12 @@ __device__ __forceinline__ CellCounts sample_counts(const CountsParams& cp, int6
     if (e > 0.0) {
         const float p0 = exp2f((float)n * l2);
         const float uf = ((float)(w.z >> 8) + 0.5f) * 5.9604645e-08f; // 24-bit uniform in (0,1)
-        if (l2 != 0.0f && p0 > 1e-30f) {
+        if (uf > 0.998f) {
+            // the upper tail: a float CDF saturates at 1.0f and a 24-bit uniform cannot fall into events rarer than 6e-8 per cell
+            // (five errors in ten reads at e = 0.01) -- exact inversion in double with 64 random bits
+            const double u = ((double)w.z + ((double)st.next() + 0.5) * 2.3283064365386963e-10) * 2.3283064365386963e-10;
+            E = binom_inversion(n, e, u);
+        } else if (l2 != 0.0f && p0 > 1e-30f) {
             // fast path: float CDF walk (e <= 0.5, no underflow); P(E=0) = p0 ends most cells here
             float p = p0, cdf = p0;
             while (uf > cdf && E < n) {
