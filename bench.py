@@ -353,6 +353,31 @@ def sub_leg(name, local, stream):
     return out
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this process to the CPU cores NVML lists as close to its GPU.  The pinned host buffers are first touched there, so the
+    DMA of the result copies ends on the GPU's own socket instead of crossing the inter-socket link (which all ranks would share).
+    Returns the number of cores bound to, or None."""
+    if os.environ.get("VGL_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in range(64 * words) if (mask[c // 64] >> (c % 64)) & 1 and c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def gpu_arm(opt):
     import numpy as np
     import torch
@@ -364,6 +389,7 @@ def gpu_arm(opt):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libvgl has no CPU path")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(torch, local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -541,7 +567,8 @@ def gpu_arm(opt):
                    "slots_in_flight": N_SLOTS,
                    "l2": "no flush: each launch writes %.2f GB of tag planes (> 126 MB L2)" % (alg_bytes / 1e9),
                    "n_samples": S, "timed_region_s": t_max * 1e-3,
-                   "sites_with_15_genotypes": g_share, "sharding": "contiguous site ranges per GPU, no collective"},
+                   "sites_with_15_genotypes": g_share, "sharding": "contiguous site ranges per GPU, no collective",
+                   "cpus_bound_near_gpu": numa_cpus},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * S * Le), "d2h_bytes_per_step": d2h_bytes * Le,
                 "steps": Ke, "launches_per_step": Le, "gpu_launches": int(e2e_launches), "timer": "host wall clock, max over ranks",

@@ -123,7 +123,7 @@ def test_fused_tags_match_oracle_on_own_counts(name):
             assert np.array_equal(u32(d["gl"]), u32(e["gl"])) and np.array_equal(d["fmt_ad"], e["fmt_ad"])
 
 
-@pytest.mark.parametrize("name,no_tile,kernels", [("gl1_d10", False, "k_fused_m1f"), ("gl1_d30", True, "k_fused_m1f"),
+@pytest.mark.parametrize("name,no_tile,kernels", [("gl1_d10", True, "k_fused_m1f"), ("gl1_d10", False, "k_tile_m1f"), ("gl1_d30", True, "k_fused_m1f"),
                                                   ("gl1_d30", False, "k_tile_m1f"), ("gl1_df", True, "k_fused_m1f"),
                                                   ("gl1_df", False, "k_tile_m1f")])
 def test_count_sampler_distributions_match_reference(name, no_tile, kernels, monkeypatch):

@@ -54,7 +54,9 @@ NATIVE = {
     "tile_m1f": ("--seed 3 -d 10 -e 0.01 -GL 1 -addPL 1 -addFormatAD 1", 100, 500, "k_tile_m1f", 8),
     "tile_m1f_unobs": ("--seed 3 -d 3 -e 0.02 -GL 1 -doUnobserved 1 -addPL 1 -addFormatAD 1 -addInfoAD 1", 37, 333, "k_tile_m1f", 8),
     "tile_m2": ("--seed 4 -d 6 -e 0.01 -GL 2 -addPL 1 -addFormatAD 1", 50, 400, "k_tile_m2", 8),
-    "general_alltags": ("--seed 5 -d 6 -e 0.02 -GL 1 -doUnobserved 1 -addGP 1 -addPL 1 -addI16 1 -addQS 1 -addInfoDP 1 -addFormatAD 1 "
+    "tile_m1f_alltags": ("--seed 5 -d 6 -e 0.02 -GL 1 -doUnobserved 1 -addGP 1 -addPL 1 -addI16 1 -addQS 1 -addInfoDP 1 -addFormatAD 1 "
+                         "-addInfoAD 1 -addFormatADF 1 -addInfoADF 1 -addFormatADR 1 -addInfoADR 1", 37, 300, "k_tile_m1f", 8),
+    "general_alltags": ("--seed 5 -d 6 -e 0.02 -eq 2 -bv 1e-4 -GL 1 -doUnobserved 1 -addGP 1 -addPL 1 -addI16 1 -addQS 1 -addInfoDP 1 -addFormatAD 1 "
                         "-addInfoAD 1 -addFormatADF 1 -addInfoADF 1 -addFormatADR 1 -addInfoADR 1", 37, 300, "k_sim+k_site+k_scan+k_emit", 8),
     "deep_u16": ("--seed 6 -d 300 -e 0.01 -GL 1 -addPL 1 -addFormatAD 1", 6, 40, None, 16),
 }

@@ -390,9 +390,10 @@ static int create_impl(vgl_ctx* ctx)
         if (alias_ok) alias = all;
         else alias_row.clear();
     }
-    // the tile kernel (tile_m1f.cu): the fused path's headline special case; its AUX variant also takes QS / I16 / INFO ADF, ADR
+    // the tile kernel (tile_m1f.cu): the fused path's headline special case; its AUX variant also takes QS / I16 / INFO ADF, ADR / GP /
+    // FORMAT ADF, ADR
     const bool tile_base = ctx->gl_mode == GL_M1_FIXED && p.sampler != VGL_SAMPLER_PER_READ && g_cap_elems < (1ull << 31) && alias_ok &&
-                           p.error_qs == 0 && ctx->fast_div && !(t & (VGL_TAG_GP | VGL_TAG_FMT_ADF | VGL_TAG_FMT_ADR)) &&
+                           p.error_qs == 0 && ctx->fast_div &&
                            p.n_samples <= tile_m1f_max_samples() && !getenv("VGL_NO_TILE");
     ctx->tile_aux = tile_base && (t & tile_m1f_aux_tags()) != 0;
     ctx->use_tile = tile_base && (ctx->tile_aux || (ctx->use_fused && !ctx->sample_strand));

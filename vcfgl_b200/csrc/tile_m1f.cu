@@ -458,10 +458,12 @@ int build_m1f_pure_table(const double* d_bsum, const double* d_het, void* out, c
 
 // GEN: any subset of the GL / PL / AD planes (else all three); BIG: a site's counts do not fit the shared-memory
 // cache -> they pass through a per-CTA scratch row in global memory (L2-resident), read one chunk ahead;
-// AUX: QS / I16 / INFO ADF, ADR (strand and tail-distance draws in phase A, per-site sums in an extra phase after B)
+// AUX: QS / I16 / INFO ADF, ADR (strand and tail-distance draws in phase A, per-site sums in an extra phase after B) and the
+// further per-cell planes GP / FORMAT ADF, ADR (an extra pass per chunk in phase C)
 // PURE: chunks whose cells all show a single base take the closed form (m1_pure table); compiled in only for runs where such
 // chunks are the rule (low depth x error rate), because the extra branch costs the general path ~10 %
-template <bool GEN, bool BIG, bool AUX, bool PURE>
+// XTRA (AUX only): GP / FORMAT ADF, ADR wanted
+template <bool GEN, bool BIG, bool AUX, bool PURE, bool XTRA>
 __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
@@ -520,6 +522,13 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
     asm volatile("mov.u32 %0, %0;" : "+r"(plane_flags));
     const bool has_gl = GEN ? (plane_flags & 1u) != 0u : true, has_pl = GEN ? (plane_flags & 2u) != 0u : true, has_ad = GEN ? (plane_flags & 4u) != 0u : true;
     const bool want_tail = AUX && (p.tag_mask & VGL_TAG_I16) != 0;
+    // further per-cell planes of the AUX variant: 1 = GP, 2 = FORMAT ADF, 4 = FORMAT ADR (staged through the same slices after GL / PL / AD)
+    uint32_t xflags = 0u;
+    if (XTRA) {
+        xflags = (p.gp != nullptr ? 1u : 0u) | (p.adf != nullptr ? 2u : 0u) | (p.adr != nullptr ? 4u : 0u);
+        asm volatile("mov.u32 %0, %0;" : "+r"(xflags));
+    }
+    const bool stage_gl = XTRA ? (has_gl || (xflags & 1u)) : has_gl; // GP is made from the staged GL values
     const uint32_t s_wg = s_smem + OFF_STAGE + warp * WST * 4; // this warp's GL slice; PL at +TILE_WST_G words, AD at +2*TILE_WST_G
     const uint32_t s_wr = s_wg + 2 * TILE_WST_G * 4;
     const uint32_t s_cnt = s_smem + OFF_CNT, s_st = s_smem + OFF_ST;
@@ -735,6 +744,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
         float* const gl_t = has_gl ? p.gl + s_base[0] : nullptr;
         int32_t* const pl_t = has_pl ? p.pl + s_base[0] : nullptr;
         int32_t* const ad_t = has_ad ? p.ad + s_base[1] : nullptr;
+        float* const gp_t = (XTRA && (xflags & 1u)) ? p.gp + s_base[0] : nullptr;
+        int32_t* const adf_t = (XTRA && (xflags & 2u)) ? p.adf + s_base[1] : nullptr;
+        int32_t* const adr_t = (XTRA && (xflags & 4u)) ? p.adr + s_base[1] : nullptr;
         const uint4* const pure_tab = reinterpret_cast<const uint4*>(p.m1_pure);
         // chunk tickets run two ahead and the counts of the next chunk are fetched before the current one is scored
         auto load_counts = [&](int chunk) -> uint32_t {
@@ -788,13 +800,13 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
                     if (g >= gmax) break;
                     const bool one = (cm >> g) & 1u;
                     if (g < G && live) {
-                        if (has_gl) sts32(dstb + 4u * g, __float_as_uint(one ? tv.gl1 : tv.gl0));
+                        if (stage_gl) sts32(dstb + 4u * g, __float_as_uint(one ? tv.gl1 : tv.gl0));
                         if (has_pl) sts32(dstb + 4u * g + TILE_WST_G * 4, (uint32_t)(one ? tv.pl1 : tv.pl0));
                     }
                 }
                 if (live) { // the slot of xx
                     const uint32_t hs = dstb + ((cm >> 16) & 0xFu) * 4u;
-                    if (has_gl) sts32(hs, 0u);
+                    if (stage_gl) sts32(hs, 0u);
                     if (has_pl) sts32(hs + TILE_WST_G * 4, 0u);
                 }
             } else {
@@ -802,8 +814,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
                 // slot test (their offsets may be 0xFF)
                 float q[15];
                 m1f_scores_noclamp(n, c0, c1, c2, c3, p.m1_bsum, p.m1_het, q);
-                if (__all_sync(0xffffffffu, (t1.z >> 16) != 0u)) tile_emit_cell<true>(q, slot, cell_g, has_gl, has_pl);
-                else tile_emit_cell<false>(q, slot, cell_g, has_gl, has_pl);
+                if (__all_sync(0xffffffffu, (t1.z >> 16) != 0u)) tile_emit_cell<true>(q, slot, cell_g, stage_gl, has_pl);
+                else tile_emit_cell<false>(q, slot, cell_g, stage_gl, has_pl);
             }
             if (has_ad) { // AD in allele order (vcfgl.cpp:806-831): byte permute, selector 4 reads 0
                 sts32(cell_r, __byte_perm(c4, 0u, t2.x));
@@ -831,14 +843,69 @@ __global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN
             }
             fence_async_smem();
             __syncwarp();
+            const uint32_t gb = (uint32_t)(g_hi - g_lo) * 4u, rb = (uint32_t)(r_hi - r_lo) * 4u;
             if (lane == 0) {
-                const uint32_t gb = (uint32_t)(g_hi - g_lo) * 4u, rb = (uint32_t)(r_hi - r_lo) * 4u;
                 if (gb) {
                     if (has_gl) bulk_store(gl_t + g_lo, s_wg, gb);
                     if (has_pl) bulk_store(pl_t + g_lo, s_wg + TILE_WST_G * 4, gb);
                 }
                 if (rb && has_ad) bulk_store(ad_t + r_lo, s_wr, rb);
                 bulk_commit();
+            }
+            if (XTRA && xflags) {
+                // GP (vcfgl.cpp:941-970) and FORMAT ADF / ADR (vcfgl.cpp:806-831) go through the same slices once the copies above
+                // have read them: GP replaces PL, ADF then ADR replace AD; the padding words are already zero.  The forward reads
+                // per base are the draws phase A summed per site.
+                uint32_t fw4 = 0u;
+                if (xflags & 6u) {
+                    const int nmax = __reduce_max_sync(0xffffffffu, n);
+                    fw4 = tile_strand_counts(p, site_base + (uint32_t)sl, (uint32_t)v, c4, nmax);
+                }
+                bulk_wait_read();
+                __syncwarp();
+                if ((xflags & 1u) && live) {
+                    if (n == 0) {
+#pragma unroll 1
+                        for (int g = 0; g < G; ++g) sts32(cell_g + 4 * (TILE_WST_G + g), VGL_F32_MISSING_BITS);
+                    } else {
+                        float sum = 0.0f;
+#pragma unroll 1
+                        for (int g = 0; g < G; ++g) {
+                            const float e10 = __double2float_rn(exp10((double)__uint_as_float(lds32(cell_g + 4 * g))));
+                            sts32(cell_g + 4 * (TILE_WST_G + g), __float_as_uint(e10));
+                            sum = __fadd_rn(sum, e10);
+                        }
+#pragma unroll 1
+                        for (int g = 0; g < G; ++g)
+                            sts32(cell_g + 4 * (TILE_WST_G + g), __float_as_uint(__fdiv_rn(__uint_as_float(lds32(cell_g + 4 * (TILE_WST_G + g))), sum)));
+                    }
+                }
+                auto put_r = [&](uint32_t c) { // per-base counts in allele order, like AD
+                    sts32(cell_r, __byte_perm(c, 0u, t2.x));
+                    if (A > 1) sts32(cell_r + 4, __byte_perm(c, 0u, t2.x >> 16));
+                    if (A > 2) sts32(cell_r + 8, __byte_perm(c, 0u, t2.y));
+                    if (A > 3) sts32(cell_r + 12, __byte_perm(c, 0u, t2.y >> 16));
+                    if (A > 4) sts32(cell_r + 16, __byte_perm(c, 0u, t1.w));
+                };
+                if (xflags & 2u) put_r(fw4);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0 && (xflags & 3u)) {
+                    if (gb && (xflags & 1u)) bulk_store(gp_t + g_lo, s_wg + TILE_WST_G * 4, gb);
+                    if (rb && (xflags & 2u)) bulk_store(adf_t + r_lo, s_wr, rb);
+                    bulk_commit();
+                }
+                if (xflags & 4u) {
+                    bulk_wait_read();
+                    __syncwarp();
+                    put_r(__vsub4(c4, fw4));
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (rb) bulk_store(adr_t + r_lo, s_wr, rb);
+                        bulk_commit();
+                    }
+                }
             }
             cur = nxt;
             c4 = c4_next;
@@ -862,25 +929,28 @@ static size_t tile_dyn_smem(bool big)
            (big ? 0 : (size_t)TILE_CELLS * 4);
 }
 
-template <bool GEN, bool BIG, bool AUX, bool PURE>
+template <bool GEN, bool BIG, bool AUX, bool PURE, bool XTRA>
 static void launch_tile_p(const DevParams& p, cudaStream_t st, int n_sms)
 {
     const size_t dyn = tile_dyn_smem(BIG) + (AUX ? TILE_MAX_SITES * sizeof(TAux) + (BIG ? 0 : (TILE_CELLS / 32) * 32) : 0);
-    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX, PURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX, PURE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX, PURE, XTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_tile_m1f<GEN, BIG, AUX, PURE, XTRA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN, BIG, AUX, PURE>, TILE_BLOCK, dyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_m1f<GEN, BIG, AUX, PURE, XTRA>, TILE_BLOCK, dyn);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > TILE_SCRATCH_CTAS_PER_SM) per_sm = TILE_SCRATCH_CTAS_PER_SM;
     int grid = n_sms * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    k_tile_m1f<GEN, BIG, AUX, PURE><<<grid, TILE_BLOCK, dyn, st>>>(p);
+    k_tile_m1f<GEN, BIG, AUX, PURE, XTRA><<<grid, TILE_BLOCK, dyn, st>>>(p);
 }
 template <bool GEN, bool BIG, bool AUX>
 static void launch_tile_t(const DevParams& p, cudaStream_t st, int n_sms)
 {
-    if (p.m1_pure != nullptr) launch_tile_p<GEN, BIG, AUX, true>(p, st, n_sms);
-    else launch_tile_p<GEN, BIG, AUX, false>(p, st, n_sms);
+    const bool xtra = AUX && (p.gp != nullptr || p.adf != nullptr || p.adr != nullptr);
+    if (AUX && xtra) { // the extra planes come with the general code (no closed form for pure chunks: GP needs the staged GL values of every cell anyway)
+        launch_tile_p<GEN, BIG, AUX, false, AUX>(p, st, n_sms);
+    } else if (p.m1_pure != nullptr) launch_tile_p<GEN, BIG, AUX, true, false>(p, st, n_sms);
+    else launch_tile_p<GEN, BIG, AUX, false, false>(p, st, n_sms);
 }
 
 // aux: QS / I16 / INFO ADF, ADR wanted (tile_m1f_aux_tags)
@@ -958,7 +1028,7 @@ void launch_tile_m1f_draws(const DevParams& p, cudaStream_t st, int pass, int32_
 }
 
 // tags the AUX variant adds to the tile kernel's GL / PL / AD / DP / INFO AD, DP
-uint32_t tile_m1f_aux_tags() { return VGL_TAG_QS | VGL_TAG_I16 | VGL_TAG_INFO_ADF | VGL_TAG_INFO_ADR; }
+uint32_t tile_m1f_aux_tags() { return VGL_TAG_QS | VGL_TAG_I16 | VGL_TAG_INFO_ADF | VGL_TAG_INFO_ADR | VGL_TAG_GP | VGL_TAG_FMT_ADF | VGL_TAG_FMT_ADR; }
 
 // largest S the tile kernel takes (the slot arithmetic needs (S4 + block) * S4 < 2^32)
 int tile_m1f_max_samples() { return 60000; }
