@@ -29,6 +29,9 @@ namespace vgl {
 #define M2_TAB_MAXQ 8                     // scores whose tables fit the shared-memory copy
 #define M2_TAB_CLS 544                    // byte offset of the class table
 #define M2_SCR_BYTES 2048                 // per-warp scratch: 16 words per lane (the quality classes of up to 64 reads, LUT mode)
+#ifndef M2_MIN_CTAS_LUT
+#define M2_MIN_CTAS_LUT 4                // MODE 2 (per-read quality classes): more registers beat a fifth resident CTA (0.706 -> 0.648 ms on cfg3(ii))
+#endif
 #ifndef M2_MIN_CTAS
 #define M2_MIN_CTAS 5
 #endif
@@ -378,7 +381,7 @@ struct __align__(16) M2Chunk { // per chunk of 32 virtual cells, written in phas
 // (every lane a mixed cell), runs the per-read chains and parks the 15 results per cell in a per-CTA scratch row in
 // global memory (L2-resident); phase C then only assembles: table values for pure cells, parked values for mixed ones.
 template <int MODE, bool BIG, bool TAB, bool GLPL>
-__global__ void __launch_bounds__(TILE_BLOCK, M2_MIN_CTAS) k_tile_m2(const __grid_constant__ DevParams p)
+__global__ void __launch_bounds__(TILE_BLOCK, MODE == 2 ? M2_MIN_CTAS_LUT : M2_MIN_CTAS) k_tile_m2(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     // layout: alias [256] u64 | cdf_e [256] uint4 | stage | st [sites] | tot [sites][4] | site_e [sites] |
