@@ -635,41 +635,53 @@ def input_path_leg(a, gt, hap, B, S, first_site, local, peak_of):
     ctx.close()
     # VCF text in -> finished BCF records out: input path + simulation + device BCF serialisation (VGL_HOST_BCF); the host only
     # copies POS from the parser's site records into the pass-through records and would append the returned bytes to the file
-    text_to_bcf = None
-    if not a.do_gvcf:
-        ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=2, device_id=local, host_output=capi.HOST_BCF,
+    def text_to_records(mode, n_slots, n_batches):
+        ctx = capi.Context(capi.params_from_args(a, S, max_batch_sites=B, n_slots=n_slots, device_id=local, host_output=mode,
                                                  bcf_dict=dict(DP=1, GL=2, PL=3, GP=4, AD=5, ADF=6, ADR=7, QS=8, I16=9)))
         ps = ctx.parser(n_text + 64, B)
         ps.parse(body, capi.SOURCE_BINARY, 0)
-        bcf_in = [ctx.bcf_input(0)[0], ctx.bcf_input(1)[0]]
+        bcf_in = [ctx.bcf_input(k)[0] for k in range(n_slots)]
 
-        def step_bcf(i, slot):
+        def step_rec(i, slot):
             r = ps.parse(None, capi.SOURCE_BINARY, 0, n_bytes=n_text)
             sin = bcf_in[slot]
             sin["pos"][:B] = r.sites["pos"]
             sin["qual_bits"][:B] = capi.F32_MISSING_BITS
             ctx.place_rows(slot, ps, B)
             ctx.submit(slot, first_site + i * B, B, flags=capi.SUBMIT_GT_ON_DEVICE)
-        for i in range(2):
-            step_bcf(i, i & 1)
-        ctx.wait(0), ctx.wait(1)
+
+        def size_of(b):
+            return b.bgzf_bytes if mode == capi.HOST_BGZF else b.bcf_bytes
+        for i in range(n_slots):
+            step_rec(i, i)
+        for k in range(n_slots):
+            ctx.wait(k)
         torch.cuda.synchronize()
         t0 = _t.perf_counter()
         pend, nbytes = [], 0
-        for i in range(n_e2e):
-            slot = i & 1
-            if len(pend) == 2:
-                nbytes = ctx.wait(pend.pop(0)).bcf_bytes
-            step_bcf(i, slot)
+        for i in range(n_batches):
+            slot = i % n_slots
+            if len(pend) == n_slots:
+                nbytes = size_of(ctx.wait(pend.pop(0)))
+            step_rec(i, slot)
             pend.append(slot)
         for slot in pend:
-            nbytes = ctx.wait(slot).bcf_bytes
+            nbytes = size_of(ctx.wait(slot))
         torch.cuda.synchronize()
-        wall_bcf = _t.perf_counter() - t0
+        wall_rec = _t.perf_counter() - t0
         ps.close()
         ctx.close()
-        text_to_bcf = {"value": n_e2e * B * S / wall_bcf, "unit": UNIT, "h2d_bytes_per_step": n_text, "d2h_bytes_per_step": int(nbytes), "steps": n_e2e,
+        return n_batches * B * S / wall_rec, int(nbytes)
+
+    text_to_bcf = text_to_bgzf = None
+    if not a.do_gvcf:
+        v, nbytes = text_to_records(capi.HOST_BCF, 2, n_e2e)
+        text_to_bcf = {"value": v, "unit": UNIT, "h2d_bytes_per_step": n_text, "d2h_bytes_per_step": nbytes, "steps": n_e2e,
                        "note": "VCF text in pinned host memory -> BCF records in pinned host memory: k_vcf_* + k_place_rows + simulation + k_bcf_*; host wall clock"}
+        v, nbytes = text_to_records(capi.HOST_BGZF, 3, 4 * n_e2e)
+        text_to_bgzf = {"value": v, "unit": UNIT, "h2d_bytes_per_step": n_text, "d2h_bytes_per_step": nbytes, "steps": 4 * n_e2e,
+                        "note": "the same with the records BGZF-compressed on the device (k_bgzf_*): what the reference program does from its input file "
+                                "to its default (-O b) output file, minus reading and writing the files; three slots; host wall clock"}
     # CPU baseline: oracle restatement, one thread, bounded sample
     cpu = None
     try:
@@ -700,7 +712,7 @@ def input_path_leg(a, gt, hap, B, S, first_site, local, peak_of):
                          "algorithmic_bytes_per_step": alg, "bytes_per_cell": alg / (B * S)},
             "e2e": {"value": n_e2e * B * S / wall, "unit": UNIT, "h2d_bytes_per_step": n_text, "steps": n_e2e,
                     "note": "pinned host text -> H2D -> k_vcf_* -> k_place_rows -> simulate -> D2H (VGL_HOST_NARROW); host wall clock, two slots"},
-            "text_to_bcf": text_to_bcf, "cpu_baseline": cpu}
+            "text_to_bcf": text_to_bcf, "text_to_bgzf": text_to_bgzf, "cpu_baseline": cpu}
 
 
 def main():

@@ -236,7 +236,9 @@ typedef struct vgl_batch_out {
      * default container, -O b), each block a gzip member holding 32 KiB of the stream.  `bgzf` holds the blocks back to back:
      * the host appends the bytes to the output file after its own (BGZF-compressed) header and closes the file with the 28-byte
      * BGZF EOF block.  `bcf` is NULL in this mode; bcf_off / bcf_bytes still describe the UNCOMPRESSED stream (record i starts at
-     * uncompressed offset bcf_off[i], e.g. for an index), bgzf_bytes the compressed one. */
+     * uncompressed offset bcf_off[i], e.g. for an index), bgzf_bytes the compressed one.  The blocks of a context share one
+     * dynamic Huffman code built by the first vgl_submit from the symbol statistics of its record stream (that call synchronises
+     * the slot's stream once); blocks that would not shrink to three quarters are stored (RFC 1951 3.2.4). */
     const uint8_t* bgzf;
     int64_t bgzf_bytes;
     int32_t bgzf_blocks;

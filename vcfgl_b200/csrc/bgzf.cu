@@ -253,12 +253,14 @@ __device__ unsigned long long g_bgzf_prof[16];
 #define PROFW(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs a)
+// one block of the stream (a whole CTA); the CRC and code tables are the kernel's, loaded once per CTA
+__device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, unsigned char* const sm, const uint32_t* const crc_tab,
+                                              const uint32_t* const lit_tab, const uint32_t* const len_tab, const uint32_t* const dist_tab,
+                                              const uint32_t eob_s, const uint32_t hdr_bits_s)
 {
 #ifdef BGZF_PROF
     long long prof_t = clock64();
 #endif
-    extern __shared__ __align__(16) unsigned char sm[];
     uint8_t* const in = sm;                                                       // [BGZF_IN]
     uint32_t* const out = reinterpret_cast<uint32_t*>(sm + BGZF_IN);              // [OUT_WORDS]
     Seg* const segs = reinterpret_cast<Seg*>(sm + BGZF_IN + OUT_WORDS * 4);        // [MAX_SEG]
@@ -266,17 +268,13 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     uint32_t* const htab = seg_bit + MAX_SEG;                                     // [HASH_SLOTS] tag << 16 | position
     uint32_t* const rng = htab + HASH_SLOTS;                                      // [MAX_RANGES][4]: pos, len, cell bytes (0: gap), first segment
     uint16_t* const lit_list = reinterpret_cast<uint16_t*>(rng + MAX_RANGES * 4);  // [MAX_SEG] the segments that are not matches (any order)
-    __shared__ uint32_t crc_tab[1024]; // slicing-by-four tables of CRC-32
-    __shared__ uint32_t lit_tab[256], len_tab[256], dist_tab[32]; // the context's prefix code (BgzfCode)
-    __shared__ uint32_t eob_s, hdr_bits_s;
     __shared__ uint32_t warp_tot[32];
     __shared__ int n_rng_s, n_seg_s, lit_only_s, n_lit_s;
     __shared__ uint32_t crc_s, total_bits_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total = a.totals[3];
-    const long long b0 = (long long)blockIdx.x * BGZF_IN;
-    if (b0 >= total || total > a.in_cap) return;
+    const long long b0 = (long long)blk * BGZF_IN;
     const int L = (int)min((long long)BGZF_IN, total - b0);
 
     // ---- warps 1..: the block's bytes, the CRC and literal-code tables, cleared tables; meanwhile warp 0: the ranges
@@ -289,13 +287,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         if (t < n16) v0 = __ldcs(src + t);
         if (t + nt < n16) v1 = __ldcs(src + t + nt);
         if (t + 2 * nt < n16) v2 = __ldcs(src + t + 2 * nt);
-        for (int i = t; i < 1024; i += nt) crc_tab[i] = __ldg(a.crc_pow + 1024 + i);
-        if (t < 256) {
-            lit_tab[t] = __ldg(a.code->lit + t);
-            len_tab[t] = __ldg(a.code->len + t);
-            if (t < 32) dist_tab[t] = __ldg(a.code->dist + t);
-        }
-        if (t == 0) { crc_s = 0u; n_lit_s = 0; eob_s = a.code->eob; hdr_bits_s = a.code->hdr_bits; }
+        if (t == 0) { crc_s = 0u; n_lit_s = 0; }
         for (int i = t; i < OUT_WORDS / 4; i += nt) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = t; i < HASH_SLOTS / 4; i += nt) reinterpret_cast<uint4*>(htab)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         if (t < n16) reinterpret_cast<uint4*>(in)[t] = v0;
@@ -334,10 +326,10 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
 
     // ---- ranges: made by k_bgzf_ranges ahead of this kernel (on one warp they would take as long as everything else here)
     if (warp == 0) {
-        const uint32_t* const g = a.rng_g + (size_t)blockIdx.x * BGZF_RNG_WORDS;
+        const uint32_t* const g = a.rng_g + (size_t)blk * BGZF_RNG_WORDS;
         const uint4 h = __ldg(reinterpret_cast<const uint4*>(g)); // ranges, segments, state
         int n_r = (int)h.x, n_s = (int)h.y, state = (int)h.z;
-        if (state == 2) bgzf_block_ranges(a, (int)blockIdx.x, b0, L, lane, rng, MAX_RANGES, n_r, n_s, state); // more than the list holds
+        if (state == 2) bgzf_block_ranges(a, blk, b0, L, lane, rng, MAX_RANGES, n_r, n_s, state); // more than the list holds
         else if (state == 0)
             for (int i = lane; i < n_r; i += 32) reinterpret_cast<uint4*>(rng)[i] = __ldg(reinterpret_cast<const uint4*>(g) + 1 + i);
         if (lane == 0) { n_rng_s = n_r; n_seg_s = n_s; lit_only_s = state != 0; }
@@ -598,7 +590,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
     }
     __syncthreads();
     PROF(6); // prefix
-    uint8_t* const dst = a.stage + (size_t)blockIdx.x * BGZF_STRIDE + 2; // + 2: the deflate data (at + 18) starts on a word
+    uint8_t* const dst = a.stage + (size_t)blk * BGZF_STRIDE + 2; // + 2: the deflate data (at + 18) starts on a word
     if (total_bits_s + (eob_s >> 16) > CAP_BITS) {
         // the image does not hold the block (it would barely shrink, or the context's code was built from other statistics):
         // a stored block (RFC 1951 3.2.4) -- BFINAL = 1, BTYPE = 00, LEN, ~LEN, the bytes
@@ -616,7 +608,7 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
             const uint32_t v = tid < 4 ? crc_s : (uint32_t)L;
             dst[23 + L + tid] = (uint8_t)(v >> (8 * (tid & 3)));
         }
-        if (tid == 0) a.blk_size[blockIdx.x] = bsize;
+        if (tid == 0) a.blk_size[blk] = bsize;
         return;
     }
     // ---- bits: the segments, then the end-of-block code.
@@ -698,8 +690,36 @@ __global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs
         const uint32_t v = tid < 4 ? crc_s : (uint32_t)L;
         dst[18 + nbytes + tid] = (uint8_t)(v >> (8 * (tid & 3)));
     }
-    if (tid == 0) a.blk_size[blockIdx.x] = bsize;
+    if (tid == 0) a.blk_size[blk] = bsize;
     PROF(11); // copy out (thread 0's share)
+}
+
+// Persistent CTAs (one per SM: the shared-memory budget), blocks b, b + grid, ...: no CTA launch between blocks, the tables are
+// loaded once, and the next block's bytes are pulled into L2 while this one is compressed.
+__global__ void __launch_bounds__(BGZF_THREADS, 1) k_bgzf_deflate(const BgzfArgs a)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    __shared__ uint32_t crc_tab[1024]; // slicing-by-four tables of CRC-32
+    __shared__ uint32_t lit_tab[256], len_tab[256], dist_tab[32]; // the context's prefix code (BgzfCode)
+    const int tid = threadIdx.x;
+    const long long total = a.totals[3];
+    if (total > a.in_cap) return;
+    long long nblk = (total + BGZF_IN - 1) / BGZF_IN;
+    if (a.hist && nblk > 8192) nblk = 8192; // the statistics pass looks at the head of the stream
+    crc_tab[tid] = __ldg(a.crc_pow + 1024 + tid);
+    if (tid < 256) {
+        lit_tab[tid] = __ldg(a.code->lit + tid);
+        len_tab[tid] = __ldg(a.code->len + tid);
+        if (tid < 32) dist_tab[tid] = __ldg(a.code->dist + tid);
+    }
+    const uint32_t eob = __ldg(&a.code->eob), hdr_bits = __ldg(&a.code->hdr_bits);
+    __syncthreads();
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long nb0 = (blk + gridDim.x) * BGZF_IN;
+        if (blk + gridDim.x < nblk && tid < 256 && nb0 + 128ll * tid < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in + nb0 + 128ll * tid));
+        deflate_block(a, (int)blk, sm, crc_tab, lit_tab, len_tab, dist_tab, eob, hdr_bits);
+        __syncthreads(); // the block's shared memory is free again
+    }
 }
 
 // exclusive prefix of the block sizes; the totals for the host: [4] compressed bytes, [5] blocks
@@ -817,11 +837,9 @@ void launch_bgzf(const BgzfArgs& a, int64_t max_blocks, cudaStream_t st, int n_s
     cudaFuncSetAttribute(k_bgzf_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bgzf_dyn_smem()); // per device
     k_bgzf_first<<<(unsigned)std::min<int64_t>((max_blocks + 255) / 256, 4096), 256, 0, st>>>(a);
     k_bgzf_ranges<<<(unsigned)((max_blocks + 7) / 8), 256, 0, st>>>(a);
-    if (a.hist) { // symbol statistics of (at most the first 8192 blocks of) this record stream
-        k_bgzf_deflate<<<(unsigned)std::min<int64_t>(max_blocks, 8192), BGZF_THREADS, bgzf_dyn_smem(), st>>>(a);
-        return;
-    }
-    k_bgzf_deflate<<<(unsigned)max_blocks, BGZF_THREADS, bgzf_dyn_smem(), st>>>(a);
+    const unsigned grid = (unsigned)std::min<int64_t>(max_blocks, n_sms);
+    k_bgzf_deflate<<<grid, BGZF_THREADS, bgzf_dyn_smem(), st>>>(a);
+    if (a.hist) return; // symbol statistics of (at most the first 8192 blocks of) this record stream
     k_bgzf_scan<<<1, 1024, 0, st>>>(a);
     k_bgzf_pack<<<(unsigned)(n_sms * 8), 256, 0, st>>>(a);
 }

@@ -463,8 +463,11 @@ int build_m1f_pure_table(const double* d_bsum, const double* d_het, void* out, c
 // PURE: chunks whose cells all show a single base take the closed form (m1_pure table); compiled in only for runs where such
 // chunks are the rule (low depth x error rate), because the extra branch costs the general path ~10 %
 // XTRA (AUX only): GP / FORMAT ADF, ADR wanted
+#ifndef TILE_MIN_CTAS_AUX
+#define TILE_MIN_CTAS_AUX (TILE_MIN_CTAS - 1)
+#endif
 template <bool GEN, bool BIG, bool AUX, bool PURE, bool XTRA>
-__global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS - 1 : TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
+__global__ void __launch_bounds__(TILE_BLOCK, AUX ? TILE_MIN_CTAS_AUX : TILE_MIN_CTAS) k_tile_m1f(const __grid_constant__ DevParams p)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     // layout: alias [256] u64 | cdf_e [256] uint4 | stage [warps][G plane, PL plane, R plane] | st [sites] | tot [sites][4] |
