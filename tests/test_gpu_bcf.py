@@ -300,3 +300,21 @@ def test_cpp_host_stream_writes_a_bcf_file_the_oracle_reads(tmp_path):
                                      {"DP": np.array([o["info_dp"]])}))
     ctx.close()
     assert recs == want
+
+
+def test_cpp_host_stream_writes_a_bgzf_file(tmp_path):
+    """the same driver with VGL_BGZF_OUT: a complete BGZF-compressed BCF file (stored header block written by the host, the
+    record blocks compressed on the device, the EOF block) -- it must gunzip to the -O u file byte for byte"""
+    import gzip
+    import os
+    import subprocess
+    exe = os.path.join(bu.ROOT, "vcfgl_b200", "host", "example_driver")
+    if not os.path.exists(exe):
+        pytest.skip("example_driver not built")
+    plain, packed = str(tmp_path / "u.bcf"), str(tmp_path / "b.bcf")
+    for n_sites, batch in ((11, 4), (3000, 1024)):
+        subprocess.check_call([exe, str(n_sites)], env=dict(os.environ, VGL_BCF_OUT=plain, VGL_BATCH=str(batch)))
+        subprocess.check_call([exe, str(n_sites)], env=dict(os.environ, VGL_BGZF_OUT=packed, VGL_BATCH=str(batch)))
+        raw = open(packed, "rb").read()
+        assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+        assert gzip.open(packed, "rb").read() == open(plain, "rb").read()

@@ -364,11 +364,17 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
     auto cell_hash = [&](const Seg& s) -> uint32_t { // sum of the 32-bit words (the tail word masked) times odd constants: no chain
         uint32_t h = 2166136261u ^ s.len, c = 0x9E3779B1u;
         const int nw = s.len >> 2;
+        // the cell's words share one alignment: every aligned word is loaded once and funnel-shifted with its neighbour
+        const uint32_t* const aw = reinterpret_cast<const uint32_t*>(in) + (s.pos >> 2);
+        const uint32_t sh = (s.pos & 3u) * 8u;
+        uint32_t prev = aw[0];
         for (int k = 0; k < nw; ++k) {
-            h += word_at(in, s.pos + 4u * k) * c;
+            const uint32_t next = aw[k + 1];
+            h += __funnelshift_r(prev, next, sh) * c;
+            prev = next;
             c += 0x7F4A7C16u; // stays odd
         }
-        if (s.len & 3) h += (word_at(in, s.pos + 4u * nw) & ((1u << (8 * (s.len & 3))) - 1u)) * c;
+        if (s.len & 3) h += (__funnelshift_r(prev, aw[nw + 1], sh) & ((1u << (8 * (s.len & 3))) - 1u)) * c;
         h ^= h >> 15;
         h *= 0x2C1B3C6Du;
         h ^= h >> 13;
@@ -407,7 +413,16 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
                         if (q < s.pos && q + s.len <= s.pos) { // an earlier cell (cells do not overlap)
                             uint32_t diff = 0u; // all words compared, no early exit: the loads are independent
                             const int nw = s.len >> 2;
-                            for (int k = 0; k < nw; ++k) diff |= word_at(in, q + 4u * k) ^ word_at(in, s.pos + 4u * k);
+                            const uint32_t* const wa = reinterpret_cast<const uint32_t*>(in) + (q >> 2);
+                            const uint32_t* const wb = reinterpret_cast<const uint32_t*>(in) + (s.pos >> 2);
+                            const uint32_t sha = (q & 3u) * 8u, shb = (s.pos & 3u) * 8u;
+                            uint32_t pa = wa[0], pb = wb[0];
+                            for (int k = 0; k < nw; ++k) {
+                                const uint32_t na = wa[k + 1], nb = wb[k + 1];
+                                diff |= __funnelshift_r(pa, na, sha) ^ __funnelshift_r(pb, nb, shb);
+                                pa = na;
+                                pb = nb;
+                            }
                             for (int k = 4 * nw; k < s.len; ++k) diff |= (uint32_t)(in[q + k] ^ in[s.pos + k]);
                             if (diff == 0u) dist = s.pos - q;
                         }

@@ -69,8 +69,13 @@ int main(int argc, char** argv)
             return e.status == VGL_ENODEV ? 3 : 1;
         }
     }
-    if (const char* path = getenv("VGL_BCF_OUT")) { // VGL_HOST_BCF: write an uncompressed BCF file, records serialised on the device
+    const bool zout = getenv("VGL_BGZF_OUT") != nullptr;
+    if (const char* path = zout ? getenv("VGL_BGZF_OUT") : getenv("VGL_BCF_OUT")) {
+        // VGL_BCF_OUT: an uncompressed BCF file (-O u), records serialised on the device (VGL_HOST_BCF).
+        // VGL_BGZF_OUT: the reference's default container (-O b) -- the header goes out as a stored BGZF block written here, the
+        // records as the BGZF blocks the device compressed (VGL_HOST_BGZF), then the 28-byte EOF block (htslib/bgzf.c).
         try {
+            if (getenv("VGL_BATCH")) p.max_batch_sites = atoi(getenv("VGL_BATCH"));
             std::string hdr = "##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\",IDX=0>\n##contig=<ID=1,length=1000,IDX=0>\n";
             hdr += "##FORMAT=<ID=DP,Number=1,Type=Integer,Description=\"depth\",IDX=1>\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"depth\",IDX=1>\n";
             hdr += "##FORMAT=<ID=GL,Number=G,Type=Float,Description=\"GL\",IDX=2>\n##FORMAT=<ID=PL,Number=G,Type=Integer,Description=\"PL\",IDX=3>\n";
@@ -80,9 +85,29 @@ int main(int argc, char** argv)
             FILE* f = fopen(path, "wb");
             if (!f) { perror(path); return 1; }
             const uint32_t l_text = (uint32_t)hdr.size() + 1;
-            fwrite("BCF\2\2", 1, 5, f);
-            fwrite(&l_text, 4, 1, f);
-            fwrite(hdr.c_str(), 1, l_text, f);
+            std::string head("BCF\2\2", 5);
+            head.append(reinterpret_cast<const char*>(&l_text), 4);
+            head.append(hdr.c_str(), l_text);
+            if (!zout) fwrite(head.data(), 1, head.size(), f);
+            else { // one stored deflate block inside a BGZF block (header texts beyond 65280 bytes would need several)
+                uint32_t crc = 0xFFFFFFFFu;
+                for (unsigned char c : head) {
+                    crc ^= c;
+                    for (int k = 0; k < 8; ++k) crc = (crc & 1u) ? (crc >> 1) ^ 0xEDB88320u : crc >> 1;
+                }
+                crc = ~crc;
+                const uint16_t len = (uint16_t)head.size(), nlen = (uint16_t)~len, bsize = (uint16_t)(18 + 5 + head.size() + 8 - 1);
+                const uint32_t isize = (uint32_t)head.size();
+                const unsigned char gz[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+                fwrite(gz, 1, 16, f);
+                fwrite(&bsize, 2, 1, f);
+                fputc(1, f); // BFINAL = 1, BTYPE = 00
+                fwrite(&len, 2, 1, f);
+                fwrite(&nlen, 2, 1, f);
+                fwrite(head.data(), 1, head.size(), f);
+                fwrite(&crc, 4, 1, f);
+                fwrite(&isize, 4, 1, f);
+            }
             vgl_bcf_dict dict;
             memset(&dict, 0, sizeof dict);
             dict.dp = 1; dict.gl = 2; dict.pl = 3; dict.ad = 4;
@@ -91,7 +116,7 @@ int main(int argc, char** argv)
                 fwrite(rec, 1, n, f); // the whole batch in one write: bcf_write() per record is gone
                 n_rec_bytes += (long)n;
                 fprintf(stderr, "batch: %d sites, %d skipped, %zu bytes\n", n_sites_b, n_skipped, n);
-            });
+            }, zout);
             std::vector<int> gts(2 * S);
             const uint8_t pass[2] = {0x11, 0x00}; // FILTER=PASS as the VCF parser encodes it
             for (int i = 0; i < n_sites; ++i) {
@@ -105,6 +130,10 @@ int main(int argc, char** argv)
                 sim.push_site(gts.data(), 0, 10 * i + 1, qual, nullptr, 0, pass, 2, 0);
             }
             sim.finish();
+            if (zout) {
+                const unsigned char eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                fwrite(eof, 1, 28, f);
+            }
             fclose(f);
             printf("wrote %s: %d sites, %ld record bytes\n", path, n_sites, n_rec_bytes);
             return 0;

@@ -426,10 +426,13 @@ public:
     using Sink = std::function<void(const uint8_t* records, size_t n_bytes, int n_sites, int n_skipped)>;
 
     // dict: bcf_hdr_id2int(out_hdr, BCF_DT_ID, "DP" / "GL" / ...) of the output header
-    BcfStreamSimulator(vgl_params params, const vgl_bcf_dict& dict, Sink on_records) : prm_(params), sink_(std::move(on_records))
+    // bgzf: the sink receives the records as BGZF blocks compressed on the device (VGL_HOST_BGZF: the reference's -O b; the host
+    //       writes them behind its own header block(s) with hwrite and ends the file with the BGZF EOF block); not with enable_gvcf
+    BcfStreamSimulator(vgl_params params, const vgl_bcf_dict& dict, Sink on_records, bool bgzf = false)
+        : prm_(params), sink_(std::move(on_records)), bgzf_(bgzf)
     {
         prm_.abi_version = VGL_ABI_VERSION;
-        prm_.host_output = VGL_HOST_BCF;
+        prm_.host_output = bgzf ? VGL_HOST_BGZF : VGL_HOST_BCF;
         prm_.bcf_dict = dict;
         if (prm_.n_slots < 2) prm_.n_slots = 2;
         if (prm_.bcf_blob_bytes_per_site == 0) prm_.bcf_blob_bytes_per_site = 16;
@@ -486,6 +489,7 @@ public:
     // in output order, the seam between batches stitched by vgl_wait; the last open block arrives with finish()
     void enable_gvcf(const std::vector<int32_t>& gvcf_dps)
     {
+        if (bgzf_) throw Error(VGL_EINVAL, "gVCF blocks are stitched across batches on the uncompressed stream: use VGL_HOST_BCF");
         check(vgl_set_gvcf_dps(ctx_, gvcf_dps.data(), (int32_t)gvcf_dps.size()), "vgl_set_gvcf_dps");
         gvcf_ = true;
     }
@@ -532,7 +536,8 @@ private:
         if (out.status != VGL_OK) throw Error(out.status, vgl_strerror(out.status));
         int skipped = 0;
         for (int i = 0; i < out.n_sites; ++i) skipped += out.sites[i].skip_code != 0; // nSitesSkipped, vcfgl.cpp:1553-1558
-        sink_(out.bcf, (size_t)out.bcf_bytes, out.n_sites, skipped);
+        if (bgzf_) sink_(out.bgzf, (size_t)out.bgzf_bytes, out.n_sites, skipped);
+        else sink_(out.bcf, (size_t)out.bcf_bytes, out.n_sites, skipped);
         in_flight_[slot] = false;
     }
 
@@ -541,7 +546,7 @@ private:
     vgl_ctx* ctx_ = nullptr;
     std::vector<bool> in_flight_;
     uint8_t *gt_ = nullptr, *blob_ = nullptr;
-    bool gvcf_ = false;
+    bool gvcf_ = false, bgzf_ = false;
     vgl_bcf_site_in* sin_ = nullptr;
     int64_t blob_cap_ = 0;
     size_t blob_fill_ = 0;
