@@ -469,26 +469,13 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         }
     };
     const int n_lit = n_lit_s;
-    for (int tb = 0; tb < n_lit * 16; tb += BGZF_THREADS) { // insert: a word of an unmatched cell per thread
-        const int task = tb + tid;
-        bool active = false;
-        uint32_t wp = 0xFFFFFFFFu, v = 0x80000000u | (uint32_t)lane;
-        if (task < n_lit * 16) {
-            const Seg ls = segs[lit_list[task >> 4]];
-            const int k = 4 * (task & 15);
-            if ((ls.info & SEG_CELL) && k + 4 <= (int)ls.len) {
-                active = true;
-                wp = ls.pos + (uint32_t)k;
-                v = word_at(in, wp);
-            }
-        }
-        // new vectors share most of their words: of the lanes of a warp that hold the same value only the earliest position goes
-        // to the table (shared-memory atomics on one address serialise)
-        const unsigned peers = __match_any_sync(0xffffffffu, v);
-        const uint32_t first = __reduce_min_sync(peers, wp);
-        if (!active || wp != first) continue;
+    for (int task = tid; task < n_lit * 16; task += BGZF_THREADS) { // insert: a word of an unmatched cell per thread
+        const Seg ls = segs[lit_list[task >> 4]];
+        const int k = 4 * (task & 15);
+        if (!(ls.info & SEG_CELL) || k + 4 > (int)ls.len) continue;
+        const uint32_t wp = ls.pos + (uint32_t)k, v = word_at(in, wp);
         uint32_t slot = (v * 2654435761u) >> (32 - WORD_BITS);
-        for (int probe = 0; probe < 8; ++probe) {
+        for (int probe = 0; probe < 8; ++probe) { // (thinning out equal values with __match_any_sync first costs more than the atomics it saves)
             uint32_t cur = wtab[slot];
             if (cur == 0xFFFFFFFFu) {
                 cur = atomicCAS(&wtab[slot], 0xFFFFFFFFu, wp);
