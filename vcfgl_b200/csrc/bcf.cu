@@ -13,6 +13,8 @@
 // writes the buffer as it is.
 #include "vgl_internal.h"
 
+#include <cstdlib>
+
 namespace vgl {
 
 namespace {
@@ -460,7 +462,7 @@ __device__ __forceinline__ uint32_t seg_byte(const SegView& v, int sg, uint32_t 
 // U = words per thread and round: 4 for long records (the plane loads of a round are all in flight together), 1 for short ones,
 // where the kernel is bound by thread 0's layout pass and more resident blocks matter more than longer rounds
 template <int U>
-__global__ void __launch_bounds__(256, U == 1 ? 8 : 5) k_bcf_emit(const BcfArgs a)
+__global__ void __launch_bounds__(256, U == 1 ? 8 : (U == 2 ? 6 : 5)) k_bcf_emit(const BcfArgs a)
 {
     const int rk = blockIdx.x, tid = threadIdx.x; // record index (see k_bcf_plan)
     __shared__ vgl_site_out s;
@@ -573,7 +575,10 @@ void launch_bcf(const BcfArgs& a, cudaStream_t st)
 {
     k_bcf_plan<<<(unsigned)a.n_sites, 128, 0, st>>>(a);
     k_bcf_scan<<<1, 1024, 0, st>>>(a);
-    if (a.S >= 1000) k_bcf_emit<4><<<(unsigned)a.n_sites, 256, 0, st>>>(a);
+    int u = a.S >= 1000 ? 4 : 1;
+    if (const char* e = getenv("VGL_EMIT_U")) u = atoi(e); // development: words per thread and round
+    if (u >= 4) k_bcf_emit<4><<<(unsigned)a.n_sites, 256, 0, st>>>(a);
+    else if (u == 2) k_bcf_emit<2><<<(unsigned)a.n_sites, 256, 0, st>>>(a);
     else k_bcf_emit<1><<<(unsigned)a.n_sites, 256, 0, st>>>(a);
 }
 

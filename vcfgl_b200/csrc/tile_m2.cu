@@ -93,7 +93,7 @@ __device__ __forceinline__ int m2_depth(const DevParams& p, const M2Rng& R, cons
     } else {
         const uint32_t col = b0.x >> 24;
         uint2 en;
-        if (p.alias_row) en = __ldg(reinterpret_cast<const uint2*>(p.pois_alias) + (size_t)__ldg(p.alias_row + sample) * 256u + col); // the sample's own mean
+        if (p.alias_row) en = __ldg(reinterpret_cast<const uint2*>(p.pois_alias) + (size_t)__ldg(p.alias_row + min(sample, (uint32_t)p.S - 1u)) * 256u + col); // the sample's own mean (padding lanes: any row, their depth is dropped)
         else en = lds64(R.s_alias + col * 8u);
         const unsigned long long frac = ((unsigned long long)__funnelshift_l(b0.y, b0.x, 8) << 32) | (b0.y << 8);
         const unsigned long long thr = ((unsigned long long)en.y << 32) | (en.x & 0xFFFFFF00u);
