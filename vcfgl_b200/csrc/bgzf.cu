@@ -41,6 +41,8 @@ constexpr int OUT_WORDS = 24576 / 4;               // the block image; a block t
 constexpr int HASH_SLOTS = 8192;
 constexpr int MAX_RANGES = 32 * 16;
 constexpr int WORD_BITS = 12, WORD_SLOTS = 1 << WORD_BITS; // word table of the unmatched cells (half of the cell table's memory)
+constexpr int DT = BGZF_THREADS - 128;       // threads of the compressor's phases; the CTA's last four warps do the CRC
+constexpr int SEG_PER_THREAD = (MAX_SEG + DT - 1) / DT;
 constexpr int CRC_CHUNK = 64;                  // bytes a thread takes in the CRC pass
 
 struct Seg { // 8 bytes
@@ -252,6 +254,7 @@ __device__ unsigned long long g_bgzf_prof[16];
 #define PROF(i) do { } while (0)
 #define PROFW(i) do { } while (0)
 #endif
+#define DSYNC() asm volatile("bar.sync 2, %0;" ::"n"(DT) : "memory")
 
 // one block of the stream (a whole CTA); the CRC and code tables are the kernel's, loaded once per CTA
 __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, unsigned char* const sm, const uint32_t* const crc_tab,
@@ -294,34 +297,10 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         if (t + nt < n16) reinterpret_cast<uint4*>(in)[t + nt] = v1;
         if (t + 2 * nt < n16) reinterpret_cast<uint4*>(in)[t + 2 * nt] = v2;
         PROFW(8); // load, clear, tables issued
-        // CRC32 of the block: 64-byte chunks from the end (slicing by four), each shifted
-        // across the bytes behind it.  Barrier 1 = warps 1 .. 31 only.
+        // Barrier 1 = warps 1 .. 31 only (the image is cleared before the header goes in).
         asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
         PROFW(9); // barrier of warps 1..31 (the loads have landed)
         if (!a.hist && t < (int)((hdr_bits_s + 31u) >> 5)) out[t] = a.code->hdr[t]; // the block header (the image is cleared)
-        for (int c = t; c < BGZF_IN / CRC_CHUNK; c += nt) {
-            const int hi = L - c * CRC_CHUNK, lo2 = max(hi - CRC_CHUNK, 0);
-            if (hi <= 0) break;
-            uint32_t r = 0xFFFFFFFFu;
-            auto step = [&](uint32_t w) {
-                r ^= w;
-                r = crc_tab[768 + (r & 0xFFu)] ^ crc_tab[512 + ((r >> 8) & 0xFFu)] ^ crc_tab[256 + ((r >> 16) & 0xFFu)] ^ crc_tab[r >> 24];
-            };
-            if (hi - lo2 == CRC_CHUNK && (lo2 & 15) == 0) { // a whole aligned chunk: 128-bit loads (word loads at this stride collide on four banks)
-#pragma unroll
-                for (int q = 0; q < CRC_CHUNK / 16; ++q) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(in + lo2 + 16 * q);
-                    step(v.x); step(v.y); step(v.z); step(v.w);
-                }
-            } else {
-                int k = lo2;
-                for (; k < hi && ((hi - k) & 3); ++k) r = crc_tab[(r ^ in[k]) & 0xFFu] ^ (r >> 8); // head bytes: the rest is whole words
-                for (; k < hi; k += 4) step(word_at(in, (uint32_t)k));
-            }
-            const uint32_t part = crc_mul_dev(__ldg(a.crc_pow + c), ~r);
-            if (part) atomicXor(&crc_s, part);
-        }
-        PROFW(10); // CRC (warp 1)
     }
 
     // ---- ranges: made by k_bgzf_ranges ahead of this kernel (on one warp they would take as long as everything else here)
@@ -335,19 +314,51 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         if (lane == 0) { n_rng_s = n_r; n_seg_s = n_s; lit_only_s = state != 0; }
     }
     __syncthreads();
-    PROF(0); // load + tables + CRC || ranges
+    PROF(0); // load + tables || ranges
+    // ---- the last four warps: CRC32 of the block -- 64-byte chunks from the end (slicing by four), each shifted across the bytes
+    // behind it -- while the other 28 run the compressor's phases (their barriers are barrier 2 from here on).  The look-ups of
+    // the slicing tables collide 3.5-way on the banks whoever does them; beside the latency-bound phases they cost nothing.
+    if (warp >= DT / 32) {
+        if (!a.hist) {
+            for (int c = tid - DT; c < BGZF_IN / CRC_CHUNK; c += BGZF_THREADS - DT) {
+                const int hi = L - c * CRC_CHUNK, lo2 = max(hi - CRC_CHUNK, 0);
+                if (hi <= 0) break;
+                uint32_t r = 0xFFFFFFFFu;
+                auto step = [&](uint32_t w) {
+                    r ^= w;
+                    r = crc_tab[768 + (r & 0xFFu)] ^ crc_tab[512 + ((r >> 8) & 0xFFu)] ^ crc_tab[256 + ((r >> 16) & 0xFFu)] ^ crc_tab[r >> 24];
+                };
+                if (hi - lo2 == CRC_CHUNK && (lo2 & 15) == 0) { // a whole aligned chunk: 128-bit loads (word loads at this stride collide on four banks)
+#pragma unroll
+                    for (int q = 0; q < CRC_CHUNK / 16; ++q) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(in + lo2 + 16 * q);
+                        step(v.x); step(v.y); step(v.z); step(v.w);
+                    }
+                } else {
+                    int k = lo2;
+                    for (; k < hi && ((hi - k) & 3); ++k) r = crc_tab[(r ^ in[k]) & 0xFFu] ^ (r >> 8); // head bytes: the rest is whole words
+                    for (; k < hi; k += 4) step(word_at(in, (uint32_t)k));
+                }
+                const uint32_t part = crc_mul_dev(__ldg(a.crc_pow + c), ~r);
+                if (part) atomicXor(&crc_s, part);
+            }
+            __threadfence_block();
+            asm volatile("bar.arrive 4, %0;" ::"n"(BGZF_THREADS) : "memory"); // the CRC is in crc_s (the trailer's writers wait on barrier 4)
+        }
+        return; // to the kernel loop's barrier
+    }
     if (lit_only_s) { // one gap over the whole block
         if (tid == 0) {
             rng[0] = 0u; rng[1] = (uint32_t)L; rng[2] = 0u; rng[3] = 0u;
             n_rng_s = 1;
             n_seg_s = (L + RUN - 1) / RUN;
         }
-        __syncthreads();
+        DSYNC();
     }
     const int n_rng = n_rng_s, n_seg = n_seg_s;
 
     // ---- segment table
-    for (int j = warp; j < n_rng; j += BGZF_THREADS / 32) {
+    for (int j = warp; j < n_rng; j += DT / 32) {
         const uint32_t pos = rng[j * 4], len = rng[j * 4 + 1], cell = rng[j * 4 + 2], first = rng[j * 4 + 3];
         const int n = cell ? (int)(len / cell) : (int)((len + RUN - 1) / RUN);
         for (int c = lane; c < n; c += 32) {
@@ -357,7 +368,7 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
             segs[first + c] = s;
         }
     }
-    __syncthreads();
+    DSYNC();
     PROF(1); // segment table
 
     // ---- cells: hash of the bytes, first occurrence per hash (atomicMin on tag << 16 | position; open addressing)
@@ -380,7 +391,7 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         h ^= h >> 13;
         return h;
     };
-    for (int j = tid; j < n_seg; j += BGZF_THREADS) {
+    for (int j = tid; j < n_seg; j += DT) {
         const Seg s = segs[j];
         if (!(s.info & SEG_CELL)) continue;
         const uint32_t h = cell_hash(s), tag = h >> 16, mine = (tag << 16) | s.pos;
@@ -393,10 +404,10 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
             slot = (slot + 1) & (HASH_SLOTS - 1);
         }
     }
-    __syncthreads();
+    DSYNC();
     PROF(2); // hash insert
     // ---- match = the first cell of the block with the same bytes; the other segments go on the list of literal segments
-    for (int j0 = warp * 32; j0 < n_seg; j0 += BGZF_THREADS) {
+    for (int j0 = warp * 32; j0 < n_seg; j0 += DT) {
         const int j = j0 + lane;
         bool is_lit = false;
         if (j < n_seg) {
@@ -447,13 +458,13 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
     // few of its values; every word that occurred before in an unmatched cell (any matched cell is a copy of one) can go out
     // as a match of length 4.  The cell table's memory now holds the word table (first position per value, the value is read
     // back from the block) and, per word of the block, the distance chosen (0: literals).
-    __syncthreads();
+    DSYNC();
     PROF(3); // match
     uint32_t* const wtab = htab;                                           // [WORD_SLOTS]
     uint16_t* const wdist = reinterpret_cast<uint16_t*>(htab + WORD_SLOTS); // [BGZF_IN / 4]
-    for (int i = tid; i < HASH_SLOTS / 4; i += BGZF_THREADS)
+    for (int i = tid; i < HASH_SLOTS / 4; i += DT)
         reinterpret_cast<uint4*>(htab)[i] = i < WORD_SLOTS / 4 ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
+    DSYNC();
     // quarter q of a literal segment: bytes [k0, k1), the first nwb of them whole words of an unmatched cell
     auto quarter = [&](const Seg& sg, int q, int& k0, int& k1, int& nwb) {
         if (sg.info & SEG_CELL) {
@@ -469,7 +480,7 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         }
     };
     const int n_lit = n_lit_s;
-    for (int task = tid; task < n_lit * 16; task += BGZF_THREADS) { // insert: a word of an unmatched cell per thread
+    for (int task = tid; task < n_lit * 16; task += DT) { // insert: a word of an unmatched cell per thread
         const Seg ls = segs[lit_list[task >> 4]];
         const int k = 4 * (task & 15);
         if (!(ls.info & SEG_CELL) || k + 4 > (int)ls.len) continue;
@@ -488,14 +499,14 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
             slot = (slot + 1) & (WORD_SLOTS - 1);
         }
     }
-    __syncthreads();
+    DSYNC();
     PROF(4); // word insert
     // ---- bit length of every segment under the context's code (the word matches are decided here: a match where it is
     // shorter than its four literals), exclusive prefix; should the image not hold them (a code built from other statistics),
     // once more under the fixed code, which always fits.  The statistics pass counts the symbols instead and stops.
     uint32_t* const hist = out; // statistics pass only (the image is clear and stays unused)
     if (a.hist) // the matches' symbols (their bit lengths are already in place)
-        for (int j = tid; j < n_seg; j += BGZF_THREADS) {
+        for (int j = tid; j < n_seg; j += DT) {
             const Seg s = segs[j];
             if (!(s.info & SEG_MATCH)) continue;
             int dc, deb;
@@ -504,7 +515,7 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
             atomicAdd(&hist[257 + len_symbol(s.len)], 1u);
             atomicAdd(&hist[288 + dc], 1u);
         }
-    for (int tb = 0; tb < n_lit * 4; tb += BGZF_THREADS) { // a quarter of a literal segment per thread; lanes 4 i .. 4 i + 3 share a segment
+    for (int tb = 0; tb < n_lit * 4; tb += DT) { // a quarter of a literal segment per thread; lanes 4 i .. 4 i + 3 share a segment
         const int t = tb + tid;
         uint32_t part = 0u;
         int jj = 0;
@@ -561,18 +572,18 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         }
     }
     if (a.hist) { // statistics pass: the counts of this block to the context's, nothing is written
-        __syncthreads();
+        DSYNC();
         if (tid < BGZF_HIST && hist[tid]) atomicAdd(&a.hist[tid], hist[tid]);
         if (tid == 0) atomicAdd(&a.hist[256], 1u);
         return;
     }
-    __syncthreads();
+    DSYNC();
     PROF(5); // bit lengths
     {
-        uint32_t v[MAX_SEG / BGZF_THREADS], sum = 0u;
+        uint32_t v[SEG_PER_THREAD], sum = 0u;
 #pragma unroll
-        for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
-            const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
+        for (int k = 0; k < SEG_PER_THREAD; ++k) {
+            const int j = tid * SEG_PER_THREAD + k;
             v[k] = j < n_seg ? seg_bit[j] : 0u;
             sum += v[k];
         }
@@ -583,9 +594,9 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
             if (lane >= o) inc += t;
         }
         if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
+        DSYNC();
         if (warp == 0) {
-            uint32_t t = warp_tot[lane];
+            uint32_t t = lane < DT / 32 ? warp_tot[lane] : 0u;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t u = __shfl_up_sync(0xffffffffu, t, o);
@@ -593,17 +604,17 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
             }
             warp_tot[lane] = t;
         }
-        __syncthreads();
+        DSYNC();
         uint32_t base = hdr_bits_s + (warp ? warp_tot[warp - 1] : 0u) + inc - sum;
 #pragma unroll
-        for (int k = 0; k < MAX_SEG / BGZF_THREADS; ++k) {
-            const int j = tid * (MAX_SEG / BGZF_THREADS) + k;
+        for (int k = 0; k < SEG_PER_THREAD; ++k) {
+            const int j = tid * SEG_PER_THREAD + k;
             if (j < n_seg) seg_bit[j] = base;
             base += v[k];
         }
-        if (tid == BGZF_THREADS - 1) total_bits_s = base;
+        if (tid == DT - 1) total_bits_s = base;
     }
-    __syncthreads();
+    DSYNC();
     PROF(6); // prefix
     uint8_t* const dst = a.stage + (size_t)blk * BGZF_STRIDE + 2; // + 2: the deflate data (at + 18) starts on a word
     if (total_bits_s + (eob_s >> 16) > CAP_BITS) {
@@ -618,7 +629,8 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
             const uint8_t sb[5] = {1, (uint8_t)(L & 0xFF), (uint8_t)(L >> 8), (uint8_t)(~L & 0xFF), (uint8_t)((~L >> 8) & 0xFF)};
             dst[18 + tid] = sb[tid];
         }
-        for (int i = tid; i < L; i += BGZF_THREADS) dst[23 + i] = in[i];
+        for (int i = tid; i < L; i += DT) dst[23 + i] = in[i];
+        asm volatile("bar.sync 4, %0;" ::"n"(BGZF_THREADS) : "memory"); // the CRC warps are done
         if (tid < 8) {
             const uint32_t v = tid < 4 ? crc_s : (uint32_t)L;
             dst[23 + L + tid] = (uint8_t)(v >> (8 * (tid & 3)));
@@ -629,7 +641,7 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
     // ---- bits: the segments, then the end-of-block code.
     // A literal segment is split into quarters (their bit offsets follow from the counts kept with the segment).
     if (tid == 0) put_bits(out, total_bits_s, eob_s & 0xFFFFu, (int)(eob_s >> 16));
-    for (int j = tid; j < n_seg; j += BGZF_THREADS) {
+    for (int j = tid; j < n_seg; j += DT) {
         const Seg s = segs[j];
         if (!(s.info & SEG_MATCH)) continue;
         unsigned long long bb;
@@ -637,7 +649,7 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         match_code(len_tab, dist_tab, s.len, (int)(s.info & 0xFFFFu), bb, n);
         put_bits64(out, seg_bit[j], bb, n);
     }
-    for (int t = tid; t < n_lit * 4; t += BGZF_THREADS) {
+    for (int t = tid; t < n_lit * 4; t += DT) {
         const int jj = lit_list[t >> 2], q = t & 3;
         const Seg ls = segs[jj];
         int k0, k1, nwb;
@@ -686,7 +698,7 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
         }
         if (fill > 0) atomicOr(&out[w], (uint32_t)acc);
     }
-    __syncthreads();
+    DSYNC();
     PROF(7); // emission
     // ---- the BGZF block: header, deflate data, CRC32, ISIZE -> its slot of the staging buffer
     const uint32_t nbytes = (total_bits_s + (eob_s >> 16) + 7u) >> 3; // + the end-of-block code, rounded up to a byte
@@ -698,9 +710,10 @@ __device__ __forceinline__ void deflate_block(const BgzfArgs& a, const int blk, 
     {
         uint32_t* const dw = reinterpret_cast<uint32_t*>(dst + 18);
         const uint8_t* const ob = reinterpret_cast<const uint8_t*>(out);
-        for (uint32_t i = tid; i < (nbytes >> 2); i += BGZF_THREADS) __stcs(dw + i, out[i]);
+        for (uint32_t i = tid; i < (nbytes >> 2); i += DT) __stcs(dw + i, out[i]);
         if (tid < (nbytes & 3u)) dst[18 + (nbytes & ~3u) + tid] = ob[(nbytes & ~3u) + tid];
     }
+    asm volatile("bar.sync 4, %0;" ::"n"(BGZF_THREADS) : "memory"); // the CRC warps are done
     if (tid < 8) {
         const uint32_t v = tid < 4 ? crc_s : (uint32_t)L;
         dst[18 + nbytes + tid] = (uint8_t)(v >> (8 * (tid & 3)));
