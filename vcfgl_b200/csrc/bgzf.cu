@@ -36,6 +36,8 @@ namespace {
 constexpr int BGZF_IN = 32768;                  // uncompressed bytes per block
 constexpr int BGZF_THREADS = 1024;
 constexpr int MAX_SEG = 8192;                   // segments (cells, literal runs) of a block
+constexpr int MIN_CELL = 8;                      // vectors shorter than this are not matched: a length / distance pair costs as much as their
+                                                 // few literals under the context's code, and a block of 5-byte cells has 6500 segments
 constexpr int RUN = 64;                         // bytes of a literal run segment
 constexpr int OUT_WORDS = 24576 / 4;               // the block image; a block that does not fit (three quarters of its input) is stored
 constexpr int HASH_SLOTS = 8192;
@@ -186,7 +188,7 @@ __device__ void bgzf_block_ranges(const BgzfArgs& a, int blk, long long b0, int 
         const long long end = min(re, b0 + L);
         for (int k = 0; k < (int)pl.n && k < 7; ++k) {
             const long long ps = rs + pl.off[k], pe = ps + (long long)pl.cell[k] * a.S;
-            if (pl.cell[k] < 3 || pl.cell[k] > RUN || pe <= cur || ps >= end) continue; // deflate matches are at least 3 bytes long; segments at most RUN
+            if (pl.cell[k] < MIN_CELL || pl.cell[k] > RUN || pe <= cur || ps >= end) continue; // short vectors go out as literals (see MIN_CELL); segments at most RUN
             // full cells of this plane inside [cur, end)
             long long c_lo = ps >= cur ? 0 : (cur - ps + pl.cell[k] - 1) / pl.cell[k];
             long long c_hi = pe <= end ? a.S : (end - ps) / pl.cell[k];
