@@ -109,6 +109,9 @@ else
   echo "build_ref.sh: vcfgl_b200/libvgl.so not built yet; skipping vcfgl_ref_vgl" >&2
 fi
 
+# (2c) a reader on the reference's htslib (oracle/hts_read_bcf.c, our code): which records does the library see in a BCF file
+gcc -O2 -w -I"$GEN" -I"$H" -I"$H/.." "$HERE/hts_read_bcf.c" -o "$OUT/hts_read_bcf" $LIBS
+
 # (3) errmod alone, for table-level cross-checks of the oracle restatement
 gcc -O2 -fPIC -shared -w -I"$GEN" -I"$H" "$H/errmod.c" "$H/hts_os.c" -o "$OUT/libref_errmod.so" -lm
 

@@ -318,3 +318,10 @@ def test_cpp_host_stream_writes_a_bgzf_file(tmp_path):
         raw = open(packed, "rb").read()
         assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
         assert gzip.open(packed, "rb").read() == open(plain, "rb").read()
+        # the reference's own htslib (oracle/_ref/hts_read_bcf: hts_open / bcf_hdr_read / bcf_read) reads the file as BGZF-compressed
+        # BCF and sees the records of the uncompressed one
+        reader = os.path.join(bu.ROOT, "oracle", "_ref", "hts_read_bcf")
+        if os.path.exists(reader):
+            a_, b_ = (subprocess.check_output([reader, f]).decode().splitlines() for f in (plain, packed))
+            assert a_[0].split()[:4] == ["format", "9", "compression", "0"] and b_[0].split()[:4] == ["format", "9", "compression", "2"]   # bcf; none / bgzf
+            assert a_[1:] == b_[1:] and a_[-1] == "records %d" % n_sites
