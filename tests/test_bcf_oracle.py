@@ -46,3 +46,28 @@ def test_encoders_match_htslib_rules():
     assert bo.enc_vint([40000, 1], 2)[0] == 0x23
     assert bo.enc_vfloat(np.array([1.0], np.float32)) == bytes([0x15, 0, 0, 0x80, 0x3F])
     assert bo.enc_vchar("<*>") == b"\x37<*>" and bo.enc_vchar("") == b"\x07"
+
+
+@pytest.mark.parametrize("cid", bu.BCF_CASES[:6])
+def test_hts_reader_tool_sees_the_reference_records(cid, tmp_path):
+    """oracle/_ref/hts_read_bcf (oracle/hts_read_bcf.c on the reference's htslib; the GPU tests use it to read device-compressed
+    BGZF files) against the oracle's own parse of the reference's -O u files"""
+    import gzip
+    import os
+    import struct
+    import subprocess
+    reader = os.path.join(bu.ROOT, "oracle", "_ref", "hts_read_bcf")
+    if not os.path.exists(reader):
+        pytest.skip("oracle/_ref not built")
+    path = str(tmp_path / "x.bcf")
+    src = os.path.join(bu.BCF_DIR, cid + ".bcf.gz")
+    with open(path, "wb") as fh:
+        fh.write(gzip.open(src, "rb").read())
+    lines = subprocess.check_output([reader, path]).decode().splitlines()
+    _, _, recs = bu.reference_bcf(cid)
+    assert lines[0].split()[:4] == ["format", "9", "compression", "0"] and lines[-1] == "records %d" % len(recs)
+    for line, rec in zip(lines[1:-1], recs):
+        l_shared, l_indiv, rid, pos = struct.unpack_from("<IIii", rec, 0)
+        f = line.split()
+        assert (int(f[0]), int(f[1])) == (rid, pos)
+        assert (int(f[7]), int(f[8])) == (l_shared - 24, l_indiv)      # htslib keeps the 24 fixed bytes out of shared.s
