@@ -6,20 +6,24 @@
 // data, CRC32 and length of the uncompressed bytes).  Every block here holds BGZF_IN = 32768 bytes of the record stream (the
 // last one less) and is compressed by one CTA on its own, so every match distance lies inside deflate's 32 KiB window:
 //
-//   k_bgzf_deflate  one block per CTA.  The record stream is not searched byte by byte: k_bcf_emit leaves a descriptor of every
-//                   record's FORMAT planes, so the CTA knows where each sample's vector of a tag ("cell": the 15 GL floats, the
-//                   15 PL bytes, the 5 AD counts ...) starts.  Cells are hashed whole; a cell whose bytes occurred earlier in the
-//                   block as a cell becomes ONE length/distance pair pointing at the first such occurrence, everything else
-//                   goes out as literals.  Cells never overlap, so the parse needs no sequential pass; the simulated tags
-//                   repeat heavily (every sample with the same read counts has the same vectors), which is what makes the
-//                   record stream compressible at all.  Codes are deflate's fixed Huffman codes (RFC 1951 3.2.6): bit lengths
-//                   per segment -> CTA-wide prefix sum -> every segment ORs its bits into the block image in shared memory.
-//                   CRC32: 32-byte chunks per thread, combined by multiplication with x^(8 n) mod P (the identity zlib's
-//                   crc32_combine uses).
 //   k_bgzf_first    thread per block: the first record that reaches into it (binary search over the record offsets)
+//   k_bgzf_ranges   warp per block: the block cut into ranges of whole cells and the gaps between them.  The record stream is not
+//                   searched byte by byte: k_bcf_emit leaves a descriptor of every record's FORMAT planes, so the compressor knows
+//                   where each sample's vector of a tag ("cell": the 15 GL floats, the 15 PL values ...) starts.
+//   k_bgzf_deflate  persistent CTAs, one per SM, a block per round.  Cells are hashed whole; a cell whose bytes occurred earlier
+//                   in the block as a cell becomes ONE length/distance pair pointing at the first such occurrence (cells never
+//                   overlap, so the parse needs no sequential pass; the simulated tags repeat heavily: every sample with the same
+//                   read counts has the same vectors).  The 32-bit words of the unmatched cells go through a second, finer table
+//                   (a new vector mostly differs from older ones in a few values) and become matches of length 4 where that is
+//                   shorter than four literals; the rest are literals.  Codes: one dynamic Huffman code per context (RFC 1951
+//                   3.2.7), built on the host from the symbol counts of the context's first record stream (tables.cpp
+//                   bgzf_build_code; this kernel in its statistics mode); every block starts with the same precomputed header
+//                   bits.  Bit lengths per segment -> CTA-wide prefix sum -> every task ORs its bits into the block image in shared
+//                   memory; a block that does not fit the image (three quarters of its input) is stored (3.2.4).  CRC32: the
+//                   CTA's last four warps, 64-byte chunks combined by multiplication with x^(8 n) mod P (the identity zlib's
+//                   crc32_combine uses), beside the 28 warps that run the phases above.
 //   k_bgzf_scan     exclusive prefix of the compressed block sizes
-//   k_bgzf_pack     blocks moved back to back into the stream the host receives -- written straight into the slot's pinned host
-//                   buffer (mapped memory), so the transfer is part of the stream's work and needs no size known to the host
+//   k_bgzf_pack     blocks moved back to back into the stream the host receives
 //
 // Parity: inflating the blocks gives back the VGL_HOST_BCF stream byte for byte (tests/test_gpu_bgzf.py: zlib on the host).
 #include "vgl_internal.h"
