@@ -303,9 +303,11 @@ int vgl_native_draws(vgl_ctx* ctx, int slot, int64_t first_site_id, int32_t n_si
 /* number of kernel launches issued by this context so far */
 int64_t vgl_launch_count(const vgl_ctx* ctx);
 
-/* which kernel set a native (non-replay) submit of this context runs: "k_tile_m1f" (one fused kernel, GL model 1 with a
- * run-constant quality score), "k_fused_m1f" (one fused kernel, remaining GL model 1 / fixed-qs options) or
- * "k_sim+k_site+k_scan+k_emit" (general path; also every replay submit) */
+/* which kernel set a native (non-replay) submit of this context runs: "k_tile_m1f" (one kernel: GL model 1 with a
+ * run-constant quality score, every tag, one Poisson mean, --depths-file or fixed depth), "k_tile_m2" (one kernel: GL model 2
+ * with run constants or the quality-score LUT; GL / PL / AD / DP tags), "k_fused_m1f" (one kernel: remaining GL model 1 /
+ * fixed-qs options -- --error-qs 1, cells deeper than 255 reads) or "k_sim+k_site+k_scan+k_emit" (general path; also every
+ * replay submit) */
 const char* vgl_native_kernels(const vgl_ctx* ctx);
 
 /* algorithmic bytes of a finished batch as defined in DESIGN.md / SURVEY.md 8(d) */
